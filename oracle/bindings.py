@@ -1,0 +1,407 @@
+"""ctypes bindings for the two CPU checkers -- TEST INFRASTRUCTURE ONLY.
+
+* ``RefLib``  -> oracle/_ref/libgmg_ref.so : the reference's own sources compiled unmodified
+  against oracle/shim (built by ``make -C oracle ref`` where /root/reference exists).
+* ``PortLib`` -> oracle/libgmg_oracle.so   : the plain-C restatement (oracle/gmg_oracle.c).
+
+Both expose the same Python surface so tests can swap them.  Arrays are numpy, C-order with
+shape (rz, ry, rx), i.e. x-fastest like UT_VoxelArray; ``res`` passed to C is (rx, ry, rz).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libgmg_ref.so")
+REF_DBG_SO = os.path.join(HERE, "_ref", "libgmg_ref_dbg.so")
+PORT_SO = os.path.join(HERE, "libgmg_oracle.so")
+
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+def build(ref: bool = True) -> None:
+    """Compile the checkers (port always; the reference bridge only where /root/reference exists)."""
+    subprocess.check_call(["make", "-C", HERE, "port"], stdout=subprocess.DEVNULL)
+    if ref and os.path.isdir("/root/reference/Source"):
+        subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def _res(a: np.ndarray):
+    return (C.c_int64 * 3)(a.shape[2], a.shape[1], a.shape[0])
+
+
+def _res_t(t):
+    return (C.c_int64 * 3)(*[int(v) for v in t])
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_i32p)
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_f64p)
+
+
+def _wptrs(w):
+    if w is None:
+        return [None, None, None], [None, None, None]
+    keep = [np.ascontiguousarray(a, dtype=np.float64) for a in w]
+    return keep, [a.ctypes.data_as(_f64p) for a in keep]
+
+
+def face_shape(shape, axis):
+    """numpy shape (rz,ry,rx) of the face grid along `axis` (0=x)."""
+    s = list(shape)
+    s[2 - axis] += 1
+    return tuple(s)
+
+
+class _Base:
+    prefix = ""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        self.lib = C.CDLL(path)
+
+    def fn(self, name, restype=C.c_int):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = restype
+        return f
+
+    # ---- shared operator wrappers (identical C shapes in both libraries) ----
+    def set_boundary_labels(self, labels, w):
+        l, lp = _i32(np.array(labels, copy=True))
+        keep, wp = _wptrs(w)
+        self.fn("set_boundary_labels", None)(lp, _res(l), *wp)
+        return l
+
+    def coarsen_labels(self, fine):
+        f, fp = _i32(fine)
+        out = np.empty(tuple(s // 2 for s in f.shape), dtype=np.int32)
+        self.fn("coarsen_labels", None)(fp, _res(f), out.ctypes.data_as(_i32p))
+        return out
+
+    def unit_test_boundary_cells(self, labels, w=None):
+        l, lp = _i32(labels)
+        keep, wp = _wptrs(w)
+        return bool(self.fn("unit_test_boundary_cells")(lp, _res(l), *wp))
+
+    def unit_test_exterior_cells(self, labels):
+        l, lp = _i32(labels)
+        return bool(self.fn("unit_test_exterior_cells")(lp, _res(l)))
+
+    def unit_test_coarsening(self, coarse, fine):
+        c, cp = _i32(coarse)
+        f, fp = _i32(fine)
+        return bool(self.fn("unit_test_coarsening")(cp, fp, _res(f)))
+
+    def jacobi(self, x, b, labels, w=None):
+        x, xp = _f64(np.array(x, copy=True))
+        b, bp = _f64(b)
+        l, lp = _i32(labels)
+        keep, wp = _wptrs(w)
+        self.fn("jacobi", None)(xp, bp, lp, _res(l), *wp)
+        return x
+
+    def gauss_seidel(self, x, b, labels, odd, forward, w=None):
+        x, xp = _f64(np.array(x, copy=True))
+        b, bp = _f64(b)
+        l, lp = _i32(labels)
+        keep, wp = _wptrs(w)
+        self.fn("gauss_seidel", None)(xp, bp, lp, _res(l), int(odd), int(forward), *wp)
+        return x
+
+    def boundary_jacobi(self, x, b, labels, cells, sweeps=1, w=None):
+        x, xp = _f64(np.array(x, copy=True))
+        b, bp = _f64(b)
+        l, lp = _i32(labels)
+        cells = np.ascontiguousarray(cells, dtype=np.int64)
+        keep, wp = _wptrs(w)
+        self.fn("boundary_jacobi", None)(xp, bp, lp, _res(l), cells.ctypes.data_as(_i64p), C.c_int64(len(cells)), int(sweeps), *wp)
+        return x
+
+    def apply(self, src, labels, w=None, dst=None):
+        s, sp = _f64(src)
+        d, dp = _f64(np.zeros_like(s) if dst is None else np.array(dst, copy=True))
+        l, lp = _i32(labels)
+        keep, wp = _wptrs(w)
+        self.fn("apply", None)(dp, sp, lp, _res(l), *wp)
+        return d
+
+    def residual(self, x, b, labels, w=None):
+        x, xp = _f64(x)
+        b, bp = _f64(b)
+        l, lp = _i32(labels)
+        r = np.empty_like(x)
+        keep, wp = _wptrs(w)
+        self.fn("residual", None)(r.ctypes.data_as(_f64p), xp, bp, lp, _res(l), *wp)
+        return r
+
+    def upsample_add(self, fine, coarse, fine_labels, coarse_labels):
+        f, fp = _f64(np.array(fine, copy=True))
+        c, cp = _f64(coarse)
+        fl, flp = _i32(fine_labels)
+        if self.prefix == "ref_":
+            cl, clp = _i32(coarse_labels)
+            self.fn("upsample_add", None)(fp, cp, flp, clp, _res(f))
+        else:
+            self.fn("upsample_add", None)(fp, cp, flp, _res(f))
+        return f
+
+    def downsample(self, fine, coarse_labels, fine_labels):
+        f, fp = _f64(fine)
+        cl, clp = _i32(coarse_labels)
+        out = np.empty(cl.shape, dtype=np.float64)
+        if self.prefix == "ref_":
+            fl, flp = _i32(fine_labels)
+            self.fn("downsample", None)(out.ctypes.data_as(_f64p), fp, clp, flp, _res(f))
+        else:
+            self.fn("downsample", None)(out.ctypes.data_as(_f64p), fp, clp, _res(f))
+        return out
+
+    def dot(self, a, b, labels):
+        a, ap = _f64(a)
+        b, bp = _f64(b)
+        l, lp = _i32(labels)
+        return float(self.fn("dot", C.c_double)(ap, bp, lp, _res(l)))
+
+    def norm2(self, a, labels):
+        a, ap = _f64(a)
+        l, lp = _i32(labels)
+        return float(self.fn("norm2", C.c_double)(ap, lp, _res(l)))
+
+    def inf_norm(self, a, labels):
+        a, ap = _f64(a)
+        l, lp = _i32(labels)
+        return float(self.fn("inf_norm", C.c_double)(ap, lp, _res(l)))
+
+    def axpy(self, dst, src, s, labels):
+        d, dp = _f64(np.array(dst, copy=True))
+        sr, sp = _f64(src)
+        l, lp = _i32(labels)
+        self.fn("axpy", None)(dp, sp, C.c_double(s), lp, _res(l))
+        return d
+
+    def add_scaled(self, a, v, s, labels, dst=None):
+        a, ap = _f64(a)
+        v, vp = _f64(v)
+        d, dp = _f64(np.zeros_like(a) if dst is None else np.array(dst, copy=True))
+        l, lp = _i32(labels)
+        self.fn("add_scaled", None)(dp, ap, vp, C.c_double(s), lp, _res(l))
+        return d
+
+    def scale(self, v, s, labels):
+        v, vp = _f64(np.array(v, copy=True))
+        l, lp = _i32(labels)
+        self.fn("scale", None)(vp, C.c_double(s), lp, _res(l))
+        return v
+
+    def expand_domain(self, base_labels, base_weights):
+        """buildExpandedDomain of Test.cpp:170-204: labels + 3 weights + setBoundaryCellLabels."""
+        labels, offset, levels = self.expand_labels(base_labels)
+        w = self.expand_weights(base_weights, base_labels.shape, labels, offset)
+        labels = self.set_boundary_labels(labels, w)
+        return labels, w, offset, levels
+
+
+class RefLib(_Base):
+    prefix = "ref_"
+
+    def __init__(self, debug=False):
+        super().__init__(REF_DBG_SO if debug else REF_SO)
+
+    def threads(self):
+        return int(self.fn("threads")())
+
+    def expand_labels(self, base):
+        b, bp = _i32(base)
+        out = _i32p()
+        ores = (C.c_int64 * 3)()
+        off = (C.c_int64 * 3)()
+        lv = C.c_int()
+        self.fn("expand_labels")(bp, _res(b), C.byref(out), ores, off, C.byref(lv))
+        shape = (ores[2], ores[1], ores[0])
+        arr = np.ctypeslib.as_array(out, shape=shape).copy()
+        self.fn("free", None)(out)
+        return arr, np.array(list(off), dtype=np.int64), int(lv.value)
+
+    def expand_weights(self, base_w, base_shape, exp_labels, offset):
+        l, lp = _i32(exp_labels)
+        res_b = _res_t(base_shape[::-1])
+        outs = []
+        for axis in range(3):
+            bw, bwp = _f64(base_w[axis])
+            out = np.empty(face_shape(l.shape, axis), dtype=np.float64)
+            self.fn("expand_weights")(bwp, res_b, lp, _res(l), _res_t(offset), axis, out.ctypes.data_as(_f64p))
+            outs.append(out)
+        return outs
+
+    def boundary_cells(self, labels, width=3):
+        l, lp = _i32(labels)
+        out = _i64p()
+        n = C.c_int64()
+        self.fn("boundary_cells")(lp, _res(l), int(width), C.byref(out), C.byref(n))
+        arr = np.ctypeslib.as_array(out, shape=(max(n.value, 1), 3))[: n.value].copy()
+        self.fn("free", None)(out)
+        return arr
+
+    def solver(self, labels, w, levels, use_gs=False, coarse_scale=1.0):
+        assert coarse_scale == 1.0 or int(os.environ.get("GMG_SHIM_JOBS", "1")) == int(coarse_scale)
+        return _RefSolver(self, labels, w, levels, use_gs)
+
+
+class _RefSolver:
+    def __init__(self, lib, labels, w, levels, use_gs):
+        self.lib = lib
+        self.labels, lp = _i32(labels)
+        keep, wp = _wptrs(w)
+        f = lib.fn("solver_create", C.c_void_p)
+        self.h = C.c_void_p(f(lp, _res(self.labels), *wp, int(levels), int(use_gs)))
+
+    @property
+    def levels(self):
+        return int(self.lib.fn("solver_levels")(self.h))
+
+    @property
+    def setup_seconds(self):
+        return float(self.lib.fn("solver_setup_seconds", C.c_double)(self.h))
+
+    def vcycle(self, x, b, use_initial_guess=False, repeats=1):
+        x, xp = _f64(np.array(x, copy=True))
+        b, bp = _f64(b)
+        self.last_seconds = float(self.lib.fn("solver_vcycle", C.c_double)(self.h, xp, bp, int(use_initial_guess), int(repeats)))
+        return x
+
+    def pcg(self, x, b, tol, max_it):
+        x, xp = _f64(np.array(x, copy=True))
+        b, bp = _f64(b)
+        hist = np.zeros(max_it + 2, dtype=np.float64)
+        cnt = C.c_int()
+        secs = C.c_double()
+        it = self.lib.fn("pcg")(self.h, xp, bp, C.c_double(tol), int(max_it), hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt), C.byref(secs))
+        self.last_seconds = secs.value
+        return x, int(it), hist[: cnt.value].copy()
+
+    def close(self):
+        if self.h:
+            self.lib.fn("solver_destroy", None)(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PortLib(_Base):
+    prefix = "orc_"
+
+    def __init__(self):
+        super().__init__(PORT_SO)
+
+    def threads(self):
+        return int(self.fn("threads")())
+
+    def expand_dims(self, base_shape):
+        ores = (C.c_int64 * 3)()
+        off = (C.c_int64 * 3)()
+        lv = C.c_int()
+        self.fn("expand_dims", None)(_res_t(base_shape[::-1]), ores, off, C.byref(lv))
+        return (ores[2], ores[1], ores[0]), np.array(list(off), dtype=np.int64), int(lv.value)
+
+    def expand_labels(self, base):
+        b, bp = _i32(base)
+        shape, off, lv = self.expand_dims(b.shape)
+        out = np.empty(shape, dtype=np.int32)
+        self.fn("expand_labels", None)(bp, _res(b), out.ctypes.data_as(_i32p), _res(out), _res_t(off))
+        return out, off, lv
+
+    def expand_weights(self, base_w, base_shape, exp_labels, offset):
+        outs = []
+        for axis in range(3):
+            bw, bwp = _f64(base_w[axis])
+            out = np.empty(face_shape(exp_labels.shape, axis), dtype=np.float64)
+            self.fn("expand_weights", None)(bwp, _res_t(base_shape[::-1]), _res(exp_labels), _res_t(offset), axis, out.ctypes.data_as(_f64p))
+            outs.append(out)
+        return outs
+
+    def boundary_cells(self, labels, width=3):
+        l, lp = _i32(labels)
+        f = self.fn("boundary_cells", C.c_int64)
+        n = f(lp, _res(l), int(width), None, C.c_int64(0))
+        out = np.empty((max(n, 1), 3), dtype=np.int64)
+        f(lp, _res(l), int(width), out.ctypes.data_as(_i64p), C.c_int64(n))
+        return out[:n]
+
+    def solver(self, labels, w, levels, use_gs=False, coarse_scale=1.0):
+        return _PortSolver(self, labels, w, levels, use_gs, coarse_scale)
+
+
+class _PortSolver:
+    def __init__(self, lib, labels, w, levels, use_gs, coarse_scale):
+        self.lib = lib
+        self.labels, lp = _i32(labels)
+        keep, wp = _wptrs(w)
+        f = lib.fn("solver_create", C.c_void_p)
+        self.h = C.c_void_p(f(lp, _res(self.labels), *wp, int(levels), int(use_gs), C.c_double(coarse_scale)))
+        if not self.h:
+            raise RuntimeError("orc_solver_create failed (no solvable level)")
+
+    @property
+    def levels(self):
+        return int(self.lib.fn("solver_levels")(self.h))
+
+    def level_labels(self, level):
+        r = (C.c_int64 * 3)()
+        self.lib.fn("solver_level_res", None)(self.h, int(level), r)
+        out = np.empty((r[2], r[1], r[0]), dtype=np.int32)
+        self.lib.fn("solver_get_labels", None)(self.h, int(level), out.ctypes.data_as(_i32p))
+        return out
+
+    def level_boundary_cells(self, level):
+        n = self.lib.fn("solver_boundary_count", C.c_int64)(self.h, int(level))
+        out = np.empty((max(n, 1), 3), dtype=np.int64)
+        self.lib.fn("solver_get_boundary_cells", None)(self.h, int(level), out.ctypes.data_as(_i64p))
+        return out[:n]
+
+    @property
+    def coarse_unknowns(self):
+        return int(self.lib.fn("solver_coarse_unknowns", C.c_int64)(self.h))
+
+    def vcycle(self, x, b, use_initial_guess=False):
+        x, xp = _f64(np.array(x, copy=True))
+        b, bp = _f64(b)
+        self.lib.fn("solver_vcycle", None)(self.h, xp, bp, int(use_initial_guess))
+        return x
+
+    def pcg(self, x, b, tol, max_it):
+        x, xp = _f64(np.array(x, copy=True))
+        b, bp = _f64(b)
+        hist = np.zeros(max_it + 2, dtype=np.float64)
+        cnt = C.c_int()
+        it = self.lib.fn("pcg")(self.h, xp, bp, C.c_double(tol), int(max_it), hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt))
+        return x, int(it), hist[: cnt.value].copy()
+
+    def close(self):
+        if self.h:
+            self.lib.fn("solver_destroy", None)(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
