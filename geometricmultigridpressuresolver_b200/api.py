@@ -1,0 +1,410 @@
+"""Python host mirror of the reference's solver interface, over the C ABI of include/gmg_b200.h.
+
+The product is the CUDA library ``libgmg_b200.so`` next to this file; this module only marshals
+numpy arrays into it through ctypes.  There is no CPU path: importing works anywhere (so the
+build check can run on a CPU box), but creating a :class:`Context` without the library or without
+a CUDA device raises.
+
+Names follow the reference (rgoldade/GeometricMultigridPressureSolver):
+``buildExpandedCellLabels`` / ``buildExpandedBoundaryWeights`` / ``setBoundaryCellLabels`` /
+``buildCoarseCellLabels`` / ``buildBoundaryCells`` (HDK_GeometricMultigridOperators.h:121-157),
+``GeometricMultigridPoissonSolver`` with ``applyVCycle`` / ``getMGLevels``
+(HDK_GeometricMultigridPoissonSolver.h:10-53) and ``solveGeometricConjugateGradient``
+(HDK_GeometricCGPoissonSolver.h:11-27).  Arrays are C-order numpy with shape (rz, ry, rx): x fastest,
+like UT_VoxelArray.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgmg_b200.so")
+
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+STATUS = {0: "GMG_OK", 1: "GMG_ERR_CUDA", 2: "GMG_ERR_INVALID", 3: "GMG_ERR_NO_ACTIVE", 4: "GMG_ERR_COARSE_SIZE", 5: "GMG_ERR_NOT_SPD", 6: "GMG_ERR_COMM"}
+
+# every symbol include/gmg_b200.h declares (tests/test_abi.py checks the header against this and the .so)
+ABI_SYMBOLS = [
+    "gmg_last_error", "gmg_version", "gmg_ctx_create", "gmg_ctx_destroy", "gmg_ctx_synchronize", "gmg_ctx_shard", "gmg_nccl_unique_id",
+    "gmg_expand_dims", "gmg_expand_labels", "gmg_expand_weights", "gmg_set_boundary_labels", "gmg_coarsen_labels", "gmg_boundary_cells",
+    "gmg_solver_default_options", "gmg_solver_create", "gmg_solver_destroy", "gmg_solver_levels", "gmg_solver_level_res",
+    "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms",
+    "gmg_vcycle", "gmg_pcg", "gmg_grid_create", "gmg_grid_destroy", "gmg_grid_upload", "gmg_grid_download", "gmg_grid_zero", "gmg_grid_copy",
+    "gmg_jacobi", "gmg_boundary_jacobi", "gmg_apply", "gmg_residual", "gmg_restrict", "gmg_prolong_add", "gmg_dot", "gmg_norm2", "gmg_inf_norm",
+    "gmg_axpy", "gmg_add_scaled", "gmg_scale", "gmg_vcycle_device", "gmg_pcg_device", "gmg_launch_count", "gmg_timer_begin", "gmg_timer_end",
+    "gmg_profile_enable", "gmg_kernel_class_count", "gmg_kernel_class_name", "gmg_profile_get", "gmg_profile_reset",
+]
+
+
+class GmgError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{STATUS.get(status, status)}: {message}")
+        self.status = status
+
+
+class SolverOptions(C.Structure):
+    _fields_ = [
+        ("use_gauss_seidel", C.c_int),
+        ("print_stats", C.c_int),
+        ("boundary_width", C.c_int),
+        ("boundary_iterations", C.c_int),
+        ("coarse_matrix_scale", C.c_double),
+        ("box_lo", C.c_int64 * 3),
+        ("box_hi", C.c_int64 * 3),
+    ]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libgmg_b200.so (fails loudly: the product has no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GmgError(1, f"{LIB_PATH} is missing: build it with __graft_entry__.build() (nvcc, sm_100a)")
+        lib = C.CDLL(LIB_PATH)
+        lib.gmg_last_error.restype = C.c_char_p
+        lib.gmg_kernel_class_name.restype = C.c_char_p
+        lib.gmg_solver_default_options.restype = None
+        _lib = lib
+    return _lib
+
+
+def _check(st):
+    if st != 0:
+        raise GmgError(st, load_library().gmg_last_error().decode())
+
+
+def _res(shape):
+    return (C.c_int64 * 3)(int(shape[2]), int(shape[1]), int(shape[0]))
+
+
+def _vec3(v):
+    return (C.c_int64 * 3)(int(v[0]), int(v[1]), int(v[2]))
+
+
+def face_shape(shape, axis):
+    s = list(shape)
+    s[2 - axis] += 1
+    return tuple(s)
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_i32p)
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_f64p)
+
+
+class Context:
+    """One CUDA device + stream (gmg_ctx)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib.gmg_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def synchronize(self):
+        _check(self.lib.gmg_ctx_synchronize(self.h))
+
+    def launch_count(self, reset=False) -> int:
+        n = C.c_int64()
+        _check(self.lib.gmg_launch_count(self.h, C.byref(n), int(reset)))
+        return int(n.value)
+
+    def timer_begin(self):
+        _check(self.lib.gmg_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_double()
+        _check(self.lib.gmg_timer_end(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def profile_enable(self, on=True):
+        _check(self.lib.gmg_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        _check(self.lib.gmg_profile_reset(self.h))
+
+    def profile(self):
+        """{class name: (ms, launches, algorithmic bytes)} accumulated since the last reset."""
+        out = {}
+        for i in range(self.lib.gmg_kernel_class_count()):
+            ms, n, by = C.c_double(), C.c_int64(), C.c_double()
+            _check(self.lib.gmg_profile_get(self.h, i, C.byref(ms), C.byref(n), C.byref(by)))
+            out[self.lib.gmg_kernel_class_name(i).decode()] = (ms.value, int(n.value), by.value)
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gmg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- domain builders (HDK::GeometricMultigridOperators) ------------------------------------
+    def buildExpandedCellLabels(self, base_labels):
+        """Ops.h:1328-1456.  Returns (expanded labels, offset (x,y,z), mgLevels)."""
+        b, bp = _i32(base_labels)
+        eres, off, lv = (C.c_int64 * 3)(), (C.c_int64 * 3)(), C.c_int()
+        _check(self.lib.gmg_expand_dims(_res(b.shape), eres, off, C.byref(lv)))
+        out = np.empty((eres[2], eres[1], eres[0]), dtype=np.int32)
+        _check(self.lib.gmg_expand_labels(self.h, bp, _res(b.shape), out.ctypes.data_as(_i32p), eres, off))
+        return out, np.array(list(off), dtype=np.int64), int(lv.value)
+
+    def buildExpandedBoundaryWeights(self, base_weights, base_shape, exp_shape, offset, axis):
+        """Ops.h:1458-1572 for one axis."""
+        w, wp = _f64(base_weights)
+        out = np.empty(face_shape(exp_shape, axis), dtype=np.float64)
+        _check(self.lib.gmg_expand_weights(self.h, wp, _res(base_shape), out.ctypes.data_as(_f64p), _res(exp_shape), _vec3(offset), int(axis)))
+        return out
+
+    def setBoundaryCellLabels(self, labels, weights, box=None):
+        """Ops.h:1574-1644 (returns a new array)."""
+        l, lp = _i32(np.array(labels, copy=True))
+        ws = [_f64(w) for w in weights]
+        lo = _vec3(box[0]) if box else None
+        hi = _vec3(box[1]) if box else None
+        _check(self.lib.gmg_set_boundary_labels(self.h, lp, _res(l.shape), ws[0][1], ws[1][1], ws[2][1], lo, hi))
+        return l
+
+    def buildCoarseCellLabels(self, fine_labels):
+        """Ops.cpp:23-163."""
+        f, fp = _i32(fine_labels)
+        out = np.empty(tuple(s // 2 for s in f.shape), dtype=np.int32)
+        _check(self.lib.gmg_coarsen_labels(self.h, fp, _res(f.shape), out.ctypes.data_as(_i32p)))
+        return out
+
+    def buildBoundaryCells(self, labels, width=3):
+        """Ops.cpp:165-469.  Returns int64 (n,3) in the reference's order."""
+        l, lp = _i32(labels)
+        n = C.c_int64()
+        _check(self.lib.gmg_boundary_cells(self.h, lp, _res(l.shape), int(width), None, C.byref(n)))
+        out = np.empty((max(n.value, 1), 3), dtype=np.int64)
+        _check(self.lib.gmg_boundary_cells(self.h, lp, _res(l.shape), int(width), out.ctypes.data_as(_i64p), C.byref(n)))
+        return out[: n.value]
+
+    def buildExpandedDomain(self, base_labels, base_weights):
+        """Test.cpp:170-204 buildExpandedDomain: labels, three weight grids, setBoundaryCellLabels."""
+        labels, offset, levels = self.buildExpandedCellLabels(base_labels)
+        w = [self.buildExpandedBoundaryWeights(base_weights[a], base_labels.shape, labels.shape, offset, a) for a in range(3)]
+        hi = [int(offset[a]) + base_labels.shape[2 - a] for a in range(3)]
+        labels = self.setBoundaryCellLabels(labels, w, box=(offset, hi))
+        return labels, w, offset, levels
+
+
+class Grid:
+    """Device-resident fp64 vector grid of one solver level (gmg_grid)."""
+
+    def __init__(self, solver: "GeometricMultigridPoissonSolver", level: int = 0, host=None):
+        self.solver = solver
+        self.level = level
+        h = C.c_void_p()
+        _check(solver.lib.gmg_grid_create(solver.h, int(level), C.byref(h)))
+        self.h = h
+        if host is not None:
+            self.upload(host)
+
+    @property
+    def shape(self):
+        return self.solver.level_shape(self.level)
+
+    def upload(self, host):
+        a, ap = _f64(host)
+        assert a.shape == self.shape, (a.shape, self.shape)
+        _check(self.solver.lib.gmg_grid_upload(self.h, ap))
+        return self
+
+    def download(self):
+        out = np.empty(self.shape, dtype=np.float64)
+        _check(self.solver.lib.gmg_grid_download(self.h, out.ctypes.data_as(_f64p)))
+        return out
+
+    def zero(self):
+        _check(self.solver.lib.gmg_grid_zero(self.h))
+        return self
+
+    def copy_from(self, other: "Grid"):
+        _check(self.solver.lib.gmg_grid_copy(self.h, other.h))
+        return self
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.solver, "h", None):
+            self.solver.lib.gmg_grid_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GeometricMultigridPoissonSolver:
+    """HDK::GeometricMultigridPoissonSolver (HDK_GeometricMultigridPoissonSolver.h:10-53) on the GPU."""
+
+    def __init__(self, ctx: Context, initialCellLabels, boundaryWeights, mgLevels: int, useGaussSeidel: bool = False, doPrintStats: bool = False,
+                 coarse_matrix_scale: float = 1.0, box=None, boundary_iterations: int = 3, boundary_width: int = 3):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        l, lp = _i32(initialCellLabels)
+        ws = [_f64(w) for w in boundaryWeights]
+        for a in range(3):
+            assert ws[a][0].shape == face_shape(l.shape, a), "boundary weight grid shape (MG.cpp:167-177)"
+        opt = SolverOptions()
+        self.lib.gmg_solver_default_options(C.byref(opt))
+        opt.use_gauss_seidel = int(useGaussSeidel)
+        opt.print_stats = int(doPrintStats)
+        opt.coarse_matrix_scale = float(coarse_matrix_scale)
+        opt.boundary_iterations = int(boundary_iterations)
+        opt.boundary_width = int(boundary_width)
+        if box is not None:
+            for a in range(3):
+                opt.box_lo[a] = int(box[0][a])
+                opt.box_hi[a] = int(box[1][a])
+        h = C.c_void_p()
+        _check(self.lib.gmg_solver_create(ctx.h, lp, _res(l.shape), ws[0][1], ws[1][1], ws[2][1], int(mgLevels), C.byref(opt), C.byref(h)))
+        self.h = h
+        self.shape = l.shape
+
+    def getMGLevels(self) -> int:
+        n = C.c_int()
+        _check(self.lib.gmg_solver_levels(self.h, C.byref(n)))
+        return int(n.value)
+
+    def level_shape(self, level):
+        r = (C.c_int64 * 3)()
+        _check(self.lib.gmg_solver_level_res(self.h, int(level), r))
+        return (int(r[2]), int(r[1]), int(r[0]))
+
+    def level_labels(self, level):
+        out = np.empty(self.level_shape(level), dtype=np.int32)
+        _check(self.lib.gmg_solver_get_labels(self.h, int(level), out.ctypes.data_as(_i32p)))
+        return out
+
+    def level_boundary_cells(self, level):
+        n = C.c_int64()
+        _check(self.lib.gmg_solver_get_boundary_cells(self.h, int(level), None, C.byref(n)))
+        out = np.empty((max(n.value, 1), 3), dtype=np.int64)
+        _check(self.lib.gmg_solver_get_boundary_cells(self.h, int(level), out.ctypes.data_as(_i64p), C.byref(n)))
+        return out[: n.value]
+
+    def active_cells(self, level=0) -> int:
+        n = C.c_int64()
+        _check(self.lib.gmg_solver_active_cells(self.h, int(level), C.byref(n)))
+        return int(n.value)
+
+    def coarse_unknowns(self) -> int:
+        n = C.c_int64()
+        _check(self.lib.gmg_solver_coarse_unknowns(self.h, C.byref(n)))
+        return int(n.value)
+
+    def setup_ms(self) -> float:
+        ms = C.c_double()
+        _check(self.lib.gmg_solver_setup_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    # ---- host-buffer entry points (what the reference's callers use) ----------------------------
+    def applyVCycle(self, solutionVector, rhsVector, useInitialGuess: bool = False):
+        """MG.cpp:420-881; returns the new solution grid."""
+        x, xp = _f64(np.array(solutionVector, copy=True))
+        b, bp = _f64(rhsVector)
+        _check(self.lib.gmg_vcycle(self.h, xp, bp, int(useInitialGuess)))
+        return x
+
+    def solveGeometricConjugateGradient(self, solutionGrid, rhsGrid, tolerance, maxIterations, useMGPreconditioner: bool = True):
+        """CG.h:11-207 with A = applyPoissonMatrix, M^-1 = applyVCycle (GFS.cpp:430-483).
+        Returns (solution, iterations printed by CG.h:198 or -1 on an early-out, relative-residual history)."""
+        x, xp = _f64(np.array(solutionGrid, copy=True))
+        b, bp = _f64(rhsGrid)
+        hist = np.zeros(int(maxIterations) + 2, dtype=np.float64)
+        it, cnt = C.c_int(), C.c_int()
+        _check(self.lib.gmg_pcg(self.h, xp, bp, C.c_double(tolerance), int(maxIterations), int(useMGPreconditioner), C.byref(it),
+                                hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt)))
+        return x, int(it.value), hist[: cnt.value].copy()
+
+    # ---- device-resident operators ----------------------------------------------------------------
+    def grid(self, level=0, host=None) -> Grid:
+        return Grid(self, level, host)
+
+    def jacobiPoissonSmoother(self, x: Grid, b: Grid):
+        _check(self.lib.gmg_jacobi(self.h, x.h, b.h))
+
+    def boundaryJacobiPoissonSmoother(self, x: Grid, b: Grid, sweeps=1):
+        _check(self.lib.gmg_boundary_jacobi(self.h, x.h, b.h, int(sweeps)))
+
+    def applyPoissonMatrix(self, dst: Grid, src: Grid):
+        _check(self.lib.gmg_apply(self.h, dst.h, src.h))
+
+    def computePoissonResidual(self, r: Grid, x: Grid, b: Grid):
+        _check(self.lib.gmg_residual(self.h, r.h, x.h, b.h))
+
+    def downsample(self, coarse: Grid, fine: Grid):
+        _check(self.lib.gmg_restrict(self.h, coarse.h, fine.h))
+
+    def upsampleAndAdd(self, fine: Grid, coarse: Grid):
+        _check(self.lib.gmg_prolong_add(self.h, fine.h, coarse.h))
+
+    def dotProduct(self, a: Grid, b: Grid) -> float:
+        out = C.c_double()
+        _check(self.lib.gmg_dot(self.h, a.h, b.h, C.byref(out)))
+        return float(out.value)
+
+    def squaredL2Norm(self, a: Grid) -> float:
+        out = C.c_double()
+        _check(self.lib.gmg_norm2(self.h, a.h, C.byref(out)))
+        return float(out.value)
+
+    def l2Norm(self, a: Grid) -> float:
+        return float(np.sqrt(self.squaredL2Norm(a)))
+
+    def infNorm(self, a: Grid) -> float:
+        out = C.c_double()
+        _check(self.lib.gmg_inf_norm(self.h, a.h, C.byref(out)))
+        return float(out.value)
+
+    def addToVector(self, dst: Grid, src: Grid, scale: float):
+        _check(self.lib.gmg_axpy(self.h, dst.h, src.h, C.c_double(scale)))
+
+    def addVectors(self, dst: Grid, a: Grid, v: Grid, scale: float):
+        _check(self.lib.gmg_add_scaled(self.h, dst.h, a.h, v.h, C.c_double(scale)))
+
+    def scaleVector(self, v: Grid, scale: float):
+        _check(self.lib.gmg_scale(self.h, v.h, C.c_double(scale)))
+
+    def applyVCycleDevice(self, x: Grid, b: Grid, useInitialGuess=False):
+        _check(self.lib.gmg_vcycle_device(self.h, x.h, b.h, int(useInitialGuess)))
+
+    def solveDevice(self, x: Grid, b: Grid, tolerance, maxIterations, useMGPreconditioner=True):
+        hist = np.zeros(int(maxIterations) + 2, dtype=np.float64)
+        it, cnt = C.c_int(), C.c_int()
+        _check(self.lib.gmg_pcg_device(self.h, x.h, b.h, C.c_double(tolerance), int(maxIterations), int(useMGPreconditioner), C.byref(it),
+                                       hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt)))
+        return int(it.value), hist[: cnt.value].copy()
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.lib.gmg_solver_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

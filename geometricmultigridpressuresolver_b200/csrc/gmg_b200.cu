@@ -1,0 +1,1598 @@
+// gmg_b200.cu -- host side of the B200-native MGPCG library: C ABI (include/gmg_b200.h), solver
+// construction (labels, bands, coarse factor), V-cycle and PCG drivers.  No CPU fallback: every
+// entry point needs a CUDA device and fails with GMG_ERR_CUDA otherwise.
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+#include "gmg_kernels.cuh"
+
+using namespace gmg;
+
+// ====================================================================================================
+// errors, launch accounting
+// ====================================================================================================
+namespace
+{
+thread_local std::string g_lastError;
+const char *kClassNames[KC_COUNT] = {"jacobi_interior", "apply_poisson", "residual", "band_jacobi", "restrict", "prolong_add",
+				     "coarse_solve",    "blas1",         "reduce",   "zero_fill",   "setup",    "halo_exchange"};
+inline int64_t divUp(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int floorDiv2(int64_t v) { return int(v >= 0 ? v / 2 : -((-v + 1) / 2)); }
+inline int ceilDiv2(int64_t v) { return int(v >= 0 ? (v + 1) / 2 : -((-v) / 2)); }
+double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+} // namespace
+
+namespace gmg
+{
+void setError(const std::string &msg) { g_lastError = msg; }
+int cudaFail(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+    g_lastError = buf;
+    return GMG_ERR_CUDA;
+}
+LaunchScope::LaunchScope(gmg_ctx *c, int k, double b) : ctx(c), klass(k), bytes(b)
+{
+    ++ctx->launches;
+    if (!ctx->profiling) return;
+    auto get = [&]() {
+	cudaEvent_t e;
+	if (!ctx->eventPool.empty()) { e = ctx->eventPool.back(); ctx->eventPool.pop_back(); }
+	else cudaEventCreate(&e);
+	return e;
+    };
+    e0 = get();
+    e1 = get();
+    cudaEventRecord(e0, ctx->stream);
+}
+LaunchScope::~LaunchScope()
+{
+    if (!ctx->profiling) return;
+    cudaEventRecord(e1, ctx->stream);
+    ctx->recs.push_back({klass, bytes, e0, e1});
+}
+} // namespace gmg
+
+static int invalid(const char *msg)
+{
+    setError(msg);
+    return GMG_ERR_INVALID;
+}
+
+static void flushProfile(gmg_ctx *ctx)
+{
+    if (ctx->recs.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &r : ctx->recs)
+    {
+	float ms = 0;
+	cudaEventElapsedTime(&ms, r.e0, r.e1);
+	ctx->classMs[r.klass] += ms;
+	ctx->classLaunches[r.klass] += 1;
+	ctx->classBytes[r.klass] += r.bytes;
+	ctx->eventPool.push_back(r.e0);
+	ctx->eventPool.push_back(r.e1);
+    }
+    ctx->recs.clear();
+}
+
+static int ensureScratch(gmg_ctx *ctx, int nPartials)
+{
+    if (nPartials <= ctx->maxPartials) return GMG_OK;
+    if (ctx->partials) cudaFree(ctx->partials);
+    ctx->maxPartials = nPartials + 1024;
+    GMG_CUDA(cudaMalloc(&ctx->partials, sizeof(double) * ctx->maxPartials));
+    return GMG_OK;
+}
+
+// ====================================================================================================
+// context
+// ====================================================================================================
+extern "C" const char *gmg_last_error(void) { return g_lastError.c_str(); }
+extern "C" int gmg_version(void) { return 100; }
+
+extern "C" int gmg_ctx_create(int device, void *stream, gmg_ctx **out)
+{
+    if (!out) return invalid("gmg_ctx_create: out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+    {
+	setError("gmg_ctx_create: no CUDA device available (this library has no CPU fallback)");
+	return GMG_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) return invalid("gmg_ctx_create: device ordinal out of range");
+    GMG_CUDA(cudaSetDevice(device));
+    gmg_ctx *ctx = new gmg_ctx;
+    ctx->device = device;
+    if (stream) ctx->stream = static_cast<cudaStream_t>(stream);
+    else
+    {
+	GMG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	ctx->ownStream = true;
+    }
+    cudaDeviceProp prop;
+    GMG_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->smCount = prop.multiProcessorCount;
+    GMG_CUDA(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
+    GMG_CUDA(cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
+    GMG_CUDA(cudaMalloc(&ctx->scalars, sizeof(Scalars)));
+    GMG_CUDA(cudaMemset(ctx->scalars, 0, sizeof(Scalars)));
+    GMG_CUDA(cudaMallocHost(&ctx->hostScalars, sizeof(Scalars)));
+    GMG_CUDA(cudaEventCreate(&ctx->t0));
+    GMG_CUDA(cudaEventCreate(&ctx->t1));
+    GMG_TRY(ensureScratch(ctx, 4096));
+    *out = ctx;
+    return GMG_OK;
+}
+
+extern "C" int gmg_ctx_destroy(gmg_ctx *ctx)
+{
+    if (!ctx) return GMG_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    flushProfile(ctx);
+    for (auto e : ctx->eventPool) cudaEventDestroy(e);
+    cudaFree(ctx->partials);
+    cudaFree(ctx->ticket);
+    cudaFree(ctx->scalars);
+    cudaFreeHost(ctx->hostScalars);
+    cudaEventDestroy(ctx->t0);
+    cudaEventDestroy(ctx->t1);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GMG_OK;
+}
+
+extern "C" int gmg_ctx_synchronize(gmg_ctx *ctx)
+{
+    if (!ctx) return invalid("null ctx");
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
+}
+
+extern "C" int gmg_ctx_shard(gmg_ctx *, int, int world, const void *)
+{
+    if (world == 1) return GMG_OK;
+    return invalid("gmg_ctx_shard: z-slab sharding is not built in this revision");
+}
+extern "C" int gmg_nccl_unique_id(void *) { return invalid("gmg_nccl_unique_id: z-slab sharding is not built in this revision"); }
+
+extern "C" int gmg_launch_count(gmg_ctx *ctx, int64_t *count, int reset)
+{
+    if (!ctx) return invalid("null ctx");
+    if (count) *count = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return GMG_OK;
+}
+extern "C" int gmg_timer_begin(gmg_ctx *ctx)
+{
+    GMG_CUDA(cudaEventRecord(ctx->t0, ctx->stream));
+    return GMG_OK;
+}
+extern "C" int gmg_timer_end(gmg_ctx *ctx, double *ms)
+{
+    GMG_CUDA(cudaEventRecord(ctx->t1, ctx->stream));
+    GMG_CUDA(cudaEventSynchronize(ctx->t1));
+    float f = 0;
+    GMG_CUDA(cudaEventElapsedTime(&f, ctx->t0, ctx->t1));
+    if (ms) *ms = f;
+    return GMG_OK;
+}
+extern "C" int gmg_profile_enable(gmg_ctx *ctx, int on)
+{
+    flushProfile(ctx);
+    ctx->profiling = on != 0;
+    return GMG_OK;
+}
+extern "C" int gmg_kernel_class_count(void) { return KC_COUNT; }
+extern "C" const char *gmg_kernel_class_name(int i) { return (i >= 0 && i < KC_COUNT) ? kClassNames[i] : ""; }
+extern "C" int gmg_profile_get(gmg_ctx *ctx, int klass, double *ms, int64_t *launches, double *bytes)
+{
+    if (klass < 0 || klass >= KC_COUNT) return invalid("bad kernel class");
+    flushProfile(ctx);
+    if (ms) *ms = ctx->classMs[klass];
+    if (launches) *launches = ctx->classLaunches[klass];
+    if (bytes) *bytes = ctx->classBytes[klass];
+    return GMG_OK;
+}
+extern "C" int gmg_profile_reset(gmg_ctx *ctx)
+{
+    flushProfile(ctx);
+    for (int i = 0; i < KC_COUNT; ++i) { ctx->classMs[i] = 0; ctx->classLaunches[i] = 0; ctx->classBytes[i] = 0; }
+    return GMG_OK;
+}
+
+// ====================================================================================================
+// geometry helpers
+// ====================================================================================================
+static BoxArgs boxArgs(const Geom &g)
+{
+    BoxArgs b;
+    for (int a = 0; a < 3; ++a) { b.n[a] = g.n[a]; b.org[a] = g.org[a]; b.res[a] = g.res[a]; }
+    b.pitch = g.pitch;
+    b.plane = g.plane;
+    b.total = g.total;
+    return b;
+}
+
+// storage box of a level from the [lo,hi) bounds of its non-EXTERIOR cells
+static void makeGeom(Geom &g, const int64_t res[3], const int64_t lo[3], const int64_t hi[3])
+{
+    for (int a = 0; a < 3; ++a)
+    {
+	g.res[a] = res[a];
+	g.org[a] = 2 * (floorDiv2(lo[a]) - 1);
+	const int end = 2 * (ceilDiv2(hi[a]) + 1);
+	g.n[a] = end - g.org[a];
+    }
+    g.pitch = int(divUp(g.n[0], 16) * 16);
+    g.plane = int64_t(g.pitch) * g.n[1];
+    g.total = g.plane * g.n[2];
+    g.chunksPerPlane = int(divUp(g.plane, CHUNK_CELLS));
+    g.zBlocks = int(divUp(g.n[2], CHUNK_Z));
+}
+
+// clip of the storage box against the host grid [0, hostRes): storage-coordinate range [lo,hi) that exists on the host
+static bool clipBox(const Geom &g, const int64_t hostRes[3], int lo[3], int hi[3])
+{
+    bool any = true;
+    for (int a = 0; a < 3; ++a)
+    {
+	lo[a] = std::max<int64_t>(0, -int64_t(g.org[a]));
+	hi[a] = int(std::min<int64_t>(g.n[a], hostRes[a] - g.org[a]));
+	if (hi[a] <= lo[a]) any = false;
+    }
+    return any;
+}
+
+template <typename T>
+static int copyBoxH2D(gmg_ctx *ctx, T *staging, const T *host, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3])
+{
+    cudaMemcpy3DParms p = {};
+    p.srcPtr = make_cudaPitchedPtr(const_cast<T *>(host), size_t(hostRes[0]) * sizeof(T), size_t(hostRes[0]), size_t(hostRes[1]));
+    p.srcPos = make_cudaPos(size_t(g.org[0] + lo[0]) * sizeof(T), size_t(g.org[1] + lo[1]), size_t(g.org[2] + lo[2]));
+    const size_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
+    p.dstPtr = make_cudaPitchedPtr(staging, nx * sizeof(T), nx, ny);
+    p.dstPos = make_cudaPos(0, 0, 0);
+    p.extent = make_cudaExtent(nx * sizeof(T), ny, nz);
+    p.kind = cudaMemcpyHostToDevice;
+    GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    return GMG_OK;
+}
+template <typename T>
+static int copyBoxD2H(gmg_ctx *ctx, T *host, const T *staging, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3])
+{
+    cudaMemcpy3DParms p = {};
+    p.dstPtr = make_cudaPitchedPtr(host, size_t(hostRes[0]) * sizeof(T), size_t(hostRes[0]), size_t(hostRes[1]));
+    p.dstPos = make_cudaPos(size_t(g.org[0] + lo[0]) * sizeof(T), size_t(g.org[1] + lo[1]), size_t(g.org[2] + lo[2]));
+    const size_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
+    p.srcPtr = make_cudaPitchedPtr(const_cast<T *>(staging), nx * sizeof(T), nx, ny);
+    p.srcPos = make_cudaPos(0, 0, 0);
+    p.extent = make_cudaExtent(nx * sizeof(T), ny, nz);
+    p.kind = cudaMemcpyDeviceToHost;
+    GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    return GMG_OK;
+}
+
+// host scan for the [lo,hi) bounds of non-EXTERIOR labels (used when the caller gives no hint)
+static bool scanBounds(const int32_t *labels, const int64_t res[3], int64_t lo[3], int64_t hi[3])
+{
+    const int nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::array<int64_t, 6>> part(nt);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+	th.emplace_back([&, t]() {
+	    std::array<int64_t, 6> b = {res[0], res[1], res[2], -1, -1, -1};
+	    for (int64_t z = t; z < res[2]; z += nt)
+		for (int64_t y = 0; y < res[1]; ++y)
+		{
+		    const int32_t *row = labels + res[0] * (y + res[1] * z);
+		    int64_t x0 = 0, x1 = res[0] - 1;
+		    while (x0 <= x1 && row[x0] == L_EXTERIOR) ++x0;
+		    if (x0 > x1) continue;
+		    while (row[x1] == L_EXTERIOR) --x1;
+		    b[0] = std::min(b[0], x0); b[3] = std::max(b[3], x1);
+		    b[1] = std::min(b[1], y); b[4] = std::max(b[4], y);
+		    b[2] = std::min(b[2], z); b[5] = std::max(b[5], z);
+		}
+	    part[t] = b;
+	});
+    for (auto &t : th) t.join();
+    std::array<int64_t, 6> b = {res[0], res[1], res[2], -1, -1, -1};
+    for (auto &p : part)
+	for (int a = 0; a < 3; ++a) { b[a] = std::min(b[a], p[a]); b[a + 3] = std::max(b[a + 3], p[a + 3]); }
+    if (b[3] < 0) return false;
+    for (int a = 0; a < 3; ++a) { lo[a] = b[a]; hi[a] = b[a + 3] + 1; }
+    return true;
+}
+
+static int uploadLabels(gmg_ctx *ctx, uint8_t *dst, const int32_t *host, const int64_t res[3], const Geom &g)
+{
+    int lo[3], hi[3];
+    const BoxArgs ba = boxArgs(g);
+    if (!clipBox(g, res, lo, hi))
+    {
+	GMG_CUDA(cudaMemsetAsync(dst, L_EXTERIOR, g.total, ctx->stream));
+	return GMG_OK;
+    }
+    int32_t *staging = nullptr;
+    const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    GMG_CUDA(cudaMalloc(&staging, sizeof(int32_t) * cnt));
+    GMG_TRY(copyBoxH2D(ctx, staging, host, res, g, lo, hi));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_labels_from_i32<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dst, staging, ba, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
+    }
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(staging));
+    return GMG_OK;
+}
+
+static int downloadLabels(gmg_ctx *ctx, int32_t *host, const uint8_t *src, const int64_t res[3], const Geom &g, bool fillExterior)
+{
+    if (fillExterior)
+    {
+	const int64_t n = res[0] * res[1] * res[2];
+	std::fill(host, host + n, int32_t(L_EXTERIOR));
+    }
+    int lo[3], hi[3];
+    if (!clipBox(g, res, lo, hi)) return GMG_OK;
+    int32_t *staging = nullptr;
+    const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    GMG_CUDA(cudaMalloc(&staging, sizeof(int32_t) * cnt));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_labels_to_i32<<<unsigned(divUp(cnt, BLOCK)), BLOCK, 0, ctx->stream>>>(staging, src, boxArgs(g), lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
+    }
+    GMG_TRY(copyBoxD2H(ctx, host, staging, res, g, lo, hi));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(staging));
+    return GMG_OK;
+}
+
+// host dense grid (hostRes may be a face grid) -> pitched storage, zero where the host has no value
+static int uploadValues(gmg_ctx *ctx, double *dst, const double *host, const int64_t hostRes[3], const Geom &g, const uint8_t *maskLabels = nullptr)
+{
+    int lo[3], hi[3];
+    if (!clipBox(g, hostRes, lo, hi))
+    {
+	GMG_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * g.total, ctx->stream));
+	return GMG_OK;
+    }
+    double *staging = nullptr;
+    const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    GMG_CUDA(cudaMalloc(&staging, sizeof(double) * cnt));
+    GMG_TRY(copyBoxH2D(ctx, staging, host, hostRes, g, lo, hi));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_values_from_staging<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dst, staging, maskLabels, boxArgs(g), lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
+    }
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(staging));
+    return GMG_OK;
+}
+
+static int downloadValues(gmg_ctx *ctx, double *host, const double *src, const int64_t hostRes[3], const Geom &g, bool fillZero)
+{
+    if (fillZero) std::memset(host, 0, sizeof(double) * size_t(hostRes[0]) * hostRes[1] * hostRes[2]);
+    int lo[3], hi[3];
+    if (!clipBox(g, hostRes, lo, hi)) return GMG_OK;
+    double *staging = nullptr;
+    const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    GMG_CUDA(cudaMalloc(&staging, sizeof(double) * cnt));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_values_to_staging<<<unsigned(divUp(cnt, BLOCK)), BLOCK, 0, ctx->stream>>>(staging, src, boxArgs(g), lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
+    }
+    GMG_TRY(copyBoxD2H(ctx, host, staging, hostRes, g, lo, hi));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(staging));
+    return GMG_OK;
+}
+
+// ====================================================================================================
+// device-side builders shared by the solver constructor and the stand-alone builder entry points
+// ====================================================================================================
+static int countLabels(gmg_ctx *ctx, const uint8_t *labels, int64_t total, int64_t *nInterior, int64_t *nBoundary)
+{
+    unsigned long long *d = nullptr, h[2] = {0, 0};
+    GMG_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    GMG_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	const unsigned grid = unsigned(std::min<int64_t>(divUp(total, BLOCK), 4096));
+	k_count_labels<<<grid, BLOCK, 0, ctx->stream>>>(labels, total, d);
+    }
+    GMG_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(d));
+    *nInterior = int64_t(h[0]);
+    *nBoundary = int64_t(h[1]);
+    return GMG_OK;
+}
+
+// compaction of the indices i in [0,n) with flags[i] != 0 (ascending)
+static int selectFlagged(gmg_ctx *ctx, const uint8_t *flags, int64_t n, int32_t **out, int *count)
+{
+    int *dCount = nullptr;
+    int32_t *tmpOut = nullptr;
+    GMG_CUDA(cudaMalloc(&dCount, sizeof(int)));
+    GMG_CUDA(cudaMalloc(&tmpOut, sizeof(int32_t) * std::max<int64_t>(n, 1)));
+    void *dTemp = nullptr;
+    size_t tempBytes = 0;
+    thrust::counting_iterator<int32_t> it(0);
+    GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, it, flags, tmpOut, dCount, int(n), ctx->stream));
+    GMG_CUDA(cudaMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
+    GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, it, flags, tmpOut, dCount, int(n), ctx->stream));
+    ++ctx->launches;
+    int h = 0;
+    GMG_CUDA(cudaMemcpyAsync(&h, dCount, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *count = h;
+    *out = nullptr;
+    GMG_CUDA(cudaMalloc(out, sizeof(int32_t) * std::max(h, 1)));
+    GMG_CUDA(cudaMemcpyAsync(*out, tmpOut, sizeof(int32_t) * h, cudaMemcpyDeviceToDevice, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(dTemp));
+    GMG_CUDA(cudaFree(tmpOut));
+    GMG_CUDA(cudaFree(dCount));
+    return GMG_OK;
+}
+
+// boundary band of one level: BOUNDARY cells first, then the INTERIOR cells within width-1 steps (Ops.cpp:165-469)
+static int buildBand(gmg_ctx *ctx, Level &L, int width)
+{
+    const Geom &g = L.g;
+    const BoxArgs ba = boxArgs(g);
+    const unsigned grid = unsigned(divUp(g.total, BLOCK));
+    uint8_t *m0 = nullptr, *m1 = nullptr;
+    GMG_CUDA(cudaMalloc(&m0, g.total));
+    GMG_CUDA(cudaMalloc(&m1, g.total));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_band_init<<<grid, BLOCK, 0, ctx->stream>>>(m0, L.labels, g.total);
+    }
+    for (int layer = 0; layer < width - 1; ++layer)
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_band_dilate<<<grid, BLOCK, 0, ctx->stream>>>(m1, m0, L.labels, ba);
+	std::swap(m0, m1);
+    }
+    int32_t *idxB = nullptr, *idxI = nullptr;
+    int nB = 0, nI = 0;
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_band_flags<<<grid, BLOCK, 0, ctx->stream>>>(m1, m0, L.labels, 0, g.total);
+    }
+    GMG_TRY(selectFlagged(ctx, m1, g.total, &idxB, &nB));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_band_flags<<<grid, BLOCK, 0, ctx->stream>>>(m1, m0, L.labels, 1, g.total);
+    }
+    GMG_TRY(selectFlagged(ctx, m1, g.total, &idxI, &nI));
+    GMG_CUDA(cudaFree(m0));
+    GMG_CUDA(cudaFree(m1));
+    L.nBoundary = nB;
+    L.nBand = nB + nI;
+    const int nBand = L.nBand;
+    GMG_CUDA(cudaMalloc(&L.bandIdx, sizeof(int32_t) * std::max(nBand, 1)));
+    GMG_CUDA(cudaMemcpyAsync(L.bandIdx, idxB, sizeof(int32_t) * nB, cudaMemcpyDeviceToDevice, ctx->stream));
+    GMG_CUDA(cudaMemcpyAsync(L.bandIdx + nB, idxI, sizeof(int32_t) * nI, cudaMemcpyDeviceToDevice, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(idxB));
+    GMG_CUDA(cudaFree(idxI));
+    GMG_CUDA(cudaMalloc(&L.bandNbr, sizeof(int32_t) * 6 * std::max(nBand, 1)));
+    GMG_CUDA(cudaMalloc(&L.bandV0, sizeof(double) * std::max(nBand, 1)));
+    GMG_CUDA(cudaMalloc(&L.bandV1, sizeof(double) * std::max(nBand, 1)));
+    GMG_CUDA(cudaMalloc(&L.bandB, sizeof(double) * std::max(nBand, 1)));
+    if (nBand > 0)
+    {
+	int32_t *pos = nullptr;
+	GMG_CUDA(cudaMalloc(&pos, sizeof(int32_t) * g.total));
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_fill_i32<<<grid, BLOCK, 0, ctx->stream>>>(pos, -1, g.total);
+	}
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_band_pos<<<unsigned(divUp(nBand, BLOCK)), BLOCK, 0, ctx->stream>>>(pos, L.bandIdx, nBand);
+	}
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_band_nbr<<<unsigned(divUp(nBand, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bandNbr, pos, L.bandIdx, nBand, g.pitch, g.plane);
+	}
+	GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+	GMG_CUDA(cudaFree(pos));
+    }
+    return GMG_OK;
+}
+
+static int buildCoefs(gmg_ctx *ctx, Level &L, const double *w0, const double *w1, const double *w2)
+{
+    GMG_CUDA(cudaMalloc(&L.bcoef, sizeof(double) * 7 * std::max(L.nBoundary, 1)));
+    if (L.nBoundary > 0)
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_band_coef<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bcoef, L.bandIdx, L.nBoundary, L.labels, w0, w1, w2, L.g.pitch,
+										   L.g.plane);
+    }
+    return GMG_OK;
+}
+
+static int buildChunks(gmg_ctx *ctx, Level &L)
+{
+    const Geom &g = L.g;
+    const int nChunks = g.chunksPerPlane * g.zBlocks;
+    uint8_t *fi = nullptr, *fa = nullptr;
+    GMG_CUDA(cudaMalloc(&fi, nChunks));
+    GMG_CUDA(cudaMalloc(&fa, nChunks));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_chunk_flags<<<nChunks, BLOCK, 0, ctx->stream>>>(fi, fa, L.labels, g.chunksPerPlane, g.plane, g.n[2]);
+    }
+    GMG_TRY(selectFlagged(ctx, fi, nChunks, &L.chunksInterior, &L.nChunksInterior));
+    GMG_TRY(selectFlagged(ctx, fa, nChunks, &L.chunksActive, &L.nChunksActive));
+    GMG_CUDA(cudaFree(fi));
+    GMG_CUDA(cudaFree(fa));
+    return GMG_OK;
+}
+
+// band list in the reference's order (tile, z, y, x) and expanded coordinates
+static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz)
+{
+    const int n = L.nBand;
+    if (n == 0) return GMG_OK;
+    unsigned long long *keys = nullptr, *keysOut = nullptr;
+    GMG_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * n));
+    GMG_CUDA(cudaMalloc(&keysOut, sizeof(unsigned long long) * n));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_band_keys<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(keys, L.bandIdx, n, boxArgs(L.g));
+    }
+    void *dTemp = nullptr;
+    size_t tempBytes = 0;
+    GMG_CUDA(cub::DeviceRadixSort::SortKeys(dTemp, tempBytes, keys, keysOut, n, 0, 64, ctx->stream));
+    GMG_CUDA(cudaMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
+    GMG_CUDA(cub::DeviceRadixSort::SortKeys(dTemp, tempBytes, keys, keysOut, n, 0, 64, ctx->stream));
+    ++ctx->launches;
+    std::vector<unsigned long long> h(n);
+    GMG_CUDA(cudaMemcpyAsync(h.data(), keysOut, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n; ++k)
+    {
+	xyz[3 * k] = int64_t(h[k] & 0xfff);
+	xyz[3 * k + 1] = int64_t((h[k] >> 12) & 0xfff);
+	xyz[3 * k + 2] = int64_t((h[k] >> 24) & 0xfff);
+    }
+    GMG_CUDA(cudaFree(dTemp));
+    GMG_CUDA(cudaFree(keys));
+    GMG_CUDA(cudaFree(keysOut));
+    return GMG_OK;
+}
+
+static void freeLevel(Level &L)
+{
+    cudaFree(L.labels); cudaFree(L.bandIdx); cudaFree(L.bandNbr); cudaFree(L.bcoef);
+    cudaFree(L.bandV0); cudaFree(L.bandV1); cudaFree(L.bandB);
+    cudaFree(L.chunksInterior); cudaFree(L.chunksActive);
+    cudaFree(L.x); cudaFree(L.xAlt); cudaFree(L.b); cudaFree(L.r);
+    L = Level();
+}
+
+// ====================================================================================================
+// stand-alone domain builders
+// ====================================================================================================
+extern "C" int gmg_expand_dims(const int64_t baseRes[3], int64_t expRes[3], int64_t offset[3], int *mgLevels)
+{
+    if (!baseRes || !expRes || !offset || !mgLevels) return invalid("gmg_expand_dims: null argument");
+    // HDK_GeometricMultigridOperators.h:1340-1360, reproduced literally (double log2 / ceil / pow / exp2)
+    double minLog = std::min(std::log2(double(baseRes[0])), std::log2(double(baseRes[1])));
+    minLog = std::min(minLog, std::log2(double(baseRes[2])));
+    const int levels = int(std::ceil(minLog) - std::log2(2.0));
+    const int pad = int(std::pow(2, levels - 1));
+    for (int a = 0; a < 3; ++a)
+    {
+	const double logSize = std::ceil(std::log2(double(baseRes[a] + 2 * pad)));
+	expRes[a] = int64_t(std::exp2(logSize));
+	offset[a] = pad;
+    }
+    *mgLevels = levels;
+    return GMG_OK;
+}
+
+extern "C" int gmg_expand_labels(gmg_ctx *ctx, const int32_t *base, const int64_t baseRes[3], int32_t *out, const int64_t expRes[3],
+				 const int64_t offset[3])
+{
+    if (!ctx || !base || !out) return invalid("gmg_expand_labels: null argument");
+    GMG_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = baseRes[0] * baseRes[1] * baseRes[2];
+    int32_t *dIn = nullptr, *dOut = nullptr;
+    GMG_CUDA(cudaMalloc(&dIn, sizeof(int32_t) * n));
+    GMG_CUDA(cudaMalloc(&dOut, sizeof(int32_t) * n));
+    GMG_CUDA(cudaMemcpyAsync(dIn, base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_expand_labels<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(dOut, dIn, n);
+    }
+    // EXTERIOR everywhere, then the mapped base box at +offset
+    std::fill(out, out + expRes[0] * expRes[1] * expRes[2], int32_t(L_EXTERIOR));
+    cudaMemcpy3DParms p = {};
+    p.dstPtr = make_cudaPitchedPtr(out, size_t(expRes[0]) * 4, size_t(expRes[0]), size_t(expRes[1]));
+    p.dstPos = make_cudaPos(size_t(offset[0]) * 4, size_t(offset[1]), size_t(offset[2]));
+    p.srcPtr = make_cudaPitchedPtr(dOut, size_t(baseRes[0]) * 4, size_t(baseRes[0]), size_t(baseRes[1]));
+    p.extent = make_cudaExtent(size_t(baseRes[0]) * 4, size_t(baseRes[1]), size_t(baseRes[2]));
+    p.kind = cudaMemcpyDeviceToHost;
+    GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(dIn));
+    GMG_CUDA(cudaFree(dOut));
+    return GMG_OK;
+}
+
+extern "C" int gmg_expand_weights(gmg_ctx *ctx, const double *baseW, const int64_t baseRes[3], double *out, const int64_t expRes[3],
+				  const int64_t offset[3], int axis)
+{
+    if (!ctx || !baseW || !out || axis < 0 || axis > 2) return invalid("gmg_expand_weights: bad argument");
+    GMG_CUDA(cudaSetDevice(ctx->device));
+    int64_t bfr[3] = {baseRes[0], baseRes[1], baseRes[2]}, efr[3] = {expRes[0], expRes[1], expRes[2]};
+    ++bfr[axis];
+    ++efr[axis];
+    const int64_t n = bfr[0] * bfr[1] * bfr[2];
+    double *dIn = nullptr, *dOut = nullptr;
+    GMG_CUDA(cudaMalloc(&dIn, sizeof(double) * n));
+    GMG_CUDA(cudaMalloc(&dOut, sizeof(double) * n));
+    GMG_CUDA(cudaMemcpyAsync(dIn, baseW, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_expand_weights<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(dOut, dIn, n);
+    }
+    std::memset(out, 0, sizeof(double) * size_t(efr[0]) * efr[1] * efr[2]);
+    cudaMemcpy3DParms p = {};
+    p.dstPtr = make_cudaPitchedPtr(out, size_t(efr[0]) * 8, size_t(efr[0]), size_t(efr[1]));
+    p.dstPos = make_cudaPos(size_t(offset[0]) * 8, size_t(offset[1]), size_t(offset[2]));
+    p.srcPtr = make_cudaPitchedPtr(dOut, size_t(bfr[0]) * 8, size_t(bfr[0]), size_t(bfr[1]));
+    p.extent = make_cudaExtent(size_t(bfr[0]) * 8, size_t(bfr[1]), size_t(bfr[2]));
+    p.kind = cudaMemcpyDeviceToHost;
+    GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(dIn));
+    GMG_CUDA(cudaFree(dOut));
+    return GMG_OK;
+}
+
+static int boundsFromHintOrScan(const int32_t *labels, const int64_t res[3], const int64_t *hLo, const int64_t *hHi, int64_t lo[3], int64_t hi[3])
+{
+    const bool hint = hLo && hHi && (hHi[0] > hLo[0]) && (hHi[1] > hLo[1]) && (hHi[2] > hLo[2]);
+    if (hint)
+    {
+	for (int a = 0; a < 3; ++a) { lo[a] = hLo[a]; hi[a] = hHi[a]; }
+	return GMG_OK;
+    }
+    if (!scanBounds(labels, res, lo, hi))
+    {
+	setError("no non-EXTERIOR cell in the label grid");
+	return GMG_ERR_NO_ACTIVE;
+    }
+    return GMG_OK;
+}
+
+static int uploadWeights(gmg_ctx *ctx, double *dW[3], const double *w0, const double *w1, const double *w2, const int64_t res[3], const Geom &g)
+{
+    const double *w[3] = {w0, w1, w2};
+    for (int a = 0; a < 3; ++a)
+    {
+	int64_t fr[3] = {res[0], res[1], res[2]};
+	++fr[a];
+	GMG_CUDA(cudaMalloc(&dW[a], sizeof(double) * g.total));
+	GMG_TRY(uploadValues(ctx, dW[a], w[a], fr, g));
+    }
+    return GMG_OK;
+}
+
+extern "C" int gmg_set_boundary_labels(gmg_ctx *ctx, int32_t *labels, const int64_t res[3], const double *w0, const double *w1, const double *w2,
+				       const int64_t boxLo[3], const int64_t boxHi[3])
+{
+    if (!ctx || !labels || !w0 || !w1 || !w2) return invalid("gmg_set_boundary_labels: null argument");
+    GMG_CUDA(cudaSetDevice(ctx->device));
+    int64_t lo[3], hi[3];
+    int st = boundsFromHintOrScan(labels, res, boxLo, boxHi, lo, hi);
+    if (st == GMG_ERR_NO_ACTIVE) return GMG_OK; // nothing to promote
+    GMG_TRY(st);
+    Geom g;
+    makeGeom(g, res, lo, hi);
+    uint8_t *dIn = nullptr, *dOut = nullptr;
+    double *dW[3] = {nullptr, nullptr, nullptr};
+    GMG_CUDA(cudaMalloc(&dIn, g.total));
+    GMG_CUDA(cudaMalloc(&dOut, g.total));
+    GMG_TRY(uploadLabels(ctx, dIn, labels, res, g));
+    GMG_TRY(uploadWeights(ctx, dW, w0, w1, w2, res, g));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_set_boundary<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dOut, dIn, dW[0], dW[1], dW[2], boxArgs(g));
+    }
+    GMG_TRY(downloadLabels(ctx, labels, dOut, res, g, false));
+    for (int a = 0; a < 3; ++a) GMG_CUDA(cudaFree(dW[a]));
+    GMG_CUDA(cudaFree(dIn));
+    GMG_CUDA(cudaFree(dOut));
+    return GMG_OK;
+}
+
+// fine (level-like) geometry + its coarse geometry
+static void coarseGeomOf(Geom &cg, int shift[3], const Geom &fg, const int64_t lo[3], const int64_t hi[3], int64_t clo[3], int64_t chi[3])
+{
+    int64_t cres[3];
+    for (int a = 0; a < 3; ++a)
+    {
+	cres[a] = fg.res[a] / 2;
+	clo[a] = floorDiv2(lo[a]);
+	chi[a] = ceilDiv2(hi[a]);
+    }
+    makeGeom(cg, cres, clo, chi);
+    for (int a = 0; a < 3; ++a) shift[a] = fg.org[a] / 2 - cg.org[a];
+}
+
+static int coarsenOnDevice(gmg_ctx *ctx, uint8_t *coarse, const Geom &cg, const uint8_t *fine, const Geom &fg, const int shift[3])
+{
+    uint8_t *tmp = nullptr;
+    GMG_CUDA(cudaMalloc(&tmp, cg.total));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_coarsen1<<<unsigned(divUp(cg.total, BLOCK)), BLOCK, 0, ctx->stream>>>(tmp, fine, boxArgs(cg), boxArgs(fg), shift[0], shift[1], shift[2]);
+    }
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_coarsen2<<<unsigned(divUp(cg.total, BLOCK)), BLOCK, 0, ctx->stream>>>(coarse, tmp, boxArgs(cg));
+    }
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaFree(tmp));
+    return GMG_OK;
+}
+
+extern "C" int gmg_coarsen_labels(gmg_ctx *ctx, const int32_t *fine, const int64_t fineRes[3], int32_t *coarse)
+{
+    if (!ctx || !fine || !coarse) return invalid("gmg_coarsen_labels: null argument");
+    for (int a = 0; a < 3; ++a)
+	if (fineRes[a] % 2) return invalid("gmg_coarsen_labels: odd resolution");
+    GMG_CUDA(cudaSetDevice(ctx->device));
+    int64_t lo[3], hi[3], clo[3], chi[3];
+    const int64_t cres[3] = {fineRes[0] / 2, fineRes[1] / 2, fineRes[2] / 2};
+    if (!scanBounds(fine, fineRes, lo, hi))
+    {
+	std::fill(coarse, coarse + cres[0] * cres[1] * cres[2], int32_t(L_EXTERIOR));
+	return GMG_OK;
+    }
+    Geom fg, cg;
+    int shift[3];
+    makeGeom(fg, fineRes, lo, hi);
+    coarseGeomOf(cg, shift, fg, lo, hi, clo, chi);
+    uint8_t *dF = nullptr, *dC = nullptr;
+    GMG_CUDA(cudaMalloc(&dF, fg.total));
+    GMG_CUDA(cudaMalloc(&dC, cg.total));
+    GMG_TRY(uploadLabels(ctx, dF, fine, fineRes, fg));
+    GMG_TRY(coarsenOnDevice(ctx, dC, cg, dF, fg, shift));
+    GMG_TRY(downloadLabels(ctx, coarse, dC, cres, cg, true));
+    GMG_CUDA(cudaFree(dF));
+    GMG_CUDA(cudaFree(dC));
+    return GMG_OK;
+}
+
+extern "C" int gmg_boundary_cells(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], int width, int64_t *xyz, int64_t *count)
+{
+    if (!ctx || !labels || !count) return invalid("gmg_boundary_cells: null argument");
+    GMG_CUDA(cudaSetDevice(ctx->device));
+    int64_t lo[3], hi[3];
+    if (!scanBounds(labels, res, lo, hi)) { *count = 0; return GMG_OK; }
+    Level L;
+    makeGeom(L.g, res, lo, hi);
+    GMG_CUDA(cudaMalloc(&L.labels, L.g.total));
+    GMG_TRY(uploadLabels(ctx, L.labels, labels, res, L.g));
+    GMG_TRY(buildBand(ctx, L, width));
+    *count = L.nBand;
+    int st = GMG_OK;
+    if (xyz) st = exportBand(ctx, L, xyz);
+    freeLevel(L);
+    return st;
+}
+
+// ====================================================================================================
+// solver construction (MG.cpp:135-418)
+// ====================================================================================================
+extern "C" void gmg_solver_default_options(gmg_solver_options *opt)
+{
+    if (!opt) return;
+    std::memset(opt, 0, sizeof(*opt));
+    opt->boundary_width = 3;
+    opt->boundary_iterations = 3;
+    opt->coarse_matrix_scale = 1.0;
+}
+
+static int allocZero(double **p, int64_t n)
+{
+    GMG_CUDA(cudaMalloc(p, sizeof(double) * n));
+    GMG_CUDA(cudaMemset(*p, 0, sizeof(double) * n));
+    return GMG_OK;
+}
+
+// coarsest level: number the active cells like the reference (tile order, x fastest in tile; MG.cpp:296-323), assemble
+// (MG.cpp:359-382), factor exactly (dense Cholesky) and keep the explicit inverse for a one-launch device solve.
+static int buildCoarseSolve(gmg_solver *s)
+{
+    gmg_ctx *ctx = s->ctx;
+    Level &L = s->lv[s->levels - 1];
+    const Geom &g = L.g;
+    std::vector<uint8_t> lab(g.total);
+    GMG_CUDA(cudaMemcpy(lab.data(), L.labels, g.total, cudaMemcpyDeviceToHost));
+    auto labelAtExp = [&](int64_t ex, int64_t ey, int64_t ez) -> int {
+	const int64_t x = ex - g.org[0], y = ey - g.org[1], z = ez - g.org[2];
+	if (x < 0 || y < 0 || z < 0 || x >= g.n[0] || y >= g.n[1] || z >= g.n[2]) return L_EXTERIOR;
+	return lab[z * g.plane + y * g.pitch + x];
+    };
+    auto isActive = [](int l) { return l == L_INTERIOR || l == L_BOUNDARY; };
+    // tile-ordered numbering over the stored box (tiles of the expanded grid)
+    std::vector<int32_t> index(g.total, -1);
+    std::vector<int32_t> cellIdx;
+    const int64_t t0[3] = {std::max<int64_t>(0, g.org[0]) >> 4, std::max<int64_t>(0, g.org[1]) >> 4, std::max<int64_t>(0, g.org[2]) >> 4};
+    const int64_t t1[3] = {(g.org[0] + g.n[0] + 15) >> 4, (g.org[1] + g.n[1] + 15) >> 4, (g.org[2] + g.n[2] + 15) >> 4};
+    for (int64_t tz = t0[2]; tz < t1[2]; ++tz)
+	for (int64_t ty = t0[1]; ty < t1[1]; ++ty)
+	    for (int64_t tx = t0[0]; tx < t1[0]; ++tx)
+		for (int64_t ez = tz * 16; ez < tz * 16 + 16; ++ez)
+		    for (int64_t ey = ty * 16; ey < ty * 16 + 16; ++ey)
+			for (int64_t ex = tx * 16; ex < tx * 16 + 16; ++ex)
+			    if (isActive(labelAtExp(ex, ey, ez)))
+			    {
+				const int64_t si = (ez - g.org[2]) * g.plane + (ey - g.org[1]) * g.pitch + (ex - g.org[0]);
+				index[si] = int32_t(cellIdx.size());
+				cellIdx.push_back(int32_t(si));
+			    }
+    const int n = int(cellIdx.size());
+    s->nCoarse = n;
+    if (n == 0) { setError("coarsest level has no active cell"); return GMG_ERR_NO_ACTIVE; }
+    if (n > MAX_COARSE)
+    {
+	char buf[256];
+	snprintf(buf, sizeof(buf), "coarsest level has %d unknowns; the dense direct solve supports at most %d", n, MAX_COARSE);
+	setError(buf);
+	return GMG_ERR_COARSE_SIZE;
+    }
+    const double scale = s->opt.coarse_matrix_scale > 0 ? s->opt.coarse_matrix_scale : 1.0;
+    std::vector<double> A(size_t(n) * n, 0.0);
+    const int64_t stride[6] = {-1, 1, -int64_t(g.pitch), int64_t(g.pitch), -g.plane, g.plane};
+    for (int r = 0; r < n; ++r)
+    {
+	const int64_t si = cellIdx[r];
+	double diag = 0;
+	for (int k = 0; k < 6; ++k)
+	{
+	    const int nl = lab[si + stride[k]];
+	    if (isActive(nl)) { A[size_t(r) * n + index[si + stride[k]]] += -1.0 * scale; diag += 1; }
+	    else if (nl == L_DIRICHLET) diag += 1;
+	}
+	A[size_t(r) * n + r] += diag * scale;
+    }
+    // Cholesky A = L L^T (in place, lower), then inverse via forward/back substitution on the identity
+    std::vector<double> Lm(A);
+    for (int j = 0; j < n; ++j)
+    {
+	double d = Lm[size_t(j) * n + j];
+	for (int k = 0; k < j; ++k) d -= Lm[size_t(j) * n + k] * Lm[size_t(j) * n + k];
+	if (!(d > 0))
+	{
+	    setError("coarse matrix is not positive definite (pure-Neumann domain without a DIRICHLET cell?)");
+	    return GMG_ERR_NOT_SPD;
+	}
+	d = std::sqrt(d);
+	Lm[size_t(j) * n + j] = d;
+	for (int i = j + 1; i < n; ++i)
+	{
+	    double v = Lm[size_t(i) * n + j];
+	    const double *ri = &Lm[size_t(i) * n], *rj = &Lm[size_t(j) * n];
+	    for (int k = 0; k < j; ++k) v -= ri[k] * rj[k];
+	    Lm[size_t(i) * n + j] = v / d;
+	}
+    }
+    // Y = L^-1 (lower triangular), inv = Y^T Y
+    std::vector<double> Y(size_t(n) * n, 0.0);
+    for (int c = 0; c < n; ++c)
+    {
+	for (int i = c; i < n; ++i)
+	{
+	    double v = (i == c) ? 1.0 : 0.0;
+	    const double *ri = &Lm[size_t(i) * n];
+	    for (int k = c; k < i; ++k) v -= ri[k] * Y[size_t(k) * n + c];
+	    Y[size_t(i) * n + c] = v / ri[i];
+	}
+    }
+    std::vector<double> inv(size_t(n) * n, 0.0);
+    for (int i = 0; i < n; ++i)
+	for (int j = 0; j <= i; ++j)
+	{
+	    double v = 0;
+	    for (int k = i; k < n; ++k) v += Y[size_t(k) * n + i] * Y[size_t(k) * n + j];
+	    inv[size_t(i) * n + j] = v;
+	    inv[size_t(j) * n + i] = v;
+	}
+    GMG_CUDA(cudaMalloc(&s->coarseIdx, sizeof(int32_t) * n));
+    GMG_CUDA(cudaMalloc(&s->coarseInv, sizeof(double) * size_t(n) * n));
+    GMG_CUDA(cudaMemcpy(s->coarseIdx, cellIdx.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    GMG_CUDA(cudaMemcpy(s->coarseInv, inv.data(), sizeof(double) * size_t(n) * n, cudaMemcpyHostToDevice));
+    return GMG_OK;
+}
+
+extern "C" int gmg_solver_destroy(gmg_solver *s)
+{
+    if (!s) return GMG_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (auto &L : s->lv) freeLevel(L);
+    cudaFree(s->coarseIdx); cudaFree(s->coarseInv);
+    cudaFree(s->pcgR); cudaFree(s->pcgP); cudaFree(s->pcgZ); cudaFree(s->pcgT); cudaFree(s->pcgX); cudaFree(s->pcgB);
+    delete s;
+    return GMG_OK;
+}
+
+extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], const double *w0, const double *w1, const double *w2,
+				 int mgLevels, const gmg_solver_options *optIn, gmg_solver **out)
+{
+    if (!ctx || !labels || !res || !w0 || !w1 || !w2 || !out) return invalid("gmg_solver_create: null argument");
+    if (mgLevels < 1) return invalid("gmg_solver_create: mgLevels must be >= 1");
+    for (int a = 0; a < 3; ++a)
+    {
+	if (res[a] % 2) return invalid("gmg_solver_create: resolution must be even (MG.cpp:155-157)");
+	if (int(std::log2(double(res[a]))) + 1 < mgLevels) return invalid("gmg_solver_create: too many levels for this resolution (MG.cpp:159-161)");
+	if ((res[a] >> (mgLevels - 1)) << (mgLevels - 1) != res[a]) return invalid("gmg_solver_create: resolution not divisible by 2^(levels-1)");
+    }
+    GMG_CUDA(cudaSetDevice(ctx->device));
+    const double tStart = nowMs();
+    gmg_solver *s = new gmg_solver;
+    s->ctx = ctx;
+    if (optIn) s->opt = *optIn;
+    else gmg_solver_default_options(&s->opt);
+    if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
+    if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
+    if (s->opt.use_gauss_seidel)
+    {
+	delete s;
+	return invalid("gmg_solver_create: the tiled Gauss-Seidel smoother is not built in this revision; pass use_gauss_seidel = 0");
+    }
+    auto fail = [&](int st) { gmg_solver_destroy(s); return st; };
+
+    int64_t lo[3], hi[3];
+    int st = boundsFromHintOrScan(labels, res, s->opt.box_lo, s->opt.box_hi, lo, hi);
+    if (st != GMG_OK) return fail(st);
+
+    s->lv.resize(mgLevels);
+    s->levels = mgLevels;
+    double *dW[3] = {nullptr, nullptr, nullptr};
+    {
+	Level &L0 = s->lv[0];
+	makeGeom(L0.g, res, lo, hi);
+	if (L0.g.total >= (int64_t(1) << 31)) return fail(invalid("gmg_solver_create: cropped box exceeds 2^31 cells"));
+	if ((st = (cudaMalloc(&L0.labels, L0.g.total) == cudaSuccess ? GMG_OK : GMG_ERR_CUDA)) != GMG_OK) return fail(st);
+	if ((st = uploadLabels(ctx, L0.labels, labels, res, L0.g)) != GMG_OK) return fail(st);
+	if ((st = uploadWeights(ctx, dW, w0, w1, w2, res, L0.g)) != GMG_OK) return fail(st);
+    }
+    // coarse labels (MG.cpp:238-253) with the reference's level cap: a level without active cells drops it AND the one before
+    int64_t clo[3] = {lo[0], lo[1], lo[2]}, chi[3] = {hi[0], hi[1], hi[2]};
+    for (int level = 0; level < s->levels; ++level)
+    {
+	Level &L = s->lv[level];
+	if (level > 0)
+	{
+	    Level &F = s->lv[level - 1];
+	    int64_t nlo[3], nhi[3];
+	    coarseGeomOf(L.g, F.shift, F.g, clo, chi, nlo, nhi);
+	    for (int a = 0; a < 3; ++a) { clo[a] = nlo[a]; chi[a] = nhi[a]; }
+	    if (cudaMalloc(&L.labels, L.g.total) != cudaSuccess) return fail(GMG_ERR_CUDA);
+	    if ((st = coarsenOnDevice(ctx, L.labels, L.g, F.labels, F.g, F.shift)) != GMG_OK) return fail(st);
+	}
+	int64_t nI = 0, nB = 0;
+	if ((st = countLabels(ctx, L.labels, L.g.total, &nI, &nB)) != GMG_OK) return fail(st);
+	L.nInterior = nI;
+	L.nActive = nI + nB;
+	if (L.nActive == 0)
+	{
+	    if (level == 0) { setError("no INTERIOR/BOUNDARY cell at level 0"); return fail(GMG_ERR_NO_ACTIVE); }
+	    const int newLevels = level - 1; // MG.cpp:245
+	    for (int l = std::max(newLevels, 0); l < int(s->lv.size()); ++l) freeLevel(s->lv[l]);
+	    s->levels = newLevels;
+	    s->lv.resize(std::max(newLevels, 0));
+	    break;
+	}
+    }
+    if (s->levels < 1)
+    {
+	setError("level cap (MG.cpp:243-248) left no level: level 1 has no active cell");
+	for (int a = 0; a < 3; ++a) cudaFree(dW[a]);
+	return fail(GMG_ERR_NO_ACTIVE);
+    }
+    // bands (MG.cpp:279-281), coefficient records, chunk lists, grids
+    int maxGrid = 0;
+    for (int level = 0; level < s->levels; ++level)
+    {
+	Level &L = s->lv[level];
+	if ((st = buildBand(ctx, L, s->opt.boundary_width)) != GMG_OK) return fail(st);
+	if ((st = buildCoefs(ctx, L, level == 0 ? dW[0] : nullptr, level == 0 ? dW[1] : nullptr, level == 0 ? dW[2] : nullptr)) != GMG_OK) return fail(st);
+	if ((st = buildChunks(ctx, L)) != GMG_OK) return fail(st);
+	maxGrid = std::max(maxGrid, L.nChunksActive + int(divUp(L.nBoundary, BLOCK)) + 1);
+	if ((st = allocZero(&L.xAlt, L.g.total)) != GMG_OK) return fail(st);
+	if ((st = allocZero(&L.r, L.g.total)) != GMG_OK) return fail(st);
+	if (level > 0)
+	{
+	    if ((st = allocZero(&L.x, L.g.total)) != GMG_OK) return fail(st);
+	    if ((st = allocZero(&L.b, L.g.total)) != GMG_OK) return fail(st);
+	}
+    }
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int a = 0; a < 3; ++a) cudaFree(dW[a]);
+    if ((st = ensureScratch(ctx, maxGrid)) != GMG_OK) return fail(st);
+    if ((st = buildCoarseSolve(s)) != GMG_OK) return fail(st);
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->setupMs = nowMs() - tStart;
+    *out = s;
+    return GMG_OK;
+}
+
+extern "C" int gmg_solver_levels(gmg_solver *s, int *levels)
+{
+    if (!s || !levels) return invalid("null argument");
+    *levels = s->levels;
+    return GMG_OK;
+}
+extern "C" int gmg_solver_level_res(gmg_solver *s, int level, int64_t res[3])
+{
+    if (!s || level < 0 || level >= s->levels) return invalid("level out of range");
+    for (int a = 0; a < 3; ++a) res[a] = s->lv[level].g.res[a];
+    return GMG_OK;
+}
+extern "C" int gmg_solver_get_labels(gmg_solver *s, int level, int32_t *out)
+{
+    if (!s || !out || level < 0 || level >= s->levels) return invalid("level out of range");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return downloadLabels(s->ctx, out, s->lv[level].labels, s->lv[level].g.res, s->lv[level].g, true);
+}
+extern "C" int gmg_solver_get_boundary_cells(gmg_solver *s, int level, int64_t *xyz, int64_t *count)
+{
+    if (!s || !count || level < 0 || level >= s->levels) return invalid("level out of range");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    *count = s->lv[level].nBand;
+    if (xyz) return exportBand(s->ctx, s->lv[level], xyz);
+    return GMG_OK;
+}
+extern "C" int gmg_solver_active_cells(gmg_solver *s, int level, int64_t *count)
+{
+    if (!s || !count || level < 0 || level >= s->levels) return invalid("level out of range");
+    *count = s->lv[level].nActive;
+    return GMG_OK;
+}
+extern "C" int gmg_solver_coarse_unknowns(gmg_solver *s, int64_t *count)
+{
+    if (!s || !count) return invalid("null argument");
+    *count = s->nCoarse;
+    return GMG_OK;
+}
+extern "C" int gmg_solver_setup_ms(gmg_solver *s, double *ms)
+{
+    if (!s || !ms) return invalid("null argument");
+    *ms = s->setupMs;
+    return GMG_OK;
+}
+
+// ====================================================================================================
+// operator launches
+// ====================================================================================================
+static StencilArgs stencilArgs(gmg_solver *s, int level, const double *in, const double *b, double *out)
+{
+    const Level &L = s->lv[level];
+    StencilArgs a;
+    a.labels = L.labels;
+    a.in = in;
+    a.b = b;
+    a.out = out;
+    a.chunks = L.chunksInterior;
+    a.nChunks = L.nChunksInterior;
+    a.chunksPerPlane = L.g.chunksPerPlane;
+    a.pitch = L.g.pitch;
+    a.plane = L.g.plane;
+    a.nz = L.g.n[2];
+    a.nBoundary = L.nBoundary;
+    a.bandIdx = L.bandIdx;
+    a.bcoef = L.bcoef;
+    a.partials = s->ctx->partials;
+    a.ticket = s->ctx->ticket;
+    a.result = nullptr;
+    return a;
+}
+
+static int launchStencil(gmg_solver *s, int level, int mode, const double *in, const double *b, double *out, double *dotResult)
+{
+    const Level &L = s->lv[level];
+    StencilArgs a = stencilArgs(s, level, in, b, out);
+    a.result = dotResult;
+    const unsigned grid = unsigned(L.nChunksInterior + divUp(L.nBoundary, BLOCK));
+    if (grid == 0) return GMG_OK;
+    cudaStream_t st = s->ctx->stream;
+    const double n = double(L.nActive);
+    if (mode == SM_JACOBI)
+    {
+	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 25.0);
+	k_stencil<SM_JACOBI, false><<<grid, BLOCK, 0, st>>>(a);
+    }
+    else if (mode == SM_RESIDUAL)
+    {
+	GMG_LAUNCH(s->ctx, KC_RESIDUAL, n * 25.0);
+	k_stencil<SM_RESIDUAL, false><<<grid, BLOCK, 0, st>>>(a);
+    }
+    else if (dotResult)
+    {
+	GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
+	k_stencil<SM_APPLY, true><<<grid, BLOCK, 0, st>>>(a);
+    }
+    else
+    {
+	GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
+	k_stencil<SM_APPLY, false><<<grid, BLOCK, 0, st>>>(a);
+    }
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+// `sweeps` boundary-band Jacobi sweeps on grid x (Ops.h:524-619); zeroGrid: x is known to be all zero
+static int launchBand(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid)
+{
+    const Level &L = s->lv[level];
+    if (L.nBand == 0 || sweeps <= 0) return GMG_OK;
+    BandArgs a;
+    a.x = x;
+    a.b = b;
+    a.bandIdx = L.bandIdx;
+    a.bandNbr = L.bandNbr;
+    a.bcoef = L.bcoef;
+    a.bandB = L.bandB;
+    a.nBoundary = L.nBoundary;
+    a.nBand = L.nBand;
+    a.pitch = L.g.pitch;
+    a.plane = L.g.plane;
+    const unsigned grid = unsigned(divUp(L.nBand, BLOCK));
+    cudaStream_t st = s->ctx->stream;
+    const double bytes = double(L.nBand) * 29.0;
+    double *cur = L.bandV0, *nxt = L.bandV1;
+    // sweep 1: grid -> compact
+    a.vin = nullptr;
+    a.vout = cur;
+    {
+	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
+	if (zeroGrid) k_band<false, false, true, true><<<grid, BLOCK, 0, st>>>(a);
+	else k_band<false, false, true, false><<<grid, BLOCK, 0, st>>>(a);
+    }
+    if (sweeps == 1)
+    {
+	GMG_LAUNCH(s->ctx, KC_BAND, double(L.nBand) * 20.0);
+	k_band_scatter<<<grid, BLOCK, 0, st>>>(x, L.bandIdx, cur, L.nBand);
+    }
+    for (int sw = 2; sw <= sweeps; ++sw)
+    {
+	a.vin = cur;
+	a.vout = nxt;
+	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
+	if (sw == sweeps) k_band<true, true, false, false><<<grid, BLOCK, 0, st>>>(a);
+	else k_band<true, false, false, false><<<grid, BLOCK, 0, st>>>(a);
+	std::swap(cur, nxt);
+    }
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+static TransferArgs transferArgs(gmg_solver *s, int fineLevel)
+{
+    const Level &F = s->lv[fineLevel], &C = s->lv[fineLevel + 1];
+    TransferArgs a;
+    a.fineLabels = F.labels;
+    a.coarseLabels = C.labels;
+    a.finePitch = F.g.pitch;
+    a.coarsePitch = C.g.pitch;
+    a.finePlane = F.g.plane;
+    a.coarsePlane = C.g.plane;
+    a.fineNz = F.g.n[2];
+    a.coarseNz = C.g.n[2];
+    a.coarseNy = C.g.n[1];
+    for (int k = 0; k < 3; ++k) a.shift[k] = F.shift[k];
+    a.fine = nullptr; a.coarse = nullptr; a.out = nullptr; a.chunks = nullptr; a.chunksPerPlane = 0;
+    return a;
+}
+
+static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const double *fine)
+{
+    const Level &C = s->lv[fineLevel + 1];
+    if (C.nChunksActive == 0) return GMG_OK;
+    TransferArgs a = transferArgs(s, fineLevel);
+    a.fine = fine;
+    a.out = coarse;
+    a.chunks = C.chunksActive;
+    a.chunksPerPlane = C.g.chunksPerPlane;
+    GMG_LAUNCH(s->ctx, KC_RESTRICT, double(s->lv[fineLevel].nActive) * 8.0 + double(C.nActive) * 9.0);
+    k_restrict<<<C.nChunksActive, BLOCK, 0, s->ctx->stream>>>(a);
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const double *coarse)
+{
+    const Level &F = s->lv[fineLevel];
+    if (F.nChunksActive == 0) return GMG_OK;
+    TransferArgs a = transferArgs(s, fineLevel);
+    a.coarse = coarse;
+    a.out = fine;
+    a.chunks = F.chunksActive;
+    a.chunksPerPlane = F.g.chunksPerPlane;
+    GMG_LAUNCH(s->ctx, KC_PROLONG, double(F.nActive) * 17.0 + double(s->lv[fineLevel + 1].nActive) * 8.0);
+    k_prolong<<<F.nChunksActive, BLOCK, 0, s->ctx->stream>>>(a);
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+static int launchZero(gmg_solver *s, int level, double *x)
+{
+    const Level &L = s->lv[level];
+    if (L.nChunksActive == 0) return GMG_OK;
+    GMG_LAUNCH(s->ctx, KC_ZERO, double(L.nActive) * 8.0);
+    k_zero<<<L.nChunksActive, BLOCK, 0, s->ctx->stream>>>(x, L.chunksActive, L.g.chunksPerPlane, L.g.plane, L.g.n[2]);
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+static int launchCoarse(gmg_solver *s, double *x, const double *b)
+{
+    const int n = s->nCoarse;
+    GMG_LAUNCH(s->ctx, KC_COARSE, double(n) * n * 8.0);
+    k_coarse_solve<<<unsigned(divUp(n, BLOCK / 32)), BLOCK, sizeof(double) * n, s->ctx->stream>>>(x, b, s->coarseIdx, s->coarseInv, n);
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+template <int OP>
+static int launchVec(gmg_solver *s, int level, double *y, const double *a, const double *c, double *y2, double sc, double *result, int klass,
+		     double bytesPerCell)
+{
+    const Level &L = s->lv[level];
+    if (L.nChunksActive == 0) return GMG_OK;
+    VecArgs v;
+    v.chunks = L.chunksActive;
+    v.chunksPerPlane = L.g.chunksPerPlane;
+    v.plane = L.g.plane;
+    v.nz = L.g.n[2];
+    v.y = y;
+    v.a = a;
+    v.c = c;
+    v.y2 = y2;
+    v.s = sc;
+    v.sc = reinterpret_cast<const Scalars *>(s->ctx->scalars);
+    v.partials = s->ctx->partials;
+    v.ticket = s->ctx->ticket;
+    v.result = result;
+    GMG_LAUNCH(s->ctx, klass, double(L.nActive) * bytesPerCell);
+    k_vec<OP><<<L.nChunksActive, BLOCK, 0, s->ctx->stream>>>(v);
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+static double *scalarPtr(gmg_solver *s, size_t offset) { return reinterpret_cast<double *>(reinterpret_cast<char *>(s->ctx->scalars) + offset); }
+
+static int readScalar(gmg_solver *s, size_t offset, double *out)
+{
+    GMG_CUDA(cudaMemcpyAsync(s->ctx->hostScalars, scalarPtr(s, offset), sizeof(double), cudaMemcpyDeviceToHost, s->ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    *out = *s->ctx->hostScalars;
+    return GMG_OK;
+}
+
+// ====================================================================================================
+// V-cycle (MG.cpp:420-881)
+// ====================================================================================================
+static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, const double *b, bool zeroGrid)
+{
+    const int it = s->opt.boundary_iterations;
+    GMG_TRY(launchBand(s, level, cur, b, it, zeroGrid));
+    GMG_TRY(launchStencil(s, level, SM_JACOBI, cur, b, alt, nullptr));
+    std::swap(cur, alt);
+    GMG_TRY(launchBand(s, level, cur, b, it, false));
+    return GMG_OK;
+}
+
+static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useInitialGuess)
+{
+    const int nl = s->levels;
+    // level 0 works on the caller's grid and the level's alternate; two Jacobi sweeps per level bring the
+    // result back into the caller's buffer (one sweep only when there is a single level)
+    double *cur0 = x, *alt0 = s->lv[0].xAlt;
+    if (!useInitialGuess) GMG_TRY(launchZero(s, 0, cur0));
+    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, !useInitialGuess));
+    if (nl == 1)
+    {
+	GMG_TRY((launchVec<VO_COPY>(s, 0, x, cur0, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
+	return GMG_OK;
+    }
+    GMG_TRY(launchStencil(s, 0, SM_RESIDUAL, cur0, b, s->lv[0].r, nullptr));
+    GMG_TRY(launchRestrict(s, 0, s->lv[1].b, s->lv[0].r));
+    std::vector<double *> cur(nl), alt(nl);
+    for (int level = 1; level < nl - 1; ++level)
+    {
+	Level &L = s->lv[level];
+	cur[level] = L.x;
+	alt[level] = L.xAlt;
+	GMG_TRY(launchZero(s, level, cur[level]));
+	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, true));
+	GMG_TRY(launchStencil(s, level, SM_RESIDUAL, cur[level], L.b, L.r, nullptr));
+	GMG_TRY(launchRestrict(s, level, s->lv[level + 1].b, L.r));
+    }
+    GMG_TRY(launchCoarse(s, s->lv[nl - 1].x, s->lv[nl - 1].b));
+    for (int level = nl - 2; level >= 1; --level)
+    {
+	Level &L = s->lv[level];
+	GMG_TRY(launchProlong(s, level, cur[level], level + 1 == nl - 1 ? s->lv[nl - 1].x : cur[level + 1]));
+	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, false));
+    }
+    GMG_TRY(launchProlong(s, 0, cur0, nl == 2 ? s->lv[1].x : cur[1]));
+    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, false));
+    // cur0 == x again after the second swap
+    if (cur0 != x) GMG_TRY((launchVec<VO_COPY>(s, 0, x, cur0, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
+    return GMG_OK;
+}
+
+// ====================================================================================================
+// PCG (CG.h:11-207)
+// ====================================================================================================
+__global__ void k_shift_rho(Scalars *sc) { sc->rho = sc->rhoNew; }
+
+static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int precond, int *iterations, double *hist, int histCap,
+		     int *histCount)
+{
+    gmg_ctx *ctx = s->ctx;
+    const int64_t total = s->lv[0].g.total;
+    if (!s->pcgR)
+    {
+	GMG_TRY(allocZero(&s->pcgR, total));
+	GMG_TRY(allocZero(&s->pcgP, total));
+	GMG_TRY(allocZero(&s->pcgZ, total));
+	GMG_TRY(allocZero(&s->pcgT, total));
+    }
+    double *r = s->pcgR, *p = s->pcgP, *z = s->pcgZ, *t = s->pcgT;
+    if (histCount) *histCount = 0;
+    if (iterations) *iterations = -1;
+    double bb = 0, rr = 0;
+    GMG_TRY((launchVec<VO_NORM2>(s, 0, const_cast<double *>(b), nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, bb)), KC_REDUCE, 8.0)));
+    GMG_TRY(readScalar(s, offsetof(Scalars, bb), &bb));
+    if (bb == 0) return GMG_OK; // "RHS is zero. Nothing to solve" (CG.h:35-40)
+    // r = b - A x (CG.h:50-51)
+    GMG_TRY(launchStencil(s, 0, SM_RESIDUAL, x, b, r, nullptr));
+    GMG_TRY((launchVec<VO_NORM2>(s, 0, r, nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, rr)), KC_REDUCE, 8.0)));
+    GMG_TRY(readScalar(s, offsetof(Scalars, rr), &rr));
+    const double threshold = tol * tol * bb;
+    if (rr < threshold) return GMG_OK; // CG.h:60-64
+    // p = M^-1 r ; rho = p.r (CG.h:66-87)
+    if (precond) GMG_TRY(vcycleDevice(s, p, r, false));
+    else GMG_TRY((launchVec<VO_COPY>(s, 0, p, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
+    GMG_TRY((launchVec<VO_DOT>(s, 0, p, r, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, rho)), KC_REDUCE, 16.0)));
+    int iteration = 0;
+    for (; iteration < maxIt; ++iteration)
+    {
+	// t = A p fused with p.t (CG.h:104-126)
+	GMG_TRY(launchStencil(s, 0, SM_APPLY, p, nullptr, t, scalarPtr(s, offsetof(Scalars, pAp))));
+	// x += alpha p ; r -= alpha t ; |r|^2 (CG.h:128-157)
+	GMG_TRY((launchVec<VO_CG_UPDATE>(s, 0, x, p, t, r, 0, scalarPtr(s, offsetof(Scalars, rr)), KC_BLAS1, 48.0)));
+	GMG_TRY(readScalar(s, offsetof(Scalars, rr), &rr));
+	if (hist && histCount && *histCount < histCap) hist[(*histCount)++] = std::sqrt(rr / bb);
+	if (rr < threshold) break;
+	// z = M^-1 r ; beta = z.r / rho ; p = z + beta p (CG.h:164-195)
+	if (precond) GMG_TRY(vcycleDevice(s, z, r, false));
+	else GMG_TRY((launchVec<VO_COPY>(s, 0, z, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
+	GMG_TRY((launchVec<VO_DOT>(s, 0, z, r, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, rhoNew)), KC_REDUCE, 16.0)));
+	GMG_TRY((launchVec<VO_CG_DIRECTION>(s, 0, p, z, nullptr, nullptr, 0, nullptr, KC_BLAS1, 24.0)));
+	{
+	    GMG_LAUNCH(ctx, KC_BLAS1, 0);
+	    k_shift_rho<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<Scalars *>(ctx->scalars));
+	}
+    }
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (iterations) *iterations = iteration;
+    return GMG_OK;
+}
+
+// ====================================================================================================
+// grids and the public operator entry points
+// ====================================================================================================
+extern "C" int gmg_grid_create(gmg_solver *s, int level, gmg_grid **out)
+{
+    if (!s || !out || level < 0 || level >= s->levels) return invalid("gmg_grid_create: bad argument");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    gmg_grid *g = new gmg_grid;
+    g->solver = s;
+    g->level = level;
+    int st = allocZero(&g->d, s->lv[level].g.total);
+    if (st != GMG_OK) { delete g; return st; }
+    *out = g;
+    return GMG_OK;
+}
+extern "C" int gmg_grid_destroy(gmg_grid *g)
+{
+    if (!g) return GMG_OK;
+    cudaStreamSynchronize(g->solver->ctx->stream);
+    cudaFree(g->d);
+    delete g;
+    return GMG_OK;
+}
+extern "C" int gmg_grid_upload(gmg_grid *g, const double *host)
+{
+    if (!g || !host) return invalid("null argument");
+    GMG_CUDA(cudaSetDevice(g->solver->ctx->device));
+    const Geom &ge = g->solver->lv[g->level].g;
+    return uploadValues(g->solver->ctx, g->d, host, ge.res, ge, g->solver->lv[g->level].labels);
+}
+extern "C" int gmg_grid_download(gmg_grid *g, double *host)
+{
+    if (!g || !host) return invalid("null argument");
+    GMG_CUDA(cudaSetDevice(g->solver->ctx->device));
+    const Geom &ge = g->solver->lv[g->level].g;
+    return downloadValues(g->solver->ctx, host, g->d, ge.res, ge, true);
+}
+extern "C" int gmg_grid_zero(gmg_grid *g)
+{
+    if (!g) return invalid("null argument");
+    GMG_CUDA(cudaMemsetAsync(g->d, 0, sizeof(double) * g->solver->lv[g->level].g.total, g->solver->ctx->stream));
+    return GMG_OK;
+}
+extern "C" int gmg_grid_copy(gmg_grid *dst, const gmg_grid *src)
+{
+    if (!dst || !src || dst->level != src->level || dst->solver != src->solver) return invalid("gmg_grid_copy: grids differ in level");
+    GMG_CUDA(cudaMemcpyAsync(dst->d, src->d, sizeof(double) * dst->solver->lv[dst->level].g.total, cudaMemcpyDeviceToDevice, dst->solver->ctx->stream));
+    return GMG_OK;
+}
+
+#define CHECK_GRIDS2(s, a, b)                                                                  \
+    if (!(s) || !(a) || !(b) || (a)->solver != (s) || (b)->solver != (s) || (a)->level != (b)->level) \
+    return invalid("grid arguments must belong to this solver and share a level")
+
+extern "C" int gmg_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b)
+{
+    CHECK_GRIDS2(s, x, b);
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    Level &L = s->lv[x->level];
+    GMG_TRY(launchStencil(s, x->level, SM_JACOBI, x->d, b->d, L.xAlt, nullptr));
+    std::swap(x->d, L.xAlt); // the out-of-place result becomes the caller's grid
+    return GMG_OK;
+}
+extern "C" int gmg_boundary_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int sweeps)
+{
+    CHECK_GRIDS2(s, x, b);
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return launchBand(s, x->level, x->d, b->d, sweeps, false);
+}
+extern "C" int gmg_apply(gmg_solver *s, gmg_grid *dst, const gmg_grid *src)
+{
+    CHECK_GRIDS2(s, dst, src);
+    if (dst == src) return invalid("gmg_apply: dst must differ from src");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return launchStencil(s, dst->level, SM_APPLY, src->d, nullptr, dst->d, nullptr);
+}
+extern "C" int gmg_residual(gmg_solver *s, gmg_grid *r, const gmg_grid *x, const gmg_grid *b)
+{
+    CHECK_GRIDS2(s, r, x);
+    CHECK_GRIDS2(s, r, b);
+    if (r == x) return invalid("gmg_residual: r must differ from x");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return launchStencil(s, r->level, SM_RESIDUAL, x->d, b->d, r->d, nullptr);
+}
+extern "C" int gmg_restrict(gmg_solver *s, gmg_grid *coarse, const gmg_grid *fine)
+{
+    if (!s || !coarse || !fine || coarse->solver != s || fine->solver != s || coarse->level != fine->level + 1)
+	return invalid("gmg_restrict: coarse must be one level above fine");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return launchRestrict(s, fine->level, coarse->d, fine->d);
+}
+extern "C" int gmg_prolong_add(gmg_solver *s, gmg_grid *fine, const gmg_grid *coarse)
+{
+    if (!s || !coarse || !fine || coarse->solver != s || fine->solver != s || coarse->level != fine->level + 1)
+	return invalid("gmg_prolong_add: coarse must be one level above fine");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return launchProlong(s, fine->level, fine->d, coarse->d);
+}
+extern "C" int gmg_dot(gmg_solver *s, const gmg_grid *a, const gmg_grid *b, double *out)
+{
+    CHECK_GRIDS2(s, a, b);
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_TRY((launchVec<VO_DOT>(s, a->level, a->d, b->d, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, tmp)), KC_REDUCE, 16.0)));
+    return readScalar(s, offsetof(Scalars, tmp), out);
+}
+extern "C" int gmg_norm2(gmg_solver *s, const gmg_grid *a, double *out)
+{
+    CHECK_GRIDS2(s, a, a);
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_TRY((launchVec<VO_NORM2>(s, a->level, a->d, nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, tmp)), KC_REDUCE, 8.0)));
+    return readScalar(s, offsetof(Scalars, tmp), out);
+}
+extern "C" int gmg_inf_norm(gmg_solver *s, const gmg_grid *a, double *out)
+{
+    CHECK_GRIDS2(s, a, a);
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_TRY((launchVec<VO_MAX>(s, a->level, a->d, nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, tmp)), KC_REDUCE, 8.0)));
+    return readScalar(s, offsetof(Scalars, tmp), out);
+}
+extern "C" int gmg_axpy(gmg_solver *s, gmg_grid *dst, const gmg_grid *src, double scale)
+{
+    CHECK_GRIDS2(s, dst, src);
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return launchVec<VO_AXPY>(s, dst->level, dst->d, src->d, nullptr, nullptr, scale, nullptr, KC_BLAS1, 24.0);
+}
+extern "C" int gmg_add_scaled(gmg_solver *s, gmg_grid *dst, const gmg_grid *a, const gmg_grid *v, double scale)
+{
+    CHECK_GRIDS2(s, dst, a);
+    CHECK_GRIDS2(s, dst, v);
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return launchVec<VO_ADD_SCALED>(s, dst->level, dst->d, a->d, v->d, nullptr, scale, nullptr, KC_BLAS1, 24.0);
+}
+extern "C" int gmg_scale(gmg_solver *s, gmg_grid *v, double scale)
+{
+    CHECK_GRIDS2(s, v, v);
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return launchVec<VO_SCALE>(s, v->level, v->d, nullptr, nullptr, nullptr, scale, nullptr, KC_BLAS1, 16.0);
+}
+
+extern "C" int gmg_vcycle_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int useInitialGuess)
+{
+    CHECK_GRIDS2(s, x, b);
+    if (x->level != 0) return invalid("gmg_vcycle_device: grids must be level 0");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return vcycleDevice(s, x->d, b->d, useInitialGuess != 0);
+}
+extern "C" int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, double tol, int maxIt, int preconditioner, int *iterations,
+			      double *relResHistory, int histCap, int *histCount)
+{
+    CHECK_GRIDS2(s, x, b);
+    if (x->level != 0) return invalid("gmg_pcg_device: grids must be level 0");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    return pcgDevice(s, x->d, b->d, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount);
+}
+
+static int ensureHostIO(gmg_solver *s)
+{
+    if (s->pcgX) return GMG_OK;
+    GMG_TRY(allocZero(&s->pcgX, s->lv[0].g.total));
+    GMG_TRY(allocZero(&s->pcgB, s->lv[0].g.total));
+    return GMG_OK;
+}
+
+extern "C" int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInitialGuess)
+{
+    if (!s || !x || !b) return invalid("gmg_vcycle: null argument");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_TRY(ensureHostIO(s));
+    const Geom &g = s->lv[0].g;
+    if (useInitialGuess) GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels));
+    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels));
+    GMG_TRY(vcycleDevice(s, s->pcgX, s->pcgB, useInitialGuess != 0));
+    // cells outside the stored box are non-active: the reference leaves them untouched (0 after constant(0))
+    return downloadValues(s->ctx, x, s->pcgX, g.res, g, !useInitialGuess);
+}
+
+extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations, double *relResHistory,
+		       int histCap, int *histCount)
+{
+    if (!s || !x || !b) return invalid("gmg_pcg: null argument");
+    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_TRY(ensureHostIO(s));
+    const Geom &g = s->lv[0].g;
+    GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels));
+    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels));
+    GMG_TRY(pcgDevice(s, s->pcgX, s->pcgB, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount));
+    return downloadValues(s->ctx, x, s->pcgX, g.res, g, false);
+}

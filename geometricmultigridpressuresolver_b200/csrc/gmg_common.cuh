@@ -1,0 +1,168 @@
+// gmg_common.cuh -- shared declarations of the B200 (sm_100a) MGPCG library.
+//
+// Data layout in HBM:
+//   * every level stores only the cropped box of non-EXTERIOR cells plus a >=2-cell halo, as a dense
+//     x-fastest array with a 128-byte aligned row pitch; expanded coordinates stay virtual.
+//   * storage origins are even on every axis, so the two x-children of a coarse cell form an aligned
+//     double2 and fine/coarse storage indices are related by cs = (fs >> 1) + shift.
+//   * values are fp64 (the reference is fp64 end to end), labels are one byte.
+//   * vector grids are exactly 0 on non-active cells; kernels only write active cells.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gmg_b200.h"
+
+namespace gmg
+{
+constexpr int L_INTERIOR = GMG_INTERIOR_CELL;
+constexpr int L_EXTERIOR = GMG_EXTERIOR_CELL;
+constexpr int L_DIRICHLET = GMG_DIRICHLET_CELL;
+constexpr int L_BOUNDARY = GMG_BOUNDARY_CELL;
+
+constexpr int BLOCK = 256;          // threads per CTA for every grid kernel
+constexpr int CHUNK_CELLS = 512;    // cells of one z-plane a CTA covers (BLOCK threads x double2)
+constexpr int CHUNK_Z = 4;          // z-planes a CTA walks
+constexpr int MAX_COARSE = 4096;    // dense coarse-solve limit (unknowns)
+
+// kernel classes for profiling / roofline accounting
+enum KClass
+{
+    KC_JACOBI = 0,
+    KC_APPLY,
+    KC_RESIDUAL,
+    KC_BAND,
+    KC_RESTRICT,
+    KC_PROLONG,
+    KC_COARSE,
+    KC_BLAS1,
+    KC_REDUCE,
+    KC_ZERO,
+    KC_SETUP,
+    KC_HALO,
+    KC_COUNT
+};
+
+struct Geom
+{
+    int64_t res[3];  // expanded (virtual) resolution of this level
+    int org[3];      // expanded coordinate of storage cell (0,0,0); even
+    int n[3];        // storage extents
+    int pitch;       // x pitch in elements (multiple of 16)
+    int64_t plane;   // pitch * n[1]
+    int64_t total;   // plane * n[2]
+    int chunksPerPlane;
+    int zBlocks;
+};
+
+struct Level
+{
+    Geom g;
+    uint8_t *labels = nullptr;
+    int64_t nActive = 0, nInterior = 0;
+    // boundary band: [0,nBoundary) BOUNDARY cells, [nBoundary,nBand) INTERIOR cells of the band; linear order inside each part
+    int nBoundary = 0, nBand = 0;
+    int32_t *bandIdx = nullptr;  // [nBand] storage index
+    int32_t *bandNbr = nullptr;  // [6][nBand] band position of the neighbour, -1 if not in the band
+    double *bcoef = nullptr;     // [7][nBoundary]: coefficient on each of the 6 neighbours, then the diagonal
+    double *bandV0 = nullptr, *bandV1 = nullptr, *bandB = nullptr;
+    // CTAs of the full-grid kernels: chunks holding at least one INTERIOR cell / one active cell
+    int nChunksInterior = 0, nChunksActive = 0;
+    int32_t *chunksInterior = nullptr, *chunksActive = nullptr;
+    // V-cycle grids (level 0 uses caller grids for x and b)
+    double *x = nullptr, *xAlt = nullptr, *b = nullptr, *r = nullptr;
+    int shift[3] = {0, 0, 0};    // coarse storage = (this level's storage >> 1) + shift   (to level+1)
+};
+
+struct ProfileRec
+{
+    int klass;
+    double bytes;
+    cudaEvent_t e0, e1;
+};
+
+} // namespace gmg
+
+struct gmg_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<gmg::ProfileRec> recs;
+    std::vector<cudaEvent_t> eventPool;
+    double classMs[gmg::KC_COUNT] = {0};
+    int64_t classLaunches[gmg::KC_COUNT] = {0};
+    double classBytes[gmg::KC_COUNT] = {0};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int smCount = 148;
+    // sharding (z-slabs); world == 1 means single GPU
+    int rank = 0, world = 1;
+    void *nccl = nullptr;
+    // reduction scratch
+    double *partials = nullptr;   // [maxPartials]
+    unsigned *ticket = nullptr;
+    double *scalars = nullptr;    // device scalars (see Scalars)
+    double *hostScalars = nullptr; // pinned mirror
+    int maxPartials = 0;
+};
+
+struct gmg_solver
+{
+    gmg_ctx *ctx = nullptr;
+    gmg_solver_options opt;
+    int levels = 0;
+    std::vector<gmg::Level> lv;
+    // coarsest direct solve
+    int nCoarse = 0;
+    int32_t *coarseIdx = nullptr; // [nCoarse] storage index at the coarsest level
+    double *coarseInv = nullptr;  // [nCoarse][nCoarse] row-major inverse
+    // PCG work grids (level 0)
+    double *pcgR = nullptr, *pcgP = nullptr, *pcgZ = nullptr, *pcgT = nullptr, *pcgX = nullptr, *pcgB = nullptr;
+    double setupMs = 0;
+};
+
+struct gmg_grid
+{
+    gmg_solver *solver = nullptr;
+    int level = 0;
+    double *d = nullptr;
+};
+
+namespace gmg
+{
+void setError(const std::string &msg);
+int cudaFail(cudaError_t e, const char *what, const char *file, int line);
+
+#define GMG_CUDA(call)                                                           \
+    do                                                                           \
+    {                                                                            \
+	cudaError_t _e = (call);                                                 \
+	if (_e != cudaSuccess) return gmg::cudaFail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define GMG_TRY(call)                    \
+    do                                   \
+    {                                    \
+	int _s = (call);                 \
+	if (_s != GMG_OK) return _s;     \
+    } while (0)
+
+// profiling bracket around one kernel launch
+struct LaunchScope
+{
+    gmg_ctx *ctx;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int klass;
+    double bytes;
+    LaunchScope(gmg_ctx *c, int k, double b);
+    ~LaunchScope();
+};
+#define GMG_LAUNCH(ctx, klass, bytes) gmg::LaunchScope _scope_##__LINE__(ctx, klass, bytes)
+
+} // namespace gmg

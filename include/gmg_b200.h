@@ -1,0 +1,177 @@
+/* gmg_b200.h -- C ABI of the B200-native multigrid-preconditioned CG pressure solve.
+ *
+ * This is the drop-in boundary for ONE path of rgoldade/GeometricMultigridPressureSolver: the
+ * McAdams-2010 MGPCG pressure solve (namespace HDK::GeometricMultigridOperators, class
+ * HDK::GeometricMultigridPoissonSolver, HDK::solveGeometricConjugateGradient).  The reference has
+ * no FFI of its own for this path -- it is plain in-process C++ called from the Houdini node
+ * (HDK_GeometricFreeSurfacePressureSolver.cpp:344-484) -- so each entry point below names the
+ * reference function it replaces; include/gmg_b200_hdk.hpp is the C++ facade with the reference's
+ * own names/signatures over these calls, and INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every function returns a gmg_status (0 = ok); there is NO CPU
+ *     fallback: without a usable CUDA device every call fails with GMG_ERR_CUDA.
+ *   - Host grids are dense, x-fastest: idx = x + res[0]*(y + res[1]*z), in the reference's
+ *     EXPANDED coordinates (the power-of-two padded grid of
+ *     HDK_GeometricMultigridOperators.h:1340-1360).  Labels are int32 with the enum of
+ *     HDK_GeometricMultigridOperators.h:11.  Values are fp64 (the reference is fp64 end to end:
+ *     HDK_GeometricMultigridPoissonSolver.h:14-15).  The face grid of axis a has res[a]+1 entries
+ *     along a; face (i,j,k) of axis 0 lies between cells (i-1,j,k) and (i,j,k).
+ *   - On the device the library stores only the cropped box of non-EXTERIOR cells (+halo) per level;
+ *     expanded coordinates stay virtual.
+ *   - A solver object is not re-entrant (like the reference's, whose scratch grids are members).
+ */
+#ifndef GMG_B200_H
+#define GMG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum gmg_status
+{
+    GMG_OK = 0,
+    GMG_ERR_CUDA = 1,        /* no device / CUDA runtime error (message via gmg_last_error) */
+    GMG_ERR_INVALID = 2,     /* bad argument (null pointer, odd resolution, level out of range ...) */
+    GMG_ERR_NO_ACTIVE = 3,   /* no INTERIOR/BOUNDARY cell at level 0 */
+    GMG_ERR_COARSE_SIZE = 4, /* coarsest level too large for the dense direct solve */
+    GMG_ERR_NOT_SPD = 5,     /* coarse matrix factorisation failed (e.g. pure-Neumann domain) */
+    GMG_ERR_COMM = 6         /* multi-GPU exchange failure */
+} gmg_status;
+
+/* HDK_GeometricMultigridOperators.h:11 */
+enum { GMG_INTERIOR_CELL = 0, GMG_EXTERIOR_CELL = 1, GMG_DIRICHLET_CELL = 2, GMG_BOUNDARY_CELL = 3 };
+
+typedef struct gmg_ctx gmg_ctx;       /* one CUDA device + stream (+ the z-slab communicator when sharded) */
+typedef struct gmg_solver gmg_solver; /* GeometricMultigridPoissonSolver */
+typedef struct gmg_grid gmg_grid;     /* device-resident fp64 vector grid of one solver level */
+
+const char *gmg_last_error(void);
+int gmg_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to
+ * let the library create its own non-blocking stream. */
+int gmg_ctx_create(int device, void *stream, gmg_ctx **out);
+int gmg_ctx_destroy(gmg_ctx *ctx);
+int gmg_ctx_synchronize(gmg_ctx *ctx);
+/* Shard the fine levels into z-slabs over `world` ranks (one process per GPU).  `nccl_unique_id` is the
+ * 128-byte ncclUniqueId made on rank 0 and handed to every rank by the caller (torch.distributed /
+ * MPI / files -- the library does not care).  Must be called before gmg_solver_create. */
+int gmg_ctx_shard(gmg_ctx *ctx, int rank, int world, const void *nccl_unique_id);
+int gmg_nccl_unique_id(void *out128);
+
+/* ---- domain builders (integer work, bit-exact) --------------------------------------------------- */
+/* HDK_GeometricMultigridOperators.h:1340-1360: level count, padding, power-of-two expanded resolution. */
+int gmg_expand_dims(const int64_t baseRes[3], int64_t expRes[3], int64_t offset[3], int *mgLevels);
+/* buildExpandedCellLabels, HDK_GeometricMultigridOperators.h:1328-1456.  out: host int32[expRes]. */
+int gmg_expand_labels(gmg_ctx *ctx, const int32_t *base, const int64_t baseRes[3], int32_t *out,
+		      const int64_t expRes[3], const int64_t offset[3]);
+/* buildExpandedBoundaryWeights, HDK_GeometricMultigridOperators.h:1458-1572.  out: host double[expRes + 1 along axis]. */
+int gmg_expand_weights(gmg_ctx *ctx, const double *baseW, const int64_t baseRes[3], double *out,
+		       const int64_t expRes[3], const int64_t offset[3], int axis);
+/* setBoundaryCellLabels, HDK_GeometricMultigridOperators.h:1574-1644.  labels rewritten in place (host).
+ * boxLo/boxHi (nullable): expanded-coordinate bounds [lo,hi) outside which every label is EXTERIOR
+ * (offset and offset+baseRes from gmg_expand_dims) -- spares a host scan. */
+int gmg_set_boundary_labels(gmg_ctx *ctx, int32_t *labels, const int64_t res[3], const double *w0,
+			    const double *w1, const double *w2, const int64_t boxLo[3], const int64_t boxHi[3]);
+/* buildCoarseCellLabels, HDK_GeometricMultigridOperators.cpp:23-163.  coarse: host int32[res/2]. */
+int gmg_coarsen_labels(gmg_ctx *ctx, const int32_t *fine, const int64_t fineRes[3], int32_t *coarse);
+/* buildBoundaryCells, HDK_GeometricMultigridOperators.cpp:165-469.  Two-call: xyz == NULL returns the count.
+ * Order = the reference's sort key (16^3-tile linear index, z, y, x). */
+int gmg_boundary_cells(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], int width, int64_t *xyz,
+		       int64_t *count);
+
+/* ---- solver ------------------------------------------------------------------------------------ */
+typedef struct gmg_solver_options
+{
+    int use_gauss_seidel;     /* 0: damped-Jacobi interior smoother (north_star); 1: tiled Gauss-Seidel (not built yet -> GMG_ERR_INVALID) */
+    int print_stats;          /* like doPrintStats: per-stage CUDA-event timings to stdout */
+    int boundary_width;       /* myBoundarySmootherWidth, default 3 (MG.cpp:141) */
+    int boundary_iterations;  /* myBoundarySmootherIterations, default 3 (MG.cpp:142) */
+    double coarse_matrix_scale; /* 1 = intended algorithm.  J reproduces the reference run with J UT_ThreadedAlgorithm jobs,
+				   whose unsplit assembly loop (MG.cpp:334-389) sums every triplet J times. */
+    int64_t box_lo[3], box_hi[3]; /* optional non-EXTERIOR bounds hint (all zero = scan the labels) */
+} gmg_solver_options;
+void gmg_solver_default_options(gmg_solver_options *opt);
+
+/* GeometricMultigridPoissonSolver::GeometricMultigridPoissonSolver, HDK_GeometricMultigridPoissonSolver.cpp:135-418.
+ * Deep-copies labels and weights to the device, builds per-level labels, boundary bands and the coarse factor. */
+int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], const double *w0, const double *w1,
+		      const double *w2, int mgLevels, const gmg_solver_options *opt, gmg_solver **out);
+int gmg_solver_destroy(gmg_solver *s);
+/* getMGLevels(), HDK_GeometricMultigridPoissonSolver.h:31 (after the level cap of MG.cpp:243-248) */
+int gmg_solver_levels(gmg_solver *s, int *levels);
+int gmg_solver_level_res(gmg_solver *s, int level, int64_t res[3]);
+/* per-level labels / boundary-band lists in expanded coordinates, for bit-exact checks */
+int gmg_solver_get_labels(gmg_solver *s, int level, int32_t *out);
+int gmg_solver_get_boundary_cells(gmg_solver *s, int level, int64_t *xyz, int64_t *count);
+int gmg_solver_active_cells(gmg_solver *s, int level, int64_t *count);
+int gmg_solver_coarse_unknowns(gmg_solver *s, int64_t *count);
+int gmg_solver_setup_ms(gmg_solver *s, double *ms);
+
+/* applyVCycle, HDK_GeometricMultigridPoissonSolver.cpp:420-881: host x (in/out), host b. */
+int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInitialGuess);
+/* solveGeometricConjugateGradient wired as HDK_GeometricFreeSurfacePressureSolver.cpp:430-483 does
+ * (A = applyPoissonMatrix with the fine weights, M^-1 = applyVCycle), HDK_GeometricCGPoissonSolver.h:11-207.
+ * x: host in/out (warm start allowed).  iterations: the index CG.h:198 prints, -1 on the two early-outs.
+ * relResHistory[k] = sqrt(|r_k|^2/|b|^2), the value CG.h:159 prints; histCount = entries written.
+ * preconditioner: 1 = multigrid V-cycle, 0 = none (plain CG). */
+int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations,
+	    double *relResHistory, int histCap, int *histCount);
+
+/* ---- device-resident grids and single operators (what the facade's operator functions call) ----------- */
+int gmg_grid_create(gmg_solver *s, int level, gmg_grid **out); /* zero-filled */
+int gmg_grid_destroy(gmg_grid *g);
+int gmg_grid_upload(gmg_grid *g, const double *host);   /* host: dense expanded grid of that level */
+int gmg_grid_download(gmg_grid *g, double *host);        /* cells outside the stored box are written as 0 */
+int gmg_grid_zero(gmg_grid *g);
+int gmg_grid_copy(gmg_grid *dst, const gmg_grid *src);
+
+/* jacobiPoissonSmoother, Ops.h:262-367 (x in place; level 0 uses the fine weights) */
+int gmg_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b);
+/* boundaryJacobiPoissonSmoother over the solver's own band, Ops.h:524-619, `sweeps` times */
+int gmg_boundary_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int sweeps);
+/* applyPoissonMatrix, Ops.h:621-714 (dst written on active cells only) */
+int gmg_apply(gmg_solver *s, gmg_grid *dst, const gmg_grid *src);
+/* computePoissonResidual, Ops.h:716-732 */
+int gmg_residual(gmg_solver *s, gmg_grid *r, const gmg_grid *x, const gmg_grid *b);
+/* downsample, Ops.h:734-835 (coarse = level of fine + 1) */
+int gmg_restrict(gmg_solver *s, gmg_grid *coarse, const gmg_grid *fine);
+/* upsampleAndAdd, Ops.h:873-972 */
+int gmg_prolong_add(gmg_solver *s, gmg_grid *fine, const gmg_grid *coarse);
+/* dotProduct Ops.h:1020-1085, squaredL2Norm :1205-1265, infNorm :1267-1326 (max(v,0) as in the reference) */
+int gmg_dot(gmg_solver *s, const gmg_grid *a, const gmg_grid *b, double *out);
+int gmg_norm2(gmg_solver *s, const gmg_grid *a, double *out);
+int gmg_inf_norm(gmg_solver *s, const gmg_grid *a, double *out);
+/* addToVector Ops.h:1087-1137: dst += scale*src */
+int gmg_axpy(gmg_solver *s, gmg_grid *dst, const gmg_grid *src, double scale);
+/* addVectors Ops.h:1139-1195: dst = a + scale*v (dst may alias a or v) */
+int gmg_add_scaled(gmg_solver *s, gmg_grid *dst, const gmg_grid *a, const gmg_grid *v, double scale);
+/* scaleVector Ops.h:974-1018 */
+int gmg_scale(gmg_solver *s, gmg_grid *v, double scale);
+/* device-resident V-cycle / PCG on grids of level 0 (no host copies; what bench.py's `value` times) */
+int gmg_vcycle_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int useInitialGuess);
+int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, double tol, int maxIt, int preconditioner,
+		   int *iterations, double *relResHistory, int histCap, int *histCount);
+
+/* ---- measurement hooks ----------------------------------------------------------------------------- */
+/* kernels launched by this library on this context since the last reset (bench.py's gpu_launches) */
+int gmg_launch_count(gmg_ctx *ctx, int64_t *count, int reset);
+/* CUDA-event timing on the context's stream: begin/end bracket, result in ms */
+int gmg_timer_begin(gmg_ctx *ctx);
+int gmg_timer_end(gmg_ctx *ctx, double *ms);
+/* accumulated device time (ms) and launches per kernel class since the last reset; classes are listed by
+ * gmg_kernel_class_name(i), i in [0, gmg_kernel_class_count()).  Only collected when enabled (adds events). */
+int gmg_profile_enable(gmg_ctx *ctx, int on);
+int gmg_kernel_class_count(void);
+const char *gmg_kernel_class_name(int i);
+int gmg_profile_get(gmg_ctx *ctx, int klass, double *ms, int64_t *launches, double *algorithmicBytes);
+int gmg_profile_reset(gmg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
