@@ -138,12 +138,12 @@ class Context:
     def profile_reset(self):
         _check(self.lib.gmg_profile_reset(self.h))
 
-    def profile(self):
+    def profile(self, fine_level_only=False):
         """{class name: (ms, launches, algorithmic bytes)} accumulated since the last reset."""
         out = {}
         for i in range(self.lib.gmg_kernel_class_count()):
             ms, n, by = C.c_double(), C.c_int64(), C.c_double()
-            _check(self.lib.gmg_profile_get(self.h, i, C.byref(ms), C.byref(n), C.byref(by)))
+            _check(self.lib.gmg_profile_get(self.h, i, int(fine_level_only), C.byref(ms), C.byref(n), C.byref(by)))
             out[self.lib.gmg_kernel_class_name(i).decode()] = (ms.value, int(n.value), by.value)
         return out
 
@@ -321,17 +321,19 @@ class GeometricMultigridPoissonSolver:
         return float(ms.value)
 
     # ---- host-buffer entry points (what the reference's callers use) ----------------------------
-    def applyVCycle(self, solutionVector, rhsVector, useInitialGuess: bool = False):
-        """MG.cpp:420-881; returns the new solution grid."""
-        x, xp = _f64(np.array(solutionVector, copy=True))
+    def applyVCycle(self, solutionVector, rhsVector, useInitialGuess: bool = False, inplace: bool = False):
+        """MG.cpp:420-881; returns the new solution grid (inplace=True mutates solutionVector like the reference does)."""
+        x, xp = _f64(solutionVector if inplace else np.array(solutionVector, copy=True))
         b, bp = _f64(rhsVector)
         _check(self.lib.gmg_vcycle(self.h, xp, bp, int(useInitialGuess)))
         return x
 
-    def solveGeometricConjugateGradient(self, solutionGrid, rhsGrid, tolerance, maxIterations, useMGPreconditioner: bool = True):
+    def solveGeometricConjugateGradient(self, solutionGrid, rhsGrid, tolerance, maxIterations, useMGPreconditioner: bool = True,
+                                        inplace: bool = False):
         """CG.h:11-207 with A = applyPoissonMatrix, M^-1 = applyVCycle (GFS.cpp:430-483).
-        Returns (solution, iterations printed by CG.h:198 or -1 on an early-out, relative-residual history)."""
-        x, xp = _f64(np.array(solutionGrid, copy=True))
+        Returns (solution, iterations printed by CG.h:198 or -1 on an early-out, relative-residual history).
+        inplace=True writes the pressure into solutionGrid itself (as the reference does) instead of a copy."""
+        x, xp = _f64(solutionGrid if inplace else np.array(solutionGrid, copy=True))
         b, bp = _f64(rhsGrid)
         hist = np.zeros(int(maxIterations) + 2, dtype=np.float64)
         it, cnt = C.c_int(), C.c_int()

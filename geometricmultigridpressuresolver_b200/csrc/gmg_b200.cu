@@ -58,9 +58,38 @@ LaunchScope::~LaunchScope()
 {
     if (!ctx->profiling) return;
     cudaEventRecord(e1, ctx->stream);
-    ctx->recs.push_back({klass, bytes, e0, e1});
+    ctx->recs.push_back({klass, ctx->curLevel, bytes, e0, e1});
 }
 } // namespace gmg
+
+
+// Stream-ordered allocation from the device's default memory pool with an unlimited release threshold: a solver is
+// built and torn down every simulation frame, so freed blocks stay cached in the pool instead of going back to the driver.
+thread_local cudaStream_t g_stream = nullptr;
+static cudaError_t enterCtx(gmg_ctx *ctx)
+{
+    g_stream = ctx->stream;
+    return cudaSetDevice(ctx->device);
+}
+static bool usePool()
+{
+    static const bool v = [] { const char *e = getenv("GMG_POOL"); return !(e && e[0] == '0'); }();
+    return v;
+}
+template <typename T>
+static cudaError_t devMalloc(T **p, size_t bytes)
+{
+    if (!usePool()) return cudaMalloc(reinterpret_cast<void **>(p), bytes ? bytes : 16);
+    return cudaMallocAsync(reinterpret_cast<void **>(p), bytes ? bytes : 16, g_stream);
+}
+static cudaError_t devFree(void *p)
+{
+    if (!p) return cudaSuccess;
+    if (!usePool()) return cudaFree(p);
+    return cudaFreeAsync(p, g_stream);
+}
+
+#define TRACE(msg) do { if (getenv("GMG_TRACE")) { fprintf(stderr, "[gmg] %s:%d %s\n", __func__, __LINE__, msg); fflush(stderr); } } while (0)
 
 static int invalid(const char *msg)
 {
@@ -76,9 +105,12 @@ static void flushProfile(gmg_ctx *ctx)
     {
 	float ms = 0;
 	cudaEventElapsedTime(&ms, r.e0, r.e1);
-	ctx->classMs[r.klass] += ms;
-	ctx->classLaunches[r.klass] += 1;
-	ctx->classBytes[r.klass] += r.bytes;
+	for (int f = 0; f < (r.level == 0 ? 2 : 1); ++f)
+	{
+	    ctx->classMs[f][r.klass] += ms;
+	    ctx->classLaunches[f][r.klass] += 1;
+	    ctx->classBytes[f][r.klass] += r.bytes;
+	}
 	ctx->eventPool.push_back(r.e0);
 	ctx->eventPool.push_back(r.e1);
     }
@@ -120,6 +152,13 @@ extern "C" int gmg_ctx_create(int device, void *stream, gmg_ctx **out)
 	GMG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	ctx->ownStream = true;
     }
+    g_stream = ctx->stream;
+    {
+	cudaMemPool_t pool;
+	GMG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+	uint64_t threshold = UINT64_MAX;
+	GMG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    }
     cudaDeviceProp prop;
     GMG_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->smCount = prop.multiProcessorCount;
@@ -138,7 +177,7 @@ extern "C" int gmg_ctx_create(int device, void *stream, gmg_ctx **out)
 extern "C" int gmg_ctx_destroy(gmg_ctx *ctx)
 {
     if (!ctx) return GMG_OK;
-    cudaSetDevice(ctx->device);
+    enterCtx(ctx);
     cudaStreamSynchronize(ctx->stream);
     flushProfile(ctx);
     for (auto e : ctx->eventPool) cudaEventDestroy(e);
@@ -146,6 +185,8 @@ extern "C" int gmg_ctx_destroy(gmg_ctx *ctx)
     cudaFree(ctx->ticket);
     cudaFree(ctx->scalars);
     cudaFreeHost(ctx->hostScalars);
+    for (int i = 0; i < 2; ++i)
+	if (ctx->pin[i]) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pinEv[i]); }
     cudaEventDestroy(ctx->t0);
     cudaEventDestroy(ctx->t1);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -196,19 +237,21 @@ extern "C" int gmg_profile_enable(gmg_ctx *ctx, int on)
 }
 extern "C" int gmg_kernel_class_count(void) { return KC_COUNT; }
 extern "C" const char *gmg_kernel_class_name(int i) { return (i >= 0 && i < KC_COUNT) ? kClassNames[i] : ""; }
-extern "C" int gmg_profile_get(gmg_ctx *ctx, int klass, double *ms, int64_t *launches, double *bytes)
+extern "C" int gmg_profile_get(gmg_ctx *ctx, int klass, int fineLevelOnly, double *ms, int64_t *launches, double *bytes)
 {
     if (klass < 0 || klass >= KC_COUNT) return invalid("bad kernel class");
     flushProfile(ctx);
-    if (ms) *ms = ctx->classMs[klass];
-    if (launches) *launches = ctx->classLaunches[klass];
-    if (bytes) *bytes = ctx->classBytes[klass];
+    const int f = fineLevelOnly ? 1 : 0;
+    if (ms) *ms = ctx->classMs[f][klass];
+    if (launches) *launches = ctx->classLaunches[f][klass];
+    if (bytes) *bytes = ctx->classBytes[f][klass];
     return GMG_OK;
 }
 extern "C" int gmg_profile_reset(gmg_ctx *ctx)
 {
     flushProfile(ctx);
-    for (int i = 0; i < KC_COUNT; ++i) { ctx->classMs[i] = 0; ctx->classLaunches[i] = 0; ctx->classBytes[i] = 0; }
+    for (int f = 0; f < 2; ++f)
+	for (int i = 0; i < KC_COUNT; ++i) { ctx->classMs[f][i] = 0; ctx->classLaunches[f][i] = 0; ctx->classBytes[f][i] = 0; }
     return GMG_OK;
 }
 
@@ -255,32 +298,95 @@ static bool clipBox(const Geom &g, const int64_t hostRes[3], int lo[3], int hi[3
     return any;
 }
 
+// Host <-> device box transfers.  The caller's arrays are dense EXPANDED grids in pageable (or pinned) memory, of which
+// only the cropped box moves: rows are gathered by a few host threads into two pinned 32 MB buffers and shipped as
+// contiguous async copies, double-buffered so the gather of slab k overlaps the DMA of slab k-1.
+static int ensurePinned(gmg_ctx *ctx)
+{
+    if (ctx->pin[0]) return GMG_OK;
+    ctx->pinCap = size_t(32) << 20;
+    for (int i = 0; i < 2; ++i)
+    {
+	GMG_CUDA(cudaMallocHost(&ctx->pin[i], ctx->pinCap));
+	GMG_CUDA(cudaEventCreateWithFlags(&ctx->pinEv[i], cudaEventDisableTiming));
+    }
+    return GMG_OK;
+}
+
+template <typename Fn>
+static void parallelRows(int64_t rows, const Fn &fn)
+{
+    const int nt = int(std::max<int64_t>(1, std::min<int64_t>(std::min(12u, std::max(1u, std::thread::hardware_concurrency())), rows / 64)));
+    if (nt <= 1) { fn(0, rows); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (rows + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t)
+    {
+	const int64_t r0 = t * per, r1 = std::min(rows, r0 + per);
+	if (r0 < r1) th.emplace_back([&fn, r0, r1]() { fn(r0, r1); });
+    }
+    for (auto &t : th) t.join();
+}
+
 template <typename T>
 static int copyBoxH2D(gmg_ctx *ctx, T *staging, const T *host, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3])
 {
-    cudaMemcpy3DParms p = {};
-    p.srcPtr = make_cudaPitchedPtr(const_cast<T *>(host), size_t(hostRes[0]) * sizeof(T), size_t(hostRes[0]), size_t(hostRes[1]));
-    p.srcPos = make_cudaPos(size_t(g.org[0] + lo[0]) * sizeof(T), size_t(g.org[1] + lo[1]), size_t(g.org[2] + lo[2]));
-    const size_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
-    p.dstPtr = make_cudaPitchedPtr(staging, nx * sizeof(T), nx, ny);
-    p.dstPos = make_cudaPos(0, 0, 0);
-    p.extent = make_cudaExtent(nx * sizeof(T), ny, nz);
-    p.kind = cudaMemcpyHostToDevice;
-    GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    GMG_TRY(ensurePinned(ctx));
+    const int64_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
+    const int64_t x0 = g.org[0] + lo[0], y0 = g.org[1] + lo[1], z0 = g.org[2] + lo[2];
+    const int64_t slabBytes = nx * ny * int64_t(sizeof(T));
+    const int64_t zPer = std::max<int64_t>(1, int64_t(ctx->pinCap) / std::max<int64_t>(slabBytes, 1));
+    if (slabBytes > int64_t(ctx->pinCap)) return gmg::cudaFail(cudaErrorInvalidValue, "box slab larger than the pinned staging buffer", __FILE__, __LINE__);
+    int buf = 0;
+    for (int64_t zs = 0; zs < nz; zs += zPer, buf ^= 1)
+    {
+	const int64_t zc = std::min(zPer, nz - zs);
+	GMG_CUDA(cudaEventSynchronize(ctx->pinEv[buf]));
+	T *pin = static_cast<T *>(ctx->pin[buf]);
+	parallelRows(zc * ny, [&](int64_t r0, int64_t r1) {
+	    for (int64_t r = r0; r < r1; ++r)
+	    {
+		const int64_t z = r / ny, y = r - z * ny;
+		std::memcpy(pin + r * nx, host + x0 + hostRes[0] * ((y0 + y) + hostRes[1] * (z0 + zs + z)), size_t(nx) * sizeof(T));
+	    }
+	});
+	GMG_CUDA(cudaMemcpyAsync(staging + zs * nx * ny, pin, size_t(zc * slabBytes), cudaMemcpyHostToDevice, ctx->stream));
+	GMG_CUDA(cudaEventRecord(ctx->pinEv[buf], ctx->stream));
+    }
     return GMG_OK;
 }
 template <typename T>
 static int copyBoxD2H(gmg_ctx *ctx, T *host, const T *staging, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3])
 {
-    cudaMemcpy3DParms p = {};
-    p.dstPtr = make_cudaPitchedPtr(host, size_t(hostRes[0]) * sizeof(T), size_t(hostRes[0]), size_t(hostRes[1]));
-    p.dstPos = make_cudaPos(size_t(g.org[0] + lo[0]) * sizeof(T), size_t(g.org[1] + lo[1]), size_t(g.org[2] + lo[2]));
-    const size_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
-    p.srcPtr = make_cudaPitchedPtr(const_cast<T *>(staging), nx * sizeof(T), nx, ny);
-    p.srcPos = make_cudaPos(0, 0, 0);
-    p.extent = make_cudaExtent(nx * sizeof(T), ny, nz);
-    p.kind = cudaMemcpyDeviceToHost;
-    GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    GMG_TRY(ensurePinned(ctx));
+    const int64_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
+    const int64_t x0 = g.org[0] + lo[0], y0 = g.org[1] + lo[1], z0 = g.org[2] + lo[2];
+    const int64_t slabBytes = nx * ny * int64_t(sizeof(T));
+    const int64_t zPer = std::max<int64_t>(1, int64_t(ctx->pinCap) / std::max<int64_t>(slabBytes, 1));
+    if (slabBytes > int64_t(ctx->pinCap)) return gmg::cudaFail(cudaErrorInvalidValue, "box slab larger than the pinned staging buffer", __FILE__, __LINE__);
+    // issue slab k+1's DMA before scattering slab k
+    auto issue = [&](int64_t zs, int buf) -> int {
+	const int64_t zc = std::min(zPer, nz - zs);
+	GMG_CUDA(cudaMemcpyAsync(ctx->pin[buf], staging + zs * nx * ny, size_t(zc * slabBytes), cudaMemcpyDeviceToHost, ctx->stream));
+	GMG_CUDA(cudaEventRecord(ctx->pinEv[buf], ctx->stream));
+	return GMG_OK;
+    };
+    int buf = 0;
+    if (nz > 0) GMG_TRY(issue(0, 0));
+    for (int64_t zs = 0; zs < nz; zs += zPer, buf ^= 1)
+    {
+	const int64_t zc = std::min(zPer, nz - zs);
+	if (zs + zPer < nz) GMG_TRY(issue(zs + zPer, buf ^ 1));
+	GMG_CUDA(cudaEventSynchronize(ctx->pinEv[buf]));
+	const T *pin = static_cast<const T *>(ctx->pin[buf]);
+	parallelRows(zc * ny, [&](int64_t r0, int64_t r1) {
+	    for (int64_t r = r0; r < r1; ++r)
+	    {
+		const int64_t z = r / ny, y = r - z * ny;
+		std::memcpy(host + x0 + hostRes[0] * ((y0 + y) + hostRes[1] * (z0 + zs + z)), pin + r * nx, size_t(nx) * sizeof(T));
+	    }
+	});
+    }
     return GMG_OK;
 }
 
@@ -327,14 +433,14 @@ static int uploadLabels(gmg_ctx *ctx, uint8_t *dst, const int32_t *host, const i
     }
     int32_t *staging = nullptr;
     const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-    GMG_CUDA(cudaMalloc(&staging, sizeof(int32_t) * cnt));
+    GMG_CUDA(devMalloc(&staging, sizeof(int32_t) * cnt));
     GMG_TRY(copyBoxH2D(ctx, staging, host, res, g, lo, hi));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_labels_from_i32<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dst, staging, ba, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(staging));
+    GMG_CUDA(devFree(staging));
     return GMG_OK;
 }
 
@@ -349,14 +455,14 @@ static int downloadLabels(gmg_ctx *ctx, int32_t *host, const uint8_t *src, const
     if (!clipBox(g, res, lo, hi)) return GMG_OK;
     int32_t *staging = nullptr;
     const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-    GMG_CUDA(cudaMalloc(&staging, sizeof(int32_t) * cnt));
+    GMG_CUDA(devMalloc(&staging, sizeof(int32_t) * cnt));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_labels_to_i32<<<unsigned(divUp(cnt, BLOCK)), BLOCK, 0, ctx->stream>>>(staging, src, boxArgs(g), lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
     }
     GMG_TRY(copyBoxD2H(ctx, host, staging, res, g, lo, hi));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(staging));
+    GMG_CUDA(devFree(staging));
     return GMG_OK;
 }
 
@@ -371,14 +477,14 @@ static int uploadValues(gmg_ctx *ctx, double *dst, const double *host, const int
     }
     double *staging = nullptr;
     const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-    GMG_CUDA(cudaMalloc(&staging, sizeof(double) * cnt));
+    GMG_CUDA(devMalloc(&staging, sizeof(double) * cnt));
     GMG_TRY(copyBoxH2D(ctx, staging, host, hostRes, g, lo, hi));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_values_from_staging<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dst, staging, maskLabels, boxArgs(g), lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(staging));
+    GMG_CUDA(devFree(staging));
     return GMG_OK;
 }
 
@@ -389,14 +495,14 @@ static int downloadValues(gmg_ctx *ctx, double *host, const double *src, const i
     if (!clipBox(g, hostRes, lo, hi)) return GMG_OK;
     double *staging = nullptr;
     const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-    GMG_CUDA(cudaMalloc(&staging, sizeof(double) * cnt));
+    GMG_CUDA(devMalloc(&staging, sizeof(double) * cnt));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_values_to_staging<<<unsigned(divUp(cnt, BLOCK)), BLOCK, 0, ctx->stream>>>(staging, src, boxArgs(g), lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
     }
     GMG_TRY(copyBoxD2H(ctx, host, staging, hostRes, g, lo, hi));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(staging));
+    GMG_CUDA(devFree(staging));
     return GMG_OK;
 }
 
@@ -406,7 +512,7 @@ static int downloadValues(gmg_ctx *ctx, double *host, const double *src, const i
 static int countLabels(gmg_ctx *ctx, const uint8_t *labels, int64_t total, int64_t *nInterior, int64_t *nBoundary)
 {
     unsigned long long *d = nullptr, h[2] = {0, 0};
-    GMG_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    GMG_CUDA(devMalloc(&d, 2 * sizeof(unsigned long long)));
     GMG_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), ctx->stream));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
@@ -415,7 +521,7 @@ static int countLabels(gmg_ctx *ctx, const uint8_t *labels, int64_t total, int64
     }
     GMG_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(d));
+    GMG_CUDA(devFree(d));
     *nInterior = int64_t(h[0]);
     *nBoundary = int64_t(h[1]);
     return GMG_OK;
@@ -426,13 +532,13 @@ static int selectFlagged(gmg_ctx *ctx, const uint8_t *flags, int64_t n, int32_t 
 {
     int *dCount = nullptr;
     int32_t *tmpOut = nullptr;
-    GMG_CUDA(cudaMalloc(&dCount, sizeof(int)));
-    GMG_CUDA(cudaMalloc(&tmpOut, sizeof(int32_t) * std::max<int64_t>(n, 1)));
+    GMG_CUDA(devMalloc(&dCount, sizeof(int)));
+    GMG_CUDA(devMalloc(&tmpOut, sizeof(int32_t) * std::max<int64_t>(n, 1)));
     void *dTemp = nullptr;
     size_t tempBytes = 0;
     thrust::counting_iterator<int32_t> it(0);
     GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, it, flags, tmpOut, dCount, int(n), ctx->stream));
-    GMG_CUDA(cudaMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
+    GMG_CUDA(devMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
     GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, it, flags, tmpOut, dCount, int(n), ctx->stream));
     ++ctx->launches;
     int h = 0;
@@ -440,12 +546,12 @@ static int selectFlagged(gmg_ctx *ctx, const uint8_t *flags, int64_t n, int32_t 
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     *count = h;
     *out = nullptr;
-    GMG_CUDA(cudaMalloc(out, sizeof(int32_t) * std::max(h, 1)));
+    GMG_CUDA(devMalloc(out, sizeof(int32_t) * std::max(h, 1)));
     GMG_CUDA(cudaMemcpyAsync(*out, tmpOut, sizeof(int32_t) * h, cudaMemcpyDeviceToDevice, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(dTemp));
-    GMG_CUDA(cudaFree(tmpOut));
-    GMG_CUDA(cudaFree(dCount));
+    GMG_CUDA(devFree(dTemp));
+    GMG_CUDA(devFree(tmpOut));
+    GMG_CUDA(devFree(dCount));
     return GMG_OK;
 }
 
@@ -456,8 +562,8 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
     const BoxArgs ba = boxArgs(g);
     const unsigned grid = unsigned(divUp(g.total, BLOCK));
     uint8_t *m0 = nullptr, *m1 = nullptr;
-    GMG_CUDA(cudaMalloc(&m0, g.total));
-    GMG_CUDA(cudaMalloc(&m1, g.total));
+    GMG_CUDA(devMalloc(&m0, g.total));
+    GMG_CUDA(devMalloc(&m1, g.total));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_band_init<<<grid, BLOCK, 0, ctx->stream>>>(m0, L.labels, g.total);
@@ -480,25 +586,25 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 	k_band_flags<<<grid, BLOCK, 0, ctx->stream>>>(m1, m0, L.labels, 1, g.total);
     }
     GMG_TRY(selectFlagged(ctx, m1, g.total, &idxI, &nI));
-    GMG_CUDA(cudaFree(m0));
-    GMG_CUDA(cudaFree(m1));
+    GMG_CUDA(devFree(m0));
+    GMG_CUDA(devFree(m1));
     L.nBoundary = nB;
     L.nBand = nB + nI;
     const int nBand = L.nBand;
-    GMG_CUDA(cudaMalloc(&L.bandIdx, sizeof(int32_t) * std::max(nBand, 1)));
+    GMG_CUDA(devMalloc(&L.bandIdx, sizeof(int32_t) * std::max(nBand, 1)));
     GMG_CUDA(cudaMemcpyAsync(L.bandIdx, idxB, sizeof(int32_t) * nB, cudaMemcpyDeviceToDevice, ctx->stream));
     GMG_CUDA(cudaMemcpyAsync(L.bandIdx + nB, idxI, sizeof(int32_t) * nI, cudaMemcpyDeviceToDevice, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(idxB));
-    GMG_CUDA(cudaFree(idxI));
-    GMG_CUDA(cudaMalloc(&L.bandNbr, sizeof(int32_t) * 6 * std::max(nBand, 1)));
-    GMG_CUDA(cudaMalloc(&L.bandV0, sizeof(double) * std::max(nBand, 1)));
-    GMG_CUDA(cudaMalloc(&L.bandV1, sizeof(double) * std::max(nBand, 1)));
-    GMG_CUDA(cudaMalloc(&L.bandB, sizeof(double) * std::max(nBand, 1)));
+    GMG_CUDA(devFree(idxB));
+    GMG_CUDA(devFree(idxI));
+    GMG_CUDA(devMalloc(&L.bandNbr, sizeof(int32_t) * 6 * std::max(nBand, 1)));
+    GMG_CUDA(devMalloc(&L.bandV0, sizeof(double) * std::max(nBand, 1)));
+    GMG_CUDA(devMalloc(&L.bandV1, sizeof(double) * std::max(nBand, 1)));
+    GMG_CUDA(devMalloc(&L.bandB, sizeof(double) * std::max(nBand, 1)));
     if (nBand > 0)
     {
 	int32_t *pos = nullptr;
-	GMG_CUDA(cudaMalloc(&pos, sizeof(int32_t) * g.total));
+	GMG_CUDA(devMalloc(&pos, sizeof(int32_t) * g.total));
 	{
 	    GMG_LAUNCH(ctx, KC_SETUP, 0);
 	    k_fill_i32<<<grid, BLOCK, 0, ctx->stream>>>(pos, -1, g.total);
@@ -512,14 +618,14 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 	    k_band_nbr<<<unsigned(divUp(nBand, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bandNbr, pos, L.bandIdx, nBand, g.pitch, g.plane);
 	}
 	GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-	GMG_CUDA(cudaFree(pos));
+	GMG_CUDA(devFree(pos));
     }
     return GMG_OK;
 }
 
 static int buildCoefs(gmg_ctx *ctx, Level &L, const double *w0, const double *w1, const double *w2)
 {
-    GMG_CUDA(cudaMalloc(&L.bcoef, sizeof(double) * 7 * std::max(L.nBoundary, 1)));
+    GMG_CUDA(devMalloc(&L.bcoef, sizeof(double) * 7 * std::max(L.nBoundary, 1)));
     if (L.nBoundary > 0)
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
@@ -534,16 +640,16 @@ static int buildChunks(gmg_ctx *ctx, Level &L)
     const Geom &g = L.g;
     const int nChunks = g.chunksPerPlane * g.zBlocks;
     uint8_t *fi = nullptr, *fa = nullptr;
-    GMG_CUDA(cudaMalloc(&fi, nChunks));
-    GMG_CUDA(cudaMalloc(&fa, nChunks));
+    GMG_CUDA(devMalloc(&fi, nChunks));
+    GMG_CUDA(devMalloc(&fa, nChunks));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_chunk_flags<<<nChunks, BLOCK, 0, ctx->stream>>>(fi, fa, L.labels, g.chunksPerPlane, g.plane, g.n[2]);
     }
     GMG_TRY(selectFlagged(ctx, fi, nChunks, &L.chunksInterior, &L.nChunksInterior));
     GMG_TRY(selectFlagged(ctx, fa, nChunks, &L.chunksActive, &L.nChunksActive));
-    GMG_CUDA(cudaFree(fi));
-    GMG_CUDA(cudaFree(fa));
+    GMG_CUDA(devFree(fi));
+    GMG_CUDA(devFree(fa));
     return GMG_OK;
 }
 
@@ -553,8 +659,8 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz)
     const int n = L.nBand;
     if (n == 0) return GMG_OK;
     unsigned long long *keys = nullptr, *keysOut = nullptr;
-    GMG_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * n));
-    GMG_CUDA(cudaMalloc(&keysOut, sizeof(unsigned long long) * n));
+    GMG_CUDA(devMalloc(&keys, sizeof(unsigned long long) * n));
+    GMG_CUDA(devMalloc(&keysOut, sizeof(unsigned long long) * n));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_band_keys<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(keys, L.bandIdx, n, boxArgs(L.g));
@@ -562,7 +668,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz)
     void *dTemp = nullptr;
     size_t tempBytes = 0;
     GMG_CUDA(cub::DeviceRadixSort::SortKeys(dTemp, tempBytes, keys, keysOut, n, 0, 64, ctx->stream));
-    GMG_CUDA(cudaMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
+    GMG_CUDA(devMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
     GMG_CUDA(cub::DeviceRadixSort::SortKeys(dTemp, tempBytes, keys, keysOut, n, 0, 64, ctx->stream));
     ++ctx->launches;
     std::vector<unsigned long long> h(n);
@@ -574,18 +680,18 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz)
 	xyz[3 * k + 1] = int64_t((h[k] >> 12) & 0xfff);
 	xyz[3 * k + 2] = int64_t((h[k] >> 24) & 0xfff);
     }
-    GMG_CUDA(cudaFree(dTemp));
-    GMG_CUDA(cudaFree(keys));
-    GMG_CUDA(cudaFree(keysOut));
+    GMG_CUDA(devFree(dTemp));
+    GMG_CUDA(devFree(keys));
+    GMG_CUDA(devFree(keysOut));
     return GMG_OK;
 }
 
 static void freeLevel(Level &L)
 {
-    cudaFree(L.labels); cudaFree(L.bandIdx); cudaFree(L.bandNbr); cudaFree(L.bcoef);
-    cudaFree(L.bandV0); cudaFree(L.bandV1); cudaFree(L.bandB);
-    cudaFree(L.chunksInterior); cudaFree(L.chunksActive);
-    cudaFree(L.x); cudaFree(L.xAlt); cudaFree(L.b); cudaFree(L.r);
+    devFree(L.labels); devFree(L.bandIdx); devFree(L.bandNbr); devFree(L.bcoef);
+    devFree(L.bandV0); devFree(L.bandV1); devFree(L.bandB);
+    devFree(L.chunksInterior); devFree(L.chunksActive);
+    devFree(L.x); devFree(L.xAlt); devFree(L.b); devFree(L.r);
     L = Level();
 }
 
@@ -614,18 +720,23 @@ extern "C" int gmg_expand_labels(gmg_ctx *ctx, const int32_t *base, const int64_
 				 const int64_t offset[3])
 {
     if (!ctx || !base || !out) return invalid("gmg_expand_labels: null argument");
-    GMG_CUDA(cudaSetDevice(ctx->device));
+    TRACE("enter");
+    GMG_CUDA(enterCtx(ctx));
+    TRACE("ctx set");
     const int64_t n = baseRes[0] * baseRes[1] * baseRes[2];
     int32_t *dIn = nullptr, *dOut = nullptr;
-    GMG_CUDA(cudaMalloc(&dIn, sizeof(int32_t) * n));
-    GMG_CUDA(cudaMalloc(&dOut, sizeof(int32_t) * n));
+    GMG_CUDA(devMalloc(&dIn, sizeof(int32_t) * n));
+    GMG_CUDA(devMalloc(&dOut, sizeof(int32_t) * n));
+    TRACE("allocated");
     GMG_CUDA(cudaMemcpyAsync(dIn, base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_expand_labels<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(dOut, dIn, n);
     }
+    TRACE("kernel launched");
     // EXTERIOR everywhere, then the mapped base box at +offset
     std::fill(out, out + expRes[0] * expRes[1] * expRes[2], int32_t(L_EXTERIOR));
+    TRACE("host filled");
     cudaMemcpy3DParms p = {};
     p.dstPtr = make_cudaPitchedPtr(out, size_t(expRes[0]) * 4, size_t(expRes[0]), size_t(expRes[1]));
     p.dstPos = make_cudaPos(size_t(offset[0]) * 4, size_t(offset[1]), size_t(offset[2]));
@@ -633,9 +744,11 @@ extern "C" int gmg_expand_labels(gmg_ctx *ctx, const int32_t *base, const int64_
     p.extent = make_cudaExtent(size_t(baseRes[0]) * 4, size_t(baseRes[1]), size_t(baseRes[2]));
     p.kind = cudaMemcpyDeviceToHost;
     GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    TRACE("3d copy issued");
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(dIn));
-    GMG_CUDA(cudaFree(dOut));
+    TRACE("synced");
+    GMG_CUDA(devFree(dIn));
+    GMG_CUDA(devFree(dOut));
     return GMG_OK;
 }
 
@@ -643,14 +756,14 @@ extern "C" int gmg_expand_weights(gmg_ctx *ctx, const double *baseW, const int64
 				  const int64_t offset[3], int axis)
 {
     if (!ctx || !baseW || !out || axis < 0 || axis > 2) return invalid("gmg_expand_weights: bad argument");
-    GMG_CUDA(cudaSetDevice(ctx->device));
+    GMG_CUDA(enterCtx(ctx));
     int64_t bfr[3] = {baseRes[0], baseRes[1], baseRes[2]}, efr[3] = {expRes[0], expRes[1], expRes[2]};
     ++bfr[axis];
     ++efr[axis];
     const int64_t n = bfr[0] * bfr[1] * bfr[2];
     double *dIn = nullptr, *dOut = nullptr;
-    GMG_CUDA(cudaMalloc(&dIn, sizeof(double) * n));
-    GMG_CUDA(cudaMalloc(&dOut, sizeof(double) * n));
+    GMG_CUDA(devMalloc(&dIn, sizeof(double) * n));
+    GMG_CUDA(devMalloc(&dOut, sizeof(double) * n));
     GMG_CUDA(cudaMemcpyAsync(dIn, baseW, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
@@ -665,8 +778,8 @@ extern "C" int gmg_expand_weights(gmg_ctx *ctx, const double *baseW, const int64
     p.kind = cudaMemcpyDeviceToHost;
     GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(dIn));
-    GMG_CUDA(cudaFree(dOut));
+    GMG_CUDA(devFree(dIn));
+    GMG_CUDA(devFree(dOut));
     return GMG_OK;
 }
 
@@ -693,7 +806,7 @@ static int uploadWeights(gmg_ctx *ctx, double *dW[3], const double *w0, const do
     {
 	int64_t fr[3] = {res[0], res[1], res[2]};
 	++fr[a];
-	GMG_CUDA(cudaMalloc(&dW[a], sizeof(double) * g.total));
+	GMG_CUDA(devMalloc(&dW[a], sizeof(double) * g.total));
 	GMG_TRY(uploadValues(ctx, dW[a], w[a], fr, g));
     }
     return GMG_OK;
@@ -703,7 +816,7 @@ extern "C" int gmg_set_boundary_labels(gmg_ctx *ctx, int32_t *labels, const int6
 				       const int64_t boxLo[3], const int64_t boxHi[3])
 {
     if (!ctx || !labels || !w0 || !w1 || !w2) return invalid("gmg_set_boundary_labels: null argument");
-    GMG_CUDA(cudaSetDevice(ctx->device));
+    GMG_CUDA(enterCtx(ctx));
     int64_t lo[3], hi[3];
     int st = boundsFromHintOrScan(labels, res, boxLo, boxHi, lo, hi);
     if (st == GMG_ERR_NO_ACTIVE) return GMG_OK; // nothing to promote
@@ -712,8 +825,8 @@ extern "C" int gmg_set_boundary_labels(gmg_ctx *ctx, int32_t *labels, const int6
     makeGeom(g, res, lo, hi);
     uint8_t *dIn = nullptr, *dOut = nullptr;
     double *dW[3] = {nullptr, nullptr, nullptr};
-    GMG_CUDA(cudaMalloc(&dIn, g.total));
-    GMG_CUDA(cudaMalloc(&dOut, g.total));
+    GMG_CUDA(devMalloc(&dIn, g.total));
+    GMG_CUDA(devMalloc(&dOut, g.total));
     GMG_TRY(uploadLabels(ctx, dIn, labels, res, g));
     GMG_TRY(uploadWeights(ctx, dW, w0, w1, w2, res, g));
     {
@@ -721,9 +834,9 @@ extern "C" int gmg_set_boundary_labels(gmg_ctx *ctx, int32_t *labels, const int6
 	k_set_boundary<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dOut, dIn, dW[0], dW[1], dW[2], boxArgs(g));
     }
     GMG_TRY(downloadLabels(ctx, labels, dOut, res, g, false));
-    for (int a = 0; a < 3; ++a) GMG_CUDA(cudaFree(dW[a]));
-    GMG_CUDA(cudaFree(dIn));
-    GMG_CUDA(cudaFree(dOut));
+    for (int a = 0; a < 3; ++a) GMG_CUDA(devFree(dW[a]));
+    GMG_CUDA(devFree(dIn));
+    GMG_CUDA(devFree(dOut));
     return GMG_OK;
 }
 
@@ -744,7 +857,7 @@ static void coarseGeomOf(Geom &cg, int shift[3], const Geom &fg, const int64_t l
 static int coarsenOnDevice(gmg_ctx *ctx, uint8_t *coarse, const Geom &cg, const uint8_t *fine, const Geom &fg, const int shift[3])
 {
     uint8_t *tmp = nullptr;
-    GMG_CUDA(cudaMalloc(&tmp, cg.total));
+    GMG_CUDA(devMalloc(&tmp, cg.total));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_coarsen1<<<unsigned(divUp(cg.total, BLOCK)), BLOCK, 0, ctx->stream>>>(tmp, fine, boxArgs(cg), boxArgs(fg), shift[0], shift[1], shift[2]);
@@ -754,7 +867,7 @@ static int coarsenOnDevice(gmg_ctx *ctx, uint8_t *coarse, const Geom &cg, const 
 	k_coarsen2<<<unsigned(divUp(cg.total, BLOCK)), BLOCK, 0, ctx->stream>>>(coarse, tmp, boxArgs(cg));
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(cudaFree(tmp));
+    GMG_CUDA(devFree(tmp));
     return GMG_OK;
 }
 
@@ -763,7 +876,7 @@ extern "C" int gmg_coarsen_labels(gmg_ctx *ctx, const int32_t *fine, const int64
     if (!ctx || !fine || !coarse) return invalid("gmg_coarsen_labels: null argument");
     for (int a = 0; a < 3; ++a)
 	if (fineRes[a] % 2) return invalid("gmg_coarsen_labels: odd resolution");
-    GMG_CUDA(cudaSetDevice(ctx->device));
+    GMG_CUDA(enterCtx(ctx));
     int64_t lo[3], hi[3], clo[3], chi[3];
     const int64_t cres[3] = {fineRes[0] / 2, fineRes[1] / 2, fineRes[2] / 2};
     if (!scanBounds(fine, fineRes, lo, hi))
@@ -776,25 +889,25 @@ extern "C" int gmg_coarsen_labels(gmg_ctx *ctx, const int32_t *fine, const int64
     makeGeom(fg, fineRes, lo, hi);
     coarseGeomOf(cg, shift, fg, lo, hi, clo, chi);
     uint8_t *dF = nullptr, *dC = nullptr;
-    GMG_CUDA(cudaMalloc(&dF, fg.total));
-    GMG_CUDA(cudaMalloc(&dC, cg.total));
+    GMG_CUDA(devMalloc(&dF, fg.total));
+    GMG_CUDA(devMalloc(&dC, cg.total));
     GMG_TRY(uploadLabels(ctx, dF, fine, fineRes, fg));
     GMG_TRY(coarsenOnDevice(ctx, dC, cg, dF, fg, shift));
     GMG_TRY(downloadLabels(ctx, coarse, dC, cres, cg, true));
-    GMG_CUDA(cudaFree(dF));
-    GMG_CUDA(cudaFree(dC));
+    GMG_CUDA(devFree(dF));
+    GMG_CUDA(devFree(dC));
     return GMG_OK;
 }
 
 extern "C" int gmg_boundary_cells(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], int width, int64_t *xyz, int64_t *count)
 {
     if (!ctx || !labels || !count) return invalid("gmg_boundary_cells: null argument");
-    GMG_CUDA(cudaSetDevice(ctx->device));
+    GMG_CUDA(enterCtx(ctx));
     int64_t lo[3], hi[3];
     if (!scanBounds(labels, res, lo, hi)) { *count = 0; return GMG_OK; }
     Level L;
     makeGeom(L.g, res, lo, hi);
-    GMG_CUDA(cudaMalloc(&L.labels, L.g.total));
+    GMG_CUDA(devMalloc(&L.labels, L.g.total));
     GMG_TRY(uploadLabels(ctx, L.labels, labels, res, L.g));
     GMG_TRY(buildBand(ctx, L, width));
     *count = L.nBand;
@@ -818,8 +931,8 @@ extern "C" void gmg_solver_default_options(gmg_solver_options *opt)
 
 static int allocZero(double **p, int64_t n)
 {
-    GMG_CUDA(cudaMalloc(p, sizeof(double) * n));
-    GMG_CUDA(cudaMemset(*p, 0, sizeof(double) * n));
+    GMG_CUDA(devMalloc(p, sizeof(double) * n));
+    GMG_CUDA(cudaMemsetAsync(*p, 0, sizeof(double) * n, g_stream));
     return GMG_OK;
 }
 
@@ -922,8 +1035,8 @@ static int buildCoarseSolve(gmg_solver *s)
 	    inv[size_t(i) * n + j] = v;
 	    inv[size_t(j) * n + i] = v;
 	}
-    GMG_CUDA(cudaMalloc(&s->coarseIdx, sizeof(int32_t) * n));
-    GMG_CUDA(cudaMalloc(&s->coarseInv, sizeof(double) * size_t(n) * n));
+    GMG_CUDA(devMalloc(&s->coarseIdx, sizeof(int32_t) * n));
+    GMG_CUDA(devMalloc(&s->coarseInv, sizeof(double) * size_t(n) * n));
     GMG_CUDA(cudaMemcpy(s->coarseIdx, cellIdx.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
     GMG_CUDA(cudaMemcpy(s->coarseInv, inv.data(), sizeof(double) * size_t(n) * n, cudaMemcpyHostToDevice));
     return GMG_OK;
@@ -932,11 +1045,12 @@ static int buildCoarseSolve(gmg_solver *s)
 extern "C" int gmg_solver_destroy(gmg_solver *s)
 {
     if (!s) return GMG_OK;
-    cudaSetDevice(s->ctx->device);
+    enterCtx(s->ctx);
     cudaStreamSynchronize(s->ctx->stream);
+    for (auto &g : s->graphs) { cudaGraphExecDestroy(g.second.exec); cudaGraphDestroy(g.second.graph); }
     for (auto &L : s->lv) freeLevel(L);
-    cudaFree(s->coarseIdx); cudaFree(s->coarseInv);
-    cudaFree(s->pcgR); cudaFree(s->pcgP); cudaFree(s->pcgZ); cudaFree(s->pcgT); cudaFree(s->pcgX); cudaFree(s->pcgB);
+    devFree(s->coarseIdx); devFree(s->coarseInv);
+    devFree(s->pcgR); devFree(s->pcgP); devFree(s->pcgZ); devFree(s->pcgT); devFree(s->pcgX); devFree(s->pcgB);
     delete s;
     return GMG_OK;
 }
@@ -952,12 +1066,13 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	if (int(std::log2(double(res[a]))) + 1 < mgLevels) return invalid("gmg_solver_create: too many levels for this resolution (MG.cpp:159-161)");
 	if ((res[a] >> (mgLevels - 1)) << (mgLevels - 1) != res[a]) return invalid("gmg_solver_create: resolution not divisible by 2^(levels-1)");
     }
-    GMG_CUDA(cudaSetDevice(ctx->device));
+    GMG_CUDA(enterCtx(ctx));
     const double tStart = nowMs();
     gmg_solver *s = new gmg_solver;
     s->ctx = ctx;
     if (optIn) s->opt = *optIn;
     else gmg_solver_default_options(&s->opt);
+    if (const char *e = getenv("GMG_NO_GRAPHS")) s->useGraphs = !(e[0] == '1');
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel)
@@ -966,6 +1081,14 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	return invalid("gmg_solver_create: the tiled Gauss-Seidel smoother is not built in this revision; pass use_gauss_seidel = 0");
     }
     auto fail = [&](int st) { gmg_solver_destroy(s); return st; };
+    double tPhase = tStart;
+    auto lap = [&](const char *name) {
+	if (!s->opt.print_stats) return;
+	cudaStreamSynchronize(ctx->stream);
+	const double t = nowMs();
+	printf("      %-28s %8.3f ms\n", name, t - tPhase);
+	tPhase = t;
+    };
 
     int64_t lo[3], hi[3];
     int st = boundsFromHintOrScan(labels, res, s->opt.box_lo, s->opt.box_hi, lo, hi);
@@ -978,10 +1101,11 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	Level &L0 = s->lv[0];
 	makeGeom(L0.g, res, lo, hi);
 	if (L0.g.total >= (int64_t(1) << 31)) return fail(invalid("gmg_solver_create: cropped box exceeds 2^31 cells"));
-	if ((st = (cudaMalloc(&L0.labels, L0.g.total) == cudaSuccess ? GMG_OK : GMG_ERR_CUDA)) != GMG_OK) return fail(st);
+	if ((st = (devMalloc(&L0.labels, L0.g.total) == cudaSuccess ? GMG_OK : GMG_ERR_CUDA)) != GMG_OK) return fail(st);
 	if ((st = uploadLabels(ctx, L0.labels, labels, res, L0.g)) != GMG_OK) return fail(st);
 	if ((st = uploadWeights(ctx, dW, w0, w1, w2, res, L0.g)) != GMG_OK) return fail(st);
     }
+    lap("upload labels + weights");
     // coarse labels (MG.cpp:238-253) with the reference's level cap: a level without active cells drops it AND the one before
     int64_t clo[3] = {lo[0], lo[1], lo[2]}, chi[3] = {hi[0], hi[1], hi[2]};
     for (int level = 0; level < s->levels; ++level)
@@ -993,7 +1117,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	    int64_t nlo[3], nhi[3];
 	    coarseGeomOf(L.g, F.shift, F.g, clo, chi, nlo, nhi);
 	    for (int a = 0; a < 3; ++a) { clo[a] = nlo[a]; chi[a] = nhi[a]; }
-	    if (cudaMalloc(&L.labels, L.g.total) != cudaSuccess) return fail(GMG_ERR_CUDA);
+	    if (devMalloc(&L.labels, L.g.total) != cudaSuccess) return fail(GMG_ERR_CUDA);
 	    if ((st = coarsenOnDevice(ctx, L.labels, L.g, F.labels, F.g, F.shift)) != GMG_OK) return fail(st);
 	}
 	int64_t nI = 0, nB = 0;
@@ -1013,9 +1137,10 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     if (s->levels < 1)
     {
 	setError("level cap (MG.cpp:243-248) left no level: level 1 has no active cell");
-	for (int a = 0; a < 3; ++a) cudaFree(dW[a]);
+	for (int a = 0; a < 3; ++a) devFree(dW[a]);
 	return fail(GMG_ERR_NO_ACTIVE);
     }
+    lap("coarse labels");
     // bands (MG.cpp:279-281), coefficient records, chunk lists, grids
     int maxGrid = 0;
     for (int level = 0; level < s->levels; ++level)
@@ -1034,9 +1159,11 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	}
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int a = 0; a < 3; ++a) cudaFree(dW[a]);
+    for (int a = 0; a < 3; ++a) devFree(dW[a]);
+    lap("bands, records, chunks, grids");
     if ((st = ensureScratch(ctx, maxGrid)) != GMG_OK) return fail(st);
     if ((st = buildCoarseSolve(s)) != GMG_OK) return fail(st);
+    lap("coarse direct solver");
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     s->setupMs = nowMs() - tStart;
     *out = s;
@@ -1058,13 +1185,13 @@ extern "C" int gmg_solver_level_res(gmg_solver *s, int level, int64_t res[3])
 extern "C" int gmg_solver_get_labels(gmg_solver *s, int level, int32_t *out)
 {
     if (!s || !out || level < 0 || level >= s->levels) return invalid("level out of range");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return downloadLabels(s->ctx, out, s->lv[level].labels, s->lv[level].g.res, s->lv[level].g, true);
 }
 extern "C" int gmg_solver_get_boundary_cells(gmg_solver *s, int level, int64_t *xyz, int64_t *count)
 {
     if (!s || !count || level < 0 || level >= s->levels) return invalid("level out of range");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     *count = s->lv[level].nBand;
     if (xyz) return exportBand(s->ctx, s->lv[level], xyz);
     return GMG_OK;
@@ -1116,6 +1243,7 @@ static StencilArgs stencilArgs(gmg_solver *s, int level, const double *in, const
 
 static int launchStencil(gmg_solver *s, int level, int mode, const double *in, const double *b, double *out, double *dotResult)
 {
+    s->ctx->curLevel = level;
     const Level &L = s->lv[level];
     StencilArgs a = stencilArgs(s, level, in, b, out);
     a.result = dotResult;
@@ -1150,6 +1278,7 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
 // `sweeps` boundary-band Jacobi sweeps on grid x (Ops.h:524-619); zeroGrid: x is known to be all zero
 static int launchBand(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid)
 {
+    s->ctx->curLevel = level;
     const Level &L = s->lv[level];
     if (L.nBand == 0 || sweeps <= 0) return GMG_OK;
     BandArgs a;
@@ -1213,6 +1342,7 @@ static TransferArgs transferArgs(gmg_solver *s, int fineLevel)
 
 static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const double *fine)
 {
+    s->ctx->curLevel = fineLevel + 1;
     const Level &C = s->lv[fineLevel + 1];
     if (C.nChunksActive == 0) return GMG_OK;
     TransferArgs a = transferArgs(s, fineLevel);
@@ -1228,6 +1358,7 @@ static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const do
 
 static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const double *coarse)
 {
+    s->ctx->curLevel = fineLevel;
     const Level &F = s->lv[fineLevel];
     if (F.nChunksActive == 0) return GMG_OK;
     TransferArgs a = transferArgs(s, fineLevel);
@@ -1243,6 +1374,7 @@ static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const doubl
 
 static int launchZero(gmg_solver *s, int level, double *x)
 {
+    s->ctx->curLevel = level;
     const Level &L = s->lv[level];
     if (L.nChunksActive == 0) return GMG_OK;
     GMG_LAUNCH(s->ctx, KC_ZERO, double(L.nActive) * 8.0);
@@ -1253,6 +1385,7 @@ static int launchZero(gmg_solver *s, int level, double *x)
 
 static int launchCoarse(gmg_solver *s, double *x, const double *b)
 {
+    s->ctx->curLevel = s->levels - 1;
     const int n = s->nCoarse;
     GMG_LAUNCH(s->ctx, KC_COARSE, double(n) * n * 8.0);
     k_coarse_solve<<<unsigned(divUp(n, BLOCK / 32)), BLOCK, sizeof(double) * n, s->ctx->stream>>>(x, b, s->coarseIdx, s->coarseInv, n);
@@ -1264,6 +1397,7 @@ template <int OP>
 static int launchVec(gmg_solver *s, int level, double *y, const double *a, const double *c, double *y2, double sc, double *result, int klass,
 		     double bytesPerCell)
 {
+    s->ctx->curLevel = level;
     const Level &L = s->lv[level];
     if (L.nChunksActive == 0) return GMG_OK;
     VecArgs v;
@@ -1309,7 +1443,7 @@ static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, con
     return GMG_OK;
 }
 
-static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useInitialGuess)
+static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useInitialGuess)
 {
     const int nl = s->levels;
     // level 0 works on the caller's grid and the level's alternate; two Jacobi sweeps per level bring the
@@ -1349,6 +1483,43 @@ static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useIniti
     return GMG_OK;
 }
 
+// Replays `body` (a fixed sequence of kernel launches on the context's stream) from a cached CUDA graph.
+template <typename Body>
+static int runGraphed(gmg_solver *s, int kind, const void *p0, const void *p1, int flag, const Body &body)
+{
+    gmg_ctx *ctx = s->ctx;
+    if (!s->useGraphs || ctx->profiling) return body(); // per-launch events cannot live inside a graph
+    auto key = std::make_tuple(kind, p0, p1, flag);
+    auto it = s->graphs.find(key);
+    if (it == s->graphs.end())
+    {
+	if (s->graphs.size() >= 16)
+	{
+	    for (auto &g : s->graphs) { cudaGraphExecDestroy(g.second.exec); cudaGraphDestroy(g.second.graph); }
+	    s->graphs.clear();
+	}
+	gmg_solver::GraphEntry e;
+	const int64_t before = ctx->launches;
+	GMG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+	const int st = body();
+	cudaError_t ce = cudaStreamEndCapture(ctx->stream, &e.graph);
+	if (st != GMG_OK) { if (e.graph) cudaGraphDestroy(e.graph); return st; }
+	GMG_CUDA(ce);
+	e.kernels = ctx->launches - before;
+	ctx->launches = before;
+	GMG_CUDA(cudaGraphInstantiate(&e.exec, e.graph, 0));
+	it = s->graphs.emplace(key, e).first;
+    }
+    GMG_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
+    ctx->launches += it->second.kernels;
+    return GMG_OK;
+}
+
+static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useInitialGuess)
+{
+    return runGraphed(s, 0, x, b, useInitialGuess ? 1 : 0, [&]() { return vcycleLaunches(s, x, b, useInitialGuess); });
+}
+
 // ====================================================================================================
 // PCG (CG.h:11-207)
 // ====================================================================================================
@@ -1383,25 +1554,35 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
     if (precond) GMG_TRY(vcycleDevice(s, p, r, false));
     else GMG_TRY((launchVec<VO_COPY>(s, 0, p, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
     GMG_TRY((launchVec<VO_DOT>(s, 0, p, r, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, rho)), KC_REDUCE, 16.0)));
-    int iteration = 0;
-    for (; iteration < maxIt; ++iteration)
-    {
-	// t = A p fused with p.t (CG.h:104-126)
+    // Reference loop (CG.h:100-195): [t = A p, alpha, x += alpha p, r -= alpha t, |r|^2, test] then
+    // [z = M^-1 r, beta, p = z + beta p].  Re-bracketed here as: first [apply, update]; then per iteration one
+    // graph {V-cycle, z.r, direction, apply (+p.Ap), update (+|r|^2)} and one scalar read-back for the test.
+    auto applyUpdate = [&]() -> int {
 	GMG_TRY(launchStencil(s, 0, SM_APPLY, p, nullptr, t, scalarPtr(s, offsetof(Scalars, pAp))));
-	// x += alpha p ; r -= alpha t ; |r|^2 (CG.h:128-157)
 	GMG_TRY((launchVec<VO_CG_UPDATE>(s, 0, x, p, t, r, 0, scalarPtr(s, offsetof(Scalars, rr)), KC_BLAS1, 48.0)));
-	GMG_TRY(readScalar(s, offsetof(Scalars, rr), &rr));
-	if (hist && histCount && *histCount < histCap) hist[(*histCount)++] = std::sqrt(rr / bb);
-	if (rr < threshold) break;
-	// z = M^-1 r ; beta = z.r / rho ; p = z + beta p (CG.h:164-195)
-	if (precond) GMG_TRY(vcycleDevice(s, z, r, false));
+	return GMG_OK;
+    };
+    auto iterationBody = [&]() -> int {
+	if (precond) GMG_TRY(vcycleLaunches(s, z, r, false));
 	else GMG_TRY((launchVec<VO_COPY>(s, 0, z, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
 	GMG_TRY((launchVec<VO_DOT>(s, 0, z, r, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, rhoNew)), KC_REDUCE, 16.0)));
 	GMG_TRY((launchVec<VO_CG_DIRECTION>(s, 0, p, z, nullptr, nullptr, 0, nullptr, KC_BLAS1, 24.0)));
 	{
+	    s->ctx->curLevel = 0;
 	    GMG_LAUNCH(ctx, KC_BLAS1, 0);
 	    k_shift_rho<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<Scalars *>(ctx->scalars));
 	}
+	return applyUpdate();
+    };
+    GMG_TRY(runGraphed(s, 1, x, nullptr, 0, applyUpdate));
+    int iteration = 0;
+    for (;;)
+    {
+	GMG_TRY(readScalar(s, offsetof(Scalars, rr), &rr));
+	if (hist && histCount && *histCount < histCap) hist[(*histCount)++] = std::sqrt(rr / bb);
+	if (rr < threshold) break;
+	if (++iteration >= maxIt) break; // CG.h:198 then prints maxIterations
+	GMG_TRY(runGraphed(s, 2, x, nullptr, precond ? 1 : 0, iterationBody));
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     if (iterations) *iterations = iteration;
@@ -1414,7 +1595,7 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 extern "C" int gmg_grid_create(gmg_solver *s, int level, gmg_grid **out)
 {
     if (!s || !out || level < 0 || level >= s->levels) return invalid("gmg_grid_create: bad argument");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     gmg_grid *g = new gmg_grid;
     g->solver = s;
     g->level = level;
@@ -1426,22 +1607,22 @@ extern "C" int gmg_grid_create(gmg_solver *s, int level, gmg_grid **out)
 extern "C" int gmg_grid_destroy(gmg_grid *g)
 {
     if (!g) return GMG_OK;
-    cudaStreamSynchronize(g->solver->ctx->stream);
-    cudaFree(g->d);
+    enterCtx(g->solver->ctx);
+    devFree(g->d);
     delete g;
     return GMG_OK;
 }
 extern "C" int gmg_grid_upload(gmg_grid *g, const double *host)
 {
     if (!g || !host) return invalid("null argument");
-    GMG_CUDA(cudaSetDevice(g->solver->ctx->device));
+    GMG_CUDA(enterCtx(g->solver->ctx));
     const Geom &ge = g->solver->lv[g->level].g;
     return uploadValues(g->solver->ctx, g->d, host, ge.res, ge, g->solver->lv[g->level].labels);
 }
 extern "C" int gmg_grid_download(gmg_grid *g, double *host)
 {
     if (!g || !host) return invalid("null argument");
-    GMG_CUDA(cudaSetDevice(g->solver->ctx->device));
+    GMG_CUDA(enterCtx(g->solver->ctx));
     const Geom &ge = g->solver->lv[g->level].g;
     return downloadValues(g->solver->ctx, host, g->d, ge.res, ge, true);
 }
@@ -1465,23 +1646,23 @@ extern "C" int gmg_grid_copy(gmg_grid *dst, const gmg_grid *src)
 extern "C" int gmg_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b)
 {
     CHECK_GRIDS2(s, x, b);
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     Level &L = s->lv[x->level];
     GMG_TRY(launchStencil(s, x->level, SM_JACOBI, x->d, b->d, L.xAlt, nullptr));
-    std::swap(x->d, L.xAlt); // the out-of-place result becomes the caller's grid
-    return GMG_OK;
+    // copy back rather than swap pointers: cached V-cycle graphs hold the level's xAlt address
+    return launchVec<VO_COPY>(s, x->level, x->d, L.xAlt, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0);
 }
 extern "C" int gmg_boundary_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int sweeps)
 {
     CHECK_GRIDS2(s, x, b);
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return launchBand(s, x->level, x->d, b->d, sweeps, false);
 }
 extern "C" int gmg_apply(gmg_solver *s, gmg_grid *dst, const gmg_grid *src)
 {
     CHECK_GRIDS2(s, dst, src);
     if (dst == src) return invalid("gmg_apply: dst must differ from src");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return launchStencil(s, dst->level, SM_APPLY, src->d, nullptr, dst->d, nullptr);
 }
 extern "C" int gmg_residual(gmg_solver *s, gmg_grid *r, const gmg_grid *x, const gmg_grid *b)
@@ -1489,61 +1670,61 @@ extern "C" int gmg_residual(gmg_solver *s, gmg_grid *r, const gmg_grid *x, const
     CHECK_GRIDS2(s, r, x);
     CHECK_GRIDS2(s, r, b);
     if (r == x) return invalid("gmg_residual: r must differ from x");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return launchStencil(s, r->level, SM_RESIDUAL, x->d, b->d, r->d, nullptr);
 }
 extern "C" int gmg_restrict(gmg_solver *s, gmg_grid *coarse, const gmg_grid *fine)
 {
     if (!s || !coarse || !fine || coarse->solver != s || fine->solver != s || coarse->level != fine->level + 1)
 	return invalid("gmg_restrict: coarse must be one level above fine");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return launchRestrict(s, fine->level, coarse->d, fine->d);
 }
 extern "C" int gmg_prolong_add(gmg_solver *s, gmg_grid *fine, const gmg_grid *coarse)
 {
     if (!s || !coarse || !fine || coarse->solver != s || fine->solver != s || coarse->level != fine->level + 1)
 	return invalid("gmg_prolong_add: coarse must be one level above fine");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return launchProlong(s, fine->level, fine->d, coarse->d);
 }
 extern "C" int gmg_dot(gmg_solver *s, const gmg_grid *a, const gmg_grid *b, double *out)
 {
     CHECK_GRIDS2(s, a, b);
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY((launchVec<VO_DOT>(s, a->level, a->d, b->d, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, tmp)), KC_REDUCE, 16.0)));
     return readScalar(s, offsetof(Scalars, tmp), out);
 }
 extern "C" int gmg_norm2(gmg_solver *s, const gmg_grid *a, double *out)
 {
     CHECK_GRIDS2(s, a, a);
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY((launchVec<VO_NORM2>(s, a->level, a->d, nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, tmp)), KC_REDUCE, 8.0)));
     return readScalar(s, offsetof(Scalars, tmp), out);
 }
 extern "C" int gmg_inf_norm(gmg_solver *s, const gmg_grid *a, double *out)
 {
     CHECK_GRIDS2(s, a, a);
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY((launchVec<VO_MAX>(s, a->level, a->d, nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, tmp)), KC_REDUCE, 8.0)));
     return readScalar(s, offsetof(Scalars, tmp), out);
 }
 extern "C" int gmg_axpy(gmg_solver *s, gmg_grid *dst, const gmg_grid *src, double scale)
 {
     CHECK_GRIDS2(s, dst, src);
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return launchVec<VO_AXPY>(s, dst->level, dst->d, src->d, nullptr, nullptr, scale, nullptr, KC_BLAS1, 24.0);
 }
 extern "C" int gmg_add_scaled(gmg_solver *s, gmg_grid *dst, const gmg_grid *a, const gmg_grid *v, double scale)
 {
     CHECK_GRIDS2(s, dst, a);
     CHECK_GRIDS2(s, dst, v);
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return launchVec<VO_ADD_SCALED>(s, dst->level, dst->d, a->d, v->d, nullptr, scale, nullptr, KC_BLAS1, 24.0);
 }
 extern "C" int gmg_scale(gmg_solver *s, gmg_grid *v, double scale)
 {
     CHECK_GRIDS2(s, v, v);
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return launchVec<VO_SCALE>(s, v->level, v->d, nullptr, nullptr, nullptr, scale, nullptr, KC_BLAS1, 16.0);
 }
 
@@ -1551,7 +1732,7 @@ extern "C" int gmg_vcycle_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, 
 {
     CHECK_GRIDS2(s, x, b);
     if (x->level != 0) return invalid("gmg_vcycle_device: grids must be level 0");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return vcycleDevice(s, x->d, b->d, useInitialGuess != 0);
 }
 extern "C" int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, double tol, int maxIt, int preconditioner, int *iterations,
@@ -1559,7 +1740,7 @@ extern "C" int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, dou
 {
     CHECK_GRIDS2(s, x, b);
     if (x->level != 0) return invalid("gmg_pcg_device: grids must be level 0");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     return pcgDevice(s, x->d, b->d, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount);
 }
 
@@ -1574,7 +1755,7 @@ static int ensureHostIO(gmg_solver *s)
 extern "C" int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInitialGuess)
 {
     if (!s || !x || !b) return invalid("gmg_vcycle: null argument");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY(ensureHostIO(s));
     const Geom &g = s->lv[0].g;
     if (useInitialGuess) GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels));
@@ -1588,7 +1769,7 @@ extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, in
 		       int histCap, int *histCount)
 {
     if (!s || !x || !b) return invalid("gmg_pcg: null argument");
-    GMG_CUDA(cudaSetDevice(s->ctx->device));
+    GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY(ensureHostIO(s));
     const Geom &g = s->lv[0].g;
     GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels));

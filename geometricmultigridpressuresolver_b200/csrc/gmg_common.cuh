@@ -12,7 +12,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/gmg_b200.h"
@@ -81,6 +83,7 @@ struct Level
 struct ProfileRec
 {
     int klass;
+    int level;
     double bytes;
     cudaEvent_t e0, e1;
 };
@@ -96,9 +99,11 @@ struct gmg_ctx
     bool profiling = false;
     std::vector<gmg::ProfileRec> recs;
     std::vector<cudaEvent_t> eventPool;
-    double classMs[gmg::KC_COUNT] = {0};
-    int64_t classLaunches[gmg::KC_COUNT] = {0};
-    double classBytes[gmg::KC_COUNT] = {0};
+    // [0] = all levels, [1] = launches on level 0 only (the fine level, where the roofline is quoted)
+    double classMs[2][gmg::KC_COUNT] = {{0}};
+    int64_t classLaunches[2][gmg::KC_COUNT] = {{0}};
+    double classBytes[2][gmg::KC_COUNT] = {{0}};
+    int curLevel = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int smCount = 148;
     // sharding (z-slabs); world == 1 means single GPU
@@ -110,6 +115,10 @@ struct gmg_ctx
     double *scalars = nullptr;    // device scalars (see Scalars)
     double *hostScalars = nullptr; // pinned mirror
     int maxPartials = 0;
+    // pinned double buffer for host<->device box transfers
+    void *pin[2] = {nullptr, nullptr};
+    size_t pinCap = 0;
+    cudaEvent_t pinEv[2] = {nullptr, nullptr};
 };
 
 struct gmg_solver
@@ -125,6 +134,16 @@ struct gmg_solver
     // PCG work grids (level 0)
     double *pcgR = nullptr, *pcgP = nullptr, *pcgZ = nullptr, *pcgT = nullptr, *pcgX = nullptr, *pcgB = nullptr;
     double setupMs = 0;
+    // CUDA-graph cache: a V-cycle is ~100 dependent launches, most of them on tiny coarse levels, so the
+    // launch sequence is captured once per (kind, x, b, flag) and replayed
+    struct GraphEntry
+    {
+	cudaGraph_t graph = nullptr;
+	cudaGraphExec_t exec = nullptr;
+	int64_t kernels = 0;
+    };
+    std::map<std::tuple<int, const void *, const void *, int>, GraphEntry> graphs;
+    bool useGraphs = true;
 };
 
 struct gmg_grid

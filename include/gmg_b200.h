@@ -164,11 +164,12 @@ int gmg_launch_count(gmg_ctx *ctx, int64_t *count, int reset);
 int gmg_timer_begin(gmg_ctx *ctx);
 int gmg_timer_end(gmg_ctx *ctx, double *ms);
 /* accumulated device time (ms) and launches per kernel class since the last reset; classes are listed by
- * gmg_kernel_class_name(i), i in [0, gmg_kernel_class_count()).  Only collected when enabled (adds events). */
+ * gmg_kernel_class_name(i), i in [0, gmg_kernel_class_count()).  Only collected when enabled (adds events).
+ * fineLevelOnly != 0 restricts the sums to launches on level 0, where the HBM roofline is quoted. */
 int gmg_profile_enable(gmg_ctx *ctx, int on);
 int gmg_kernel_class_count(void);
 const char *gmg_kernel_class_name(int i);
-int gmg_profile_get(gmg_ctx *ctx, int klass, double *ms, int64_t *launches, double *algorithmicBytes);
+int gmg_profile_get(gmg_ctx *ctx, int klass, int fineLevelOnly, double *ms, int64_t *launches, double *algorithmicBytes);
 int gmg_profile_reset(gmg_ctx *ctx);
 
 #ifdef __cplusplus

@@ -1,0 +1,212 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (include/gmg_b200.h via the ctypes mirror), against
+(a) the fixtures the compiled reference produced and (b) the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): labels and boundary lists bit-exact; per-iteration residual history within
+1e-5 relative; iteration count within +-1; final pressure within 1e-5 relative L-inf.  The kernels keep the
+reference's operation order, so the asserts below are far tighter than those bars (TOL_*)."""
+import numpy as np
+import pytest
+
+from geometricmultigridpressuresolver_b200 import api
+from geometricmultigridpressuresolver_b200 import domains as D
+from tests.common import CASES, FULL_CASES, base_inputs, crop, load_golden, relerr, rhs_for, sha
+
+pytestmark = pytest.mark.gpu
+
+TOL_OP = 1e-12       # single operator vs reference, relative L-inf
+TOL_HISTORY = 1e-8   # residual history, relative per iteration (bar: 1e-5)
+TOL_X = 1e-9         # final pressure, relative L-inf (bar: 1e-5)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_labels_and_boundary_lists_bit_exact(gpu_ctx, name):
+    g = load_golden(name)
+    bl, bw, dx = base_inputs(name)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    assert levels == int(g["mg_levels"]) and (off == g["offset"]).all()
+    assert sha(labels.astype(np.int32)) == str(g["labels_sha"])
+    assert "".join(sha(a) for a in w) == str(g["weights_sha"])
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    assert s.getMGLevels() == int(g["solver_levels"])
+    for l in range(s.getMGLevels()):
+        ll, cells = s.level_labels(l), s.level_boundary_cells(l)
+        assert sha(ll.astype(np.int32)) == str(g[f"labels_sha_L{l}"])
+        assert len(cells) == int(g[f"cells_count_L{l}"])
+        assert sha(cells.astype(np.int64)) == str(g[f"cells_sha_L{l}"])
+    # stand-alone builders (buildCoarseCellLabels / buildBoundaryCells on host arrays)
+    if "labels_L1" in g:
+        assert (gpu_ctx.buildCoarseCellLabels(labels) == g["labels_L1"]).all()
+        assert (gpu_ctx.buildBoundaryCells(labels, 3) == g["cells_L0"]).all()
+    s.close()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_pcg(gpu_ctx, name):
+    g = load_golden(name)
+    bl, bw, dx = base_inputs(name)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    b = rhs_for(labels, off, bl.shape, dx)
+    assert sha(b) == str(g["rhs_sha"])
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    x, iters, hist = s.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 1000)
+    assert abs(iters - int(g["pcg_iterations"])) <= 1 and iters == int(g["pcg_iterations"])
+    assert (np.abs(hist - g["pcg_history"]) / g["pcg_history"]).max() < TOL_HISTORY
+    xc = crop(x, off, bl.shape)
+    gold = g["pcg_x"]
+    if gold.shape != xc.shape:
+        xc = xc[::4, ::4, ::4]
+    assert relerr(xc, gold) < TOL_X
+    assert not x[~D.active_mask(labels)].any()
+    s.close()
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_golden_vcycle_and_operators(gpu_ctx, name):
+    g = load_golden(name)
+    bl, bw, dx = base_inputs(name)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    c = lambda a: crop(a, off, bl.shape)
+    rb = D.random_rhs(labels, dx, seed=7)
+    assert relerr(c(s.applyVCycle(np.zeros_like(rb), rb)), g["vcycle_x"]) < TOL_OP
+    x0 = D.random_active(labels, 11, scale=dx * dx)
+    assert relerr(c(s.applyVCycle(x0, rb, True)), g["vcycle_guess_x"]) < TOL_OP
+    xs, bs = D.random_active(labels, 1), D.random_active(labels, 2)
+    X, B, R = s.grid(0, xs), s.grid(0, bs), s.grid(0)
+    s.jacobiPoissonSmoother(X, B)
+    assert relerr(c(X.download()), g["op_jacobi"]) < TOL_OP
+    X.upload(xs)
+    s.boundaryJacobiPoissonSmoother(X, B, 3)
+    assert relerr(c(X.download()), g["op_band3"]) < TOL_OP
+    X.upload(xs)
+    s.applyPoissonMatrix(R, X)
+    assert relerr(c(R.download()), g["op_apply"]) < TOL_OP
+    s.computePoissonResidual(R, X, B)
+    assert relerr(c(R.download()), g["op_residual"]) < TOL_OP
+    assert abs(s.dotProduct(X, B) - float(g["op_dot"])) < 1e-11 * float(g["op_norm2"])
+    assert abs(s.squaredL2Norm(X) - float(g["op_norm2"])) < 1e-12 * float(g["op_norm2"])
+    assert s.infNorm(X) == float(g["op_inf_norm"])
+    if s.getMGLevels() > 1:
+        l1 = s.level_labels(1)
+        C1 = s.grid(1)
+        s.downsample(C1, X)
+        assert relerr(C1.download(), g["op_downsample"]) < TOL_OP
+        xc1, b1 = D.random_active(l1, 3), D.random_active(l1, 4)
+        C1.upload(xc1)
+        s.upsampleAndAdd(X, C1)
+        assert relerr(c(X.download()), g["op_upsample"]) < TOL_OP
+        B1 = s.grid(1, b1)
+        s.jacobiPoissonSmoother(C1, B1)
+        assert relerr(C1.download(), g["op_jacobi_L1"]) < TOL_OP
+        C1.upload(xc1)
+        s.boundaryJacobiPoissonSmoother(C1, B1, 3)
+        assert relerr(C1.download(), g["op_band3_L1"]) < TOL_OP
+    s.close()
+
+
+# ---- against the CPU oracle on the BASELINE configs that fit a test (SURVEY.md 8d configs 1, 2 and small 3/4/5) ----
+ORACLE_CASES = [("sphere", 64, {}), ("sphere", 128, {}), ("flipsplash", 96, {"shape": (96, 64, 96)}), ("liquid_box", 64, {}),
+                ("narrow_band", 96, {}), ("complex", 64, {}), ("simple", 48, {})]
+
+
+@pytest.mark.parametrize("dom,n,kw", ORACLE_CASES)
+def test_oracle_parity_full_solve(gpu_ctx, port, dom, n, kw):
+    bl, bw, dx = D.DOMAINS[dom](n, **kw)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    pl, pw, poff, plv = port.expand_domain(bl, bw)
+    assert levels == plv and (labels == pl).all() and all((w[a] == pw[a]).all() for a in range(3))
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    ps = port.solver(pl, pw, plv, False)
+    assert s.getMGLevels() == ps.levels and s.coarse_unknowns() == ps.coarse_unknowns
+    for l in range(ps.levels):
+        assert (s.level_labels(l) == ps.level_labels(l)).all()
+        gc, pc = s.level_boundary_cells(l), ps.level_boundary_cells(l)
+        assert gc.shape == pc.shape and (gc == pc).all()
+    b = rhs_for(labels, off, bl.shape, dx)
+    x, it, hist = s.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 1000)
+    xo, ito, histo = ps.pcg(np.zeros_like(b), b, 1e-6, 1000)
+    assert abs(it - ito) <= 1 and it == ito
+    assert (np.abs(hist - histo) / histo).max() < TOL_HISTORY
+    assert relerr(x, xo) < TOL_X
+    # warm start (production passes the old pressure, GFS.cpp:408-418)
+    x2, it2, hist2 = s.solveGeometricConjugateGradient(0.5 * xo, b, 1e-6, 1000)
+    xo2, ito2, histo2 = ps.pcg(0.5 * xo, b, 1e-6, 1000)
+    assert it2 == ito2 and (np.abs(hist2 - histo2) / histo2).max() < 1e-6 and relerr(x2, xo2) < TOL_X
+    s.close()
+
+
+def test_early_outs_and_errors(gpu_ctx):
+    bl, bw, dx = D.sphere_domain(24)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    zero = np.zeros(labels.shape)
+    x, it, hist = s.solveGeometricConjugateGradient(zero, zero, 1e-6, 10)  # "RHS is zero" (CG.h:35-40)
+    assert it == -1 and len(hist) == 0 and not x.any()
+    b = rhs_for(labels, off, bl.shape, dx)
+    xs, it, hist = s.solveGeometricConjugateGradient(zero, b, 1e-10, 1000)
+    x2, it2, hist2 = s.solveGeometricConjugateGradient(xs, b, 1e-6, 1000)  # "Residual already below error" (CG.h:60-64)
+    assert it2 == -1 and len(hist2) == 0 and (x2 == xs).all()
+    x3, it3, hist3 = s.solveGeometricConjugateGradient(zero, b, 1e-12, 3)  # iteration cap: CG.h:198 prints maxIterations
+    assert it3 == 3 and len(hist3) == 3
+    with pytest.raises(api.GmgError):  # odd resolution (MG.cpp:155-157)
+        api.GeometricMultigridPoissonSolver(gpu_ctx, labels[:-1], [w[0][:-1], w[1][:-1], w[2][:-1]], levels)
+    with pytest.raises(api.GmgError):  # Gauss-Seidel mode is a later row
+        api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels, useGaussSeidel=True)
+    # pure-Neumann box: singular coarse matrix is reported, not silently "solved"
+    box = np.full((16, 16, 16), D.EXTERIOR, dtype=np.int32)
+    box[1:-1, 1:-1, 1:-1] = D.INTERIOR
+    wbox = []
+    for axis in range(3):
+        ww = np.zeros(D.face_shape(box.shape, axis))
+        sl = [slice(1, -1)] * 3
+        sl[2 - axis] = slice(2, -2)
+        ww[tuple(sl)] = 1.0
+        wbox.append(ww)
+    el, ew, eo, elv = gpu_ctx.buildExpandedDomain(box, wbox)
+    with pytest.raises(api.GmgError) as e:
+        api.GeometricMultigridPoissonSolver(gpu_ctx, el, ew, elv)
+    assert e.value.status == 5
+    s.close()
+
+
+def test_diagonal_free_plain_cg_matches_oracle_operators(gpu_ctx, port):
+    """preconditioner = 0 runs plain CG on the same kernels; cross-check with numpy CG over oracle operators."""
+    bl, bw, dx = D.complex_domain(24)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    b = D.random_rhs(labels, dx, 3)
+    cap = 40  # unpreconditioned CG drifts chaotically over hundreds of iterations; compare a bounded prefix
+    x, it, hist = s.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, cap, useMGPreconditioner=False)
+    xr = np.zeros_like(b)
+    r = b.copy()
+    p = r.copy()
+    rho = port.dot(p, r, labels)
+    bb = port.norm2(b, labels)
+    hist_o = []
+    for k in range(cap):
+        t = port.apply(p, labels, w)
+        alpha = rho / port.dot(p, t, labels)
+        xr = port.axpy(xr, p, alpha, labels)
+        r = port.axpy(r, t, -alpha, labels)
+        rr = port.norm2(r, labels)
+        hist_o.append(np.sqrt(rr / bb))
+        if rr < 1e-12 * bb:
+            break
+        rho_new = port.dot(r, r, labels)
+        p = port.add_scaled(r, p, rho_new / rho, labels)
+        rho = rho_new
+    assert it == cap and len(hist) == len(hist_o) == cap
+    assert (np.abs(hist - np.array(hist_o)) / np.array(hist_o)).max() < 1e-6
+    assert relerr(x, xr) < 1e-8
+    s.close()
+
+
+def test_coarse_matrix_scale_quirk(gpu_ctx, port):
+    bl, bw, dx = D.sphere_domain(20)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    b = D.random_rhs(labels, dx, 5)
+    s3 = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels, coarse_matrix_scale=3.0)
+    v3 = s3.applyVCycle(np.zeros_like(b), b)
+    vo = port.solver(labels, w, levels, False, coarse_scale=3.0).vcycle(np.zeros_like(b), b)
+    assert relerr(v3, vo) < 1e-11
+    s3.close()

@@ -1,0 +1,144 @@
+"""GPU (-m gpu): size-independent properties at the BASELINE sizes the CPU oracle is too slow for, plus the
+reference's own symmetry battery (Test.cpp:1171-1875) re-run on the GPU operators."""
+import numpy as np
+import pytest
+
+from geometricmultigridpressuresolver_b200 import api
+from geometricmultigridpressuresolver_b200 import domains as D
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def flip256(gpu_ctx):
+    bl, bw, dx = D.flipsplash_domain(256)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    hi = [int(off[a]) + 256 for a in range(3)]
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels, box=(off, hi))
+    yield dict(s=s, labels=labels, dx=dx, off=off, levels=levels)
+    s.close()
+
+
+def _rand_grid(s, labels, seed, level=0):
+    return s.grid(level, D.random_active(labels, seed))
+
+
+def test_config3_256_pcg_converges_and_true_residual(flip256):
+    s, labels, dx = flip256["s"], flip256["labels"], flip256["dx"]
+    assert labels.shape == (512, 512, 512) and flip256["levels"] == 7
+    b = D.random_rhs(labels, dx, 12345)
+    B, X, R = s.grid(0, b), s.grid(0), s.grid(0)
+    it, hist = s.solveDevice(X, B, 1e-6, 1000)
+    assert 0 < it < 60 and hist[-1] < 1e-6 and (len(hist) == it + 1)
+    s.computePoissonResidual(R, X, B)
+    true_rel = np.sqrt(s.squaredL2Norm(R) / s.squaredL2Norm(B))
+    assert true_rel < 1.05e-6 and abs(true_rel - hist[-1]) < 1e-3 * hist[-1] + 1e-9  # drifted vs recomputed (CG.h:198-206)
+    x = X.download()
+    assert not x[~D.active_mask(labels)].any()  # vector-grid invariant survives the whole solve
+
+
+def test_vcycle_is_symmetric(flip256):
+    """u.M v == v.M u for the Jacobi V-cycle (Test.cpp:1808-1841 runs 4 V-cycles; one is enough in fp64)."""
+    s, labels = flip256["s"], flip256["labels"]
+    U, V, MU, MV = _rand_grid(s, labels, 21), _rand_grid(s, labels, 22), s.grid(0), s.grid(0)
+    s.applyVCycleDevice(MU, U)
+    s.applyVCycleDevice(MV, V)
+    a, b = s.dotProduct(V, MU), s.dotProduct(U, MV)
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+    assert np.float32(a) == np.float32(b) or abs(a - b) <= 1e-7 * abs(a)  # the reference's own criterion (float-rounded dots)
+
+
+def test_smoother_sequence_is_symmetric(flip256):
+    """bJ + J + bJ from a zero guess is a symmetric operator (Test.cpp:1197-1226)."""
+    s, labels = flip256["s"], flip256["labels"]
+    outs = []
+    ins = [_rand_grid(s, labels, 31), _rand_grid(s, labels, 32)]
+    for B in ins:
+        X = s.grid(0)
+        s.boundaryJacobiPoissonSmoother(X, B, 3)
+        s.jacobiPoissonSmoother(X, B)
+        s.boundaryJacobiPoissonSmoother(X, B, 3)
+        outs.append(X)
+    a, b = s.dotProduct(ins[1], outs[0]), s.dotProduct(ins[0], outs[1])
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+
+
+def test_restriction_is_the_scaled_adjoint_of_prolongation(flip256):
+    """<P v, u>_fine = 32 <v, R u>_coarse: P = 4*trilinear, R = (1,3,3,1)^3/512 (Ops.h:741, :960-966; Test.cpp:1521-1562)."""
+    s, labels = flip256["s"], flip256["labels"]
+    l1 = s.level_labels(1)
+    U, V = _rand_grid(s, labels, 41), _rand_grid(s, l1, 42, level=1)
+    RU, PV = s.grid(1), s.grid(0)
+    s.downsample(RU, U)
+    s.upsampleAndAdd(PV, V)
+    a, b = s.dotProduct(PV, U), 32.0 * s.dotProduct(V, RU)
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
+
+
+def test_operator_is_symmetric_positive_and_linear(flip256):
+    s, labels = flip256["s"], flip256["labels"]
+    U, V, AU, AV, W = _rand_grid(s, labels, 51), _rand_grid(s, labels, 52), s.grid(0), s.grid(0), s.grid(0)
+    s.applyPoissonMatrix(AU, U)
+    s.applyPoissonMatrix(AV, V)
+    a, b = s.dotProduct(V, AU), s.dotProduct(U, AV)
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
+    assert s.dotProduct(U, AU) > 0
+    # A(u + 2v) = Au + 2Av
+    s.addVectors(W, U, V, 2.0)
+    AW, S = s.grid(0), s.grid(0)
+    s.applyPoissonMatrix(AW, W)
+    s.addVectors(S, AU, AV, 2.0)
+    s.addToVector(S, AW, -1.0)
+    assert np.sqrt(s.squaredL2Norm(S)) <= 1e-12 * np.sqrt(s.squaredL2Norm(AW))
+    # residual(x, b) == b - A x
+    s.computePoissonResidual(S, U, V)
+    s.addToVector(S, V, -1.0)
+    s.addToVector(S, AU, 1.0)
+    assert np.sqrt(s.squaredL2Norm(S)) <= 1e-12 * np.sqrt(s.squaredL2Norm(AU))
+
+
+def test_labels_obey_the_reference_invariants_at_every_level(flip256, port):
+    """unitTestCoarsening / unitTestBoundaryCells / unitTestExteriorCells (MG.cpp:233-252) on GPU-built labels."""
+    s = flip256["s"]
+    prev = None
+    for l in range(s.getMGLevels()):
+        ll = s.level_labels(l)
+        if ll.size <= 256 ** 3:  # the dense CPU checkers are run where they finish in seconds
+            assert port.unit_test_exterior_cells(ll)
+            assert port.unit_test_boundary_cells(ll)
+            if prev is not None and prev.size <= 256 ** 3:
+                assert port.unit_test_coarsening(ll, prev)
+            cells = s.level_boundary_cells(l)
+            ref_cells = port.boundary_cells(ll, 3)
+            assert cells.shape == ref_cells.shape and (cells == ref_cells).all()
+        prev = ll
+
+
+def test_band_sweeps_only_touch_the_band(flip256):
+    s, labels = flip256["s"], flip256["labels"]
+    x = D.random_active(labels, 61)
+    X, B = s.grid(0, x), _rand_grid(s, labels, 62)
+    s.boundaryJacobiPoissonSmoother(X, B, 3)
+    y = X.download()
+    cells = s.level_boundary_cells(0)
+    mask = np.zeros(labels.shape, dtype=bool)
+    mask[cells[:, 2], cells[:, 1], cells[:, 0]] = True
+    assert (y[~mask] == x[~mask]).all() and (y[mask] != x[mask]).any()
+
+
+def test_config4_liquid_box_vcycle_contracts(gpu_ctx):
+    """V-cycle as a stationary iteration on b = 0 from a sinusoid guess shrinks the error (Test.cpp:1877-1960)."""
+    n = 128
+    bl, bw, dx = D.liquid_box_domain(n)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    k, j, i = np.meshgrid(*[np.arange(m, dtype=np.float64) for m in labels.shape], indexing="ij", sparse=True)
+    x0 = np.sin(2 * np.pi * dx * i) * np.sin(2 * np.pi * dx * j) * np.sin(2 * np.pi * dx * k) * D.active_mask(labels)
+    X, B = s.grid(0, x0), s.grid(0)
+    norms = [s.l2Norm(X)]
+    for _ in range(6):
+        s.applyVCycleDevice(X, B, useInitialGuess=True)
+        norms.append(s.l2Norm(X))
+    ratios = np.array(norms[1:]) / np.array(norms[:-1])
+    assert (ratios < 0.5).all(), ratios
+    s.close()
