@@ -57,6 +57,7 @@ class SolverOptions(C.Structure):
         ("coarse_matrix_scale", C.c_double),
         ("box_lo", C.c_int64 * 3),
         ("box_hi", C.c_int64 * 3),
+        ("operators_only", C.c_int),
     ]
 
 

@@ -1058,7 +1058,8 @@ extern "C" int gmg_solver_destroy(gmg_solver *s)
 extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], const double *w0, const double *w1, const double *w2,
 				 int mgLevels, const gmg_solver_options *optIn, gmg_solver **out)
 {
-    if (!ctx || !labels || !res || !w0 || !w1 || !w2 || !out) return invalid("gmg_solver_create: null argument");
+    if (!ctx || !labels || !res || !out) return invalid("gmg_solver_create: null argument");
+    if ((w0 || w1 || w2) && !(w0 && w1 && w2)) return invalid("gmg_solver_create: pass all three weight grids or none");
     if (mgLevels < 1) return invalid("gmg_solver_create: mgLevels must be >= 1");
     for (int a = 0; a < 3; ++a)
     {
@@ -1103,7 +1104,8 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	if (L0.g.total >= (int64_t(1) << 31)) return fail(invalid("gmg_solver_create: cropped box exceeds 2^31 cells"));
 	if ((st = (devMalloc(&L0.labels, L0.g.total) == cudaSuccess ? GMG_OK : GMG_ERR_CUDA)) != GMG_OK) return fail(st);
 	if ((st = uploadLabels(ctx, L0.labels, labels, res, L0.g)) != GMG_OK) return fail(st);
-	if ((st = uploadWeights(ctx, dW, w0, w1, w2, res, L0.g)) != GMG_OK) return fail(st);
+	// no weight grids = the reference's boundaryWeights == nullptr form (weight 1 to active/DIRICHLET neighbours, Ops.h:237-248)
+	if (w0 && (st = uploadWeights(ctx, dW, w0, w1, w2, res, L0.g)) != GMG_OK) return fail(st);
     }
     lap("upload labels + weights");
     // coarse labels (MG.cpp:238-253) with the reference's level cap: a level without active cells drops it AND the one before
@@ -1162,7 +1164,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     for (int a = 0; a < 3; ++a) devFree(dW[a]);
     lap("bands, records, chunks, grids");
     if ((st = ensureScratch(ctx, maxGrid)) != GMG_OK) return fail(st);
-    if ((st = buildCoarseSolve(s)) != GMG_OK) return fail(st);
+    if (!s->opt.operators_only && (st = buildCoarseSolve(s)) != GMG_OK) return fail(st);
     lap("coarse direct solver");
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     s->setupMs = nowMs() - tStart;
@@ -1517,6 +1519,7 @@ static int runGraphed(gmg_solver *s, int kind, const void *p0, const void *p1, i
 
 static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useInitialGuess)
 {
+    if (s->opt.operators_only && s->levels > 1) return invalid("this solver handle was created with operators_only: no coarse factor, no V-cycle");
     return runGraphed(s, 0, x, b, useInitialGuess ? 1 : 0, [&]() { return vcycleLaunches(s, x, b, useInitialGuess); });
 }
 

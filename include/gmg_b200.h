@@ -94,11 +94,14 @@ typedef struct gmg_solver_options
     double coarse_matrix_scale; /* 1 = intended algorithm.  J reproduces the reference run with J UT_ThreadedAlgorithm jobs,
 				   whose unsplit assembly loop (MG.cpp:334-389) sums every triplet J times. */
     int64_t box_lo[3], box_hi[3]; /* optional non-EXTERIOR bounds hint (all zero = scan the labels) */
+    int operators_only;       /* 1: build labels/bands/records only, no coarse factor -- a handle for the stateless operator
+				 functions of the facade (gmg_vcycle / gmg_pcg with the V-cycle then fail with GMG_ERR_INVALID) */
 } gmg_solver_options;
 void gmg_solver_default_options(gmg_solver_options *opt);
 
 /* GeometricMultigridPoissonSolver::GeometricMultigridPoissonSolver, HDK_GeometricMultigridPoissonSolver.cpp:135-418.
- * Deep-copies labels and weights to the device, builds per-level labels, boundary bands and the coarse factor. */
+ * Deep-copies labels and weights to the device, builds per-level labels, boundary bands and the coarse factor.
+ * w0 = w1 = w2 = NULL is the reference's `boundaryWeights == nullptr` operator form (weight 1, Ops.h:237-248). */
 int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], const double *w0, const double *w1,
 		      const double *w2, int mgLevels, const gmg_solver_options *opt, gmg_solver **out);
 int gmg_solver_destroy(gmg_solver *s);

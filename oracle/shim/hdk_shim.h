@@ -348,6 +348,7 @@ public:
 	if (!myData) { if (v == myConst) return; uncompress(); }
 	myData[(lz * myRes[1] + ly) * myRes[0] + lx] = v;
     }
+    T operator()(int lx, int ly, int lz) const { return get(lx, ly, lz); } // HDK: UT_VoxelTile::operator()(x, y, z)
     T constantValue() const { return myConst; }
     T *rawData() { return myData; }
     const T *rawData() const { return myData; }
