@@ -1042,6 +1042,8 @@ static int buildCoarseSolve(gmg_solver *s)
     return GMG_OK;
 }
 
+static int buildFusedCycle(gmg_solver *s);
+
 extern "C" int gmg_solver_destroy(gmg_solver *s)
 {
     if (!s) return GMG_OK;
@@ -1049,7 +1051,7 @@ extern "C" int gmg_solver_destroy(gmg_solver *s)
     cudaStreamSynchronize(s->ctx->stream);
     for (auto &g : s->graphs) { cudaGraphExecDestroy(g.second.exec); cudaGraphDestroy(g.second.graph); }
     for (auto &L : s->lv) freeLevel(L);
-    devFree(s->coarseIdx); devFree(s->coarseInv);
+    devFree(s->coarseIdx); devFree(s->coarseInv); devFree(s->devLevels);
     devFree(s->pcgR); devFree(s->pcgP); devFree(s->pcgZ); devFree(s->pcgT); devFree(s->pcgX); devFree(s->pcgB);
     delete s;
     return GMG_OK;
@@ -1165,6 +1167,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     lap("bands, records, chunks, grids");
     if ((st = ensureScratch(ctx, maxGrid)) != GMG_OK) return fail(st);
     if (!s->opt.operators_only && (st = buildCoarseSolve(s)) != GMG_OK) return fail(st);
+    if ((st = buildFusedCycle(s)) != GMG_OK) return fail(st);
     lap("coarse direct solver");
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     s->setupMs = nowMs() - tStart;
@@ -1234,6 +1237,8 @@ static StencilArgs stencilArgs(gmg_solver *s, int level, const double *in, const
     a.pitch = L.g.pitch;
     a.plane = L.g.plane;
     a.nz = L.g.n[2];
+    a.zlo = 0;
+    a.zhi = L.g.n[2];
     a.nBoundary = L.nBoundary;
     a.bandIdx = L.bandIdx;
     a.bcoef = L.bcoef;
@@ -1339,6 +1344,7 @@ static TransferArgs transferArgs(gmg_solver *s, int fineLevel)
     a.coarseNy = C.g.n[1];
     for (int k = 0; k < 3; ++k) a.shift[k] = F.shift[k];
     a.fine = nullptr; a.coarse = nullptr; a.out = nullptr; a.chunks = nullptr; a.chunksPerPlane = 0;
+    a.zlo = 0; a.zhi = 0;
     return a;
 }
 
@@ -1352,6 +1358,8 @@ static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const do
     a.out = coarse;
     a.chunks = C.chunksActive;
     a.chunksPerPlane = C.g.chunksPerPlane;
+    a.zlo = 0;
+    a.zhi = C.g.n[2];
     GMG_LAUNCH(s->ctx, KC_RESTRICT, double(s->lv[fineLevel].nActive) * 8.0 + double(C.nActive) * 9.0);
     k_restrict<<<C.nChunksActive, BLOCK, 0, s->ctx->stream>>>(a);
     GMG_CUDA(cudaGetLastError());
@@ -1368,6 +1376,8 @@ static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const doubl
     a.out = fine;
     a.chunks = F.chunksActive;
     a.chunksPerPlane = F.g.chunksPerPlane;
+    a.zlo = 0;
+    a.zhi = F.g.n[2];
     GMG_LAUNCH(s->ctx, KC_PROLONG, double(F.nActive) * 17.0 + double(s->lv[fineLevel + 1].nActive) * 8.0);
     k_prolong<<<F.nChunksActive, BLOCK, 0, s->ctx->stream>>>(a);
     GMG_CUDA(cudaGetLastError());
@@ -1395,6 +1405,72 @@ static int launchCoarse(gmg_solver *s, double *x, const double *b)
     return GMG_OK;
 }
 
+// levels [fusedFirst, levels-1] in one persistent cluster kernel (gmg_kernels.cuh: k_coarse_cycle)
+static int buildFusedCycle(gmg_solver *s)
+{
+    s->fusedFirst = -1;
+    const char *e = getenv("GMG_COARSE_FUSED");
+    if (e && e[0] == '0') return GMG_OK;
+    if (s->opt.operators_only || s->levels < 3) return GMG_OK;
+    int64_t limit = 200000;
+    if (const char *c = getenv("GMG_FUSED_CELLS")) limit = atoll(c);
+    int first = -1;
+    for (int l = 1; l < s->levels - 1; ++l)
+	if (s->lv[l].nActive <= limit) { first = l; break; }
+    if (first < 0) return GMG_OK;
+    s->clusterSize = 8;
+    if (const char *c = getenv("GMG_CLUSTER")) s->clusterSize = std::max(1, std::min(16, atoi(c)));
+    if (s->clusterSize > 8) GMG_CUDA(cudaFuncSetAttribute(k_coarse_cycle, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    std::vector<DevLevel> h(s->levels);
+    for (int l = 0; l < s->levels; ++l)
+    {
+	const Level &L = s->lv[l];
+	DevLevel &d = h[l];
+	d.labels = L.labels; d.x = L.x; d.xAlt = L.xAlt; d.b = L.b; d.r = L.r;
+	d.chunksInterior = L.chunksInterior; d.chunksActive = L.chunksActive;
+	d.nChunksInterior = L.nChunksInterior; d.nChunksActive = L.nChunksActive;
+	d.chunksPerPlane = L.g.chunksPerPlane; d.pitch = L.g.pitch; d.ny = L.g.n[1]; d.nz = L.g.n[2]; d.plane = L.g.plane;
+	d.nBoundary = L.nBoundary; d.nBand = L.nBand; d.bandIdx = L.bandIdx; d.bandNbr = L.bandNbr; d.bcoef = L.bcoef;
+	d.bandV0 = L.bandV0; d.bandV1 = L.bandV1; d.bandB = L.bandB;
+	for (int k = 0; k < 3; ++k) d.shift[k] = L.shift[k];
+    }
+    GMG_CUDA(devMalloc(&s->devLevels, sizeof(DevLevel) * s->levels));
+    GMG_CUDA(cudaMemcpyAsync(s->devLevels, h.data(), sizeof(DevLevel) * s->levels, cudaMemcpyHostToDevice, s->ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    s->fusedFirst = first;
+    return GMG_OK;
+}
+
+static int launchCoarseCycle(gmg_solver *s)
+{
+    s->ctx->curLevel = s->fusedFirst;
+    CycleArgs c;
+    c.lv = reinterpret_cast<const DevLevel *>(s->devLevels);
+    c.first = s->fusedFirst;
+    c.last = s->levels - 1;
+    c.bandSweeps = s->opt.boundary_iterations;
+    c.coarseIdx = s->coarseIdx;
+    c.coarseInv = s->coarseInv;
+    c.nCoarse = s->nCoarse;
+    double bytes = 0;
+    for (int l = c.first; l < c.last; ++l) bytes += double(s->lv[l].nActive) * 126.0;
+    GMG_LAUNCH(s->ctx, KC_COARSE, bytes);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(s->clusterSize));
+    cfg.blockDim = dim3(CYCLE_THREADS);
+    cfg.dynamicSmemBytes = sizeof(double) * size_t(s->nCoarse);
+    cfg.stream = s->ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(s->clusterSize);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GMG_CUDA(cudaLaunchKernelEx(&cfg, k_coarse_cycle, c));
+    return GMG_OK;
+}
+
 template <int OP>
 static int launchVec(gmg_solver *s, int level, double *y, const double *a, const double *c, double *y2, double sc, double *result, int klass,
 		     double bytesPerCell)
@@ -1407,6 +1483,8 @@ static int launchVec(gmg_solver *s, int level, double *y, const double *a, const
     v.chunksPerPlane = L.g.chunksPerPlane;
     v.plane = L.g.plane;
     v.nz = L.g.n[2];
+    v.zlo = 0;
+    v.zhi = L.g.n[2];
     v.y = y;
     v.a = a;
     v.c = c;
@@ -1461,7 +1539,9 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
     GMG_TRY(launchStencil(s, 0, SM_RESIDUAL, cur0, b, s->lv[0].r, nullptr));
     GMG_TRY(launchRestrict(s, 0, s->lv[1].b, s->lv[0].r));
     std::vector<double *> cur(nl), alt(nl);
-    for (int level = 1; level < nl - 1; ++level)
+    // levels [fusedFirst, nl-1] run inside the persistent cluster kernel; its result is lv[fusedFirst].x
+    const int nReg = (s->fusedFirst > 0) ? s->fusedFirst : nl - 1;  // regular levels are 1 .. nReg-1
+    for (int level = 1; level < nReg; ++level)
     {
 	Level &L = s->lv[level];
 	cur[level] = L.x;
@@ -1471,14 +1551,16 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
 	GMG_TRY(launchStencil(s, level, SM_RESIDUAL, cur[level], L.b, L.r, nullptr));
 	GMG_TRY(launchRestrict(s, level, s->lv[level + 1].b, L.r));
     }
-    GMG_TRY(launchCoarse(s, s->lv[nl - 1].x, s->lv[nl - 1].b));
-    for (int level = nl - 2; level >= 1; --level)
+    if (s->fusedFirst > 0) GMG_TRY(launchCoarseCycle(s));
+    else GMG_TRY(launchCoarse(s, s->lv[nl - 1].x, s->lv[nl - 1].b));
+    for (int level = nReg - 1; level >= 1; --level)
     {
 	Level &L = s->lv[level];
-	GMG_TRY(launchProlong(s, level, cur[level], level + 1 == nl - 1 ? s->lv[nl - 1].x : cur[level + 1]));
+	// the level below hands over its result in its own x grid (two Jacobi swaps, or the direct solve / fused cycle)
+	GMG_TRY(launchProlong(s, level, cur[level], s->lv[level + 1].x));
 	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, false));
     }
-    GMG_TRY(launchProlong(s, 0, cur0, nl == 2 ? s->lv[1].x : cur[1]));
+    GMG_TRY(launchProlong(s, 0, cur0, s->lv[1].x));
     GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, false));
     // cur0 == x again after the second swap
     if (cur0 != x) GMG_TRY((launchVec<VO_COPY>(s, 0, x, cur0, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));

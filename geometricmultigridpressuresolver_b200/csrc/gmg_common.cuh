@@ -131,6 +131,10 @@ struct gmg_solver
     int nCoarse = 0;
     int32_t *coarseIdx = nullptr; // [nCoarse] storage index at the coarsest level
     double *coarseInv = nullptr;  // [nCoarse][nCoarse] row-major inverse
+    // persistent coarse sub-V-cycle: levels [fusedFirst, levels-1] in one cluster kernel (-1 = off)
+    int fusedFirst = -1;
+    int clusterSize = 8;
+    void *devLevels = nullptr;    // DevLevel[levels]
     // PCG work grids (level 0)
     double *pcgR = nullptr, *pcgP = nullptr, *pcgZ = nullptr, *pcgT = nullptr, *pcgX = nullptr, *pcgB = nullptr;
     double setupMs = 0;

@@ -8,10 +8,13 @@
 // reductions with warp shuffles.
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include "gmg_common.cuh"
 
 namespace gmg
 {
+namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
@@ -118,6 +121,7 @@ struct StencilArgs
     int pitch;
     int64_t plane;
     int nz;
+    int zlo, zhi;       // z-plane clip [zlo, zhi): planes outside are left untouched (deep-halo sharding)
     // boundary records
     int nBoundary;
     const int32_t *bandIdx;
@@ -138,15 +142,17 @@ __device__ __forceinline__ double stencilFinish(double lap, double centre, doubl
     return centre + (2.0 / 3.0) * r;
 }
 
+// vb = virtual CTA index (blockIdx.x of the stand-alone kernel, a strided index inside the persistent coarse-cycle kernel),
+// tid = thread index inside the BLOCK-wide virtual CTA.  Returns this thread's part of dot(in, A in) when DOT.
 template <int MODE, bool DOT>
-__global__ void __launch_bounds__(BLOCK) k_stencil(const StencilArgs a)
+__device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int tid)
 {
     double acc = 0.0;
-    if (blockIdx.x < a.nChunks)
+    if (vb < a.nChunks)
     {
-	const int c = a.chunks[blockIdx.x];
+	const int c = a.chunks[vb];
 	const int zb = c / a.chunksPerPlane;
-	const int64_t inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * threadIdx.x;
+	const int64_t inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * tid;
 	if (inPlane < a.plane)
 	{
 	    const int z0 = zb * CHUNK_Z;
@@ -154,7 +160,8 @@ __global__ void __launch_bounds__(BLOCK) k_stencil(const StencilArgs a)
 	    for (int dz = 0; dz < CHUNK_Z; ++dz)
 	    {
 		const int z = z0 + dz;
-		if (z >= a.nz) break;
+		if (z >= a.zhi) break;
+		if (z < a.zlo) continue;
 		const int64_t i = int64_t(z) * a.plane + inPlane;
 		const uchar2 l = *reinterpret_cast<const uchar2 *>(a.labels + i);
 		const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
@@ -182,10 +189,11 @@ __global__ void __launch_bounds__(BLOCK) k_stencil(const StencilArgs a)
     }
     else
     {
-	const int k = (blockIdx.x - a.nChunks) * BLOCK + threadIdx.x;
-	if (k < a.nBoundary)
+	const int k = (vb - a.nChunks) * BLOCK + tid;
+	const int64_t i = k < a.nBoundary ? int64_t(a.bandIdx[k]) : 0;
+	const int z = int(i / a.plane);
+	if (k < a.nBoundary && z >= a.zlo && z < a.zhi)
 	{
-	    const int64_t i = a.bandIdx[k];
 	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
 	    const double centre = a.in[i];
 	    double lap = 0.0;
@@ -202,6 +210,13 @@ __global__ void __launch_bounds__(BLOCK) k_stencil(const StencilArgs a)
 	    if (DOT) acc += centre * lap;
 	}
     }
+    return acc;
+}
+
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(BLOCK) k_stencil(const StencilArgs a)
+{
+    const double acc = stencilBody<MODE, DOT>(a, blockIdx.x, threadIdx.x);
     if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
 }
 
@@ -230,9 +245,9 @@ struct BandArgs
 // FROM_COMPACT: centre/band-neighbour values come from vin; TO_GRID: result goes to x[idx];
 // FIRST: rhs is gathered from the grid and cached in bandB; ZERO: the grid is known to be all zero.
 template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO>
-__global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
+__device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 {
-    const int k = blockIdx.x * BLOCK + threadIdx.x;
+    const int k = vb * BLOCK + tid;
     if (k >= a.nBand) return;
     const int64_t i = a.bandIdx[k];
     double rhs;
@@ -265,6 +280,11 @@ __global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
     if (TO_GRID) a.x[i] = v;
     else a.vout[k] = v;
 }
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO>
+__global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
+{
+    bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO>(a, blockIdx.x, threadIdx.x);
+}
 
 __global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t *bandIdx, const double *v, int nBand)
 {
@@ -288,23 +308,25 @@ struct TransferArgs
     int64_t finePlane, coarsePlane;
     int fineNz, coarseNz, coarseNy;
     int shift[3];
+    int zlo, zhi;  // clip on the destination's z-planes (coarse planes for restriction, fine planes for prolongation)
 };
 
-__global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a)
+__device__ __forceinline__ void restrictBody(const TransferArgs &a, int vb, int tid)
 {
     const double rw[4] = {1. / 8., 3. / 8., 3. / 8., 1. / 8.};
-    const int c = a.chunks[blockIdx.x];
+    const int c = a.chunks[vb];
     const int zb = c / a.chunksPerPlane;
     const int64_t base = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS;
 #pragma unroll 1
     for (int dz = 0; dz < CHUNK_Z; ++dz)
     {
 	const int cz = zb * CHUNK_Z + dz;
-	if (cz >= a.coarseNz) break;
+	if (cz >= a.zhi) break;
+	if (cz < a.zlo) continue;
 #pragma unroll 1
 	for (int h = 0; h < 2; ++h)
 	{
-	    const int64_t inPlane = base + h * BLOCK + threadIdx.x;
+	    const int64_t inPlane = base + h * BLOCK + tid;
 	    if (inPlane >= a.coarsePlane) continue;
 	    const int64_t ci = int64_t(cz) * a.coarsePlane + inPlane;
 	    const int l = a.coarseLabels[ci];
@@ -332,6 +354,7 @@ __global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a)
 	}
     }
 }
+__global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a) { restrictBody(a, blockIdx.x, threadIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
 // Prolongation (Ops.h:873-972): fine (active) += 4 * trilerp(8 coarse cells), fractions .25/.75.
@@ -339,11 +362,11 @@ __global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double lerpRef(double v0, double v1, double f) { return (1. - f) * v0 + f * v1; }  // Ops.h:841-848
 
-__global__ void __launch_bounds__(BLOCK) k_prolong(const TransferArgs a)
+__device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int tid)
 {
-    const int c = a.chunks[blockIdx.x];
+    const int c = a.chunks[vb];
     const int zb = c / a.chunksPerPlane;
-    const int64_t inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * threadIdx.x;
+    const int64_t inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * tid;
     if (inPlane >= a.finePlane) return;
     const int fy = int(inPlane / a.finePitch), fx = int(inPlane - int64_t(fy) * a.finePitch);
     const int mx = (fx >> 1) + a.shift[0];
@@ -354,7 +377,8 @@ __global__ void __launch_bounds__(BLOCK) k_prolong(const TransferArgs a)
     for (int dz = 0; dz < CHUNK_Z; ++dz)
     {
 	const int fz = zb * CHUNK_Z + dz;
-	if (fz >= a.fineNz) break;
+	if (fz >= a.zhi) break;
+	if (fz < a.zlo) continue;
 	const int64_t i = int64_t(fz) * a.finePlane + inPlane;
 	const uchar2 l = *reinterpret_cast<const uchar2 *>(a.fineLabels + i);
 	const bool a0 = (l.x == L_INTERIOR || l.x == L_BOUNDARY), a1 = (l.y == L_INTERIOR || l.y == L_BOUNDARY);
@@ -385,6 +409,7 @@ __global__ void __launch_bounds__(BLOCK) k_prolong(const TransferArgs a)
 	else a.out[i + 1] = n1;
     }
 }
+__global__ void __launch_bounds__(BLOCK) k_prolong(const TransferArgs a) { prolongBody(a, blockIdx.x, threadIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
 // Coarsest level (MG.cpp:669-692): gather b, x = A^-1 b (dense inverse of the SPD matrix, built on the
@@ -415,6 +440,7 @@ struct VecArgs
     int chunksPerPlane;
     int64_t plane;
     int nz;
+    int zlo, zhi;       // z-plane clip [zlo, zhi)
     double *y;          // destination / first operand
     const double *a;    // second operand
     const double *c;    // third operand
@@ -455,7 +481,8 @@ __global__ void __launch_bounds__(BLOCK) k_vec(const VecArgs v)
 	for (int dz = 0; dz < CHUNK_Z; ++dz)
 	{
 	    const int z = zb * CHUNK_Z + dz;
-	    if (z >= v.nz) break;
+	    if (z >= v.zhi) break;
+	    if (z < v.zlo) continue;
 	    const int64_t i = int64_t(z) * v.plane + inPlane;
 	    if (OP == VO_AXPY)
 	    {
@@ -515,11 +542,11 @@ __global__ void __launch_bounds__(BLOCK) k_vec(const VecArgs v)
 }
 
 // zero the active chunks of a grid (x = 0 at the start of a V-cycle level, MG.cpp:439-440, :566)
-__global__ void __launch_bounds__(BLOCK) k_zero(double *y, const int32_t *chunks, int chunksPerPlane, int64_t plane, int nz)
+__device__ __forceinline__ void zeroBody(double *y, const int32_t *chunks, int chunksPerPlane, int64_t plane, int nz, int vb, int tid)
 {
-    const int c = chunks[blockIdx.x];
+    const int c = chunks[vb];
     const int zb = c / chunksPerPlane;
-    const int64_t inPlane = int64_t(c - zb * chunksPerPlane) * CHUNK_CELLS + 2 * threadIdx.x;
+    const int64_t inPlane = int64_t(c - zb * chunksPerPlane) * CHUNK_CELLS + 2 * tid;
     if (inPlane >= plane) return;
 #pragma unroll
     for (int dz = 0; dz < CHUNK_Z; ++dz)
@@ -527,6 +554,173 @@ __global__ void __launch_bounds__(BLOCK) k_zero(double *y, const int32_t *chunks
 	const int z = zb * CHUNK_Z + dz;
 	if (z >= nz) break;
 	st2(y + int64_t(z) * plane + inPlane, make_double2(0.0, 0.0));
+    }
+}
+__global__ void __launch_bounds__(BLOCK) k_zero(double *y, const int32_t *chunks, int chunksPerPlane, int64_t plane, int nz)
+{
+    zeroBody(y, chunks, chunksPerPlane, plane, nz, blockIdx.x, threadIdx.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent coarse sub-V-cycle.  Below a few hundred thousand cells a level is pure launch latency
+// (19 dependent launches of ~3 us each), so levels [first, last] -- down-stroke, direct solve, up-stroke --
+// run inside ONE kernel: a single thread-block cluster whose CTAs walk the same virtual-CTA bodies as
+// the stand-alone kernels and meet at the hardware cluster barrier (release/acquire at cluster scope,
+// which orders the global-memory traffic between the steps) instead of at kernel boundaries.
+// Same arithmetic, same order as the per-kernel path: results are bitwise identical.
+// ------------------------------------------------------------------------------------------------
+constexpr int CYCLE_THREADS = 1024;
+
+struct DevLevel
+{
+    const uint8_t *labels;
+    double *x, *xAlt, *b, *r;
+    const int32_t *chunksInterior, *chunksActive;
+    int nChunksInterior, nChunksActive;
+    int chunksPerPlane, pitch, ny, nz;
+    int64_t plane;
+    int nBoundary, nBand;
+    const int32_t *bandIdx, *bandNbr;
+    const double *bcoef;
+    double *bandV0, *bandV1, *bandB;
+    int shift[3];
+};
+
+struct CycleArgs
+{
+    const DevLevel *lv;  // device array indexed by level
+    int first, last;     // `last` is the direct-solve level
+    int bandSweeps;
+    const int32_t *coarseIdx;
+    const double *coarseInv;
+    int nCoarse;
+};
+
+template <typename F>
+__device__ __forceinline__ void forVirtualCtas(int nvb, const F &f)
+{
+    constexpr int PER = CYCLE_THREADS / BLOCK;
+    const int sub = threadIdx.x / BLOCK, tid = threadIdx.x % BLOCK;
+    for (int vb = blockIdx.x * PER + sub; vb < nvb; vb += gridDim.x * PER) f(vb, tid);
+}
+
+__device__ __forceinline__ void cycleSync() { cg::this_cluster().sync(); }
+
+__device__ __forceinline__ StencilArgs devStencilArgs(const DevLevel &L, const double *in, const double *b, double *out)
+{
+    StencilArgs a;
+    a.labels = L.labels; a.in = in; a.b = b; a.out = out;
+    a.chunks = L.chunksInterior; a.nChunks = L.nChunksInterior; a.chunksPerPlane = L.chunksPerPlane;
+    a.pitch = L.pitch; a.plane = L.plane; a.nz = L.nz; a.zlo = 0; a.zhi = L.nz;
+    a.nBoundary = L.nBoundary; a.bandIdx = L.bandIdx; a.bcoef = L.bcoef;
+    a.partials = nullptr; a.ticket = nullptr; a.result = nullptr;
+    return a;
+}
+
+// `sweeps` band sweeps on grid x, ending on a cluster barrier (mirrors launchBand on the host)
+__device__ __forceinline__ void cycleBand(const DevLevel &L, double *x, const double *b, int sweeps, bool zeroGrid)
+{
+    if (L.nBand == 0 || sweeps <= 0) return;
+    BandArgs a;
+    a.x = x; a.b = b; a.bandIdx = L.bandIdx; a.bandNbr = L.bandNbr; a.bcoef = L.bcoef; a.bandB = L.bandB;
+    a.nBoundary = L.nBoundary; a.nBand = L.nBand; a.pitch = L.pitch; a.plane = L.plane;
+    const int nvb = (L.nBand + BLOCK - 1) / BLOCK;
+    double *cur = L.bandV0, *nxt = L.bandV1;
+    a.vin = nullptr;
+    a.vout = cur;
+    if (zeroGrid) forVirtualCtas(nvb, [&](int vb, int tid) { bandBody<false, false, true, true>(a, vb, tid); });
+    else forVirtualCtas(nvb, [&](int vb, int tid) { bandBody<false, false, true, false>(a, vb, tid); });
+    cycleSync();
+    if (sweeps == 1)
+    {
+	forVirtualCtas(nvb, [&](int vb, int tid) { const int k = vb * BLOCK + tid; if (k < L.nBand) x[L.bandIdx[k]] = cur[k]; });
+	cycleSync();
+	return;
+    }
+    for (int sw = 2; sw <= sweeps; ++sw)
+    {
+	a.vin = cur;
+	a.vout = nxt;
+	if (sw == sweeps) forVirtualCtas(nvb, [&](int vb, int tid) { bandBody<true, true, false, false>(a, vb, tid); });
+	else forVirtualCtas(nvb, [&](int vb, int tid) { bandBody<true, false, false, false>(a, vb, tid); });
+	cycleSync();
+	double *t = cur; cur = nxt; nxt = t;
+    }
+}
+
+// band sweeps, interior Jacobi cur -> alt, band sweeps on alt (MG.cpp:557-667 / :695-784); the result is in alt
+__device__ __forceinline__ void cycleSmooth(const DevLevel &L, double *cur, double *alt, int sweeps, bool zeroGrid)
+{
+    cycleBand(L, cur, L.b, sweeps, zeroGrid);
+    const StencilArgs a = devStencilArgs(L, cur, L.b, alt);
+    forVirtualCtas(L.nChunksInterior + (L.nBoundary + BLOCK - 1) / BLOCK, [&](int vb, int tid) { stencilBody<SM_JACOBI, false>(a, vb, tid); });
+    cycleSync();
+    cycleBand(L, alt, L.b, sweeps, false);
+}
+
+__device__ __forceinline__ TransferArgs devTransferArgs(const DevLevel &F, const DevLevel &C)
+{
+    TransferArgs a;
+    a.fineLabels = F.labels; a.coarseLabels = C.labels;
+    a.finePitch = F.pitch; a.coarsePitch = C.pitch; a.finePlane = F.plane; a.coarsePlane = C.plane;
+    a.fineNz = F.nz; a.coarseNz = C.nz; a.coarseNy = C.ny;
+    a.shift[0] = F.shift[0]; a.shift[1] = F.shift[1]; a.shift[2] = F.shift[2];
+    a.fine = nullptr; a.coarse = nullptr; a.out = nullptr; a.chunks = nullptr; a.chunksPerPlane = 0; a.zlo = 0; a.zhi = 0;
+    return a;
+}
+
+__global__ void __launch_bounds__(CYCLE_THREADS, 1) k_coarse_cycle(const CycleArgs c)
+{
+    extern __shared__ double sb[];
+    // ---- down-stroke
+    for (int l = c.first; l < c.last; ++l)
+    {
+	const DevLevel &L = c.lv[l];
+	const DevLevel &C = c.lv[l + 1];
+	forVirtualCtas(L.nChunksActive, [&](int vb, int tid) { zeroBody(L.x, L.chunksActive, L.chunksPerPlane, L.plane, L.nz, vb, tid); });
+	cycleSync();
+	cycleSmooth(L, L.x, L.xAlt, c.bandSweeps, true);
+	{
+	    const StencilArgs a = devStencilArgs(L, L.xAlt, L.b, L.r);
+	    forVirtualCtas(L.nChunksInterior + (L.nBoundary + BLOCK - 1) / BLOCK, [&](int vb, int tid) { stencilBody<SM_RESIDUAL, false>(a, vb, tid); });
+	}
+	cycleSync();
+	{
+	    TransferArgs a = devTransferArgs(L, C);
+	    a.fine = L.r; a.out = C.b; a.chunks = C.chunksActive; a.chunksPerPlane = C.chunksPerPlane; a.zlo = 0; a.zhi = C.nz;
+	    forVirtualCtas(C.nChunksActive, [&](int vb, int tid) { restrictBody(a, vb, tid); });
+	}
+	cycleSync();
+    }
+    // ---- direct solve on the coarsest level: x = A^-1 b
+    {
+	const DevLevel &L = c.lv[c.last];
+	const int n = c.nCoarse;
+	for (int i = threadIdx.x; i < n; i += CYCLE_THREADS) sb[i] = L.b[c.coarseIdx[i]];
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	for (int row = blockIdx.x * (CYCLE_THREADS / 32) + (threadIdx.x >> 5); row < n; row += gridDim.x * (CYCLE_THREADS / 32))
+	{
+	    const double *r = c.coarseInv + int64_t(row) * n;
+	    double acc = 0.0;
+	    for (int j = lane; j < n; j += 32) acc += r[j] * sb[j];
+	    acc = warpSum(acc);
+	    if (lane == 0) L.x[c.coarseIdx[row]] = acc;
+	}
+	cycleSync();
+    }
+    // ---- up-stroke: x_l (in xAlt after the down-stroke) += P x_{l+1}; smooth back into x
+    for (int l = c.last - 1; l >= c.first; --l)
+    {
+	const DevLevel &L = c.lv[l];
+	const DevLevel &C = c.lv[l + 1];
+	{
+	    TransferArgs a = devTransferArgs(L, C);
+	    a.coarse = C.x; a.out = L.xAlt; a.chunks = L.chunksActive; a.chunksPerPlane = L.chunksPerPlane; a.zlo = 0; a.zhi = L.nz;
+	    forVirtualCtas(L.nChunksActive, [&](int vb, int tid) { prolongBody(a, vb, tid); });
+	}
+	cycleSync();
+	cycleSmooth(L, L.xAlt, L.x, c.bandSweeps, false);
     }
 }
 
