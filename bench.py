@@ -176,6 +176,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     ctx = api.Context(local_rank)
+    if dist is not None:
+        ctx.shard_with_torch(dist)  # z-slabs over the ranks: NCCL halo planes + scalar all-reduces inside the library
     n = args.size
     base_labels, base_w, dx = build_inputs(n)
     labels, w, off, levels = ctx.buildExpandedDomain(base_labels, base_w)
@@ -215,6 +217,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     barrier()
     wall_s = time.perf_counter() - t_wall0
     launches = ctx.launch_count()
+    comm_ops = ctx.comm_count()
     clocks = sampler.stop()
     ms_per_step = float(np.mean(step_ms))
     if dist is not None:
@@ -262,9 +265,9 @@ def run_gpu_arm(args, rank, world, local_rank):
                    "fine_level_gbs": (prof_fine[k][2] / (prof_fine[k][0] * 1e-3) / 1e9) if prof_fine[k][0] > 0 and prof_fine[k][2] > 0 else None}
                for k, v in solve_classes.items()}
 
-    # ---- e2e: host buffers through the reference-facing calls --------------------------------------------
+    # ---- e2e: host buffers through the reference-facing calls (every rank takes part; max over ranks) ------
     e2e = None
-    if rank == 0:
+    if True:
         xb = torch.zeros(labels.shape, dtype=torch.float64).pin_memory()
         bb = torch.from_numpy(b_host).pin_memory()
         x_np, b_np = xb.numpy(), bb.numpy()
@@ -283,7 +286,20 @@ def run_gpu_arm(args, rank, world, local_rank):
         box_cells = int(np.prod([hi[a] - int(off[a]) + 4 for a in range(3)]))
         h2d = box_cells * (4 + 3 * 8) + 2 * box_cells * 8  # labels + 3 weight grids at construction, rhs + x0 per solve
         d2h = box_cells * 8
-        e2e = {"value": float(np.mean(e2e_ms)), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e_val = float(np.mean(e2e_ms))
+        if dist is not None:
+            t = torch.tensor([e2e_val], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_val = float(t.item())
+            sh, zlo, zhi, _ = solver.shard_info(0)
+            if sh:  # per rank: its slab of the weights / rhs / x0 (+ the replicated one-byte labels); summed over the ranks below
+                frac = (zhi - zlo + 20) / float(hi[2] - int(off[2]) + 4)
+                h2d = int(box_cells * 4 + box_cells * frac * (3 * 8 + 2 * 8))
+                d2h = int(box_cells * 8 * (zhi - zlo) / float(hi[2] - int(off[2]) + 4))
+            t = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t)
+            h2d, d2h = int(t[0].item()), int(t[1].item())
+        e2e = {"value": e2e_val, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "setup_ms": float(np.mean(e2e_setup)), "iterations": int(it2), "what": "gmg_solver_create + gmg_pcg (pinned host rhs/x) + gmg_solver_destroy"}
 
     cpu = None
@@ -299,14 +315,15 @@ def run_gpu_arm(args, rank, world, local_rank):
             "metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n), "levels": solver.getMGLevels(), "active_cells": active, "l2": "256 MB flush write before every timed step",
-                       "parallelism": "single GPU" if world == 1 else f"{world} replicas (z-slab sharding not built yet)"},
+                       "parallelism": "single GPU" if world == 1 else
+                       f"{world} z-slabs over NCCL, levels 0..{sum(1 for l in range(solver.getMGLevels()) if solver.shard_info(l)[0]) - 1} sharded with deep halos, coarser levels replicated"},
             "iterations": int(it), "final_rel_residual": float(hist[-1]), "setup_ms": solver.setup_ms(),
             "vcycle_ms": vcycle_ms, "vcycle_algorithmic_gbs": vcycle_bytes / (vcycle_ms * 1e-3) / 1e9,
             "vcycle_frac_of_hbm_peak": vcycle_bytes / (vcycle_ms * 1e-3) / 1e9 / peak,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "launches": d_n, "avg_launch_us": d_ms / d_n * 1e3,
                          "algorithmic_bytes_per_launch": d_bytes / d_n},
-            "kernels": kernels, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "wall_s_timed_region": wall_s,
+            "kernels": kernels, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "wall_s_timed_region": wall_s,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -31,7 +31,7 @@ STATUS = {0: "GMG_OK", 1: "GMG_ERR_CUDA", 2: "GMG_ERR_INVALID", 3: "GMG_ERR_NO_A
 
 # every symbol include/gmg_b200.h declares (tests/test_abi.py checks the header against this and the .so)
 ABI_SYMBOLS = [
-    "gmg_last_error", "gmg_version", "gmg_ctx_create", "gmg_ctx_destroy", "gmg_ctx_synchronize", "gmg_ctx_shard", "gmg_nccl_unique_id",
+    "gmg_last_error", "gmg_version", "gmg_ctx_create", "gmg_ctx_destroy", "gmg_ctx_synchronize", "gmg_ctx_shard", "gmg_nccl_unique_id", "gmg_ctx_rank", "gmg_shard_plan", "gmg_solver_shard_info", "gmg_comm_count",
     "gmg_expand_dims", "gmg_expand_labels", "gmg_expand_weights", "gmg_set_boundary_labels", "gmg_coarsen_labels", "gmg_boundary_cells",
     "gmg_solver_default_options", "gmg_solver_create", "gmg_solver_destroy", "gmg_solver_levels", "gmg_solver_level_res",
     "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms",
@@ -40,6 +40,18 @@ ABI_SYMBOLS = [
     "gmg_axpy", "gmg_add_scaled", "gmg_scale", "gmg_vcycle_device", "gmg_pcg_device", "gmg_launch_count", "gmg_timer_begin", "gmg_timer_end",
     "gmg_profile_enable", "gmg_kernel_class_count", "gmg_kernel_class_name", "gmg_profile_get", "gmg_profile_reset",
 ]
+
+
+def shard_plan(level_planes, level_shift_z, level_cells, world, max_shard_levels=3, min_cells=1500000):
+    """gmg_shard_plan: (number of sharded levels, cuts[level][rank] in storage planes).  Host-only, needs no GPU."""
+    lib = load_library()
+    n = len(level_planes)
+    arr = lambda v: (C.c_int64 * n)(*[int(x) for x in v])
+    cuts = (C.c_int64 * (n * (world + 1)))()
+    S = C.c_int()
+    _check(lib.gmg_shard_plan(arr(level_planes), arr(level_shift_z), arr(level_cells), n, int(world), int(max_shard_levels), C.c_int64(min_cells),
+                              C.byref(S), cuts))
+    return int(S.value), [[int(cuts[l * (world + 1) + k]) for k in range(world + 1)] for l in range(S.value)]
 
 
 class GmgError(RuntimeError):
@@ -116,9 +128,33 @@ class Context:
         _check(self.lib.gmg_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self.h = h
         self.device = device
+        self.rank, self.world = 0, 1
 
     def synchronize(self):
         _check(self.lib.gmg_ctx_synchronize(self.h))
+
+    # ---- z-slab sharding: one process per GPU, the 128-byte NCCL id travels over the caller's own channel ----
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(self.lib.gmg_nccl_unique_id(buf))
+        return buf.raw
+
+    def shard(self, rank: int, world: int, unique_id: bytes | None):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        _check(self.lib.gmg_ctx_shard(self.h, int(rank), int(world), buf))
+        self.rank, self.world = int(rank), int(world)
+
+    def shard_with_torch(self, dist):
+        """Shard over an initialised torch.distributed group: rank 0 makes the NCCL id, everyone receives it."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [self.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.shard(rank, world, box[0])
+
+    def comm_count(self) -> int:
+        n = C.c_int64()
+        _check(self.lib.gmg_comm_count(self.h, C.byref(n)))
+        return int(n.value)
 
     def launch_count(self, reset=False) -> int:
         n = C.c_int64()
@@ -310,6 +346,12 @@ class GeometricMultigridPoissonSolver:
         n = C.c_int64()
         _check(self.lib.gmg_solver_active_cells(self.h, int(level), C.byref(n)))
         return int(n.value)
+
+    def shard_info(self, level=0):
+        """(is this level a z-slab, expanded z range [lo, hi) of the owned planes, active cells stored on this rank)"""
+        sh, lo, hi, act = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+        _check(self.lib.gmg_solver_shard_info(self.h, int(level), C.byref(sh), C.byref(lo), C.byref(hi), C.byref(act)))
+        return bool(sh.value), int(lo.value), int(hi.value), int(act.value)
 
     def coarse_unknowns(self) -> int:
         n = C.c_int64()

@@ -12,7 +12,10 @@
 #include <mutex>
 #include <thread>
 
+#include <dlfcn.h>
+
 #include "gmg_kernels.cuh"
+#include "gmg_nccl.h"
 
 using namespace gmg;
 
@@ -42,7 +45,8 @@ int cudaFail(cudaError_t e, const char *what, const char *file, int line)
 }
 LaunchScope::LaunchScope(gmg_ctx *c, int k, double b) : ctx(c), klass(k), bytes(b)
 {
-    ++ctx->launches;
+    if (k == KC_HALO) ++ctx->commOps;  // NCCL operations are not this library's kernels
+    else ++ctx->launches;
     if (!ctx->profiling) return;
     auto get = [&]() {
 	cudaEvent_t e;
@@ -87,6 +91,22 @@ static cudaError_t devFree(void *p)
     if (!p) return cudaSuccess;
     if (!usePool()) return cudaFree(p);
     return cudaFreeAsync(p, g_stream);
+}
+
+// Vector grids carry one zero guard plane below and above the stored box: on a z-slab the first / last stored plane has
+// no EXTERIOR halo of its own, and the stencils of its cells reach one plane out.
+static int allocGrid(double **p, const Geom &g)
+{
+    double *base = nullptr;
+    const int64_t n = g.total + 2 * g.plane;
+    GMG_CUDA(devMalloc(&base, sizeof(double) * n));
+    GMG_CUDA(cudaMemsetAsync(base, 0, sizeof(double) * n, g_stream));
+    *p = base + g.plane;
+    return GMG_OK;
+}
+static void freeGrid(double *p, const Geom &g)
+{
+    if (p) devFree(p - g.plane);
 }
 
 #define TRACE(msg) do { if (getenv("GMG_TRACE")) { fprintf(stderr, "[gmg] %s:%d %s\n", __func__, __LINE__, msg); fflush(stderr); } } while (0)
@@ -181,6 +201,8 @@ extern "C" int gmg_ctx_destroy(gmg_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     flushProfile(ctx);
     for (auto e : ctx->eventPool) cudaEventDestroy(e);
+    if (ctx->nccl)
+	if (const NcclApi *api = ncclApi(nullptr)) api->CommDestroy(static_cast<NcclComm>(ctx->nccl));
     cudaFree(ctx->partials);
     cudaFree(ctx->ticket);
     cudaFree(ctx->scalars);
@@ -201,18 +223,111 @@ extern "C" int gmg_ctx_synchronize(gmg_ctx *ctx)
     return GMG_OK;
 }
 
-extern "C" int gmg_ctx_shard(gmg_ctx *, int, int world, const void *)
+// ---- NCCL, bound at run time (gmg_nccl.h) ----------------------------------------------------------
+namespace gmg
 {
-    if (world == 1) return GMG_OK;
-    return invalid("gmg_ctx_shard: z-slab sharding is not built in this revision");
+const NcclApi *ncclApi(const char **why)
+{
+    static NcclApi api;
+    static std::string err;
+    static std::once_flag once;
+    std::call_once(once, [] {
+	const char *names[] = {getenv("GMG_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+	for (const char *n : names)
+	{
+	    if (!n || !n[0]) continue;
+	    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+	    if (api.lib) break;
+	    err = dlerror();
+	}
+	if (!api.lib) return;
+	bool ok = true;
+	auto sym = [&](const char *name) { void *p = dlsym(api.lib, name); if (!p) { ok = false; err = std::string("missing symbol ") + name; } return p; };
+	api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+	api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+	api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+	api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+	api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+	api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+	api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+	api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+	api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+	api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+	api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+	if (!ok) { dlclose(api.lib); api.lib = nullptr; }
+    });
+    if (!api.lib) { if (why) *why = err.c_str(); return nullptr; }
+    return &api;
 }
-extern "C" int gmg_nccl_unique_id(void *) { return invalid("gmg_nccl_unique_id: z-slab sharding is not built in this revision"); }
+} // namespace gmg
+
+static int ncclFail(int r, const char *what)
+{
+    const NcclApi *api = ncclApi(nullptr);
+    char buf[512];
+    snprintf(buf, sizeof(buf), "NCCL error %d (%s) in %s", r, api ? api->GetErrorString(r) : "?", what);
+    setError(buf);
+    return GMG_ERR_COMM;
+}
+#define GMG_NCCL(call)                                        \
+    do                                                        \
+    {                                                         \
+	int _r = (call);                                      \
+	if (_r != NCCL_SUCCESS) return ncclFail(_r, #call);   \
+    } while (0)
+
+extern "C" int gmg_nccl_unique_id(void *out128)
+{
+    if (!out128) return invalid("gmg_nccl_unique_id: null argument");
+    const char *why = nullptr;
+    const NcclApi *api = ncclApi(&why);
+    if (!api) { setError(std::string("gmg_nccl_unique_id: cannot load libnccl.so.2: ") + (why ? why : "")); return GMG_ERR_COMM; }
+    GMG_NCCL(api->GetUniqueId(static_cast<NcclUniqueId *>(out128)));
+    return GMG_OK;
+}
+
+extern "C" int gmg_ctx_shard(gmg_ctx *ctx, int rank, int world, const void *ncclUniqueId)
+{
+    if (!ctx) return invalid("gmg_ctx_shard: null ctx");
+    if (world < 1 || rank < 0 || rank >= world) return invalid("gmg_ctx_shard: rank/world out of range");
+    if (ctx->nccl) return invalid("gmg_ctx_shard: context is already sharded");
+    if (world == 1) return GMG_OK;
+    if (!ncclUniqueId) return invalid("gmg_ctx_shard: null unique id");
+    const char *why = nullptr;
+    const NcclApi *api = ncclApi(&why);
+    if (!api) { setError(std::string("gmg_ctx_shard: cannot load libnccl.so.2: ") + (why ? why : "")); return GMG_ERR_COMM; }
+    GMG_CUDA(enterCtx(ctx));
+    NcclUniqueId id;
+    std::memcpy(&id, ncclUniqueId, sizeof(id));
+    NcclComm comm = nullptr;
+    GMG_NCCL(api->CommInitRank(&comm, world, id, rank));
+    ctx->nccl = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    // one tiny all-reduce now: connection setup happens outside any later stream capture
+    GMG_NCCL(api->AllReduce(ctx->scalars, ctx->scalars, 1, NCCL_FLOAT64, NCCL_SUM, comm, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
+}
+extern "C" int gmg_ctx_rank(gmg_ctx *ctx, int *rank, int *world)
+{
+    if (!ctx) return invalid("null ctx");
+    if (rank) *rank = ctx->rank;
+    if (world) *world = ctx->world;
+    return GMG_OK;
+}
 
 extern "C" int gmg_launch_count(gmg_ctx *ctx, int64_t *count, int reset)
 {
     if (!ctx) return invalid("null ctx");
     if (count) *count = ctx->launches;
-    if (reset) ctx->launches = 0;
+    if (reset) { ctx->launches = 0; ctx->commOps = 0; }
+    return GMG_OK;
+}
+extern "C" int gmg_comm_count(gmg_ctx *ctx, int64_t *count)
+{
+    if (!ctx || !count) return invalid("null argument");
+    *count = ctx->commOps;
     return GMG_OK;
 }
 extern "C" int gmg_timer_begin(gmg_ctx *ctx)
@@ -558,32 +673,38 @@ static int selectFlagged(gmg_ctx *ctx, const uint8_t *flags, int64_t n, int32_t 
 // boundary band of one level: BOUNDARY cells first, then the INTERIOR cells within width-1 steps (Ops.cpp:165-469)
 static int buildBand(gmg_ctx *ctx, Level &L, int width)
 {
+    // the band mask is grown over the level's GLOBAL box (a slab edge must not clip the dilation); the lists are
+    // compacted over the rank's stored planes and hold local storage indices
     const Geom &g = L.g;
-    const BoxArgs ba = boxArgs(g);
+    const Geom &gg = L.gg;
+    const uint8_t *labelsG = L.labelsAlloc ? L.labelsAlloc : L.labels;
+    const BoxArgs bg = boxArgs(gg);
+    const unsigned gridG = unsigned(divUp(gg.total, BLOCK));
     const unsigned grid = unsigned(divUp(g.total, BLOCK));
     uint8_t *m0 = nullptr, *m1 = nullptr;
-    GMG_CUDA(devMalloc(&m0, g.total));
-    GMG_CUDA(devMalloc(&m1, g.total));
+    GMG_CUDA(devMalloc(&m0, gg.total));
+    GMG_CUDA(devMalloc(&m1, gg.total));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_band_init<<<grid, BLOCK, 0, ctx->stream>>>(m0, L.labels, g.total);
+	k_band_init<<<gridG, BLOCK, 0, ctx->stream>>>(m0, labelsG, gg.total);
     }
     for (int layer = 0; layer < width - 1; ++layer)
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_band_dilate<<<grid, BLOCK, 0, ctx->stream>>>(m1, m0, L.labels, ba);
+	k_band_dilate<<<gridG, BLOCK, 0, ctx->stream>>>(m1, m0, labelsG, bg);
 	std::swap(m0, m1);
     }
+    const uint8_t *mLocal = m0 + int64_t(L.zOff) * g.plane;
     int32_t *idxB = nullptr, *idxI = nullptr;
     int nB = 0, nI = 0;
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_band_flags<<<grid, BLOCK, 0, ctx->stream>>>(m1, m0, L.labels, 0, g.total);
+	k_band_flags<<<grid, BLOCK, 0, ctx->stream>>>(m1, mLocal, L.labels, 0, g.total);
     }
     GMG_TRY(selectFlagged(ctx, m1, g.total, &idxB, &nB));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_band_flags<<<grid, BLOCK, 0, ctx->stream>>>(m1, m0, L.labels, 1, g.total);
+	k_band_flags<<<grid, BLOCK, 0, ctx->stream>>>(m1, mLocal, L.labels, 1, g.total);
     }
     GMG_TRY(selectFlagged(ctx, m1, g.total, &idxI, &nI));
     GMG_CUDA(devFree(m0));
@@ -603,11 +724,14 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
     GMG_CUDA(devMalloc(&L.bandB, sizeof(double) * std::max(nBand, 1)));
     if (nBand > 0)
     {
-	int32_t *pos = nullptr;
-	GMG_CUDA(devMalloc(&pos, sizeof(int32_t) * g.total));
+	// one guard plane each side: band cells of a slab's first / last stored plane look one plane out
+	int32_t *posBase = nullptr;
+	const int64_t posN = g.total + 2 * g.plane;
+	GMG_CUDA(devMalloc(&posBase, sizeof(int32_t) * posN));
+	int32_t *pos = posBase + g.plane;
 	{
 	    GMG_LAUNCH(ctx, KC_SETUP, 0);
-	    k_fill_i32<<<grid, BLOCK, 0, ctx->stream>>>(pos, -1, g.total);
+	    k_fill_i32<<<unsigned(divUp(posN, BLOCK)), BLOCK, 0, ctx->stream>>>(posBase, -1, posN);
 	}
 	{
 	    GMG_LAUNCH(ctx, KC_SETUP, 0);
@@ -618,7 +742,7 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 	    k_band_nbr<<<unsigned(divUp(nBand, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bandNbr, pos, L.bandIdx, nBand, g.pitch, g.plane);
 	}
 	GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-	GMG_CUDA(devFree(pos));
+	GMG_CUDA(devFree(posBase));
     }
     return GMG_OK;
 }
@@ -654,9 +778,11 @@ static int buildChunks(gmg_ctx *ctx, Level &L)
 }
 
 // band list in the reference's order (tile, z, y, x) and expanded coordinates
-static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz)
+// (a sharded level exports the cells of the rank's owned planes; the ranks' lists tile the global one)
+static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count)
 {
     const int n = L.nBand;
+    if (count) *count = 0;
     if (n == 0) return GMG_OK;
     unsigned long long *keys = nullptr, *keysOut = nullptr;
     GMG_CUDA(devMalloc(&keys, sizeof(unsigned long long) * n));
@@ -674,12 +800,21 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz)
     std::vector<unsigned long long> h(n);
     GMG_CUDA(cudaMemcpyAsync(h.data(), keysOut, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int64_t zLo = int64_t(L.g.org[2]) + L.ownLo, zHi = int64_t(L.g.org[2]) + L.ownHi;
+    int64_t m = 0;
     for (int k = 0; k < n; ++k)
     {
-	xyz[3 * k] = int64_t(h[k] & 0xfff);
-	xyz[3 * k + 1] = int64_t((h[k] >> 12) & 0xfff);
-	xyz[3 * k + 2] = int64_t((h[k] >> 24) & 0xfff);
+	const int64_t ez = int64_t((h[k] >> 24) & 0xfff);
+	if (L.sharded && (ez < zLo || ez >= zHi)) continue;
+	if (xyz)
+	{
+	    xyz[3 * m] = int64_t(h[k] & 0xfff);
+	    xyz[3 * m + 1] = int64_t((h[k] >> 12) & 0xfff);
+	    xyz[3 * m + 2] = ez;
+	}
+	++m;
     }
+    if (count) *count = m;
     GMG_CUDA(devFree(dTemp));
     GMG_CUDA(devFree(keys));
     GMG_CUDA(devFree(keysOut));
@@ -688,10 +823,10 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz)
 
 static void freeLevel(Level &L)
 {
-    devFree(L.labels); devFree(L.bandIdx); devFree(L.bandNbr); devFree(L.bcoef);
+    devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandIdx); devFree(L.bandNbr); devFree(L.bcoef);
     devFree(L.bandV0); devFree(L.bandV1); devFree(L.bandB);
     devFree(L.chunksInterior); devFree(L.chunksActive);
-    devFree(L.x); devFree(L.xAlt); devFree(L.b); devFree(L.r);
+    freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
     L = Level();
 }
 
@@ -799,15 +934,21 @@ static int boundsFromHintOrScan(const int32_t *labels, const int64_t res[3], con
     return GMG_OK;
 }
 
+// dW[a] are ALLOCATION bases covering the stored box plus one plane below and above (a slab's edge cells read the
+// forward z-face weight of the next plane); kernels take dW[a] + g.plane.
 static int uploadWeights(gmg_ctx *ctx, double *dW[3], const double *w0, const double *w1, const double *w2, const int64_t res[3], const Geom &g)
 {
     const double *w[3] = {w0, w1, w2};
+    Geom ge = g;
+    ge.org[2] = g.org[2] - 1;
+    ge.n[2] = g.n[2] + 2;
+    ge.total = ge.plane * ge.n[2];
     for (int a = 0; a < 3; ++a)
     {
 	int64_t fr[3] = {res[0], res[1], res[2]};
 	++fr[a];
-	GMG_CUDA(devMalloc(&dW[a], sizeof(double) * g.total));
-	GMG_TRY(uploadValues(ctx, dW[a], w[a], fr, g));
+	GMG_CUDA(devMalloc(&dW[a], sizeof(double) * ge.total));
+	GMG_TRY(uploadValues(ctx, dW[a], w[a], fr, ge));
     }
     return GMG_OK;
 }
@@ -831,7 +972,7 @@ extern "C" int gmg_set_boundary_labels(gmg_ctx *ctx, int32_t *labels, const int6
     GMG_TRY(uploadWeights(ctx, dW, w0, w1, w2, res, g));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_set_boundary<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dOut, dIn, dW[0], dW[1], dW[2], boxArgs(g));
+	k_set_boundary<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dOut, dIn, dW[0] + g.plane, dW[1] + g.plane, dW[2] + g.plane, boxArgs(g));
     }
     GMG_TRY(downloadLabels(ctx, labels, dOut, res, g, false));
     for (int a = 0; a < 3; ++a) GMG_CUDA(devFree(dW[a]));
@@ -909,10 +1050,10 @@ extern "C" int gmg_boundary_cells(gmg_ctx *ctx, const int32_t *labels, const int
     makeGeom(L.g, res, lo, hi);
     GMG_CUDA(devMalloc(&L.labels, L.g.total));
     GMG_TRY(uploadLabels(ctx, L.labels, labels, res, L.g));
+    L.gg = L.g;
+    L.ownHi = L.g.n[2];
     GMG_TRY(buildBand(ctx, L, width));
-    *count = L.nBand;
-    int st = GMG_OK;
-    if (xyz) st = exportBand(ctx, L, xyz);
+    int st = exportBand(ctx, L, xyz, count);
     freeLevel(L);
     return st;
 }
@@ -927,13 +1068,6 @@ extern "C" void gmg_solver_default_options(gmg_solver_options *opt)
     opt->boundary_width = 3;
     opt->boundary_iterations = 3;
     opt->coarse_matrix_scale = 1.0;
-}
-
-static int allocZero(double **p, int64_t n)
-{
-    GMG_CUDA(devMalloc(p, sizeof(double) * n));
-    GMG_CUDA(cudaMemsetAsync(*p, 0, sizeof(double) * n, g_stream));
-    return GMG_OK;
 }
 
 // coarsest level: number the active cells like the reference (tile order, x fastest in tile; MG.cpp:296-323), assemble
@@ -1042,7 +1176,191 @@ static int buildCoarseSolve(gmg_solver *s)
     return GMG_OK;
 }
 
+// ====================================================================================================
+// z-slab sharding
+// ====================================================================================================
+// Levels [0, S) are cut into z-slabs, one per rank, with cut planes that nest from level to level (a coarse plane and
+// its two child planes always belong to the same rank); levels [S, L) are replicated.  Every rank stores its owned
+// planes plus a deep halo and recomputes the halo redundantly, so a level needs two plane exchanges per V-cycle (rhs on
+// the way down, solution on the way up) instead of one per sweep; each cell is computed with the same arithmetic as on
+// one GPU, so sharded results are bitwise equal to unsharded ones apart from the order of the dot-product partial sums.
+extern "C" int gmg_shard_plan(const int64_t *levelPlanes, const int64_t *levelShiftZ, const int64_t *levelCells, int levels, int world,
+			      int maxShardLevels, int64_t minCells, int *shardLevels, int64_t *cuts)
+{
+    // levelPlanes[l]: z extent of level l's global storage box; levelShiftZ[l]: coarse plane = (fine plane >> 1) + shift;
+    // cuts: [levels][world + 1] global storage planes (filled for the sharded levels)
+    if (!levelPlanes || !levelShiftZ || !levelCells || !shardLevels || !cuts || levels < 1 || world < 1) return invalid("gmg_shard_plan: bad argument");
+    int S = 0;
+    if (world > 1)
+	for (int l = 0; l < std::min(levels - 1, maxShardLevels); ++l)
+	{
+	    if (levelCells[l] < minCells) break;
+	    S = l + 1;
+	}
+    for (; S > 0; --S)
+    {
+	bool ok = true;
+	const int64_t nS = levelPlanes[S - 1];
+	int64_t *c = cuts + int64_t(S - 1) * (world + 1);
+	for (int k = 0; k <= world; ++k) c[k] = 2 * int64_t(std::llround(double(k) * double(nS) / (2.0 * world)));
+	c[0] = 0;
+	c[world] = nS;
+	for (int l = S - 2; l >= 0; --l)
+	{
+	    const int64_t *cc = cuts + int64_t(l + 1) * (world + 1);
+	    int64_t *cf = cuts + int64_t(l) * (world + 1);
+	    for (int k = 1; k < world; ++k) cf[k] = std::max<int64_t>(0, std::min<int64_t>(levelPlanes[l], 2 * (cc[k] - levelShiftZ[l])));
+	    cf[0] = 0;
+	    cf[world] = levelPlanes[l];
+	}
+	for (int l = 0; l < S && ok; ++l)
+	{
+	    const int64_t need = (l == 0) ? HALO_STORE0 : HALO_STORE;
+	    const int64_t *cl = cuts + int64_t(l) * (world + 1);
+	    for (int k = 0; k < world; ++k)
+		if (cl[k + 1] - cl[k] < need || (cl[k] & 1)) ok = false;
+	}
+	if (ok) break;
+    }
+    *shardLevels = S;
+    return GMG_OK;
+}
+
+static int planShards(gmg_solver *s)
+{
+    gmg_ctx *ctx = s->ctx;
+    const int nl = s->levels, world = ctx->world, rank = ctx->rank;
+    for (auto &L : s->lv)
+    {
+	L.gg = L.g;
+	L.labelsAlloc = L.labels;
+	L.sharded = false;
+	L.zOff = 0;
+	L.ownLo = 0;
+	L.ownHi = L.g.n[2];
+    }
+    s->shardLevels = 0;
+    if (world == 1) return GMG_OK;
+    if (s->opt.boundary_iterations > 3) return invalid("sharded contexts support at most 3 boundary smoother iterations (halo depth)");
+    int maxS = 3;
+    int64_t minCells = 1500000;
+    if (const char *e = getenv("GMG_SHARD_LEVELS")) maxS = atoi(e);
+    if (const char *e = getenv("GMG_SHARD_MIN_CELLS")) minCells = atoll(e);
+    std::vector<int64_t> planes(nl), shiftZ(nl), cells(nl), cuts(size_t(nl) * (world + 1), 0);
+    for (int l = 0; l < nl; ++l) { planes[l] = s->lv[l].g.n[2]; shiftZ[l] = s->lv[l].shift[2]; cells[l] = s->lv[l].g.total; }
+    int S = 0;
+    GMG_TRY(gmg_shard_plan(planes.data(), shiftZ.data(), cells.data(), nl, world, maxS, minCells, &S, cuts.data()));
+    s->shardLevels = S;
+    if (S == 0) return GMG_OK;
+    for (int l = 0; l < S; ++l)
+    {
+	Level &L = s->lv[l];
+	const int64_t *c = cuts.data() + size_t(l) * (world + 1);
+	const int H = (l == 0) ? HALO_STORE0 : HALO_STORE;
+	const int zs = int(std::max<int64_t>(0, c[rank] - H)), ze = int(std::min<int64_t>(L.gg.n[2], c[rank + 1] + H));
+	L.sharded = true;
+	L.zOff = zs;
+	L.ownLo = int(c[rank]) - zs;
+	L.ownHi = int(c[rank + 1]) - zs;
+	L.g.org[2] = L.gg.org[2] + zs;
+	L.g.n[2] = ze - zs;
+	L.g.total = L.g.plane * L.g.n[2];
+	L.g.zBlocks = int(divUp(L.g.n[2], CHUNK_Z));
+	L.labels = L.labelsAlloc + int64_t(zs) * L.g.plane;
+	int64_t nI = 0, nB = 0;
+	GMG_TRY(countLabels(ctx, L.labels, L.g.total, &nI, &nB));
+	L.nInterior = nI;
+	L.nActive = nI + nB;
+    }
+    // fine -> coarse storage relation between the LOCAL boxes
+    for (int l = 0; l + 1 < nl; ++l)
+	for (int a = 0; a < 3; ++a) s->lv[l].shift[a] = s->lv[l].g.org[a] / 2 - s->lv[l + 1].g.org[a];
+    // planes of the first replicated level each rank restricts into (they tile that level's box)
+    {
+	const int64_t *c = cuts.data() + size_t(S - 1) * (world + 1);
+	const int64_t nC = s->lv[S].gg.n[2];
+	s->gatherLo.assign(world, 0);
+	s->gatherHi.assign(world, 0);
+	for (int k = 0; k < world; ++k)
+	{
+	    s->gatherLo[k] = (k == 0) ? 0 : int(std::min<int64_t>(nC, std::max<int64_t>(0, (c[k] >> 1) + shiftZ[S - 1])));
+	    s->gatherHi[k] = (k == world - 1) ? int(nC) : int(std::min<int64_t>(nC, std::max<int64_t>(0, (c[k + 1] >> 1) + shiftZ[S - 1])));
+	}
+    }
+    return GMG_OK;
+}
+
+struct ZRange { int lo, hi; };
+// planes within `depth` of the owned slab (everything on an unsharded level)
+static ZRange clipDepth(const Level &L, int depth)
+{
+    if (!L.sharded) return {0, L.g.n[2]};
+    return {std::max(0, L.ownLo - depth), std::min(L.g.n[2], L.ownHi + depth)};
+}
+
+// refresh `depth` halo planes of grid p on a sharded level from the two z-neighbours (NCCL P2P over NVLink)
+static int haloExchange(gmg_solver *s, int level, double *p, int depth)
+{
+    gmg_ctx *ctx = s->ctx;
+    const Level &L = s->lv[level];
+    if (!L.sharded || ctx->world == 1 || depth <= 0) return GMG_OK;
+    const NcclApi *api = ncclApi(nullptr);
+    NcclComm comm = static_cast<NcclComm>(ctx->nccl);
+    const size_t cnt = size_t(depth) * size_t(L.g.plane);
+    const int rank = ctx->rank, world = ctx->world;
+    ctx->curLevel = level;
+    GMG_LAUNCH(ctx, KC_HALO, double(cnt) * 8.0 * ((rank > 0) + (rank < world - 1)) * 2.0);
+    GMG_NCCL(api->GroupStart());
+    if (rank > 0)
+    {
+	GMG_NCCL(api->Send(p + int64_t(L.ownLo) * L.g.plane, cnt, NCCL_FLOAT64, rank - 1, comm, ctx->stream));
+	GMG_NCCL(api->Recv(p + int64_t(L.ownLo - depth) * L.g.plane, cnt, NCCL_FLOAT64, rank - 1, comm, ctx->stream));
+    }
+    if (rank < world - 1)
+    {
+	GMG_NCCL(api->Send(p + int64_t(L.ownHi - depth) * L.g.plane, cnt, NCCL_FLOAT64, rank + 1, comm, ctx->stream));
+	GMG_NCCL(api->Recv(p + int64_t(L.ownHi) * L.g.plane, cnt, NCCL_FLOAT64, rank + 1, comm, ctx->stream));
+    }
+    GMG_NCCL(api->GroupEnd());
+    return GMG_OK;
+}
+
+// all-gather of the first replicated level's grid: every rank contributes the planes it restricted into
+static int gatherReplicated(gmg_solver *s, double *p)
+{
+    gmg_ctx *ctx = s->ctx;
+    if (ctx->world == 1 || s->shardLevels == 0) return GMG_OK;
+    const Level &C = s->lv[s->shardLevels];
+    const NcclApi *api = ncclApi(nullptr);
+    NcclComm comm = static_cast<NcclComm>(ctx->nccl);
+    ctx->curLevel = s->shardLevels;
+    GMG_LAUNCH(ctx, KC_HALO, double(C.g.total) * 8.0);
+    GMG_NCCL(api->GroupStart());
+    for (int k = 0; k < ctx->world; ++k)
+    {
+	const size_t cnt = size_t(s->gatherHi[k] - s->gatherLo[k]) * size_t(C.g.plane);
+	if (cnt == 0) continue;
+	double *q = p + int64_t(s->gatherLo[k]) * C.g.plane;
+	GMG_NCCL(api->Broadcast(q, q, cnt, NCCL_FLOAT64, k, comm, ctx->stream));
+    }
+    GMG_NCCL(api->GroupEnd());
+    return GMG_OK;
+}
+
+// sum of one device double over the ranks (CG dot products), in place
+static int allreduceScalar(gmg_solver *s, double *dev, int op = NCCL_SUM)
+{
+    gmg_ctx *ctx = s->ctx;
+    if (ctx->world == 1 || s->shardLevels == 0) return GMG_OK;
+    const NcclApi *api = ncclApi(nullptr);
+    ctx->curLevel = 0;
+    GMG_LAUNCH(ctx, KC_HALO, 8.0);
+    GMG_NCCL(api->AllReduce(dev, dev, 1, NCCL_FLOAT64, op, static_cast<NcclComm>(ctx->nccl), ctx->stream));
+    return GMG_OK;
+}
+
 static int buildFusedCycle(gmg_solver *s);
+static double *scalarPtr(gmg_solver *s, size_t offset);
 
 extern "C" int gmg_solver_destroy(gmg_solver *s)
 {
@@ -1050,9 +1368,13 @@ extern "C" int gmg_solver_destroy(gmg_solver *s)
     enterCtx(s->ctx);
     cudaStreamSynchronize(s->ctx->stream);
     for (auto &g : s->graphs) { cudaGraphExecDestroy(g.second.exec); cudaGraphDestroy(g.second.graph); }
-    for (auto &L : s->lv) freeLevel(L);
     devFree(s->coarseIdx); devFree(s->coarseInv); devFree(s->devLevels);
-    devFree(s->pcgR); devFree(s->pcgP); devFree(s->pcgZ); devFree(s->pcgT); devFree(s->pcgX); devFree(s->pcgB);
+    if (!s->lv.empty())
+    {
+	const Geom &g0 = s->lv[0].g;
+	freeGrid(s->pcgR, g0); freeGrid(s->pcgP, g0); freeGrid(s->pcgZ, g0); freeGrid(s->pcgT, g0); freeGrid(s->pcgX, g0); freeGrid(s->pcgB, g0);
+    }
+    for (auto &L : s->lv) freeLevel(L);
     delete s;
     return GMG_OK;
 }
@@ -1106,11 +1428,10 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	if (L0.g.total >= (int64_t(1) << 31)) return fail(invalid("gmg_solver_create: cropped box exceeds 2^31 cells"));
 	if ((st = (devMalloc(&L0.labels, L0.g.total) == cudaSuccess ? GMG_OK : GMG_ERR_CUDA)) != GMG_OK) return fail(st);
 	if ((st = uploadLabels(ctx, L0.labels, labels, res, L0.g)) != GMG_OK) return fail(st);
-	// no weight grids = the reference's boundaryWeights == nullptr form (weight 1 to active/DIRICHLET neighbours, Ops.h:237-248)
-	if (w0 && (st = uploadWeights(ctx, dW, w0, w1, w2, res, L0.g)) != GMG_OK) return fail(st);
     }
-    lap("upload labels + weights");
-    // coarse labels (MG.cpp:238-253) with the reference's level cap: a level without active cells drops it AND the one before
+    lap("upload labels");
+    // coarse labels (MG.cpp:238-253) over the GLOBAL box of every level (one byte per cell, replicated on every rank),
+    // with the reference's level cap: a level without active cells drops it AND the one before
     int64_t clo[3] = {lo[0], lo[1], lo[2]}, chi[3] = {hi[0], hi[1], hi[2]};
     for (int level = 0; level < s->levels; ++level)
     {
@@ -1128,6 +1449,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	if ((st = countLabels(ctx, L.labels, L.g.total, &nI, &nB)) != GMG_OK) return fail(st);
 	L.nInterior = nI;
 	L.nActive = nI + nB;
+	L.nActiveGlobal = nI + nB;
 	if (L.nActive == 0)
 	{
 	    if (level == 0) { setError("no INTERIOR/BOUNDARY cell at level 0"); return fail(GMG_ERR_NO_ACTIVE); }
@@ -1141,25 +1463,31 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     if (s->levels < 1)
     {
 	setError("level cap (MG.cpp:243-248) left no level: level 1 has no active cell");
-	for (int a = 0; a < 3; ++a) devFree(dW[a]);
 	return fail(GMG_ERR_NO_ACTIVE);
     }
     lap("coarse labels");
+    // z-slab views of the fine levels (world > 1); afterwards L.g / L.labels are the rank's local box
+    if ((st = planShards(s)) != GMG_OK) return fail(st);
+    // no weight grids = the reference's boundaryWeights == nullptr form (weight 1 to active/DIRICHLET neighbours, Ops.h:237-248)
+    if (w0 && (st = uploadWeights(ctx, dW, w0, w1, w2, res, s->lv[0].g)) != GMG_OK) return fail(st);
+    lap("shard plan, upload weights");
     // bands (MG.cpp:279-281), coefficient records, chunk lists, grids
     int maxGrid = 0;
     for (int level = 0; level < s->levels; ++level)
     {
 	Level &L = s->lv[level];
 	if ((st = buildBand(ctx, L, s->opt.boundary_width)) != GMG_OK) return fail(st);
-	if ((st = buildCoefs(ctx, L, level == 0 ? dW[0] : nullptr, level == 0 ? dW[1] : nullptr, level == 0 ? dW[2] : nullptr)) != GMG_OK) return fail(st);
+	const int64_t wOff = L.g.plane;
+	const bool fw = level == 0 && dW[0];
+	if ((st = buildCoefs(ctx, L, fw ? dW[0] + wOff : nullptr, fw ? dW[1] + wOff : nullptr, fw ? dW[2] + wOff : nullptr)) != GMG_OK) return fail(st);
 	if ((st = buildChunks(ctx, L)) != GMG_OK) return fail(st);
 	maxGrid = std::max(maxGrid, L.nChunksActive + int(divUp(L.nBoundary, BLOCK)) + 1);
-	if ((st = allocZero(&L.xAlt, L.g.total)) != GMG_OK) return fail(st);
-	if ((st = allocZero(&L.r, L.g.total)) != GMG_OK) return fail(st);
+	if ((st = allocGrid(&L.xAlt, L.g)) != GMG_OK) return fail(st);
+	if ((st = allocGrid(&L.r, L.g)) != GMG_OK) return fail(st);
 	if (level > 0)
 	{
-	    if ((st = allocZero(&L.x, L.g.total)) != GMG_OK) return fail(st);
-	    if ((st = allocZero(&L.b, L.g.total)) != GMG_OK) return fail(st);
+	    if ((st = allocGrid(&L.x, L.g)) != GMG_OK) return fail(st);
+	    if ((st = allocGrid(&L.b, L.g)) != GMG_OK) return fail(st);
 	}
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1169,6 +1497,17 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     if (!s->opt.operators_only && (st = buildCoarseSolve(s)) != GMG_OK) return fail(st);
     if ((st = buildFusedCycle(s)) != GMG_OK) return fail(st);
     lap("coarse direct solver");
+    if (s->shardLevels > 0)
+    {
+	// run every communication pattern once now: NCCL sets up its peer connections on first use, which must not
+	// happen inside the stream capture of the V-cycle / PCG graphs
+	for (int l = 0; l < s->shardLevels; ++l)
+	    if ((st = haloExchange(s, l, s->lv[l].r, 1)) != GMG_OK) return fail(st);
+	if ((st = gatherReplicated(s, s->lv[s->shardLevels].b)) != GMG_OK) return fail(st);
+	if ((st = allreduceScalar(s, scalarPtr(s, offsetof(Scalars, tmp)))) != GMG_OK) return fail(st);
+	if ((st = allreduceScalar(s, scalarPtr(s, offsetof(Scalars, tmp)), NCCL_MAX)) != GMG_OK) return fail(st);
+	lap("communication warm-up");
+    }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     s->setupMs = nowMs() - tStart;
     *out = s;
@@ -1191,20 +1530,29 @@ extern "C" int gmg_solver_get_labels(gmg_solver *s, int level, int32_t *out)
 {
     if (!s || !out || level < 0 || level >= s->levels) return invalid("level out of range");
     GMG_CUDA(enterCtx(s->ctx));
-    return downloadLabels(s->ctx, out, s->lv[level].labels, s->lv[level].g.res, s->lv[level].g, true);
+    const Level &L = s->lv[level];
+    return downloadLabels(s->ctx, out, L.labelsAlloc ? L.labelsAlloc : L.labels, L.gg.res, L.gg, true);
 }
 extern "C" int gmg_solver_get_boundary_cells(gmg_solver *s, int level, int64_t *xyz, int64_t *count)
 {
     if (!s || !count || level < 0 || level >= s->levels) return invalid("level out of range");
     GMG_CUDA(enterCtx(s->ctx));
-    *count = s->lv[level].nBand;
-    if (xyz) return exportBand(s->ctx, s->lv[level], xyz);
-    return GMG_OK;
+    return exportBand(s->ctx, s->lv[level], xyz, count);
 }
 extern "C" int gmg_solver_active_cells(gmg_solver *s, int level, int64_t *count)
 {
     if (!s || !count || level < 0 || level >= s->levels) return invalid("level out of range");
-    *count = s->lv[level].nActive;
+    *count = s->lv[level].nActiveGlobal;
+    return GMG_OK;
+}
+extern "C" int gmg_solver_shard_info(gmg_solver *s, int level, int *sharded, int64_t *ownLoZ, int64_t *ownHiZ, int64_t *localActive)
+{
+    if (!s || level < 0 || level >= s->levels) return invalid("level out of range");
+    const Level &L = s->lv[level];
+    if (sharded) *sharded = L.sharded ? 1 : 0;
+    if (ownLoZ) *ownLoZ = int64_t(L.g.org[2]) + L.ownLo;  // expanded z coordinates [lo, hi) of the rank's owned planes
+    if (ownHiZ) *ownHiZ = int64_t(L.g.org[2]) + L.ownHi;
+    if (localActive) *localActive = L.nActive;
     return GMG_OK;
 }
 extern "C" int gmg_solver_coarse_unknowns(gmg_solver *s, int64_t *count)
@@ -1248,12 +1596,14 @@ static StencilArgs stencilArgs(gmg_solver *s, int level, const double *in, const
     return a;
 }
 
-static int launchStencil(gmg_solver *s, int level, int mode, const double *in, const double *b, double *out, double *dotResult)
+static int launchStencil(gmg_solver *s, int level, int mode, const double *in, const double *b, double *out, double *dotResult, ZRange zr)
 {
     s->ctx->curLevel = level;
     const Level &L = s->lv[level];
     StencilArgs a = stencilArgs(s, level, in, b, out);
     a.result = dotResult;
+    a.zlo = zr.lo;
+    a.zhi = zr.hi;
     const unsigned grid = unsigned(L.nChunksInterior + divUp(L.nBoundary, BLOCK));
     if (grid == 0) return GMG_OK;
     cudaStream_t st = s->ctx->stream;
@@ -1348,7 +1698,7 @@ static TransferArgs transferArgs(gmg_solver *s, int fineLevel)
     return a;
 }
 
-static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const double *fine)
+static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const double *fine, ZRange zr)
 {
     s->ctx->curLevel = fineLevel + 1;
     const Level &C = s->lv[fineLevel + 1];
@@ -1358,15 +1708,15 @@ static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const do
     a.out = coarse;
     a.chunks = C.chunksActive;
     a.chunksPerPlane = C.g.chunksPerPlane;
-    a.zlo = 0;
-    a.zhi = C.g.n[2];
+    a.zlo = zr.lo;
+    a.zhi = zr.hi;
     GMG_LAUNCH(s->ctx, KC_RESTRICT, double(s->lv[fineLevel].nActive) * 8.0 + double(C.nActive) * 9.0);
     k_restrict<<<C.nChunksActive, BLOCK, 0, s->ctx->stream>>>(a);
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }
 
-static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const double *coarse)
+static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const double *coarse, ZRange zr)
 {
     s->ctx->curLevel = fineLevel;
     const Level &F = s->lv[fineLevel];
@@ -1376,8 +1726,8 @@ static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const doubl
     a.out = fine;
     a.chunks = F.chunksActive;
     a.chunksPerPlane = F.g.chunksPerPlane;
-    a.zlo = 0;
-    a.zhi = F.g.n[2];
+    a.zlo = zr.lo;
+    a.zhi = zr.hi;
     GMG_LAUNCH(s->ctx, KC_PROLONG, double(F.nActive) * 17.0 + double(s->lv[fineLevel + 1].nActive) * 8.0);
     k_prolong<<<F.nChunksActive, BLOCK, 0, s->ctx->stream>>>(a);
     GMG_CUDA(cudaGetLastError());
@@ -1412,10 +1762,10 @@ static int buildFusedCycle(gmg_solver *s)
     const char *e = getenv("GMG_COARSE_FUSED");
     if (e && e[0] == '0') return GMG_OK;
     if (s->opt.operators_only || s->levels < 3) return GMG_OK;
-    int64_t limit = 200000;
+    int64_t limit = 12000;  // above this a level has enough work to fill the machine through ordinary launches
     if (const char *c = getenv("GMG_FUSED_CELLS")) limit = atoll(c);
     int first = -1;
-    for (int l = 1; l < s->levels - 1; ++l)
+    for (int l = std::max(1, s->shardLevels); l < s->levels - 1; ++l)  // replicated levels only
 	if (s->lv[l].nActive <= limit) { first = l; break; }
     if (first < 0) return GMG_OK;
     s->clusterSize = 8;
@@ -1473,7 +1823,7 @@ static int launchCoarseCycle(gmg_solver *s)
 
 template <int OP>
 static int launchVec(gmg_solver *s, int level, double *y, const double *a, const double *c, double *y2, double sc, double *result, int klass,
-		     double bytesPerCell)
+		     double bytesPerCell, ZRange zr = {0, 1 << 30})
 {
     s->ctx->curLevel = level;
     const Level &L = s->lv[level];
@@ -1483,8 +1833,8 @@ static int launchVec(gmg_solver *s, int level, double *y, const double *a, const
     v.chunksPerPlane = L.g.chunksPerPlane;
     v.plane = L.g.plane;
     v.nz = L.g.n[2];
-    v.zlo = 0;
-    v.zhi = L.g.n[2];
+    v.zlo = std::max(0, zr.lo);
+    v.zhi = std::min(L.g.n[2], zr.hi);
     v.y = y;
     v.a = a;
     v.c = c;
@@ -1513,31 +1863,50 @@ static int readScalar(gmg_solver *s, size_t offset, double *out)
 // ====================================================================================================
 // V-cycle (MG.cpp:420-881)
 // ====================================================================================================
-static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, const double *b, bool zeroGrid)
+// jacobiDepth: how far into the halo the interior sweep still produces valid values (sharded levels)
+static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, const double *b, bool zeroGrid, int jacobiDepth)
 {
     const int it = s->opt.boundary_iterations;
     GMG_TRY(launchBand(s, level, cur, b, it, zeroGrid));
-    GMG_TRY(launchStencil(s, level, SM_JACOBI, cur, b, alt, nullptr));
+    GMG_TRY(launchStencil(s, level, SM_JACOBI, cur, b, alt, nullptr, clipDepth(s->lv[level], jacobiDepth)));
     std::swap(cur, alt);
     GMG_TRY(launchBand(s, level, cur, b, it, false));
+    return GMG_OK;
+}
+
+// Halo bookkeeping on a sharded level (it = 3 band sweeps): the rhs is valid HALO_X = 8 planes deep.  Down: x = 0, so the
+// first sweep is free and after 3 + 1 + 3 sweeps x is valid 2 deep, the residual 1 deep -- what the restriction of the owned
+// coarse planes reads.  Up: the prolonged x is refreshed 8 deep, 7 sweeps leave it valid 1 deep -- what the next finer
+// prolongation reads.  With an initial guess at level 0 the first sweep is not free: x and b must be valid HALO_P = 9 deep.
+static int restrictDown(gmg_solver *s, int level, const double *r)
+{
+    Level &F = s->lv[level], &C = s->lv[level + 1];
+    ZRange zr = {0, C.g.n[2]};
+    if (C.sharded) zr = {C.ownLo, C.ownHi};
+    else if (F.sharded) zr = {s->gatherLo[s->ctx->rank], s->gatherHi[s->ctx->rank]};
+    GMG_TRY(launchRestrict(s, level, C.b, r, zr));
+    if (C.sharded) GMG_TRY(haloExchange(s, level + 1, C.b, HALO_X));
+    else if (F.sharded) GMG_TRY(gatherReplicated(s, C.b));
     return GMG_OK;
 }
 
 static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useInitialGuess)
 {
     const int nl = s->levels;
+    const int it = s->opt.boundary_iterations;
+    const int downJacobi = HALO_X - (it - 1) - 1, upJacobi = HALO_X - it - 1;
     // level 0 works on the caller's grid and the level's alternate; two Jacobi sweeps per level bring the
     // result back into the caller's buffer (one sweep only when there is a single level)
     double *cur0 = x, *alt0 = s->lv[0].xAlt;
     if (!useInitialGuess) GMG_TRY(launchZero(s, 0, cur0));
-    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, !useInitialGuess));
+    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, !useInitialGuess, downJacobi));
     if (nl == 1)
     {
 	GMG_TRY((launchVec<VO_COPY>(s, 0, x, cur0, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
 	return GMG_OK;
     }
-    GMG_TRY(launchStencil(s, 0, SM_RESIDUAL, cur0, b, s->lv[0].r, nullptr));
-    GMG_TRY(launchRestrict(s, 0, s->lv[1].b, s->lv[0].r));
+    GMG_TRY(launchStencil(s, 0, SM_RESIDUAL, cur0, b, s->lv[0].r, nullptr, clipDepth(s->lv[0], 1)));
+    GMG_TRY(restrictDown(s, 0, s->lv[0].r));
     std::vector<double *> cur(nl), alt(nl);
     // levels [fusedFirst, nl-1] run inside the persistent cluster kernel; its result is lv[fusedFirst].x
     const int nReg = (s->fusedFirst > 0) ? s->fusedFirst : nl - 1;  // regular levels are 1 .. nReg-1
@@ -1547,9 +1916,9 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
 	cur[level] = L.x;
 	alt[level] = L.xAlt;
 	GMG_TRY(launchZero(s, level, cur[level]));
-	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, true));
-	GMG_TRY(launchStencil(s, level, SM_RESIDUAL, cur[level], L.b, L.r, nullptr));
-	GMG_TRY(launchRestrict(s, level, s->lv[level + 1].b, L.r));
+	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, true, downJacobi));
+	GMG_TRY(launchStencil(s, level, SM_RESIDUAL, cur[level], L.b, L.r, nullptr, clipDepth(L, 1)));
+	GMG_TRY(restrictDown(s, level, L.r));
     }
     if (s->fusedFirst > 0) GMG_TRY(launchCoarseCycle(s));
     else GMG_TRY(launchCoarse(s, s->lv[nl - 1].x, s->lv[nl - 1].b));
@@ -1557,11 +1926,13 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
     {
 	Level &L = s->lv[level];
 	// the level below hands over its result in its own x grid (two Jacobi swaps, or the direct solve / fused cycle)
-	GMG_TRY(launchProlong(s, level, cur[level], s->lv[level + 1].x));
-	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, false));
+	GMG_TRY(launchProlong(s, level, cur[level], s->lv[level + 1].x, clipDepth(L, 0)));
+	GMG_TRY(haloExchange(s, level, cur[level], HALO_X));
+	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, false, upJacobi));
     }
-    GMG_TRY(launchProlong(s, 0, cur0, s->lv[1].x));
-    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, false));
+    GMG_TRY(launchProlong(s, 0, cur0, s->lv[1].x, clipDepth(s->lv[0], 0)));
+    GMG_TRY(haloExchange(s, 0, cur0, HALO_X));
+    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, false, upJacobi));
     // cur0 == x again after the second swap
     if (cur0 != x) GMG_TRY((launchVec<VO_COPY>(s, 0, x, cur0, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
     return GMG_OK;
@@ -1583,19 +1954,22 @@ static int runGraphed(gmg_solver *s, int kind, const void *p0, const void *p1, i
 	    s->graphs.clear();
 	}
 	gmg_solver::GraphEntry e;
-	const int64_t before = ctx->launches;
+	const int64_t before = ctx->launches, commBefore = ctx->commOps;
 	GMG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
 	const int st = body();
 	cudaError_t ce = cudaStreamEndCapture(ctx->stream, &e.graph);
 	if (st != GMG_OK) { if (e.graph) cudaGraphDestroy(e.graph); return st; }
 	GMG_CUDA(ce);
 	e.kernels = ctx->launches - before;
+	e.comms = ctx->commOps - commBefore;
 	ctx->launches = before;
+	ctx->commOps = commBefore;
 	GMG_CUDA(cudaGraphInstantiate(&e.exec, e.graph, 0));
 	it = s->graphs.emplace(key, e).first;
     }
     GMG_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
     ctx->launches += it->second.kernels;
+    ctx->commOps += it->second.comms;
     return GMG_OK;
 }
 
@@ -1610,48 +1984,74 @@ static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useIniti
 // ====================================================================================================
 __global__ void k_shift_rho(Scalars *sc) { sc->rho = sc->rhoNew; }
 
+// owned-plane reduction into a device scalar, summed over the ranks on a sharded level 0
+template <int OP>
+static int reduceOwned(gmg_solver *s, double *y, const double *a, size_t scalarOffset, double bytesPerCell, int level = 0)
+{
+    const Level &L = s->lv[level];
+    GMG_TRY((launchVec<OP>(s, level, y, a, nullptr, nullptr, 0, scalarPtr(s, scalarOffset), KC_REDUCE, bytesPerCell, clipDepth(L, 0))));
+    if (L.sharded) GMG_TRY(allreduceScalar(s, scalarPtr(s, scalarOffset), OP == VO_MAX ? NCCL_MAX : NCCL_SUM));
+    return GMG_OK;
+}
+
+// Sharded level 0: x0 and b come in valid over the whole stored slab.  Each iteration the search
+// direction p is refreshed HALO_P = 9 planes deep, so t = A p is valid 8 deep and the update r -= alpha t keeps r valid
+// 8 deep redundantly -- exactly what the next V-cycle needs as its right-hand side -- without an exchange of its own.
 static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int precond, int *iterations, double *hist, int histCap,
 		     int *histCount)
 {
     gmg_ctx *ctx = s->ctx;
-    const int64_t total = s->lv[0].g.total;
+    const Level &L0 = s->lv[0];
     if (!s->pcgR)
     {
-	GMG_TRY(allocZero(&s->pcgR, total));
-	GMG_TRY(allocZero(&s->pcgP, total));
-	GMG_TRY(allocZero(&s->pcgZ, total));
-	GMG_TRY(allocZero(&s->pcgT, total));
+	GMG_TRY(allocGrid(&s->pcgR, s->lv[0].g));
+	GMG_TRY(allocGrid(&s->pcgP, s->lv[0].g));
+	GMG_TRY(allocGrid(&s->pcgZ, s->lv[0].g));
+	GMG_TRY(allocGrid(&s->pcgT, s->lv[0].g));
     }
     double *r = s->pcgR, *p = s->pcgP, *z = s->pcgZ, *t = s->pcgT;
+    const ZRange own = clipDepth(L0, 0), deep = clipDepth(L0, HALO_X);
     if (histCount) *histCount = 0;
     if (iterations) *iterations = -1;
     double bb = 0, rr = 0;
-    GMG_TRY((launchVec<VO_NORM2>(s, 0, const_cast<double *>(b), nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, bb)), KC_REDUCE, 8.0)));
+    GMG_TRY((reduceOwned<VO_NORM2>(s, const_cast<double *>(b), nullptr, offsetof(Scalars, bb), 8.0)));
     GMG_TRY(readScalar(s, offsetof(Scalars, bb), &bb));
     if (bb == 0) return GMG_OK; // "RHS is zero. Nothing to solve" (CG.h:35-40)
     // r = b - A x (CG.h:50-51)
-    GMG_TRY(launchStencil(s, 0, SM_RESIDUAL, x, b, r, nullptr));
-    GMG_TRY((launchVec<VO_NORM2>(s, 0, r, nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, rr)), KC_REDUCE, 8.0)));
+    GMG_TRY(launchStencil(s, 0, SM_RESIDUAL, x, b, r, nullptr, deep));
+    GMG_TRY((reduceOwned<VO_NORM2>(s, r, nullptr, offsetof(Scalars, rr), 8.0)));
     GMG_TRY(readScalar(s, offsetof(Scalars, rr), &rr));
     const double threshold = tol * tol * bb;
     if (rr < threshold) return GMG_OK; // CG.h:60-64
     // p = M^-1 r ; rho = p.r (CG.h:66-87)
     if (precond) GMG_TRY(vcycleDevice(s, p, r, false));
-    else GMG_TRY((launchVec<VO_COPY>(s, 0, p, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
-    GMG_TRY((launchVec<VO_DOT>(s, 0, p, r, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, rho)), KC_REDUCE, 16.0)));
+    else GMG_TRY((launchVec<VO_COPY>(s, 0, p, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, own)));
+    GMG_TRY((reduceOwned<VO_DOT>(s, p, r, offsetof(Scalars, rho), 16.0)));
     // Reference loop (CG.h:100-195): [t = A p, alpha, x += alpha p, r -= alpha t, |r|^2, test] then
     // [z = M^-1 r, beta, p = z + beta p].  Re-bracketed here as: first [apply, update]; then per iteration one
     // graph {V-cycle, z.r, direction, apply (+p.Ap), update (+|r|^2)} and one scalar read-back for the test.
     auto applyUpdate = [&]() -> int {
-	GMG_TRY(launchStencil(s, 0, SM_APPLY, p, nullptr, t, scalarPtr(s, offsetof(Scalars, pAp))));
-	GMG_TRY((launchVec<VO_CG_UPDATE>(s, 0, x, p, t, r, 0, scalarPtr(s, offsetof(Scalars, rr)), KC_BLAS1, 48.0)));
+	GMG_TRY(haloExchange(s, 0, p, HALO_P));
+	if (!L0.sharded) GMG_TRY(launchStencil(s, 0, SM_APPLY, p, nullptr, t, scalarPtr(s, offsetof(Scalars, pAp)), own));
+	else
+	{
+	    // the fused dot would also sum the halo planes: apply over the deep range, then p.t over the owned planes
+	    GMG_TRY(launchStencil(s, 0, SM_APPLY, p, nullptr, t, nullptr, deep));
+	    GMG_TRY((reduceOwned<VO_DOT>(s, p, t, offsetof(Scalars, pAp), 16.0)));
+	}
+	if (!L0.sharded) GMG_TRY((launchVec<VO_CG_UPDATE>(s, 0, x, p, t, r, 0, scalarPtr(s, offsetof(Scalars, rr)), KC_BLAS1, 48.0)));
+	else
+	{
+	    GMG_TRY((launchVec<VO_CG_UPDATE>(s, 0, x, p, t, r, 0, nullptr, KC_BLAS1, 48.0, deep)));
+	    GMG_TRY((reduceOwned<VO_NORM2>(s, r, nullptr, offsetof(Scalars, rr), 8.0)));
+	}
 	return GMG_OK;
     };
     auto iterationBody = [&]() -> int {
 	if (precond) GMG_TRY(vcycleLaunches(s, z, r, false));
-	else GMG_TRY((launchVec<VO_COPY>(s, 0, z, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
-	GMG_TRY((launchVec<VO_DOT>(s, 0, z, r, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, rhoNew)), KC_REDUCE, 16.0)));
-	GMG_TRY((launchVec<VO_CG_DIRECTION>(s, 0, p, z, nullptr, nullptr, 0, nullptr, KC_BLAS1, 24.0)));
+	else GMG_TRY((launchVec<VO_COPY>(s, 0, z, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, own)));
+	GMG_TRY((reduceOwned<VO_DOT>(s, z, r, offsetof(Scalars, rhoNew), 16.0)));
+	GMG_TRY((launchVec<VO_CG_DIRECTION>(s, 0, p, z, nullptr, nullptr, 0, nullptr, KC_BLAS1, 24.0, own)));
 	{
 	    s->ctx->curLevel = 0;
 	    GMG_LAUNCH(ctx, KC_BLAS1, 0);
@@ -1684,16 +2084,16 @@ extern "C" int gmg_grid_create(gmg_solver *s, int level, gmg_grid **out)
     gmg_grid *g = new gmg_grid;
     g->solver = s;
     g->level = level;
-    int st = allocZero(&g->d, s->lv[level].g.total);
+    int st = allocGrid(&g->d, s->lv[level].g);
     if (st != GMG_OK) { delete g; return st; }
+    g->plane = s->lv[level].g.plane;
     *out = g;
     return GMG_OK;
 }
 extern "C" int gmg_grid_destroy(gmg_grid *g)
 {
     if (!g) return GMG_OK;
-    enterCtx(g->solver->ctx);
-    devFree(g->d);
+    if (g->d) devFree(g->d - g->plane);
     delete g;
     return GMG_OK;
 }
@@ -1704,12 +2104,23 @@ extern "C" int gmg_grid_upload(gmg_grid *g, const double *host)
     const Geom &ge = g->solver->lv[g->level].g;
     return uploadValues(g->solver->ctx, g->d, host, ge.res, ge, g->solver->lv[g->level].labels);
 }
+// the rank's owned planes as a box of their own (what a sharded context hands back to the host)
+static Geom ownedGeom(const Level &L)
+{
+    Geom go = L.g;
+    go.org[2] = L.g.org[2] + L.ownLo;
+    go.n[2] = L.ownHi - L.ownLo;
+    go.total = go.plane * go.n[2];
+    go.zBlocks = int(divUp(go.n[2], CHUNK_Z));
+    return go;
+}
 extern "C" int gmg_grid_download(gmg_grid *g, double *host)
 {
     if (!g || !host) return invalid("null argument");
     GMG_CUDA(enterCtx(g->solver->ctx));
-    const Geom &ge = g->solver->lv[g->level].g;
-    return downloadValues(g->solver->ctx, host, g->d, ge.res, ge, true);
+    const Level &L = g->solver->lv[g->level];
+    const Geom go = ownedGeom(L);
+    return downloadValues(g->solver->ctx, host, g->d + int64_t(L.ownLo) * L.g.plane, go.res, go, true);
 }
 extern "C" int gmg_grid_zero(gmg_grid *g)
 {
@@ -1728,19 +2139,31 @@ extern "C" int gmg_grid_copy(gmg_grid *dst, const gmg_grid *src)
     if (!(s) || !(a) || !(b) || (a)->solver != (s) || (b)->solver != (s) || (a)->level != (b)->level) \
     return invalid("grid arguments must belong to this solver and share a level")
 
+// On a sharded level the single-operator entry points first refresh the halo planes their stencil reads, then compute
+// the rank's owned planes; reductions sum the owned planes of every rank.
+static int checkSweeps(const Level &L, int sweeps)
+{
+    if (L.sharded && sweeps > HALO_STORE) return invalid("at most 8 boundary sweeps per call on a sharded level (stored halo depth)");
+    return GMG_OK;
+}
+
 extern "C" int gmg_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b)
 {
     CHECK_GRIDS2(s, x, b);
     GMG_CUDA(enterCtx(s->ctx));
     Level &L = s->lv[x->level];
-    GMG_TRY(launchStencil(s, x->level, SM_JACOBI, x->d, b->d, L.xAlt, nullptr));
+    GMG_TRY(haloExchange(s, x->level, x->d, 1));
+    GMG_TRY(launchStencil(s, x->level, SM_JACOBI, x->d, b->d, L.xAlt, nullptr, clipDepth(L, 0)));
     // copy back rather than swap pointers: cached V-cycle graphs hold the level's xAlt address
-    return launchVec<VO_COPY>(s, x->level, x->d, L.xAlt, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0);
+    return launchVec<VO_COPY>(s, x->level, x->d, L.xAlt, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, clipDepth(L, 0));
 }
 extern "C" int gmg_boundary_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int sweeps)
 {
     CHECK_GRIDS2(s, x, b);
     GMG_CUDA(enterCtx(s->ctx));
+    GMG_TRY(checkSweeps(s->lv[x->level], sweeps));
+    GMG_TRY(haloExchange(s, x->level, x->d, sweeps));
+    GMG_TRY(haloExchange(s, x->level, b->d, std::max(0, sweeps - 1)));
     return launchBand(s, x->level, x->d, b->d, sweeps, false);
 }
 extern "C" int gmg_apply(gmg_solver *s, gmg_grid *dst, const gmg_grid *src)
@@ -1748,7 +2171,8 @@ extern "C" int gmg_apply(gmg_solver *s, gmg_grid *dst, const gmg_grid *src)
     CHECK_GRIDS2(s, dst, src);
     if (dst == src) return invalid("gmg_apply: dst must differ from src");
     GMG_CUDA(enterCtx(s->ctx));
-    return launchStencil(s, dst->level, SM_APPLY, src->d, nullptr, dst->d, nullptr);
+    GMG_TRY(haloExchange(s, src->level, src->d, 1));
+    return launchStencil(s, dst->level, SM_APPLY, src->d, nullptr, dst->d, nullptr, clipDepth(s->lv[dst->level], 0));
 }
 extern "C" int gmg_residual(gmg_solver *s, gmg_grid *r, const gmg_grid *x, const gmg_grid *b)
 {
@@ -1756,41 +2180,50 @@ extern "C" int gmg_residual(gmg_solver *s, gmg_grid *r, const gmg_grid *x, const
     CHECK_GRIDS2(s, r, b);
     if (r == x) return invalid("gmg_residual: r must differ from x");
     GMG_CUDA(enterCtx(s->ctx));
-    return launchStencil(s, r->level, SM_RESIDUAL, x->d, b->d, r->d, nullptr);
+    GMG_TRY(haloExchange(s, x->level, x->d, 1));
+    return launchStencil(s, r->level, SM_RESIDUAL, x->d, b->d, r->d, nullptr, clipDepth(s->lv[r->level], 0));
 }
 extern "C" int gmg_restrict(gmg_solver *s, gmg_grid *coarse, const gmg_grid *fine)
 {
     if (!s || !coarse || !fine || coarse->solver != s || fine->solver != s || coarse->level != fine->level + 1)
 	return invalid("gmg_restrict: coarse must be one level above fine");
     GMG_CUDA(enterCtx(s->ctx));
-    return launchRestrict(s, fine->level, coarse->d, fine->d);
+    const Level &F = s->lv[fine->level], &C = s->lv[coarse->level];
+    GMG_TRY(haloExchange(s, fine->level, fine->d, 1));
+    ZRange zr = {0, C.g.n[2]};
+    if (C.sharded) zr = {C.ownLo, C.ownHi};
+    else if (F.sharded) zr = {s->gatherLo[s->ctx->rank], s->gatherHi[s->ctx->rank]};
+    GMG_TRY(launchRestrict(s, fine->level, coarse->d, fine->d, zr));
+    if (F.sharded && !C.sharded) GMG_TRY(gatherReplicated(s, coarse->d));
+    return GMG_OK;
 }
 extern "C" int gmg_prolong_add(gmg_solver *s, gmg_grid *fine, const gmg_grid *coarse)
 {
     if (!s || !coarse || !fine || coarse->solver != s || fine->solver != s || coarse->level != fine->level + 1)
 	return invalid("gmg_prolong_add: coarse must be one level above fine");
     GMG_CUDA(enterCtx(s->ctx));
-    return launchProlong(s, fine->level, fine->d, coarse->d);
+    GMG_TRY(haloExchange(s, coarse->level, coarse->d, 1));
+    return launchProlong(s, fine->level, fine->d, coarse->d, clipDepth(s->lv[fine->level], 0));
 }
 extern "C" int gmg_dot(gmg_solver *s, const gmg_grid *a, const gmg_grid *b, double *out)
 {
     CHECK_GRIDS2(s, a, b);
     GMG_CUDA(enterCtx(s->ctx));
-    GMG_TRY((launchVec<VO_DOT>(s, a->level, a->d, b->d, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, tmp)), KC_REDUCE, 16.0)));
+    GMG_TRY((reduceOwned<VO_DOT>(s, a->d, b->d, offsetof(Scalars, tmp), 16.0, a->level)));
     return readScalar(s, offsetof(Scalars, tmp), out);
 }
 extern "C" int gmg_norm2(gmg_solver *s, const gmg_grid *a, double *out)
 {
     CHECK_GRIDS2(s, a, a);
     GMG_CUDA(enterCtx(s->ctx));
-    GMG_TRY((launchVec<VO_NORM2>(s, a->level, a->d, nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, tmp)), KC_REDUCE, 8.0)));
+    GMG_TRY((reduceOwned<VO_NORM2>(s, a->d, nullptr, offsetof(Scalars, tmp), 8.0, a->level)));
     return readScalar(s, offsetof(Scalars, tmp), out);
 }
 extern "C" int gmg_inf_norm(gmg_solver *s, const gmg_grid *a, double *out)
 {
     CHECK_GRIDS2(s, a, a);
     GMG_CUDA(enterCtx(s->ctx));
-    GMG_TRY((launchVec<VO_MAX>(s, a->level, a->d, nullptr, nullptr, nullptr, 0, scalarPtr(s, offsetof(Scalars, tmp)), KC_REDUCE, 8.0)));
+    GMG_TRY((reduceOwned<VO_MAX>(s, a->d, nullptr, offsetof(Scalars, tmp), 8.0, a->level)));
     return readScalar(s, offsetof(Scalars, tmp), out);
 }
 extern "C" int gmg_axpy(gmg_solver *s, gmg_grid *dst, const gmg_grid *src, double scale)
@@ -1813,11 +2246,21 @@ extern "C" int gmg_scale(gmg_solver *s, gmg_grid *v, double scale)
     return launchVec<VO_SCALE>(s, v->level, v->d, nullptr, nullptr, nullptr, scale, nullptr, KC_BLAS1, 16.0);
 }
 
+// device-resident grids may have been produced by owned-plane operators: refresh the deep halo the solve starts from
+static int refreshForSolve(gmg_solver *s, double *x, const double *b, bool xMatters)
+{
+    if (!s->lv[0].sharded) return GMG_OK;
+    GMG_TRY(haloExchange(s, 0, const_cast<double *>(b), HALO_STORE0));
+    if (xMatters) GMG_TRY(haloExchange(s, 0, x, HALO_STORE0));
+    return GMG_OK;
+}
+
 extern "C" int gmg_vcycle_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int useInitialGuess)
 {
     CHECK_GRIDS2(s, x, b);
     if (x->level != 0) return invalid("gmg_vcycle_device: grids must be level 0");
     GMG_CUDA(enterCtx(s->ctx));
+    GMG_TRY(refreshForSolve(s, x->d, b->d, useInitialGuess != 0));
     return vcycleDevice(s, x->d, b->d, useInitialGuess != 0);
 }
 extern "C" int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, double tol, int maxIt, int preconditioner, int *iterations,
@@ -1826,14 +2269,15 @@ extern "C" int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, dou
     CHECK_GRIDS2(s, x, b);
     if (x->level != 0) return invalid("gmg_pcg_device: grids must be level 0");
     GMG_CUDA(enterCtx(s->ctx));
+    GMG_TRY(refreshForSolve(s, x->d, b->d, true));
     return pcgDevice(s, x->d, b->d, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount);
 }
 
 static int ensureHostIO(gmg_solver *s)
 {
     if (s->pcgX) return GMG_OK;
-    GMG_TRY(allocZero(&s->pcgX, s->lv[0].g.total));
-    GMG_TRY(allocZero(&s->pcgB, s->lv[0].g.total));
+    GMG_TRY(allocGrid(&s->pcgX, s->lv[0].g));
+    GMG_TRY(allocGrid(&s->pcgB, s->lv[0].g));
     return GMG_OK;
 }
 
@@ -1846,8 +2290,10 @@ extern "C" int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInit
     if (useInitialGuess) GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels));
     GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels));
     GMG_TRY(vcycleDevice(s, s->pcgX, s->pcgB, useInitialGuess != 0));
-    // cells outside the stored box are non-active: the reference leaves them untouched (0 after constant(0))
-    return downloadValues(s->ctx, x, s->pcgX, g.res, g, !useInitialGuess);
+    // cells outside the stored box are non-active: the reference leaves them untouched (0 after constant(0));
+    // a sharded context writes the rank's owned planes only
+    const Geom go = ownedGeom(s->lv[0]);
+    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, !useInitialGuess);
 }
 
 extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations, double *relResHistory,
@@ -1860,5 +2306,6 @@ extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, in
     GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels));
     GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels));
     GMG_TRY(pcgDevice(s, s->pcgX, s->pcgB, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount));
-    return downloadValues(s->ctx, x, s->pcgX, g.res, g, false);
+    const Geom go = ownedGeom(s->lv[0]);
+    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, false);
 }

@@ -61,11 +61,23 @@ struct Geom
     int zBlocks;
 };
 
+// deep-halo depths of the z-slab sharding, in planes of the level they apply to
+constexpr int HALO_X = 8;        // rhs / solution refresh depth per sharded level (7 smoothing sweeps + residual / prolongation)
+constexpr int HALO_P = 9;        // CG search direction at level 0 (A p valid to depth 8 keeps r consistent without its own exchange)
+constexpr int HALO_STORE0 = 10;  // stored halo planes at level 0 (even, >= HALO_P)
+constexpr int HALO_STORE = 8;    // stored halo planes at the other sharded levels
+
 struct Level
 {
-    Geom g;
-    uint8_t *labels = nullptr;
-    int64_t nActive = 0, nInterior = 0;
+    Geom g;                      // LOCAL storage box: the rank's z-slab (+ stored halo) on a sharded level, else == gg
+    Geom gg;                     // global storage box of the level
+    bool sharded = false;
+    int zOff = 0;                // local plane 0 is global storage plane zOff (even)
+    int ownLo = 0, ownHi = 0;    // owned planes [ownLo, ownHi) in local storage coordinates
+    uint8_t *labelsAlloc = nullptr; // the level's labels over the GLOBAL box (every rank holds them; 1 byte per cell)
+    uint8_t *labels = nullptr;   // = labelsAlloc + zOff * plane
+    int64_t nActive = 0, nInterior = 0; // over the local stored box
+    int64_t nActiveGlobal = 0;
     // boundary band: [0,nBoundary) BOUNDARY cells, [nBoundary,nBand) INTERIOR cells of the band; linear order inside each part
     int nBoundary = 0, nBand = 0;
     int32_t *bandIdx = nullptr;  // [nBand] storage index
@@ -108,7 +120,8 @@ struct gmg_ctx
     int smCount = 148;
     // sharding (z-slabs); world == 1 means single GPU
     int rank = 0, world = 1;
-    void *nccl = nullptr;
+    void *nccl = nullptr;         // ncclComm_t
+    int64_t commOps = 0;          // NCCL operations (groups) enqueued since the last launch-count reset
     // reduction scratch
     double *partials = nullptr;   // [maxPartials]
     unsigned *ticket = nullptr;
@@ -131,6 +144,9 @@ struct gmg_solver
     int nCoarse = 0;
     int32_t *coarseIdx = nullptr; // [nCoarse] storage index at the coarsest level
     double *coarseInv = nullptr;  // [nCoarse][nCoarse] row-major inverse
+    // z-slab sharding: levels [0, shardLevels) are slabs, the rest replicated on every rank
+    int shardLevels = 0;
+    std::vector<int> gatherLo, gatherHi; // per rank: planes of the first replicated level it restricts into
     // persistent coarse sub-V-cycle: levels [fusedFirst, levels-1] in one cluster kernel (-1 = off)
     int fusedFirst = -1;
     int clusterSize = 8;
@@ -144,7 +160,7 @@ struct gmg_solver
     {
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t exec = nullptr;
-	int64_t kernels = 0;
+	int64_t kernels = 0, comms = 0;
     };
     std::map<std::tuple<int, const void *, const void *, int>, GraphEntry> graphs;
     bool useGraphs = true;
@@ -155,6 +171,7 @@ struct gmg_grid
     gmg_solver *solver = nullptr;
     int level = 0;
     double *d = nullptr;
+    int64_t plane = 0; // guard-plane size: the allocation starts at d - plane
 };
 
 namespace gmg

@@ -79,7 +79,7 @@ __device__ __forceinline__ bool gridReduce(double v, double *partials, unsigned 
     acc = blockReduce<IS_MAX>(acc);
     if (threadIdx.x == 0)
     {
-	*result = acc;
+	if (result) *result = acc;
 	*ticket = 0u;
 	return true;
     }

@@ -62,6 +62,20 @@ int gmg_ctx_synchronize(gmg_ctx *ctx);
  * MPI / files -- the library does not care).  Must be called before gmg_solver_create. */
 int gmg_ctx_shard(gmg_ctx *ctx, int rank, int world, const void *nccl_unique_id);
 int gmg_nccl_unique_id(void *out128);
+int gmg_ctx_rank(gmg_ctx *ctx, int *rank, int *world);
+/* Sharded contexts (the reference has no counterpart: it is one shared-memory process).  Levels
+ * [0, S) are cut into z-slabs with nesting cut planes, one per rank, stored with a deep halo that is recomputed
+ * redundantly (two plane exchanges per level per V-cycle instead of one per sweep); levels [S, L) are replicated.
+ * Every rank passes the SAME full host grids to gmg_solver_create / gmg_grid_upload / gmg_vcycle / gmg_pcg and keeps
+ * its slab; host outputs (gmg_grid_download, x of gmg_vcycle / gmg_pcg) carry the rank's OWNED z-planes only.
+ * Scalars (dot products, norms, iteration counts, residual histories) are identical on every rank.
+ *
+ * gmg_shard_plan is the pure host function behind the partition (no device needed): levelPlanes[l] = z extent of level
+ * l's storage box, levelShiftZ[l]: coarse plane = (fine plane >> 1) + shift, levelCells[l] = cells of the box.  It returns
+ * the number of sharded levels S (<= maxShardLevels, boxes of >= minCells cells, every rank owning at least the halo
+ * depth) and cuts[l*(world+1) + k] = first storage plane of rank k at level l (even; cuts nest between levels). */
+int gmg_shard_plan(const int64_t *levelPlanes, const int64_t *levelShiftZ, const int64_t *levelCells, int levels, int world,
+		   int maxShardLevels, int64_t minCells, int *shardLevels, int64_t *cuts);
 
 /* ---- domain builders (integer work, bit-exact) --------------------------------------------------- */
 /* HDK_GeometricMultigridOperators.h:1340-1360: level count, padding, power-of-two expanded resolution. */
@@ -111,7 +125,9 @@ int gmg_solver_level_res(gmg_solver *s, int level, int64_t res[3]);
 /* per-level labels / boundary-band lists in expanded coordinates, for bit-exact checks */
 int gmg_solver_get_labels(gmg_solver *s, int level, int32_t *out);
 int gmg_solver_get_boundary_cells(gmg_solver *s, int level, int64_t *xyz, int64_t *count);
-int gmg_solver_active_cells(gmg_solver *s, int level, int64_t *count);
+int gmg_solver_active_cells(gmg_solver *s, int level, int64_t *count); /* over the whole level, also when sharded */
+/* sharded: is this level a z-slab; expanded z range [lo, hi) of the rank's owned planes; active cells it stores */
+int gmg_solver_shard_info(gmg_solver *s, int level, int *sharded, int64_t *ownLoZ, int64_t *ownHiZ, int64_t *localActive);
 int gmg_solver_coarse_unknowns(gmg_solver *s, int64_t *count);
 int gmg_solver_setup_ms(gmg_solver *s, double *ms);
 
@@ -163,6 +179,8 @@ int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, double tol, in
 /* ---- measurement hooks ----------------------------------------------------------------------------- */
 /* kernels launched by this library on this context since the last reset (bench.py's gpu_launches) */
 int gmg_launch_count(gmg_ctx *ctx, int64_t *count, int reset);
+/* NCCL operations (halo exchanges, gathers, scalar all-reduces) enqueued since the last gmg_launch_count reset */
+int gmg_comm_count(gmg_ctx *ctx, int64_t *count);
 /* CUDA-event timing on the context's stream: begin/end bracket, result in ms */
 int gmg_timer_begin(gmg_ctx *ctx);
 int gmg_timer_end(gmg_ctx *ctx, double *ms);

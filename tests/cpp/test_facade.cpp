@@ -8,6 +8,10 @@
 //
 // Gates: labels / coarse labels / boundary lists bit-exact; every operator <= 1e-13 relative L-inf;
 // PCG residual history <= 1e-5 relative per iteration, iteration count +-1, pressure <= 1e-5 relative L-inf.
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -96,8 +100,21 @@ static std::vector<double> parseHistory(const std::string &out, int *iterations)
     return h;
 }
 
+static void onSegv(int sig)
+{
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "test_facade: fatal signal, backtrace:\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 int main(int argc, char **argv)
 {
+    setvbuf(stdout, nullptr, _IONBF, 0);
+    signal(SIGSEGV, onSegv);
+    signal(SIGBUS, onSegv);
     if (argc < 2) { std::printf("usage: test_facade <input.bin>\n"); return 2; }
     std::ifstream in(argv[1], std::ios::binary);
     int32_t n[3];
@@ -140,6 +157,11 @@ int main(int argc, char **argv)
     Weights wR, wN;
     for (int a = 0; a < 3; ++a)
     {
+	// the reference expects the caller to size the expanded face grid (Test.cpp:182-197 does); the facade sizes its own
+	UT_Vector3I fr = labR.getVoxelRes();
+	fr[a] += 1;
+	wR[a].size(int(fr[0]), int(fr[1]), int(fr[2]));
+	wR[a].constant(0);
 	Ref::buildExpandedBoundaryWeights(wR[a], baseW[a], labR, pr.first, a);
 	New::buildExpandedBoundaryWeights(wN[a], baseW[a], labN, pn.first, a);
 	EXPECT(sameGrid(wR[a], wN[a]), "buildExpandedBoundaryWeights differs on axis %d", a);

@@ -175,7 +175,9 @@ def test_diagonal_free_plain_cg_matches_oracle_operators(gpu_ctx, port):
     labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
     s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
     b = D.random_rhs(labels, dx, 3)
-    cap = 40  # unpreconditioned CG drifts chaotically over hundreds of iterations; compare a bounded prefix
+    # unpreconditioned CG on this system is chaotic: two summation orders drift apart by ~2.4x per iteration (1e-15 at
+    # iteration 3, O(1) by iteration 40 -- measured), so only a short prefix can be compared
+    cap = 12
     x, it, hist = s.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, cap, useMGPreconditioner=False)
     xr = np.zeros_like(b)
     r = b.copy()
@@ -196,7 +198,7 @@ def test_diagonal_free_plain_cg_matches_oracle_operators(gpu_ctx, port):
         p = port.add_scaled(r, p, rho_new / rho, labels)
         rho = rho_new
     assert it == cap and len(hist) == len(hist_o) == cap
-    assert (np.abs(hist - np.array(hist_o)) / np.array(hist_o)).max() < 1e-6
+    assert (np.abs(hist - np.array(hist_o)) / np.array(hist_o)).max() < 1e-8
     assert relerr(x, xr) < 1e-8
     s.close()
 
