@@ -36,9 +36,9 @@ ABI_SYMBOLS = [
     "gmg_solver_default_options", "gmg_solver_create", "gmg_solver_destroy", "gmg_solver_levels", "gmg_solver_level_res",
     "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms",
     "gmg_vcycle", "gmg_pcg", "gmg_grid_create", "gmg_grid_destroy", "gmg_grid_upload", "gmg_grid_download", "gmg_grid_zero", "gmg_grid_copy",
-    "gmg_jacobi", "gmg_boundary_jacobi", "gmg_apply", "gmg_residual", "gmg_restrict", "gmg_prolong_add", "gmg_dot", "gmg_norm2", "gmg_inf_norm",
+    "gmg_jacobi", "gmg_gauss_seidel", "gmg_boundary_jacobi", "gmg_apply", "gmg_residual", "gmg_restrict", "gmg_prolong_add", "gmg_dot", "gmg_norm2", "gmg_inf_norm",
     "gmg_axpy", "gmg_add_scaled", "gmg_scale", "gmg_vcycle_device", "gmg_pcg_device", "gmg_launch_count", "gmg_timer_begin", "gmg_timer_end",
-    "gmg_profile_enable", "gmg_kernel_class_count", "gmg_kernel_class_name", "gmg_profile_get", "gmg_profile_reset",
+    "gmg_profile_enable", "gmg_kernel_class_count", "gmg_kernel_class_name", "gmg_profile_get", "gmg_profile_reset", "gmg_profile_get_level",
 ]
 
 
@@ -182,6 +182,19 @@ class Context:
             ms, n, by = C.c_double(), C.c_int64(), C.c_double()
             _check(self.lib.gmg_profile_get(self.h, i, int(fine_level_only), C.byref(ms), C.byref(n), C.byref(by)))
             out[self.lib.gmg_kernel_class_name(i).decode()] = (ms.value, int(n.value), by.value)
+        return out
+
+    def profile_by_level(self, levels):
+        """{level: {class name: (ms, launches)}} for the classes that ran on that level."""
+        out = {}
+        for l in range(levels):
+            row = {}
+            for i in range(self.lib.gmg_kernel_class_count()):
+                ms, n = C.c_double(), C.c_int64()
+                _check(self.lib.gmg_profile_get_level(self.h, i, l, C.byref(ms), C.byref(n)))
+                if n.value:
+                    row[self.lib.gmg_kernel_class_name(i).decode()] = (ms.value, int(n.value))
+            out[l] = row
         return out
 
     def close(self):
@@ -390,6 +403,9 @@ class GeometricMultigridPoissonSolver:
 
     def jacobiPoissonSmoother(self, x: Grid, b: Grid):
         _check(self.lib.gmg_jacobi(self.h, x.h, b.h))
+
+    def tiledGaussSeidelPoissonSmoother(self, x: Grid, b: Grid, doSmoothOddTiles: bool, doSmoothForward: bool):
+        _check(self.lib.gmg_gauss_seidel(self.h, x.h, b.h, int(doSmoothOddTiles), int(doSmoothForward)))
 
     def boundaryJacobiPoissonSmoother(self, x: Grid, b: Grid, sweeps=1):
         _check(self.lib.gmg_boundary_jacobi(self.h, x.h, b.h, int(sweeps)))

@@ -26,7 +26,8 @@ namespace
 {
 thread_local std::string g_lastError;
 const char *kClassNames[KC_COUNT] = {"jacobi_interior", "apply_poisson", "residual", "band_jacobi", "restrict", "prolong_add",
-				     "coarse_solve",    "blas1",         "reduce",   "zero_fill",   "setup",    "halo_exchange"};
+				     "coarse_solve",    "blas1",         "reduce",   "zero_fill",   "setup",    "halo_exchange",
+				     "gauss_seidel"};
 inline int64_t divUp(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int floorDiv2(int64_t v) { return int(v >= 0 ? v / 2 : -((-v + 1) / 2)); }
 inline int ceilDiv2(int64_t v) { return int(v >= 0 ? (v + 1) / 2 : -((-v) / 2)); }
@@ -56,12 +57,14 @@ LaunchScope::LaunchScope(gmg_ctx *c, int k, double b) : ctx(c), klass(k), bytes(
     };
     e0 = get();
     e1 = get();
-    cudaEventRecord(e0, ctx->stream);
+    if (ctx->capturing) cudaEventRecordWithFlags(e0, ctx->stream, cudaEventRecordExternal);
+    else cudaEventRecord(e0, ctx->stream);
 }
 LaunchScope::~LaunchScope()
 {
     if (!ctx->profiling) return;
-    cudaEventRecord(e1, ctx->stream);
+    if (ctx->capturing) cudaEventRecordWithFlags(e1, ctx->stream, cudaEventRecordExternal);
+    else cudaEventRecord(e1, ctx->stream);
     ctx->recs.push_back({klass, ctx->curLevel, bytes, e0, e1});
 }
 } // namespace gmg
@@ -109,6 +112,31 @@ static void freeGrid(double *p, const Geom &g)
     if (p) devFree(p - g.plane);
 }
 
+// Programmatic dependent launch: a V-cycle is a chain of ~60 dependent kernels, most of them a few microseconds long, so the
+// launch-to-launch gap matters as much as the kernels.  Every hot kernel starts with griddepcontrol.launch_dependents +
+// griddepcontrol.wait (gmg_kernels.cuh: pdlEnter), and is launched with the programmatic-stream-serialization attribute:
+// the next kernel's CTAs are set up while the current one still runs and only wait for its memory to be flushed.
+static bool usePdl()
+{
+    static const bool v = [] { const char *e = getenv("GMG_PDL"); return !(e && e[0] == '0'); }();
+    return v;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launchK(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = usePdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 #define TRACE(msg) do { if (getenv("GMG_TRACE")) { fprintf(stderr, "[gmg] %s:%d %s\n", __func__, __LINE__, msg); fflush(stderr); } } while (0)
 
 static int invalid(const char *msg)
@@ -117,11 +145,9 @@ static int invalid(const char *msg)
     return GMG_ERR_INVALID;
 }
 
-static void flushProfile(gmg_ctx *ctx)
+static void accumulateRecs(gmg_ctx *ctx, const std::vector<ProfileRec> &recs, bool recycle)
 {
-    if (ctx->recs.empty()) return;
-    cudaStreamSynchronize(ctx->stream);
-    for (auto &r : ctx->recs)
+    for (auto &r : recs)
     {
 	float ms = 0;
 	cudaEventElapsedTime(&ms, r.e0, r.e1);
@@ -131,9 +157,19 @@ static void flushProfile(gmg_ctx *ctx)
 	    ctx->classLaunches[f][r.klass] += 1;
 	    ctx->classBytes[f][r.klass] += r.bytes;
 	}
-	ctx->eventPool.push_back(r.e0);
-	ctx->eventPool.push_back(r.e1);
+	if (r.level >= 0 && r.level < 16) { ctx->levelMs[r.level][r.klass] += ms; ctx->levelLaunches[r.level][r.klass] += 1; }
+	if (recycle)
+	{
+	    ctx->eventPool.push_back(r.e0);
+	    ctx->eventPool.push_back(r.e1);
+	}
     }
+}
+static void flushProfile(gmg_ctx *ctx)
+{
+    if (ctx->recs.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    accumulateRecs(ctx, ctx->recs, true);
     ctx->recs.clear();
 }
 
@@ -367,6 +403,16 @@ extern "C" int gmg_profile_reset(gmg_ctx *ctx)
     flushProfile(ctx);
     for (int f = 0; f < 2; ++f)
 	for (int i = 0; i < KC_COUNT; ++i) { ctx->classMs[f][i] = 0; ctx->classLaunches[f][i] = 0; ctx->classBytes[f][i] = 0; }
+    for (int l = 0; l < 16; ++l)
+	for (int i = 0; i < KC_COUNT; ++i) { ctx->levelMs[l][i] = 0; ctx->levelLaunches[l][i] = 0; }
+    return GMG_OK;
+}
+extern "C" int gmg_profile_get_level(gmg_ctx *ctx, int klass, int level, double *ms, int64_t *launches)
+{
+    if (klass < 0 || klass >= KC_COUNT || level < 0 || level >= 16) return invalid("bad kernel class / level");
+    flushProfile(ctx);
+    if (ms) *ms = ctx->levelMs[level][klass];
+    if (launches) *launches = ctx->levelLaunches[level][klass];
     return GMG_OK;
 }
 
@@ -443,9 +489,39 @@ static void parallelRows(int64_t rows, const Fn &fn)
     for (auto &t : th) t.join();
 }
 
+// page-locked caller memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) is DMA'd in place: one strided 3D copy
+// of the cropped box, no host-side gather
+static bool isPinnedHost(const void *p)
+{
+    static const bool off = [] { const char *e = getenv("GMG_NO_DIRECT_DMA"); return e && e[0] == '1'; }();
+    if (off) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+template <typename T>
+static int copyBox3D(gmg_ctx *ctx, T *staging, T *host, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3], bool toDevice)
+{
+    const size_t nx = size_t(hi[0] - lo[0]), ny = size_t(hi[1] - lo[1]), nz = size_t(hi[2] - lo[2]);
+    const size_t x0 = size_t(g.org[0] + lo[0]), y0 = size_t(g.org[1] + lo[1]), z0 = size_t(g.org[2] + lo[2]);
+    cudaMemcpy3DParms p = {};
+    const cudaPitchedPtr hp = make_cudaPitchedPtr(host, size_t(hostRes[0]) * sizeof(T), size_t(hostRes[0]) * sizeof(T), size_t(hostRes[1]));
+    const cudaPitchedPtr dp = make_cudaPitchedPtr(staging, nx * sizeof(T), nx * sizeof(T), ny);
+    const cudaPos hpos = make_cudaPos(x0 * sizeof(T), y0, z0), dpos = make_cudaPos(0, 0, 0);
+    p.srcPtr = toDevice ? hp : dp;
+    p.srcPos = toDevice ? hpos : dpos;
+    p.dstPtr = toDevice ? dp : hp;
+    p.dstPos = toDevice ? dpos : hpos;
+    p.extent = make_cudaExtent(nx * sizeof(T), ny, nz);
+    p.kind = toDevice ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    return GMG_OK;
+}
+
 template <typename T>
 static int copyBoxH2D(gmg_ctx *ctx, T *staging, const T *host, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3])
 {
+    if (isPinnedHost(host)) return copyBox3D(ctx, staging, const_cast<T *>(host), hostRes, g, lo, hi, true);
     GMG_TRY(ensurePinned(ctx));
     const int64_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
     const int64_t x0 = g.org[0] + lo[0], y0 = g.org[1] + lo[1], z0 = g.org[2] + lo[2];
@@ -473,6 +549,7 @@ static int copyBoxH2D(gmg_ctx *ctx, T *staging, const T *host, const int64_t hos
 template <typename T>
 static int copyBoxD2H(gmg_ctx *ctx, T *host, const T *staging, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3])
 {
+    if (isPinnedHost(host)) return copyBox3D(ctx, const_cast<T *>(staging), host, hostRes, g, lo, hi, false);
     GMG_TRY(ensurePinned(ctx));
     const int64_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
     const int64_t x0 = g.org[0] + lo[0], y0 = g.org[1] + lo[1], z0 = g.org[2] + lo[2];
@@ -777,6 +854,42 @@ static int buildChunks(gmg_ctx *ctx, Level &L)
     return GMG_OK;
 }
 
+// tile lists of the tiled Gauss-Seidel smoother (Ops.h:441-448: tiles of the expanded grid, parity of tx+ty+tz)
+static int buildGsTiles(gmg_ctx *ctx, Level &L)
+{
+    const Geom &g = L.g;
+    auto floorDiv16 = [](int v) { return v >= 0 ? v / 16 : -((-v + 15) / 16); };
+    int t0[3], nt[3];
+    for (int a = 0; a < 3; ++a)
+    {
+	t0[a] = floorDiv16(g.org[a]);
+	nt[a] = int(divUp(g.org[a] + g.n[a], 16)) - t0[a];
+	L.gsOff[a] = t0[a] * 16 - g.org[a];
+    }
+    L.gsTilesX = nt[0];
+    L.gsTilesY = nt[1];
+    const int nTiles = nt[0] * nt[1] * nt[2];
+    uint8_t *fo = nullptr, *fe = nullptr;
+    GMG_CUDA(devMalloc(&fo, nTiles));
+    GMG_CUDA(devMalloc(&fe, nTiles));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_gs_tile_flags<<<nTiles, BLOCK, 0, ctx->stream>>>(fo, fe, L.labels, nt[0], nt[1], L.gsOff[0], L.gsOff[1], L.gsOff[2], g.n[0], g.n[1], g.n[2], g.pitch,
+							  g.plane, (t0[0] + t0[1] + t0[2]) & 1);
+    }
+    GMG_TRY(selectFlagged(ctx, fe, nTiles, &L.gsTiles[0], &L.nGsTiles[0]));
+    GMG_TRY(selectFlagged(ctx, fo, nTiles, &L.gsTiles[1], &L.nGsTiles[1]));
+    GMG_CUDA(devFree(fo));
+    GMG_CUDA(devFree(fe));
+    GMG_CUDA(devMalloc(&L.bpos, sizeof(int32_t) * g.total));
+    if (L.nBoundary > 0)
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_band_pos<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bpos, L.bandIdx, L.nBoundary);
+    }
+    return GMG_OK;
+}
+
 // band list in the reference's order (tile, z, y, x) and expanded coordinates
 // (a sharded level exports the cells of the rank's owned planes; the ranks' lists tile the global one)
 static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count)
@@ -826,6 +939,7 @@ static void freeLevel(Level &L)
     devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandIdx); devFree(L.bandNbr); devFree(L.bcoef);
     devFree(L.bandV0); devFree(L.bandV1); devFree(L.bandB);
     devFree(L.chunksInterior); devFree(L.chunksActive);
+    devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
     L = Level();
 }
@@ -1368,7 +1482,8 @@ extern "C" int gmg_solver_destroy(gmg_solver *s)
     enterCtx(s->ctx);
     cudaStreamSynchronize(s->ctx->stream);
     for (auto &g : s->graphs) { cudaGraphExecDestroy(g.second.exec); cudaGraphDestroy(g.second.graph); }
-    devFree(s->coarseIdx); devFree(s->coarseInv); devFree(s->devLevels);
+    devFree(s->coarseIdx); devFree(s->coarseInv); devFree(s->compactBlob);
+    delete static_cast<CompactArgs *>(s->compactArgs);
     if (!s->lv.empty())
     {
 	const Geom &g0 = s->lv[0].g;
@@ -1398,12 +1513,14 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     if (optIn) s->opt = *optIn;
     else gmg_solver_default_options(&s->opt);
     if (const char *e = getenv("GMG_NO_GRAPHS")) s->useGraphs = !(e[0] == '1');
+    if (const char *e = getenv("GMG_PRINT_STATS")) s->opt.print_stats = (e[0] == '1');
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
-    if (s->opt.use_gauss_seidel)
+    if (s->opt.use_gauss_seidel && ctx->world > 1)
     {
 	delete s;
-	return invalid("gmg_solver_create: the tiled Gauss-Seidel smoother is not built in this revision; pass use_gauss_seidel = 0");
+	return invalid("gmg_solver_create: the tiled Gauss-Seidel smoother is not available on a sharded context (its in-tile dependencies reach 16 "
+		       "cells, beyond the deep halo); use the damped-Jacobi smoother there");
     }
     auto fail = [&](int st) { gmg_solver_destroy(s); return st; };
     double tPhase = tStart;
@@ -1481,6 +1598,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	const bool fw = level == 0 && dW[0];
 	if ((st = buildCoefs(ctx, L, fw ? dW[0] + wOff : nullptr, fw ? dW[1] + wOff : nullptr, fw ? dW[2] + wOff : nullptr)) != GMG_OK) return fail(st);
 	if ((st = buildChunks(ctx, L)) != GMG_OK) return fail(st);
+	if (s->opt.use_gauss_seidel && (st = buildGsTiles(ctx, L)) != GMG_OK) return fail(st);
 	maxGrid = std::max(maxGrid, L.nChunksActive + int(divUp(L.nBoundary, BLOCK)) + 1);
 	if ((st = allocGrid(&L.xAlt, L.g)) != GMG_OK) return fail(st);
 	if ((st = allocGrid(&L.r, L.g)) != GMG_OK) return fail(st);
@@ -1611,22 +1729,22 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
     if (mode == SM_JACOBI)
     {
 	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 25.0);
-	k_stencil<SM_JACOBI, false><<<grid, BLOCK, 0, st>>>(a);
+	GMG_CUDA(launchK((k_stencil<SM_JACOBI, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     else if (mode == SM_RESIDUAL)
     {
 	GMG_LAUNCH(s->ctx, KC_RESIDUAL, n * 25.0);
-	k_stencil<SM_RESIDUAL, false><<<grid, BLOCK, 0, st>>>(a);
+	GMG_CUDA(launchK((k_stencil<SM_RESIDUAL, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     else if (dotResult)
     {
 	GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
-	k_stencil<SM_APPLY, true><<<grid, BLOCK, 0, st>>>(a);
+	GMG_CUDA(launchK((k_stencil<SM_APPLY, true>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     else
     {
 	GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
-	k_stencil<SM_APPLY, false><<<grid, BLOCK, 0, st>>>(a);
+	GMG_CUDA(launchK((k_stencil<SM_APPLY, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
@@ -1658,21 +1776,21 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
     a.vout = cur;
     {
 	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
-	if (zeroGrid) k_band<false, false, true, true><<<grid, BLOCK, 0, st>>>(a);
-	else k_band<false, false, true, false><<<grid, BLOCK, 0, st>>>(a);
+	if (zeroGrid) GMG_CUDA(launchK((k_band<false, false, true, true>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	else GMG_CUDA(launchK((k_band<false, false, true, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     if (sweeps == 1)
     {
 	GMG_LAUNCH(s->ctx, KC_BAND, double(L.nBand) * 20.0);
-	k_band_scatter<<<grid, BLOCK, 0, st>>>(x, L.bandIdx, cur, L.nBand);
+	GMG_CUDA(launchK(k_band_scatter, unsigned(grid), unsigned(BLOCK), size_t(0), st, x, L.bandIdx, cur, L.nBand));
     }
     for (int sw = 2; sw <= sweeps; ++sw)
     {
 	a.vin = cur;
 	a.vout = nxt;
 	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
-	if (sw == sweeps) k_band<true, true, false, false><<<grid, BLOCK, 0, st>>>(a);
-	else k_band<true, false, false, false><<<grid, BLOCK, 0, st>>>(a);
+	if (sw == sweeps) GMG_CUDA(launchK((k_band<true, true, false, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	else GMG_CUDA(launchK((k_band<true, false, false, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
 	std::swap(cur, nxt);
     }
     GMG_CUDA(cudaGetLastError());
@@ -1711,7 +1829,7 @@ static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const do
     a.zlo = zr.lo;
     a.zhi = zr.hi;
     GMG_LAUNCH(s->ctx, KC_RESTRICT, double(s->lv[fineLevel].nActive) * 8.0 + double(C.nActive) * 9.0);
-    k_restrict<<<C.nChunksActive, BLOCK, 0, s->ctx->stream>>>(a);
+    GMG_CUDA(launchK(k_restrict, unsigned(C.nChunksActive * RESTRICT_SPLIT), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }
@@ -1729,7 +1847,7 @@ static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const doubl
     a.zlo = zr.lo;
     a.zhi = zr.hi;
     GMG_LAUNCH(s->ctx, KC_PROLONG, double(F.nActive) * 17.0 + double(s->lv[fineLevel + 1].nActive) * 8.0);
-    k_prolong<<<F.nChunksActive, BLOCK, 0, s->ctx->stream>>>(a);
+    GMG_CUDA(launchK(k_prolong, unsigned(F.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }
@@ -1740,7 +1858,7 @@ static int launchZero(gmg_solver *s, int level, double *x)
     const Level &L = s->lv[level];
     if (L.nChunksActive == 0) return GMG_OK;
     GMG_LAUNCH(s->ctx, KC_ZERO, double(L.nActive) * 8.0);
-    k_zero<<<L.nChunksActive, BLOCK, 0, s->ctx->stream>>>(x, L.chunksActive, L.g.chunksPerPlane, L.g.plane, L.g.n[2]);
+    GMG_CUDA(launchK(k_zero, unsigned(L.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, x, L.chunksActive, L.g.chunksPerPlane, L.g.plane, L.g.n[2]));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }
@@ -1750,43 +1868,191 @@ static int launchCoarse(gmg_solver *s, double *x, const double *b)
     s->ctx->curLevel = s->levels - 1;
     const int n = s->nCoarse;
     GMG_LAUNCH(s->ctx, KC_COARSE, double(n) * n * 8.0);
-    k_coarse_solve<<<unsigned(divUp(n, BLOCK / 32)), BLOCK, sizeof(double) * n, s->ctx->stream>>>(x, b, s->coarseIdx, s->coarseInv, n);
+    GMG_CUDA(launchK(k_coarse_solve, unsigned(unsigned(divUp(n, BLOCK / 32))), unsigned(BLOCK), size_t(sizeof(double) * n), s->ctx->stream, x, b, s->coarseIdx, s->coarseInv, n));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }
 
-// levels [fusedFirst, levels-1] in one persistent cluster kernel (gmg_kernels.cuh: k_coarse_cycle)
+// levels [fusedFirst, levels-1] in one shared-memory CTA (gmg_kernels.cuh: k_compact_cycle).  The tables are built on the
+// host: these levels hold a few thousand cells at most.
 static int buildFusedCycle(gmg_solver *s)
 {
     s->fusedFirst = -1;
     const char *e = getenv("GMG_COARSE_FUSED");
     if (e && e[0] == '0') return GMG_OK;
-    if (s->opt.operators_only || s->levels < 3) return GMG_OK;
-    int64_t limit = 12000;  // above this a level has enough work to fill the machine through ordinary launches
-    if (const char *c = getenv("GMG_FUSED_CELLS")) limit = atoll(c);
+    if (s->opt.operators_only || s->levels < 2) return GMG_OK;
+    if (s->opt.use_gauss_seidel) return GMG_OK;  // the compact cycle implements the Jacobi interior sweep only
+    gmg_ctx *ctx = s->ctx;
+    int smemMax = 0;
+    GMG_CUDA(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    // finest level (>= 1: level 0 carries face weights and the caller's grids; replicated levels only) whose vectors
+    // (3 doubles per cell) and 16-bit index tables (<= 12 + 128 + 16 + 2 bytes per cell) fit one CTA's shared memory
+    auto smemOf = [&](int first) {
+	size_t bytes = 0;
+	for (int l = first; l < s->levels; ++l)
+	{
+	    const size_t n = size_t(s->lv[l].nActive);
+	    bytes += n * (3 * sizeof(double) + 12 + 2 + 16) + (l > first ? n * 128 : 0) + 64;
+	}
+	return bytes + size_t(s->nCoarse) * 2 + 64;
+    };
     int first = -1;
-    for (int l = std::max(1, s->shardLevels); l < s->levels - 1; ++l)  // replicated levels only
-	if (s->lv[l].nActive <= limit) { first = l; break; }
-    if (first < 0) return GMG_OK;
-    s->clusterSize = 8;
-    if (const char *c = getenv("GMG_CLUSTER")) s->clusterSize = std::max(1, std::min(16, atoi(c)));
-    if (s->clusterSize > 8) GMG_CUDA(cudaFuncSetAttribute(k_coarse_cycle, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    std::vector<DevLevel> h(s->levels);
-    for (int l = 0; l < s->levels; ++l)
+    for (int l = std::max(1, s->shardLevels); l < s->levels; ++l)
+	if (s->levels - l <= CYCLE_MAX_LEVELS && s->lv[l].nActive < 65535 && smemOf(l) + 1024 <= size_t(smemMax)) { first = l; break; }
+    if (const char *c = getenv("GMG_FUSED_FIRST")) first = std::max(first, atoi(c));
+    if (first < 0 || first >= s->levels) return GMG_OK;
+    if (first == s->levels - 1) return GMG_OK;  // only the direct solve: its own kernel does that
+    const int nl = s->levels - first;
+    struct HostLevel
     {
-	const Level &L = s->lv[l];
-	DevLevel &d = h[l];
-	d.labels = L.labels; d.x = L.x; d.xAlt = L.xAlt; d.b = L.b; d.r = L.r;
-	d.chunksInterior = L.chunksInterior; d.chunksActive = L.chunksActive;
-	d.nChunksInterior = L.nChunksInterior; d.nChunksActive = L.nChunksActive;
-	d.chunksPerPlane = L.g.chunksPerPlane; d.pitch = L.g.pitch; d.ny = L.g.n[1]; d.nz = L.g.n[2]; d.plane = L.g.plane;
-	d.nBoundary = L.nBoundary; d.nBand = L.nBand; d.bandIdx = L.bandIdx; d.bandNbr = L.bandNbr; d.bcoef = L.bcoef;
-	d.bandV0 = L.bandV0; d.bandV1 = L.bandV1; d.bandB = L.bandB;
-	for (int k = 0; k < 3; ++k) d.shift[k] = L.shift[k];
+	std::vector<int32_t> cell, pos;
+	std::vector<uint16_t> nbr, rst, pro;
+	std::vector<uint8_t> diag, flags, lab;
+    };
+    std::vector<HostLevel> h(nl);
+    for (int q = 0; q < nl; ++q)
+    {
+	const Level &L = s->lv[first + q];
+	const Geom &g = L.g;
+	HostLevel &H = h[q];
+	H.lab.resize(g.total);
+	GMG_CUDA(cudaMemcpy(H.lab.data(), L.labels, g.total, cudaMemcpyDeviceToHost));
+	H.pos.assign(g.total, -1);
+	for (int64_t i = 0; i < g.total; ++i)
+	    if (H.lab[i] == L_INTERIOR || H.lab[i] == L_BOUNDARY) { H.pos[i] = int32_t(H.cell.size()); H.cell.push_back(int32_t(i)); }
+	const int n = int(H.cell.size());
+	if (n != L.nActive) return invalid("compact coarse cycle: active-cell count mismatch");
+	H.nbr.assign(size_t(6) * n, CYCLE_NONE);
+	H.diag.assign(n, 0);
+	H.flags.assign(n, 0);
+	const int64_t stride[6] = {-1, 1, -int64_t(g.pitch), int64_t(g.pitch), -g.plane, g.plane};
+	for (int k = 0; k < n; ++k)
+	{
+	    const int64_t i = H.cell[k];
+	    int diag = 0;
+	    for (int d = 0; d < 6; ++d)
+	    {
+		const int nlab = H.lab[i + stride[d]];
+		if (nlab == L_INTERIOR || nlab == L_BOUNDARY) { H.nbr[size_t(d) * n + k] = uint16_t(H.pos[i + stride[d]]); ++diag; }
+		else if (nlab == L_DIRICHLET) ++diag;
+	    }
+	    H.diag[k] = uint8_t(diag);  // 6 for an INTERIOR cell (all neighbours active by construction)
+	    const int z = int(i / g.plane);
+	    const int64_t rem = i - int64_t(z) * g.plane;
+	    const int y = int(rem / g.pitch), x = int(rem - int64_t(y) * g.pitch);
+	    H.flags[k] = uint8_t(((x & 1) << 1) | ((y & 1) << 2) | ((z & 1) << 3));
+	}
+	std::vector<int32_t> band(std::max(L.nBand, 1));
+	GMG_CUDA(cudaMemcpy(band.data(), L.bandIdx, sizeof(int32_t) * L.nBand, cudaMemcpyDeviceToHost));
+	for (int k = 0; k < L.nBand; ++k) H.flags[H.pos[band[k]]] |= 1;
     }
-    GMG_CUDA(devMalloc(&s->devLevels, sizeof(DevLevel) * s->levels));
-    GMG_CUDA(cudaMemcpyAsync(s->devLevels, h.data(), sizeof(DevLevel) * s->levels, cudaMemcpyHostToDevice, s->ctx->stream));
-    GMG_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    auto compact = [](int32_t p) { return p < 0 ? uint16_t(CYCLE_NONE) : uint16_t(p); };
+    for (int q = 0; q < nl; ++q)
+    {
+	const Level &L = s->lv[first + q];
+	const Geom &g = L.g;
+	HostLevel &H = h[q];
+	const int n = int(H.cell.size());
+	if (q > 0)
+	{
+	    // restriction taps of this (coarse) level in the next finer compact level (Ops.h:760-834)
+	    const Level &F = s->lv[first + q - 1];
+	    const HostLevel &HF = h[q - 1];
+	    H.rst.assign(size_t(64) * n, CYCLE_NONE);
+	    for (int k = 0; k < n; ++k)
+	    {
+		const int64_t i = H.cell[k];
+		const int cz = int(i / g.plane);
+		const int64_t rem = i - int64_t(cz) * g.plane;
+		const int cy = int(rem / g.pitch), cx = int(rem - int64_t(cy) * g.pitch);
+		const int fx = 2 * (cx - F.shift[0]) - 1, fy = 2 * (cy - F.shift[1]) - 1, fz = 2 * (cz - F.shift[2]) - 1;
+		for (int z = 0; z < 4; ++z)
+		    for (int y = 0; y < 4; ++y)
+			for (int x = 0; x < 4; ++x)
+			{
+			    const int X = fx + x, Y = fy + y, Z = fz + z;
+			    if (X < 0 || Y < 0 || Z < 0 || X >= F.g.n[0] || Y >= F.g.n[1] || Z >= F.g.n[2]) continue;
+			    H.rst[size_t((z * 4 + y) * 4 + x) * n + k] = compact(HF.pos[int64_t(Z) * F.g.plane + int64_t(Y) * F.g.pitch + X]);
+			}
+	    }
+	}
+	if (q + 1 < nl)
+	{
+	    // prolongation corners of this (fine) level in the next coarser compact level (Ops.h:895-971)
+	    const Level &C = s->lv[first + q + 1];
+	    const HostLevel &HC = h[q + 1];
+	    H.pro.assign(size_t(8) * n, CYCLE_NONE);
+	    for (int k = 0; k < n; ++k)
+	    {
+		const int64_t i = H.cell[k];
+		const int fz = int(i / g.plane);
+		const int64_t rem = i - int64_t(fz) * g.plane;
+		const int fy = int(rem / g.pitch), fx = int(rem - int64_t(fy) * g.pitch);
+		const int mx = (fx >> 1) + L.shift[0], my = (fy >> 1) + L.shift[1], mz = (fz >> 1) + L.shift[2];
+		const int xs = (fx & 1) ? mx : mx - 1, ys = (fy & 1) ? my : my - 1, zs = (fz & 1) ? mz : mz - 1;
+		for (int c = 0; c < 8; ++c)
+		{
+		    const int X = xs + (c & 1), Y = ys + ((c >> 1) & 1), Z = zs + (c >> 2);
+		    if (X < 0 || Y < 0 || Z < 0 || X >= C.g.n[0] || Y >= C.g.n[1] || Z >= C.g.n[2]) continue;
+		    H.pro[size_t(c) * n + k] = compact(HC.pos[int64_t(Z) * C.g.plane + int64_t(Y) * C.g.pitch + X]);
+		}
+	    }
+	}
+    }
+    // direct-solve numbering -> compact index of the last level
+    std::vector<uint16_t> solveIdx(s->nCoarse);
+    std::vector<int32_t> coarseIdx(s->nCoarse);
+    GMG_CUDA(cudaMemcpy(coarseIdx.data(), s->coarseIdx, sizeof(int32_t) * s->nCoarse, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < s->nCoarse; ++k) solveIdx[k] = compact(h[nl - 1].pos[coarseIdx[k]]);
+    // table blob (goes to shared memory as a whole; 16-byte aligned pieces), followed by the top level's cell list
+    std::vector<char> blob;
+    auto put = [&](const void *p, size_t bytes) {
+	const size_t off = (blob.size() + 15) & ~size_t(15);
+	blob.resize(off + bytes);
+	if (bytes) std::memcpy(blob.data() + off, p, bytes);
+	return int(off);
+    };
+    CompactArgs *c = new CompactArgs;
+    std::memset(c, 0, sizeof(*c));
+    int off = 0;
+    for (int q = 0; q < nl; ++q)
+    {
+	HostLevel &H = h[q];
+	CompactLevel &L = c->lv[q];
+	L.n = int(H.cell.size());
+	L.off = off;
+	off += 3 * L.n;
+	L.nbr = put(H.nbr.data(), H.nbr.size() * 2);
+	L.rst = put(H.rst.data(), H.rst.size() * 2);
+	L.pro = put(H.pro.data(), H.pro.size() * 2);
+	L.diag = put(H.diag.data(), H.diag.size());
+	L.flags = put(H.flags.data(), H.flags.size());
+    }
+    c->solveIdx = put(solveIdx.data(), solveIdx.size() * 2);
+    blob.resize((blob.size() + 15) & ~size_t(15));
+    c->blobBytes = int(blob.size());
+    c->vectorDoubles = (off + 1) & ~1;
+    const size_t cellOff = blob.size();
+    blob.resize(cellOff + h[0].cell.size() * 4);
+    std::memcpy(blob.data() + cellOff, h[0].cell.data(), h[0].cell.size() * 4);
+    const size_t smem = size_t(c->vectorDoubles) * sizeof(double) + size_t(c->blobBytes);
+    if (smem > size_t(smemMax)) { delete c; return GMG_OK; }  // estimate was too tight: keep the per-kernel path
+    char *d = nullptr;
+    GMG_CUDA(devMalloc(&d, blob.size()));
+    GMG_CUDA(cudaMemcpyAsync(d, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    c->blob = reinterpret_cast<const unsigned char *>(d);
+    c->cellTop = reinterpret_cast<const int32_t *>(d + cellOff);
+    c->nLevels = nl;
+    c->sweeps = s->opt.boundary_iterations;
+    c->bTop = s->lv[first].b;
+    c->xTop = s->lv[first].x;
+    c->inv = s->coarseInv;
+    c->nSolve = s->nCoarse;
+    s->compactArgs = c;
+    s->compactBlob = d;
+    s->compactSmem = smem;
+    GMG_CUDA(cudaFuncSetAttribute(k_compact_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->compactSmem)));
     s->fusedFirst = first;
     return GMG_OK;
 }
@@ -1794,30 +2060,12 @@ static int buildFusedCycle(gmg_solver *s)
 static int launchCoarseCycle(gmg_solver *s)
 {
     s->ctx->curLevel = s->fusedFirst;
-    CycleArgs c;
-    c.lv = reinterpret_cast<const DevLevel *>(s->devLevels);
-    c.first = s->fusedFirst;
-    c.last = s->levels - 1;
-    c.bandSweeps = s->opt.boundary_iterations;
-    c.coarseIdx = s->coarseIdx;
-    c.coarseInv = s->coarseInv;
-    c.nCoarse = s->nCoarse;
+    const CompactArgs &c = *static_cast<const CompactArgs *>(s->compactArgs);
     double bytes = 0;
-    for (int l = c.first; l < c.last; ++l) bytes += double(s->lv[l].nActive) * 126.0;
+    for (int l = s->fusedFirst; l < s->levels - 1; ++l) bytes += double(s->lv[l].nActive) * 126.0;
     GMG_LAUNCH(s->ctx, KC_COARSE, bytes);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(unsigned(s->clusterSize));
-    cfg.blockDim = dim3(CYCLE_THREADS);
-    cfg.dynamicSmemBytes = sizeof(double) * size_t(s->nCoarse);
-    cfg.stream = s->ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = unsigned(s->clusterSize);
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    GMG_CUDA(cudaLaunchKernelEx(&cfg, k_coarse_cycle, c));
+    GMG_CUDA(launchK(k_compact_cycle, unsigned(1), unsigned(CYCLE_THREADS), size_t(s->compactSmem), s->ctx->stream, c));
+    GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }
 
@@ -1845,7 +2093,7 @@ static int launchVec(gmg_solver *s, int level, double *y, const double *a, const
     v.ticket = s->ctx->ticket;
     v.result = result;
     GMG_LAUNCH(s->ctx, klass, double(L.nActive) * bytesPerCell);
-    k_vec<OP><<<L.nChunksActive, BLOCK, 0, s->ctx->stream>>>(v);
+    GMG_CUDA(launchK((k_vec<OP>), unsigned(L.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, v));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }
@@ -1863,13 +2111,45 @@ static int readScalar(gmg_solver *s, size_t offset, double *out)
 // ====================================================================================================
 // V-cycle (MG.cpp:420-881)
 // ====================================================================================================
+// one half-pass of the tiled Gauss-Seidel smoother, in place (Ops.h:369-520)
+static int launchGaussSeidel(gmg_solver *s, int level, double *x, const double *b, bool oddTiles, bool forward)
+{
+    s->ctx->curLevel = level;
+    const Level &L = s->lv[level];
+    if (!L.bpos) return invalid("this solver was not created with use_gauss_seidel");
+    const int n = L.nGsTiles[oddTiles ? 1 : 0];
+    if (n == 0) return GMG_OK;
+    GsArgs a;
+    a.x = x; a.b = b; a.labels = L.labels; a.tiles = L.gsTiles[oddTiles ? 1 : 0]; a.bpos = L.bpos; a.bcoef = L.bcoef; a.nBoundary = L.nBoundary;
+    a.tilesX = L.gsTilesX; a.tilesY = L.gsTilesY;
+    for (int k = 0; k < 3; ++k) { a.off[k] = L.gsOff[k]; a.n[k] = L.g.n[k]; }
+    a.pitch = L.g.pitch; a.plane = L.g.plane; a.forward = forward ? 1 : 0;
+    const size_t smem = sizeof(double) * (GS_HALO * GS_HALO * GS_HALO + GS_TILE * GS_TILE * GS_TILE) + GS_TILE * GS_TILE * GS_TILE;
+    static bool attr = false;
+    if (!attr) { GMG_CUDA(cudaFuncSetAttribute(k_gauss_seidel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+    GMG_LAUNCH(s->ctx, KC_GS, double(L.nActive) * 25.0 * 0.5);
+    GMG_CUDA(launchK(k_gauss_seidel, unsigned(n), unsigned(BLOCK), size_t(smem), s->ctx->stream, a));
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
 // jacobiDepth: how far into the halo the interior sweep still produces valid values (sharded levels)
-static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, const double *b, bool zeroGrid, int jacobiDepth)
+// down: the smoothing before the coarse-grid correction (GS: odd then even tiles, forwards; MG.cpp:466-479), else after it
+// (GS: even then odd tiles, backwards; MG.cpp:740-751)
+static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, const double *b, bool zeroGrid, int jacobiDepth, bool down)
 {
     const int it = s->opt.boundary_iterations;
     GMG_TRY(launchBand(s, level, cur, b, it, zeroGrid));
-    GMG_TRY(launchStencil(s, level, SM_JACOBI, cur, b, alt, nullptr, clipDepth(s->lv[level], jacobiDepth)));
-    std::swap(cur, alt);
+    if (s->opt.use_gauss_seidel)
+    {
+	GMG_TRY(launchGaussSeidel(s, level, cur, b, down, down));
+	GMG_TRY(launchGaussSeidel(s, level, cur, b, !down, down));
+    }
+    else
+    {
+	GMG_TRY(launchStencil(s, level, SM_JACOBI, cur, b, alt, nullptr, clipDepth(s->lv[level], jacobiDepth)));
+	std::swap(cur, alt);
+    }
     GMG_TRY(launchBand(s, level, cur, b, it, false));
     return GMG_OK;
 }
@@ -1899,10 +2179,10 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
     // result back into the caller's buffer (one sweep only when there is a single level)
     double *cur0 = x, *alt0 = s->lv[0].xAlt;
     if (!useInitialGuess) GMG_TRY(launchZero(s, 0, cur0));
-    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, !useInitialGuess, downJacobi));
+    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, !useInitialGuess, downJacobi, true));
     if (nl == 1)
     {
-	GMG_TRY((launchVec<VO_COPY>(s, 0, x, cur0, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
+	if (cur0 != x) GMG_TRY((launchVec<VO_COPY>(s, 0, x, cur0, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
 	return GMG_OK;
     }
     GMG_TRY(launchStencil(s, 0, SM_RESIDUAL, cur0, b, s->lv[0].r, nullptr, clipDepth(s->lv[0], 1)));
@@ -1916,7 +2196,7 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
 	cur[level] = L.x;
 	alt[level] = L.xAlt;
 	GMG_TRY(launchZero(s, level, cur[level]));
-	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, true, downJacobi));
+	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, true, downJacobi, true));
 	GMG_TRY(launchStencil(s, level, SM_RESIDUAL, cur[level], L.b, L.r, nullptr, clipDepth(L, 1)));
 	GMG_TRY(restrictDown(s, level, L.r));
     }
@@ -1928,11 +2208,11 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
 	// the level below hands over its result in its own x grid (two Jacobi swaps, or the direct solve / fused cycle)
 	GMG_TRY(launchProlong(s, level, cur[level], s->lv[level + 1].x, clipDepth(L, 0)));
 	GMG_TRY(haloExchange(s, level, cur[level], HALO_X));
-	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, false, upJacobi));
+	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, false, upJacobi, false));
     }
     GMG_TRY(launchProlong(s, 0, cur0, s->lv[1].x, clipDepth(s->lv[0], 0)));
     GMG_TRY(haloExchange(s, 0, cur0, HALO_X));
-    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, false, upJacobi));
+    GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, false, upJacobi, false));
     // cur0 == x again after the second swap
     if (cur0 != x) GMG_TRY((launchVec<VO_COPY>(s, 0, x, cur0, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0)));
     return GMG_OK;
@@ -1943,8 +2223,11 @@ template <typename Body>
 static int runGraphed(gmg_solver *s, int kind, const void *p0, const void *p1, int flag, const Body &body)
 {
     gmg_ctx *ctx = s->ctx;
-    if (!s->useGraphs || ctx->profiling) return body(); // per-launch events cannot live inside a graph
-    auto key = std::make_tuple(kind, p0, p1, flag);
+    if (!s->useGraphs) return body();
+    // profiling: a second variant of the graph with an external event-record node before and after every launch, so the
+    // per-kernel times are those of the real replayed pipeline (warm L2, back-to-back launches), not of isolated launches
+    const bool prof = ctx->profiling;
+    auto key = std::make_tuple(kind + (prof ? 1000 : 0), p0, p1, flag);
     auto it = s->graphs.find(key);
     if (it == s->graphs.end())
     {
@@ -1955,9 +2238,13 @@ static int runGraphed(gmg_solver *s, int kind, const void *p0, const void *p1, i
 	}
 	gmg_solver::GraphEntry e;
 	const int64_t before = ctx->launches, commBefore = ctx->commOps;
+	if (prof) flushProfile(ctx);
 	GMG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+	ctx->capturing = true;
 	const int st = body();
+	ctx->capturing = false;
 	cudaError_t ce = cudaStreamEndCapture(ctx->stream, &e.graph);
+	if (prof) { e.recs.swap(ctx->recs); ctx->recs.clear(); }
 	if (st != GMG_OK) { if (e.graph) cudaGraphDestroy(e.graph); return st; }
 	GMG_CUDA(ce);
 	e.kernels = ctx->launches - before;
@@ -1970,6 +2257,11 @@ static int runGraphed(gmg_solver *s, int kind, const void *p0, const void *p1, i
     GMG_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
     ctx->launches += it->second.kernels;
     ctx->commOps += it->second.comms;
+    if (prof)
+    {
+	GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+	accumulateRecs(ctx, it->second.recs, false);
+    }
     return GMG_OK;
 }
 
@@ -1982,7 +2274,7 @@ static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useIniti
 // ====================================================================================================
 // PCG (CG.h:11-207)
 // ====================================================================================================
-__global__ void k_shift_rho(Scalars *sc) { sc->rho = sc->rhoNew; }
+__global__ void k_shift_rho(Scalars *sc) { pdlEnter(); sc->rho = sc->rhoNew; }
 
 // owned-plane reduction into a device scalar, summed over the ranks on a sharded level 0
 template <int OP>
@@ -2055,7 +2347,7 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 	{
 	    s->ctx->curLevel = 0;
 	    GMG_LAUNCH(ctx, KC_BLAS1, 0);
-	    k_shift_rho<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<Scalars *>(ctx->scalars));
+	    GMG_CUDA(launchK(k_shift_rho, unsigned(1), unsigned(1), size_t(0), ctx->stream, reinterpret_cast<Scalars *>(ctx->scalars)));
 	}
 	return applyUpdate();
     };
@@ -2156,6 +2448,12 @@ extern "C" int gmg_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b)
     GMG_TRY(launchStencil(s, x->level, SM_JACOBI, x->d, b->d, L.xAlt, nullptr, clipDepth(L, 0)));
     // copy back rather than swap pointers: cached V-cycle graphs hold the level's xAlt address
     return launchVec<VO_COPY>(s, x->level, x->d, L.xAlt, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, clipDepth(L, 0));
+}
+extern "C" int gmg_gauss_seidel(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int oddTiles, int forward)
+{
+    CHECK_GRIDS2(s, x, b);
+    GMG_CUDA(enterCtx(s->ctx));
+    return launchGaussSeidel(s, x->level, x->d, b->d, oddTiles != 0, forward != 0);
 }
 extern "C" int gmg_boundary_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int sweeps)
 {

@@ -46,6 +46,7 @@ enum KClass
     KC_ZERO,
     KC_SETUP,
     KC_HALO,
+    KC_GS,
     KC_COUNT
 };
 
@@ -90,6 +91,11 @@ struct Level
     // V-cycle grids (level 0 uses caller grids for x and b)
     double *x = nullptr, *xAlt = nullptr, *b = nullptr, *r = nullptr;
     int shift[3] = {0, 0, 0};    // coarse storage = (this level's storage >> 1) + shift   (to level+1)
+    // tiled Gauss-Seidel (only built when the solver uses it): 16^3 tiles of the EXPANDED grid laid over the storage box
+    int32_t *gsTiles[2] = {nullptr, nullptr};  // [0] even, [1] odd tiles holding an active cell (linear tile ids)
+    int nGsTiles[2] = {0, 0};
+    int gsTilesX = 0, gsTilesY = 0, gsOff[3] = {0, 0, 0};
+    int32_t *bpos = nullptr;     // grid: boundary-record index of BOUNDARY cells
 };
 
 struct ProfileRec
@@ -109,12 +115,15 @@ struct gmg_ctx
     bool ownStream = false;
     int64_t launches = 0;
     bool profiling = false;
+    bool capturing = false;       // inside a stream capture: profiling events become external event-record nodes
     std::vector<gmg::ProfileRec> recs;
     std::vector<cudaEvent_t> eventPool;
     // [0] = all levels, [1] = launches on level 0 only (the fine level, where the roofline is quoted)
     double classMs[2][gmg::KC_COUNT] = {{0}};
     int64_t classLaunches[2][gmg::KC_COUNT] = {{0}};
     double classBytes[2][gmg::KC_COUNT] = {{0}};
+    double levelMs[16][gmg::KC_COUNT] = {{0}};      // the same device times split by multigrid level
+    int64_t levelLaunches[16][gmg::KC_COUNT] = {{0}};
     int curLevel = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int smCount = 148;
@@ -147,10 +156,11 @@ struct gmg_solver
     // z-slab sharding: levels [0, shardLevels) are slabs, the rest replicated on every rank
     int shardLevels = 0;
     std::vector<int> gatherLo, gatherHi; // per rank: planes of the first replicated level it restricts into
-    // persistent coarse sub-V-cycle: levels [fusedFirst, levels-1] in one cluster kernel (-1 = off)
+    // compact coarse sub-V-cycle: levels [fusedFirst, levels-1] in one shared-memory CTA (-1 = off)
     int fusedFirst = -1;
-    int clusterSize = 8;
-    void *devLevels = nullptr;    // DevLevel[levels]
+    void *compactArgs = nullptr;  // host copy of the kernel's CompactArgs
+    void *compactBlob = nullptr;  // device tables behind it
+    size_t compactSmem = 0;
     // PCG work grids (level 0)
     double *pcgR = nullptr, *pcgP = nullptr, *pcgZ = nullptr, *pcgT = nullptr, *pcgX = nullptr, *pcgB = nullptr;
     double setupMs = 0;
@@ -161,6 +171,7 @@ struct gmg_solver
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t exec = nullptr;
 	int64_t kernels = 0, comms = 0;
+	std::vector<gmg::ProfileRec> recs; // profiled variant: per-launch event pairs living inside the graph
     };
     std::map<std::tuple<int, const void *, const void *, int>, GraphEntry> graphs;
     bool useGraphs = true;

@@ -21,6 +21,14 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 
+// Programmatic dependent launch (see launchK in gmg_b200.cu): let the next kernel of the chain be set up right away, then wait
+// until everything the previous kernel wrote is visible.  Both are no-ops for a launch without the PDL attribute.
+__device__ __forceinline__ void pdlEnter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ double warpSum(double v)
 {
 #pragma unroll
@@ -215,7 +223,7 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 
 template <int MODE, bool DOT>
 __global__ void __launch_bounds__(BLOCK) k_stencil(const StencilArgs a)
-{
+{ pdlEnter();
     const double acc = stencilBody<MODE, DOT>(a, blockIdx.x, threadIdx.x);
     if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
 }
@@ -282,12 +290,12 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 }
 template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO>
 __global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
-{
+{ pdlEnter();
     bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO>(a, blockIdx.x, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t *bandIdx, const double *v, int nBand)
-{
+{ pdlEnter();
     const int k = blockIdx.x * BLOCK + threadIdx.x;
     if (k < nBand) x[bandIdx[k]] = v[k];
 }
@@ -311,50 +319,45 @@ struct TransferArgs
     int zlo, zhi;  // clip on the destination's z-planes (coarse planes for restriction, fine planes for prolongation)
 };
 
+// One virtual CTA covers one z-plane and one 256-cell half of a chunk (8 virtual CTAs per chunk): a coarse cell is 64 fine
+// reads, so the work is spread over as many threads as there are coarse cells.
+constexpr int RESTRICT_SPLIT = CHUNK_Z * 2;
 __device__ __forceinline__ void restrictBody(const TransferArgs &a, int vb, int tid)
 {
     const double rw[4] = {1. / 8., 3. / 8., 3. / 8., 1. / 8.};
-    const int c = a.chunks[vb];
+    const int c = a.chunks[vb / RESTRICT_SPLIT];
+    const int sub = vb % RESTRICT_SPLIT;
     const int zb = c / a.chunksPerPlane;
     const int64_t base = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS;
-#pragma unroll 1
-    for (int dz = 0; dz < CHUNK_Z; ++dz)
-    {
-	const int cz = zb * CHUNK_Z + dz;
-	if (cz >= a.zhi) break;
-	if (cz < a.zlo) continue;
-#pragma unroll 1
-	for (int h = 0; h < 2; ++h)
+    const int cz = zb * CHUNK_Z + (sub >> 1);
+    if (cz >= a.zhi || cz < a.zlo) return;
+    const int64_t inPlane = base + (sub & 1) * BLOCK + tid;
+    if (inPlane >= a.coarsePlane) return;
+    const int64_t ci = int64_t(cz) * a.coarsePlane + inPlane;
+    const int l = a.coarseLabels[ci];
+    if (!(l == L_INTERIOR || l == L_BOUNDARY)) return;
+    const int cy = int(inPlane / a.coarsePitch), cx = int(inPlane - int64_t(cy) * a.coarsePitch);
+    const int fx = 2 * (cx - a.shift[0]) - 1, fy = 2 * (cy - a.shift[1]) - 1, fz = 2 * (cz - a.shift[2]) - 1;
+    const double *f = a.fine + (int64_t(fz) * a.finePlane + int64_t(fy) * a.finePitch + fx);
+    double v = 0.0;
+#pragma unroll
+    for (int z = 0; z < 4; ++z)
+#pragma unroll
+	for (int y = 0; y < 4; ++y)
 	{
-	    const int64_t inPlane = base + h * BLOCK + tid;
-	    if (inPlane >= a.coarsePlane) continue;
-	    const int64_t ci = int64_t(cz) * a.coarsePlane + inPlane;
-	    const int l = a.coarseLabels[ci];
-	    if (!(l == L_INTERIOR || l == L_BOUNDARY)) continue;
-	    const int cy = int(inPlane / a.coarsePitch), cx = int(inPlane - int64_t(cy) * a.coarsePitch);
-	    const int fx = 2 * (cx - a.shift[0]) - 1, fy = 2 * (cy - a.shift[1]) - 1, fz = 2 * (cz - a.shift[2]) - 1;
-	    const double *f = a.fine + (int64_t(fz) * a.finePlane + int64_t(fy) * a.finePitch + fx);
-	    double v = 0.0;
-#pragma unroll
-	    for (int z = 0; z < 4; ++z)
-#pragma unroll
-		for (int y = 0; y < 4; ++y)
-		{
-		    const double *row = f + int64_t(z) * a.finePlane + int64_t(y) * a.finePitch;
-		    // fx is odd: row[1..2] is an aligned pair
-		    const double s0 = row[0];
-		    const double2 s12 = ld2(row + 1);
-		    const double s3 = row[3];
-		    v += rw[0] * rw[y] * rw[z] * s0;
-		    v += rw[1] * rw[y] * rw[z] * s12.x;
-		    v += rw[2] * rw[y] * rw[z] * s12.y;
-		    v += rw[3] * rw[y] * rw[z] * s3;
-		}
-	    a.out[ci] = v;
+	    const double *row = f + int64_t(z) * a.finePlane + int64_t(y) * a.finePitch;
+	    // fx is odd: row[1..2] is an aligned pair
+	    const double s0 = row[0];
+	    const double2 s12 = ld2(row + 1);
+	    const double s3 = row[3];
+	    v += rw[0] * rw[y] * rw[z] * s0;
+	    v += rw[1] * rw[y] * rw[z] * s12.x;
+	    v += rw[2] * rw[y] * rw[z] * s12.y;
+	    v += rw[3] * rw[y] * rw[z] * s3;
 	}
-    }
+    a.out[ci] = v;
 }
-__global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a) { restrictBody(a, blockIdx.x, threadIdx.x); }
+__global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a) { pdlEnter(); restrictBody(a, blockIdx.x, threadIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
 // Prolongation (Ops.h:873-972): fine (active) += 4 * trilerp(8 coarse cells), fractions .25/.75.
@@ -409,14 +412,14 @@ __device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int t
 	else a.out[i + 1] = n1;
     }
 }
-__global__ void __launch_bounds__(BLOCK) k_prolong(const TransferArgs a) { prolongBody(a, blockIdx.x, threadIdx.x); }
+__global__ void __launch_bounds__(BLOCK) k_prolong(const TransferArgs a) { pdlEnter(); prolongBody(a, blockIdx.x, threadIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
 // Coarsest level (MG.cpp:669-692): gather b, x = A^-1 b (dense inverse of the SPD matrix, built on the
 // host at setup from an exact Cholesky factor), scatter.  One warp per row, b staged in shared memory.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK) k_coarse_solve(double *x, const double *b, const int32_t *idx, const double *inv, int n)
-{
+{ pdlEnter();
     extern __shared__ double sb[];
     for (int i = threadIdx.x; i < n; i += BLOCK) sb[i] = b[idx[i]];
     __syncthreads();
@@ -467,7 +470,7 @@ enum VecOp
 
 template <int OP>
 __global__ void __launch_bounds__(BLOCK) k_vec(const VecArgs v)
-{
+{ pdlEnter();
     const int c = v.chunks[blockIdx.x];
     const int zb = c / v.chunksPerPlane;
     const int64_t inPlane = int64_t(c - zb * v.chunksPerPlane) * CHUNK_CELLS + 2 * threadIdx.x;
@@ -557,170 +560,332 @@ __device__ __forceinline__ void zeroBody(double *y, const int32_t *chunks, int c
     }
 }
 __global__ void __launch_bounds__(BLOCK) k_zero(double *y, const int32_t *chunks, int chunksPerPlane, int64_t plane, int nz)
-{
+{ pdlEnter();
     zeroBody(y, chunks, chunksPerPlane, plane, nz, blockIdx.x, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent coarse sub-V-cycle.  Below a few hundred thousand cells a level is pure launch latency
-// (19 dependent launches of ~3 us each), so levels [first, last] -- down-stroke, direct solve, up-stroke --
-// run inside ONE kernel: a single thread-block cluster whose CTAs walk the same virtual-CTA bodies as
-// the stand-alone kernels and meet at the hardware cluster barrier (release/acquire at cluster scope,
-// which orders the global-memory traffic between the steps) instead of at kernel boundaries.
-// Same arithmetic, same order as the per-kernel path: results are bitwise identical.
+// Tiled Gauss-Seidel (Ops.h:369-520), the reference's production smoother (GFS.cpp:463-466).  The reference sweeps the
+// 16^3 tiles of one parity of (tx+ty+tz) in parallel and the cells of a tile one after the other in lexicographic order
+// (x fastest), forwards or backwards, undamped: u += (b - A u) / diag.  Face-adjacent tiles have opposite parity, so a
+// tile only sees frozen values outside itself; inside, cell (x,y,z) depends on the NEW values of (x-1,y,z), (x,y-1,z),
+// (x,y,z-1) and the OLD values of the +1 neighbours (mirrored for the backward sweep).  All cells of one wavefront
+// x+y+z = s are therefore independent, and sweeping s = 0..45 (or 45..0) reproduces the sequential result exactly.
+// One CTA per tile: the tile and its one-cell halo live in shared memory for the 46 steps.
+// ------------------------------------------------------------------------------------------------
+constexpr int GS_TILE = 16;
+constexpr int GS_HALO = GS_TILE + 2;
+
+struct GsArgs
+{
+    double *x;
+    const double *b;
+    const uint8_t *labels;
+    const int32_t *tiles;    // linear tile ids (x fastest) of the active tiles of the wanted parity
+    const int32_t *bpos;     // grid: boundary-record index of a BOUNDARY cell (undefined elsewhere)
+    const double *bcoef;
+    int nBoundary;
+    int tilesX, tilesY;      // tile grid over the storage box
+    int off[3];              // storage coordinate of tile (0,0,0)'s first cell (<= 0)
+    int n[3];
+    int pitch;
+    int64_t plane;
+    int forward;
+};
+
+__global__ void __launch_bounds__(BLOCK) k_gauss_seidel(const GsArgs a)
+{ pdlEnter();
+    extern __shared__ double gsm[];
+    double *xs = gsm;                                   // [18][18][18]
+    double *bs = gsm + GS_HALO * GS_HALO * GS_HALO;     // [16][16][16]
+    uint8_t *ls = reinterpret_cast<uint8_t *>(bs + GS_TILE * GS_TILE * GS_TILE);  // [16][16][16]
+    const int t = a.tiles[blockIdx.x];
+    const int tz = t / (a.tilesX * a.tilesY), ty = (t - tz * a.tilesX * a.tilesY) / a.tilesX, tx = t - (tz * a.tilesY + ty) * a.tilesX;
+    const int ox = a.off[0] + tx * GS_TILE, oy = a.off[1] + ty * GS_TILE, oz = a.off[2] + tz * GS_TILE;
+    for (int i = threadIdx.x; i < GS_HALO * GS_HALO * GS_HALO; i += BLOCK)
+    {
+	const int lz = i / (GS_HALO * GS_HALO), ly = (i - lz * GS_HALO * GS_HALO) / GS_HALO, lx = i - (lz * GS_HALO + ly) * GS_HALO;
+	const int gx = ox + lx - 1, gy = oy + ly - 1, gz = oz + lz - 1;
+	double v = 0.0;
+	if (gx >= 0 && gy >= 0 && gz >= 0 && gx < a.n[0] && gy < a.n[1] && gz < a.n[2]) v = a.x[int64_t(gz) * a.plane + int64_t(gy) * a.pitch + gx];
+	xs[i] = v;
+    }
+    for (int i = threadIdx.x; i < GS_TILE * GS_TILE * GS_TILE; i += BLOCK)
+    {
+	const int lz = i >> 8, ly = (i >> 4) & 15, lx = i & 15;
+	const int gx = ox + lx, gy = oy + ly, gz = oz + lz;
+	double v = 0.0;
+	uint8_t l = L_EXTERIOR;
+	if (gx >= 0 && gy >= 0 && gz >= 0 && gx < a.n[0] && gy < a.n[1] && gz < a.n[2])
+	{
+	    const int64_t g = int64_t(gz) * a.plane + int64_t(gy) * a.pitch + gx;
+	    l = a.labels[g];
+	    if (l == L_INTERIOR || l == L_BOUNDARY) v = a.b[g];
+	}
+	bs[i] = v;
+	ls[i] = l;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    for (int step = 0; step <= 3 * (GS_TILE - 1); ++step)
+    {
+	const int sfront = a.forward ? step : 3 * (GS_TILE - 1) - step;
+	const int lz = sfront - lx - ly;
+	if (lz >= 0 && lz < GS_TILE)
+	{
+	    const int li = (lz << 8) | (ly << 4) | lx;
+	    const int l = ls[li];
+	    if (l == L_INTERIOR || l == L_BOUNDARY)
+	    {
+		const int c = ((lz + 1) * GS_HALO + (ly + 1)) * GS_HALO + (lx + 1);
+		const double u[6] = {xs[c - 1], xs[c + 1], xs[c - GS_HALO], xs[c + GS_HALO], xs[c - GS_HALO * GS_HALO], xs[c + GS_HALO * GS_HALO]};
+		const double centre = xs[c];
+		double lap = 0.0, diag = 6.0;
+		if (l == L_INTERIOR)
+		{
+#pragma unroll
+		    for (int n = 0; n < 6; ++n) lap -= u[n];
+		}
+		else
+		{
+		    const int64_t g = int64_t(oz + lz) * a.plane + int64_t(oy + ly) * a.pitch + (ox + lx);
+		    const int k = a.bpos[g];
+#pragma unroll
+		    for (int n = 0; n < 6; ++n)
+		    {
+			const double cn = a.bcoef[int64_t(n) * a.nBoundary + k];
+			if (cn != 0.0) lap -= cn * u[n];
+		    }
+		    diag = a.bcoef[int64_t(6) * a.nBoundary + k];
+		}
+		lap += diag * centre;
+		double r = bs[li] - lap;   // Ops.h:490-493
+		r /= diag;
+		xs[c] = centre + r;
+	    }
+	}
+	__syncthreads();
+    }
+    for (int i = threadIdx.x; i < GS_TILE * GS_TILE * GS_TILE; i += BLOCK)
+    {
+	const int l = ls[i];
+	if (!(l == L_INTERIOR || l == L_BOUNDARY)) continue;
+	const int lz = i >> 8, ly2 = (i >> 4) & 15, lx2 = i & 15;
+	a.x[int64_t(oz + lz) * a.plane + int64_t(oy + ly2) * a.pitch + (ox + lx2)] = xs[((lz + 1) * GS_HALO + (ly2 + 1)) * GS_HALO + (lx2 + 1)];
+    }
+}
+
+// tile flags for the two parities: bit set when the tile holds an active cell
+__global__ void __launch_bounds__(BLOCK) k_gs_tile_flags(uint8_t *flagOdd, uint8_t *flagEven, const uint8_t *labels, int tilesX, int tilesY, int off0,
+							int off1, int off2, int n0, int n1, int n2, int pitch, int64_t plane, int parity0)
+{
+    const int t = blockIdx.x;
+    const int tz = t / (tilesX * tilesY), ty = (t - tz * tilesX * tilesY) / tilesX, tx = t - (tz * tilesY + ty) * tilesX;
+    const int ox = off0 + tx * GS_TILE, oy = off1 + ty * GS_TILE, oz = off2 + tz * GS_TILE;
+    int any = 0;
+    for (int i = threadIdx.x; i < GS_TILE * GS_TILE * GS_TILE; i += BLOCK)
+    {
+	const int gx = ox + (i & 15), gy = oy + ((i >> 4) & 15), gz = oz + (i >> 8);
+	if (gx >= 0 && gy >= 0 && gz >= 0 && gx < n0 && gy < n1 && gz < n2)
+	{
+	    const int l = labels[int64_t(gz) * plane + int64_t(gy) * pitch + gx];
+	    any |= (l == L_INTERIOR || l == L_BOUNDARY);
+	}
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0)
+    {
+	const int odd = (parity0 + tx + ty + tz) & 1;
+	flagOdd[t] = uint8_t(any && odd);
+	flagEven[t] = uint8_t(any && !odd);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compact coarse sub-V-cycle.  Below a few thousand cells a level is pure latency: 19 dependent launches of ~3 us, each
+// a chain of L2 round trips.  Levels [first, last] -- down-stroke, direct solve, up-stroke -- therefore run in ONE CTA
+// whose vectors (x, rhs, scratch of every level) AND index tables live in SHARED MEMORY: compact lists of the active
+// cells with precomputed 16-bit neighbour / restriction / prolongation indices, copied in once per launch.  A step
+// costs a __syncthreads instead of a kernel boundary and touches no global memory.  Per cell the arithmetic and its order are those of k_stencil / k_band /
+// k_restrict / k_prolong / k_coarse_solve, so the result is bitwise identical to the per-kernel path.
 // ------------------------------------------------------------------------------------------------
 constexpr int CYCLE_THREADS = 1024;
+constexpr int CYCLE_MAX_LEVELS = 8;
+constexpr unsigned short CYCLE_NONE = 0xffffu;
 
-struct DevLevel
+// Byte offsets into the table blob (copied into shared memory at kernel start; 16-bit compact indices, CYCLE_NONE = not active)
+struct CompactLevel
 {
-    const uint8_t *labels;
-    double *x, *xAlt, *b, *r;
-    const int32_t *chunksInterior, *chunksActive;
-    int nChunksInterior, nChunksActive;
-    int chunksPerPlane, pitch, ny, nz;
-    int64_t plane;
-    int nBoundary, nBand;
-    const int32_t *bandIdx, *bandNbr;
-    const double *bcoef;
-    double *bandV0, *bandV1, *bandB;
-    int shift[3];
+    int n;         // active cells of the level (< 65535)
+    int off;       // offset (in doubles) of the level's x | t | b arrays in shared memory
+    int nbr;       // u16 [6][n]  compact index of the -x,+x,-y,+y,-z,+z neighbour
+    int rst;       // u16 [64][n] compact indices (in the next FINER level) of the 4x4x4 restriction taps
+    int pro;       // u16 [8][n]  compact indices (in the next COARSER level) of the 2x2x2 prolongation corners
+    int diag;      // u8  [n]     6 for INTERIOR; number of non-EXTERIOR neighbours for BOUNDARY (Ops.h:237-248, weight 1)
+    int flags;     // u8  [n]     bit0 = cell belongs to the boundary band, bits 1..3 = parity of its x, y, z storage index
 };
 
-struct CycleArgs
+struct CompactArgs
 {
-    const DevLevel *lv;  // device array indexed by level
-    int first, last;     // `last` is the direct-solve level
-    int bandSweeps;
-    const int32_t *coarseIdx;
-    const double *coarseInv;
-    int nCoarse;
+    CompactLevel lv[CYCLE_MAX_LEVELS];  // lv[0] is the finest compact level
+    int nLevels;
+    int sweeps;
+    int vectorDoubles;        // doubles of the vector region; the table blob follows it in shared memory
+    int blobBytes;            // multiple of 16
+    int solveIdx;             // u16 [nSolve] compact index of the direct solve's k-th unknown (MG.cpp:296-323 numbering)
+    int nSolve;
+    const unsigned char *blob;
+    const int32_t *cellTop;   // [lv[0].n] storage index of lv[0]'s cells in its grid
+    const double *bTop;       // rhs grid of lv[0] (written by the restriction kernel of the level above)
+    double *xTop;             // solution grid of lv[0] (read by the prolongation kernel of the level above)
+    const double *inv;        // [nSolve][nSolve]
 };
 
-template <typename F>
-__device__ __forceinline__ void forVirtualCtas(int nvb, const F &f)
+// A x at compact cell k, in the operation order of computeLaplacian (Ops.h:177-260): neighbours by (axis, direction), centre last
+__device__ __forceinline__ double compactLap(const unsigned short *nbr, int n, const double *x, int k, double diag)
 {
-    constexpr int PER = CYCLE_THREADS / BLOCK;
-    const int sub = threadIdx.x / BLOCK, tid = threadIdx.x % BLOCK;
-    for (int vb = blockIdx.x * PER + sub; vb < nvb; vb += gridDim.x * PER) f(vb, tid);
-}
-
-__device__ __forceinline__ void cycleSync() { cg::this_cluster().sync(); }
-
-__device__ __forceinline__ StencilArgs devStencilArgs(const DevLevel &L, const double *in, const double *b, double *out)
-{
-    StencilArgs a;
-    a.labels = L.labels; a.in = in; a.b = b; a.out = out;
-    a.chunks = L.chunksInterior; a.nChunks = L.nChunksInterior; a.chunksPerPlane = L.chunksPerPlane;
-    a.pitch = L.pitch; a.plane = L.plane; a.nz = L.nz; a.zlo = 0; a.zhi = L.nz;
-    a.nBoundary = L.nBoundary; a.bandIdx = L.bandIdx; a.bcoef = L.bcoef;
-    a.partials = nullptr; a.ticket = nullptr; a.result = nullptr;
-    return a;
-}
-
-// `sweeps` band sweeps on grid x, ending on a cluster barrier (mirrors launchBand on the host)
-__device__ __forceinline__ void cycleBand(const DevLevel &L, double *x, const double *b, int sweeps, bool zeroGrid)
-{
-    if (L.nBand == 0 || sweeps <= 0) return;
-    BandArgs a;
-    a.x = x; a.b = b; a.bandIdx = L.bandIdx; a.bandNbr = L.bandNbr; a.bcoef = L.bcoef; a.bandB = L.bandB;
-    a.nBoundary = L.nBoundary; a.nBand = L.nBand; a.pitch = L.pitch; a.plane = L.plane;
-    const int nvb = (L.nBand + BLOCK - 1) / BLOCK;
-    double *cur = L.bandV0, *nxt = L.bandV1;
-    a.vin = nullptr;
-    a.vout = cur;
-    if (zeroGrid) forVirtualCtas(nvb, [&](int vb, int tid) { bandBody<false, false, true, true>(a, vb, tid); });
-    else forVirtualCtas(nvb, [&](int vb, int tid) { bandBody<false, false, true, false>(a, vb, tid); });
-    cycleSync();
-    if (sweeps == 1)
+    double lap = 0.0;
+#pragma unroll
+    for (int d = 0; d < 6; ++d)
     {
-	forVirtualCtas(nvb, [&](int vb, int tid) { const int k = vb * BLOCK + tid; if (k < L.nBand) x[L.bandIdx[k]] = cur[k]; });
-	cycleSync();
-	return;
+	const unsigned short j = nbr[d * n + k];
+	if (j != CYCLE_NONE) lap -= x[j];
     }
-    for (int sw = 2; sw <= sweeps; ++sw)
+    lap += diag * x[k];
+    return lap;
+}
+
+// one damped-Jacobi sweep over the band cells (bandOnly) or all cells: t = new values, then x = t (Ops.h:262-367, :524-619)
+__device__ __forceinline__ void compactSweep(const CompactLevel &L, const unsigned char *tab, double *x, double *t, const double *b, bool bandOnly)
+{
+    const unsigned short *nbr = reinterpret_cast<const unsigned short *>(tab + L.nbr);
+    const unsigned char *dg = tab + L.diag, *fl = tab + L.flags;
+    for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS)
     {
-	a.vin = cur;
-	a.vout = nxt;
-	if (sw == sweeps) forVirtualCtas(nvb, [&](int vb, int tid) { bandBody<true, true, false, false>(a, vb, tid); });
-	else forVirtualCtas(nvb, [&](int vb, int tid) { bandBody<true, false, false, false>(a, vb, tid); });
-	cycleSync();
-	double *t = cur; cur = nxt; nxt = t;
+	if (bandOnly && !(fl[k] & 1)) continue;
+	const double diag = double(dg[k]);
+	const double lap = compactLap(nbr, L.n, x, k, diag);
+	double r = b[k] - lap;
+	r /= diag;
+	t[k] = x[k] + (2.0 / 3.0) * r;
     }
-}
-
-// band sweeps, interior Jacobi cur -> alt, band sweeps on alt (MG.cpp:557-667 / :695-784); the result is in alt
-__device__ __forceinline__ void cycleSmooth(const DevLevel &L, double *cur, double *alt, int sweeps, bool zeroGrid)
-{
-    cycleBand(L, cur, L.b, sweeps, zeroGrid);
-    const StencilArgs a = devStencilArgs(L, cur, L.b, alt);
-    forVirtualCtas(L.nChunksInterior + (L.nBoundary + BLOCK - 1) / BLOCK, [&](int vb, int tid) { stencilBody<SM_JACOBI, false>(a, vb, tid); });
-    cycleSync();
-    cycleBand(L, alt, L.b, sweeps, false);
-}
-
-__device__ __forceinline__ TransferArgs devTransferArgs(const DevLevel &F, const DevLevel &C)
-{
-    TransferArgs a;
-    a.fineLabels = F.labels; a.coarseLabels = C.labels;
-    a.finePitch = F.pitch; a.coarsePitch = C.pitch; a.finePlane = F.plane; a.coarsePlane = C.plane;
-    a.fineNz = F.nz; a.coarseNz = C.nz; a.coarseNy = C.ny;
-    a.shift[0] = F.shift[0]; a.shift[1] = F.shift[1]; a.shift[2] = F.shift[2];
-    a.fine = nullptr; a.coarse = nullptr; a.out = nullptr; a.chunks = nullptr; a.chunksPerPlane = 0; a.zlo = 0; a.zhi = 0;
-    return a;
-}
-
-__global__ void __launch_bounds__(CYCLE_THREADS, 1) k_coarse_cycle(const CycleArgs c)
-{
-    extern __shared__ double sb[];
-    // ---- down-stroke
-    for (int l = c.first; l < c.last; ++l)
+    __syncthreads();
+    for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS)
     {
-	const DevLevel &L = c.lv[l];
-	const DevLevel &C = c.lv[l + 1];
-	forVirtualCtas(L.nChunksActive, [&](int vb, int tid) { zeroBody(L.x, L.chunksActive, L.chunksPerPlane, L.plane, L.nz, vb, tid); });
-	cycleSync();
-	cycleSmooth(L, L.x, L.xAlt, c.bandSweeps, true);
+	if (bandOnly && !(fl[k] & 1)) continue;
+	x[k] = t[k];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void compactSmooth(const CompactLevel &L, const unsigned char *tab, double *x, double *t, const double *b, int sweeps)
+{
+    for (int s = 0; s < sweeps; ++s) compactSweep(L, tab, x, t, b, true);
+    compactSweep(L, tab, x, t, b, false);
+    for (int s = 0; s < sweeps; ++s) compactSweep(L, tab, x, t, b, true);
+}
+
+__global__ void __launch_bounds__(CYCLE_THREADS, 1) k_compact_cycle(const CompactArgs c)
+{ pdlEnter();
+    extern __shared__ double sm[];
+    unsigned char *tab = reinterpret_cast<unsigned char *>(sm + c.vectorDoubles);
+    const int nl = c.nLevels;
+    {
+	const int4 *src = reinterpret_cast<const int4 *>(c.blob);
+	int4 *dst = reinterpret_cast<int4 *>(tab);
+	for (int i = threadIdx.x; i < c.blobBytes / 16; i += CYCLE_THREADS) dst[i] = __ldg(src + i);
+	const CompactLevel &L = c.lv[0];
+	double *b = sm + L.off + 2 * L.n;
+	for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) b[k] = c.bTop[__ldg(c.cellTop + k)];
+    }
+    // ---- down-stroke (MG.cpp:557-667): x = 0, smooth, residual, restrict
+    for (int l = 0; l + 1 < nl; ++l)
+    {
+	const CompactLevel &L = c.lv[l];
+	const CompactLevel &C = c.lv[l + 1];
+	double *x = sm + L.off, *t = x + L.n, *b = t + L.n;
+	for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) x[k] = 0.0;
+	__syncthreads();
+	compactSmooth(L, tab, x, t, b, c.sweeps);
 	{
-	    const StencilArgs a = devStencilArgs(L, L.xAlt, L.b, L.r);
-	    forVirtualCtas(L.nChunksInterior + (L.nBoundary + BLOCK - 1) / BLOCK, [&](int vb, int tid) { stencilBody<SM_RESIDUAL, false>(a, vb, tid); });
+	    const unsigned short *nbr = reinterpret_cast<const unsigned short *>(tab + L.nbr);
+	    for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS)
+	    {
+		const double lap = compactLap(nbr, L.n, x, k, double(tab[L.diag + k]));
+		t[k] = b[k] + (-1.0) * lap;  // Ops.h:731
+	    }
 	}
-	cycleSync();
+	__syncthreads();
+	double *bc = sm + C.off + 2 * C.n;
+	const unsigned short *rst = reinterpret_cast<const unsigned short *>(tab + C.rst);
+	for (int k = threadIdx.x; k < C.n; k += CYCLE_THREADS)
 	{
-	    TransferArgs a = devTransferArgs(L, C);
-	    a.fine = L.r; a.out = C.b; a.chunks = C.chunksActive; a.chunksPerPlane = C.chunksPerPlane; a.zlo = 0; a.zhi = C.nz;
-	    forVirtualCtas(C.nChunksActive, [&](int vb, int tid) { restrictBody(a, vb, tid); });
+	    const double rw[4] = {1. / 8., 3. / 8., 3. / 8., 1. / 8.};
+	    double v = 0.0;
+#pragma unroll
+	    for (int z = 0; z < 4; ++z)
+#pragma unroll
+		for (int y = 0; y < 4; ++y)
+#pragma unroll
+		    for (int xx = 0; xx < 4; ++xx)
+		    {
+			const unsigned short j = rst[((z * 4 + y) * 4 + xx) * C.n + k];
+			if (j != CYCLE_NONE) v += rw[xx] * rw[y] * rw[z] * t[j];  // an inactive tap adds +0.0, which never changes v
+		    }
+	    bc[k] = v;
 	}
-	cycleSync();
+	__syncthreads();
     }
-    // ---- direct solve on the coarsest level: x = A^-1 b
+    // ---- direct solve on the coarsest level (MG.cpp:669-692): x = A^-1 b, one warp per row as in k_coarse_solve
     {
-	const DevLevel &L = c.lv[c.last];
-	const int n = c.nCoarse;
-	for (int i = threadIdx.x; i < n; i += CYCLE_THREADS) sb[i] = L.b[c.coarseIdx[i]];
+	const CompactLevel &L = c.lv[nl - 1];
+	double *x = sm + L.off, *t = x + L.n, *b = t + L.n;
+	const unsigned short *sidx = reinterpret_cast<const unsigned short *>(tab + c.solveIdx);
+	const int n = c.nSolve;
+	for (int i = threadIdx.x; i < n; i += CYCLE_THREADS) t[i] = b[sidx[i]];
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
-	for (int row = blockIdx.x * (CYCLE_THREADS / 32) + (threadIdx.x >> 5); row < n; row += gridDim.x * (CYCLE_THREADS / 32))
+	for (int row = threadIdx.x >> 5; row < n; row += CYCLE_THREADS / 32)
 	{
-	    const double *r = c.coarseInv + int64_t(row) * n;
+	    const double *r = c.inv + int64_t(row) * n;
 	    double acc = 0.0;
-	    for (int j = lane; j < n; j += 32) acc += r[j] * sb[j];
+	    for (int j = lane; j < n; j += 32) acc += r[j] * t[j];
 	    acc = warpSum(acc);
-	    if (lane == 0) L.x[c.coarseIdx[row]] = acc;
+	    if (lane == 0) x[sidx[row]] = acc;
 	}
-	cycleSync();
+	__syncthreads();
     }
-    // ---- up-stroke: x_l (in xAlt after the down-stroke) += P x_{l+1}; smooth back into x
-    for (int l = c.last - 1; l >= c.first; --l)
+    // ---- up-stroke (MG.cpp:695-784): x += 4 trilerp(x_coarse), smooth
+    for (int l = nl - 2; l >= 0; --l)
     {
-	const DevLevel &L = c.lv[l];
-	const DevLevel &C = c.lv[l + 1];
+	const CompactLevel &L = c.lv[l];
+	const CompactLevel &C = c.lv[l + 1];
+	double *x = sm + L.off, *t = x + L.n, *b = t + L.n;
+	const double *xc = sm + C.off;
+	const unsigned short *pro = reinterpret_cast<const unsigned short *>(tab + L.pro);
+	for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS)
 	{
-	    TransferArgs a = devTransferArgs(L, C);
-	    a.coarse = C.x; a.out = L.xAlt; a.chunks = L.chunksActive; a.chunksPerPlane = L.chunksPerPlane; a.zlo = 0; a.zhi = L.nz;
-	    forVirtualCtas(L.nChunksActive, [&](int vb, int tid) { prolongBody(a, vb, tid); });
+	    const int f = tab[L.flags + k];
+	    const double wx = (f & 2) ? .25 : .75, wy = (f & 4) ? .25 : .75, wz = (f & 8) ? .25 : .75;
+	    double v[8];
+#pragma unroll
+	    for (int q = 0; q < 8; ++q)
+	    {
+		const unsigned short j = pro[q * L.n + k];
+		v[q] = j != CYCLE_NONE ? xc[j] : 0.0;
+	    }
+	    // corner q = x + 2 y + 4 z; lerp nesting x -> y -> z (Ops.h:841-871)
+	    const double e = lerpRef(lerpRef(lerpRef(v[0], v[1], wx), lerpRef(v[2], v[3], wx), wy),
+				     lerpRef(lerpRef(v[4], v[5], wx), lerpRef(v[6], v[7], wx), wy), wz);
+	    x[k] = x[k] + 4. * e;
 	}
-	cycleSync();
-	cycleSmooth(L, L.xAlt, L.x, c.bandSweeps, false);
+	__syncthreads();
+	compactSmooth(L, tab, x, t, b, c.sweeps);
+    }
+    {
+	const CompactLevel &L = c.lv[0];
+	const double *x = sm + L.off;
+	for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) c.xTop[__ldg(c.cellTop + k)] = x[k];
     }
 }
 

@@ -101,7 +101,8 @@ int gmg_boundary_cells(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3]
 /* ---- solver ------------------------------------------------------------------------------------ */
 typedef struct gmg_solver_options
 {
-    int use_gauss_seidel;     /* 0: damped-Jacobi interior smoother (north_star); 1: tiled Gauss-Seidel (not built yet -> GMG_ERR_INVALID) */
+    int use_gauss_seidel;     /* 0: damped-Jacobi interior smoother (north_star); 1: tiled Gauss-Seidel, the reference's production
+				 default (GFS.cpp:463-466) -- single-GPU contexts only */
     int print_stats;          /* like doPrintStats: per-stage CUDA-event timings to stdout */
     int boundary_width;       /* myBoundarySmootherWidth, default 3 (MG.cpp:141) */
     int boundary_iterations;  /* myBoundarySmootherIterations, default 3 (MG.cpp:142) */
@@ -151,6 +152,9 @@ int gmg_grid_copy(gmg_grid *dst, const gmg_grid *src);
 
 /* jacobiPoissonSmoother, Ops.h:262-367 (x in place; level 0 uses the fine weights) */
 int gmg_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b);
+/* tiledGaussSeidelPoissonSmoother, Ops.h:369-520: one half-pass over the odd or even 16^3 tiles, forwards or backwards
+ * (x in place).  Needs a solver created with use_gauss_seidel = 1. */
+int gmg_gauss_seidel(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int oddTiles, int forward);
 /* boundaryJacobiPoissonSmoother over the solver's own band, Ops.h:524-619, `sweeps` times */
 int gmg_boundary_jacobi(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int sweeps);
 /* applyPoissonMatrix, Ops.h:621-714 (dst written on active cells only) */
@@ -192,6 +196,8 @@ int gmg_kernel_class_count(void);
 const char *gmg_kernel_class_name(int i);
 int gmg_profile_get(gmg_ctx *ctx, int klass, int fineLevelOnly, double *ms, int64_t *launches, double *algorithmicBytes);
 int gmg_profile_reset(gmg_ctx *ctx);
+/* the same device times split by multigrid level (level < 16) */
+int gmg_profile_get_level(gmg_ctx *ctx, int klass, int level, double *ms, int64_t *launches);
 
 #ifdef __cplusplus
 }

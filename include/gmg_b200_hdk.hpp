@@ -374,11 +374,17 @@ void jacobiPoissonSmoother(UT_VoxelArray<StoreReal> &solution, const UT_VoxelArr
     d.download(solution, x);
 }
 
+// HDK_GeometricMultigridOperators.h:369-520: one half-pass over the odd or even 16^3 tiles, forwards or backwards
 template <typename SolveReal, typename StoreReal>
-void tiledGaussSeidelPoissonSmoother(UT_VoxelArray<StoreReal> &, const UT_VoxelArray<StoreReal> &, const UT_VoxelArray<int> &, const bool, const bool,
-				     const std::array<UT_VoxelArray<StoreReal>, 3> * = nullptr)
+void tiledGaussSeidelPoissonSmoother(UT_VoxelArray<StoreReal> &solution, const UT_VoxelArray<StoreReal> &rhs, const UT_VoxelArray<int> &cellLabels,
+				     const bool doSmoothOddTiles, const bool doSmoothForward,
+				     const std::array<UT_VoxelArray<StoreReal>, 3> *boundaryWeights = nullptr)
 {
-    throw B200::Error(GMG_ERR_INVALID, "tiledGaussSeidelPoissonSmoother is not built in this revision of the B200 path (use the damped-Jacobi smoother)");
+    detail::OnlyDouble<StoreReal>();
+    DeviceDomain d(cellLabels, boundaryWeights, 1, true, true);
+    auto x = d.upload(solution), b = d.upload(rhs);
+    B200::check(gmg_gauss_seidel(d.solver, x.g, b.g, doSmoothOddTiles ? 1 : 0, doSmoothForward ? 1 : 0), "gmg_gauss_seidel");
+    d.download(solution, x);
 }
 
 // The band must be the one buildBoundaryCells(cellLabels, 3) returns (what every caller in the reference passes,

@@ -207,6 +207,15 @@ int main(int argc, char **argv)
 	Ref::boundaryJacobiPoissonSmoother<double>(r, b, labR, bandR, &wR);
 	New::boundaryJacobiPoissonSmoother<double>(q, b, labN, bandN, &wN);
 	EXPECT(relDiff(q, r) <= tol, "boundaryJacobiPoissonSmoother %.3e", relDiff(q, r));
+	// tiled Gauss-Seidel, the production smoother (GFS.cpp:463-466): the four half-passes of MG.cpp:466-479 / :740-751 in sequence
+	r = x; q = x;
+	const bool gsOdd[4] = {true, false, false, true}, gsFwd[4] = {true, true, false, false};
+	for (int p = 0; p < 4; ++p)
+	{
+	    Ref::tiledGaussSeidelPoissonSmoother<double>(r, b, labR, gsOdd[p], gsFwd[p], &wR);
+	    New::tiledGaussSeidelPoissonSmoother<double>(q, b, labN, gsOdd[p], gsFwd[p], &wN);
+	    EXPECT(relDiff(q, r) <= tol, "tiledGaussSeidelPoissonSmoother pass %d %.3e", p, relDiff(q, r));
+	}
 	// no-weights form on the coarse labels (what the V-cycle uses above level 0)
 	UT_VoxelArray<double> xc, bc;
 	randomActive(xc, coarseR, 3);
@@ -315,12 +324,47 @@ int main(int argc, char **argv)
 	std::printf("functor form: iterations %d, pressure %.2e\n", itF, relDiff(pF, pR));
     }
 
-    // ---- error behaviour: no silent fallback ------------------------------------------------------------------------------
+    // ---- the production configuration: useGaussSeidel = true (GFS.cpp:463-466, Test.cpp:805-808) -------------------------------
     {
-	bool threw = false;
-	try { HDKB200::GeometricMultigridPoissonSolver gs(labN, wN, mgLevels, true); }
-	catch (const HDKB200::B200::Error &) { threw = true; }
-	EXPECT(threw, "useGaussSeidel = true must fail loudly while the tiled GS smoother is not built");
+	UT_VoxelArray<double> rhs;
+	randomActive(rhs, labR, 9);
+	Ref::scaleVector<double>(rhs, dx * dx, labR);
+	std::ostringstream quiet;
+	std::streambuf *old = std::cout.rdbuf(quiet.rdbuf());
+	HDK::GeometricMultigridPoissonSolver mgR(labR, wR, mgLevels, true);
+	std::cout.rdbuf(old);
+	HDKB200::GeometricMultigridPoissonSolver mgN(labN, wN, mgLevels, true);
+	UT_VoxelArray<double> zR = rhs, zN = rhs;
+	zR.constant(0); zN.constant(0);
+	mgR.applyVCycle(zR, rhs);
+	mgN.applyVCycle(zN, rhs);
+	EXPECT(relDiff(zN, zR) <= 1e-11, "applyVCycle (Gauss-Seidel) %.3e", relDiff(zN, zR));
+	auto A = [&](UT_VoxelArray<double> &d, const UT_VoxelArray<double> &s) { Ref::applyPoissonMatrix<double>(d, s, labR, &wR); };
+	auto M = [&](UT_VoxelArray<double> &d, const UT_VoxelArray<double> &s) { mgR.applyVCycle(d, s); };
+	auto dot = [&](const UT_VoxelArray<double> &a, const UT_VoxelArray<double> &c) { return Ref::dotProduct<double>(a, c, labR); };
+	auto nrm = [&](const UT_VoxelArray<double> &a) { return Ref::squaredL2Norm<double>(a, labR); };
+	auto axpy = [&](UT_VoxelArray<double> &d, const UT_VoxelArray<double> &s, double sc) { Ref::addToVector<double>(d, s, sc, labR); };
+	auto addS = [&](UT_VoxelArray<double> &d, const UT_VoxelArray<double> &u, const UT_VoxelArray<double> &s, double sc) {
+	    Ref::addVectors<double>(d, u, s, sc, labR);
+	};
+	UT_VoxelArray<double> pR = rhs, pN = rhs;
+	pR.constant(0); pN.constant(0);
+	std::ostringstream cap;
+	old = std::cout.rdbuf(cap.rdbuf());
+	HDK::solveGeometricConjugateGradient(pR, rhs, A, M, dot, nrm, axpy, addS, 1e-6, 1000);
+	std::cout.rdbuf(old);
+	int itR = -1;
+	const std::vector<double> hR = parseHistory(cap.str(), &itR);
+	std::vector<double> hN;
+	const int itN = HDKB200::solveGeometricConjugateGradient(mgN, pN, rhs, 1e-6, 1000, true, &hN);
+	EXPECT(std::abs(itR - itN) <= 1, "Gauss-Seidel PCG iterations %d vs %d", itR, itN);
+	const size_t m = std::min(hR.size(), hN.size());
+	double worst = 0;
+	for (size_t i = 0; i < m; ++i) worst = std::max(worst, std::fabs(hR[i] - hN[i]) / hR[i]);
+	EXPECT(m > 0 && worst <= 1e-5 + 6e-6, "Gauss-Seidel residual history deviates by %.3e", worst);
+	EXPECT(relDiff(pN, pR) <= 1e-5, "Gauss-Seidel pressure %.3e", relDiff(pN, pR));
+	std::printf("Gauss-Seidel solver: V-cycle %.2e, PCG iterations %d vs %d, history dev %.2e, pressure %.2e\n", relDiff(zN, zR), itR, itN, worst,
+		    relDiff(pN, pR));
     }
     std::printf(g_fail ? "FAILED: %d check(s)\n" : "facade parity ok (%d failures)\n", g_fail);
     return g_fail ? 1 : 0;

@@ -150,8 +150,6 @@ def test_early_outs_and_errors(gpu_ctx):
     assert it3 == 3 and len(hist3) == 3
     with pytest.raises(api.GmgError):  # odd resolution (MG.cpp:155-157)
         api.GeometricMultigridPoissonSolver(gpu_ctx, labels[:-1], [w[0][:-1], w[1][:-1], w[2][:-1]], levels)
-    with pytest.raises(api.GmgError):  # Gauss-Seidel mode is a later row
-        api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels, useGaussSeidel=True)
     # pure-Neumann box: singular coarse matrix is reported, not silently "solved"
     box = np.full((16, 16, 16), D.EXTERIOR, dtype=np.int32)
     box[1:-1, 1:-1, 1:-1] = D.INTERIOR
@@ -212,3 +210,47 @@ def test_coarse_matrix_scale_quirk(gpu_ctx, port):
     vo = port.solver(labels, w, levels, False, coarse_scale=3.0).vcycle(np.zeros_like(b), b)
     assert relerr(v3, vo) < 1e-11
     s3.close()
+
+
+# ---- tiled Gauss-Seidel, the reference's production smoother ----------------------------------------
+@pytest.mark.parametrize("dom,n", [("complex", 24), ("flipsplash", 32), ("sphere", 48), ("narrow_band", 32)])
+def test_tiled_gauss_seidel_half_passes_match_oracle(gpu_ctx, port, dom, n):
+    """Ops.h:369-520: every (odd/even tiles, forwards/backwards) half-pass, at level 0 (face weights) and level 1."""
+    bl, bw, dx = D.DOMAINS[dom](n)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels, useGaussSeidel=True)
+    for level in range(min(2, s.getMGLevels())):
+        ll = s.level_labels(level)
+        x0, b0 = D.random_active(ll, 3 + level), D.random_active(ll, 4 + level)
+        for odd in (True, False):
+            for fwd in (True, False):
+                X, B = s.grid(level, x0), s.grid(level, b0)
+                s.tiledGaussSeidelPoissonSmoother(X, B, odd, fwd)
+                ref = port.gauss_seidel(x0, b0, ll, odd, fwd, w if level == 0 else None)
+                assert relerr(X.download(), ref) < TOL_OP, (level, odd, fwd)
+    s.close()
+
+
+@pytest.mark.parametrize("dom,n", [("complex", 32), ("flipsplash", 32), ("liquid_box", 32)])
+def test_gauss_seidel_vcycle_and_pcg_match_oracle(gpu_ctx, port, dom, n):
+    """useGaussSeidel = true: MG.cpp:466-479 (odd then even tiles, forwards) and :740-751 (even then odd, backwards)."""
+    bl, bw, dx = D.DOMAINS[dom](n)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    b = D.random_rhs(labels, dx, 9)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels, useGaussSeidel=True)
+    ps = port.solver(labels, w, levels, True)
+    assert s.getMGLevels() == ps.levels
+    assert relerr(s.applyVCycle(np.zeros_like(b), b), ps.vcycle(np.zeros_like(b), b)) < 1e-11
+    x0 = D.random_active(labels, 2, 1e-3)
+    assert relerr(s.applyVCycle(x0, b, useInitialGuess=True), ps.vcycle(x0, b, True)) < 1e-11
+    x, it, hist = s.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 500)
+    xo, ito, histo = ps.pcg(np.zeros_like(b), b, 1e-6, 500)
+    assert it == ito
+    assert (np.abs(hist - histo) / histo).max() < TOL_HISTORY
+    assert relerr(x, xo) < TOL_X
+    # Gauss-Seidel halves the iteration count of the Jacobi smoother or better (why production uses it)
+    sj = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    _, itj, _ = sj.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 500)
+    assert it <= itj
+    s.close()
+    sj.close()
