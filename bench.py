@@ -317,6 +317,26 @@ def run_gpu_arm(args, rank, world, local_rank):
         for a in [x_np, b_np, labels] + list(w):
             rt.cudaHostUnregister(a.ctypes.data)
 
+    # ---- the reference's production smoother (tiled Gauss-Seidel, GFS.cpp:463-466), reported beside the Jacobi headline ----
+    gs = None
+    if world == 1:
+        sg = api.GeometricMultigridPoissonSolver(ctx, labels, w, levels, box=box, useGaussSeidel=True)
+        Bg, Xg = sg.grid(0, b_host), sg.grid(0)
+        gms = []
+        for k in range(5):
+            Xg.zero()
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            ctx.timer_begin()
+            itg, histg = sg.solveDevice(Xg, Bg, TOL, MAX_IT)
+            if k >= 2:
+                gms.append(ctx.timer_end())
+            else:
+                ctx.timer_end()
+        gs = {"solve_ms": float(np.mean(gms)), "iterations": int(itg), "final_rel_residual": float(histg[-1]),
+              "what": "same solve with useGaussSeidel = true (tiled Gauss-Seidel wavefront kernel), mean of 3 after 2 warm-ups"}
+        sg.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(n, 1, 0)
@@ -340,7 +360,102 @@ def run_gpu_arm(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": d_bytes / d_n},
             "kernels": kernels, "kernels_by_level": by_level,
             "kernel_timing": "CUDA events recorded as nodes inside the replayed PCG graphs (warm L2, back-to-back launches); separate pass from `value`",
-            "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "wall_s_timed_region": wall_s,
+            "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "gauss_seidel": gs, "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "wall_s_timed_region": wall_s,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ V-cycle sweep (BASELINE config 4)
+def run_vcycle_sweep(args, rank, world, local_rank):
+    """--workload vcycle: N^3 fully liquid box (BASELINE.json configs[3]; default 512^3 = 134 M cells), V-cycle only.
+    Per kernel class: algorithmic bytes / device time on the fine level, against the measured HBM peak."""
+    import torch
+
+    from geometricmultigridpressuresolver_b200 import api
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    ctx = api.Context(local_rank)
+    if dist is not None:
+        ctx.shard_with_torch(dist)
+    n = args.size
+    t0 = time.perf_counter()
+    bl, bw, dx = D.liquid_box_domain(n)
+    labels, w, off, levels, box = ctx.buildExpandedDomainLazy(bl, bw)
+    del bl, bw
+    solver = api.GeometricMultigridPoissonSolver(ctx, labels, w, levels, box=box)
+    active = solver.active_cells(0)
+    rng = np.random.default_rng(SEED)
+    b_host = np.zeros(labels.shape, dtype=np.float64)
+    sl = tuple(slice(int(box[0][2 - k]), int(box[1][2 - k])) for k in range(3))
+    b_host[sl] = rng.random(tuple(s.stop - s.start for s in sl)) * dx * dx * D.active_mask(labels[sl])
+    B, Z = solver.grid(0, b_host), solver.grid(0)
+    del w, b_host
+    build_s = time.perf_counter() - t0
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def sync():
+        torch.cuda.synchronize()
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        solver.applyVCycleDevice(Z, B)
+    sampler = ClockSampler(local_rank)
+    sync()
+    sampler.start()
+    ctx.launch_count(reset=True)
+    vc = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.timer_begin()
+        solver.applyVCycleDevice(Z, B)
+        vc.append(ctx.timer_end())
+    sync()
+    launches, comm_ops = ctx.launch_count(), ctx.comm_count()
+    clocks = sampler.stop()
+    ms = float(np.mean(vc))
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    nprof = 3
+    for _ in range(nprof):
+        solver.applyVCycleDevice(Z, B)
+    prof_all, prof_fine = ctx.profile(False), ctx.profile(True)
+    ctx.profile_enable(False)
+    peak, peak_kind = measured_peak()
+    fine = {k: v for k, v in prof_fine.items() if k not in ("setup", "coarse_solve", "halo_exchange") and v[1] > 0 and v[2] > 0}
+    classes = {k: {"us_per_launch": v[0] / v[1] * 1e3, "launches_per_vcycle": v[1] // nprof, "algorithmic_gbs": v[2] / (v[0] * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": v[2] / (v[0] * 1e-3) / 1e9 / peak} for k, v in fine.items()}
+    dom = max(fine, key=lambda k: fine[k][0])
+    d_ms, d_n, d_bytes = fine[dom]
+    achieved = d_bytes / (d_ms * 1e-3) / 1e9
+    if rank == 0:
+        vb = BYTES_VCYCLE_PER_CELL * active
+        line = {
+            "metric": "vcycle_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{n}^3 fully liquid box (one DIRICHLET layer), expanded {2 * n}^3, one V-cycle, Jacobi smoother", "levels": solver.getMGLevels(),
+                       "active_cells": active, "l2": "256 MB flush write before every timed step",
+                       "parallelism": "single GPU" if world == 1 else f"{world} z-slabs over NCCL"},
+            "vcycle_algorithmic_gbs": vb / (ms * 1e-3) / 1e9, "vcycle_frac_of_hbm_peak": vb / (ms * 1e-3) / 1e9 / peak / world,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "launches": d_n, "avg_launch_us": d_ms / d_n * 1e3,
+                         "algorithmic_bytes_per_launch": d_bytes / d_n},
+            "fine_level_kernels": classes, "kernel_timing": "CUDA event nodes inside the replayed V-cycle graph (rank 0's slab when sharded)",
+            "clocks": clocks, "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "host_build_s": build_s,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -353,16 +468,21 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--workload", default="pcg", choices=["pcg", "vcycle"], help="pcg: the headline 256^3 MGPCG solve; vcycle: V-cycle-only sweep (config 4)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.size is None:
+        args.size = 512 if args.workload == "vcycle" else 256
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+    elif args.workload == "vcycle":
+        run_vcycle_sweep(args, rank, world, local_rank)
     else:
         run_gpu_arm(args, rank, world, local_rank)
 

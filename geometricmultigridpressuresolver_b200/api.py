@@ -42,6 +42,14 @@ ABI_SYMBOLS = [
 ]
 
 
+def expand_dims(base_shape):
+    """Ops.h:1340-1360: (expanded shape (z,y,x), offset (x,y,z), mgLevels) of a base grid of shape (z,y,x).  Host-only."""
+    lib = load_library()
+    eres, off, lv = (C.c_int64 * 3)(), (C.c_int64 * 3)(), C.c_int()
+    _check(lib.gmg_expand_dims(_res(base_shape), eres, off, C.byref(lv)))
+    return (int(eres[2]), int(eres[1]), int(eres[0])), np.array(list(off), dtype=np.int64), int(lv.value)
+
+
 def shard_plan(level_planes, level_shift_z, level_cells, world, max_shard_levels=3, min_cells=1500000):
     """gmg_shard_plan: (number of sharded levels, cuts[level][rank] in storage planes).  Host-only, needs no GPU."""
     lib = load_library()
@@ -225,9 +233,9 @@ class Context:
         _check(self.lib.gmg_expand_weights(self.h, wp, _res(base_shape), out.ctypes.data_as(_f64p), _res(exp_shape), _vec3(offset), int(axis)))
         return out
 
-    def setBoundaryCellLabels(self, labels, weights, box=None):
-        """Ops.h:1574-1644 (returns a new array)."""
-        l, lp = _i32(np.array(labels, copy=True))
+    def setBoundaryCellLabels(self, labels, weights, box=None, inplace=False):
+        """Ops.h:1574-1644 (returns a new array; inplace=True rewrites `labels` itself, like the reference)."""
+        l, lp = _i32(labels if inplace else np.array(labels, copy=True))
         ws = [_f64(w) for w in weights]
         lo = _vec3(box[0]) if box else None
         hi = _vec3(box[1]) if box else None
@@ -249,6 +257,28 @@ class Context:
         out = np.empty((max(n.value, 1), 3), dtype=np.int64)
         _check(self.lib.gmg_boundary_cells(self.h, lp, _res(l.shape), int(width), out.ctypes.data_as(_i64p), C.byref(n)))
         return out[: n.value]
+
+    def buildExpandedDomainLazy(self, base_labels, base_weights):
+        """buildExpandedDomain for large grids: the expanded arrays come from np.zeros and only the base box is ever written,
+        so the 8x larger virtual grid costs no host memory (untouched pages are never materialised).  OUTSIDE the returned
+        box the arrays hold zeros, not EXTERIOR -- they are only valid for calls that take the box hint (this library reads
+        host arrays inside the hinted box only)."""
+        bl = np.asarray(base_labels)
+        shape, off, levels = expand_dims(bl.shape)
+        nz, ny, nx = bl.shape
+        box = (slice(int(off[2]), int(off[2]) + nz), slice(int(off[1]), int(off[1]) + ny), slice(int(off[0]), int(off[0]) + nx))
+        labels = np.zeros(shape, dtype=np.int32)
+        labels[box] = np.where(bl == 1, 1, np.where(bl == 0, 0, 2))  # Ops.h:1404-1453
+        w = []
+        for a in range(3):
+            we = np.zeros(face_shape(shape, a), dtype=np.float64)
+            fb = list(box)
+            fb[2 - a] = slice(fb[2 - a].start, fb[2 - a].stop + 1)
+            we[tuple(fb)] = np.maximum(np.asarray(base_weights[a], dtype=np.float64), 0.0)  # Ops.h:1488-1571
+            w.append(we)
+        hi = [int(off[a]) + bl.shape[2 - a] for a in range(3)]
+        self.setBoundaryCellLabels(labels, w, box=(off, hi), inplace=True)
+        return labels, w, off, levels, (off, hi)
 
     def buildExpandedDomain(self, base_labels, base_weights):
         """Test.cpp:170-204 buildExpandedDomain: labels, three weight grids, setBoundaryCellLabels."""

@@ -447,13 +447,22 @@ static void makeGeom(Geom &g, const int64_t res[3], const int64_t lo[3], const i
 }
 
 // clip of the storage box against the host grid [0, hostRes): storage-coordinate range [lo,hi) that exists on the host
-static bool clipBox(const Geom &g, const int64_t hostRes[3], int lo[3], int hi[3])
+// bounds (nullable): expanded-coordinate box [bounds, bounds+3) outside which the host array is not to be read at all
+// (the caller's non-EXTERIOR hint: labels are EXTERIOR, weights and values 0 out there by contract)
+static bool clipBox(const Geom &g, const int64_t hostRes[3], int lo[3], int hi[3], const int64_t *bounds = nullptr)
 {
     bool any = true;
     for (int a = 0; a < 3; ++a)
     {
-	lo[a] = std::max<int64_t>(0, -int64_t(g.org[a]));
-	hi[a] = int(std::min<int64_t>(g.n[a], hostRes[a] - g.org[a]));
+	int64_t l = std::max<int64_t>(0, -int64_t(g.org[a]));
+	int64_t h = std::min<int64_t>(g.n[a], hostRes[a] - g.org[a]);
+	if (bounds)
+	{
+	    l = std::max<int64_t>(l, bounds[a] - g.org[a]);
+	    h = std::min<int64_t>(h, bounds[3 + a] - g.org[a]);
+	}
+	lo[a] = int(l);
+	hi[a] = int(h);
 	if (hi[a] <= lo[a]) any = false;
     }
     return any;
@@ -614,11 +623,11 @@ static bool scanBounds(const int32_t *labels, const int64_t res[3], int64_t lo[3
     return true;
 }
 
-static int uploadLabels(gmg_ctx *ctx, uint8_t *dst, const int32_t *host, const int64_t res[3], const Geom &g)
+static int uploadLabels(gmg_ctx *ctx, uint8_t *dst, const int32_t *host, const int64_t res[3], const Geom &g, const int64_t *bounds = nullptr)
 {
     int lo[3], hi[3];
     const BoxArgs ba = boxArgs(g);
-    if (!clipBox(g, res, lo, hi))
+    if (!clipBox(g, res, lo, hi, bounds))
     {
 	GMG_CUDA(cudaMemsetAsync(dst, L_EXTERIOR, g.total, ctx->stream));
 	return GMG_OK;
@@ -636,7 +645,8 @@ static int uploadLabels(gmg_ctx *ctx, uint8_t *dst, const int32_t *host, const i
     return GMG_OK;
 }
 
-static int downloadLabels(gmg_ctx *ctx, int32_t *host, const uint8_t *src, const int64_t res[3], const Geom &g, bool fillExterior)
+static int downloadLabels(gmg_ctx *ctx, int32_t *host, const uint8_t *src, const int64_t res[3], const Geom &g, bool fillExterior,
+			  const int64_t *bounds = nullptr)
 {
     if (fillExterior)
     {
@@ -644,7 +654,7 @@ static int downloadLabels(gmg_ctx *ctx, int32_t *host, const uint8_t *src, const
 	std::fill(host, host + n, int32_t(L_EXTERIOR));
     }
     int lo[3], hi[3];
-    if (!clipBox(g, res, lo, hi)) return GMG_OK;
+    if (!clipBox(g, res, lo, hi, bounds)) return GMG_OK;
     int32_t *staging = nullptr;
     const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
     GMG_CUDA(devMalloc(&staging, sizeof(int32_t) * cnt));
@@ -659,10 +669,11 @@ static int downloadLabels(gmg_ctx *ctx, int32_t *host, const uint8_t *src, const
 }
 
 // host dense grid (hostRes may be a face grid) -> pitched storage, zero where the host has no value
-static int uploadValues(gmg_ctx *ctx, double *dst, const double *host, const int64_t hostRes[3], const Geom &g, const uint8_t *maskLabels = nullptr)
+static int uploadValues(gmg_ctx *ctx, double *dst, const double *host, const int64_t hostRes[3], const Geom &g, const uint8_t *maskLabels = nullptr,
+			const int64_t *bounds = nullptr)
 {
     int lo[3], hi[3];
-    if (!clipBox(g, hostRes, lo, hi))
+    if (!clipBox(g, hostRes, lo, hi, bounds))
     {
 	GMG_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * g.total, ctx->stream));
 	return GMG_OK;
@@ -680,11 +691,12 @@ static int uploadValues(gmg_ctx *ctx, double *dst, const double *host, const int
     return GMG_OK;
 }
 
-static int downloadValues(gmg_ctx *ctx, double *host, const double *src, const int64_t hostRes[3], const Geom &g, bool fillZero)
+static int downloadValues(gmg_ctx *ctx, double *host, const double *src, const int64_t hostRes[3], const Geom &g, bool fillZero,
+			  const int64_t *bounds = nullptr)
 {
     if (fillZero) std::memset(host, 0, sizeof(double) * size_t(hostRes[0]) * hostRes[1] * hostRes[2]);
     int lo[3], hi[3];
-    if (!clipBox(g, hostRes, lo, hi)) return GMG_OK;
+    if (!clipBox(g, hostRes, lo, hi, bounds)) return GMG_OK;
     double *staging = nullptr;
     const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
     GMG_CUDA(devMalloc(&staging, sizeof(double) * cnt));
@@ -795,7 +807,7 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_CUDA(devFree(idxB));
     GMG_CUDA(devFree(idxI));
-    GMG_CUDA(devMalloc(&L.bandNbr, sizeof(int32_t) * 6 * std::max(nBand, 1)));
+    GMG_CUDA(devMalloc(&L.bandRef, sizeof(int32_t) * 6 * std::max(nBand, 1)));
     GMG_CUDA(devMalloc(&L.bandV0, sizeof(double) * std::max(nBand, 1)));
     GMG_CUDA(devMalloc(&L.bandV1, sizeof(double) * std::max(nBand, 1)));
     GMG_CUDA(devMalloc(&L.bandB, sizeof(double) * std::max(nBand, 1)));
@@ -816,7 +828,7 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 	}
 	{
 	    GMG_LAUNCH(ctx, KC_SETUP, 0);
-	    k_band_nbr<<<unsigned(divUp(nBand, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bandNbr, pos, L.bandIdx, nBand, g.pitch, g.plane);
+	    k_band_ref<<<unsigned(divUp(nBand, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bandRef, pos, L.bandIdx, L.labels, nBand, g.pitch, g.plane);
 	}
 	GMG_CUDA(cudaStreamSynchronize(ctx->stream));
 	GMG_CUDA(devFree(posBase));
@@ -833,6 +845,7 @@ static int buildCoefs(gmg_ctx *ctx, Level &L, const double *w0, const double *w1
 	k_band_coef<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bcoef, L.bandIdx, L.nBoundary, L.labels, w0, w1, w2, L.g.pitch,
 										   L.g.plane);
     }
+    L.hasWeights = w0 != nullptr;
     return GMG_OK;
 }
 
@@ -936,7 +949,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 
 static void freeLevel(Level &L)
 {
-    devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandIdx); devFree(L.bandNbr); devFree(L.bcoef);
+    devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandIdx); devFree(L.bandRef); devFree(L.bcoef);
     devFree(L.bandV0); devFree(L.bandV1); devFree(L.bandB);
     devFree(L.chunksInterior); devFree(L.chunksActive);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
@@ -1050,7 +1063,8 @@ static int boundsFromHintOrScan(const int32_t *labels, const int64_t res[3], con
 
 // dW[a] are ALLOCATION bases covering the stored box plus one plane below and above (a slab's edge cells read the
 // forward z-face weight of the next plane); kernels take dW[a] + g.plane.
-static int uploadWeights(gmg_ctx *ctx, double *dW[3], const double *w0, const double *w1, const double *w2, const int64_t res[3], const Geom &g)
+static int uploadWeights(gmg_ctx *ctx, double *dW[3], const double *w0, const double *w1, const double *w2, const int64_t res[3], const Geom &g,
+			 const int64_t *bounds = nullptr)
 {
     const double *w[3] = {w0, w1, w2};
     Geom ge = g;
@@ -1062,7 +1076,13 @@ static int uploadWeights(gmg_ctx *ctx, double *dW[3], const double *w0, const do
 	int64_t fr[3] = {res[0], res[1], res[2]};
 	++fr[a];
 	GMG_CUDA(devMalloc(&dW[a], sizeof(double) * ge.total));
-	GMG_TRY(uploadValues(ctx, dW[a], w[a], fr, ge));
+	int64_t fb[6];
+	if (bounds)
+	{
+	    for (int k = 0; k < 6; ++k) fb[k] = bounds[k];
+	    ++fb[3 + a];  // the face behind the last non-EXTERIOR cell
+	}
+	GMG_TRY(uploadValues(ctx, dW[a], w[a], fr, ge, nullptr, bounds ? fb : nullptr));
     }
     return GMG_OK;
 }
@@ -1082,13 +1102,15 @@ extern "C" int gmg_set_boundary_labels(gmg_ctx *ctx, int32_t *labels, const int6
     double *dW[3] = {nullptr, nullptr, nullptr};
     GMG_CUDA(devMalloc(&dIn, g.total));
     GMG_CUDA(devMalloc(&dOut, g.total));
-    GMG_TRY(uploadLabels(ctx, dIn, labels, res, g));
-    GMG_TRY(uploadWeights(ctx, dW, w0, w1, w2, res, g));
+    // the host arrays are only read inside the non-EXTERIOR box (a caller may hand over lazily allocated expanded grids)
+    const int64_t bounds[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+    GMG_TRY(uploadLabels(ctx, dIn, labels, res, g, bounds));
+    GMG_TRY(uploadWeights(ctx, dW, w0, w1, w2, res, g, bounds));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_set_boundary<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dOut, dIn, dW[0] + g.plane, dW[1] + g.plane, dW[2] + g.plane, boxArgs(g));
     }
-    GMG_TRY(downloadLabels(ctx, labels, dOut, res, g, false));
+    GMG_TRY(downloadLabels(ctx, labels, dOut, res, g, false, bounds));
     for (int a = 0; a < 3; ++a) GMG_CUDA(devFree(dW[a]));
     GMG_CUDA(devFree(dIn));
     GMG_CUDA(devFree(dOut));
@@ -1544,7 +1566,8 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	makeGeom(L0.g, res, lo, hi);
 	if (L0.g.total >= (int64_t(1) << 31)) return fail(invalid("gmg_solver_create: cropped box exceeds 2^31 cells"));
 	if ((st = (devMalloc(&L0.labels, L0.g.total) == cudaSuccess ? GMG_OK : GMG_ERR_CUDA)) != GMG_OK) return fail(st);
-	if ((st = uploadLabels(ctx, L0.labels, labels, res, L0.g)) != GMG_OK) return fail(st);
+	for (int a = 0; a < 3; ++a) { s->hostBounds[a] = lo[a]; s->hostBounds[3 + a] = hi[a]; }
+	if ((st = uploadLabels(ctx, L0.labels, labels, res, L0.g, s->hostBounds)) != GMG_OK) return fail(st);
     }
     lap("upload labels");
     // coarse labels (MG.cpp:238-253) over the GLOBAL box of every level (one byte per cell, replicated on every rank),
@@ -1586,7 +1609,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     // z-slab views of the fine levels (world > 1); afterwards L.g / L.labels are the rank's local box
     if ((st = planShards(s)) != GMG_OK) return fail(st);
     // no weight grids = the reference's boundaryWeights == nullptr form (weight 1 to active/DIRICHLET neighbours, Ops.h:237-248)
-    if (w0 && (st = uploadWeights(ctx, dW, w0, w1, w2, res, s->lv[0].g)) != GMG_OK) return fail(st);
+    if (w0 && (st = uploadWeights(ctx, dW, w0, w1, w2, res, s->lv[0].g, s->hostBounds)) != GMG_OK) return fail(st);
     lap("shard plan, upload weights");
     // bands (MG.cpp:279-281), coefficient records, chunk lists, grids
     int maxGrid = 0;
@@ -1760,37 +1783,47 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
     a.x = x;
     a.b = b;
     a.bandIdx = L.bandIdx;
-    a.bandNbr = L.bandNbr;
+    a.bandRef = L.bandRef;
     a.bcoef = L.bcoef;
     a.bandB = L.bandB;
     a.nBoundary = L.nBoundary;
     a.nBand = L.nBand;
     a.pitch = L.g.pitch;
     a.plane = L.g.plane;
-    const unsigned grid = unsigned(divUp(L.nBand, BLOCK));
+    const unsigned grid = unsigned(divUp(L.nBand, BLOCK * BAND_PER_THREAD));
     cudaStream_t st = s->ctx->stream;
     const double bytes = double(L.nBand) * 29.0;
+    const bool hw = L.hasWeights;
     double *cur = L.bandV0, *nxt = L.bandV1;
     // sweep 1: grid -> compact
     a.vin = nullptr;
     a.vout = cur;
     {
 	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
-	if (zeroGrid) GMG_CUDA(launchK((k_band<false, false, true, true>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
-	else GMG_CUDA(launchK((k_band<false, false, true, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	if (zeroGrid) GMG_CUDA(launchK((k_band<false, false, true, true, false>), grid, BLOCK, 0, st, a));
+	else if (hw) GMG_CUDA(launchK((k_band<false, false, true, false, true>), grid, BLOCK, 0, st, a));
+	else GMG_CUDA(launchK((k_band<false, false, true, false, false>), grid, BLOCK, 0, st, a));
     }
     if (sweeps == 1)
     {
 	GMG_LAUNCH(s->ctx, KC_BAND, double(L.nBand) * 20.0);
-	GMG_CUDA(launchK(k_band_scatter, unsigned(grid), unsigned(BLOCK), size_t(0), st, x, L.bandIdx, cur, L.nBand));
+	GMG_CUDA(launchK(k_band_scatter, unsigned(divUp(L.nBand, BLOCK)), BLOCK, 0, st, x, L.bandIdx, cur, L.nBand));
     }
     for (int sw = 2; sw <= sweeps; ++sw)
     {
 	a.vin = cur;
 	a.vout = nxt;
 	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
-	if (sw == sweeps) GMG_CUDA(launchK((k_band<true, true, false, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
-	else GMG_CUDA(launchK((k_band<true, false, false, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	if (sw == sweeps)
+	{
+	    if (hw) GMG_CUDA(launchK((k_band<true, true, false, false, true>), grid, BLOCK, 0, st, a));
+	    else GMG_CUDA(launchK((k_band<true, true, false, false, false>), grid, BLOCK, 0, st, a));
+	}
+	else
+	{
+	    if (hw) GMG_CUDA(launchK((k_band<true, false, false, false, true>), grid, BLOCK, 0, st, a));
+	    else GMG_CUDA(launchK((k_band<true, false, false, false, false>), grid, BLOCK, 0, st, a));
+	}
 	std::swap(cur, nxt);
     }
     GMG_CUDA(cudaGetLastError());
@@ -2394,7 +2427,7 @@ extern "C" int gmg_grid_upload(gmg_grid *g, const double *host)
     if (!g || !host) return invalid("null argument");
     GMG_CUDA(enterCtx(g->solver->ctx));
     const Geom &ge = g->solver->lv[g->level].g;
-    return uploadValues(g->solver->ctx, g->d, host, ge.res, ge, g->solver->lv[g->level].labels);
+    return uploadValues(g->solver->ctx, g->d, host, ge.res, ge, g->solver->lv[g->level].labels, g->level == 0 ? g->solver->hostBounds : nullptr);
 }
 // the rank's owned planes as a box of their own (what a sharded context hands back to the host)
 static Geom ownedGeom(const Level &L)
@@ -2585,13 +2618,13 @@ extern "C" int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInit
     GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY(ensureHostIO(s));
     const Geom &g = s->lv[0].g;
-    if (useInitialGuess) GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels));
-    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels));
+    if (useInitialGuess) GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels, s->hostBounds));
+    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels, s->hostBounds));
     GMG_TRY(vcycleDevice(s, s->pcgX, s->pcgB, useInitialGuess != 0));
     // cells outside the stored box are non-active: the reference leaves them untouched (0 after constant(0));
     // a sharded context writes the rank's owned planes only
     const Geom go = ownedGeom(s->lv[0]);
-    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, !useInitialGuess);
+    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, !useInitialGuess, s->hostBounds);
 }
 
 extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations, double *relResHistory,
@@ -2601,9 +2634,9 @@ extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, in
     GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY(ensureHostIO(s));
     const Geom &g = s->lv[0].g;
-    GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels));
-    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels));
+    GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels, s->hostBounds));
+    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels, s->hostBounds));
     GMG_TRY(pcgDevice(s, s->pcgX, s->pcgB, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount));
     const Geom go = ownedGeom(s->lv[0]);
-    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, false);
+    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, false, s->hostBounds);
 }

@@ -82,7 +82,8 @@ struct Level
     // boundary band: [0,nBoundary) BOUNDARY cells, [nBoundary,nBand) INTERIOR cells of the band; linear order inside each part
     int nBoundary = 0, nBand = 0;
     int32_t *bandIdx = nullptr;  // [nBand] storage index
-    int32_t *bandNbr = nullptr;  // [6][nBand] band position of the neighbour, -1 if not in the band
+    int32_t *bandRef = nullptr;  // [6][nBand] neighbour reference (gmg_kernels.cuh: BandArgs::bandRef)
+    bool hasWeights = false;     // level 0 built with face weights: BOUNDARY cells carry fractional coefficients
     double *bcoef = nullptr;     // [7][nBoundary]: coefficient on each of the 6 neighbours, then the diagonal
     double *bandV0 = nullptr, *bandV1 = nullptr, *bandB = nullptr;
     // CTAs of the full-grid kernels: chunks holding at least one INTERIOR cell / one active cell
@@ -149,6 +150,7 @@ struct gmg_solver
     gmg_solver_options opt;
     int levels = 0;
     std::vector<gmg::Level> lv;
+    int64_t hostBounds[6] = {0, 0, 0, 0, 0, 0};  // expanded [lo, hi) of the non-EXTERIOR cells at level 0: host arrays are only read inside
     // coarsest direct solve
     int nCoarse = 0;
     int32_t *coarseIdx = nullptr; // [nCoarse] storage index at the coarsest level

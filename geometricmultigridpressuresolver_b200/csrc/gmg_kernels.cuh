@@ -199,7 +199,7 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
     {
 	const int k = (vb - a.nChunks) * BLOCK + tid;
 	const int64_t i = k < a.nBoundary ? int64_t(a.bandIdx[k]) : 0;
-	const int z = int(i / a.plane);
+	const int z = int(unsigned(i) / unsigned(a.plane));  // a level's box holds fewer than 2^31 cells: 32-bit division
 	if (k < a.nBoundary && z >= a.zlo && z < a.zhi)
 	{
 	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
@@ -240,7 +240,8 @@ struct BandArgs
     double *x;           // grid
     const double *b;     // grid rhs
     const int32_t *bandIdx;
-    const int32_t *bandNbr;
+    const int32_t *bandRef;  // [6][nBand] neighbour reference: >= 0 position in the band; BAND_SKIP: coefficient 0 (not active);
+			     // <= -2: an active cell outside the band (frozen during the band sweeps) at grid index -2 - ref
     const double *bcoef;
     const double *vin;
     double *vout;
@@ -249,49 +250,74 @@ struct BandArgs
     int pitch;
     int64_t plane;
 };
+constexpr int BAND_SKIP = -1;
+constexpr int BAND_PER_THREAD = 2;  // cells per thread: two independent gather chains in flight
 
 // FROM_COMPACT: centre/band-neighbour values come from vin; TO_GRID: result goes to x[idx];
-// FIRST: rhs is gathered from the grid and cached in bandB; ZERO: the grid is known to be all zero.
-template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO>
+// FIRST: rhs is gathered from the grid and cached in bandB; ZERO: the grid is known to be all zero;
+// HAS_W: level 0 with face weights -- BOUNDARY cells multiply by their coefficient records (elsewhere every coefficient is 1)
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W>
 __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 {
-    const int k = vb * BLOCK + tid;
-    if (k >= a.nBand) return;
-    const int64_t i = a.bandIdx[k];
-    double rhs;
-    if (FIRST) { rhs = a.b[i]; a.bandB[k] = rhs; }
-    else rhs = a.bandB[k];
-    const bool isBoundary = k < a.nBoundary;
-    const double diag = isBoundary ? a.bcoef[int64_t(6) * a.nBoundary + k] : 6.0;
-    double centre = 0.0, lap = 0.0;
-    if (!ZERO)
-    {
-	centre = FROM_COMPACT ? a.vin[k] : a.x[i];
-	const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
+    double v[BAND_PER_THREAD];
+    int64_t gi[BAND_PER_THREAD];
 #pragma unroll
-	for (int n = 0; n < 6; ++n)
+    for (int c = 0; c < BAND_PER_THREAD; ++c)
+    {
+	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
+	v[c] = 0.0;
+	gi[c] = 0;
+	if (k >= a.nBand) continue;
+	int64_t i = 0;
+	if (!FROM_COMPACT || TO_GRID || FIRST) i = a.bandIdx[k];
+	gi[c] = i;
+	double rhs;
+	if (FIRST) { rhs = a.b[i]; a.bandB[k] = rhs; }
+	else rhs = a.bandB[k];
+	const double diag = k < a.nBoundary ? a.bcoef[int64_t(6) * a.nBoundary + k] : 6.0;
+	double centre = 0.0, lap = 0.0;
+	if (!ZERO)
 	{
-	    const double cn = isBoundary ? a.bcoef[int64_t(n) * a.nBoundary + k] : 1.0;
-	    if (cn != 0.0)
+	    const bool weighted = HAS_W && k < a.nBoundary;
+	    centre = FROM_COMPACT ? a.vin[k] : a.x[i];
+	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
+	    int ref[6];
+#pragma unroll
+	    for (int n = 0; n < 6; ++n) ref[n] = a.bandRef[int64_t(n) * a.nBand + k];
+#pragma unroll
+	    for (int n = 0; n < 6; ++n)
 	    {
-		int j = -1;
-		if (FROM_COMPACT) j = a.bandNbr[int64_t(n) * a.nBand + k];
-		const double u = (j >= 0) ? a.vin[j] : a.x[i + stride[n]];
-		lap -= cn * u;
+		if (ref[n] == BAND_SKIP) continue;
+		double u;
+		if (FROM_COMPACT) u = ref[n] >= 0 ? a.vin[ref[n]] : a.x[-2 - ref[n]];
+		else u = a.x[i + stride[n]];
+		if (weighted)
+		{
+		    const double cn = a.bcoef[int64_t(n) * a.nBoundary + k];
+		    if (cn != 0.0) lap -= cn * u;
+		}
+		else lap -= u;
 	    }
+	    lap += diag * centre;
 	}
-	lap += diag * centre;
+	double r = rhs - lap;
+	r /= diag;
+	v[c] = centre + (2.0 / 3.0) * r;
     }
-    double r = rhs - lap;
-    r /= diag;
-    const double v = centre + (2.0 / 3.0) * r;
-    if (TO_GRID) a.x[i] = v;
-    else a.vout[k] = v;
+#pragma unroll
+    for (int c = 0; c < BAND_PER_THREAD; ++c)
+    {
+	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
+	if (k >= a.nBand) continue;
+	if (TO_GRID) a.x[gi[c]] = v[c];
+	else a.vout[k] = v[c];
+    }
 }
-template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO>
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W>
 __global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
-{ pdlEnter();
-    bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO>(a, blockIdx.x, threadIdx.x);
+{
+    pdlEnter();
+    bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W>(a, blockIdx.x, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t *bandIdx, const double *v, int nBand)
@@ -336,7 +362,7 @@ __device__ __forceinline__ void restrictBody(const TransferArgs &a, int vb, int 
     const int64_t ci = int64_t(cz) * a.coarsePlane + inPlane;
     const int l = a.coarseLabels[ci];
     if (!(l == L_INTERIOR || l == L_BOUNDARY)) return;
-    const int cy = int(inPlane / a.coarsePitch), cx = int(inPlane - int64_t(cy) * a.coarsePitch);
+    const int cy = int(unsigned(inPlane) / unsigned(a.coarsePitch)), cx = int(inPlane - int64_t(cy) * a.coarsePitch);
     const int fx = 2 * (cx - a.shift[0]) - 1, fy = 2 * (cy - a.shift[1]) - 1, fz = 2 * (cz - a.shift[2]) - 1;
     const double *f = a.fine + (int64_t(fz) * a.finePlane + int64_t(fy) * a.finePitch + fx);
     double v = 0.0;
@@ -365,54 +391,72 @@ __global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a) { pdlE
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double lerpRef(double v0, double v1, double f) { return (1. - f) * v0 + f * v1; }  // Ops.h:841-848
 
+// A thread owns the two x-children of one coarse cell in TWO consecutive z-planes (the two z-children): they interpolate
+// from the same 3 x 2 x 3 coarse values, which are loaded once.
 __device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int tid)
 {
     const int c = a.chunks[vb];
     const int zb = c / a.chunksPerPlane;
     const int64_t inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * tid;
     if (inPlane >= a.finePlane) return;
-    const int fy = int(inPlane / a.finePitch), fx = int(inPlane - int64_t(fy) * a.finePitch);
+    const int fy = int(unsigned(inPlane) / unsigned(a.finePitch)), fx = int(inPlane - int64_t(fy) * a.finePitch);
     const int mx = (fx >> 1) + a.shift[0];
     const int my = (fy >> 1) + a.shift[1];
     const int ys = (fy & 1) ? my : my - 1;
     const double wy = (fy & 1) ? .25 : .75;
-#pragma unroll 1
-    for (int dz = 0; dz < CHUNK_Z; ++dz)
-    {
-	const int fz = zb * CHUNK_Z + dz;
-	if (fz >= a.zhi) break;
-	if (fz < a.zlo) continue;
-	const int64_t i = int64_t(fz) * a.finePlane + inPlane;
-	const uchar2 l = *reinterpret_cast<const uchar2 *>(a.fineLabels + i);
-	const bool a0 = (l.x == L_INTERIOR || l.x == L_BOUNDARY), a1 = (l.y == L_INTERIOR || l.y == L_BOUNDARY);
-	if (!(a0 | a1)) continue;
-	const int mz = (fz >> 1) + a.shift[2];
-	const int zs = (fz & 1) ? mz : mz - 1;
-	const double wz = (fz & 1) ? .25 : .75;
-	double v[3][2][2];
 #pragma unroll
-	for (int z = 0; z < 2; ++z)
+    for (int p = 0; p < CHUNK_Z / 2; ++p)
+    {
+	const int fz0 = zb * CHUNK_Z + 2 * p;  // even: storage origins are even
+	if (fz0 >= a.zhi) break;
+	const bool do0 = fz0 >= a.zlo, do1 = fz0 + 1 >= a.zlo && fz0 + 1 < a.zhi;
+	const int64_t i0 = int64_t(fz0) * a.finePlane + inPlane, i1 = i0 + a.finePlane;
+	uchar2 l0 = make_uchar2(L_EXTERIOR, L_EXTERIOR), l1 = l0;
+	if (do0) l0 = *reinterpret_cast<const uchar2 *>(a.fineLabels + i0);
+	if (do1) l1 = *reinterpret_cast<const uchar2 *>(a.fineLabels + i1);
+	const bool a00 = (l0.x == L_INTERIOR || l0.x == L_BOUNDARY), a01 = (l0.y == L_INTERIOR || l0.y == L_BOUNDARY);
+	const bool a10 = (l1.x == L_INTERIOR || l1.x == L_BOUNDARY), a11 = (l1.y == L_INTERIOR || l1.y == L_BOUNDARY);
+	if (!(a00 | a01 | a10 | a11)) continue;
+	const int mz = (fz0 >> 1) + a.shift[2];
+	// x-lerps right after each row load (even x-child: start = m-1, f = .75; odd: start = m, f = .25), then y, then z:
+	// the nesting and operation order of Ops.h:841-871, with 12 live values instead of 18
+	double ex[2][3], ox[2][3];  // [y: ys, ys+1][z: mz-1..mz+1]
+#pragma unroll
+	for (int z = 0; z < 3; ++z)
 #pragma unroll
 	    for (int y = 0; y < 2; ++y)
 	    {
-		const double *row = a.coarse + (int64_t(zs + z) * a.coarsePlane + int64_t(ys + y) * a.coarsePitch + mx);
-		v[0][y][z] = row[-1];
-		v[1][y][z] = row[0];
-		v[2][y][z] = row[1];
+		const double *row = a.coarse + (int64_t(mz - 1 + z) * a.coarsePlane + int64_t(ys + y) * a.coarsePitch + mx);
+		const double v0 = row[-1], v1 = row[0], v2 = row[1];
+		ex[y][z] = lerpRef(v0, v1, .75);
+		ox[y][z] = lerpRef(v1, v2, .25);
 	    }
-	const double2 old = ld2(a.out + i);
-	// even child: start = m-1, f = .75; odd child: start = m, f = .25
-	const double e = lerpRef(lerpRef(lerpRef(v[0][0][0], v[1][0][0], .75), lerpRef(v[0][1][0], v[1][1][0], .75), wy),
-				 lerpRef(lerpRef(v[0][0][1], v[1][0][1], .75), lerpRef(v[0][1][1], v[1][1][1], .75), wy), wz);
-	const double o = lerpRef(lerpRef(lerpRef(v[1][0][0], v[2][0][0], .25), lerpRef(v[1][1][0], v[2][1][0], .25), wy),
-				 lerpRef(lerpRef(v[1][0][1], v[2][0][1], .25), lerpRef(v[1][1][1], v[2][1][1], .25), wy), wz);
-	const double n0 = old.x + 4. * e, n1 = old.y + 4. * o;
-	if (a0 & a1) st2(a.out + i, make_double2(n0, n1));
-	else if (a0) a.out[i] = n0;
-	else a.out[i + 1] = n1;
+	double ey[3], oy[3];
+#pragma unroll
+	for (int z = 0; z < 3; ++z)
+	{
+	    ey[z] = lerpRef(ex[0][z], ex[1][z], wy);
+	    oy[z] = lerpRef(ox[0][z], ox[1][z], wy);
+	}
+	// the two z-children: even plane start = m-1, f = .75; odd plane start = m, f = .25
+#pragma unroll
+	for (int q = 0; q < 2; ++q)
+	{
+	    const bool ax = q ? a10 : a00, ay = q ? a11 : a01;
+	    if (!(ax | ay)) continue;
+	    const int64_t i = q ? i1 : i0;
+	    const double wz = q ? .25 : .75;
+	    const double2 old = ld2(a.out + i);
+	    const double e = lerpRef(ey[q], ey[q + 1], wz);
+	    const double o = lerpRef(oy[q], oy[q + 1], wz);
+	    const double n0 = old.x + 4. * e, n1 = old.y + 4. * o;
+	    if (ax & ay) st2(a.out + i, make_double2(n0, n1));
+	    else if (ax) a.out[i] = n0;
+	    else a.out[i + 1] = n1;
+	}
     }
 }
-__global__ void __launch_bounds__(BLOCK) k_prolong(const TransferArgs a) { pdlEnter(); prolongBody(a, blockIdx.x, threadIdx.x); }
+__global__ void __launch_bounds__(BLOCK, 6) k_prolong(const TransferArgs a) { pdlEnter(); prolongBody(a, blockIdx.x, threadIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
 // Coarsest level (MG.cpp:669-692): gather b, x = A^-1 b (dense inverse of the SPD matrix, built on the
@@ -1107,14 +1151,28 @@ __global__ void __launch_bounds__(BLOCK) k_band_pos(int32_t *pos, const int32_t 
     const int k = blockIdx.x * BLOCK + threadIdx.x;
     if (k < nBand) pos[bandIdx[k]] = k;
 }
-__global__ void __launch_bounds__(BLOCK) k_band_nbr(int32_t *bandNbr, const int32_t *pos, const int32_t *bandIdx, int nBand, int pitch, int64_t plane)
+// neighbour references of the band cells (BandArgs::bandRef): position in the band, BAND_SKIP for a non-active neighbour,
+// -2 - gridIndex for an active neighbour outside the band
+__global__ void __launch_bounds__(BLOCK) k_band_ref(int32_t *bandRef, const int32_t *pos, const int32_t *bandIdx, const uint8_t *labels, int nBand,
+						   int pitch, int64_t plane)
 {
     const int k = blockIdx.x * BLOCK + threadIdx.x;
     if (k >= nBand) return;
     const int64_t i = bandIdx[k];
     const int64_t stride[6] = {-1, 1, -int64_t(pitch), int64_t(pitch), -plane, plane};
 #pragma unroll
-    for (int n = 0; n < 6; ++n) bandNbr[int64_t(n) * nBand + k] = pos[i + stride[n]];
+    for (int n = 0; n < 6; ++n)
+    {
+	const int64_t j = i + stride[n];
+	const int l = labels[j];
+	int ref = BAND_SKIP;
+	if (l == L_INTERIOR || l == L_BOUNDARY)
+	{
+	    const int p = pos[j];
+	    ref = p >= 0 ? p : int(-2 - j);
+	}
+	bandRef[int64_t(n) * nBand + k] = ref;
+    }
 }
 // coefficient record of a BOUNDARY cell (Ops.h:208-255): c_n = 1 (INTERIOR nbr), w (BOUNDARY nbr), 0 otherwise;
 // diag = sum of 1 (INTERIOR), w (BOUNDARY), w (DIRICHLET).  w == nullptr (coarse levels) means weight 1.

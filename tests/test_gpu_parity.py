@@ -254,3 +254,29 @@ def test_gauss_seidel_vcycle_and_pcg_match_oracle(gpu_ctx, port, dom, n):
     assert it <= itj
     s.close()
     sj.close()
+
+
+def test_lazy_expanded_domain_matches_the_full_one(gpu_ctx):
+    """buildExpandedDomainLazy only writes the base box of the (virtual) expanded grids; with the box hint the library never
+    reads outside it, so the solver it produces is the one the fully materialised arrays give."""
+    bl, bw, dx = D.flipsplash_domain(32)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    ll, lw, loff, llevels, box = gpu_ctx.buildExpandedDomainLazy(bl, bw)
+    assert llevels == levels and (loff == off).all()
+    sl = tuple(slice(int(box[0][2 - k]), int(box[1][2 - k])) for k in range(3))
+    assert (ll[sl] == labels[sl]).all()
+    outside = np.ones(labels.shape, dtype=bool)
+    outside[sl] = False
+    assert not ll[outside].any()  # zeros, i.e. NOT the EXTERIOR label: only usable together with the box hint
+    s1 = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    s2 = api.GeometricMultigridPoissonSolver(gpu_ctx, ll, lw, llevels, box=box)
+    assert s1.getMGLevels() == s2.getMGLevels()
+    for l in range(s1.getMGLevels()):
+        assert (s1.level_labels(l) == s2.level_labels(l)).all()
+        assert (s1.level_boundary_cells(l) == s2.level_boundary_cells(l)).all()
+    b = D.random_rhs(labels, dx, 21)
+    x1, it1, h1 = s1.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 200)
+    x2, it2, h2 = s2.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 200)
+    assert it1 == it2 and np.array_equal(h1, h2) and np.array_equal(x1, x2)
+    s1.close()
+    s2.close()

@@ -21,6 +21,8 @@ def test_expand_dims_table(port, base, levels, pad, exp):
     assert (tuple(e), tuple(o), lv.value) == (exp, (pad,) * 3, levels)
     shape, off, plv = port.expand_dims(base[::-1])
     assert (shape[::-1], tuple(off), plv) == (exp, (pad,) * 3, levels)
+    shape2, off2, lv2 = api.expand_dims(base[::-1])  # the Python mirror's host-only helper (used by buildExpandedDomainLazy)
+    assert (shape2[::-1], tuple(off2), lv2) == (exp, (pad,) * 3, levels)
 
 
 def test_ghost_fluid_theta_matches_reference_cases():
