@@ -31,7 +31,7 @@ STATUS = {0: "GMG_OK", 1: "GMG_ERR_CUDA", 2: "GMG_ERR_INVALID", 3: "GMG_ERR_NO_A
 
 # every symbol include/gmg_b200.h declares (tests/test_abi.py checks the header against this and the .so)
 ABI_SYMBOLS = [
-    "gmg_last_error", "gmg_version", "gmg_ctx_create", "gmg_ctx_destroy", "gmg_ctx_synchronize", "gmg_ctx_shard", "gmg_nccl_unique_id", "gmg_ctx_rank", "gmg_shard_plan", "gmg_solver_shard_info", "gmg_comm_count",
+    "gmg_last_error", "gmg_version", "gmg_ctx_create", "gmg_ctx_destroy", "gmg_ctx_synchronize", "gmg_ctx_shard", "gmg_nccl_unique_id", "gmg_ctx_rank", "gmg_shard_plan", "gmg_solver_shard_info", "gmg_comm_count", "gmg_comm_benchmark",
     "gmg_expand_dims", "gmg_expand_labels", "gmg_expand_weights", "gmg_set_boundary_labels", "gmg_coarsen_labels", "gmg_boundary_cells",
     "gmg_solver_default_options", "gmg_solver_create", "gmg_solver_destroy", "gmg_solver_levels", "gmg_solver_level_res",
     "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms",
@@ -395,6 +395,12 @@ class GeometricMultigridPoissonSolver:
         sh, lo, hi, act = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
         _check(self.lib.gmg_solver_shard_info(self.h, int(level), C.byref(sh), C.byref(lo), C.byref(hi), C.byref(act)))
         return bool(sh.value), int(lo.value), int(hi.value), int(act.value)
+
+    def comm_benchmark(self, kind: int, level: int = 0, depth: int = 8, reps: int = 100) -> float:
+        """ms per back-to-back communication operation (0 halo exchange, 1 replicated-level gather, 2 scalar all-reduce)."""
+        ms = C.c_double()
+        _check(self.lib.gmg_comm_benchmark(self.h, int(kind), int(level), int(depth), int(reps), C.byref(ms)))
+        return float(ms.value)
 
     def coarse_unknowns(self) -> int:
         n = C.c_int64()

@@ -16,6 +16,7 @@
 
 #include "gmg_kernels.cuh"
 #include "gmg_nccl.h"
+#include "gmg_p2p.cuh"
 
 using namespace gmg;
 
@@ -139,6 +140,9 @@ static cudaError_t launchK(void (*kernel)(KArgs...), unsigned grid, unsigned blo
 
 #define TRACE(msg) do { if (getenv("GMG_TRACE")) { fprintf(stderr, "[gmg] %s:%d %s\n", __func__, __LINE__, msg); fflush(stderr); } } while (0)
 
+static void p2pRelease(gmg_ctx *ctx);
+static double *scalarPtr(gmg_solver *s, size_t offset);
+
 static int invalid(const char *msg)
 {
     setError(msg);
@@ -237,6 +241,7 @@ extern "C" int gmg_ctx_destroy(gmg_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     flushProfile(ctx);
     for (auto e : ctx->eventPool) cudaEventDestroy(e);
+    p2pRelease(ctx);
     if (ctx->nccl)
 	if (const NcclApi *api = ncclApi(nullptr)) api->CommDestroy(static_cast<NcclComm>(ctx->nccl));
     cudaFree(ctx->partials);
@@ -1426,6 +1431,135 @@ static int planShards(gmg_solver *s)
     return GMG_OK;
 }
 
+// ---- peer-memory communication (gmg_p2p.cuh) ------------------------------------------------------------------------
+static void p2pRelease(gmg_ctx *ctx)
+{
+    P2pState *st = static_cast<P2pState *>(ctx->p2p);
+    if (!st) return;
+    for (int r = 0; r < st->world; ++r)
+	if (r != st->rank && st->peer[r]) cudaIpcCloseMemHandle(st->peer[r]);
+    cudaFree(st->arena);
+    cudaFree(st->seq);
+    cudaFree(st->tickets);
+    cudaFree(st->error);
+    delete st;
+    ctx->p2p = nullptr;
+}
+
+// mailboxes for this solver's sharded levels; (re)allocates and re-maps the arenas when they are too small.  Collective.
+static int p2pEnsure(gmg_solver *s)
+{
+    gmg_ctx *ctx = s->ctx;
+    if (ctx->world == 1 || s->shardLevels == 0 || ctx->p2pDisabled) return GMG_OK;
+    if (const char *e = getenv("GMG_P2P")) if (e[0] == '0') { ctx->p2pDisabled = true; return GMG_OK; }
+    if (ctx->world > P2P_MAX_WORLD || s->shardLevels > P2P_MAX_LEVELS) { ctx->p2pDisabled = true; return GMG_OK; }
+    const NcclApi *api = ncclApi(nullptr);
+    NcclComm comm = static_cast<NcclComm>(ctx->nccl);
+    P2pLayout lay;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    lay.flags = take(sizeof(unsigned long long) * P2P_FLAG_COUNT);
+    lay.scalars = take(sizeof(double) * 2 * P2P_MAX_WORLD);
+    for (int l = 0; l < P2P_MAX_LEVELS; ++l)
+	for (int d = 0; d < 2; ++d)
+	    for (int k = 0; k < 2; ++k)
+	    {
+		lay.halo[l][d][k] = 0;
+		if (l < s->shardLevels) lay.halo[l][d][k] = take(sizeof(double) * size_t(l == 0 ? HALO_STORE0 : HALO_STORE) * size_t(s->lv[l].g.plane));
+	    }
+    for (int k = 0; k < 2; ++k) lay.gather[k] = take(sizeof(double) * size_t(s->lv[s->shardLevels].g.total));
+    lay.bytes = off;
+    P2pState *st = static_cast<P2pState *>(ctx->p2p);
+    if (st && st->layout.bytes >= lay.bytes)
+    {
+	const size_t have = st->layout.bytes;
+	st->layout = lay;
+	st->layout.bytes = have;
+	s->p2pGeneration = st->generation;
+	return GMG_OK;
+    }
+    // (re)build: everybody drains, frees, allocates, exchanges IPC handles
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_NCCL(api->AllReduce(ctx->scalars, ctx->scalars, 1, NCCL_FLOAT64, NCCL_SUM, comm, ctx->stream));  // barrier
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    p2pRelease(ctx);
+    st = new P2pState;
+    st->rank = ctx->rank;
+    st->world = ctx->world;
+    st->generation = ++ctx->p2pGenerations;
+    s->p2pGeneration = st->generation;
+    st->layout = lay;
+    st->layout.bytes = std::max<size_t>(lay.bytes + (lay.bytes >> 2), size_t(64) << 20);  // head-room: the next frame's boxes differ by a few planes
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    std::vector<cudaIpcMemHandle_t> all(ctx->world);
+    unsigned char *dh = nullptr;
+    if (cudaMalloc(&st->arena, st->layout.bytes) != cudaSuccess) ok = 0;
+    if (ok) ok = cudaMemset(st->arena, 0, st->layout.bytes) == cudaSuccess;
+    if (ok) ok = cudaMalloc(&st->seq, sizeof(unsigned long long) * (P2P_MAX_LEVELS + 2)) == cudaSuccess && cudaMalloc(&st->tickets, 2 * sizeof(unsigned)) == cudaSuccess &&
+		 cudaMalloc(&st->error, sizeof(int)) == cudaSuccess;
+    if (ok)
+    {
+	cudaMemset(st->seq, 0, sizeof(unsigned long long) * (P2P_MAX_LEVELS + 2));
+	cudaMemset(st->tickets, 0, 2 * sizeof(unsigned));
+	cudaMemset(st->error, 0, sizeof(int));
+	ok = cudaIpcGetMemHandle(&mine, st->arena) == cudaSuccess;
+    }
+    cudaGetLastError();
+    if (!ok) std::memset(&mine, 0, sizeof(mine));
+    GMG_CUDA(cudaMalloc(&dh, sizeof(cudaIpcMemHandle_t) * ctx->world));
+    GMG_CUDA(cudaMemcpy(dh + sizeof(mine) * ctx->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    GMG_NCCL(api->GroupStart());
+    for (int r = 0; r < ctx->world; ++r)
+	GMG_NCCL(api->Broadcast(dh + sizeof(mine) * r, dh + sizeof(mine) * r, sizeof(mine), NCCL_UINT8, r, comm, ctx->stream));
+    GMG_NCCL(api->GroupEnd());
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaMemcpy(all.data(), dh, sizeof(mine) * ctx->world, cudaMemcpyDeviceToHost));
+    cudaFree(dh);
+    st->peer[ctx->rank] = st->arena;
+    for (int r = 0; r < ctx->world && ok; ++r)
+    {
+	if (r == ctx->rank) continue;
+	void *p = nullptr;
+	if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+	st->peer[r] = static_cast<char *>(p);
+    }
+    // all or nothing: one rank that cannot map its peers sends everybody back to NCCL
+    double flag = ok ? 0.0 : 1.0, *dflag = scalarPtr(s, offsetof(Scalars, tmp));
+    GMG_CUDA(cudaMemcpy(dflag, &flag, sizeof(double), cudaMemcpyHostToDevice));
+    GMG_NCCL(api->AllReduce(dflag, dflag, 1, NCCL_FLOAT64, NCCL_SUM, comm, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaMemcpy(&flag, dflag, sizeof(double), cudaMemcpyDeviceToHost));
+    ctx->p2p = st;
+    if (flag != 0.0)
+    {
+	p2pRelease(ctx);
+	ctx->p2pDisabled = true;
+	if (getenv("GMG_TRACE")) fprintf(stderr, "[gmg] peer-memory mapping failed on some rank: NCCL for every exchange\n");
+    }
+    return GMG_OK;
+}
+
+static int p2pCheckError(gmg_ctx *ctx)
+{
+    P2pState *st = static_cast<P2pState *>(ctx->p2p);
+    if (!st) return GMG_OK;
+    int e = 0;
+    GMG_CUDA(cudaMemcpy(&e, st->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e)
+    {
+	setError("peer-memory exchange timed out waiting for a neighbour rank (ranks must make the same calls in the same order)");
+	return GMG_ERR_COMM;
+    }
+    return GMG_OK;
+}
+
+static P2pState *p2pOf(gmg_solver *s)
+{
+    P2pState *st = static_cast<P2pState *>(s->ctx->p2p);
+    return (st && st->generation == s->p2pGeneration) ? st : nullptr;
+}
+
 struct ZRange { int lo, hi; };
 // planes within `depth` of the owned slab (everything on an unsharded level)
 static ZRange clipDepth(const Level &L, int depth)
@@ -1446,6 +1580,37 @@ static int haloExchange(gmg_solver *s, int level, double *p, int depth)
     const int rank = ctx->rank, world = ctx->world;
     ctx->curLevel = level;
     GMG_LAUNCH(ctx, KC_HALO, double(cnt) * 8.0 * ((rank > 0) + (rank < world - 1)) * 2.0);
+    if (P2pState *st = p2pOf(s))
+    {
+	const P2pLayout &lay = st->layout;
+	HaloP2pArgs a;
+	a.grid = p; a.plane = L.g.plane; a.ownLo = L.ownLo; a.ownHi = L.ownHi; a.depth = depth;
+	a.hasLower = rank > 0; a.hasUpper = rank < world - 1;
+	a.slotStride = int64_t((lay.halo[level][0][1] - lay.halo[level][0][0]) / sizeof(double));
+	unsigned long long *myFlags = reinterpret_cast<unsigned long long *>(st->arena + lay.flags);
+	// box / flag index: dir 0 = data that came from the lower neighbour, dir 1 = from the upper neighbour
+	a.fromLower = reinterpret_cast<const double *>(st->arena + lay.halo[level][0][0]);
+	a.fromUpper = reinterpret_cast<const double *>(st->arena + lay.halo[level][1][0]);
+	a.myFlagLower = myFlags + P2P_FLAG_HALO + (level * 2 + 0) * 2;
+	a.myFlagUpper = myFlags + P2P_FLAG_HALO + (level * 2 + 1) * 2;
+	a.toLower = a.toUpper = nullptr; a.flagOnLower = a.flagOnUpper = nullptr;
+	if (a.hasLower)
+	{
+	    a.toLower = reinterpret_cast<double *>(st->peer[rank - 1] + lay.halo[level][1][0]);  // I am its upper neighbour
+	    a.flagOnLower = reinterpret_cast<unsigned long long *>(st->peer[rank - 1] + lay.flags) + P2P_FLAG_HALO + (level * 2 + 1) * 2;
+	}
+	if (a.hasUpper)
+	{
+	    a.toUpper = reinterpret_cast<double *>(st->peer[rank + 1] + lay.halo[level][0][0]);  // I am its lower neighbour
+	    a.flagOnUpper = reinterpret_cast<unsigned long long *>(st->peer[rank + 1] + lay.flags) + P2P_FLAG_HALO + (level * 2 + 0) * 2;
+	}
+	a.seq = st->seq + level; a.tickets = st->tickets; a.error = st->error;
+	// small messages: fewer CTAs meet at the tickets and poll the flags (one CTA per 64 KB, at least 8)
+	const unsigned ctas = unsigned(std::max<size_t>(8, std::min<size_t>(P2P_CTAS, cnt * sizeof(double) / 65536)));
+	k_halo_p2p<<<ctas, 256, 0, ctx->stream>>>(a);
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     GMG_NCCL(api->GroupStart());
     if (rank > 0)
     {
@@ -1471,6 +1636,26 @@ static int gatherReplicated(gmg_solver *s, double *p)
     NcclComm comm = static_cast<NcclComm>(ctx->nccl);
     ctx->curLevel = s->shardLevels;
     GMG_LAUNCH(ctx, KC_HALO, double(C.g.total) * 8.0);
+    if (P2pState *st = p2pOf(s))
+    {
+	const P2pLayout &lay = st->layout;
+	GatherP2pArgs a;
+	a.grid = p; a.plane = C.g.plane; a.rank = ctx->rank; a.world = ctx->world;
+	for (int k = 0; k < ctx->world; ++k)
+	{
+	    a.lo[k] = s->gatherLo[k]; a.hi[k] = s->gatherHi[k];
+	    a.peerBox[k] = reinterpret_cast<double *>(st->peer[k] + lay.gather[0]);
+	    a.flagOnPeer[k] = reinterpret_cast<unsigned long long *>(st->peer[k] + lay.flags) + P2P_FLAG_GATHER;
+	}
+	a.slotStride = int64_t((lay.gather[1] - lay.gather[0]) / sizeof(double));
+	a.myBox = reinterpret_cast<const double *>(st->arena + lay.gather[0]);
+	a.myFlags = reinterpret_cast<const unsigned long long *>(st->arena + lay.flags) + P2P_FLAG_GATHER;
+	a.seq = st->seq + P2P_MAX_LEVELS; a.tickets = st->tickets; a.error = st->error;
+	const unsigned ctas = unsigned(std::max<size_t>(8, std::min<size_t>(P2P_CTAS, size_t(C.g.total) * sizeof(double) / 65536)));
+	k_gather_p2p<<<ctas, 256, 0, ctx->stream>>>(a);
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     GMG_NCCL(api->GroupStart());
     for (int k = 0; k < ctx->world; ++k)
     {
@@ -1491,12 +1676,28 @@ static int allreduceScalar(gmg_solver *s, double *dev, int op = NCCL_SUM)
     const NcclApi *api = ncclApi(nullptr);
     ctx->curLevel = 0;
     GMG_LAUNCH(ctx, KC_HALO, 8.0);
+    if (P2pState *st = p2pOf(s))
+    {
+	const P2pLayout &lay = st->layout;
+	ScalarP2pArgs a;
+	a.value = dev; a.rank = ctx->rank; a.world = ctx->world; a.isMax = (op == NCCL_MAX);
+	for (int k = 0; k < ctx->world; ++k)
+	{
+	    a.peerSlots[k] = reinterpret_cast<double *>(st->peer[k] + lay.scalars);
+	    a.flagOnPeer[k] = reinterpret_cast<unsigned long long *>(st->peer[k] + lay.flags) + P2P_FLAG_SCALAR;
+	}
+	a.mySlots = reinterpret_cast<const double *>(st->arena + lay.scalars);
+	a.myFlags = reinterpret_cast<const unsigned long long *>(st->arena + lay.flags) + P2P_FLAG_SCALAR;
+	a.seq = st->seq + P2P_MAX_LEVELS + 1; a.error = st->error;
+	k_scalar_p2p<<<1, 32, 0, ctx->stream>>>(a);
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     GMG_NCCL(api->AllReduce(dev, dev, 1, NCCL_FLOAT64, op, static_cast<NcclComm>(ctx->nccl), ctx->stream));
     return GMG_OK;
 }
 
 static int buildFusedCycle(gmg_solver *s);
-static double *scalarPtr(gmg_solver *s, size_t offset);
 
 extern "C" int gmg_solver_destroy(gmg_solver *s)
 {
@@ -1638,6 +1839,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     if (!s->opt.operators_only && (st = buildCoarseSolve(s)) != GMG_OK) return fail(st);
     if ((st = buildFusedCycle(s)) != GMG_OK) return fail(st);
     lap("coarse direct solver");
+    if ((st = p2pEnsure(s)) != GMG_OK) return fail(st);
     if (s->shardLevels > 0)
     {
 	// run every communication pattern once now: NCCL sets up its peer connections on first use, which must not
@@ -1728,6 +1930,8 @@ static StencilArgs stencilArgs(gmg_solver *s, int level, const double *in, const
     a.nz = L.g.n[2];
     a.zlo = 0;
     a.zhi = L.g.n[2];
+    a.dotLo = L.ownLo;
+    a.dotHi = L.ownHi;
     a.nBoundary = L.nBoundary;
     a.bandIdx = L.bandIdx;
     a.bcoef = L.bcoef;
@@ -2085,7 +2289,8 @@ static int buildFusedCycle(gmg_solver *s)
     s->compactArgs = c;
     s->compactBlob = d;
     s->compactSmem = smem;
-    GMG_CUDA(cudaFuncSetAttribute(k_compact_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->compactSmem)));
+    // the attribute is per function, not per solver: always the device maximum, so solvers of different sizes can coexist
+    GMG_CUDA(cudaFuncSetAttribute(k_compact_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
     s->fusedFirst = first;
     return GMG_OK;
 }
@@ -2116,6 +2321,8 @@ static int launchVec(gmg_solver *s, int level, double *y, const double *a, const
     v.nz = L.g.n[2];
     v.zlo = std::max(0, zr.lo);
     v.zhi = std::min(L.g.n[2], zr.hi);
+    v.redLo = L.ownLo;
+    v.redHi = L.ownHi;
     v.y = y;
     v.a = a;
     v.c = c;
@@ -2357,19 +2564,12 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
     // graph {V-cycle, z.r, direction, apply (+p.Ap), update (+|r|^2)} and one scalar read-back for the test.
     auto applyUpdate = [&]() -> int {
 	GMG_TRY(haloExchange(s, 0, p, HALO_P));
-	if (!L0.sharded) GMG_TRY(launchStencil(s, 0, SM_APPLY, p, nullptr, t, scalarPtr(s, offsetof(Scalars, pAp)), own));
-	else
-	{
-	    // the fused dot would also sum the halo planes: apply over the deep range, then p.t over the owned planes
-	    GMG_TRY(launchStencil(s, 0, SM_APPLY, p, nullptr, t, nullptr, deep));
-	    GMG_TRY((reduceOwned<VO_DOT>(s, p, t, offsetof(Scalars, pAp), 16.0)));
-	}
-	if (!L0.sharded) GMG_TRY((launchVec<VO_CG_UPDATE>(s, 0, x, p, t, r, 0, scalarPtr(s, offsetof(Scalars, rr)), KC_BLAS1, 48.0)));
-	else
-	{
-	    GMG_TRY((launchVec<VO_CG_UPDATE>(s, 0, x, p, t, r, 0, nullptr, KC_BLAS1, 48.0, deep)));
-	    GMG_TRY((reduceOwned<VO_NORM2>(s, r, nullptr, offsetof(Scalars, rr), 8.0)));
-	}
+	// sharded: t = A p and the update run over the deep halo range (r stays valid 8 planes deep), their fused reductions
+	// only sum the rank's owned planes and are then summed over the ranks
+	GMG_TRY(launchStencil(s, 0, SM_APPLY, p, nullptr, t, scalarPtr(s, offsetof(Scalars, pAp)), deep));
+	if (L0.sharded) GMG_TRY(allreduceScalar(s, scalarPtr(s, offsetof(Scalars, pAp))));
+	GMG_TRY((launchVec<VO_CG_UPDATE>(s, 0, x, p, t, r, 0, scalarPtr(s, offsetof(Scalars, rr)), KC_BLAS1, 48.0, deep)));
+	if (L0.sharded) GMG_TRY(allreduceScalar(s, scalarPtr(s, offsetof(Scalars, rr))));
 	return GMG_OK;
     };
     auto iterationBody = [&]() -> int {
@@ -2396,7 +2596,7 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     if (iterations) *iterations = iteration;
-    return GMG_OK;
+    return p2pCheckError(ctx);
 }
 
 // ====================================================================================================
@@ -2602,6 +2802,33 @@ extern "C" int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, dou
     GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY(refreshForSolve(s, x->d, b->d, true));
     return pcgDevice(s, x->d, b->d, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount);
+}
+
+// communication micro-benchmark: `reps` back-to-back operations of one kind on a sharded solver (no compute in between,
+// so no load skew): kind 0 = halo exchange of `depth` planes at `level`, 1 = gather of the first replicated level,
+// 2 = scalar all-reduce.  Collective.  msPerOp: device time per operation on this rank.
+extern "C" int gmg_comm_benchmark(gmg_solver *s, int kind, int level, int depth, int reps, double *msPerOp)
+{
+    if (!s || !msPerOp || reps < 1) return invalid("gmg_comm_benchmark: bad argument");
+    if (s->shardLevels == 0) return invalid("gmg_comm_benchmark: the solver is not sharded");
+    if (kind == 0 && (level < 0 || level >= s->shardLevels || depth < 1 || depth > HALO_STORE)) return invalid("gmg_comm_benchmark: bad level / depth");
+    gmg_ctx *ctx = s->ctx;
+    GMG_CUDA(enterCtx(ctx));
+    auto once = [&]() -> int {
+	if (kind == 0) return haloExchange(s, level, s->lv[level].r, depth);
+	if (kind == 1) return gatherReplicated(s, s->lv[s->shardLevels].b);
+	return allreduceScalar(s, scalarPtr(s, offsetof(Scalars, tmp)));
+    };
+    for (int i = 0; i < 3; ++i) GMG_TRY(once());
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaEventRecord(ctx->t0, ctx->stream));
+    for (int i = 0; i < reps; ++i) GMG_TRY(once());
+    GMG_CUDA(cudaEventRecord(ctx->t1, ctx->stream));
+    GMG_CUDA(cudaEventSynchronize(ctx->t1));
+    float ms = 0;
+    GMG_CUDA(cudaEventElapsedTime(&ms, ctx->t0, ctx->t1));
+    *msPerOp = double(ms) / reps;
+    return p2pCheckError(ctx);
 }
 
 static int ensureHostIO(gmg_solver *s)

@@ -131,7 +131,10 @@ struct gmg_ctx
     // sharding (z-slabs); world == 1 means single GPU
     int rank = 0, world = 1;
     void *nccl = nullptr;         // ncclComm_t
-    int64_t commOps = 0;          // NCCL operations (groups) enqueued since the last launch-count reset
+    int64_t commOps = 0;          // communication operations enqueued since the last launch-count reset
+    void *p2p = nullptr;          // gmg::P2pState: peer-memory mailboxes (gmg_p2p.cuh); null = NCCL for every exchange
+    bool p2pDisabled = false;
+    int p2pGenerations = 0;
     // reduction scratch
     double *partials = nullptr;   // [maxPartials]
     unsigned *ticket = nullptr;
@@ -157,6 +160,7 @@ struct gmg_solver
     double *coarseInv = nullptr;  // [nCoarse][nCoarse] row-major inverse
     // z-slab sharding: levels [0, shardLevels) are slabs, the rest replicated on every rank
     int shardLevels = 0;
+    int p2pGeneration = -1;       // generation of the context's peer-memory arenas this solver was built against
     std::vector<int> gatherLo, gatherHi; // per rank: planes of the first replicated level it restricts into
     // compact coarse sub-V-cycle: levels [fusedFirst, levels-1] in one shared-memory CTA (-1 = off)
     int fusedFirst = -1;

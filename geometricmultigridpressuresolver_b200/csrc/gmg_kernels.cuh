@@ -130,6 +130,7 @@ struct StencilArgs
     int64_t plane;
     int nz;
     int zlo, zhi;       // z-plane clip [zlo, zhi): planes outside are left untouched (deep-halo sharding)
+    int dotLo, dotHi;   // planes whose cells enter the fused dot product (the rank's owned planes)
     // boundary records
     int nBoundary;
     const int32_t *bandIdx;
@@ -191,7 +192,7 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
 		else if (a0) a.out[i] = o0;
 		else a.out[i + 1] = o1;
-		if (DOT) acc += (a0 ? c2.x * lap0 : 0.0) + (a1 ? c2.y * lap1 : 0.0);
+		if (DOT && z >= a.dotLo && z < a.dotHi) acc += (a0 ? c2.x * lap0 : 0.0) + (a1 ? c2.y * lap1 : 0.0);
 	    }
 	}
     }
@@ -215,7 +216,7 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 	    lap += diag * centre;
 	    const double rhs = (MODE != SM_APPLY) ? a.b[i] : 0.0;
 	    a.out[i] = stencilFinish<MODE>(lap, centre, rhs, diag);
-	    if (DOT) acc += centre * lap;
+	    if (DOT && z >= a.dotLo && z < a.dotHi) acc += centre * lap;
 	}
     }
     return acc;
@@ -488,6 +489,7 @@ struct VecArgs
     int64_t plane;
     int nz;
     int zlo, zhi;       // z-plane clip [zlo, zhi)
+    int redLo, redHi;   // planes that enter a fused reduction (the rank's owned planes)
     double *y;          // destination / first operand
     const double *a;    // second operand
     const double *c;    // third operand
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(BLOCK) k_vec(const VecArgs v)
 		r.x = r.x + (-s) * t.x; r.y = r.y + (-s) * t.y;
 		st2(v.y + i, x);
 		st2(v.y2 + i, r);
-		acc += r.x * r.x; acc += r.y * r.y;
+		if (z >= v.redLo && z < v.redHi) { acc += r.x * r.x; acc += r.y * r.y; }
 	    }
 	    else if (OP == VO_CG_DIRECTION)
 	    {

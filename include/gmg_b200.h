@@ -183,7 +183,10 @@ int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, double tol, in
 /* ---- measurement hooks ----------------------------------------------------------------------------- */
 /* kernels launched by this library on this context since the last reset (bench.py's gpu_launches) */
 int gmg_launch_count(gmg_ctx *ctx, int64_t *count, int reset);
-/* NCCL operations (halo exchanges, gathers, scalar all-reduces) enqueued since the last gmg_launch_count reset */
+/* communication micro-benchmark on a sharded solver (collective): `reps` back-to-back operations with no compute between them.
+ * kind 0 = halo exchange of `depth` planes at `level`, 1 = gather of the first replicated level, 2 = scalar all-reduce. */
+int gmg_comm_benchmark(gmg_solver *s, int kind, int level, int depth, int reps, double *msPerOp);
+/* communication operations (halo exchanges, gathers, scalar all-reduces) enqueued since the last gmg_launch_count reset */
 int gmg_comm_count(gmg_ctx *ctx, int64_t *count);
 /* CUDA-event timing on the context's stream: begin/end bracket, result in ms */
 int gmg_timer_begin(gmg_ctx *ctx);
