@@ -7,7 +7,7 @@ A step is one complete multigrid-preconditioned CG solve of the 256^3 flipSplash
 (BASELINE.json configs[2]; expanded 512^3, 7 levels, seeded random rhs, zero initial guess, tol 1e-6).
   value      solve ms with labels/weights/rhs already resident in HBM (gmg_pcg_device), CUDA events on the library's stream
   e2e        the same solve through the reference-facing entry points with HOST buffers:
-             gmg_solver_create (labels + 3 weight grids H2D, hierarchy build) + gmg_pcg (rhs/x0 H2D from pinned memory,
+             gmg_solver_create (labels + BOUNDARY-cell face weights H2D, hierarchy build) + gmg_pcg (rhs/x0 H2D from pinned memory,
              pressure D2H) + gmg_solver_destroy -- wall clock around the blocking calls
   roofline   the dominant fine-level kernel class: algorithmic bytes per launch / CUDA-event duration per launch,
              against MEASURED_PEAKS.json's HBM copy bandwidth
@@ -296,8 +296,11 @@ def run_gpu_arm(args, rank, world, local_rank):
                 e2e_ms.append((t2 - t0) * 1e3)
                 e2e_setup.append((t1 - t0) * 1e3)
         box_cells = int(np.prod([hi[a] - int(off[a]) + 4 for a in range(3)]))
-        h2d = box_cells * (4 + 3 * 8) + 2 * box_cells * 8  # labels + 3 weight grids at construction, rhs + x0 per solve
-        d2h = box_cells * 8
+        # construction: int32 labels of the box + the six face weights of every BOUNDARY cell (the weight grids themselves stay on the
+        # host: only BOUNDARY cells look at them; their index list comes back first); per solve: rhs + x0 in, pressure out
+        n_boundary = int((labels == 3).sum())
+        h2d = box_cells * 4 + n_boundary * 48 + 2 * box_cells * 8
+        d2h = box_cells * 8 + n_boundary * 4
         e2e_val = float(np.mean(e2e_ms))
         if dist is not None:
             t = torch.tensor([e2e_val], device="cuda", dtype=torch.float64)
@@ -306,14 +309,14 @@ def run_gpu_arm(args, rank, world, local_rank):
             sh, zlo, zhi, _ = solver.shard_info(0)
             if sh:  # per rank: its slab of the weights / rhs / x0 (+ the replicated one-byte labels); summed over the ranks below
                 frac = (zhi - zlo + 20) / float(hi[2] - int(off[2]) + 4)
-                h2d = int(box_cells * 4 + box_cells * frac * (3 * 8 + 2 * 8))
+                h2d = int(box_cells * 4 + n_boundary * frac * 48 + box_cells * frac * 2 * 8)
                 d2h = int(box_cells * 8 * (zhi - zlo) / float(hi[2] - int(off[2]) + 4))
             t = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64)
             dist.all_reduce(t)
             h2d, d2h = int(t[0].item()), int(t[1].item())
         e2e = {"value": e2e_val, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "setup_ms": float(np.mean(e2e_setup)), "iterations": int(it2),
-               "what": "gmg_solver_create (labels + 3 weight grids H2D, hierarchy build) + gmg_pcg (rhs/x0 H2D, pressure D2H) + gmg_solver_destroy; all host buffers page-locked"}
+               "what": "gmg_solver_create (labels + BOUNDARY-cell face weights H2D, hierarchy build) + gmg_pcg (rhs/x0 H2D, pressure D2H) + gmg_solver_destroy; all host buffers page-locked"}
         for a in [x_np, b_np, labels] + list(w):
             rt.cudaHostUnregister(a.ctypes.data)
 

@@ -280,3 +280,24 @@ def test_lazy_expanded_domain_matches_the_full_one(gpu_ctx):
     assert it1 == it2 and np.array_equal(h1, h2) and np.array_equal(x1, x2)
     s1.close()
     s2.close()
+
+
+@pytest.mark.parametrize("dom,n,kw", [("complex", 32, {}), ("flipsplash", 48, {"shape": (48, 32, 48)}), ("narrow_band", 48, {})])
+def test_band_smoother_any_sweep_count_matches_oracle(gpu_ctx, port, dom, n, kw):
+    """The temporally blocked band kernel runs groups of up to three sweeps per launch on shrinking shared-memory boxes;
+    every sweep count must give what that many separate boundaryJacobiPoissonSmoother calls give (Ops.h:524-619)."""
+    bl, bw, dx = D.DOMAINS[dom](n, **kw)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    for level in range(min(2, s.getMGLevels())):
+        ll = s.level_labels(level)
+        cells = s.level_boundary_cells(level)
+        lw = w if level == 0 else None
+        xs, bs = D.random_active(ll, 31 + level), D.random_active(ll, 41 + level)
+        X, B = s.grid(level, xs), s.grid(level, bs)
+        for sweeps in (1, 2, 3, 4, 5, 7):
+            X.upload(xs)
+            s.boundaryJacobiPoissonSmoother(X, B, sweeps)
+            want = port.boundary_jacobi(xs.copy(), bs, ll, cells, sweeps, lw)
+            assert relerr(X.download(), want) < TOL_OP, (level, sweeps)
+    s.close()
