@@ -765,15 +765,25 @@ static int selectFlagged(gmg_ctx *ctx, const uint8_t *flags, int64_t n, int32_t 
 }
 
 // boundary band of one level: BOUNDARY cells first, then the INTERIOR cells within width-1 steps (Ops.cpp:165-469)
-static bool useBricks()
+// GMG_BAND = grid (default: sweeps on the grids, k_band_grid) | list (compact lists with neighbour references, k_band) |
+// brick (temporally blocked brick lists, k_band_brick)
+enum BandMode { BAND_NONE = -1, BAND_GRID = 0, BAND_LIST = 1, BAND_BRICK = 2 };
+static int bandModeEnv()
 {
-    static const bool v = [] { const char *e = getenv("GMG_BAND_BRICKS"); return e && e[0] == '1'; }();
+    static const int v = [] {
+	const char *e = getenv("GMG_BAND");
+	if (e && !strcmp(e, "list")) return int(BAND_LIST);
+	if (e && !strcmp(e, "brick")) return int(BAND_BRICK);
+	return int(BAND_GRID);
+    }();
     return v;
 }
+static bool useBricks() { return bandModeEnv() == BAND_BRICK; }
 
-// legacy: also build the per-cell neighbour references of the sweep-per-launch band kernel (k_band)
-static int buildBand(gmg_ctx *ctx, Level &L, int width, bool legacy, int bricksH = 0)
+// mode: which smoother structures to build besides the cell list itself
+static int buildBand(gmg_ctx *ctx, Level &L, int width, int mode, int bricksH = 0)
 {
+    const bool legacy = mode == BAND_LIST;
     // the band mask is grown over the level's GLOBAL box (a slab edge must not clip the dilation); the lists are
     // compacted over the rank's stored planes and hold local storage indices
     const Geom &g = L.g;
@@ -798,7 +808,7 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width, bool legacy, int bricksH
     const uint8_t *mLocal = m0 + int64_t(L.zOff) * g.plane;
     // code bytes for the brick lists of the temporally blocked band smoother (built by buildBricks once bpos exists)
     if (L.bandCode) { GMG_CUDA(devFree(L.bandCode)); L.bandCode = nullptr; }
-    if (!legacy && bricksH > 0)
+    if (mode == BAND_BRICK && bricksH > 0)
     {
 	GMG_CUDA(devMalloc(&L.bandCode, g.total));
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
@@ -816,7 +826,6 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width, bool legacy, int bricksH
 	k_band_flags<<<grid, BLOCK, 0, ctx->stream>>>(m1, mLocal, L.labels, 1, g.total);
     }
     GMG_TRY(selectFlagged(ctx, m1, g.total, &idxI, &nI));
-    GMG_CUDA(devFree(m0));
     GMG_CUDA(devFree(m1));
     L.nBoundary = nB;
     L.nBand = nB + nI;
@@ -827,6 +836,17 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width, bool legacy, int bricksH
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_CUDA(devFree(idxB));
     GMG_CUDA(devFree(idxI));
+    if (mode == BAND_GRID)
+    {
+	GMG_CUDA(devMalloc(&L.bandMask, std::max(nBand, 1)));
+	GMG_CUDA(devMalloc(&L.bandB, sizeof(double) * std::max(nBand, 1)));
+	if (nBand > 0)
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_band_mask<<<unsigned(divUp(nBand, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bandMask, L.bandIdx, mLocal, nBand, g.pitch, g.plane);
+	}
+    }
+    GMG_CUDA(devFree(m0));
     if (!legacy) return GMG_OK;
     GMG_CUDA(devMalloc(&L.bandRef, sizeof(int32_t) * 6 * std::max(nBand, 1)));
     GMG_CUDA(devMalloc(&L.bandV0, sizeof(double) * std::max(nBand, 1)));
@@ -1161,7 +1181,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 static void freeLevel(Level &L)
 {
     devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandIdx); devFree(L.bandRef); devFree(L.bcoef);
-    devFree(L.bandV0); devFree(L.bandV1); devFree(L.bandB); devFree(L.bandCode); devFree(L.brickMeta); devFree(L.brickGidx); devFree(L.brickCells);
+    devFree(L.bandV0); devFree(L.bandV1); devFree(L.bandB); devFree(L.bandMask); devFree(L.bandCode); devFree(L.brickMeta); devFree(L.brickGidx); devFree(L.brickCells);
     devFree(L.chunksInterior); devFree(L.chunksActive);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
@@ -1399,7 +1419,7 @@ extern "C" int gmg_boundary_cells(gmg_ctx *ctx, const int32_t *labels, const int
     GMG_TRY(uploadLabels(ctx, L.labels, labels, res, L.g));
     L.gg = L.g;
     L.ownHi = L.g.n[2];
-    GMG_TRY(buildBand(ctx, L, width, false));
+    GMG_TRY(buildBand(ctx, L, width, BAND_NONE));
     int st = exportBand(ctx, L, xyz, count);
     freeLevel(L);
     return st;
@@ -1943,7 +1963,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     else gmg_solver_default_options(&s->opt);
     if (const char *e = getenv("GMG_NO_GRAPHS")) s->useGraphs = !(e[0] == '1');
     if (const char *e = getenv("GMG_PRINT_STATS")) s->opt.print_stats = (e[0] == '1');
-    s->legacyBand = !useBricks();
+    s->bandMode = bandModeEnv();
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel && ctx->world > 1)
@@ -2028,14 +2048,14 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     {
 	Level &L = s->lv[level];
 	const int brickSweeps = s->opt.boundary_iterations >= 1 ? s->opt.boundary_iterations : BRICK_HMAX;
-	if ((st = buildBand(ctx, L, s->opt.boundary_width, s->legacyBand, brickSweeps)) != GMG_OK) return fail(st);
+	if ((st = buildBand(ctx, L, s->opt.boundary_width, s->bandMode, brickSweeps)) != GMG_OK) return fail(st);
 	const int64_t wOff = L.g.plane;
 	const bool fw = level == 0 && dW[0];
 	if (level == 0 && w0 && !fullWeights) st = buildCoefsSparse(ctx, L, w0, w1, w2, res, s->hostBounds);
 	else st = buildCoefs(ctx, L, fw ? dW[0] + wOff : nullptr, fw ? dW[1] + wOff : nullptr, fw ? dW[2] + wOff : nullptr);
 	if (st != GMG_OK) return fail(st);
 	if (level == 0) lap("level 0 band + coefficient records");
-	if (!s->legacyBand && (st = buildBricks(ctx, L, brickSweeps)) != GMG_OK) return fail(st);
+	if (s->bandMode == BAND_BRICK && (st = buildBricks(ctx, L, brickSweeps)) != GMG_OK) return fail(st);
 	if (s->opt.print_stats)
 	    printf("      level %d: %lld active, band %d (%d BOUNDARY), %d bricks: %lld listed, %lld updated, max %d / %d per brick\n", level,
 		   (long long)L.nActive, L.nBand, L.nBoundary, L.nBricks, (long long)L.brickListed, (long long)L.brickUpdated, L.brickMaxLocal, L.brickMaxComp);
@@ -2251,13 +2271,64 @@ static int launchBandBricks(gmg_solver *s, int level, double *x, const double *b
     return GMG_OK;
 }
 
-// `sweeps` boundary-band Jacobi sweeps on grid x (Ops.h:524-619); zeroGrid: x is known to be all zero
-static int launchBand(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid)
+// Band sweeps on the grids (k_band_grid).  scratch: a grid of the level whose contents are dead (the smoother's alternate
+// buffer); the level's residual grid is the second scratch.  Sweep j reads the band cells where sweep j-1 put them and
+// writes the other scratch; the last sweep writes x.
+static int launchBandGrid(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid, double *scratch)
+{
+    const Level &L = s->lv[level];
+    double *y = scratch ? scratch : L.xAlt, *z = L.r;
+    if (x == y || x == z || y == z) return invalid("band sweeps: the grid aliases a scratch grid of its level");
+    BandGridArgs a;
+    a.x = x;
+    a.b = b;
+    a.bandIdx = L.bandIdx;
+    a.bandMask = L.bandMask;
+    a.bcoef = L.bcoef;
+    a.bandB = L.bandB;
+    a.nBoundary = L.nBoundary;
+    a.nBand = L.nBand;
+    a.pitch = L.g.pitch;
+    a.plane = L.g.plane;
+    const unsigned grid = unsigned(divUp(L.nBand, BLOCK * BAND_PER_THREAD));
+    cudaStream_t st = s->ctx->stream;
+    const double bytes = double(L.nBand) * 29.0;
+    const bool hw = L.hasWeights;
+    const double *src = x;
+    for (int sw = 1; sw <= sweeps; ++sw)
+    {
+	double *dst = (sw == sweeps && sweeps > 1) ? x : (src == y ? z : y);
+	a.s = src;
+	a.d = dst;
+	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
+	if (sw == 1)
+	{
+	    if (zeroGrid) GMG_CUDA(launchK((k_band_grid<true, true, false>), grid, BLOCK, 0, st, a));
+	    else if (hw) GMG_CUDA(launchK((k_band_grid<true, false, true>), grid, BLOCK, 0, st, a));
+	    else GMG_CUDA(launchK((k_band_grid<true, false, false>), grid, BLOCK, 0, st, a));
+	}
+	else if (hw) GMG_CUDA(launchK((k_band_grid<false, false, true>), grid, BLOCK, 0, st, a));
+	else GMG_CUDA(launchK((k_band_grid<false, false, false>), grid, BLOCK, 0, st, a));
+	src = dst;
+    }
+    if (sweeps == 1)
+    {
+	GMG_LAUNCH(s->ctx, KC_BAND, double(L.nBand) * 20.0);
+	GMG_CUDA(launchK(k_band_copy, unsigned(divUp(L.nBand, BLOCK)), BLOCK, 0, st, x, src, L.bandIdx, L.nBand));
+    }
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+// `sweeps` boundary-band Jacobi sweeps on grid x (Ops.h:524-619); zeroGrid: x is known to be all zero;
+// scratch: a dead grid of the level for the grid-based sweeps (null = the level's alternate solution grid)
+static int launchBand(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid, double *scratch = nullptr)
 {
     s->ctx->curLevel = level;
     const Level &L = s->lv[level];
     if (L.nBand == 0 || sweeps <= 0) return GMG_OK;
-    if (!s->legacyBand) return launchBandBricks(s, level, x, b, sweeps, zeroGrid);
+    if (s->bandMode == BAND_BRICK) return launchBandBricks(s, level, x, b, sweeps, zeroGrid);
+    if (s->bandMode == BAND_GRID) return launchBandGrid(s, level, x, b, sweeps, zeroGrid, scratch);
     BandArgs a;
     a.x = x;
     a.b = b;
@@ -2654,7 +2725,7 @@ static int launchGaussSeidel(gmg_solver *s, int level, double *x, const double *
 static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, const double *b, bool zeroGrid, int jacobiDepth, bool down)
 {
     const int it = s->opt.boundary_iterations;
-    GMG_TRY(launchBand(s, level, cur, b, it, zeroGrid));
+    GMG_TRY(launchBand(s, level, cur, b, it, zeroGrid, alt));
     if (s->opt.use_gauss_seidel)
     {
 	GMG_TRY(launchGaussSeidel(s, level, cur, b, down, down));
@@ -2665,7 +2736,7 @@ static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, con
 	GMG_TRY(launchStencil(s, level, SM_JACOBI, cur, b, alt, nullptr, clipDepth(s->lv[level], jacobiDepth)));
 	std::swap(cur, alt);
     }
-    GMG_TRY(launchBand(s, level, cur, b, it, false));
+    GMG_TRY(launchBand(s, level, cur, b, it, false, alt));
     return GMG_OK;
 }
 

@@ -86,6 +86,7 @@ struct Level
     bool hasWeights = false;     // level 0 built with face weights: BOUNDARY cells carry fractional coefficients
     double *bcoef = nullptr;     // [7][nBoundary]: coefficient on each of the 6 neighbours, then the diagonal
     double *bandV0 = nullptr, *bandV1 = nullptr, *bandB = nullptr;
+    uint8_t *bandMask = nullptr; // [nBand] which neighbours of a band cell are band cells (gmg_kernels.cuh: BandGridArgs::bandMask)
     // temporally blocked band smoother (gmg_kernels.cuh: k_band_brick): per brick with a band cell, the local cell list
     uint8_t *bandCode = nullptr; // setup only: one code byte per cell
     void *brickMeta = nullptr;   // BrickMeta[nBricks]
@@ -167,7 +168,7 @@ struct gmg_solver
     double *coarseInv = nullptr;  // [nCoarse][nCoarse] row-major inverse
     // z-slab sharding: levels [0, shardLevels) are slabs, the rest replicated on every rank
     int shardLevels = 0;
-    bool legacyBand = false;      // sweep-per-launch band kernels on compact lists (GMG_BAND_BRICKS=0) instead of k_band_brick
+    int bandMode = 0;             // 0 = sweeps on the grids (k_band_grid), 1 = compact lists with neighbour references (k_band), 2 = brick lists (k_band_brick)
     int p2pGeneration = -1;       // generation of the context's peer-memory arenas this solver was built against
     std::vector<int> gatherLo, gatherHi; // per rank: planes of the first replicated level it restricts into
     // compact coarse sub-V-cycle: levels [fusedFirst, levels-1] in one shared-memory CTA (-1 = off)

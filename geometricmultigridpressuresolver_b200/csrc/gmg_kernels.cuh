@@ -321,6 +321,107 @@ __global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
     bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W>(a, blockIdx.x, threadIdx.x);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Band sweep on the GRIDS (default).  The band values stay in grid layout, so a neighbour is one fixed stride away and a
+// sweep is ONE dependent step (index -> seven values) instead of two (index -> reference -> value), and there are no
+// 24-byte reference records to read.  Sweep j of a group reads band neighbours from `s` (where sweep j-1 wrote them: the
+// grid itself for the first sweep), frozen non-band neighbours from the grid `x`, and writes the band cells of `d`; one
+// mask byte per band cell says which of its six neighbours are band cells.  The last sweep writes `x` itself, which is
+// race-free because that sweep reads x at non-band cells only.  s/d alternate between two scratch grids of the level.
+// ------------------------------------------------------------------------------------------------
+struct BandGridArgs
+{
+    const double *x;     // frozen (non-band) neighbours
+    const double *s;     // band cells after the previous sweep
+    double *d;           // receives the band cells
+    const double *b;
+    const int32_t *bandIdx;
+    const uint8_t *bandMask;  // bit n: neighbour n (-x,+x,-y,+y,-z,+z) is a band cell
+    const double *bcoef;
+    double *bandB;       // compact rhs of the band cells (written by the FIRST sweep of a group)
+    int nBoundary, nBand;
+    int pitch;
+    int64_t plane;
+};
+
+template <bool FIRST, bool ZERO, bool HAS_W>
+__device__ __forceinline__ void bandGridBody(const BandGridArgs &a, int vb, int tid)
+{
+    double v[BAND_PER_THREAD];
+    int64_t gi[BAND_PER_THREAD];
+#pragma unroll
+    for (int c = 0; c < BAND_PER_THREAD; ++c)
+    {
+	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
+	v[c] = 0.0;
+	gi[c] = 0;
+	if (k >= a.nBand) continue;
+	const int64_t i = a.bandIdx[k];
+	gi[c] = i;
+	double rhs;
+	if (FIRST) { rhs = a.b[i]; a.bandB[k] = rhs; }
+	else rhs = a.bandB[k];
+	const double diag = k < a.nBoundary ? a.bcoef[int64_t(6) * a.nBoundary + k] : 6.0;
+	double centre = 0.0, lap = 0.0;
+	if (!ZERO)
+	{
+	    const int m = a.bandMask[k];
+	    const bool weighted = HAS_W && k < a.nBoundary;
+	    centre = a.s[i];
+	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
+	    double u[6];
+#pragma unroll
+	    for (int n = 0; n < 6; ++n) u[n] = ((m >> n) & 1) ? a.s[i + stride[n]] : a.x[i + stride[n]];
+#pragma unroll
+	    for (int n = 0; n < 6; ++n)
+	    {
+		if (weighted)
+		{
+		    const double cn = a.bcoef[int64_t(n) * a.nBoundary + k];
+		    if (cn != 0.0) lap -= cn * u[n];
+		}
+		else lap -= u[n];  // an inactive neighbour holds exactly 0 (vector-grid invariant), and v - 0 == v
+	    }
+	    lap += diag * centre;
+	}
+	double r = rhs - lap;
+	r /= diag;
+	v[c] = centre + (2.0 / 3.0) * r;
+    }
+#pragma unroll
+    for (int c = 0; c < BAND_PER_THREAD; ++c)
+    {
+	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
+	if (k < a.nBand) a.d[gi[c]] = v[c];
+    }
+}
+template <bool FIRST, bool ZERO, bool HAS_W>
+__global__ void __launch_bounds__(BLOCK) k_band_grid(const BandGridArgs a)
+{
+    pdlEnter();
+    bandGridBody<FIRST, ZERO, HAS_W>(a, blockIdx.x, threadIdx.x);
+}
+
+// x[band] = v[band] between two grids (a group of ONE sweep cannot write the grid it reads)
+__global__ void __launch_bounds__(BLOCK) k_band_copy(double *x, const double *v, const int32_t *bandIdx, int nBand)
+{ pdlEnter();
+    const int k = blockIdx.x * BLOCK + threadIdx.x;
+    if (k < nBand) { const int64_t i = bandIdx[k]; x[i] = v[i]; }
+}
+
+// mask byte of every band cell (BandGridArgs::bandMask) from the band mask grown over the level's GLOBAL box
+__global__ void __launch_bounds__(BLOCK) k_band_mask(uint8_t *bandMask, const int32_t *bandIdx, const uint8_t *mask, int nBand, int pitch, int64_t plane)
+{
+    const int k = blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= nBand) return;
+    const int64_t i = bandIdx[k];
+    const int64_t stride[6] = {-1, 1, -int64_t(pitch), int64_t(pitch), -plane, plane};
+    int m = 0;
+#pragma unroll
+    for (int n = 0; n < 6; ++n) m |= (mask[i + stride[n]] & 1) << n;
+    bandMask[k] = uint8_t(m);
+}
+
 __global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t *bandIdx, const double *v, int nBand)
 { pdlEnter();
     const int k = blockIdx.x * BLOCK + threadIdx.x;
