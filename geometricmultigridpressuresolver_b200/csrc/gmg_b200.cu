@@ -765,25 +765,8 @@ static int selectFlagged(gmg_ctx *ctx, const uint8_t *flags, int64_t n, int32_t 
 }
 
 // boundary band of one level: BOUNDARY cells first, then the INTERIOR cells within width-1 steps (Ops.cpp:165-469)
-// GMG_BAND = grid (default: sweeps on the grids, k_band_grid) | list (compact lists with neighbour references, k_band) |
-// brick (temporally blocked brick lists, k_band_brick)
-enum BandMode { BAND_NONE = -1, BAND_GRID = 0, BAND_LIST = 1, BAND_BRICK = 2 };
-static int bandModeEnv()
+static int buildBand(gmg_ctx *ctx, Level &L, int width)
 {
-    static const int v = [] {
-	const char *e = getenv("GMG_BAND");
-	if (e && !strcmp(e, "list")) return int(BAND_LIST);
-	if (e && !strcmp(e, "brick")) return int(BAND_BRICK);
-	return int(BAND_GRID);
-    }();
-    return v;
-}
-static bool useBricks() { return bandModeEnv() == BAND_BRICK; }
-
-// mode: which smoother structures to build besides the cell list itself
-static int buildBand(gmg_ctx *ctx, Level &L, int width, int mode, int bricksH = 0)
-{
-    const bool legacy = mode == BAND_LIST;
     // the band mask is grown over the level's GLOBAL box (a slab edge must not clip the dilation); the lists are
     // compacted over the rank's stored planes and hold local storage indices
     const Geom &g = L.g;
@@ -806,14 +789,6 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width, int mode, int bricksH = 
 	std::swap(m0, m1);
     }
     const uint8_t *mLocal = m0 + int64_t(L.zOff) * g.plane;
-    // code bytes for the brick lists of the temporally blocked band smoother (built by buildBricks once bpos exists)
-    if (L.bandCode) { GMG_CUDA(devFree(L.bandCode)); L.bandCode = nullptr; }
-    if (mode == BAND_BRICK && bricksH > 0)
-    {
-	GMG_CUDA(devMalloc(&L.bandCode, g.total));
-	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_band_code<<<grid, BLOCK, 0, ctx->stream>>>(L.bandCode, mLocal, L.labels, g.total, g.pitch, g.plane);
-    }
     int32_t *idxB = nullptr, *idxI = nullptr;
     int nB = 0, nI = 0;
     {
@@ -826,6 +801,7 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width, int mode, int bricksH = 
 	k_band_flags<<<grid, BLOCK, 0, ctx->stream>>>(m1, mLocal, L.labels, 1, g.total);
     }
     GMG_TRY(selectFlagged(ctx, m1, g.total, &idxI, &nI));
+    GMG_CUDA(devFree(m0));
     GMG_CUDA(devFree(m1));
     L.nBoundary = nB;
     L.nBand = nB + nI;
@@ -836,18 +812,6 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width, int mode, int bricksH = 
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_CUDA(devFree(idxB));
     GMG_CUDA(devFree(idxI));
-    if (mode == BAND_GRID)
-    {
-	GMG_CUDA(devMalloc(&L.bandMask, std::max(nBand, 1)));
-	GMG_CUDA(devMalloc(&L.bandB, sizeof(double) * std::max(nBand, 1)));
-	if (nBand > 0)
-	{
-	    GMG_LAUNCH(ctx, KC_SETUP, 0);
-	    k_band_mask<<<unsigned(divUp(nBand, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bandMask, L.bandIdx, mLocal, nBand, g.pitch, g.plane);
-	}
-    }
-    GMG_CUDA(devFree(m0));
-    if (!legacy) return GMG_OK;
     GMG_CUDA(devMalloc(&L.bandRef, sizeof(int32_t) * 6 * std::max(nBand, 1)));
     GMG_CUDA(devMalloc(&L.bandV0, sizeof(double) * std::max(nBand, 1)));
     GMG_CUDA(devMalloc(&L.bandV1, sizeof(double) * std::max(nBand, 1)));
@@ -887,16 +851,6 @@ static int buildCoefs(gmg_ctx *ctx, Level &L, const double *w0, const double *w1
 										   L.g.plane);
     }
     L.hasWeights = w0 != nullptr;
-    if (L.hasWeights && !L.bpos && useBricks())
-    {
-	// the brick band kernel finds the coefficient record of a BOUNDARY cell through the grid
-	GMG_CUDA(devMalloc(&L.bpos, sizeof(int32_t) * L.g.total));
-	if (L.nBoundary > 0)
-	{
-	    GMG_LAUNCH(ctx, KC_SETUP, 0);
-	    k_band_pos<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bpos, L.bandIdx, L.nBoundary);
-	}
-    }
     return GMG_OK;
 }
 
@@ -959,122 +913,7 @@ static int buildCoefsSparse(gmg_ctx *ctx, Level &L, const double *w0, const doub
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_CUDA(devFree(dw));
-    if (!L.bpos && !useBricks()) return GMG_OK;
-    if (!L.bpos)
-    {
-	GMG_CUDA(devMalloc(&L.bpos, sizeof(int32_t) * g.total));
-	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_band_pos<<<unsigned(divUp(nB, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bpos, L.bandIdx, nB);
-    }
     return GMG_OK;
-}
-
-static int exclusiveSum(gmg_ctx *ctx, const int *in, int *out, int n)
-{
-    void *dTemp = nullptr;
-    size_t tempBytes = 0;
-    GMG_CUDA(cub::DeviceScan::ExclusiveSum(dTemp, tempBytes, in, out, n, ctx->stream));
-    GMG_CUDA(devMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
-    GMG_CUDA(cub::DeviceScan::ExclusiveSum(dTemp, tempBytes, in, out, n, ctx->stream));
-    ++ctx->launches;
-    GMG_CUDA(devFree(dTemp));
-    return GMG_OK;
-}
-
-template <int H>
-static int buildBricksH(gmg_ctx *ctx, Level &L, const int32_t *bricks, int bricksX, int bricksY)
-{
-    const Geom &g = L.g;
-    const int nb = L.nBricks;
-    int *cnt = nullptr;  // [4][nb]: nLocal, nComp, off, offC
-    GMG_CUDA(devMalloc(&cnt, sizeof(int) * 4 * nb));
-    BrickBuildArgs a;
-    a.code = L.bandCode;
-    a.bricks = bricks;
-    a.bricksX = bricksX;
-    a.bricksY = bricksY;
-    for (int k = 0; k < 3; ++k) a.n[k] = g.n[k];
-    a.pitch = g.pitch;
-    a.plane = g.plane;
-    a.nLocal = cnt;
-    a.nComp = cnt + nb;
-    a.off = cnt + 2 * nb;
-    a.offC = cnt + 3 * nb;
-    a.meta = nullptr;
-    a.gidx = nullptr;
-    a.cells = nullptr;
-    a.bpos = L.hasWeights ? L.bpos : nullptr;
-    {
-	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_brick_build<H, false><<<nb, BLOCK, 0, ctx->stream>>>(a);
-    }
-    GMG_TRY(exclusiveSum(ctx, cnt, cnt + 2 * nb, nb));
-    GMG_TRY(exclusiveSum(ctx, cnt + nb, cnt + 3 * nb, nb));
-    // totals and maxima (the kernel's shared-memory layout) on the host: one read-back of the per-brick counts
-    std::vector<int> h(size_t(2) * nb);
-    GMG_CUDA(cudaMemcpyAsync(h.data(), cnt, sizeof(int) * 2 * nb, cudaMemcpyDeviceToHost, ctx->stream));
-    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    int64_t totLocal = 0, totComp = 0;
-    int maxLocal = 0, maxComp = 0;
-    for (int k = 0; k < nb; ++k)
-    {
-	totLocal += h[k];
-	totComp += h[size_t(nb) + k];
-	maxLocal = std::max(maxLocal, h[k]);
-	maxComp = std::max(maxComp, h[size_t(nb) + k]);
-    }
-    if (totLocal >= (int64_t(1) << 31)) return invalid("band brick lists exceed 2^31 entries");
-    BrickMeta *meta = nullptr;
-    uint4 *cells = nullptr;
-    GMG_CUDA(devMalloc(&meta, sizeof(BrickMeta) * nb));
-    GMG_CUDA(devMalloc(&L.brickGidx, sizeof(int32_t) * std::max<int64_t>(totLocal, 1)));
-    GMG_CUDA(devMalloc(&cells, sizeof(uint4) * std::max<int64_t>(totComp, 1)));
-    a.meta = meta;
-    a.gidx = L.brickGidx;
-    a.cells = cells;
-    {
-	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_brick_build<H, true><<<nb, BLOCK, 0, ctx->stream>>>(a);
-    }
-    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    GMG_CUDA(devFree(cnt));
-    L.brickMeta = meta;
-    L.brickCells = cells;
-    L.brickH = H;
-    L.brickMaxLocal = maxLocal;
-    L.brickMaxComp = maxComp;
-    L.brickListed = totLocal;
-    L.brickUpdated = totComp;
-    return GMG_OK;
-}
-
-// brick lists of the temporally blocked band smoother (needs the code bytes of buildBand and, with face weights, bpos of buildCoefs)
-static int buildBricks(gmg_ctx *ctx, Level &L, int sweeps)
-{
-    if (!L.bandCode || L.nBand == 0 || sweeps < 1) return GMG_OK;
-    const Geom &g = L.g;
-    const int bricksX = int(divUp(g.n[0], BBX)), bricksY = int(divUp(g.n[1], BBY));
-    const int nAll = bricksX * bricksY * int(divUp(g.n[2], BBZ));
-    uint8_t *bf = nullptr;
-    GMG_CUDA(devMalloc(&bf, nAll));
-    {
-	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_brick_flags<<<nAll, BLOCK, 0, ctx->stream>>>(bf, L.bandCode, bricksX, bricksY, g.n[0], g.n[1], g.n[2], g.pitch, g.plane);
-    }
-    int32_t *bricks = nullptr;
-    GMG_TRY(selectFlagged(ctx, bf, nAll, &bricks, &L.nBricks));
-    GMG_CUDA(devFree(bf));
-    int st = GMG_OK;
-    if (L.nBricks > 0)
-    {
-	const int H = std::min(sweeps, BRICK_HMAX);
-	st = H == 3 ? buildBricksH<3>(ctx, L, bricks, bricksX, bricksY) : H == 2 ? buildBricksH<2>(ctx, L, bricks, bricksX, bricksY)
-									     : buildBricksH<1>(ctx, L, bricks, bricksX, bricksY);
-    }
-    GMG_CUDA(devFree(bricks));
-    GMG_CUDA(devFree(L.bandCode));
-    L.bandCode = nullptr;
-    return st;
 }
 
 static int buildChunks(gmg_ctx *ctx, Level &L)
@@ -1122,14 +961,11 @@ static int buildGsTiles(gmg_ctx *ctx, Level &L)
     GMG_TRY(selectFlagged(ctx, fo, nTiles, &L.gsTiles[1], &L.nGsTiles[1]));
     GMG_CUDA(devFree(fo));
     GMG_CUDA(devFree(fe));
-    if (!L.bpos)
+    GMG_CUDA(devMalloc(&L.bpos, sizeof(int32_t) * g.total));
+    if (L.nBoundary > 0)
     {
-	GMG_CUDA(devMalloc(&L.bpos, sizeof(int32_t) * g.total));
-	if (L.nBoundary > 0)
-	{
-	    GMG_LAUNCH(ctx, KC_SETUP, 0);
-	    k_band_pos<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bpos, L.bandIdx, L.nBoundary);
-	}
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_band_pos<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bpos, L.bandIdx, L.nBoundary);
     }
     return GMG_OK;
 }
@@ -1181,7 +1017,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 static void freeLevel(Level &L)
 {
     devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandIdx); devFree(L.bandRef); devFree(L.bcoef);
-    devFree(L.bandV0); devFree(L.bandV1); devFree(L.bandB); devFree(L.bandMask); devFree(L.bandCode); devFree(L.brickMeta); devFree(L.brickGidx); devFree(L.brickCells);
+    devFree(L.bandV0); devFree(L.bandV1); devFree(L.bandB);
     devFree(L.chunksInterior); devFree(L.chunksActive);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
@@ -1419,7 +1255,7 @@ extern "C" int gmg_boundary_cells(gmg_ctx *ctx, const int32_t *labels, const int
     GMG_TRY(uploadLabels(ctx, L.labels, labels, res, L.g));
     L.gg = L.g;
     L.ownHi = L.g.n[2];
-    GMG_TRY(buildBand(ctx, L, width, BAND_NONE));
+    GMG_TRY(buildBand(ctx, L, width));
     int st = exportBand(ctx, L, xyz, count);
     freeLevel(L);
     return st;
@@ -1963,7 +1799,6 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     else gmg_solver_default_options(&s->opt);
     if (const char *e = getenv("GMG_NO_GRAPHS")) s->useGraphs = !(e[0] == '1');
     if (const char *e = getenv("GMG_PRINT_STATS")) s->opt.print_stats = (e[0] == '1');
-    s->bandMode = bandModeEnv();
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel && ctx->world > 1)
@@ -2047,18 +1882,13 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     for (int level = 0; level < s->levels; ++level)
     {
 	Level &L = s->lv[level];
-	const int brickSweeps = s->opt.boundary_iterations >= 1 ? s->opt.boundary_iterations : BRICK_HMAX;
-	if ((st = buildBand(ctx, L, s->opt.boundary_width, s->bandMode, brickSweeps)) != GMG_OK) return fail(st);
+	if ((st = buildBand(ctx, L, s->opt.boundary_width)) != GMG_OK) return fail(st);
 	const int64_t wOff = L.g.plane;
 	const bool fw = level == 0 && dW[0];
 	if (level == 0 && w0 && !fullWeights) st = buildCoefsSparse(ctx, L, w0, w1, w2, res, s->hostBounds);
 	else st = buildCoefs(ctx, L, fw ? dW[0] + wOff : nullptr, fw ? dW[1] + wOff : nullptr, fw ? dW[2] + wOff : nullptr);
 	if (st != GMG_OK) return fail(st);
 	if (level == 0) lap("level 0 band + coefficient records");
-	if (s->bandMode == BAND_BRICK && (st = buildBricks(ctx, L, brickSweeps)) != GMG_OK) return fail(st);
-	if (s->opt.print_stats)
-	    printf("      level %d: %lld active, band %d (%d BOUNDARY), %d bricks: %lld listed, %lld updated, max %d / %d per brick\n", level,
-		   (long long)L.nActive, L.nBand, L.nBoundary, L.nBricks, (long long)L.brickListed, (long long)L.brickUpdated, L.brickMaxLocal, L.brickMaxComp);
 	if ((st = buildChunks(ctx, L)) != GMG_OK) return fail(st);
 	if (s->opt.use_gauss_seidel && (st = buildGsTiles(ctx, L)) != GMG_OK) return fail(st);
 	maxGrid = std::max(maxGrid, L.nChunksActive + int(divUp(L.nBoundary, BLOCK)) + 1);
@@ -2215,120 +2045,12 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
     return GMG_OK;
 }
 
-// Temporally blocked band sweeps (k_band_brick): groups of up to brickH sweeps per launch.  A group that starts from a grid
-// known to be zero writes its own cells in place (it reads nothing from the grid); any other group writes them to the level's
-// residual grid (free during the smoothing) and a second launch copies them back.
-static size_t brickSmem(const Level &L) { return sizeof(double) * (2 * size_t(L.brickMaxLocal + 1) + size_t(L.brickMaxComp)); }
-
-static int launchBandBricks(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid)
-{
-    const Level &L = s->lv[level];
-    if (L.nBricks == 0 || L.brickH < 1) return invalid("band brick lists missing");
-    static const cudaError_t attr = [] {
-	const int bytes = 200 * 1024;
-	cudaError_t e = cudaFuncSetAttribute(k_band_brick<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band_brick<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band_brick<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band_brick<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-	return e;
-    }();
-    GMG_CUDA(attr);
-    cudaStream_t st = s->ctx->stream;
-    const size_t smem = brickSmem(L);
-    const unsigned grid = unsigned(L.nBricks);
-    BrickArgs a;
-    a.b = b;
-    a.meta = static_cast<const BrickMeta *>(L.brickMeta);
-    a.gidx = L.brickGidx;
-    a.cells = static_cast<const uint4 *>(L.brickCells);
-    a.bcoef = L.bcoef;
-    a.nBoundary = L.nBoundary;
-    a.maxLocal = L.brickMaxLocal;
-    a.maxComp = L.brickMaxComp;
-    bool zero = zeroGrid;
-    for (int left = sweeps; left > 0;)
-    {
-	const int h = std::min(left, L.brickH);
-	a.x = x;
-	a.out = zero ? x : L.r;
-	a.sweeps = h;
-	{
-	    GMG_LAUNCH(s->ctx, KC_BAND, double(L.nBand) * 29.0 * h);
-	    if (zero && L.hasWeights) GMG_CUDA(launchK((k_band_brick<true, true>), grid, unsigned(BLOCK), smem, st, a));
-	    else if (zero) GMG_CUDA(launchK((k_band_brick<true, false>), grid, unsigned(BLOCK), smem, st, a));
-	    else if (L.hasWeights) GMG_CUDA(launchK((k_band_brick<false, true>), grid, unsigned(BLOCK), smem, st, a));
-	    else GMG_CUDA(launchK((k_band_brick<false, false>), grid, unsigned(BLOCK), smem, st, a));
-	}
-	if (!zero)
-	{
-	    GMG_LAUNCH(s->ctx, KC_BAND, 0.0);
-	    GMG_CUDA(launchK(k_band_brick_commit, grid, unsigned(BLOCK), size_t(0), st, x, static_cast<const double *>(L.r), a.meta, a.gidx));
-	}
-	zero = false;
-	left -= h;
-    }
-    GMG_CUDA(cudaGetLastError());
-    return GMG_OK;
-}
-
-// Band sweeps on the grids (k_band_grid).  scratch: a grid of the level whose contents are dead (the smoother's alternate
-// buffer); the level's residual grid is the second scratch.  Sweep j reads the band cells where sweep j-1 put them and
-// writes the other scratch; the last sweep writes x.
-static int launchBandGrid(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid, double *scratch)
-{
-    const Level &L = s->lv[level];
-    double *y = scratch ? scratch : L.xAlt, *z = L.r;
-    if (x == y || x == z || y == z) return invalid("band sweeps: the grid aliases a scratch grid of its level");
-    BandGridArgs a;
-    a.x = x;
-    a.b = b;
-    a.bandIdx = L.bandIdx;
-    a.bandMask = L.bandMask;
-    a.bcoef = L.bcoef;
-    a.bandB = L.bandB;
-    a.nBoundary = L.nBoundary;
-    a.nBand = L.nBand;
-    a.pitch = L.g.pitch;
-    a.plane = L.g.plane;
-    const unsigned grid = unsigned(divUp(L.nBand, BLOCK * BAND_PER_THREAD));
-    cudaStream_t st = s->ctx->stream;
-    const double bytes = double(L.nBand) * 29.0;
-    const bool hw = L.hasWeights;
-    const double *src = x;
-    for (int sw = 1; sw <= sweeps; ++sw)
-    {
-	double *dst = (sw == sweeps && sweeps > 1) ? x : (src == y ? z : y);
-	a.s = src;
-	a.d = dst;
-	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
-	if (sw == 1)
-	{
-	    if (zeroGrid) GMG_CUDA(launchK((k_band_grid<true, true, false>), grid, BLOCK, 0, st, a));
-	    else if (hw) GMG_CUDA(launchK((k_band_grid<true, false, true>), grid, BLOCK, 0, st, a));
-	    else GMG_CUDA(launchK((k_band_grid<true, false, false>), grid, BLOCK, 0, st, a));
-	}
-	else if (hw) GMG_CUDA(launchK((k_band_grid<false, false, true>), grid, BLOCK, 0, st, a));
-	else GMG_CUDA(launchK((k_band_grid<false, false, false>), grid, BLOCK, 0, st, a));
-	src = dst;
-    }
-    if (sweeps == 1)
-    {
-	GMG_LAUNCH(s->ctx, KC_BAND, double(L.nBand) * 20.0);
-	GMG_CUDA(launchK(k_band_copy, unsigned(divUp(L.nBand, BLOCK)), BLOCK, 0, st, x, src, L.bandIdx, L.nBand));
-    }
-    GMG_CUDA(cudaGetLastError());
-    return GMG_OK;
-}
-
-// `sweeps` boundary-band Jacobi sweeps on grid x (Ops.h:524-619); zeroGrid: x is known to be all zero;
-// scratch: a dead grid of the level for the grid-based sweeps (null = the level's alternate solution grid)
-static int launchBand(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid, double *scratch = nullptr)
+// `sweeps` boundary-band Jacobi sweeps on grid x (Ops.h:524-619); zeroGrid: x is known to be all zero
+static int launchBand(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid)
 {
     s->ctx->curLevel = level;
     const Level &L = s->lv[level];
     if (L.nBand == 0 || sweeps <= 0) return GMG_OK;
-    if (s->bandMode == BAND_BRICK) return launchBandBricks(s, level, x, b, sweeps, zeroGrid);
-    if (s->bandMode == BAND_GRID) return launchBandGrid(s, level, x, b, sweeps, zeroGrid, scratch);
     BandArgs a;
     a.x = x;
     a.b = b;
@@ -2702,7 +2424,7 @@ static int launchGaussSeidel(gmg_solver *s, int level, double *x, const double *
 {
     s->ctx->curLevel = level;
     const Level &L = s->lv[level];
-    if (!L.gsTiles[0] && !L.gsTiles[1]) return invalid("this solver was not created with use_gauss_seidel");
+    if (!L.bpos) return invalid("this solver was not created with use_gauss_seidel");
     const int n = L.nGsTiles[oddTiles ? 1 : 0];
     if (n == 0) return GMG_OK;
     GsArgs a;
@@ -2725,7 +2447,7 @@ static int launchGaussSeidel(gmg_solver *s, int level, double *x, const double *
 static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, const double *b, bool zeroGrid, int jacobiDepth, bool down)
 {
     const int it = s->opt.boundary_iterations;
-    GMG_TRY(launchBand(s, level, cur, b, it, zeroGrid, alt));
+    GMG_TRY(launchBand(s, level, cur, b, it, zeroGrid));
     if (s->opt.use_gauss_seidel)
     {
 	GMG_TRY(launchGaussSeidel(s, level, cur, b, down, down));
@@ -2736,7 +2458,7 @@ static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, con
 	GMG_TRY(launchStencil(s, level, SM_JACOBI, cur, b, alt, nullptr, clipDepth(s->lv[level], jacobiDepth)));
 	std::swap(cur, alt);
     }
-    GMG_TRY(launchBand(s, level, cur, b, it, false, alt));
+    GMG_TRY(launchBand(s, level, cur, b, it, false));
     return GMG_OK;
 }
 

@@ -86,14 +86,6 @@ struct Level
     bool hasWeights = false;     // level 0 built with face weights: BOUNDARY cells carry fractional coefficients
     double *bcoef = nullptr;     // [7][nBoundary]: coefficient on each of the 6 neighbours, then the diagonal
     double *bandV0 = nullptr, *bandV1 = nullptr, *bandB = nullptr;
-    uint8_t *bandMask = nullptr; // [nBand] which neighbours of a band cell are band cells (gmg_kernels.cuh: BandGridArgs::bandMask)
-    // temporally blocked band smoother (gmg_kernels.cuh: k_band_brick): per brick with a band cell, the local cell list
-    uint8_t *bandCode = nullptr; // setup only: one code byte per cell
-    void *brickMeta = nullptr;   // BrickMeta[nBricks]
-    int32_t *brickGidx = nullptr;
-    void *brickCells = nullptr;  // uint4 per updated cell
-    int nBricks = 0, brickH = 0, brickMaxLocal = 0, brickMaxComp = 0;
-    int64_t brickListed = 0, brickUpdated = 0;  // totals over the bricks (traffic accounting)
     // CTAs of the full-grid kernels: chunks holding at least one INTERIOR cell / one active cell
     int nChunksInterior = 0, nChunksActive = 0;
     int32_t *chunksInterior = nullptr, *chunksActive = nullptr;
@@ -168,7 +160,6 @@ struct gmg_solver
     double *coarseInv = nullptr;  // [nCoarse][nCoarse] row-major inverse
     // z-slab sharding: levels [0, shardLevels) are slabs, the rest replicated on every rank
     int shardLevels = 0;
-    int bandMode = 0;             // 0 = sweeps on the grids (k_band_grid), 1 = compact lists with neighbour references (k_band), 2 = brick lists (k_band_brick)
     int p2pGeneration = -1;       // generation of the context's peer-memory arenas this solver was built against
     std::vector<int> gatherLo, gatherHi; // per rank: planes of the first replicated level it restricts into
     // compact coarse sub-V-cycle: levels [fusedFirst, levels-1] in one shared-memory CTA (-1 = off)

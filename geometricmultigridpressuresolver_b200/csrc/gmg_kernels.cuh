@@ -321,467 +321,10 @@ __global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
     bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W>(a, blockIdx.x, threadIdx.x);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Band sweep on the GRIDS (default).  The band values stay in grid layout, so a neighbour is one fixed stride away and a
-// sweep is ONE dependent step (index -> seven values) instead of two (index -> reference -> value), and there are no
-// 24-byte reference records to read.  Sweep j of a group reads band neighbours from `s` (where sweep j-1 wrote them: the
-// grid itself for the first sweep), frozen non-band neighbours from the grid `x`, and writes the band cells of `d`; one
-// mask byte per band cell says which of its six neighbours are band cells.  The last sweep writes `x` itself, which is
-// race-free because that sweep reads x at non-band cells only.  s/d alternate between two scratch grids of the level.
-// ------------------------------------------------------------------------------------------------
-struct BandGridArgs
-{
-    const double *x;     // frozen (non-band) neighbours
-    const double *s;     // band cells after the previous sweep
-    double *d;           // receives the band cells
-    const double *b;
-    const int32_t *bandIdx;
-    const uint8_t *bandMask;  // bit n: neighbour n (-x,+x,-y,+y,-z,+z) is a band cell
-    const double *bcoef;
-    double *bandB;       // compact rhs of the band cells (written by the FIRST sweep of a group)
-    int nBoundary, nBand;
-    int pitch;
-    int64_t plane;
-};
-
-template <bool FIRST, bool ZERO, bool HAS_W>
-__device__ __forceinline__ void bandGridBody(const BandGridArgs &a, int vb, int tid)
-{
-    double v[BAND_PER_THREAD];
-    int64_t gi[BAND_PER_THREAD];
-#pragma unroll
-    for (int c = 0; c < BAND_PER_THREAD; ++c)
-    {
-	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
-	v[c] = 0.0;
-	gi[c] = 0;
-	if (k >= a.nBand) continue;
-	const int64_t i = a.bandIdx[k];
-	gi[c] = i;
-	double rhs;
-	if (FIRST) { rhs = a.b[i]; a.bandB[k] = rhs; }
-	else rhs = a.bandB[k];
-	const double diag = k < a.nBoundary ? a.bcoef[int64_t(6) * a.nBoundary + k] : 6.0;
-	double centre = 0.0, lap = 0.0;
-	if (!ZERO)
-	{
-	    const int m = a.bandMask[k];
-	    const bool weighted = HAS_W && k < a.nBoundary;
-	    centre = a.s[i];
-	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
-	    double u[6];
-#pragma unroll
-	    for (int n = 0; n < 6; ++n) u[n] = ((m >> n) & 1) ? a.s[i + stride[n]] : a.x[i + stride[n]];
-#pragma unroll
-	    for (int n = 0; n < 6; ++n)
-	    {
-		if (weighted)
-		{
-		    const double cn = a.bcoef[int64_t(n) * a.nBoundary + k];
-		    if (cn != 0.0) lap -= cn * u[n];
-		}
-		else lap -= u[n];  // an inactive neighbour holds exactly 0 (vector-grid invariant), and v - 0 == v
-	    }
-	    lap += diag * centre;
-	}
-	double r = rhs - lap;
-	r /= diag;
-	v[c] = centre + (2.0 / 3.0) * r;
-    }
-#pragma unroll
-    for (int c = 0; c < BAND_PER_THREAD; ++c)
-    {
-	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
-	if (k < a.nBand) a.d[gi[c]] = v[c];
-    }
-}
-template <bool FIRST, bool ZERO, bool HAS_W>
-__global__ void __launch_bounds__(BLOCK) k_band_grid(const BandGridArgs a)
-{
-    pdlEnter();
-    bandGridBody<FIRST, ZERO, HAS_W>(a, blockIdx.x, threadIdx.x);
-}
-
-// x[band] = v[band] between two grids (a group of ONE sweep cannot write the grid it reads)
-__global__ void __launch_bounds__(BLOCK) k_band_copy(double *x, const double *v, const int32_t *bandIdx, int nBand)
-{ pdlEnter();
-    const int k = blockIdx.x * BLOCK + threadIdx.x;
-    if (k < nBand) { const int64_t i = bandIdx[k]; x[i] = v[i]; }
-}
-
-// mask byte of every band cell (BandGridArgs::bandMask) from the band mask grown over the level's GLOBAL box
-__global__ void __launch_bounds__(BLOCK) k_band_mask(uint8_t *bandMask, const int32_t *bandIdx, const uint8_t *mask, int nBand, int pitch, int64_t plane)
-{
-    const int k = blockIdx.x * BLOCK + threadIdx.x;
-    if (k >= nBand) return;
-    const int64_t i = bandIdx[k];
-    const int64_t stride[6] = {-1, 1, -int64_t(pitch), int64_t(pitch), -plane, plane};
-    int m = 0;
-#pragma unroll
-    for (int n = 0; n < 6; ++n) m |= (mask[i + stride[n]] & 1) << n;
-    bandMask[k] = uint8_t(m);
-}
-
 __global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t *bandIdx, const double *v, int nBand)
 { pdlEnter();
     const int k = blockIdx.x * BLOCK + threadIdx.x;
     if (k < nBand) x[bandIdx[k]] = v[k];
-}
-
-// ------------------------------------------------------------------------------------------------
-// Temporally blocked boundary-band Jacobi: ALL sweeps of one boundaryJacobiPoissonSmoother group (Ops.h:524-619,
-// called 3 times in a row by MG.cpp:449-459 / :753-763) in ONE kernel.  The storage box is cut into BBX x BBY x BBZ
-// bricks; a CTA owns the band cells of one brick.  At setup every brick gets a LOCAL CELL LIST, ordered by the distance
-// d of a cell from the brick (Chebyshev, in cells):
-//     [ band cells, d = 0 (own) | band cells, d = 1 | ... | band cells, d = H-1 | frozen cells ]
-// where "frozen" are the cells read but not updated: band cells at d = H and active non-band cells next to an updated one.
-// The kernel stages the values of the list in shared memory and runs sweep j of a group of h on the prefix d <= h - j:
-// the box on which the sweep is still exact shrinks by one cell per sweep, so after h sweeps the own cells hold exactly what
-// h global sweeps give them.  Per updated cell the list holds six 16-bit local neighbour indices (an inactive neighbour points
-// at a slot that holds 0) and the diagonal / coefficient-record index: 16 bytes, one vector load.  Per cell the arithmetic
-// and its order are those of bandBody, so the result is bitwise the one of h separate sweeps.
-// The grid the sweeps read must not be written while other CTAs still stage their lists from it, so the results go to
-// `out`: the grid itself when it is known to be all zero (down-stroke; nothing is read from it), else a staging grid from
-// which k_band_brick_commit copies the own cells back.
-// ------------------------------------------------------------------------------------------------
-constexpr int BBX = 16, BBY = 8, BBZ = 8;
-constexpr int BRICK_CELLS = BBX * BBY * BBZ;
-constexpr int BRICK_HMAX = 3;
-// code byte of a cell: bit 7 = band cell, bit 6 = its value is read by a band sweep (band cell or active neighbour of one),
-// bit 5 = BOUNDARY label, bits 0..2 = diagonal of the unweighted operator (6 INTERIOR; non-EXTERIOR neighbours of a BOUNDARY cell)
-constexpr int BC_BAND = 0x80, BC_NEAR = 0x40, BC_BOUNDARY = 0x20, BC_DIAG = 0x07;
-constexpr unsigned BRICK_AUX_RECORD = 0x80000000u;  // aux word: bit 31 = the low bits are a coefficient-record index, else the diagonal
-
-struct BrickMeta
-{
-    int off;      // first entry of the brick in the local-cell arrays (gidx)
-    int offC;     // first entry of the brick in the updated-cell array (cells)
-    int p[BRICK_HMAX];  // p[k] = number of band cells with d <= k (p[0] = own cells)
-    int nLocal;   // all listed cells
-    int pad[2];
-};
-
-struct BrickArgs
-{
-    const double *x;       // grid the sweeps start from (unused when ZERO)
-    double *out;           // grid that receives the own cells after the last sweep
-    const double *b;
-    const BrickMeta *meta;
-    const int32_t *gidx;   // storage index of every listed cell
-    const uint4 *cells;    // per updated cell: 6 x u16 local neighbour index (-x,+x,-y,+y,-z,+z), aux word
-    const double *bcoef;   // coefficient records (level 0 with face weights)
-    int nBoundary;
-    int maxLocal, maxComp; // largest list / updated-cell count of a brick of the level: shared-memory layout
-    int sweeps;            // 1..H the lists were built for
-};
-
-__device__ __forceinline__ void cpAsync8(void *smemDst, const void *gmemSrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(unsigned(__cvta_generic_to_shared(smemDst))), "l"(gmemSrc) : "memory");
-}
-__device__ __forceinline__ void cpAsync16(void *smemDst, const void *gmemSrc)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(unsigned(__cvta_generic_to_shared(smemDst))), "l"(gmemSrc) : "memory");
-}
-
-// Shared memory: A [maxLocal + 1], B [maxLocal + 1], rhs [maxComp].  Values are staged
-// with asynchronous copies issued back to back (the only dependent step is index -> value), then the sweeps run out of
-// shared memory alone.
-template <bool ZERO, bool HAS_W>
-__global__ void __launch_bounds__(BLOCK) k_band_brick(const BrickArgs a)
-{
-    pdlEnter();
-    extern __shared__ __align__(16) unsigned char bsmRaw[];
-    double *A = reinterpret_cast<double *>(bsmRaw);  // slot nLocal holds 0
-    double *B = A + a.maxLocal + 1;
-    double *rhs = B + a.maxLocal + 1;
-    const BrickMeta m = a.meta[blockIdx.x];
-    const int h = a.sweeps;
-    const int p0 = m.p[0], p1 = m.p[1], p2 = m.p[2];
-    auto prefix = [&](int k) { return k == 0 ? p0 : (k == 1 ? p1 : p2); };
-    const int nFirst = prefix(h - 1);     // cells the first sweep updates
-    const int32_t *gi = a.gidx + m.off;
-    const uint4 *cellS = a.cells + m.offC;
-    constexpr int K = 4;  // indices in flight per thread
-    for (int base = threadIdx.x; base < m.nLocal; base += BLOCK * K)
-    {
-	int g[K];
-#pragma unroll
-	for (int k = 0; k < K; ++k)
-	{
-	    const int i = base + k * BLOCK;
-	    g[k] = i < m.nLocal ? __ldg(gi + i) : -1;
-	}
-#pragma unroll
-	for (int k = 0; k < K; ++k)
-	{
-	    const int i = base + k * BLOCK;
-	    if (g[k] < 0) continue;
-	    if (ZERO) A[i] = 0.0;
-	    else cpAsync8(A + i, a.x + g[k]);
-	    if (i < nFirst) cpAsync8(rhs + i, a.b + g[k]);
-	    else if (ZERO) B[i] = 0.0;
-	    else cpAsync8(B + i, a.x + g[k]);  // never updated in this group: both buffers hold it
-	}
-    }
-    if (threadIdx.x == 0) { A[m.nLocal] = 0.0; B[m.nLocal] = 0.0; }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    const double *src = A;
-    double *dst = B;
-    for (int j = 1; j <= h; ++j)
-    {
-	const int n = prefix(h - j);
-	const bool last = (j == h);
-	for (int i = threadIdx.x; i < n; i += BLOCK)
-	{
-	    const int g = last ? __ldg(gi + i) : 0;
-	    const uint4 q = __ldg(cellS + i);
-	    double diag;
-	    double centre = 0.0, lap = 0.0;
-	    const bool weighted = HAS_W && (q.w & BRICK_AUX_RECORD);
-	    const int k = int(q.w & ~BRICK_AUX_RECORD);
-	    if (weighted) diag = __ldg(a.bcoef + int64_t(6) * a.nBoundary + k);
-	    else diag = double(k);
-	    if (!(ZERO && j == 1))
-	    {
-		centre = src[i];
-		const double u[6] = {src[q.x & 0xffffu], src[q.x >> 16], src[q.y & 0xffffu], src[q.y >> 16], src[q.z & 0xffffu], src[q.z >> 16]};
-		if (weighted)
-		{
-#pragma unroll
-		    for (int d = 0; d < 6; ++d)
-		    {
-			const double cn = __ldg(a.bcoef + int64_t(d) * a.nBoundary + k);
-			if (cn != 0.0) lap -= cn * u[d];
-		    }
-		}
-		else
-		{
-		    // an inactive neighbour reads the zero slot, and v - 0 == v: no label test needed
-#pragma unroll
-		    for (int d = 0; d < 6; ++d) lap -= u[d];
-		}
-		lap += diag * centre;
-	    }
-	    double r = rhs[i] - lap;
-	    r /= diag;
-	    const double v = centre + (2.0 / 3.0) * r;
-	    if (last) a.out[g] = v;
-	    else dst[i] = v;
-	}
-	if (!last) __syncthreads();
-	const double *t = src; src = dst; dst = const_cast<double *>(t);
-    }
-}
-
-// x[own cells of the brick] = stage[same cells]
-__global__ void __launch_bounds__(BLOCK) k_band_brick_commit(double *x, const double *stage, const BrickMeta *meta, const int32_t *gidx)
-{
-    pdlEnter();
-    const BrickMeta m = meta[blockIdx.x];
-    for (int i = threadIdx.x; i < m.p[0]; i += BLOCK)
-    {
-	const int64_t g = gidx[m.off + i];
-	x[g] = stage[g];
-    }
-}
-
-// Setup of the brick lists.  One CTA per brick with a band cell enumerates the brick +- H in a fixed order (thread t owns the
-// dense cells [t*PER, (t+1)*PER)), classifies them and -- second pass, FILL -- numbers them class by class.
-struct BrickBuildArgs
-{
-    const uint8_t *code;
-    const int32_t *bricks;   // linear brick ids (x fastest)
-    int bricksX, bricksY;
-    int n[3];
-    int pitch;
-    int64_t plane;
-    int *nLocal, *nComp;     // COUNT: per brick totals (input of the two prefix sums)
-    const int *off, *offC;   // FILL: the prefix sums
-    BrickMeta *meta;
-    int32_t *gidx;
-    uint4 *cells;
-    const int32_t *bpos;     // grid: coefficient-record index of BOUNDARY cells (level 0 with face weights), else null
-};
-
-template <int H, bool FILL>
-__global__ void __launch_bounds__(BLOCK) k_brick_build(const BrickBuildArgs a)
-{
-    constexpr int X0 = BBX + 2 * H, Y0 = BBY + 2 * H, Z0 = BBZ + 2 * H;
-    constexpr int N0 = X0 * Y0 * Z0;
-    constexpr int PER = (N0 + BLOCK - 1) / BLOCK;
-    constexpr int NONE = 0xff;
-    __shared__ uint8_t cs[N0];        // code byte
-    __shared__ uint8_t cls[N0];       // class: 0..H-1 updated band cell at that distance, H frozen, NONE not listed
-    __shared__ unsigned short lid[FILL ? N0 : 1];  // local index
-    __shared__ unsigned long long total;
-    const int t = a.bricks[blockIdx.x];
-    const int tz = t / (a.bricksX * a.bricksY), ty = (t - tz * a.bricksX * a.bricksY) / a.bricksX, tx = t - (tz * a.bricksY + ty) * a.bricksX;
-    const int ox = tx * BBX - H, oy = ty * BBY - H, oz = tz * BBZ - H;  // storage coordinate of dense cell (0,0,0)
-    for (int i = threadIdx.x; i < N0; i += BLOCK)
-    {
-	const int lz = i / (X0 * Y0), ly = (i - lz * X0 * Y0) / X0, lx = i - (lz * Y0 + ly) * X0;
-	const int gx = ox + lx, gy = oy + ly, gz = oz + lz;
-	uint8_t c = 0;
-	if (gx >= 0 && gy >= 0 && gz >= 0 && gx < a.n[0] && gy < a.n[1] && gz < a.n[2]) c = a.code[int64_t(gz) * a.plane + int64_t(gy) * a.pitch + gx];
-	cs[i] = c;
-    }
-    __syncthreads();
-    auto dist = [&](int i) {
-	const int lz = i / (X0 * Y0), ly = (i - lz * X0 * Y0) / X0, lx = i - (lz * Y0 + ly) * X0;
-	const int dx = max(max(H - lx, lx - (H + BBX - 1)), 0), dy = max(max(H - ly, ly - (H + BBY - 1)), 0), dz = max(max(H - lz, lz - (H + BBZ - 1)), 0);
-	return max(dx, max(dy, dz));
-    };
-    // updated band cells first (their class is the distance), then the frozen cells next to one
-    for (int i = threadIdx.x; i < N0; i += BLOCK)
-    {
-	const int d = dist(i);
-	cls[i] = ((cs[i] & BC_BAND) && d < H) ? uint8_t(d) : uint8_t(NONE);
-    }
-    __syncthreads();
-    const int i0 = threadIdx.x * PER, i1 = min(i0 + PER, N0);
-    unsigned long long cnt = 0;  // four 16-bit counters, one per class
-    for (int i = i0; i < i1; ++i)
-    {
-	int c = cls[i];
-	if (c == NONE && (cs[i] & BC_NEAR))
-	{
-	    const int lz = i / (X0 * Y0), ly = (i - lz * X0 * Y0) / X0, lx = i - (lz * Y0 + ly) * X0;
-	    bool adj = false;
-	    if (lx > 0) adj |= cls[i - 1] < H;
-	    if (lx < X0 - 1) adj |= cls[i + 1] < H;
-	    if (ly > 0) adj |= cls[i - X0] < H;
-	    if (ly < Y0 - 1) adj |= cls[i + X0] < H;
-	    if (lz > 0) adj |= cls[i - X0 * Y0] < H;
-	    if (lz < Z0 - 1) adj |= cls[i + X0 * Y0] < H;
-	    if (adj) c = H;
-	}
-	if (c != NONE) cnt += 1ull << (16 * c);
-    }
-    // (a frozen cell's class is only known to its owner thread: the adjacency test reads classes < H, which are final)
-    typedef cub::BlockScan<unsigned long long, BLOCK> Scan;
-    __shared__ typename Scan::TempStorage scanTmp;
-    unsigned long long before = 0, all = 0;
-    Scan(scanTmp).ExclusiveSum(cnt, before, all);
-    if (threadIdx.x == 0) total = all;
-    __syncthreads();
-    all = total;
-    int classBase[H + 2];
-    classBase[0] = 0;
-#pragma unroll
-    for (int c = 0; c <= H; ++c) classBase[c + 1] = classBase[c] + int((all >> (16 * c)) & 0xffffu);
-    const int nLocal = classBase[H + 1], nComp = classBase[H];
-    if (!FILL)
-    {
-	if (threadIdx.x == 0) { a.nLocal[blockIdx.x] = nLocal; a.nComp[blockIdx.x] = nComp; }
-	return;
-    }
-    const int off = a.off[blockIdx.x], offC = a.offC[blockIdx.x];
-    if (threadIdx.x == 0)
-    {
-	BrickMeta m;
-	m.off = off; m.offC = offC; m.nLocal = nLocal; m.pad[0] = m.pad[1] = 0;
-	for (int k = 0; k < BRICK_HMAX; ++k) m.p[k] = classBase[min(k, H - 1) + 1];
-	a.meta[blockIdx.x] = m;
-    }
-    // numbering: class-major, dense order inside a class
-    for (int i = threadIdx.x; i < N0; i += BLOCK) lid[i] = 0xffffu;
-    __syncthreads();
-    {
-	int next[H + 1];
-#pragma unroll
-	for (int c = 0; c <= H; ++c) next[c] = classBase[c] + int((before >> (16 * c)) & 0xffffu);
-	for (int i = i0; i < i1; ++i)
-	{
-	    int c = cls[i];
-	    if (c == NONE && (cs[i] & BC_NEAR))
-	    {
-		const int lz = i / (X0 * Y0), ly = (i - lz * X0 * Y0) / X0, lx = i - (lz * Y0 + ly) * X0;
-		bool adj = false;
-		if (lx > 0) adj |= cls[i - 1] < H;
-		if (lx < X0 - 1) adj |= cls[i + 1] < H;
-		if (ly > 0) adj |= cls[i - X0] < H;
-		if (ly < Y0 - 1) adj |= cls[i + X0] < H;
-		if (lz > 0) adj |= cls[i - X0 * Y0] < H;
-		if (lz < Z0 - 1) adj |= cls[i + X0 * Y0] < H;
-		if (adj) c = H;
-	    }
-	    if (c == NONE) continue;
-#pragma unroll
-	    for (int q = 0; q <= H; ++q)
-		if (c == q) lid[i] = (unsigned short)(next[q]++);
-	}
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < N0; i += BLOCK)
-    {
-	const int li = lid[i];
-	if (li == 0xffffu) continue;
-	const int lz = i / (X0 * Y0), ly = (i - lz * X0 * Y0) / X0, lx = i - (lz * Y0 + ly) * X0;
-	const int64_t g = int64_t(oz + lz) * a.plane + int64_t(oy + ly) * a.pitch + (ox + lx);
-	a.gidx[off + li] = int32_t(g);
-	if (li >= nComp) continue;
-	// an updated cell sits at d < H, so its six neighbours are inside the dense box; a neighbour that is not listed is
-	// inactive (every active neighbour of a band cell is listed) and reads the zero slot nLocal
-	const int nb[6] = {i - 1, i + 1, i - X0, i + X0, i - X0 * Y0, i + X0 * Y0};
-	unsigned r[6];
-#pragma unroll
-	for (int d = 0; d < 6; ++d)
-	{
-	    const unsigned v = lid[nb[d]];
-	    r[d] = (v == 0xffffu) ? unsigned(nLocal) : v;
-	}
-	unsigned aux = unsigned(cs[i] & BC_DIAG);
-	if (a.bpos && (cs[i] & BC_BOUNDARY)) aux = BRICK_AUX_RECORD | unsigned(a.bpos[g]);
-	a.cells[offC + li] = make_uint4(r[0] | (r[1] << 16), r[2] | (r[3] << 16), r[4] | (r[5] << 16), aux);
-    }
-}
-
-// code bytes of a level (BrickArgs::code).  mask = band mask over the level's GLOBAL box (bit 0), labels/mask pointers are
-// already offset to the rank's first stored plane; neighbours of an active cell are always inside the global allocation.
-__global__ void __launch_bounds__(BLOCK) k_band_code(uint8_t *code, const uint8_t *mask, const uint8_t *labels, int64_t total, int pitch, int64_t plane)
-{
-    const int64_t i = int64_t(blockIdx.x) * BLOCK + threadIdx.x;
-    if (i >= total) return;
-    const int l = labels[i];
-    int c = 0;
-    if (l == L_INTERIOR || l == L_BOUNDARY)
-    {
-	const int64_t stride[6] = {-1, 1, -int64_t(pitch), int64_t(pitch), -plane, plane};
-	int diag = 0, near = mask[i] & 1;
-#pragma unroll
-	for (int n = 0; n < 6; ++n)
-	{
-	    const int nl = labels[i + stride[n]];
-	    if (nl != L_EXTERIOR) ++diag;
-	    near |= mask[i + stride[n]] & 1;
-	}
-	if (mask[i] & 1) c |= BC_BAND;
-	if (near) c |= BC_NEAR;
-	if (l == L_BOUNDARY) c |= BC_BOUNDARY;
-	c |= (l == L_INTERIOR) ? 6 : diag;
-    }
-    code[i] = uint8_t(c);
-}
-
-// flag = brick holds a band cell
-__global__ void __launch_bounds__(BLOCK) k_brick_flags(uint8_t *flags, const uint8_t *code, int bricksX, int bricksY, int n0, int n1, int n2, int pitch,
-						       int64_t plane)
-{
-    const int t = blockIdx.x;
-    const int tz = t / (bricksX * bricksY), ty = (t - tz * bricksX * bricksY) / bricksX, tx = t - (tz * bricksY + ty) * bricksX;
-    int any = 0;
-#pragma unroll
-    for (int j = 0; j < BRICK_CELLS / BLOCK; ++j)
-    {
-	const int i = threadIdx.x + j * BLOCK;
-	const int gx = tx * BBX + i % BBX, gy = ty * BBY + (i / BBX) % BBY, gz = tz * BBZ + i / (BBX * BBY);
-	if (gx < n0 && gy < n1 && gz < n2) any |= code[int64_t(gz) * plane + int64_t(gy) * pitch + gx] & BC_BAND;
-    }
-    any = __syncthreads_or(any);
-    if (threadIdx.x == 0) flags[t] = uint8_t(any != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
