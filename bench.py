@@ -299,8 +299,9 @@ def run_gpu_arm(args, rank, world, local_rank):
         # construction: int32 labels of the box + the six face weights of every BOUNDARY cell (the weight grids themselves stay on the
         # host: only BOUNDARY cells look at them; their index list comes back first); per solve: rhs + x0 in, pressure out
         n_boundary = int((labels == 3).sum())
-        h2d = box_cells * 4 + n_boundary * 48 + 2 * box_cells * 8
-        d2h = box_cells * 8 + n_boundary * 4
+        io_cells, io_copies = solver.transfer_cells()  # rhs / x0 / pressure move the active rectangles of each z-plane only
+        h2d = box_cells * 4 + n_boundary * 48 + 2 * io_cells * 8
+        d2h = io_cells * 8 + n_boundary * 4
         e2e_val = float(np.mean(e2e_ms))
         if dist is not None:
             t = torch.tensor([e2e_val], device="cuda", dtype=torch.float64)
@@ -309,8 +310,8 @@ def run_gpu_arm(args, rank, world, local_rank):
             sh, zlo, zhi, _ = solver.shard_info(0)
             if sh:  # per rank: its slab of the weights / rhs / x0 (+ the replicated one-byte labels); summed over the ranks below
                 frac = (zhi - zlo + 20) / float(hi[2] - int(off[2]) + 4)
-                h2d = int(box_cells * 4 + n_boundary * frac * 48 + box_cells * frac * 2 * 8)
-                d2h = int(box_cells * 8 * (zhi - zlo) / float(hi[2] - int(off[2]) + 4))
+                h2d = int(box_cells * 4 + n_boundary * frac * 48 + io_cells * 2 * 8)
+                d2h = int(io_cells * 8 * (zhi - zlo) / float(zhi - zlo + 20))
             t = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64)
             dist.all_reduce(t)
             h2d, d2h = int(t[0].item()), int(t[1].item())

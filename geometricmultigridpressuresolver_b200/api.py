@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "gmg_last_error", "gmg_version", "gmg_ctx_create", "gmg_ctx_destroy", "gmg_ctx_synchronize", "gmg_ctx_shard", "gmg_nccl_unique_id", "gmg_ctx_rank", "gmg_shard_plan", "gmg_solver_shard_info", "gmg_comm_count", "gmg_comm_benchmark",
     "gmg_expand_dims", "gmg_expand_labels", "gmg_expand_weights", "gmg_set_boundary_labels", "gmg_coarsen_labels", "gmg_boundary_cells",
     "gmg_solver_default_options", "gmg_solver_create", "gmg_solver_destroy", "gmg_solver_levels", "gmg_solver_level_res",
-    "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms",
+    "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms", "gmg_solver_transfer_cells",
     "gmg_vcycle", "gmg_pcg", "gmg_grid_create", "gmg_grid_destroy", "gmg_grid_upload", "gmg_grid_download", "gmg_grid_zero", "gmg_grid_copy",
     "gmg_jacobi", "gmg_gauss_seidel", "gmg_boundary_jacobi", "gmg_apply", "gmg_residual", "gmg_restrict", "gmg_prolong_add", "gmg_dot", "gmg_norm2", "gmg_inf_norm",
     "gmg_axpy", "gmg_add_scaled", "gmg_scale", "gmg_vcycle_device", "gmg_pcg_device", "gmg_launch_count", "gmg_timer_begin", "gmg_timer_end",
@@ -406,6 +406,13 @@ class GeometricMultigridPoissonSolver:
         n = C.c_int64()
         _check(self.lib.gmg_solver_coarse_unknowns(self.h, C.byref(n)))
         return int(n.value)
+
+    def transfer_cells(self):
+        """(cells one host<->device transfer of a level-0 vector grid moves, number of 3D copies): only the bounding rectangles of the
+        active cells of each z-plane travel."""
+        n, k = C.c_int64(), C.c_int64()
+        _check(self.lib.gmg_solver_transfer_cells(self.h, C.byref(n), C.byref(k)))
+        return int(n.value), int(k.value)
 
     def setup_ms(self) -> float:
         ms = C.c_double()

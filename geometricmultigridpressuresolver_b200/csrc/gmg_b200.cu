@@ -532,10 +532,43 @@ static int copyBox3D(gmg_ctx *ctx, T *staging, T *host, const int64_t hostRes[3]
     return GMG_OK;
 }
 
+// The same for the sub-boxes of `groups` only (clipped to [lo, hi); zShift = local storage plane of g's plane 0): the rest of the
+// staging box is not transferred.  Used for vector grids, whose cells outside the groups are 0 on both sides.
 template <typename T>
-static int copyBoxH2D(gmg_ctx *ctx, T *staging, const T *host, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3])
+static int copyGroups3D(gmg_ctx *ctx, T *staging, T *host, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3], bool toDevice,
+			const std::vector<IoGroup> &groups, int zShift)
 {
-    if (isPinnedHost(host)) return copyBox3D(ctx, staging, const_cast<T *>(host), hostRes, g, lo, hi, true);
+    const size_t nx = size_t(hi[0] - lo[0]), ny = size_t(hi[1] - lo[1]);
+    const cudaPitchedPtr hp = make_cudaPitchedPtr(host, size_t(hostRes[0]) * sizeof(T), size_t(hostRes[0]) * sizeof(T), size_t(hostRes[1]));
+    const cudaPitchedPtr dp = make_cudaPitchedPtr(staging, nx * sizeof(T), nx * sizeof(T), ny);
+    for (const IoGroup &q : groups)
+    {
+	const int a0[3] = {std::max(q.x0, lo[0]), std::max(q.y0, lo[1]), std::max(q.z0 - zShift, lo[2])};
+	const int a1[3] = {std::min(q.x1, hi[0]), std::min(q.y1, hi[1]), std::min(q.z1 - zShift, hi[2])};
+	if (a1[0] <= a0[0] || a1[1] <= a0[1] || a1[2] <= a0[2]) continue;
+	cudaMemcpy3DParms p = {};
+	const cudaPos hpos = make_cudaPos(size_t(g.org[0] + a0[0]) * sizeof(T), size_t(g.org[1] + a0[1]), size_t(g.org[2] + a0[2]));
+	const cudaPos dpos = make_cudaPos(size_t(a0[0] - lo[0]) * sizeof(T), size_t(a0[1] - lo[1]), size_t(a0[2] - lo[2]));
+	p.srcPtr = toDevice ? hp : dp;
+	p.srcPos = toDevice ? hpos : dpos;
+	p.dstPtr = toDevice ? dp : hp;
+	p.dstPos = toDevice ? dpos : hpos;
+	p.extent = make_cudaExtent(size_t(a1[0] - a0[0]) * sizeof(T), size_t(a1[1] - a0[1]), size_t(a1[2] - a0[2]));
+	p.kind = toDevice ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+	GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    }
+    return GMG_OK;
+}
+
+template <typename T>
+static int copyBoxH2D(gmg_ctx *ctx, T *staging, const T *host, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3],
+		      const std::vector<IoGroup> *groups = nullptr, int zShift = 0)
+{
+    if (isPinnedHost(host))
+    {
+	if (groups && !groups->empty()) return copyGroups3D(ctx, staging, const_cast<T *>(host), hostRes, g, lo, hi, true, *groups, zShift);
+	return copyBox3D(ctx, staging, const_cast<T *>(host), hostRes, g, lo, hi, true);
+    }
     GMG_TRY(ensurePinned(ctx));
     const int64_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
     const int64_t x0 = g.org[0] + lo[0], y0 = g.org[1] + lo[1], z0 = g.org[2] + lo[2];
@@ -561,9 +594,14 @@ static int copyBoxH2D(gmg_ctx *ctx, T *staging, const T *host, const int64_t hos
     return GMG_OK;
 }
 template <typename T>
-static int copyBoxD2H(gmg_ctx *ctx, T *host, const T *staging, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3])
+static int copyBoxD2H(gmg_ctx *ctx, T *host, const T *staging, const int64_t hostRes[3], const Geom &g, const int lo[3], const int hi[3],
+		      const std::vector<IoGroup> *groups = nullptr, int zShift = 0)
 {
-    if (isPinnedHost(host)) return copyBox3D(ctx, const_cast<T *>(staging), host, hostRes, g, lo, hi, false);
+    if (isPinnedHost(host))
+    {
+	if (groups && !groups->empty()) return copyGroups3D(ctx, const_cast<T *>(staging), host, hostRes, g, lo, hi, false, *groups, zShift);
+	return copyBox3D(ctx, const_cast<T *>(staging), host, hostRes, g, lo, hi, false);
+    }
     GMG_TRY(ensurePinned(ctx));
     const int64_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
     const int64_t x0 = g.org[0] + lo[0], y0 = g.org[1] + lo[1], z0 = g.org[2] + lo[2];
@@ -674,9 +712,12 @@ static int downloadLabels(gmg_ctx *ctx, int32_t *host, const uint8_t *src, const
 }
 
 // host dense grid (hostRes may be a face grid) -> pitched storage, zero where the host has no value
+// groups (only together with maskLabels, which zeroes whatever the untransferred part of the staging box holds): move the
+// active rectangles only
 static int uploadValues(gmg_ctx *ctx, double *dst, const double *host, const int64_t hostRes[3], const Geom &g, const uint8_t *maskLabels = nullptr,
-			const int64_t *bounds = nullptr)
+			const int64_t *bounds = nullptr, const std::vector<IoGroup> *groups = nullptr, int zShift = 0)
 {
+    if (!maskLabels) groups = nullptr;
     int lo[3], hi[3];
     if (!clipBox(g, hostRes, lo, hi, bounds))
     {
@@ -686,7 +727,7 @@ static int uploadValues(gmg_ctx *ctx, double *dst, const double *host, const int
     double *staging = nullptr;
     const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
     GMG_CUDA(devMalloc(&staging, sizeof(double) * cnt));
-    GMG_TRY(copyBoxH2D(ctx, staging, host, hostRes, g, lo, hi));
+    GMG_TRY(copyBoxH2D(ctx, staging, host, hostRes, g, lo, hi, groups, zShift));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_values_from_staging<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dst, staging, maskLabels, boxArgs(g), lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
@@ -697,7 +738,7 @@ static int uploadValues(gmg_ctx *ctx, double *dst, const double *host, const int
 }
 
 static int downloadValues(gmg_ctx *ctx, double *host, const double *src, const int64_t hostRes[3], const Geom &g, bool fillZero,
-			  const int64_t *bounds = nullptr)
+			  const int64_t *bounds = nullptr, const std::vector<IoGroup> *groups = nullptr, int zShift = 0)
 {
     if (fillZero) std::memset(host, 0, sizeof(double) * size_t(hostRes[0]) * hostRes[1] * hostRes[2]);
     int lo[3], hi[3];
@@ -709,7 +750,7 @@ static int downloadValues(gmg_ctx *ctx, double *host, const double *src, const i
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
 	k_values_to_staging<<<unsigned(divUp(cnt, BLOCK)), BLOCK, 0, ctx->stream>>>(staging, src, boxArgs(g), lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
     }
-    GMG_TRY(copyBoxD2H(ctx, host, staging, hostRes, g, lo, hi));
+    GMG_TRY(copyBoxD2H(ctx, host, staging, hostRes, g, lo, hi, groups, zShift));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_CUDA(devFree(staging));
     return GMG_OK;
@@ -913,6 +954,55 @@ static int buildCoefsSparse(gmg_ctx *ctx, Level &L, const double *w0, const doub
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_CUDA(devFree(dw));
+    return GMG_OK;
+}
+
+// Transfer plan of the level-0 vector grids (rhs, initial guess, pressure): per z-plane the bounding rectangle of the active
+// cells, consecutive planes merged into one 3D copy while the merged box stays within 15 % of the planes' own rectangles.
+static int buildIoGroups(gmg_solver *s)
+{
+    s->ioGroups.clear();
+    s->ioCells = 0;
+    static const bool off = [] { const char *e = getenv("GMG_IO_GROUPS"); return e && e[0] == '0'; }();
+    gmg_ctx *ctx = s->ctx;
+    const Level &L = s->lv[0];
+    const Geom &g = L.g;
+    const int nz = g.n[2];
+    if (off || nz == 0) { s->ioCells = g.total; return GMG_OK; }
+    int4 *d = nullptr;
+    GMG_CUDA(devMalloc(&d, sizeof(int4) * nz));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_plane_extents<<<nz, BLOCK, 0, ctx->stream>>>(d, L.labels, g.n[0], g.n[1], g.pitch, g.plane);
+    }
+    std::vector<int4> e(nz);
+    GMG_CUDA(cudaMemcpyAsync(e.data(), d, sizeof(int4) * nz, cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(devFree(d));
+    IoGroup cur = {0, 0, 0, 0, 0, 0};
+    int64_t own = 0;  // sum of the member planes' own rectangle areas
+    auto flush = [&]() {
+	if (cur.z1 > cur.z0) { s->ioGroups.push_back(cur); s->ioCells += int64_t(cur.x1 - cur.x0) * (cur.y1 - cur.y0) * (cur.z1 - cur.z0); }
+	cur.z0 = cur.z1 = 0;
+	own = 0;
+    };
+    for (int z = 0; z < nz; ++z)
+    {
+	const int4 r = e[z];
+	if (r.y <= r.x || r.w <= r.z) { flush(); continue; }
+	const int64_t area = int64_t(r.y - r.x) * (r.w - r.z);
+	if (cur.z1 > cur.z0)
+	{
+	    IoGroup m = cur;
+	    m.x0 = std::min(m.x0, r.x); m.x1 = std::max(m.x1, r.y); m.y0 = std::min(m.y0, r.z); m.y1 = std::max(m.y1, r.w); m.z1 = z + 1;
+	    const int64_t vol = int64_t(m.x1 - m.x0) * (m.y1 - m.y0) * (m.z1 - m.z0);
+	    if (double(vol) <= 1.15 * double(own + area)) { cur = m; own += area; continue; }
+	    flush();
+	}
+	cur = {z, z + 1, r.x, r.y, r.z, r.w};
+	own = area;
+    }
+    flush();
     return GMG_OK;
 }
 
@@ -1903,6 +1993,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int a = 0; a < 3; ++a) devFree(dW[a]);
     lap("bands, records, chunks, grids");
+    if ((st = buildIoGroups(s)) != GMG_OK) return fail(st);
     if ((st = ensureScratch(ctx, maxGrid)) != GMG_OK) return fail(st);
     if (!s->opt.operators_only && (st = buildCoarseSolve(s)) != GMG_OK) return fail(st);
     if ((st = buildFusedCycle(s)) != GMG_OK) return fail(st);
@@ -1972,6 +2063,14 @@ extern "C" int gmg_solver_coarse_unknowns(gmg_solver *s, int64_t *count)
     *count = s->nCoarse;
     return GMG_OK;
 }
+extern "C" int gmg_solver_transfer_cells(gmg_solver *s, int64_t *cells, int64_t *copies)
+{
+    if (!s || !cells) return invalid("null argument");
+    *cells = s->ioCells;
+    if (copies) *copies = s->ioGroups.empty() ? 1 : int64_t(s->ioGroups.size());
+    return GMG_OK;
+}
+
 extern "C" int gmg_solver_setup_ms(gmg_solver *s, double *ms)
 {
     if (!s || !ms) return invalid("null argument");
@@ -2913,13 +3012,13 @@ extern "C" int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInit
     GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY(ensureHostIO(s));
     const Geom &g = s->lv[0].g;
-    if (useInitialGuess) GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels, s->hostBounds));
-    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels, s->hostBounds));
+    if (useInitialGuess) GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels, s->hostBounds, &s->ioGroups));
+    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels, s->hostBounds, &s->ioGroups));
     GMG_TRY(vcycleDevice(s, s->pcgX, s->pcgB, useInitialGuess != 0));
     // cells outside the stored box are non-active: the reference leaves them untouched (0 after constant(0));
     // a sharded context writes the rank's owned planes only
     const Geom go = ownedGeom(s->lv[0]);
-    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, !useInitialGuess, s->hostBounds);
+    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, !useInitialGuess, s->hostBounds, &s->ioGroups, s->lv[0].ownLo);
 }
 
 extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations, double *relResHistory,
@@ -2929,9 +3028,9 @@ extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, in
     GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY(ensureHostIO(s));
     const Geom &g = s->lv[0].g;
-    GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels, s->hostBounds));
-    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels, s->hostBounds));
+    GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels, s->hostBounds, &s->ioGroups));
+    GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels, s->hostBounds, &s->ioGroups));
     GMG_TRY(pcgDevice(s, s->pcgX, s->pcgB, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount));
     const Geom go = ownedGeom(s->lv[0]);
-    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, false, s->hostBounds);
+    return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, false, s->hostBounds, &s->ioGroups, s->lv[0].ownLo);
 }

@@ -99,6 +99,13 @@ struct Level
     int32_t *bpos = nullptr;     // grid: boundary-record index of BOUNDARY cells
 };
 
+// host transfers of level-0 vector grids: groups of consecutive z-planes with the bounding rectangle of their active cells
+// (local storage coordinates, half-open)
+struct IoGroup
+{
+    int z0, z1, x0, x1, y0, y1;
+};
+
 struct ProfileRec
 {
     int klass;
@@ -170,6 +177,8 @@ struct gmg_solver
     // PCG work grids (level 0)
     double *pcgR = nullptr, *pcgP = nullptr, *pcgZ = nullptr, *pcgT = nullptr, *pcgX = nullptr, *pcgB = nullptr;
     double setupMs = 0;
+    std::vector<gmg::IoGroup> ioGroups;  // empty = move the whole box
+    int64_t ioCells = 0;                 // cells one grid transfer moves
     // CUDA-graph cache: a V-cycle is ~100 dependent launches, most of them on tiny coarse levels, so the
     // launch sequence is captured once per (kind, x, b, flag) and replayed
     struct GraphEntry

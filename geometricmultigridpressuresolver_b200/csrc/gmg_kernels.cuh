@@ -1230,6 +1230,31 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef_sparse(double *bcoef, const
     bcoef[int64_t(6) * nBoundary + k] = diag;
 }
 
+// bounding rectangle of the ACTIVE cells of every z-plane: ext[z] = (x0, x1, y0, y1), half-open; x1 <= x0 for an empty plane.
+// Host transfers of vector grids only move these rectangles (everything else in the box is 0 by the vector-grid invariant).
+__global__ void __launch_bounds__(BLOCK) k_plane_extents(int4 *ext, const uint8_t *labels, int n0, int n1, int pitch, int64_t plane)
+{
+    __shared__ int sx0, sx1, sy0, sy1;
+    if (threadIdx.x == 0) { sx0 = n0; sx1 = 0; sy0 = n1; sy1 = 0; }
+    __syncthreads();
+    const uint8_t *p = labels + int64_t(blockIdx.x) * plane;
+    int x0 = n0, x1 = 0, y0 = n1, y1 = 0;
+    for (int i = threadIdx.x; i < n1 * pitch; i += BLOCK)
+    {
+	const int l = p[i];
+	if (l == L_INTERIOR || l == L_BOUNDARY)
+	{
+	    const int y = i / pitch, x = i - y * pitch;
+	    x0 = min(x0, x); x1 = max(x1, x + 1); y0 = min(y0, y); y1 = max(y1, y + 1);
+	}
+    }
+    x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+    y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&sx0, x0); atomicMax(&sx1, x1); atomicMin(&sy0, y0); atomicMax(&sy1, y1); }
+    __syncthreads();
+    if (threadIdx.x == 0) ext[blockIdx.x] = make_int4(sx0, sx1, sy0, sy1);
+}
+
 // chunk flags: bit0 = chunk holds an INTERIOR cell, bit1 = chunk holds an active cell
 __global__ void __launch_bounds__(BLOCK) k_chunk_flags(uint8_t *flagInterior, uint8_t *flagActive, const uint8_t *labels, int chunksPerPlane,
 						      int64_t plane, int nz)

@@ -131,6 +131,10 @@ int gmg_solver_active_cells(gmg_solver *s, int level, int64_t *count); /* over t
 int gmg_solver_shard_info(gmg_solver *s, int level, int *sharded, int64_t *ownLoZ, int64_t *ownHiZ, int64_t *localActive);
 int gmg_solver_coarse_unknowns(gmg_solver *s, int64_t *count);
 int gmg_solver_setup_ms(gmg_solver *s, double *ms);
+/* cells one host<->device transfer of a level-0 vector grid (rhs, initial guess, pressure) moves, and the number of 3D copies it
+   is split into: only the bounding rectangles of the active cells of each z-plane travel (everything else is 0 on both sides,
+   the reference's "vector grids are zero off the active cells" invariant, HDK_GeometricMultigridOperators.h:756) */
+int gmg_solver_transfer_cells(gmg_solver *s, int64_t *cells, int64_t *copies);
 
 /* applyVCycle, HDK_GeometricMultigridPoissonSolver.cpp:420-881: host x (in/out), host b. */
 int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInitialGuess);

@@ -301,3 +301,36 @@ def test_band_smoother_any_sweep_count_matches_oracle(gpu_ctx, port, dom, n, kw)
             want = port.boundary_jacobi(xs.copy(), bs, ll, cells, sweeps, lw)
             assert relerr(X.download(), want) < TOL_OP, (level, sweeps)
     s.close()
+
+
+def test_pinned_host_buffers_move_only_the_active_rectangles(gpu_ctx):
+    """With page-locked caller buffers rhs / x0 / pressure travel as per-z-plane bounding rectangles of the active cells
+    (gmg_solver_transfer_cells); the result must be the one the pageable path (whole box through staging buffers) gives,
+    and cells outside the rectangles must stay untouched on the host."""
+    import torch
+
+    bl, bw, dx = D.flipsplash_domain(48)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    cells, copies = s.transfer_cells()
+    box = np.argwhere(labels != 1)
+    box_cells = int(np.prod(box.max(0) - box.min(0) + 1))
+    assert D.active_mask(labels).sum() <= cells < box_cells and copies >= 1
+    b = D.random_rhs(labels, dx, 5)
+    x0 = 0.25 * D.random_active(labels, 6, scale=dx * dx)
+    x_ref, it_ref, h_ref = s.solveGeometricConjugateGradient(x0, b, 1e-6, 200)
+    rt = torch.cuda.cudart()
+    xp, bp = np.ascontiguousarray(x0.copy()), np.ascontiguousarray(b.copy())
+    for a in (xp, bp):
+        assert int(rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0
+    try:
+        x_pin, it_pin, h_pin = s.solveGeometricConjugateGradient(xp, bp, 1e-6, 200, inplace=True)
+        assert it_pin == it_ref and np.array_equal(h_pin, h_ref) and np.array_equal(x_pin, x_ref)
+        v_ref = s.applyVCycle(np.zeros_like(b), b)
+        xp[...] = 0.0
+        v_pin = s.applyVCycle(xp, bp, inplace=True)
+        assert np.array_equal(v_pin, v_ref)
+    finally:
+        for a in (xp, bp):
+            rt.cudaHostUnregister(a.ctypes.data)
+    s.close()
