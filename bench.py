@@ -103,6 +103,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload, klass):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the class's fine-level kernels, from the committed ncu --set full
+    capture of this workload (profiles/traffic.json names the report); None when that workload was not captured."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(tp))[workload]["bytes_per_launch"].get(klass)
+    except Exception:
+        return None
+
+
 def build_inputs(n):
     base_labels, base_w, dx = D.flipsplash_domain(n)
     return base_labels, base_w, dx
@@ -256,13 +266,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     dom = max(fine, key=lambda k: fine[k][0])
     d_ms, d_n, d_bytes = fine[dom]
     achieved = d_bytes / d_n / (d_ms / d_n * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(dom)
-        except Exception:
-            traffic = None
+    traffic = ncu_traffic(f"pcg{n}", dom)
     kernels = {k: {"ms_per_solve": v[0] / max(1, min(args.steps, 3)), "launches_per_solve": v[1] // max(1, min(args.steps, 3)),
                    "share": v[0] / total_ms,
                    "fine_level_gbs": (prof_fine[k][2] / (prof_fine[k][0] * 1e-3) / 1e9) if prof_fine[k][0] > 0 and prof_fine[k][2] > 0 else None}
@@ -455,7 +459,7 @@ def run_vcycle_sweep(args, rank, world, local_rank):
                        "active_cells": active, "l2": "256 MB flush write before every timed step",
                        "parallelism": "single GPU" if world == 1 else f"{world} z-slabs over NCCL"},
             "vcycle_algorithmic_gbs": vb / (ms * 1e-3) / 1e9, "vcycle_frac_of_hbm_peak": vb / (ms * 1e-3) / 1e9 / peak / world,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(f"vcycle{n}", dom),
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "launches": d_n, "avg_launch_us": d_ms / d_n * 1e3,
                          "algorithmic_bytes_per_launch": d_bytes / d_n},
             "fine_level_kernels": classes, "kernel_timing": "CUDA event nodes inside the replayed V-cycle graph (rank 0's slab when sharded)",
