@@ -2807,7 +2807,13 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
     const double threshold = tol * tol * bb;
     if (rr < threshold) return GMG_OK; // CG.h:60-64
     // p = M^-1 r ; rho = p.r (CG.h:66-87)
-    if (precond) GMG_TRY(vcycleDevice(s, p, r, false));
+    // The first solve of a solver launches its one-off pieces (first preconditioner application, first update) directly: a
+    // solver is typically built, used for ONE solve and destroyed every simulation frame, and capturing + instantiating a
+    // graph that is replayed once costs more than it saves.  From the second solve on they are cached graphs like the rest.
+    if (precond && s->opt.operators_only && s->levels > 1) return invalid("this solver handle was created with operators_only: no coarse factor, no V-cycle");
+    const bool firstSolve = (s->pcgSolves++ == 0) && !ctx->profiling;
+    if (precond && firstSolve) GMG_TRY(vcycleLaunches(s, p, r, false));
+    else if (precond) GMG_TRY(vcycleDevice(s, p, r, false));
     else GMG_TRY((launchVec<VO_COPY>(s, 0, p, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, own)));
     GMG_TRY((reduceOwned<VO_DOT>(s, p, r, offsetof(Scalars, rho), 16.0)));
     // Reference loop (CG.h:100-195): [t = A p, alpha, x += alpha p, r -= alpha t, |r|^2, test] then
@@ -2835,7 +2841,8 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 	}
 	return applyUpdate();
     };
-    GMG_TRY(runGraphed(s, 1, x, nullptr, 0, applyUpdate));
+    if (firstSolve) GMG_TRY(applyUpdate());
+    else GMG_TRY(runGraphed(s, 1, x, nullptr, 0, applyUpdate));
     int iteration = 0;
     for (;;)
     {

@@ -177,6 +177,7 @@ struct gmg_solver
     // PCG work grids (level 0)
     double *pcgR = nullptr, *pcgP = nullptr, *pcgZ = nullptr, *pcgT = nullptr, *pcgX = nullptr, *pcgB = nullptr;
     double setupMs = 0;
+    int64_t pcgSolves = 0;               // solves run on this solver so far
     std::vector<gmg::IoGroup> ioGroups;  // empty = move the whole box
     int64_t ioCells = 0;                 // cells one grid transfer moves
     // CUDA-graph cache: a V-cycle is ~100 dependent launches, most of them on tiny coarse levels, so the
