@@ -2811,7 +2811,8 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
     // solver is typically built, used for ONE solve and destroyed every simulation frame, and capturing + instantiating a
     // graph that is replayed once costs more than it saves.  From the second solve on they are cached graphs like the rest.
     if (precond && s->opt.operators_only && s->levels > 1) return invalid("this solver handle was created with operators_only: no coarse factor, no V-cycle");
-    const bool firstSolve = (s->pcgSolves++ == 0) && !ctx->profiling;
+    // (single GPU only: on a sharded context every exchange stays inside the graphs it was validated in)
+    const bool firstSolve = (s->pcgSolves++ == 0) && !ctx->profiling && ctx->world == 1;
     if (precond && firstSolve) GMG_TRY(vcycleLaunches(s, p, r, false));
     else if (precond) GMG_TRY(vcycleDevice(s, p, r, false));
     else GMG_TRY((launchVec<VO_COPY>(s, 0, p, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, own)));
