@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "gmg_last_error", "gmg_version", "gmg_ctx_create", "gmg_ctx_destroy", "gmg_ctx_synchronize", "gmg_ctx_shard", "gmg_nccl_unique_id", "gmg_ctx_rank", "gmg_shard_plan", "gmg_solver_shard_info", "gmg_comm_count", "gmg_comm_benchmark",
     "gmg_expand_dims", "gmg_expand_labels", "gmg_expand_weights", "gmg_set_boundary_labels", "gmg_coarsen_labels", "gmg_boundary_cells",
     "gmg_solver_default_options", "gmg_solver_create", "gmg_solver_destroy", "gmg_solver_levels", "gmg_solver_level_res",
-    "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms", "gmg_solver_transfer_cells",
+    "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms", "gmg_solver_transfer_cells", "gmg_transfer_plan", "gmg_gather_face_weights",
     "gmg_vcycle", "gmg_pcg", "gmg_grid_create", "gmg_grid_destroy", "gmg_grid_upload", "gmg_grid_download", "gmg_grid_zero", "gmg_grid_copy",
     "gmg_jacobi", "gmg_gauss_seidel", "gmg_boundary_jacobi", "gmg_apply", "gmg_residual", "gmg_restrict", "gmg_prolong_add", "gmg_dot", "gmg_norm2", "gmg_inf_norm",
     "gmg_axpy", "gmg_add_scaled", "gmg_scale", "gmg_vcycle_device", "gmg_pcg_device", "gmg_launch_count", "gmg_timer_begin", "gmg_timer_end",
@@ -48,6 +48,32 @@ def expand_dims(base_shape):
     eres, off, lv = (C.c_int64 * 3)(), (C.c_int64 * 3)(), C.c_int()
     _check(lib.gmg_expand_dims(_res(base_shape), eres, off, C.byref(lv)))
     return (int(eres[2]), int(eres[1]), int(eres[0])), np.array(list(off), dtype=np.int64), int(lv.value)
+
+
+def transfer_plan(extents):
+    """gmg_transfer_plan: extents (planes, 4) = per z-plane (x0, x1, y0, y1) of the active cells -> (groups (k, 6) = (z0, z1, x0, x1, y0, y1),
+    cells they hold).  Host-only, needs no GPU."""
+    lib = load_library()
+    e = np.ascontiguousarray(extents, dtype=np.int32).reshape(-1, 4)
+    groups = np.zeros((max(len(e), 1), 6), dtype=np.int32)
+    n, cells = C.c_int(), C.c_int64()
+    _check(lib.gmg_transfer_plan(e.ctypes.data_as(_i32p), len(e), groups.ctypes.data_as(_i32p), C.byref(n), C.byref(cells)))
+    return groups[: n.value].copy(), int(cells.value)
+
+
+def gather_face_weights(idx, pitch, plane, org, weights, bounds=None):
+    """gmg_gather_face_weights: (6, count) face weights of the cells with storage indices idx in a box of row pitch `pitch`, plane
+    size `plane` and expanded origin org (x, y, z); weights = the three expanded face-weight grids.  Host-only, needs no GPU."""
+    lib = load_library()
+    i = np.ascontiguousarray(idx, dtype=np.int32)
+    w = [np.ascontiguousarray(a, dtype=np.float64) for a in weights]
+    res = [w[0].shape[2] - 1, w[0].shape[1], w[0].shape[0]]
+    out = np.zeros((6, len(i)), dtype=np.float64)
+    b = (C.c_int64 * 6)(*[int(v) for v in bounds]) if bounds is not None else None
+    _check(lib.gmg_gather_face_weights(i.ctypes.data_as(_i32p), C.c_int64(len(i)), int(pitch), C.c_int64(plane), (C.c_int32 * 3)(*[int(v) for v in org]),
+                                       w[0].ctypes.data_as(_f64p), w[1].ctypes.data_as(_f64p), w[2].ctypes.data_as(_f64p),
+                                       (C.c_int64 * 3)(*res), b, out.ctypes.data_as(_f64p)))
+    return out
 
 
 def shard_plan(level_planes, level_shift_z, level_cells, world, max_shard_levels=3, min_cells=1500000):

@@ -939,6 +939,34 @@ static void gatherFaceWeights(const int32_t *idx, double *hw, int64_t nb, Geom g
     });
 }
 
+static FaceLimits faceLimits(const int64_t res[3], const int64_t *bounds)
+{
+    FaceLimits fl;
+    for (int a = 0; a < 3; ++a)
+	for (int c = 0; c < 3; ++c)
+	{
+	    fl.fr[a][c] = res[c] + (c == a ? 1 : 0);
+	    fl.lim[a][c][0] = bounds ? bounds[c] : 0;
+	    fl.lim[a][c][1] = std::min<int64_t>((bounds ? bounds[3 + c] : res[c]) + (c == a ? 1 : 0), fl.fr[a][c]);
+	}
+    return fl;
+}
+
+// Pure host function behind the sparse face weights (no device needed): out[n * count + k] = weight of face n
+// (-x,+x,-y,+y,-z,+z) of the cell with storage index idx[k] in a box of row pitch `pitch`, plane size `plane` and expanded
+// origin org; 0 outside bounds (lo[3], hi[3]; null = the whole grids).  w0/w1/w2 have one more entry along their own axis.
+extern "C" int gmg_gather_face_weights(const int32_t *idx, int64_t count, int pitch, int64_t plane, const int32_t org[3], const double *w0,
+				       const double *w1, const double *w2, const int64_t res[3], const int64_t *bounds, double *out)
+{
+    if (!idx || !org || !w0 || !w1 || !w2 || !res || !out || count < 0 || pitch <= 0 || plane <= 0) return invalid("gmg_gather_face_weights: bad argument");
+    Geom g = {};
+    g.pitch = pitch;
+    g.plane = plane;
+    for (int a = 0; a < 3; ++a) g.org[a] = org[a];
+    gatherFaceWeights(idx, out, count, g, w0, w1, w2, faceLimits(res, bounds));
+    return GMG_OK;
+}
+
 // host gather of the level-0 face weights running beside the rest of the setup (joined by finishCoefsSparse)
 struct CoefJob
 {
@@ -963,14 +991,7 @@ static int buildCoefsSparse(gmg_ctx *ctx, Level &L, const double *w0, const doub
     if (nB == 0) return GMG_OK;
     const Geom &g = L.g;
     GMG_TRY(ensurePinned(ctx));
-    FaceLimits fl;
-    for (int a = 0; a < 3; ++a)
-	for (int c = 0; c < 3; ++c)
-	{
-	    fl.fr[a][c] = res[c] + (c == a ? 1 : 0);
-	    fl.lim[a][c][0] = bounds ? bounds[c] : 0;
-	    fl.lim[a][c][1] = std::min<int64_t>((bounds ? bounds[3 + c] : res[c]) + (c == a ? 1 : 0), fl.fr[a][c]);
-	}
+    const FaceLimits fl = faceLimits(res, bounds);
     // pinned buffer 0 receives the cell indices of a batch, pinned buffer 1 carries its face weights
     const int64_t batch = std::min<int64_t>(int64_t(ctx->pinCap / sizeof(int32_t)), int64_t(ctx->pinCap / (6 * sizeof(double))));
     int32_t *idx = static_cast<int32_t *>(ctx->pin[0]);
@@ -1019,6 +1040,48 @@ static int finishCoefsSparse(gmg_ctx *ctx, Level &L, CoefJob *job)
     return GMG_OK;
 }
 
+// Pure host function behind the transfer plan (no device needed): extents[z] = (x0, x1, y0, y1) of plane z's active cells,
+// half-open, x1 <= x0 for an empty plane.  Consecutive non-empty planes are merged into one box while the merged box holds at
+// most 15 % more cells than the planes' own rectangles; groups[k] = (z0, z1, x0, x1, y0, y1).
+extern "C" int gmg_transfer_plan(const int32_t *extents, int planes, int32_t *groups, int *groupCount, int64_t *cells)
+{
+    if (!extents || !groups || !groupCount || planes < 0) return invalid("gmg_transfer_plan: bad argument");
+    int n = 0;
+    int64_t total = 0;
+    IoGroup cur = {0, 0, 0, 0, 0, 0};
+    int64_t own = 0;  // sum of the member planes' own rectangle areas
+    auto flush = [&]() {
+	if (cur.z1 > cur.z0)
+	{
+	    int32_t *q = groups + size_t(6) * n++;
+	    q[0] = cur.z0; q[1] = cur.z1; q[2] = cur.x0; q[3] = cur.x1; q[4] = cur.y0; q[5] = cur.y1;
+	    total += int64_t(cur.x1 - cur.x0) * (cur.y1 - cur.y0) * (cur.z1 - cur.z0);
+	}
+	cur.z0 = cur.z1 = 0;
+	own = 0;
+    };
+    for (int z = 0; z < planes; ++z)
+    {
+	const int32_t *r = extents + size_t(4) * z;
+	if (r[1] <= r[0] || r[3] <= r[2]) { flush(); continue; }
+	const int64_t area = int64_t(r[1] - r[0]) * (r[3] - r[2]);
+	if (cur.z1 > cur.z0)
+	{
+	    IoGroup m = cur;
+	    m.x0 = std::min(m.x0, r[0]); m.x1 = std::max(m.x1, r[1]); m.y0 = std::min(m.y0, r[2]); m.y1 = std::max(m.y1, r[3]); m.z1 = z + 1;
+	    const int64_t vol = int64_t(m.x1 - m.x0) * (m.y1 - m.y0) * (m.z1 - m.z0);
+	    if (double(vol) <= 1.15 * double(own + area)) { cur = m; own += area; continue; }
+	    flush();
+	}
+	cur = {z, z + 1, r[0], r[1], r[2], r[3]};
+	own = area;
+    }
+    flush();
+    *groupCount = n;
+    if (cells) *cells = total;
+    return GMG_OK;
+}
+
 // Transfer plan of the level-0 vector grids (rhs, initial guess, pressure): per z-plane the bounding rectangle of the active
 // cells, consecutive planes merged into one 3D copy while the merged box stays within 15 % of the planes' own rectangles.
 static int buildIoGroups(gmg_solver *s)
@@ -1041,30 +1104,14 @@ static int buildIoGroups(gmg_solver *s)
     GMG_CUDA(cudaMemcpyAsync(e.data(), d, sizeof(int4) * nz, cudaMemcpyDeviceToHost, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_CUDA(devFree(d));
-    IoGroup cur = {0, 0, 0, 0, 0, 0};
-    int64_t own = 0;  // sum of the member planes' own rectangle areas
-    auto flush = [&]() {
-	if (cur.z1 > cur.z0) { s->ioGroups.push_back(cur); s->ioCells += int64_t(cur.x1 - cur.x0) * (cur.y1 - cur.y0) * (cur.z1 - cur.z0); }
-	cur.z0 = cur.z1 = 0;
-	own = 0;
-    };
-    for (int z = 0; z < nz; ++z)
+    std::vector<int32_t> groups(size_t(6) * nz);
+    int nGroups = 0;
+    GMG_TRY(gmg_transfer_plan(reinterpret_cast<const int32_t *>(e.data()), nz, groups.data(), &nGroups, &s->ioCells));
+    for (int k = 0; k < nGroups; ++k)
     {
-	const int4 r = e[z];
-	if (r.y <= r.x || r.w <= r.z) { flush(); continue; }
-	const int64_t area = int64_t(r.y - r.x) * (r.w - r.z);
-	if (cur.z1 > cur.z0)
-	{
-	    IoGroup m = cur;
-	    m.x0 = std::min(m.x0, r.x); m.x1 = std::max(m.x1, r.y); m.y0 = std::min(m.y0, r.z); m.y1 = std::max(m.y1, r.w); m.z1 = z + 1;
-	    const int64_t vol = int64_t(m.x1 - m.x0) * (m.y1 - m.y0) * (m.z1 - m.z0);
-	    if (double(vol) <= 1.15 * double(own + area)) { cur = m; own += area; continue; }
-	    flush();
-	}
-	cur = {z, z + 1, r.x, r.y, r.z, r.w};
-	own = area;
+	const int32_t *q = groups.data() + size_t(6) * k;
+	s->ioGroups.push_back({q[0], q[1], q[2], q[3], q[4], q[5]});
     }
-    flush();
     return GMG_OK;
 }
 

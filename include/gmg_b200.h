@@ -135,6 +135,15 @@ int gmg_solver_setup_ms(gmg_solver *s, double *ms);
    is split into: only the bounding rectangles of the active cells of each z-plane travel (everything else is 0 on both sides,
    the reference's "vector grids are zero off the active cells" invariant, HDK_GeometricMultigridOperators.h:756) */
 int gmg_solver_transfer_cells(gmg_solver *s, int64_t *cells, int64_t *copies);
+/* the pure host function behind that plan (no device needed): extents[z] = (x0, x1, y0, y1), half-open, of the active cells of
+   plane z (x1 <= x0: empty plane); groups[k] = (z0, z1, x0, x1, y0, y1), at most `planes` of them; cells = cells the groups hold */
+int gmg_transfer_plan(const int32_t *extents, int planes, int32_t *groups, int *groupCount, int64_t *cells);
+/* the pure host function behind the constructor's sparse face weights (no device needed; the weight grids of
+   buildExpandedBoundaryWeights, HDK_GeometricMultigridOperators.h:1458-1572, are read where they lie): out[n * count + k] = weight
+   of face n (-x,+x,-y,+y,-z,+z) of the cell with storage index idx[k] in a box of row pitch `pitch`, plane size `plane` and
+   expanded origin org; 0 outside bounds = (lo[3], hi[3]) (null: the whole grids) */
+int gmg_gather_face_weights(const int32_t *idx, int64_t count, int pitch, int64_t plane, const int32_t org[3], const double *w0, const double *w1,
+			    const double *w2, const int64_t res[3], const int64_t *bounds, double *out);
 
 /* applyVCycle, HDK_GeometricMultigridPoissonSolver.cpp:420-881: host x (in/out), host b. */
 int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInitialGuess);

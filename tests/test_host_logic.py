@@ -56,3 +56,84 @@ def test_rhs_builders_respect_the_zero_invariant(port):
     exp, we, off, lv = port.expand_domain(labels, w)
     for b in (D.random_rhs(exp, dx), D.delta_rhs(exp, [int(off[0]) + 12] * 3, dx), D.random_active(exp, 3)):
         assert b.any() and not b[~D.active_mask(exp)].any()
+
+
+def _plane_extents(active):
+    """(planes, 4) bounding rectangles (x0, x1, y0, y1) of a (z, y, x) boolean mask, as k_plane_extents produces them."""
+    ext = np.zeros((active.shape[0], 4), dtype=np.int32)
+    for z in range(active.shape[0]):
+        ys, xs = np.nonzero(active[z])
+        ext[z] = (xs.min(), xs.max() + 1, ys.min(), ys.max() + 1) if len(xs) else (active.shape[2], 0, active.shape[1], 0)
+    return ext
+
+
+@pytest.mark.parametrize("name", ["flipsplash", "sphere", "narrow_band", "liquid_box"])
+def test_transfer_plan_covers_every_active_cell_and_little_else(name):
+    """gmg_transfer_plan (pure host): the groups tile the non-empty planes in order, every active cell lies inside its plane's
+    group, and merging never inflates a group beyond 15 % of its members' own rectangles."""
+    labels, w, dx = D.DOMAINS[name](32)
+    active = labels == D.INTERIOR
+    ext = _plane_extents(active)
+    groups, cells = api.transfer_plan(ext)
+    assert cells == sum(int(g[1] - g[0]) * int(g[3] - g[2]) * int(g[5] - g[4]) for g in groups)
+    assert active.sum() <= cells <= active.size
+    covered = np.zeros_like(active)
+    last = 0
+    for z0, z1, x0, x1, y0, y1 in groups:
+        assert z0 >= last and z1 > z0 and x1 > x0 and y1 > y0
+        last = z1
+        covered[z0:z1, y0:y1, x0:x1] = True
+        own = sum(int(e[1] - e[0]) * int(e[3] - e[2]) for e in ext[z0:z1])
+        assert all(e[1] > e[0] for e in ext[z0:z1])  # no empty plane inside a group
+        assert (z1 - z0) * (x1 - x0) * (y1 - y0) <= 1.15 * own + 1e-9
+    assert covered[active].all()
+    empty = np.nonzero(ext[:, 1] <= ext[:, 0])[0]
+    assert not covered[empty].any()
+
+
+def test_transfer_plan_edge_cases():
+    groups, cells = api.transfer_plan(np.zeros((0, 4), dtype=np.int32))
+    assert len(groups) == 0 and cells == 0
+    groups, cells = api.transfer_plan(np.array([[5, 0, 5, 0]] * 3, dtype=np.int32))  # all planes empty
+    assert len(groups) == 0 and cells == 0
+    ext = np.array([[2, 6, 1, 4], [2, 6, 1, 4], [9, 0, 9, 0], [0, 40, 0, 40], [10, 12, 10, 12]], dtype=np.int32)
+    groups, cells = api.transfer_plan(ext)
+    # identical planes merge; the empty plane splits; a tiny rectangle is not merged into a huge one (it would waste > 15 %)
+    assert groups.tolist() == [[0, 2, 2, 6, 1, 4], [3, 4, 0, 40, 0, 40], [4, 5, 10, 12, 10, 12]]
+    assert cells == 2 * 12 + 1600 + 4
+
+
+def test_gather_face_weights_matches_direct_indexing():
+    """gmg_gather_face_weights (pure host, what the constructor runs beside the hierarchy build): the six face weights of a cell
+    list, read where the caller's expanded weight grids lie, 0 outside the hint box (+1 on a face's own axis)."""
+    rng = np.random.default_rng(3)
+    res = (20, 18, 16)  # x, y, z
+    w = [rng.random((res[2] + (a == 2), res[1] + (a == 1), res[0] + (a == 0))) for a in range(3)]
+    org, n = (4, 2, 6), (12, 10, 8)  # a storage box inside the grid
+    pitch, plane = 16, 16 * n[1]
+    cells = np.array([(x, y, z) for z in range(1, n[2] - 1) for y in range(1, n[1] - 1) for x in range(1, n[0] - 1)])
+    cells = cells[rng.permutation(len(cells))[:300]]
+    idx = cells[:, 2] * plane + cells[:, 1] * pitch + cells[:, 0]
+
+    def expect(bounds):
+        out = np.zeros((6, len(cells)))
+        for k, (x, y, z) in enumerate(cells):
+            e = np.array([x + org[0], y + org[1], z + org[2]])
+            for f in range(6):
+                a = f >> 1
+                p = e.copy()
+                p[a] += f & 1
+                lo = np.array(bounds[:3]) if bounds is not None else np.zeros(3, dtype=int)
+                hi = np.array(bounds[3:]) if bounds is not None else np.array(res)
+                hi = hi.copy()
+                hi[a] += 1
+                if (p >= lo).all() and (p < hi).all():
+                    out[f, k] = w[a][p[2], p[1], p[0]]
+        return out
+
+    got = api.gather_face_weights(idx, pitch, plane, org, w)
+    assert np.array_equal(got, expect(None))
+    bounds = (6, 4, 8, 13, 10, 12)  # a hint box cutting through the cell list
+    got = api.gather_face_weights(idx, pitch, plane, org, w, bounds)
+    want = expect(bounds)
+    assert np.array_equal(got, want) and (want == 0).any() and (want != 0).any()
