@@ -115,7 +115,10 @@ typedef struct gmg_solver_options
 void gmg_solver_default_options(gmg_solver_options *opt);
 
 /* GeometricMultigridPoissonSolver::GeometricMultigridPoissonSolver, HDK_GeometricMultigridPoissonSolver.cpp:135-418.
- * Deep-copies labels and weights to the device, builds per-level labels, boundary bands and the coarse factor.
+ * Copies what it needs to the device (the labels of the non-EXTERIOR box; of the weights only the six face weights of every
+ * level-0 BOUNDARY cell, gathered on the host: nothing else reads a face weight, Ops.h:208-255) -- the host grids may be freed
+ * when the call returns, as with the reference's deep copies (MG.cpp:164-180) --, builds per-level labels, boundary bands and
+ * the coarse factor.
  * w0 = w1 = w2 = NULL is the reference's `boundaryWeights == nullptr` operator form (weight 1, Ops.h:237-248). */
 int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], const double *w0, const double *w1,
 		      const double *w2, int mgLevels, const gmg_solver_options *opt, gmg_solver **out);
