@@ -1,4 +1,4 @@
-# usage: bash scripts/_run_mgpu.sh N tag [sweep]
+# usage (from the repo root): bash scripts/gpurun_calls/_run_mgpu.sh N tag [sweep]
 N=$1; TAG=$2; SWEEP=$3
 set -x
 mkdir -p gpurun_out
