@@ -141,7 +141,13 @@ static cudaError_t launchK(void (*kernel)(KArgs...), unsigned grid, unsigned blo
 #define TRACE(msg) do { if (getenv("GMG_TRACE")) { fprintf(stderr, "[gmg] %s:%d %s\n", __func__, __LINE__, msg); fflush(stderr); } } while (0)
 
 static void p2pRelease(gmg_ctx *ctx);
+static int p2pCheckError(gmg_ctx *ctx);
 static double *scalarPtr(gmg_solver *s, size_t offset);
+static void dropGraphs(gmg_solver *s)
+{
+    for (auto &g : s->graphs) { cudaGraphExecDestroy(g.second.exec); cudaGraphDestroy(g.second.graph); }
+    s->graphs.clear();
+}
 
 static int invalid(const char *msg)
 {
@@ -180,7 +186,12 @@ static void flushProfile(gmg_ctx *ctx)
 static int ensureScratch(gmg_ctx *ctx, int nPartials)
 {
     if (nPartials <= ctx->maxPartials) return GMG_OK;
-    if (ctx->partials) cudaFree(ctx->partials);
+    // Reduction kernels captured in the cached graphs of solvers that are still alive hold the old pointer as a kernel
+    // argument: the outgrown buffer is retired (freed with the context), never freed here.  Solvers of one context run
+    // one after the other on its stream, so sharing a buffer between them is safe; an old graph keeps using the smaller
+    // buffer, which was sized for that solver's own grids.
+    if (ctx->partials) ctx->retired.push_back(ctx->partials);
+    ctx->partials = nullptr;
     ctx->maxPartials = nPartials + 1024;
     GMG_CUDA(cudaMalloc(&ctx->partials, sizeof(double) * ctx->maxPartials));
     return GMG_OK;
@@ -192,6 +203,7 @@ static int ensureScratch(gmg_ctx *ctx, int nPartials)
 extern "C" const char *gmg_last_error(void) { return g_lastError.c_str(); }
 extern "C" int gmg_version(void) { return 100; }
 
+extern "C" int gmg_ctx_destroy(gmg_ctx *ctx);
 extern "C" int gmg_ctx_create(int device, void *stream, gmg_ctx **out)
 {
     if (!out) return invalid("gmg_ctx_create: out is null");
@@ -206,30 +218,42 @@ extern "C" int gmg_ctx_create(int device, void *stream, gmg_ctx **out)
     GMG_CUDA(cudaSetDevice(device));
     gmg_ctx *ctx = new gmg_ctx;
     ctx->device = device;
-    if (stream) ctx->stream = static_cast<cudaStream_t>(stream);
-    else
+    // every failure below goes through gmg_ctx_destroy, which frees whatever was created so far
+    auto build = [&]() -> int {
+	if (stream) ctx->stream = static_cast<cudaStream_t>(stream);
+	else
+	{
+	    GMG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	    ctx->ownStream = true;
+	}
+	g_stream = ctx->stream;
+	{
+	    cudaMemPool_t pool;
+	    GMG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+	    uint64_t threshold = UINT64_MAX;
+	    GMG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+	}
+	cudaDeviceProp prop;
+	GMG_CUDA(cudaGetDeviceProperties(&prop, device));
+	ctx->smCount = prop.multiProcessorCount;
+	GMG_CUDA(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
+	GMG_CUDA(cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
+	GMG_CUDA(cudaMalloc(&ctx->scalars, sizeof(Scalars)));
+	GMG_CUDA(cudaMemset(ctx->scalars, 0, sizeof(Scalars)));
+	GMG_CUDA(cudaMallocHost(&ctx->hostScalars, sizeof(Scalars)));
+	GMG_CUDA(cudaEventCreate(&ctx->t0));
+	GMG_CUDA(cudaEventCreate(&ctx->t1));
+	GMG_TRY(ensureScratch(ctx, 4096));
+	return GMG_OK;
+    };
+    const int st = build();
+    if (st != GMG_OK)
     {
-	GMG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-	ctx->ownStream = true;
+	const std::string why = g_lastError;
+	gmg_ctx_destroy(ctx);
+	g_lastError = why;
+	return st;
     }
-    g_stream = ctx->stream;
-    {
-	cudaMemPool_t pool;
-	GMG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-	uint64_t threshold = UINT64_MAX;
-	GMG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-    }
-    cudaDeviceProp prop;
-    GMG_CUDA(cudaGetDeviceProperties(&prop, device));
-    ctx->smCount = prop.multiProcessorCount;
-    GMG_CUDA(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
-    GMG_CUDA(cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
-    GMG_CUDA(cudaMalloc(&ctx->scalars, sizeof(Scalars)));
-    GMG_CUDA(cudaMemset(ctx->scalars, 0, sizeof(Scalars)));
-    GMG_CUDA(cudaMallocHost(&ctx->hostScalars, sizeof(Scalars)));
-    GMG_CUDA(cudaEventCreate(&ctx->t0));
-    GMG_CUDA(cudaEventCreate(&ctx->t1));
-    GMG_TRY(ensureScratch(ctx, 4096));
     *out = ctx;
     return GMG_OK;
 }
@@ -238,21 +262,23 @@ extern "C" int gmg_ctx_destroy(gmg_ctx *ctx)
 {
     if (!ctx) return GMG_OK;
     enterCtx(ctx);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     flushProfile(ctx);
     for (auto e : ctx->eventPool) cudaEventDestroy(e);
     p2pRelease(ctx);
     if (ctx->nccl)
 	if (const NcclApi *api = ncclApi(nullptr)) api->CommDestroy(static_cast<NcclComm>(ctx->nccl));
     cudaFree(ctx->partials);
+    for (void *p : ctx->retired) cudaFree(p);
     cudaFree(ctx->ticket);
     cudaFree(ctx->scalars);
     cudaFreeHost(ctx->hostScalars);
     for (int i = 0; i < 2; ++i)
 	if (ctx->pin[i]) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pinEv[i]); }
-    cudaEventDestroy(ctx->t0);
-    cudaEventDestroy(ctx->t1);
-    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
     delete ctx;
     return GMG_OK;
 }
@@ -261,7 +287,7 @@ extern "C" int gmg_ctx_synchronize(gmg_ctx *ctx)
 {
     if (!ctx) return invalid("null ctx");
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    return GMG_OK;
+    return p2pCheckError(ctx);
 }
 
 // ---- NCCL, bound at run time (gmg_nccl.h) ----------------------------------------------------------
@@ -348,6 +374,12 @@ extern "C" int gmg_ctx_shard(gmg_ctx *ctx, int rank, int world, const void *nccl
     // one tiny all-reduce now: connection setup happens outside any later stream capture
     GMG_NCCL(api->AllReduce(ctx->scalars, ctx->scalars, 1, NCCL_FLOAT64, NCCL_SUM, comm, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaMemsetAsync(ctx->scalars, 0, sizeof(Scalars), ctx->stream));
+    if (const char *e = getenv("GMG_P2P_TIMEOUT_S"))
+    {
+	const unsigned long long ns = (unsigned long long)(std::max(1.0, atof(e)) * 1e9);
+	GMG_CUDA(cudaMemcpyToSymbol(g_p2pTimeoutNs, &ns, sizeof(ns)));
+    }
     return GMG_OK;
 }
 extern "C" int gmg_ctx_rank(gmg_ctx *ctx, int *rank, int *world)
@@ -1717,6 +1749,23 @@ static int p2pEnsure(gmg_solver *s)
     if (ctx->world > P2P_MAX_WORLD || s->shardLevels > P2P_MAX_LEVELS) { ctx->p2pDisabled = true; return GMG_OK; }
     const NcclApi *api = ncclApi(nullptr);
     NcclComm comm = static_cast<NcclComm>(ctx->nccl);
+    // Box capacities only ever grow within a context: ONE layout per arena generation, shared by every live solver, so two
+    // solvers of different sizes can never disagree about where a mailbox lives (a solver's planes just fill part of a box).
+    size_t needHalo[P2P_MAX_LEVELS] = {0, 0, 0, 0};
+    for (int l = 0; l < s->shardLevels; ++l) needHalo[l] = sizeof(double) * size_t(l == 0 ? HALO_STORE0 : HALO_STORE) * size_t(s->lv[l].g.plane);
+    const size_t needGather = sizeof(double) * size_t(s->lv[s->shardLevels].g.total);
+    P2pState *st = static_cast<P2pState *>(ctx->p2p);
+    bool fits = st != nullptr;
+    for (int l = 0; fits && l < P2P_MAX_LEVELS; ++l) fits = needHalo[l] <= st->haloCap[l];
+    if (fits && needGather <= st->gatherCap)
+    {
+	s->p2pGeneration = st->generation;
+	return GMG_OK;
+    }
+    size_t capHalo[P2P_MAX_LEVELS], capGather;
+    auto grow = [](size_t need, size_t have) { return need <= have ? have : ((need + (need >> 2) + 255) & ~size_t(255)); };  // head-room: the next frame's boxes differ by a few planes
+    for (int l = 0; l < P2P_MAX_LEVELS; ++l) capHalo[l] = grow(needHalo[l], st ? st->haloCap[l] : 0);
+    capGather = grow(needGather, st ? st->gatherCap : 0);
     P2pLayout lay;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
@@ -1724,26 +1773,16 @@ static int p2pEnsure(gmg_solver *s)
     lay.scalars = take(sizeof(double) * 2 * P2P_MAX_WORLD);
     for (int l = 0; l < P2P_MAX_LEVELS; ++l)
 	for (int d = 0; d < 2; ++d)
-	    for (int k = 0; k < 2; ++k)
-	    {
-		lay.halo[l][d][k] = 0;
-		if (l < s->shardLevels) lay.halo[l][d][k] = take(sizeof(double) * size_t(l == 0 ? HALO_STORE0 : HALO_STORE) * size_t(s->lv[l].g.plane));
-	    }
-    for (int k = 0; k < 2; ++k) lay.gather[k] = take(sizeof(double) * size_t(s->lv[s->shardLevels].g.total));
+	    for (int k = 0; k < 2; ++k) lay.halo[l][d][k] = take(capHalo[l]);
+    for (int k = 0; k < 2; ++k) lay.gather[k] = take(capGather);
     lay.bytes = off;
-    P2pState *st = static_cast<P2pState *>(ctx->p2p);
-    if (st && st->layout.bytes >= lay.bytes)
-    {
-	const size_t have = st->layout.bytes;
-	st->layout = lay;
-	st->layout.bytes = have;
-	s->p2pGeneration = st->generation;
-	return GMG_OK;
-    }
     // (re)build: everybody drains, frees, allocates, exchanges IPC handles
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_NCCL(api->AllReduce(ctx->scalars, ctx->scalars, 1, NCCL_FLOAT64, NCCL_SUM, comm, ctx->stream));  // barrier
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    // cached graphs of the solvers that are still alive point into the arenas about to be freed: drop them (they are
+    // re-captured against the new arenas on their next use; the grown layout holds every older solver's planes too)
+    for (gmg_solver *o : ctx->solvers) dropGraphs(o);
     p2pRelease(ctx);
     st = new P2pState;
     st->rank = ctx->rank;
@@ -1751,7 +1790,8 @@ static int p2pEnsure(gmg_solver *s)
     st->generation = ++ctx->p2pGenerations;
     s->p2pGeneration = st->generation;
     st->layout = lay;
-    st->layout.bytes = std::max<size_t>(lay.bytes + (lay.bytes >> 2), size_t(64) << 20);  // head-room: the next frame's boxes differ by a few planes
+    for (int l = 0; l < P2P_MAX_LEVELS; ++l) st->haloCap[l] = capHalo[l];
+    st->gatherCap = capGather;
     int ok = 1;
     cudaIpcMemHandle_t mine;
     std::vector<cudaIpcMemHandle_t> all(ctx->world);
@@ -1816,10 +1856,11 @@ static int p2pCheckError(gmg_ctx *ctx)
     return GMG_OK;
 }
 
+// the context's arenas, for a solver whose planes were sized into them (capacities never shrink, so any generation will do)
 static P2pState *p2pOf(gmg_solver *s)
 {
     P2pState *st = static_cast<P2pState *>(s->ctx->p2p);
-    return (st && st->generation == s->p2pGeneration) ? st : nullptr;
+    return (st && s->p2pGeneration >= 0) ? st : nullptr;
 }
 
 struct ZRange { int lo, hi; };
@@ -1966,7 +2007,11 @@ extern "C" int gmg_solver_destroy(gmg_solver *s)
     if (!s) return GMG_OK;
     enterCtx(s->ctx);
     cudaStreamSynchronize(s->ctx->stream);
-    for (auto &g : s->graphs) { cudaGraphExecDestroy(g.second.exec); cudaGraphDestroy(g.second.graph); }
+    dropGraphs(s);
+    {
+	auto &v = s->ctx->solvers;
+	v.erase(std::remove(v.begin(), v.end(), s), v.end());
+    }
     devFree(s->coarseIdx); devFree(s->coarseInv); devFree(s->compactBlob);
     delete static_cast<CompactArgs *>(s->compactArgs);
     if (!s->lv.empty())
@@ -1995,6 +2040,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     const double tStart = nowMs();
     gmg_solver *s = new gmg_solver;
     s->ctx = ctx;
+    ctx->solvers.push_back(s);
     if (optIn) s->opt = *optIn;
     else gmg_solver_default_options(&s->opt);
     if (const char *e = getenv("GMG_NO_GRAPHS")) s->useGraphs = !(e[0] == '1');
@@ -2003,6 +2049,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel && ctx->world > 1)
     {
+	ctx->solvers.pop_back();
 	delete s;
 	return invalid("gmg_solver_create: the tiled Gauss-Seidel smoother is not available on a sharded context (its in-tile dependencies reach 16 "
 		       "cells, beyond the deep halo); use the damped-Jacobi smoother there");
@@ -2119,7 +2166,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
 	    if ((st = allocGrid(&L.b, L.g)) != GMG_OK) return fail(st);
 	}
     }
-    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(cudaFail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__));
     for (int a = 0; a < 3; ++a) devFree(dW[a]);
     lap("bands, records, chunks, grids");
     if ((st = buildIoGroups(s)) != GMG_OK) return fail(st);
@@ -2142,7 +2189,7 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     }
     if ((st = finishCoefsSparse(ctx, s->lv[0], &coefJob)) != GMG_OK) return fail(st);
     lap("level 0 coefficient records (join)");
-    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(cudaFail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__));
     s->setupMs = nowMs() - tStart;
     *out = s;
     return GMG_OK;
@@ -2770,11 +2817,7 @@ static int runGraphed(gmg_solver *s, int kind, const void *p0, const void *p1, i
     auto it = s->graphs.find(key);
     if (it == s->graphs.end())
     {
-	if (s->graphs.size() >= 16)
-	{
-	    for (auto &g : s->graphs) { cudaGraphExecDestroy(g.second.exec); cudaGraphDestroy(g.second.graph); }
-	    s->graphs.clear();
-	}
+	if (s->graphs.size() >= 16) dropGraphs(s);
 	gmg_solver::GraphEntry e;
 	const int64_t before = ctx->launches, commBefore = ctx->commOps;
 	if (prof) flushProfile(ctx);
@@ -2854,6 +2897,13 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
     GMG_TRY(readScalar(s, offsetof(Scalars, rr), &rr));
     const double threshold = tol * tol * bb;
     if (rr < threshold) return GMG_OK; // CG.h:60-64
+    if (maxIt <= 0)
+    {
+	// CG.h:100: the loop body never runs -- x is left untouched and the index printed at CG.h:198 is 0 (the reference
+	// still applies the preconditioner once for a search direction nobody uses; that has no visible effect)
+	if (iterations) *iterations = 0;
+	return GMG_OK;
+    }
     // p = M^-1 r ; rho = p.r (CG.h:66-87)
     // The first solve of a solver launches its one-off pieces (first preconditioner application, first update) directly: a
     // solver is typically built, used for ONE solve and destroyed every simulation frame, and capturing + instantiating a
@@ -2925,6 +2975,7 @@ extern "C" int gmg_grid_create(gmg_solver *s, int level, gmg_grid **out)
 extern "C" int gmg_grid_destroy(gmg_grid *g)
 {
     if (!g) return GMG_OK;
+    enterCtx(g->solver->ctx);  // the free is ordered on THIS context's stream, behind the work that still uses the grid
     if (g->d) devFree(g->d - g->plane);
     delete g;
     return GMG_OK;
@@ -2952,17 +3003,20 @@ extern "C" int gmg_grid_download(gmg_grid *g, double *host)
     GMG_CUDA(enterCtx(g->solver->ctx));
     const Level &L = g->solver->lv[g->level];
     const Geom go = ownedGeom(L);
-    return downloadValues(g->solver->ctx, host, g->d + int64_t(L.ownLo) * L.g.plane, go.res, go, true);
+    GMG_TRY(downloadValues(g->solver->ctx, host, g->d + int64_t(L.ownLo) * L.g.plane, go.res, go, true));
+    return p2pCheckError(g->solver->ctx);  // sticky: a timed-out exchange anywhere before this download
 }
 extern "C" int gmg_grid_zero(gmg_grid *g)
 {
     if (!g) return invalid("null argument");
+    GMG_CUDA(enterCtx(g->solver->ctx));
     GMG_CUDA(cudaMemsetAsync(g->d, 0, sizeof(double) * g->solver->lv[g->level].g.total, g->solver->ctx->stream));
     return GMG_OK;
 }
 extern "C" int gmg_grid_copy(gmg_grid *dst, const gmg_grid *src)
 {
     if (!dst || !src || dst->level != src->level || dst->solver != src->solver) return invalid("gmg_grid_copy: grids differ in level");
+    GMG_CUDA(enterCtx(dst->solver->ctx));
     GMG_CUDA(cudaMemcpyAsync(dst->d, src->d, sizeof(double) * dst->solver->lv[dst->level].g.total, cudaMemcpyDeviceToDevice, dst->solver->ctx->stream));
     return GMG_OK;
 }

@@ -116,6 +116,7 @@ struct ProfileRec
 
 } // namespace gmg
 
+struct gmg_solver;
 struct gmg_ctx
 {
     int device = 0;
@@ -142,8 +143,10 @@ struct gmg_ctx
     void *p2p = nullptr;          // gmg::P2pState: peer-memory mailboxes (gmg_p2p.cuh); null = NCCL for every exchange
     bool p2pDisabled = false;
     int p2pGenerations = 0;
+    std::vector<gmg_solver *> solvers;  // live solvers of this context (their cached graphs are dropped when the arenas are re-mapped)
     // reduction scratch
     double *partials = nullptr;   // [maxPartials]
+    std::vector<void *> retired;  // outgrown scratch buffers that cached graphs of live solvers may still reference
     unsigned *ticket = nullptr;
     double *scalars = nullptr;    // device scalars (see Scalars)
     double *hostScalars = nullptr; // pinned mirror

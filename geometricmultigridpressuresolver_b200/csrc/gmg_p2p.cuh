@@ -19,7 +19,17 @@ namespace gmg
 constexpr int P2P_MAX_WORLD = 16;
 constexpr int P2P_MAX_LEVELS = 4;
 constexpr int P2P_CTAS = 128;              // every CTA must be resident at once (they wait on each other's flags)
-constexpr long long P2P_SPIN_LIMIT = 20000000LL;   // ~10 s of polling, then give up loudly instead of hanging the GPU
+// A rank that waits longer than this for a neighbour gives up loudly instead of hanging the GPU: the error word becomes
+// sticky, the stale mailbox is NOT copied and the channel's sequence number is NOT advanced.  Wall-clock (%globaltimer), so
+// legitimate skew between the ranks' host threads (first-use graph instantiation, a slow upload) is covered; GMG_P2P_TIMEOUT_S
+// overrides the default at gmg_ctx_shard time.
+__device__ unsigned long long g_p2pTimeoutNs = 120ull * 1000000000ull;
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // layout of one rank's arena (identical on every rank)
 struct P2pLayout
@@ -40,7 +50,9 @@ struct P2pState
 {
     int rank = 0, world = 1;
     int generation = 0;                          // bumped whenever the arenas are re-allocated (older solvers' graphs point into freed memory)
-    P2pLayout layout;
+    P2pLayout layout;                            // ONE layout per generation, shared by every solver of the context
+    size_t haloCap[P2P_MAX_LEVELS] = {0, 0, 0, 0};  // bytes one slot of a level's halo boxes holds; capacities only grow
+    size_t gatherCap = 0;
     char *arena = nullptr;                       // mine
     char *peer[P2P_MAX_WORLD] = {nullptr};       // peers' arenas mapped into this process (peer[rank] == arena)
     // local (not shared) counters: sequence numbers per channel, CTA tickets, error word
@@ -59,16 +71,28 @@ __device__ __forceinline__ void stReleaseSys(unsigned long long *p, unsigned lon
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// thread 0 polls, the CTA follows
-__device__ __forceinline__ void waitFlag(const unsigned long long *flag, unsigned long long want, int *error)
+// one thread polls; false after the timeout (or when an earlier exchange already failed: the error is sticky)
+__device__ __forceinline__ bool pollFlag(const unsigned long long *flag, unsigned long long want, int *error)
 {
-    if (threadIdx.x == 0)
+    if (ldAcquireSys(flag) >= want) return true;
+    if (*reinterpret_cast<volatile int *>(error)) return false;
+    const unsigned long long t0 = globalTimerNs();
+    unsigned spins = 0;
+    while (ldAcquireSys(flag) < want)
     {
-	long long spins = 0;
-	while (ldAcquireSys(flag) < want)
-	    if (++spins > P2P_SPIN_LIMIT) { atomicExch(error, 1); break; }
+	if ((++spins & 1023u) == 0 && globalTimerNs() - t0 > g_p2pTimeoutNs) { atomicExch(error, 1); return false; }
     }
+    return true;
+}
+// thread 0 polls, the CTA follows; returns whether the data arrived
+__device__ __forceinline__ bool waitFlag(const unsigned long long *flag, unsigned long long want, int *error)
+{
+    __shared__ int arrived;
+    if (threadIdx.x == 0) arrived = pollFlag(flag, want, error) ? 1 : 0;
     __syncthreads();
+    const bool ok = arrived != 0;
+    __syncthreads();
+    return ok;
 }
 // all CTAs of the grid have passed this point once the returned value is true in the last one (one ticket per phase).
 // The CTA barrier orders every thread's stores before thread 0's fence (the pattern of a cooperative grid sync), so one
@@ -130,19 +154,19 @@ __global__ void __launch_bounds__(256) k_halo_p2p(const HaloP2pArgs a)
     }
     if (a.hasLower)
     {
-	waitFlag(a.myFlagLower + slot, seq, a.error);
-	copyPlanes(a.grid + int64_t(a.ownLo - a.depth) * a.plane, a.fromLower + slot * a.slotStride, n, true);
+	if (waitFlag(a.myFlagLower + slot, seq, a.error))
+	    copyPlanes(a.grid + int64_t(a.ownLo - a.depth) * a.plane, a.fromLower + slot * a.slotStride, n, true);
     }
     if (a.hasUpper)
     {
-	waitFlag(a.myFlagUpper + slot, seq, a.error);
-	copyPlanes(a.grid + int64_t(a.ownHi) * a.plane, a.fromUpper + slot * a.slotStride, n, true);
+	if (waitFlag(a.myFlagUpper + slot, seq, a.error))
+	    copyPlanes(a.grid + int64_t(a.ownHi) * a.plane, a.fromUpper + slot * a.slotStride, n, true);
     }
     if (lastCta<false>(a.tickets + 1))
     {
 	if (threadIdx.x == 0)
 	{
-	    *a.seq = seq;
+	    if (!*reinterpret_cast<volatile int *>(a.error)) *a.seq = seq;  // a failed exchange leaves the channel where it was
 	    a.tickets[0] = 0;
 	    a.tickets[1] = 0;
 	}
@@ -179,7 +203,7 @@ __global__ void __launch_bounds__(256) k_gather_p2p(const GatherP2pArgs a)
     for (int r = 0; r < a.world; ++r)
     {
 	if (r == a.rank) continue;
-	waitFlag(a.myFlags + slot * P2P_MAX_WORLD + r, seq, a.error);
+	if (!waitFlag(a.myFlags + slot * P2P_MAX_WORLD + r, seq, a.error)) continue;
 	const int64_t o = int64_t(a.lo[r]) * a.plane;
 	copyPlanes(a.grid + o, a.myBox + slot * a.slotStride + o, int64_t(a.hi[r] - a.lo[r]) * a.plane, true);
     }
@@ -187,7 +211,7 @@ __global__ void __launch_bounds__(256) k_gather_p2p(const GatherP2pArgs a)
     {
 	if (threadIdx.x == 0)
 	{
-	    *a.seq = seq;
+	    if (!*reinterpret_cast<volatile int *>(a.error)) *a.seq = seq;  // a failed exchange leaves the channel where it was
 	    a.tickets[0] = 0;
 	    a.tickets[1] = 0;
 	}
@@ -218,9 +242,7 @@ __global__ void __launch_bounds__(32) k_scalar_p2p(const ScalarP2pArgs a)
 	a.peerSlots[r][slot * P2P_MAX_WORLD + a.rank] = mine;
 	__threadfence_system();
 	stReleaseSys(a.flagOnPeer[r] + slot * P2P_MAX_WORLD + a.rank, seq);
-	long long spins = 0;
-	while (ldAcquireSys(a.myFlags + slot * P2P_MAX_WORLD + r) < seq)
-	    if (++spins > P2P_SPIN_LIMIT) { atomicExch(a.error, 1); break; }
+	pollFlag(a.myFlags + slot * P2P_MAX_WORLD + r, seq, a.error);
     }
     __syncwarp();
     if (r == 0)
@@ -232,8 +254,11 @@ __global__ void __launch_bounds__(32) k_scalar_p2p(const ScalarP2pArgs a)
 	    const double v = (k == a.rank) ? mine : __ldcg(a.mySlots + slot * P2P_MAX_WORLD + k);
 	    acc = a.isMax ? fmax(acc, v) : acc + v;
 	}
-	*a.value = acc;
-	*a.seq = seq;
+	if (!*reinterpret_cast<volatile int *>(a.error))
+	{
+	    *a.value = acc;
+	    *a.seq = seq;
+	}
     }
 }
 } // namespace gmg
