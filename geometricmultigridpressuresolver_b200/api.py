@@ -453,16 +453,25 @@ class GeometricMultigridPoissonSolver:
         _check(self.lib.gmg_vcycle(self.h, xp, bp, int(useInitialGuess)))
         return x
 
-    def solveGeometricConjugateGradient(self, solutionGrid, rhsGrid, tolerance, maxIterations, useMGPreconditioner: bool = True,
+    @staticmethod
+    def _precond(useMGPreconditioner):
+        """The node's useMGPreconditioner toggle (GFS.cpp:428): True = multigrid V-cycle, "diagonal" (or 2) = its other branch,
+        the diagonal preconditioner of GFS.cpp:485-618; False = none (plain CG, not a mode of the node)."""
+        if isinstance(useMGPreconditioner, str):
+            return {"mg": 1, "multigrid": 1, "diagonal": 2, "none": 0}[useMGPreconditioner]
+        return int(useMGPreconditioner)
+
+    def solveGeometricConjugateGradient(self, solutionGrid, rhsGrid, tolerance, maxIterations, useMGPreconditioner=True,
                                         inplace: bool = False):
-        """CG.h:11-207 with A = applyPoissonMatrix, M^-1 = applyVCycle (GFS.cpp:430-483).
+        """CG.h:11-207 with A = applyPoissonMatrix, M^-1 = applyVCycle (GFS.cpp:430-483) or the diagonal preconditioner
+        (GFS.cpp:485-618, useMGPreconditioner="diagonal").
         Returns (solution, iterations printed by CG.h:198 or -1 on an early-out, relative-residual history).
         inplace=True writes the pressure into solutionGrid itself (as the reference does) instead of a copy."""
         x, xp = _f64(solutionGrid if inplace else np.array(solutionGrid, copy=True))
         b, bp = _f64(rhsGrid)
         hist = np.zeros(int(maxIterations) + 2, dtype=np.float64)
         it, cnt = C.c_int(), C.c_int()
-        _check(self.lib.gmg_pcg(self.h, xp, bp, C.c_double(tolerance), int(maxIterations), int(useMGPreconditioner), C.byref(it),
+        _check(self.lib.gmg_pcg(self.h, xp, bp, C.c_double(tolerance), int(maxIterations), self._precond(useMGPreconditioner), C.byref(it),
                                 hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt)))
         return x, int(it.value), hist[: cnt.value].copy()
 
@@ -524,7 +533,7 @@ class GeometricMultigridPoissonSolver:
     def solveDevice(self, x: Grid, b: Grid, tolerance, maxIterations, useMGPreconditioner=True):
         hist = np.zeros(int(maxIterations) + 2, dtype=np.float64)
         it, cnt = C.c_int(), C.c_int()
-        _check(self.lib.gmg_pcg_device(self.h, x.h, b.h, C.c_double(tolerance), int(maxIterations), int(useMGPreconditioner), C.byref(it),
+        _check(self.lib.gmg_pcg_device(self.h, x.h, b.h, C.c_double(tolerance), int(maxIterations), self._precond(useMGPreconditioner), C.byref(it),
                                        hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt)))
         return int(it.value), hist[: cnt.value].copy()
 

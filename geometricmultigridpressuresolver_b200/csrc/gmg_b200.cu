@@ -244,6 +244,11 @@ extern "C" int gmg_ctx_create(int device, void *stream, gmg_ctx **out)
 	GMG_CUDA(cudaEventCreate(&ctx->t0));
 	GMG_CUDA(cudaEventCreate(&ctx->t1));
 	GMG_TRY(ensureScratch(ctx, 4096));
+	if (const char *e = getenv("GMG_PDL_PREFETCH"))
+	{
+	    const int waitFirst = e[0] == '0' ? 1 : 0;
+	    GMG_CUDA(cudaMemcpyToSymbol(c_pdlWaitFirst, &waitFirst, sizeof(int)));
+	}
 	return GMG_OK;
     };
     const int st = build();
@@ -916,7 +921,7 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 
 static int buildCoefs(gmg_ctx *ctx, Level &L, const double *w0, const double *w1, const double *w2)
 {
-    GMG_CUDA(devMalloc(&L.bcoef, sizeof(double) * 7 * std::max(L.nBoundary, 1)));
+    GMG_CUDA(devMalloc(&L.bcoef, sizeof(double) * 8 * std::max(L.nBoundary, 1)));
     if (L.nBoundary > 0)
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
@@ -1018,7 +1023,7 @@ static int buildCoefsSparse(gmg_ctx *ctx, Level &L, const double *w0, const doub
 			    CoefJob *job)
 {
     const int nB = L.nBoundary;
-    GMG_CUDA(devMalloc(&L.bcoef, sizeof(double) * 7 * std::max(nB, 1)));
+    GMG_CUDA(devMalloc(&L.bcoef, sizeof(double) * 8 * std::max(nB, 1)));
     L.hasWeights = true;
     if (nB == 0) return GMG_OK;
     const Geom &g = L.g;
@@ -2012,12 +2017,13 @@ extern "C" int gmg_solver_destroy(gmg_solver *s)
 	auto &v = s->ctx->solvers;
 	v.erase(std::remove(v.begin(), v.end(), s), v.end());
     }
-    devFree(s->coarseIdx); devFree(s->coarseInv); devFree(s->compactBlob);
+    devFree(s->coarseIdx); devFree(s->coarseInv); devFree(s->compactBlob); devFree(s->pcgLoop);
+    if (s->pcgLoopHost) cudaFreeHost(s->pcgLoopHost);
     delete static_cast<CompactArgs *>(s->compactArgs);
     if (!s->lv.empty())
     {
 	const Geom &g0 = s->lv[0].g;
-	freeGrid(s->pcgR, g0); freeGrid(s->pcgP, g0); freeGrid(s->pcgZ, g0); freeGrid(s->pcgT, g0); freeGrid(s->pcgX, g0); freeGrid(s->pcgB, g0);
+	freeGrid(s->pcgR, g0); freeGrid(s->pcgP, g0); freeGrid(s->pcgZ, g0); freeGrid(s->pcgT, g0); freeGrid(s->pcgX, g0); freeGrid(s->pcgB, g0); freeGrid(s->diagInv, g0);
     }
     for (auto &L : s->lv) freeLevel(L);
     delete s;
@@ -2674,7 +2680,7 @@ static int launchVec(gmg_solver *s, int level, double *y, const double *a, const
     v.c = c;
     v.y2 = y2;
     v.s = sc;
-    v.sc = reinterpret_cast<const Scalars *>(s->ctx->scalars);
+    v.sc = reinterpret_cast<Scalars *>(s->ctx->scalars);
     v.partials = s->ctx->partials;
     v.ticket = s->ctx->ticket;
     v.result = result;
@@ -2856,7 +2862,25 @@ static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useIniti
 // ====================================================================================================
 // PCG (CG.h:11-207)
 // ====================================================================================================
-__global__ void k_shift_rho(Scalars *sc) { pdlEnter(); sc->rho = sc->rhoNew; }
+// Device-side convergence test of the PCG loop (CG.h:159-161, :198): records sqrt(|r|^2/|b|^2), decides whether another
+// iteration runs and tells the graph's WHILE node.  One thread.
+struct PcgLoopState
+{
+    double threshold, bb;
+    int iteration;    // the index CG.h:198 prints
+    int maxIt;
+    int histCount, histCap;
+};
+__global__ void k_pcg_check(PcgLoopState *st, double *hist, const Scalars *sc, cudaGraphConditionalHandle handle)
+{
+    pdlEnter();
+    const double rr = sc->rr;
+    if (st->histCount < st->histCap) hist[st->histCount++] = sqrt(rr / st->bb);
+    unsigned more = 1u;
+    if (rr < st->threshold) more = 0u;                 // CG.h:161
+    else if (++st->iteration >= st->maxIt) more = 0u;  // CG.h:100
+    cudaGraphSetConditional(handle, more);
+}
 
 // owned-plane reduction into a device scalar, summed over the ranks on a sharded level 0
 template <int OP>
@@ -2868,6 +2892,38 @@ static int reduceOwned(gmg_solver *s, double *y, const double *a, size_t scalarO
     return GMG_OK;
 }
 
+// the grid the diagonal preconditioner multiplies by (GFS.cpp:487-560), built on first use
+static int ensureDiagInverse(gmg_solver *s)
+{
+    if (s->diagInv) return GMG_OK;
+    gmg_ctx *ctx = s->ctx;
+    Level &L = s->lv[0];
+    GMG_TRY(allocGrid(&s->diagInv, L.g));
+    const unsigned grid = unsigned(L.nChunksActive + divUp(L.nBoundary, BLOCK));
+    if (grid == 0) return GMG_OK;
+    GMG_LAUNCH(ctx, KC_SETUP, 0);
+    k_diag_inverse<<<grid, BLOCK, 0, ctx->stream>>>(s->diagInv, L.labels, L.chunksActive, L.nChunksActive, L.g.chunksPerPlane, L.g.plane, L.g.n[2],
+						    L.bandIdx, L.bcoef, L.nBoundary);
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+// z = M^-1 r for the three preconditioners of the ABI: 0 none (plain CG), 1 multigrid V-cycle (GFS.cpp:468-472),
+// 2 diagonal (GFS.cpp:562-603)
+static int applyPreconditioner(gmg_solver *s, int precond, double *z, const double *r, bool direct)
+{
+    const ZRange own = clipDepth(s->lv[0], 0);
+    if (precond == 1) return direct ? vcycleLaunches(s, z, r, false) : vcycleDevice(s, z, r, false);
+    if (precond == 2) return launchVec<VO_MUL>(s, 0, z, r, s->diagInv, nullptr, 0, nullptr, KC_BLAS1, 24.0, own);
+    return launchVec<VO_COPY>(s, 0, z, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, own);
+}
+
+static bool useDeviceLoop()
+{
+    static const bool v = [] { const char *e = getenv("GMG_DEVICE_LOOP"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
 // Sharded level 0: x0 and b come in valid over the whole stored slab.  Each iteration the search
 // direction p is refreshed HALO_P = 9 planes deep, so t = A p is valid 8 deep and the update r -= alpha t keeps r valid
 // 8 deep redundantly -- exactly what the next V-cycle needs as its right-hand side -- without an exchange of its own.
@@ -2876,6 +2932,7 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 {
     gmg_ctx *ctx = s->ctx;
     const Level &L0 = s->lv[0];
+    if (precond < 0 || precond > 2) return invalid("gmg_pcg: preconditioner must be 0 (none), 1 (multigrid V-cycle) or 2 (diagonal)");
     if (!s->pcgR)
     {
 	GMG_TRY(allocGrid(&s->pcgR, s->lv[0].g));
@@ -2905,19 +2962,18 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 	return GMG_OK;
     }
     // p = M^-1 r ; rho = p.r (CG.h:66-87)
-    // The first solve of a solver launches its one-off pieces (first preconditioner application, first update) directly: a
-    // solver is typically built, used for ONE solve and destroyed every simulation frame, and capturing + instantiating a
-    // graph that is replayed once costs more than it saves.  From the second solve on they are cached graphs like the rest.
-    if (precond && s->opt.operators_only && s->levels > 1) return invalid("this solver handle was created with operators_only: no coarse factor, no V-cycle");
+    // The first solve of a solver launches its one-off pieces (first preconditioner application) directly: a solver is
+    // typically built, used for ONE solve and destroyed every simulation frame, and capturing + instantiating a graph that
+    // is replayed once costs more than it saves.  From the second solve on they are cached graphs like the rest.
+    if (precond == 1 && s->opt.operators_only && s->levels > 1) return invalid("this solver handle was created with operators_only: no coarse factor, no V-cycle");
+    if (precond == 2) GMG_TRY(ensureDiagInverse(s));
     // (single GPU only: on a sharded context every exchange stays inside the graphs it was validated in)
     const bool firstSolve = (s->pcgSolves++ == 0) && !ctx->profiling && ctx->world == 1;
-    if (precond && firstSolve) GMG_TRY(vcycleLaunches(s, p, r, false));
-    else if (precond) GMG_TRY(vcycleDevice(s, p, r, false));
-    else GMG_TRY((launchVec<VO_COPY>(s, 0, p, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, own)));
-    GMG_TRY((reduceOwned<VO_DOT>(s, p, r, offsetof(Scalars, rho), 16.0)));
+    GMG_TRY(applyPreconditioner(s, precond, p, r, firstSolve));
+    GMG_TRY((reduceOwned<VO_DOT>(s, p, r, offsetof(Scalars, rhoNew), 16.0)));
     // Reference loop (CG.h:100-195): [t = A p, alpha, x += alpha p, r -= alpha t, |r|^2, test] then
-    // [z = M^-1 r, beta, p = z + beta p].  Re-bracketed here as: first [apply, update]; then per iteration one
-    // graph {V-cycle, z.r, direction, apply (+p.Ap), update (+|r|^2)} and one scalar read-back for the test.
+    // [z = M^-1 r, beta, p = z + beta p].  Re-bracketed here as: first [apply, update]; then per iteration
+    // {preconditioner, z.r, direction, apply (+p.Ap), update (+|r|^2, retires rho)} and the test.
     auto applyUpdate = [&]() -> int {
 	GMG_TRY(haloExchange(s, 0, p, HALO_P));
 	// sharded: t = A p and the update run over the deep halo range (r stays valid 8 planes deep), their fused reductions
@@ -2929,27 +2985,115 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 	return GMG_OK;
     };
     auto iterationBody = [&]() -> int {
-	if (precond) GMG_TRY(vcycleLaunches(s, z, r, false));
-	else GMG_TRY((launchVec<VO_COPY>(s, 0, z, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, own)));
+	GMG_TRY(applyPreconditioner(s, precond, z, r, true));
 	GMG_TRY((reduceOwned<VO_DOT>(s, z, r, offsetof(Scalars, rhoNew), 16.0)));
 	GMG_TRY((launchVec<VO_CG_DIRECTION>(s, 0, p, z, nullptr, nullptr, 0, nullptr, KC_BLAS1, 24.0, own)));
-	{
-	    s->ctx->curLevel = 0;
-	    GMG_LAUNCH(ctx, KC_BLAS1, 0);
-	    GMG_CUDA(launchK(k_shift_rho, unsigned(1), unsigned(1), size_t(0), ctx->stream, reinterpret_cast<Scalars *>(ctx->scalars)));
-	}
 	return applyUpdate();
     };
+    int iteration = 0;
+    if (useDeviceLoop() && s->useGraphs && !ctx->profiling && ctx->world == 1)
+    {
+	// The whole loop as ONE graph launch: [apply, update, test] then a WHILE node around {iteration, test}; the residual
+	// history stays on the device until the loop ends, so the host synchronises once per solve instead of once per
+	// iteration.  The loop parameters live in device memory, so the cached graph serves every (tol, maxIt).
+	constexpr int HIST_MAX = 4096;
+	if (!s->pcgLoop)
+	{
+	    char *blk = nullptr;
+	    GMG_CUDA(devMalloc(&blk, sizeof(PcgLoopState) + sizeof(double) * HIST_MAX));
+	    s->pcgLoop = blk;
+	    GMG_CUDA(cudaMallocHost(&s->pcgLoopHost, sizeof(PcgLoopState) + sizeof(double) * HIST_MAX));
+	}
+	PcgLoopState *dst = static_cast<PcgLoopState *>(s->pcgLoop);
+	double *dhist = reinterpret_cast<double *>(dst + 1);
+	PcgLoopState *hst = static_cast<PcgLoopState *>(s->pcgLoopHost);
+	hst->threshold = threshold; hst->bb = bb; hst->iteration = 0; hst->maxIt = maxIt; hst->histCount = 0;
+	hst->histCap = std::min(HIST_MAX, std::max(maxIt + 1, 1));
+	GMG_CUDA(cudaMemcpyAsync(dst, hst, sizeof(PcgLoopState), cudaMemcpyHostToDevice, ctx->stream));
+	auto key = std::make_tuple(3, static_cast<const void *>(x), static_cast<const void *>(b), precond);
+	auto it = s->graphs.find(key);
+	if (it == s->graphs.end())
+	{
+	    if (s->graphs.size() >= 16) dropGraphs(s);
+	    gmg_solver::GraphEntry e;
+	    const int64_t before = ctx->launches;
+	    GMG_CUDA(cudaGraphCreate(&e.graph, 0));
+	    cudaGraphConditionalHandle handle;
+	    GMG_CUDA(cudaGraphConditionalHandleCreate(&handle, e.graph, 0, cudaGraphCondAssignDefault));
+	    Scalars *sc = reinterpret_cast<Scalars *>(ctx->scalars);
+	    auto check = [&]() -> int {
+		ctx->curLevel = 0;
+		GMG_LAUNCH(ctx, KC_BLAS1, 0);
+		GMG_CUDA(launchK(k_pcg_check, unsigned(1), unsigned(1), size_t(0), ctx->stream, dst, dhist, static_cast<const Scalars *>(sc), handle));
+		return GMG_OK;
+	    };
+	    // head: [apply, update, test]
+	    GMG_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, e.graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+	    ctx->capturing = true;
+	    int st = applyUpdate();
+	    if (st == GMG_OK) st = check();
+	    ctx->capturing = false;
+	    cudaStreamCaptureStatus cs;
+	    const cudaGraphNode_t *deps = nullptr;
+	    size_t nDeps = 0;
+	    cudaError_t ce = cudaStreamGetCaptureInfo(ctx->stream, &cs, nullptr, nullptr, &deps, &nDeps);
+	    std::vector<cudaGraphNode_t> tail(deps, deps + (ce == cudaSuccess ? nDeps : 0));
+	    cudaGraph_t g1 = nullptr;
+	    cudaError_t ce2 = cudaStreamEndCapture(ctx->stream, &g1);
+	    const int64_t headKernels = ctx->launches - before;
+	    if (st != GMG_OK || ce != cudaSuccess || ce2 != cudaSuccess)
+	    {
+		cudaGraphDestroy(e.graph);
+		ctx->launches = before;
+		if (st != GMG_OK) return st;
+		GMG_CUDA(ce);
+		GMG_CUDA(ce2);
+	    }
+	    // WHILE node around {iteration, test}
+	    cudaGraphNodeParams np = {};
+	    np.type = cudaGraphNodeTypeConditional;
+	    np.conditional.handle = handle;
+	    np.conditional.type = cudaGraphCondTypeWhile;
+	    np.conditional.size = 1;
+	    cudaGraphNode_t whileNode;
+	    GMG_CUDA(cudaGraphAddNode(&whileNode, e.graph, tail.data(), tail.size(), &np));
+	    cudaGraph_t body = np.conditional.phGraph_out[0];
+	    const int64_t beforeBody = ctx->launches;
+	    GMG_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+	    ctx->capturing = true;
+	    st = iterationBody();
+	    if (st == GMG_OK) st = check();
+	    ctx->capturing = false;
+	    cudaGraph_t g2 = nullptr;
+	    ce2 = cudaStreamEndCapture(ctx->stream, &g2);
+	    e.kernels = headKernels;
+	    e.comms = ctx->launches - beforeBody;  // (re-used field: kernels per loop iteration)
+	    ctx->launches = before;
+	    if (st != GMG_OK) { cudaGraphDestroy(e.graph); return st; }
+	    GMG_CUDA(ce2);
+	    GMG_CUDA(cudaGraphInstantiate(&e.exec, e.graph, 0));
+	    it = s->graphs.emplace(key, e).first;
+	}
+	GMG_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
+	GMG_CUDA(cudaMemcpyAsync(hst, dst, sizeof(PcgLoopState) + sizeof(double) * hst->histCap, cudaMemcpyDeviceToHost, ctx->stream));
+	GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+	iteration = hst->iteration;
+	ctx->launches += it->second.kernels + int64_t(std::max(0, hst->histCount - 1)) * it->second.comms;
+	const double *hh = reinterpret_cast<const double *>(hst + 1);
+	if (hist && histCount)
+	    for (int k = 0; k < hst->histCount && *histCount < histCap; ++k) hist[(*histCount)++] = hh[k];
+	if (iterations) *iterations = iteration;
+	return GMG_OK;
+    }
     if (firstSolve) GMG_TRY(applyUpdate());
     else GMG_TRY(runGraphed(s, 1, x, nullptr, 0, applyUpdate));
-    int iteration = 0;
     for (;;)
     {
 	GMG_TRY(readScalar(s, offsetof(Scalars, rr), &rr));
 	if (hist && histCount && *histCount < histCap) hist[(*histCount)++] = std::sqrt(rr / bb);
 	if (rr < threshold) break;
 	if (++iteration >= maxIt) break; // CG.h:198 then prints maxIterations
-	GMG_TRY(runGraphed(s, 2, x, nullptr, precond ? 1 : 0, iterationBody));
+	GMG_TRY(runGraphed(s, 2, x, nullptr, precond, iterationBody));
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     if (iterations) *iterations = iteration;

@@ -84,7 +84,7 @@ struct Level
     int32_t *bandIdx = nullptr;  // [nBand] storage index
     int32_t *bandRef = nullptr;  // [6][nBand] neighbour reference (gmg_kernels.cuh: BandArgs::bandRef)
     bool hasWeights = false;     // level 0 built with face weights: BOUNDARY cells carry fractional coefficients
-    double *bcoef = nullptr;     // [7][nBoundary]: coefficient on each of the 6 neighbours, then the diagonal
+    double *bcoef = nullptr;     // [8][nBoundary]: coefficient on each of the 6 neighbours, the diagonal, the sum of the six face weights
     double *bandV0 = nullptr, *bandV1 = nullptr, *bandB = nullptr;
     // CTAs of the full-grid kernels: chunks holding at least one INTERIOR cell / one active cell
     int nChunksInterior = 0, nChunksActive = 0;
@@ -179,6 +179,9 @@ struct gmg_solver
     size_t compactSmem = 0;
     // PCG work grids (level 0)
     double *pcgR = nullptr, *pcgP = nullptr, *pcgZ = nullptr, *pcgT = nullptr, *pcgX = nullptr, *pcgB = nullptr;
+    double *diagInv = nullptr;           // diagonal preconditioner grid (GFS.cpp:487-560), built on first use
+    void *pcgLoop = nullptr;             // device PcgLoopState + residual history of the device-side PCG loop
+    void *pcgLoopHost = nullptr;         // pinned mirror
     double setupMs = 0;
     int64_t pcgSolves = 0;               // solves run on this solver so far
     std::vector<gmg::IoGroup> ioGroups;  // empty = move the whole box

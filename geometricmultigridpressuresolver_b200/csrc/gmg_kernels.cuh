@@ -21,12 +21,25 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 
-// Programmatic dependent launch (see launchK in gmg_b200.cu): let the next kernel of the chain be set up right away, then wait
-// until everything the previous kernel wrote is visible.  Both are no-ops for a launch without the PDL attribute.
-__device__ __forceinline__ void pdlEnter()
+// Programmatic dependent launch (see launchK in gmg_b200.cu).  A V-cycle at 256^3 is ~70 dependent steps of a few
+// microseconds, each a chain of dependent loads (chunk id -> labels / neighbour references -> values), so every hot
+// kernel is split in two: a PROLOGUE that lets the next kernel of the chain be scheduled right away (pdlLaunch) and loads
+// its own STATIC metadata -- chunk ids, labels, band indices / references / coefficient records, none of which is ever
+// written after the constructor -- while the previous kernel is still running, then pdlWait(), after which everything the
+// previous kernel wrote is visible and only the value loads remain on the critical path.  Both instructions are no-ops
+// for a launch without the PDL attribute.  The "memory" clobbers keep the compiler from moving a load across the wait.
+// A/B switch (GMG_PDL_PREFETCH=0): wait right at the top, i.e. no prologue overlap -- the round-1 behaviour
+__constant__ int c_pdlWaitFirst = 0;
+__device__ __forceinline__ void pdlLaunch()
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (c_pdlWaitFirst) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdlEnter()
+{
+    pdlLaunch();
+    pdlWait();
 }
 
 __device__ __forceinline__ double warpSum(double v)
@@ -99,10 +112,10 @@ __device__ __forceinline__ bool gridReduce(double v, double *partials, unsigned 
 // ------------------------------------------------------------------------------------------------
 struct Scalars
 {
-    double rho;      // z.r of the current direction
+    double rho;      // z.r of the previous direction (retired by the update kernel)
     double pAp;      // p.Ap
     double rr;       // |r|^2
-    double rhoNew;   // z.r after the preconditioner
+    double rhoNew;   // z.r of the current direction
     double bb;       // |b|^2
     double tmp;      // generic reduction result
     double alpha, beta;
@@ -151,8 +164,9 @@ __device__ __forceinline__ double stencilFinish(double lap, double centre, doubl
     return centre + (2.0 / 3.0) * r;
 }
 
-// vb = virtual CTA index (blockIdx.x of the stand-alone kernel, a strided index inside the persistent coarse-cycle kernel),
-// tid = thread index inside the BLOCK-wide virtual CTA.  Returns this thread's part of dot(in, A in) when DOT.
+// vb = virtual CTA index (blockIdx.x of the stand-alone kernel), tid = thread index inside the BLOCK-wide virtual CTA.
+// Returns this thread's part of dot(in, A in) when DOT.  Prologue (before pdlWait): chunk id and the labels of the
+// thread's cells, or the boundary cell's index and coefficient record.
 template <int MODE, bool DOT>
 __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int tid)
 {
@@ -162,38 +176,42 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 	const int c = a.chunks[vb];
 	const int zb = c / a.chunksPerPlane;
 	const int64_t inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * tid;
-	if (inPlane < a.plane)
-	{
-	    const int z0 = zb * CHUNK_Z;
+	const int z0 = zb * CHUNK_Z;
+	uchar2 lab[CHUNK_Z];
 #pragma unroll
-	    for (int dz = 0; dz < CHUNK_Z; ++dz)
-	    {
-		const int z = z0 + dz;
-		if (z >= a.zhi) break;
-		if (z < a.zlo) continue;
-		const int64_t i = int64_t(z) * a.plane + inPlane;
-		const uchar2 l = *reinterpret_cast<const uchar2 *>(a.labels + i);
-		const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
-		if (!(a0 | a1)) continue;
-		const double2 c2 = ld2(a.in + i);
-		const double xm = a.in[i - 1], xp = a.in[i + 2];
-		const double2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
-		const double2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
-		double2 rhs = make_double2(0.0, 0.0);
-		if (MODE != SM_APPLY) rhs = ld2(a.b + i);
-		double lap0 = -xm;
-		lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
-		lap0 += 6.0 * c2.x;
-		double lap1 = -c2.x;
-		lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
-		lap1 += 6.0 * c2.y;
-		const double o0 = stencilFinish<MODE>(lap0, c2.x, rhs.x, 6.0);
-		const double o1 = stencilFinish<MODE>(lap1, c2.y, rhs.y, 6.0);
-		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
-		else if (a0) a.out[i] = o0;
-		else a.out[i + 1] = o1;
-		if (DOT && z >= a.dotLo && z < a.dotHi) acc += (a0 ? c2.x * lap0 : 0.0) + (a1 ? c2.y * lap1 : 0.0);
-	    }
+	for (int dz = 0; dz < CHUNK_Z; ++dz)
+	{
+	    const int z = z0 + dz;
+	    lab[dz] = make_uchar2(L_EXTERIOR, L_EXTERIOR);
+	    if (inPlane < a.plane && z >= a.zlo && z < a.zhi) lab[dz] = *reinterpret_cast<const uchar2 *>(a.labels + int64_t(z) * a.plane + inPlane);
+	}
+	pdlWait();
+#pragma unroll
+	for (int dz = 0; dz < CHUNK_Z; ++dz)
+	{
+	    const int z = z0 + dz;
+	    const uchar2 l = lab[dz];
+	    const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
+	    if (!(a0 | a1)) continue;
+	    const int64_t i = int64_t(z) * a.plane + inPlane;
+	    const double2 c2 = ld2(a.in + i);
+	    const double xm = a.in[i - 1], xp = a.in[i + 2];
+	    const double2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
+	    const double2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
+	    double2 rhs = make_double2(0.0, 0.0);
+	    if (MODE != SM_APPLY) rhs = ld2(a.b + i);
+	    double lap0 = -xm;
+	    lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
+	    lap0 += 6.0 * c2.x;
+	    double lap1 = -c2.x;
+	    lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
+	    lap1 += 6.0 * c2.y;
+	    const double o0 = stencilFinish<MODE>(lap0, c2.x, rhs.x, 6.0);
+	    const double o1 = stencilFinish<MODE>(lap1, c2.y, rhs.y, 6.0);
+	    if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
+	    else if (a0) a.out[i] = o0;
+	    else a.out[i + 1] = o1;
+	    if (DOT && z >= a.dotLo && z < a.dotHi) acc += (a0 ? c2.x * lap0 : 0.0) + (a1 ? c2.y * lap1 : 0.0);
 	}
     }
     else
@@ -201,18 +219,20 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 	const int k = (vb - a.nChunks) * BLOCK + tid;
 	const int64_t i = k < a.nBoundary ? int64_t(a.bandIdx[k]) : 0;
 	const int z = int(unsigned(i) / unsigned(a.plane));  // a level's box holds fewer than 2^31 cells: 32-bit division
-	if (k < a.nBoundary && z >= a.zlo && z < a.zhi)
+	const bool live = k < a.nBoundary && z >= a.zlo && z < a.zhi;
+	double cn[7];
+#pragma unroll
+	for (int n = 0; n < 7; ++n) cn[n] = live ? a.bcoef[int64_t(n) * a.nBoundary + k] : 0.0;
+	pdlWait();
+	if (live)
 	{
 	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
 	    const double centre = a.in[i];
 	    double lap = 0.0;
 #pragma unroll
 	    for (int n = 0; n < 6; ++n)
-	    {
-		const double cn = a.bcoef[int64_t(n) * a.nBoundary + k];
-		if (cn != 0.0) lap -= cn * a.in[i + stride[n]];
-	    }
-	    const double diag = a.bcoef[int64_t(6) * a.nBoundary + k];
+		if (cn[n] != 0.0) lap -= cn[n] * a.in[i + stride[n]];
+	    const double diag = cn[6];
 	    lap += diag * centre;
 	    const double rhs = (MODE != SM_APPLY) ? a.b[i] : 0.0;
 	    a.out[i] = stencilFinish<MODE>(lap, centre, rhs, diag);
@@ -224,7 +244,8 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 
 template <int MODE, bool DOT>
 __global__ void __launch_bounds__(BLOCK) k_stencil(const StencilArgs a)
-{ pdlEnter();
+{
+    pdlLaunch();
     const double acc = stencilBody<MODE, DOT>(a, blockIdx.x, threadIdx.x);
     if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
 }
@@ -257,52 +278,67 @@ constexpr int BAND_PER_THREAD = 2;  // cells per thread: two independent gather 
 // FROM_COMPACT: centre/band-neighbour values come from vin; TO_GRID: result goes to x[idx];
 // FIRST: rhs is gathered from the grid and cached in bandB; ZERO: the grid is known to be all zero;
 // HAS_W: level 0 with face weights -- BOUNDARY cells multiply by their coefficient records (elsewhere every coefficient is 1)
+// Prologue (static metadata, before pdlWait): grid index, neighbour references, diagonal, coefficient record.
 template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W>
 __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 {
-    double v[BAND_PER_THREAD];
     int64_t gi[BAND_PER_THREAD];
+    int ref[BAND_PER_THREAD][6];
+    double diag[BAND_PER_THREAD];
+#pragma unroll
+    for (int c = 0; c < BAND_PER_THREAD; ++c)
+    {
+	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
+	gi[c] = 0;
+	diag[c] = 6.0;
+#pragma unroll
+	for (int n = 0; n < 6; ++n) ref[c][n] = BAND_SKIP;
+	if (k >= a.nBand) continue;
+	if (!FROM_COMPACT || TO_GRID || FIRST) gi[c] = a.bandIdx[k];
+	if (k < a.nBoundary) diag[c] = a.bcoef[int64_t(6) * a.nBoundary + k];
+	if (!ZERO)
+	{
+#pragma unroll
+	    for (int n = 0; n < 6; ++n) ref[c][n] = a.bandRef[int64_t(n) * a.nBand + k];
+	}
+    }
+    pdlWait();
+    double v[BAND_PER_THREAD];
 #pragma unroll
     for (int c = 0; c < BAND_PER_THREAD; ++c)
     {
 	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
 	v[c] = 0.0;
-	gi[c] = 0;
 	if (k >= a.nBand) continue;
-	int64_t i = 0;
-	if (!FROM_COMPACT || TO_GRID || FIRST) i = a.bandIdx[k];
-	gi[c] = i;
+	const int64_t i = gi[c];
 	double rhs;
 	if (FIRST) { rhs = a.b[i]; a.bandB[k] = rhs; }
 	else rhs = a.bandB[k];
-	const double diag = k < a.nBoundary ? a.bcoef[int64_t(6) * a.nBoundary + k] : 6.0;
 	double centre = 0.0, lap = 0.0;
 	if (!ZERO)
 	{
 	    const bool weighted = HAS_W && k < a.nBoundary;
 	    centre = FROM_COMPACT ? a.vin[k] : a.x[i];
 	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
-	    int ref[6];
-#pragma unroll
-	    for (int n = 0; n < 6; ++n) ref[n] = a.bandRef[int64_t(n) * a.nBand + k];
 #pragma unroll
 	    for (int n = 0; n < 6; ++n)
 	    {
-		if (ref[n] == BAND_SKIP) continue;
+		const int r = ref[c][n];
+		if (r == BAND_SKIP) continue;
 		double u;
-		if (FROM_COMPACT) u = ref[n] >= 0 ? a.vin[ref[n]] : a.x[-2 - ref[n]];
+		if (FROM_COMPACT) u = r >= 0 ? a.vin[r] : a.x[-2 - r];
 		else u = a.x[i + stride[n]];
 		if (weighted)
 		{
-		    const double cn = a.bcoef[int64_t(n) * a.nBoundary + k];
+		    const double cn = a.bcoef[int64_t(n) * a.nBoundary + k];  // independent of the value gathers: not on the dependent chain
 		    if (cn != 0.0) lap -= cn * u;
 		}
 		else lap -= u;
 	    }
-	    lap += diag * centre;
+	    lap += diag[c] * centre;
 	}
 	double r = rhs - lap;
-	r /= diag;
+	r /= diag[c];
 	v[c] = centre + (2.0 / 3.0) * r;
     }
 #pragma unroll
@@ -317,14 +353,17 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W>
 __global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
 {
-    pdlEnter();
+    pdlLaunch();
     bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W>(a, blockIdx.x, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t *bandIdx, const double *v, int nBand)
-{ pdlEnter();
+{
+    pdlLaunch();
     const int k = blockIdx.x * BLOCK + threadIdx.x;
-    if (k < nBand) x[bandIdx[k]] = v[k];
+    const int i = k < nBand ? bandIdx[k] : 0;
+    pdlWait();
+    if (k < nBand) x[i] = v[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -362,6 +401,7 @@ __device__ __forceinline__ void restrictBody(const TransferArgs &a, int vb, int 
     if (inPlane >= a.coarsePlane) return;
     const int64_t ci = int64_t(cz) * a.coarsePlane + inPlane;
     const int l = a.coarseLabels[ci];
+    pdlWait();
     if (!(l == L_INTERIOR || l == L_BOUNDARY)) return;
     const int cy = int(unsigned(inPlane) / unsigned(a.coarsePitch)), cx = int(inPlane - int64_t(cy) * a.coarsePitch);
     const int fx = 2 * (cx - a.shift[0]) - 1, fy = 2 * (cy - a.shift[1]) - 1, fz = 2 * (cz - a.shift[2]) - 1;
@@ -384,7 +424,7 @@ __device__ __forceinline__ void restrictBody(const TransferArgs &a, int vb, int 
 	}
     a.out[ci] = v;
 }
-__global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a) { pdlEnter(); restrictBody(a, blockIdx.x, threadIdx.x); }
+__global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a) { pdlLaunch(); restrictBody(a, blockIdx.x, threadIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
 // Prolongation (Ops.h:873-972): fine (active) += 4 * trilerp(8 coarse cells), fractions .25/.75.
@@ -399,6 +439,16 @@ __device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int t
     const int c = a.chunks[vb];
     const int zb = c / a.chunksPerPlane;
     const int64_t inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * tid;
+    // prologue: the fine labels of the thread's cells (static)
+    uchar2 lab[CHUNK_Z];
+#pragma unroll
+    for (int q = 0; q < CHUNK_Z; ++q)
+    {
+	const int fz = zb * CHUNK_Z + q;
+	lab[q] = make_uchar2(L_EXTERIOR, L_EXTERIOR);
+	if (inPlane < a.finePlane && fz >= a.zlo && fz < a.zhi) lab[q] = *reinterpret_cast<const uchar2 *>(a.fineLabels + int64_t(fz) * a.finePlane + inPlane);
+    }
+    pdlWait();
     if (inPlane >= a.finePlane) return;
     const int fy = int(unsigned(inPlane) / unsigned(a.finePitch)), fx = int(inPlane - int64_t(fy) * a.finePitch);
     const int mx = (fx >> 1) + a.shift[0];
@@ -409,12 +459,8 @@ __device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int t
     for (int p = 0; p < CHUNK_Z / 2; ++p)
     {
 	const int fz0 = zb * CHUNK_Z + 2 * p;  // even: storage origins are even
-	if (fz0 >= a.zhi) break;
-	const bool do0 = fz0 >= a.zlo, do1 = fz0 + 1 >= a.zlo && fz0 + 1 < a.zhi;
 	const int64_t i0 = int64_t(fz0) * a.finePlane + inPlane, i1 = i0 + a.finePlane;
-	uchar2 l0 = make_uchar2(L_EXTERIOR, L_EXTERIOR), l1 = l0;
-	if (do0) l0 = *reinterpret_cast<const uchar2 *>(a.fineLabels + i0);
-	if (do1) l1 = *reinterpret_cast<const uchar2 *>(a.fineLabels + i1);
+	const uchar2 l0 = lab[2 * p], l1 = lab[2 * p + 1];
 	const bool a00 = (l0.x == L_INTERIOR || l0.x == L_BOUNDARY), a01 = (l0.y == L_INTERIOR || l0.y == L_BOUNDARY);
 	const bool a10 = (l1.x == L_INTERIOR || l1.x == L_BOUNDARY), a11 = (l1.y == L_INTERIOR || l1.y == L_BOUNDARY);
 	if (!(a00 | a01 | a10 | a11)) continue;
@@ -457,7 +503,7 @@ __device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int t
 	}
     }
 }
-__global__ void __launch_bounds__(BLOCK, 6) k_prolong(const TransferArgs a) { pdlEnter(); prolongBody(a, blockIdx.x, threadIdx.x); }
+__global__ void __launch_bounds__(BLOCK, 6) k_prolong(const TransferArgs a) { pdlLaunch(); prolongBody(a, blockIdx.x, threadIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
 // Coarsest level (MG.cpp:669-692): gather b, x = A^-1 b (dense inverse of the SPD matrix, built on the
@@ -495,7 +541,7 @@ struct VecArgs
     const double *c;    // third operand
     double *y2;         // second destination (fused CG update)
     double s;           // host scalar
-    const Scalars *sc;  // device scalars
+    Scalars *sc;        // device scalars
     double *partials;
     unsigned *ticket;
     double *result;
@@ -509,20 +555,23 @@ enum VecOp
     VO_DOT,            // result = sum y*a
     VO_NORM2,          // result = sum y*y
     VO_MAX,            // result = max(y, 0)
-    VO_CG_UPDATE,      // alpha = rho/pAp; y(x) += alpha*a(p); y2(r) -= alpha*c(Ap); result = |r|^2
+    VO_CG_UPDATE,      // alpha = rhoNew/pAp; y(x) += alpha*a(p); y2(r) -= alpha*c(Ap); result = |r|^2; then rho = rhoNew
     VO_CG_DIRECTION,   // beta = rhoNew/rho; y(p) = a(z) + beta*y(p)
-    VO_COPY            // y = a
+    VO_COPY,           // y = a
+    VO_MUL             // y = a * c  (diagonal preconditioner, GFS.cpp:562-603)
 };
 
 template <int OP>
 __global__ void __launch_bounds__(BLOCK) k_vec(const VecArgs v)
-{ pdlEnter();
+{
+    pdlLaunch();
     const int c = v.chunks[blockIdx.x];
+    pdlWait();
     const int zb = c / v.chunksPerPlane;
     const int64_t inPlane = int64_t(c - zb * v.chunksPerPlane) * CHUNK_CELLS + 2 * threadIdx.x;
     double acc = 0.0;
     double s = v.s;
-    if (OP == VO_CG_UPDATE) s = v.sc->rho / v.sc->pAp;
+    if (OP == VO_CG_UPDATE) s = v.sc->rhoNew / v.sc->pAp;
     if (OP == VO_CG_DIRECTION) s = v.sc->rhoNew / v.sc->rho;
     if (inPlane < v.plane)
     {
@@ -584,16 +633,26 @@ __global__ void __launch_bounds__(BLOCK) k_vec(const VecArgs v)
 	    {
 		st2(v.y + i, ld2(v.a + i));
 	    }
+	    else if (OP == VO_MUL)
+	    {
+		const double2 a = ld2(v.a + i), cc = ld2(v.c + i);
+		st2(v.y + i, make_double2(a.x * cc.x, a.y * cc.y));
+	    }
 	}
     }
-    if (OP == VO_DOT || OP == VO_NORM2 || OP == VO_CG_UPDATE) gridReduce<false>(acc, v.partials, v.ticket, v.result);
+    if (OP == VO_DOT || OP == VO_NORM2) gridReduce<false>(acc, v.partials, v.ticket, v.result);
+    if (OP == VO_CG_UPDATE)
+    {
+	// the CTA that finishes the reduction also retires this iteration's rho (CG.h:165-176: absOld = absNew): every CTA has
+	// read rhoNew by then, and nothing reads rho before the next direction update
+	if (gridReduce<false>(acc, v.partials, v.ticket, v.result)) v.sc->rho = v.sc->rhoNew;
+    }
     if (OP == VO_MAX) gridReduce<true>(acc, v.partials, v.ticket, v.result);
 }
 
 // zero the active chunks of a grid (x = 0 at the start of a V-cycle level, MG.cpp:439-440, :566)
-__device__ __forceinline__ void zeroBody(double *y, const int32_t *chunks, int chunksPerPlane, int64_t plane, int nz, int vb, int tid)
+__device__ __forceinline__ void zeroBody(double *y, int c, int chunksPerPlane, int64_t plane, int nz, int tid)
 {
-    const int c = chunks[vb];
     const int zb = c / chunksPerPlane;
     const int64_t inPlane = int64_t(c - zb * chunksPerPlane) * CHUNK_CELLS + 2 * tid;
     if (inPlane >= plane) return;
@@ -606,8 +665,11 @@ __device__ __forceinline__ void zeroBody(double *y, const int32_t *chunks, int c
     }
 }
 __global__ void __launch_bounds__(BLOCK) k_zero(double *y, const int32_t *chunks, int chunksPerPlane, int64_t plane, int nz)
-{ pdlEnter();
-    zeroBody(y, chunks, chunksPerPlane, plane, nz, blockIdx.x, threadIdx.x);
+{
+    pdlLaunch();
+    const int c = chunks[blockIdx.x];
+    pdlWait();
+    zeroBody(y, c, chunksPerPlane, plane, nz, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -832,14 +894,17 @@ __device__ __forceinline__ void compactSmooth(const CompactLevel &L, const unsig
 }
 
 __global__ void __launch_bounds__(CYCLE_THREADS, 1) k_compact_cycle(const CompactArgs c)
-{ pdlEnter();
+{
+    pdlLaunch();
     extern __shared__ double sm[];
     unsigned char *tab = reinterpret_cast<unsigned char *>(sm + c.vectorDoubles);
     const int nl = c.nLevels;
     {
+	// prologue: the (static) index tables go to shared memory while the restriction above this level is still running
 	const int4 *src = reinterpret_cast<const int4 *>(c.blob);
 	int4 *dst = reinterpret_cast<int4 *>(tab);
 	for (int i = threadIdx.x; i < c.blobBytes / 16; i += CYCLE_THREADS) dst[i] = __ldg(src + i);
+	pdlWait();
 	const CompactLevel &L = c.lv[0];
 	double *b = sm + L.off + 2 * L.n;
 	for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) b[k] = c.bTop[__ldg(c.cellTop + k)];
@@ -1186,7 +1251,7 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef(double *bcoef, const int32_
     const int64_t i = bandIdx[k];
     const int64_t stride[3] = {1, pitch, plane};
     const double *w[3] = {w0, w1, w2};
-    double diag = 0.0;
+    double diag = 0.0, wsum = 0.0;
 #pragma unroll
     for (int n = 0; n < 6; ++n)
     {
@@ -1199,9 +1264,13 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef(double *bcoef, const int32_
 	if (nl == L_INTERIOR) { cn = 1.0; diag += 1.0; }
 	else if (nl == L_BOUNDARY) { cn = wt; diag += wt; }
 	else if (nl == L_DIRICHLET) { diag += wt; }
+	wsum += wt;
 	bcoef[int64_t(n) * nBoundary + k] = cn;
     }
     bcoef[int64_t(6) * nBoundary + k] = diag;
+    // row 7: the plain sum of the six face weights -- the diagonal the reference's diagonal preconditioner inverts
+    // (GFS.cpp:538-548); without weight grids there is no such sum and the operator's diagonal stands in
+    bcoef[int64_t(7) * nBoundary + k] = w0 ? wsum : diag;
 }
 
 // The same records from SPARSE face weights: wf[n][k] = weight of face n (-x,+x,-y,+y,-z,+z) of BOUNDARY cell k, gathered on the
@@ -1213,7 +1282,7 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef_sparse(double *bcoef, const
     if (k >= nBoundary) return;
     const int64_t i = bandIdx[k];
     const int64_t stride[3] = {1, pitch, plane};
-    double diag = 0.0;
+    double diag = 0.0, wsum = 0.0;
 #pragma unroll
     for (int n = 0; n < 6; ++n)
     {
@@ -1225,9 +1294,38 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef_sparse(double *bcoef, const
 	if (nl == L_INTERIOR) { cn = 1.0; diag += 1.0; }
 	else if (nl == L_BOUNDARY) { cn = wt; diag += wt; }
 	else if (nl == L_DIRICHLET) { diag += wt; }
+	wsum += wt;
 	bcoef[int64_t(n) * nBoundary + k] = cn;
     }
     bcoef[int64_t(6) * nBoundary + k] = diag;
+    bcoef[int64_t(7) * nBoundary + k] = wsum;  // GFS.cpp:538-548
+}
+
+// Diagonal preconditioner grid of GFS.cpp:493-560: 1/6 on INTERIOR cells, 1/(sum of the six face weights) on BOUNDARY cells,
+// 0 elsewhere.  CTAs [0, nChunks) walk the active chunks, the rest the boundary records.
+__global__ void __launch_bounds__(BLOCK) k_diag_inverse(double *d, const uint8_t *labels, const int32_t *chunks, int nChunks, int chunksPerPlane,
+						       int64_t plane, int nz, const int32_t *bandIdx, const double *bcoef, int nBoundary)
+{
+    if (int(blockIdx.x) < nChunks)
+    {
+	const int c = chunks[blockIdx.x];
+	const int zb = c / chunksPerPlane;
+	const int64_t inPlane = int64_t(c - zb * chunksPerPlane) * CHUNK_CELLS + 2 * threadIdx.x;
+	if (inPlane >= plane) return;
+	for (int dz = 0; dz < CHUNK_Z; ++dz)
+	{
+	    const int z = zb * CHUNK_Z + dz;
+	    if (z >= nz) break;
+	    const int64_t i = int64_t(z) * plane + inPlane;
+	    if (labels[i] == L_INTERIOR) d[i] = 1. / 6.;
+	    if (labels[i + 1] == L_INTERIOR) d[i + 1] = 1. / 6.;
+	}
+    }
+    else
+    {
+	const int k = (blockIdx.x - nChunks) * BLOCK + threadIdx.x;
+	if (k < nBoundary) d[bandIdx[k]] = 1. / bcoef[int64_t(7) * nBoundary + k];
+    }
 }
 
 // bounding rectangle of the ACTIVE cells of every z-plane: ext[z] = (x0, x1, y0, y1), half-open; x1 <= x0 for an empty plane.

@@ -154,7 +154,10 @@ int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInitialGuess);
  * (A = applyPoissonMatrix with the fine weights, M^-1 = applyVCycle), HDK_GeometricCGPoissonSolver.h:11-207.
  * x: host in/out (warm start allowed).  iterations: the index CG.h:198 prints, -1 on the two early-outs.
  * relResHistory[k] = sqrt(|r_k|^2/|b|^2), the value CG.h:159 prints; histCount = entries written.
- * preconditioner: 1 = multigrid V-cycle, 0 = none (plain CG). */
+ * preconditioner: 1 = multigrid V-cycle (GFS.cpp:468-483); 2 = the node's other branch, the diagonal preconditioner of
+ * HDK_GeometricFreeSurfacePressureSolver.cpp:485-618 (1/6 on INTERIOR cells, 1/(sum of the six face weights) on BOUNDARY cells);
+ * 0 = none (plain CG; not a mode of the node).  maxIt <= 0: x untouched, iterations = 0 (CG.h:100).
+ * The loop itself runs on the device (a WHILE node around the captured iteration): one host synchronisation per solve. */
 int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations,
 	    double *relResHistory, int histCap, int *histCount);
 

@@ -225,6 +225,11 @@ class RefLib(_Base):
     def threads(self):
         return int(self.fn("threads")())
 
+    def set_threads(self, n=None):
+        """Use n (default: every host core) OpenMP threads, whatever OMP_NUM_THREADS the launcher exported."""
+        self.fn("set_threads", None)(int(n or os.cpu_count() or 1))
+        return self.threads()
+
     def expand_labels(self, base):
         b, bp = _i32(base)
         out = _i32p()
@@ -284,13 +289,16 @@ class _RefSolver:
         self.last_seconds = float(self.lib.fn("solver_vcycle", C.c_double)(self.h, xp, bp, int(use_initial_guess), int(repeats)))
         return x
 
-    def pcg(self, x, b, tol, max_it):
+    def pcg(self, x, b, tol, max_it, diagonal=False):
+        """CG.h:11-207 with the multigrid V-cycle (GFS.cpp:468-483) or, diagonal=True, the diagonal preconditioner of
+        GFS.cpp:485-618."""
         x, xp = _f64(np.array(x, copy=True))
         b, bp = _f64(b)
         hist = np.zeros(max_it + 2, dtype=np.float64)
         cnt = C.c_int()
         secs = C.c_double()
-        it = self.lib.fn("pcg")(self.h, xp, bp, C.c_double(tol), int(max_it), hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt), C.byref(secs))
+        it = self.lib.fn("pcg_diag" if diagonal else "pcg")(self.h, xp, bp, C.c_double(tol), int(max_it), hist.ctypes.data_as(_f64p), len(hist),
+                                                            C.byref(cnt), C.byref(secs))
         self.last_seconds = secs.value
         return x, int(it), hist[: cnt.value].copy()
 
@@ -314,6 +322,11 @@ class PortLib(_Base):
 
     def threads(self):
         return int(self.fn("threads")())
+
+    def set_threads(self, n=None):
+        """Use n (default: every host core) OpenMP threads, whatever OMP_NUM_THREADS the launcher exported."""
+        self.fn("set_threads", None)(int(n or os.cpu_count() or 1))
+        return self.threads()
 
     def expand_dims(self, base_shape):
         ores = (C.c_int64 * 3)()
@@ -387,12 +400,13 @@ class _PortSolver:
         self.lib.fn("solver_vcycle", None)(self.h, xp, bp, int(use_initial_guess))
         return x
 
-    def pcg(self, x, b, tol, max_it):
+    def pcg(self, x, b, tol, max_it, diagonal=False):
         x, xp = _f64(np.array(x, copy=True))
         b, bp = _f64(b)
         hist = np.zeros(max_it + 2, dtype=np.float64)
         cnt = C.c_int()
-        it = self.lib.fn("pcg")(self.h, xp, bp, C.c_double(tol), int(max_it), hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt))
+        it = self.lib.fn("pcg_diag" if diagonal else "pcg")(self.h, xp, bp, C.c_double(tol), int(max_it), hist.ctypes.data_as(_f64p), len(hist),
+                                                            C.byref(cnt))
         return x, int(it), hist[: cnt.value].copy()
 
     def close(self):

@@ -853,12 +853,60 @@ void orc_solver_vcycle(OrcSolver *s, double *x, const double *b, int useInitialG
 
 /* CG.h:11-207 with the operators wired as Test.cpp:746-832 does. Returns the iteration index the reference
  * prints (CG.h:198), or -1 on the two early-outs (CG.h:35-40, :60-64). history[k] is the value CG.h:159 prints. */
+static int pcg_impl(OrcSolver *s, double *x, const double *b, double tol, int maxIt, int precond, double *history, int histCap, int *histCount);
 int orc_pcg(OrcSolver *s, double *x, const double *b, double tol, int maxIt, double *history, int histCap, int *histCount)
+{
+    return pcg_impl(s, x, b, tol, maxIt, 1, history, histCap, histCount);
+}
+/* The node's other mode (GFS.cpp:485-618): the same CG driver with the diagonal preconditioner, 1/6 on INTERIOR cells and
+ * 1/(sum of the six face weights) on BOUNDARY cells (GFS.cpp:520-548); destination = source * that (GFS.cpp:598). */
+int orc_pcg_diag(OrcSolver *s, double *x, const double *b, double tol, int maxIt, double *history, int histCap, int *histCount)
+{
+    return pcg_impl(s, x, b, tol, maxIt, 2, history, histCap, histCount);
+}
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+static void precondition(OrcSolver *s, int precond, const double *dinv, double *dst, const double *src)
+{
+    if (precond == 1) { orc_solver_vcycle(s, dst, src, 0); return; }
+    const i64 n = cells_of(s->res[0]);
+    const int *labels = s->labels[0];
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < n; ++i)
+	if (is_active(labels[i])) dst[i] = src[i] * dinv[i];
+}
+static int pcg_impl(OrcSolver *s, double *x, const double *b, double tol, int maxIt, int precond, double *history, int histCap, int *histCount)
 {
     const i64 *res = s->res[0];
     const int *labels = s->labels[0];
     const i64 n = cells_of(res);
     *histCount = 0;
+    double *dinv = NULL;
+    if (precond == 2)
+    {
+	const double *const w[3] = {s->w[0], s->w[1], s->w[2]};
+	dinv = (double *)calloc((size_t)n, sizeof(double));
+	for (i64 z = 0; z < res[2]; ++z)
+	    for (i64 y = 0; y < res[1]; ++y)
+		for (i64 xx = 0; xx < res[0]; ++xx)
+		{
+		    const i64 i = lin(res, xx, y, z);
+		    if (labels[i] == INTERIOR_CELL) dinv[i] = 1. / 6.;
+		    else if (labels[i] == BOUNDARY_CELL)
+		    {
+			double diagonal = 0;
+			for (int axis = 0; axis < 3; ++axis)
+			    for (int dir = 0; dir < 2; ++dir) diagonal += face_weight(w, res, xx, y, z, axis, dir);
+			dinv[i] = 1. / diagonal;
+		    }
+		}
+    }
     const double rhsNorm2 = orc_norm2(b, labels, res);
     if (rhsNorm2 == 0) return -1;
     double *r = (double *)calloc((size_t)n, sizeof(double));
@@ -872,7 +920,7 @@ int orc_pcg(OrcSolver *s, double *x, const double *b, double tol, int maxIt, dou
     int iteration = -1;
     if (!(rNorm2 < threshold))
     {
-	orc_solver_vcycle(s, p, r, 0);
+	precondition(s, precond, dinv, p, r);
 	double absNew = orc_dot(p, r, labels, res);
 	for (iteration = 0; iteration < maxIt; ++iteration)
 	{
@@ -883,13 +931,13 @@ int orc_pcg(OrcSolver *s, double *x, const double *b, double tol, int maxIt, dou
 	    rNorm2 = orc_norm2(r, labels, res);
 	    if (*histCount < histCap) history[(*histCount)++] = sqrt(rNorm2 / rhsNorm2);
 	    if (rNorm2 < threshold) break;
-	    orc_solver_vcycle(s, z, r, 0);
+	    precondition(s, precond, dinv, z, r);
 	    const double absOld = absNew;
 	    absNew = orc_dot(z, r, labels, res);
 	    const double beta = absNew / absOld;
 	    orc_add_scaled(p, z, p, beta, labels, res);
 	}
     }
-    free(r); free(p); free(z); free(t);
+    free(r); free(p); free(z); free(t); free(dinv);
     return iteration;
 }

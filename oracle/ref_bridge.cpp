@@ -436,11 +436,13 @@ double ref_solver_vcycle(RefSolver *s, double *x, const double *b, int useInitia
 }
 
 // CG.h:11-207 solveGeometricConjugateGradient wired exactly as Test.cpp:746-832 / GFS.cpp:430-483 do.
-// precond: 1 = multigrid V-cycle (needs s->mg), 0 = none requested is not a reference mode -> rejected.
+// precond: 1 = multigrid V-cycle (needs s->mg); 2 = the node's other mode, the diagonal preconditioner of GFS.cpp:485-603
+// (that file needs live SIM fields and cannot be compiled here, so its two lambdas are restated below over the same
+// containers: 1/6 on INTERIOR cells, 1/(sum of the six face weights) on BOUNDARY cells; destination = source * that).
 // history[k] = sqrt(|r_k|^2/|b|^2) for every iteration the loop ran (the value CG.h:159 prints).
 // Returns the iteration index CG.h:198 prints, or -1 on the two early-outs (CG.h:35-40, :60-64).
-int ref_pcg(RefSolver *s, double *x, const double *b, double tol, int maxIt, double *history, int histCap, int *histCount,
-	    double *solveSeconds)
+static int refPcgImpl(RefSolver *s, double *x, const double *b, double tol, int maxIt, int precond, double *history, int histCap, int *histCount,
+		      double *solveSeconds)
 {
     CoutSilencer quiet;
     UT_VoxelArray<Real> X, B;
@@ -450,9 +452,49 @@ int ref_pcg(RefSolver *s, double *x, const double *b, double tol, int maxIt, dou
     const WeightArray &weights = s->weights;
     HDK::GeometricMultigridPoissonSolver &mg = *s->mg;
 
+    // GFS.cpp:487-560
+    UT_VoxelArray<Real> diagonalPrecondGrid;
+    if (precond == 2)
+    {
+	diagonalPrecondGrid.size(labels.getVoxelRes()[0], labels.getVoxelRes()[1], labels.getVoxelRes()[2]);
+	diagonalPrecondGrid.constant(0);
+	Ops::uncompressActiveGrid(diagonalPrecondGrid, labels);
+	for (int64_t z = 0; z < s->res[2]; ++z)
+	    for (int64_t y = 0; y < s->res[1]; ++y)
+		for (int64_t xx = 0; xx < s->res[0]; ++xx)
+		{
+		    const int l = labels(xx, y, z);
+		    UT_Vector3I cell(xx, y, z);
+		    if (l == Ops::CellLabels::INTERIOR_CELL) diagonalPrecondGrid.setValue(cell, 1. / 6.);
+		    else if (l == Ops::CellLabels::BOUNDARY_CELL)
+		    {
+			double diagonal = 0;
+			for (int axis : {0, 1, 2})
+			    for (int direction : {0, 1})
+			    {
+				UT_Vector3I face = SIM::FieldUtils::cellToFaceMap(cell, axis, direction);
+				diagonal += weights[axis](face);
+			    }
+			diagonalPrecondGrid.setValue(cell, 1. / diagonal);
+		    }
+		}
+    }
+
     std::vector<double> norms;
     auto A = [&](UT_VoxelArray<Real> &dst, const UT_VoxelArray<Real> &src) { Ops::applyPoissonMatrix<Real>(dst, src, labels, &weights); };
-    auto M = [&](UT_VoxelArray<Real> &dst, const UT_VoxelArray<Real> &src) { mg.applyVCycle(dst, src); };
+    auto M = [&](UT_VoxelArray<Real> &dst, const UT_VoxelArray<Real> &src) {
+	if (precond == 1) { mg.applyVCycle(dst, src); return; }
+	// GFS.cpp:562-603
+	Ops::uncompressActiveGrid(dst, labels);
+	for (int64_t z = 0; z < s->res[2]; ++z)
+	    for (int64_t y = 0; y < s->res[1]; ++y)
+		for (int64_t xx = 0; xx < s->res[0]; ++xx)
+		{
+		    const int l = labels(xx, y, z);
+		    if (l == Ops::CellLabels::INTERIOR_CELL || l == Ops::CellLabels::BOUNDARY_CELL)
+			dst.setValue(xx, y, z, double(src(xx, y, z)) * double(diagonalPrecondGrid(xx, y, z)));
+		}
+    };
     auto dot = [&](const UT_VoxelArray<Real> &a, const UT_VoxelArray<Real> &c) { return Ops::dotProduct<Real>(a, c, labels); };
     auto norm2 = [&](const UT_VoxelArray<Real> &a) { double v = Ops::squaredL2Norm<Real>(a, labels); norms.push_back(v); return v; };
     auto axpy = [&](UT_VoxelArray<Real> &dst, const UT_VoxelArray<Real> &src, const Real sc) { Ops::addToVector<Real>(dst, src, sc, labels); };
@@ -473,5 +515,18 @@ int ref_pcg(RefSolver *s, double *x, const double *b, double tol, int maxIt, dou
     // CG.h prints the loop index at break; if the cap was hit it prints maxIt.
     if (loopCount > 0 && norms[1 + loopCount] < threshold) return int(loopCount) - 1;
     return int(loopCount);
+}
+int ref_pcg(RefSolver *s, double *x, const double *b, double tol, int maxIt, double *history, int histCap, int *histCount, double *solveSeconds)
+{
+    return refPcgImpl(s, x, b, tol, maxIt, 1, history, histCap, histCount, solveSeconds);
+}
+int ref_pcg_diag(RefSolver *s, double *x, const double *b, double tol, int maxIt, double *history, int histCap, int *histCount, double *solveSeconds)
+{
+    return refPcgImpl(s, x, b, tol, maxIt, 2, history, histCap, histCount, solveSeconds);
+}
+// bench.py --impl reference: use every host core even when the launcher (torchrun) exported OMP_NUM_THREADS=1
+void ref_set_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
 }
 } // extern "C"

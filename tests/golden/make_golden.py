@@ -98,6 +98,12 @@ def build_case(ref: RefLib, dbg: RefLib, name: str):
     xc = crop(x, off, base_labels.shape)
     out["pcg_x"] = xc if full else xc[::4, ::4, ::4].copy()
     out["pcg_x_norm2"] = float((x * x).sum())
+    # the node's other mode: diagonal-preconditioned CG (GFS.cpp:485-618), capped at 60 iterations (slow convergence)
+    xd, ditd, dhd = solver.pcg(np.zeros_like(b), b, 1e-6, 60, diagonal=True)
+    out["dpcg_iterations"] = ditd
+    out["dpcg_history"] = dhd
+    xdc = crop(xd, off, base_labels.shape)
+    out["dpcg_x"] = xdc if full else xdc[::4, ::4, ::4].copy()
     # one V-cycle on a seeded random rhs, and with an initial guess
     rb = D.random_rhs(labels, dx, seed=7)
     v = solver.vcycle(np.zeros_like(rb), rb)

@@ -60,6 +60,30 @@ def test_golden_pcg(gpu_ctx, name):
     s.close()
 
 
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_diagonal_pcg(gpu_ctx, name):
+    """preconditioner = 2: the reference node's diagonal-preconditioned mode (GFS.cpp:485-618), 60 iterations of the
+    reference's own CG driver on the fixture; also maxIt = 0 (CG.h:100: x untouched, iteration 0)."""
+    g = load_golden(name)
+    bl, bw, dx = base_inputs(name)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    b = rhs_for(labels, off, bl.shape, dx)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    x, iters, hist = s.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 60, useMGPreconditioner="diagonal")
+    assert iters == int(g["dpcg_iterations"]) and len(hist) == len(g["dpcg_history"])
+    # relative per iteration; a residual that hit round-off (the delta-rhs fixtures converge to 1e-20) is compared absolutely
+    assert (np.abs(hist - g["dpcg_history"]) <= 1e-7 * g["dpcg_history"] + 1e-15).all()
+    xc = crop(x, off, bl.shape)
+    gold = g["dpcg_x"]
+    if gold.shape != xc.shape:
+        xc = xc[::4, ::4, ::4]
+    assert relerr(xc, gold) < TOL_X
+    x0 = D.random_active(labels, 5, scale=dx * dx)
+    x1, it1, h1 = s.solveGeometricConjugateGradient(x0, b, 1e-6, 0)
+    assert it1 == 0 and len(h1) == 0 and (x1 == x0).all()
+    s.close()
+
+
 @pytest.mark.parametrize("name", FULL_CASES)
 def test_golden_vcycle_and_operators(gpu_ctx, name):
     g = load_golden(name)

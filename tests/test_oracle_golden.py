@@ -66,6 +66,25 @@ def test_pcg_history_and_solution(port, name):
     assert not x[~D.active_mask(labels)].any()
 
 
+@pytest.mark.parametrize("name", list(CASES))
+def test_diagonal_pcg_history_and_solution(port, name):
+    """The node's other mode (GFS.cpp:485-618): CG.h's driver with the diagonal preconditioner, capped at 60 iterations."""
+    g = load_golden(name)
+    bl, bw, dx = base_inputs(name)
+    labels, w, off, levels = port.expand_domain(bl, bw)
+    b = rhs_for(labels, off, bl.shape, dx)
+    s = port.solver(labels, w, levels, False)
+    x, iters, hist = s.pcg(np.zeros_like(b), b, 1e-6, 60, diagonal=True)
+    assert iters == int(g["dpcg_iterations"]) and len(hist) == len(g["dpcg_history"])
+    # relative per iteration; a residual that hit round-off (the delta-rhs fixtures converge to 1e-20) is compared absolutely
+    assert (np.abs(hist - g["dpcg_history"]) <= 1e-7 * g["dpcg_history"] + 1e-15).all()
+    xc = crop(x, off, bl.shape)
+    gold = g["dpcg_x"]
+    if gold.shape != xc.shape:
+        xc = xc[::4, ::4, ::4]
+    assert relerr(xc, gold) < 1e-9
+
+
 @pytest.mark.parametrize("name", FULL_CASES)
 def test_vcycle_and_operators(port, name):
     g = load_golden(name)
