@@ -119,8 +119,9 @@ def build_inputs(n):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_run(n, steps, warmup, budget_s=240.0):
-    """Times the reference's CPU implementation (constructor + PCG) on this box's host cores."""
+def cpu_reference_run(n, steps, warmup, budget_s=240.0, keep_solution=False):
+    """Times the reference's CPU implementation (constructor + PCG) on this box's host cores -- ALL of them: torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which round 1's N>1 reference arm silently obeyed."""
     from oracle import bindings
 
     kind = "reference"
@@ -131,12 +132,14 @@ def cpu_reference_run(n, steps, warmup, budget_s=240.0):
             bindings.build(ref=False)
         lib = bindings.PortLib()
         kind = "port"
+    lib.set_threads(os.cpu_count())
     base_labels, base_w, dx = build_inputs(n)
     labels, w, off, levels = lib.expand_domain(base_labels, base_w)
     b = D.random_rhs(labels, dx, SEED)
     times, setups, solves, iters, hist = [], [], [], None, None
     t_begin = time.perf_counter()
     done = 0
+    clamp = None
     for step in range(warmup + steps):
         t0 = time.perf_counter()
         s = lib.solver(labels, w, levels, False)
@@ -149,19 +152,25 @@ def cpu_reference_run(n, steps, warmup, budget_s=240.0):
             solves.append((getattr(s, "last_seconds", None) or (t2 - t1)) * 1e3)
             times.append(setups[-1] + solves[-1])
             done += 1
-        if time.perf_counter() - t_begin > budget_s and done >= 1:
+        if time.perf_counter() - t_begin > budget_s and done >= 1 and step + 1 < warmup + steps:
+            clamp = f"time budget of {budget_s:.0f} s reached after {done} of {steps} timed steps (one step is a ~2 s CPU solve)"
             break
-    return dict(kind=kind, cores=lib.threads(), ms=float(np.mean(times)), setup_ms=float(np.mean(setups)), solve_ms=float(np.mean(solves)),
-                steps=done, iterations=int(iters), final_rel_residual=float(hist[-1]) if len(hist) else None,
-                active_cells=int(D.active_mask(labels).sum()))
+    out = dict(kind=kind, cores=lib.threads(), ms=float(np.mean(times)), setup_ms=float(np.mean(setups)), solve_ms=float(np.mean(solves)),
+               steps=done, iterations=int(iters), final_rel_residual=float(hist[-1]) if len(hist) else None,
+               active_cells=int(D.active_mask(labels).sum()), history=[float(v) for v in hist], steps_clamped_reason=clamp)
+    if keep_solution:
+        out["x"] = x
+    return out
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    r = cpu_reference_run(args.size, min(args.steps, 3), min(args.warmup, 1))
+    # the driver's own --steps / --warmup, up to a stated time budget (a step is a ~2-3 s CPU solve)
+    r = cpu_reference_run(args.size, args.steps, args.warmup, budget_s=150.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["ms"], "unit": "ms", "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": METRIC, "value": r["ms"], "unit": "ms", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+        "steps_requested": args.steps, "steps_clamped_reason": r["steps_clamped_reason"],
         "ms_per_step": r["ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.size), "step": "solver constructor + PCG solve on the host cores", "iterations": r["iterations"],
                    "active_cells": r["active_cells"]},
@@ -171,6 +180,239 @@ def run_reference_arm(args, rank, world):
         "setup_ms": r["setup_ms"], "solve_only_ms": r["solve_ms"], "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ parity blocks
+def rel_history_dev(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    m = min(len(a), len(b))
+    if m == 0:
+        return 0.0
+    return float((np.abs(a[:m] - b[:m]) / np.abs(b[:m])).max())
+
+
+def gather_owned_box(torch, dist, X, off, hi, solver):
+    """The solution of a sharded solve as ONE dense array of the base box on every rank: each rank downloads its owned
+    z-planes (everything else 0) and the boxes are summed over the ranks."""
+    x = X.download()
+    box = np.ascontiguousarray(x[int(off[2]):hi[2], int(off[1]):hi[1], int(off[0]):hi[0]])
+    del x
+    if dist is not None:
+        t = torch.from_numpy(box).cuda()
+        dist.all_reduce(t)
+        box = t.cpu().numpy()
+    return box
+
+
+# ------------------------------------------------------------------------------------------------ 512^3 V-cycle sweep
+def measure_sweep(torch, api, ctx, dist, rank, world, n, steps, warmup, flush):
+    """BASELINE.json configs[3]: N^3 fully liquid box (one DIRICHLET layer), V-cycle only.  Returns the block bench lines carry
+    as `sweep512`: V-cycle ms (max over ranks), algorithmic GB/s, per-kernel-class fractions of the measured HBM peak."""
+    t0 = time.perf_counter()
+    bl, bw, dx = D.liquid_box_domain(n)
+    labels, w, off, levels, box = ctx.buildExpandedDomainLazy(bl, bw)
+    del bl, bw
+    solver = api.GeometricMultigridPoissonSolver(ctx, labels, w, levels, box=box)
+    active = solver.active_cells(0)
+    rng = np.random.default_rng(SEED)
+    b_host = np.zeros(labels.shape, dtype=np.float64)
+    sl = tuple(slice(int(box[0][2 - k]), int(box[1][2 - k])) for k in range(3))
+    b_host[sl] = rng.random(tuple(s.stop - s.start for s in sl)) * dx * dx * D.active_mask(labels[sl])
+    B, Z = solver.grid(0, b_host), solver.grid(0)
+    nlev = solver.getMGLevels()
+    del w, b_host, labels
+    build_s = time.perf_counter() - t0
+
+    def sync():
+        torch.cuda.synchronize()
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(warmup):
+        solver.applyVCycleDevice(Z, B)
+    sync()
+    ctx.launch_count(reset=True)
+    vc = []
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.timer_begin()
+        solver.applyVCycleDevice(Z, B)
+        vc.append(ctx.timer_end())
+    sync()
+    launches, comm_ops = ctx.launch_count(), ctx.comm_count()
+    ms = float(np.mean(vc))
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    nprof = 3
+    for _ in range(nprof):
+        solver.applyVCycleDevice(Z, B)
+    prof_fine = ctx.profile(True)
+    ctx.profile_enable(False)
+    peak, peak_kind = measured_peak()
+    fine = {k: v for k, v in prof_fine.items() if k not in ("setup", "coarse_solve", "halo_exchange") and v[1] > 0 and v[2] > 0}
+    classes = {k: {"us_per_launch": v[0] / v[1] * 1e3, "launches_per_vcycle": v[1] // nprof, "algorithmic_gbs": v[2] / (v[0] * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": v[2] / (v[0] * 1e-3) / 1e9 / peak, "traffic_bytes_per_launch": ncu_traffic(f"vcycle{n}", k)} for k, v in fine.items()}
+    halo = prof_fine.get("halo_exchange")
+    dom = max(fine, key=lambda k: fine[k][0])
+    d_ms, d_n, d_bytes = fine[dom]
+    achieved = d_bytes / (d_ms * 1e-3) / 1e9
+    vb = BYTES_VCYCLE_PER_CELL * active
+    out = {
+        "workload": f"{n}^3 fully liquid box (one DIRICHLET layer), expanded {2 * n}^3, one V-cycle, Jacobi smoother", "levels": nlev, "active_cells": active,
+        "vcycle_ms": ms, "steps": steps, "warmup": warmup, "l2": "256 MB flush write before every timed V-cycle",
+        "vcycle_algorithmic_gbs": vb / (ms * 1e-3) / 1e9, "vcycle_frac_of_hbm_peak": vb / (ms * 1e-3) / 1e9 / peak / world,
+        "algorithmic_bytes_per_cell": BYTES_VCYCLE_PER_CELL,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(f"vcycle{n}", dom), "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "launches": d_n,
+                     "avg_launch_us": d_ms / d_n * 1e3, "algorithmic_bytes_per_launch": d_bytes / d_n},
+        "fine_level_kernels": classes,
+        "halo_exchange_ms_per_vcycle": (halo[0] / nprof) if halo and halo[1] else 0.0,
+        "kernel_timing": "CUDA event nodes inside the replayed V-cycle graph (rank 0's slab when sharded)",
+        "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "host_build_s": build_s,
+        "parallelism": "single GPU" if world == 1 else f"{world} z-slabs",
+    }
+    B.close(); Z.close(); solver.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ 1024^3 narrow band
+def narrow_band_labels_u8(n, thickness=12):
+    """BASELINE.json configs[4] without ever holding a dense n^3 float array: the EXPANDED one-byte label
+    grid is np.zeros (pages outside the base box are never materialised) and the base box is filled plane by plane with
+    terrain h(x,z) = N(0.5 + 0.1 sin(2 pi x/N) sin(2 pi z/N)); y < h - thickness solid, <= h liquid, above air; walls solid.
+    BOUNDARY cells by the rule of setBoundaryCellLabels with unit weights (Ops.h:1574-1644): an INTERIOR cell with a DIRICHLET
+    or EXTERIOR 6-neighbour.  Returns (labels uint8 expanded, offset, mgLevels, (lo, hi))."""
+    from geometricmultigridpressuresolver_b200 import api
+
+    shape, off, levels = api.expand_dims((n, n, n))
+    labels = np.zeros(shape, dtype=np.uint8)
+    i = np.arange(n, dtype=np.float64)[None, :]
+    j = np.arange(n, dtype=np.float64)[:, None]
+
+    def plane(k):
+        if k <= 0 or k >= n - 1:
+            return np.full((n, n), D.EXTERIOR, dtype=np.uint8)
+        h = n * (0.5 + 0.1 * np.sin(2 * np.pi * i / n) * np.sin(2 * np.pi * k / n))
+        p = np.where(j > h, D.DIRICHLET, np.where(j < h - thickness, D.EXTERIOR, D.INTERIOR)).astype(np.uint8)
+        p[:, 0] = D.EXTERIOR
+        p[:, n - 1] = D.EXTERIOR
+        p[0, :] = D.EXTERIOR
+        return p
+
+    prev, cur = plane(-1), plane(0)
+    ox, oy, oz = int(off[0]), int(off[1]), int(off[2])
+    for k in range(n):
+        nxt = plane(k + 1)
+        nonint = cur != D.INTERIOR  # DIRICHLET or EXTERIOR (BOUNDARY does not exist yet in cur/prev/nxt)
+        nb = (prev != D.INTERIOR) | (nxt != D.INTERIOR)
+        nb[1:, :] |= nonint[:-1, :]
+        nb[:-1, :] |= nonint[1:, :]
+        nb[:, 1:] |= nonint[:, :-1]
+        nb[:, :-1] |= nonint[:, 1:]
+        out = cur.copy()
+        out[(cur == D.INTERIOR) & nb] = D.BOUNDARY
+        labels[oz + k, oy:oy + n, ox:ox + n] = out
+        prev, cur = cur, nxt
+    hi = [ox + n, oy + n, oz + n]
+    return labels, off, levels, (off, hi)
+
+
+def measure_narrow(torch, api, ctx, dist, rank, world, local_rank, n, flush, thickness=12):
+    """configs[4]: n^3 narrow-band liquid sheet, MGPCG to 1e-6 on `world` z-slabs; 1-vs-N agreement against an unsharded solve on
+    rank 0 (iteration count, residual history, |x|^2)."""
+    out = {"workload": f"{n}^3 narrow-band liquid sheet ({thickness} cells) over sinusoidal terrain, expanded {2 * n}^3, unit face weights, MGPCG to 1e-6"}
+    try:
+        t0 = time.perf_counter()
+        labels, off, levels, box = narrow_band_labels_u8(n, thickness)
+        gen_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        solver = api.GeometricMultigridPoissonSolver(ctx, labels, None, levels, box=box)
+        setup_s = time.perf_counter() - t0
+        sl = tuple(slice(int(box[0][2 - k]), int(box[1][2 - k])) for k in range(3))
+        act = D.active_mask(labels[sl])
+        b_host = np.zeros(labels.shape, dtype=np.float64)
+        rng = np.random.default_rng(SEED)
+        sub = np.zeros(act.shape, dtype=np.float64)
+        sub[act] = rng.random(int(act.sum())) / float(n * n)
+        b_host[sl] = sub
+        del sub
+        B, X = solver.grid(0, b_host), solver.grid(0)
+        active = solver.active_cells(0)
+        box_cells = int(np.prod([s.stop - s.start for s in sl]))
+
+        def one():
+            X.zero()
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            ctx.timer_begin()
+            it, hist = solver.solveDevice(X, B, TOL, MAX_IT)
+            return ctx.timer_end(), it, hist
+
+        one()
+        ms = []
+        for _ in range(3):
+            t, it, hist = one()
+            ms.append(t)
+        val = float(np.mean(ms))
+        xx = solver.dotProduct(X, X)
+        if dist is not None:
+            t = torch.tensor([val], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            val = float(t.item())
+        # one V-cycle for the bandwidth figure
+        Z = solver.grid(0)
+        solver.applyVCycleDevice(Z, B)
+        vc = []
+        for _ in range(5):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            ctx.timer_begin()
+            solver.applyVCycleDevice(Z, B)
+            vc.append(ctx.timer_end())
+        vms = float(np.mean(vc))
+        if dist is not None:
+            t = torch.tensor([vms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            vms = float(t.item())
+        peak, _ = measured_peak()
+        nlev = solver.getMGLevels()
+        sharded = [l for l in range(nlev) if solver.shard_info(l)[0]]
+        out.update({"levels_requested": int(levels), "levels": nlev, "active_cells": int(active), "occupancy_of_base_grid": active / float(n) ** 3,
+                    "stored_box_cells": box_cells, "coarse_unknowns": solver.coarse_unknowns(), "solve_ms": val, "iterations": int(it),
+                    "final_rel_residual": float(hist[-1]), "vcycle_ms": vms,
+                    "vcycle_algorithmic_gbs": BYTES_VCYCLE_PER_CELL * active / (vms * 1e-3) / 1e9,
+                    "vcycle_frac_of_hbm_peak": BYTES_VCYCLE_PER_CELL * active / (vms * 1e-3) / 1e9 / peak / world,
+                    "sharded_levels": sharded, "setup_s": setup_s, "label_generation_s": gen_s, "steps": 3, "warmup": 1})
+        Z.close(); B.close(); X.close(); solver.close()
+        if world > 1:
+            agree = None
+            if rank == 0:
+                ctx1 = api.Context(local_rank)
+                s1 = api.GeometricMultigridPoissonSolver(ctx1, labels, None, levels, box=box)
+                B1, X1 = s1.grid(0, b_host), s1.grid(0)
+                it1, hist1 = s1.solveDevice(X1, B1, TOL, MAX_IT)
+                ctx1.timer_begin()
+                X1.zero()
+                it1, hist1 = s1.solveDevice(X1, B1, TOL, MAX_IT)
+                ms1 = ctx1.timer_end()
+                xx1 = s1.dotProduct(X1, X1)
+                agree = {"n1_solve_ms": ms1, "iterations_equal": bool(it1 == it), "max_rel_history_dev": rel_history_dev(hist, hist1),
+                         "rel_dev_x_norm2": abs(xx - xx1) / xx1, "bar": 1e-12}
+                B1.close(); X1.close(); s1.close(); ctx1.close()
+            out["agreement_1_vs_n"] = agree
+    except Exception as e:  # a refused configuration (e.g. a coarsest level beyond the dense direct solve) is reported, not fatal
+        out["error"] = f"{type(e).__name__}: {e}"
+    if dist is not None:
+        dist.barrier()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -275,7 +517,7 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---- e2e: host buffers through the reference-facing calls (every rank takes part; max over ranks) ------
     e2e = None
-    if True:
+    if not args.quick:
         # every host buffer the reference-facing calls take is page-locked (the contract's "pinned host memory"): the
         # library then DMAs the cropped box straight out of / into the caller's arrays
         rt = torch.cuda.cudart()
@@ -328,7 +570,7 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---- the reference's production smoother (tiled Gauss-Seidel, GFS.cpp:463-466), reported beside the Jacobi headline ----
     gs = None
-    if world == 1:
+    if world == 1 and not args.quick:
         sg = api.GeometricMultigridPoissonSolver(ctx, labels, w, levels, box=box, useGaussSeidel=True)
         Bg, Xg = sg.grid(0, b_host), sg.grid(0)
         gms = []
@@ -346,22 +588,69 @@ def run_gpu_arm(args, rank, world, local_rank):
               "what": "same solve with useGaussSeidel = true (tiled Gauss-Seidel wavefront kernel), mean of 3 after 2 warm-ups"}
         sg.close()
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(n, 1, 0)
+    # ---- parity, asserted (a failed bar makes the process exit non-zero after the line is printed) -------------------------
+    parity_failed = []
+    X.zero()
+    it, hist = solver.solveDevice(X, B, TOL, MAX_IT)
+    x_box = gather_owned_box(torch, dist, X, off, hi, solver)
+    cpu, parity_vs_cpu, parity_vs_n1 = None, None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
+        # the reference's own sources on this box's host cores, same inputs: timed (cpu_baseline) AND compared
+        r = cpu_reference_run(n, 1, 0, keep_solution=True)
         cpu = {"value": r["ms"], "unit": "ms", "cores": r["cores"], "kind": r["kind"],
                "sample": f"full {n}^3 workload once: constructor {r['setup_ms']:.0f} ms + PCG {r['solve_ms']:.0f} ms, {r['iterations'] + 1} iterations",
                "iterations": r["iterations"], "final_rel_residual": r["final_rel_residual"]}
+        xr = r.pop("x")[int(off[2]):hi[2], int(off[1]):hi[1], int(off[0]):hi[0]]
+        parity_vs_cpu = {"iterations_gpu": int(it), "iterations_cpu": int(r["iterations"]), "iterations_equal": bool(int(it) == int(r["iterations"])),
+                         "max_rel_history_dev": rel_history_dev(hist, r["history"]),
+                         "max_rel_x_dev": float(np.abs(x_box - xr).max() / np.abs(xr).max()),
+                         "bars": {"history": 1e-5, "x": 1e-5, "iterations": "+-1"}, "oracle": r["kind"]}
+        if abs(int(it) - int(r["iterations"])) > 1 or parity_vs_cpu["max_rel_history_dev"] > 1e-5 or parity_vs_cpu["max_rel_x_dev"] > 1e-5:
+            parity_failed.append("parity_vs_cpu")
+        del xr
+    if world > 1:
+        # the driver's GPU test box has one GPU, so the sharded path proves itself here: rank 0 repeats the solve on an
+        # UNSHARDED context of its own GPU and the line carries the deviation; history deviation above 1e-9 fails the run
+        if rank == 0:
+            ctx1 = api.Context(local_rank)
+            s1 = api.GeometricMultigridPoissonSolver(ctx1, labels, w, levels, box=box)
+            B1, X1 = s1.grid(0, b_host), s1.grid(0)
+            it1, hist1 = s1.solveDevice(X1, B1, TOL, MAX_IT)
+            x1 = X1.download()[int(off[2]):hi[2], int(off[1]):hi[1], int(off[0]):hi[0]]
+            parity_vs_n1 = {"iterations_equal": bool(it1 == it), "max_rel_history_dev": rel_history_dev(hist, hist1),
+                            "max_rel_x_dev": float(np.abs(x_box - x1).max() / np.abs(x1).max()), "bars": {"history": 1e-9, "x": 1e-9}}
+            if it1 != it or parity_vs_n1["max_rel_history_dev"] > 1e-9 or parity_vs_n1["max_rel_x_dev"] > 1e-9:
+                parity_failed.append("parity_vs_n1")
+            B1.close(); X1.close(); s1.close(); ctx1.close()
+            del x1
+        dist.barrier()
+    del x_box
+    n_levels, shard_desc = solver.getMGLevels(), None
+    if world > 1:
+        shard_desc = f"{world} z-slabs, levels 0..{sum(1 for l in range(n_levels) if solver.shard_info(l)[0]) - 1} sharded with deep halos, coarser levels replicated"
+    setup_ms_resident = solver.setup_ms()
+    # ---- the HBM-bound and the sparse configurations, in the same line (BASELINE.json configs[3] and [4]) -------------------
+    B.close(); X.close(); Z.close(); solver.close()
+    del labels, w, b_host
+    sweep = None
+    if not args.no_sweep and not args.quick:
+        sweep = measure_sweep(torch, api, ctx, dist, rank, world, args.sweep_size, 10, 3, flush)
+    narrow = None
+    narrow_size = args.narrow_size if args.narrow_size is not None else (1024 if world == 8 else 0)
+    if narrow_size:
+        narrow = measure_narrow(torch, api, ctx, dist, rank, world, local_rank, narrow_size, flush)
+        ag = (narrow or {}).get("agreement_1_vs_n")
+        if ag and (not ag["iterations_equal"] or ag["max_rel_history_dev"] > 1e-9):
+            parity_failed.append("narrow_agreement_1_vs_n")
 
     if rank == 0:
         vcycle_bytes = BYTES_VCYCLE_PER_CELL * active
         line = {
             "metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n), "levels": solver.getMGLevels(), "active_cells": active, "l2": "256 MB flush write before every timed step",
-                       "parallelism": "single GPU" if world == 1 else
-                       f"{world} z-slabs over NCCL, levels 0..{sum(1 for l in range(solver.getMGLevels()) if solver.shard_info(l)[0]) - 1} sharded with deep halos, coarser levels replicated"},
-            "iterations": int(it), "final_rel_residual": float(hist[-1]), "setup_ms": solver.setup_ms(),
+            "config": {"workload": workload_name(n), "levels": n_levels, "active_cells": active, "l2": "256 MB flush write before every timed step",
+                       "parallelism": "single GPU" if world == 1 else shard_desc},
+            "iterations": int(it), "final_rel_residual": float(hist[-1]), "setup_ms": setup_ms_resident,
             "vcycle_ms": vcycle_ms, "vcycle_algorithmic_gbs": vcycle_bytes / (vcycle_ms * 1e-3) / 1e9,
             "vcycle_frac_of_hbm_peak": vcycle_bytes / (vcycle_ms * 1e-3) / 1e9 / peak,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -370,17 +659,23 @@ def run_gpu_arm(args, rank, world, local_rank):
             "kernels": kernels, "kernels_by_level": by_level,
             "kernel_timing": "CUDA events recorded as nodes inside the replayed PCG graphs (warm L2, back-to-back launches); separate pass from `value`",
             "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "gauss_seidel": gs, "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "wall_s_timed_region": wall_s,
+            "parity_vs_cpu": parity_vs_cpu, "parity_vs_n1": parity_vs_n1, "parity_failed": parity_failed,
+            "sweep512": sweep, "narrow1024": narrow,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        t = torch.tensor([float(len(parity_failed))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity_failed = parity_failed or (["on another rank"] if t.item() > 0 else [])
         dist.barrier()
         dist.destroy_process_group()
+    if parity_failed:
+        sys.exit(f"bench.py: parity bar missed: {parity_failed}")
 
 
 # ------------------------------------------------------------------------------------------------ V-cycle sweep (BASELINE config 4)
 def run_vcycle_sweep(args, rank, world, local_rank):
-    """--workload vcycle: N^3 fully liquid box (BASELINE.json configs[3]; default 512^3 = 134 M cells), V-cycle only.
-    Per kernel class: algorithmic bytes / device time on the fine level, against the measured HBM peak."""
+    """--workload vcycle: the sweep512 block (BASELINE.json configs[3]) as a line of its own, at any --size."""
     import torch
 
     from geometricmultigridpressuresolver_b200 import api
@@ -394,78 +689,17 @@ def run_vcycle_sweep(args, rank, world, local_rank):
     ctx = api.Context(local_rank)
     if dist is not None:
         ctx.shard_with_torch(dist)
-    n = args.size
-    t0 = time.perf_counter()
-    bl, bw, dx = D.liquid_box_domain(n)
-    labels, w, off, levels, box = ctx.buildExpandedDomainLazy(bl, bw)
-    del bl, bw
-    solver = api.GeometricMultigridPoissonSolver(ctx, labels, w, levels, box=box)
-    active = solver.active_cells(0)
-    rng = np.random.default_rng(SEED)
-    b_host = np.zeros(labels.shape, dtype=np.float64)
-    sl = tuple(slice(int(box[0][2 - k]), int(box[1][2 - k])) for k in range(3))
-    b_host[sl] = rng.random(tuple(s.stop - s.start for s in sl)) * dx * dx * D.active_mask(labels[sl])
-    B, Z = solver.grid(0, b_host), solver.grid(0)
-    del w, b_host
-    build_s = time.perf_counter() - t0
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-
-    def sync():
-        torch.cuda.synchronize()
-        ctx.synchronize()
-        if dist is not None:
-            dist.barrier()
-
-    for _ in range(args.warmup):
-        solver.applyVCycleDevice(Z, B)
     sampler = ClockSampler(local_rank)
-    sync()
     sampler.start()
-    ctx.launch_count(reset=True)
-    vc = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        ctx.timer_begin()
-        solver.applyVCycleDevice(Z, B)
-        vc.append(ctx.timer_end())
-    sync()
-    launches, comm_ops = ctx.launch_count(), ctx.comm_count()
+    blk = measure_sweep(torch, api, ctx, dist, rank, world, args.size, args.steps, args.warmup, flush)
     clocks = sampler.stop()
-    ms = float(np.mean(vc))
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ctx.profile_enable(True)
-    ctx.profile_reset()
-    nprof = 3
-    for _ in range(nprof):
-        solver.applyVCycleDevice(Z, B)
-    prof_all, prof_fine = ctx.profile(False), ctx.profile(True)
-    ctx.profile_enable(False)
-    peak, peak_kind = measured_peak()
-    fine = {k: v for k, v in prof_fine.items() if k not in ("setup", "coarse_solve", "halo_exchange") and v[1] > 0 and v[2] > 0}
-    classes = {k: {"us_per_launch": v[0] / v[1] * 1e3, "launches_per_vcycle": v[1] // nprof, "algorithmic_gbs": v[2] / (v[0] * 1e-3) / 1e9,
-                   "frac_of_hbm_peak": v[2] / (v[0] * 1e-3) / 1e9 / peak} for k, v in fine.items()}
-    dom = max(fine, key=lambda k: fine[k][0])
-    d_ms, d_n, d_bytes = fine[dom]
-    achieved = d_bytes / (d_ms * 1e-3) / 1e9
     if rank == 0:
-        vb = BYTES_VCYCLE_PER_CELL * active
-        line = {
-            "metric": "vcycle_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{n}^3 fully liquid box (one DIRICHLET layer), expanded {2 * n}^3, one V-cycle, Jacobi smoother", "levels": solver.getMGLevels(),
-                       "active_cells": active, "l2": "256 MB flush write before every timed step",
-                       "parallelism": "single GPU" if world == 1 else f"{world} z-slabs over NCCL"},
-            "vcycle_algorithmic_gbs": vb / (ms * 1e-3) / 1e9, "vcycle_frac_of_hbm_peak": vb / (ms * 1e-3) / 1e9 / peak / world,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(f"vcycle{n}", dom),
-                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "launches": d_n, "avg_launch_us": d_ms / d_n * 1e3,
-                         "algorithmic_bytes_per_launch": d_bytes / d_n},
-            "fine_level_kernels": classes, "kernel_timing": "CUDA event nodes inside the replayed V-cycle graph (rank 0's slab when sharded)",
-            "clocks": clocks, "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "host_build_s": build_s,
-        }
+        line = {"metric": "vcycle_ms", "value": blk["vcycle_ms"], "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": blk["vcycle_ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": blk["workload"], "levels": blk["levels"], "active_cells": blk["active_cells"], "l2": blk["l2"],
+                           "parallelism": blk["parallelism"]}, "clocks": clocks}
+        line.update({k: v for k, v in blk.items() if k not in ("workload", "levels", "active_cells", "l2", "parallelism", "steps", "warmup")})
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -481,6 +715,10 @@ def main():
     ap.add_argument("--workload", default="pcg", choices=["pcg", "vcycle"], help="pcg: the headline 256^3 MGPCG solve; vcycle: V-cycle-only sweep (config 4)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="A/B runs: value, V-cycle and per-kernel times only (no e2e, Gauss-Seidel, CPU baseline, sweep512)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the sweep512 block (BASELINE.json configs[3]) of the default run")
+    ap.add_argument("--sweep-size", type=int, default=512)
+    ap.add_argument("--narrow-size", type=int, default=None, help="narrow-band block size (default: 1024 at 8 GPUs, else off; 0 = off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.size is None:

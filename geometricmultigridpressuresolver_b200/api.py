@@ -33,7 +33,7 @@ STATUS = {0: "GMG_OK", 1: "GMG_ERR_CUDA", 2: "GMG_ERR_INVALID", 3: "GMG_ERR_NO_A
 ABI_SYMBOLS = [
     "gmg_last_error", "gmg_version", "gmg_ctx_create", "gmg_ctx_destroy", "gmg_ctx_synchronize", "gmg_ctx_shard", "gmg_nccl_unique_id", "gmg_ctx_rank", "gmg_shard_plan", "gmg_solver_shard_info", "gmg_comm_count", "gmg_comm_benchmark",
     "gmg_expand_dims", "gmg_expand_labels", "gmg_expand_weights", "gmg_set_boundary_labels", "gmg_coarsen_labels", "gmg_boundary_cells",
-    "gmg_solver_default_options", "gmg_solver_create", "gmg_solver_destroy", "gmg_solver_levels", "gmg_solver_level_res",
+    "gmg_solver_default_options", "gmg_solver_create", "gmg_solver_create_u8", "gmg_solver_destroy", "gmg_solver_levels", "gmg_solver_level_res",
     "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms", "gmg_solver_transfer_cells", "gmg_transfer_plan", "gmg_gather_face_weights",
     "gmg_vcycle", "gmg_pcg", "gmg_grid_create", "gmg_grid_destroy", "gmg_grid_upload", "gmg_grid_download", "gmg_grid_zero", "gmg_grid_copy",
     "gmg_jacobi", "gmg_gauss_seidel", "gmg_boundary_jacobi", "gmg_apply", "gmg_residual", "gmg_restrict", "gmg_prolong_add", "gmg_dot", "gmg_norm2", "gmg_inf_norm",
@@ -369,10 +369,19 @@ class GeometricMultigridPoissonSolver:
                  coarse_matrix_scale: float = 1.0, box=None, boundary_iterations: int = 3, boundary_width: int = 3):
         self.ctx = ctx
         self.lib = ctx.lib
-        l, lp = _i32(initialCellLabels)
-        ws = [_f64(w) for w in boundaryWeights]
-        for a in range(3):
-            assert ws[a][0].shape == face_shape(l.shape, a), "boundary weight grid shape (MG.cpp:167-177)"
+        # one-byte labels (uint8 / int8 arrays) go through gmg_solver_create_u8: a quarter of the host memory and PCIe traffic
+        byte_labels = np.asarray(initialCellLabels).dtype.itemsize == 1
+        if byte_labels:
+            l = np.ascontiguousarray(initialCellLabels).view(np.uint8)
+            lp = l.ctypes.data_as(C.c_void_p)
+        else:
+            l, lp = _i32(initialCellLabels)
+        if boundaryWeights is None:  # the operators' `boundaryWeights == nullptr` form: weight 1 (Ops.h:237-248)
+            ws = [(None, None)] * 3
+        else:
+            ws = [_f64(w) for w in boundaryWeights]
+            for a in range(3):
+                assert ws[a][0].shape == face_shape(l.shape, a), "boundary weight grid shape (MG.cpp:167-177)"
         opt = SolverOptions()
         self.lib.gmg_solver_default_options(C.byref(opt))
         opt.use_gauss_seidel = int(useGaussSeidel)
@@ -385,7 +394,8 @@ class GeometricMultigridPoissonSolver:
                 opt.box_lo[a] = int(box[0][a])
                 opt.box_hi[a] = int(box[1][a])
         h = C.c_void_p()
-        _check(self.lib.gmg_solver_create(ctx.h, lp, _res(l.shape), ws[0][1], ws[1][1], ws[2][1], int(mgLevels), C.byref(opt), C.byref(h)))
+        create = self.lib.gmg_solver_create_u8 if byte_labels else self.lib.gmg_solver_create
+        _check(create(ctx.h, lp, _res(l.shape), ws[0][1], ws[1][1], ws[2][1], int(mgLevels), C.byref(opt), C.byref(h)))
         self.h = h
         self.shape = l.shape
 

@@ -236,6 +236,21 @@ extern "C" int gmg_ctx_create(int device, void *stream, gmg_ctx **out)
 	cudaDeviceProp prop;
 	GMG_CUDA(cudaGetDeviceProperties(&prop, device));
 	ctx->smCount = prop.multiProcessorCount;
+	{
+	    // up to half of L2 set aside for persisting lines (the band slab of the solver in use, applyBandWindow)
+	    const char *e = getenv("GMG_L2_PERSIST");
+	    if (!(e && e[0] == '0') && prop.persistingL2CacheMaxSize > 0)
+	    {
+		size_t want = std::min<size_t>(size_t(prop.persistingL2CacheMaxSize), size_t(prop.l2CacheSize) / 2);
+		if (e && atoi(e) > 1) want = std::min<size_t>(size_t(prop.persistingL2CacheMaxSize), size_t(atoi(e)) << 20);
+		if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+		{
+		    ctx->persistBytes = want;
+		    ctx->maxWindowBytes = size_t(prop.accessPolicyMaxWindowSize);
+		}
+		else cudaGetLastError();
+	    }
+	}
 	GMG_CUDA(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
 	GMG_CUDA(cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
 	GMG_CUDA(cudaMalloc(&ctx->scalars, sizeof(Scalars)));
@@ -672,7 +687,8 @@ static int copyBoxD2H(gmg_ctx *ctx, T *host, const T *staging, const int64_t hos
 }
 
 // host scan for the [lo,hi) bounds of non-EXTERIOR labels (used when the caller gives no hint)
-static bool scanBounds(const int32_t *labels, const int64_t res[3], int64_t lo[3], int64_t hi[3])
+template <typename LabelT>
+static bool scanBounds(const LabelT *labels, const int64_t res[3], int64_t lo[3], int64_t hi[3])
 {
     const int nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<std::array<int64_t, 6>> part(nt);
@@ -683,7 +699,7 @@ static bool scanBounds(const int32_t *labels, const int64_t res[3], int64_t lo[3
 	    for (int64_t z = t; z < res[2]; z += nt)
 		for (int64_t y = 0; y < res[1]; ++y)
 		{
-		    const int32_t *row = labels + res[0] * (y + res[1] * z);
+		    const LabelT *row = labels + res[0] * (y + res[1] * z);
 		    int64_t x0 = 0, x1 = res[0] - 1;
 		    while (x0 <= x1 && row[x0] == L_EXTERIOR) ++x0;
 		    if (x0 > x1) continue;
@@ -703,7 +719,8 @@ static bool scanBounds(const int32_t *labels, const int64_t res[3], int64_t lo[3
     return true;
 }
 
-static int uploadLabels(gmg_ctx *ctx, uint8_t *dst, const int32_t *host, const int64_t res[3], const Geom &g, const int64_t *bounds = nullptr)
+template <typename LabelT>
+static int uploadLabels(gmg_ctx *ctx, uint8_t *dst, const LabelT *host, const int64_t res[3], const Geom &g, const int64_t *bounds = nullptr)
 {
     int lo[3], hi[3];
     const BoxArgs ba = boxArgs(g);
@@ -712,13 +729,13 @@ static int uploadLabels(gmg_ctx *ctx, uint8_t *dst, const int32_t *host, const i
 	GMG_CUDA(cudaMemsetAsync(dst, L_EXTERIOR, g.total, ctx->stream));
 	return GMG_OK;
     }
-    int32_t *staging = nullptr;
+    LabelT *staging = nullptr;
     const int64_t cnt = int64_t(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-    GMG_CUDA(devMalloc(&staging, sizeof(int32_t) * cnt));
+    GMG_CUDA(devMalloc(&staging, sizeof(LabelT) * cnt));
     GMG_TRY(copyBoxH2D(ctx, staging, host, res, g, lo, hi));
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_labels_from_i32<<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dst, staging, ba, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
+	k_labels_from_host<LabelT><<<unsigned(divUp(g.total, BLOCK)), BLOCK, 0, ctx->stream>>>(dst, staging, ba, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
     }
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_CUDA(devFree(staging));
@@ -884,16 +901,32 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
     L.nBoundary = nB;
     L.nBand = nB + nI;
     const int nBand = L.nBand;
-    GMG_CUDA(devMalloc(&L.bandIdx, sizeof(int32_t) * std::max(nBand, 1)));
+    // ONE slab per level for everything the band sweeps touch (indices, neighbour references, the three compact value
+    // arrays, the coefficient records): a single address range that can be given an L2 persisting access-policy window
+    // (bandWindow below), so the twelve sweeps of a V-cycle find their metadata in L2 instead of re-reading it from HBM
+    // after every full-grid pass has streamed through the cache.
+    {
+	size_t off = 0;
+	auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+	const size_t n1 = size_t(std::max(nBand, 1)), nb1 = size_t(std::max(nB, 1));
+	const size_t oIdx = take(sizeof(int32_t) * n1), oRef = take(sizeof(int32_t) * 6 * n1), oV0 = take(sizeof(double) * n1), oV1 = take(sizeof(double) * n1),
+		     oB = take(sizeof(double) * n1), oCoef = take(sizeof(double) * 8 * nb1);
+	char *slab = nullptr;
+	GMG_CUDA(devMalloc(&slab, off));
+	L.bandSlab = slab;
+	L.bandSlabBytes = off;
+	L.bandIdx = reinterpret_cast<int32_t *>(slab + oIdx);
+	L.bandRef = reinterpret_cast<int32_t *>(slab + oRef);
+	L.bandV0 = reinterpret_cast<double *>(slab + oV0);
+	L.bandV1 = reinterpret_cast<double *>(slab + oV1);
+	L.bandB = reinterpret_cast<double *>(slab + oB);
+	L.bcoef = reinterpret_cast<double *>(slab + oCoef);
+    }
     GMG_CUDA(cudaMemcpyAsync(L.bandIdx, idxB, sizeof(int32_t) * nB, cudaMemcpyDeviceToDevice, ctx->stream));
     GMG_CUDA(cudaMemcpyAsync(L.bandIdx + nB, idxI, sizeof(int32_t) * nI, cudaMemcpyDeviceToDevice, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     GMG_CUDA(devFree(idxB));
     GMG_CUDA(devFree(idxI));
-    GMG_CUDA(devMalloc(&L.bandRef, sizeof(int32_t) * 6 * std::max(nBand, 1)));
-    GMG_CUDA(devMalloc(&L.bandV0, sizeof(double) * std::max(nBand, 1)));
-    GMG_CUDA(devMalloc(&L.bandV1, sizeof(double) * std::max(nBand, 1)));
-    GMG_CUDA(devMalloc(&L.bandB, sizeof(double) * std::max(nBand, 1)));
     if (nBand > 0)
     {
 	// one guard plane each side: band cells of a slab's first / last stored plane look one plane out
@@ -921,7 +954,6 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 
 static int buildCoefs(gmg_ctx *ctx, Level &L, const double *w0, const double *w1, const double *w2)
 {
-    GMG_CUDA(devMalloc(&L.bcoef, sizeof(double) * 8 * std::max(L.nBoundary, 1)));
     if (L.nBoundary > 0)
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
@@ -1023,7 +1055,6 @@ static int buildCoefsSparse(gmg_ctx *ctx, Level &L, const double *w0, const doub
 			    CoefJob *job)
 {
     const int nB = L.nBoundary;
-    GMG_CUDA(devMalloc(&L.bcoef, sizeof(double) * 8 * std::max(nB, 1)));
     L.hasWeights = true;
     if (nB == 0) return GMG_OK;
     const Geom &g = L.g;
@@ -1253,8 +1284,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 
 static void freeLevel(Level &L)
 {
-    devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandIdx); devFree(L.bandRef); devFree(L.bcoef);
-    devFree(L.bandV0); devFree(L.bandV1); devFree(L.bandB);
+    devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab);
     devFree(L.chunksInterior); devFree(L.chunksActive);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
@@ -1349,7 +1379,8 @@ extern "C" int gmg_expand_weights(gmg_ctx *ctx, const double *baseW, const int64
     return GMG_OK;
 }
 
-static int boundsFromHintOrScan(const int32_t *labels, const int64_t res[3], const int64_t *hLo, const int64_t *hHi, int64_t lo[3], int64_t hi[3])
+template <typename LabelT>
+static int boundsFromHintOrScan(const LabelT *labels, const int64_t res[3], const int64_t *hLo, const int64_t *hHi, int64_t lo[3], int64_t hi[3])
 {
     const bool hint = hLo && hHi && (hHi[0] > hLo[0]) && (hHi[1] > hLo[1]) && (hHi[2] > hLo[2]);
     if (hint)
@@ -2013,6 +2044,12 @@ extern "C" int gmg_solver_destroy(gmg_solver *s)
     enterCtx(s->ctx);
     cudaStreamSynchronize(s->ctx->stream);
     dropGraphs(s);
+    if (s->ctx->windowOwner == s)
+    {
+	cudaStreamAttrValue attr = {};
+	cudaStreamSetAttribute(s->ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+	s->ctx->windowOwner = nullptr;
+    }
     {
 	auto &v = s->ctx->solvers;
 	v.erase(std::remove(v.begin(), v.end(), s), v.end());
@@ -2030,8 +2067,9 @@ extern "C" int gmg_solver_destroy(gmg_solver *s)
     return GMG_OK;
 }
 
-extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], const double *w0, const double *w1, const double *w2,
-				 int mgLevels, const gmg_solver_options *optIn, gmg_solver **out)
+template <typename LabelT>
+static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3], const double *w0, const double *w1, const double *w2,
+			int mgLevels, const gmg_solver_options *optIn, gmg_solver **out)
 {
     if (!ctx || !labels || !res || !out) return invalid("gmg_solver_create: null argument");
     if ((w0 || w1 || w2) && !(w0 && w1 && w2)) return invalid("gmg_solver_create: pass all three weight grids or none");
@@ -2199,6 +2237,18 @@ extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int6
     s->setupMs = nowMs() - tStart;
     *out = s;
     return GMG_OK;
+}
+
+extern "C" int gmg_solver_create(gmg_ctx *ctx, const int32_t *labels, const int64_t res[3], const double *w0, const double *w1, const double *w2,
+				 int mgLevels, const gmg_solver_options *optIn, gmg_solver **out)
+{
+    return solverCreate(ctx, labels, res, w0, w1, w2, mgLevels, optIn, out);
+}
+// the same constructor on ONE-BYTE labels (the enum of Ops.h:11 as uint8): a quarter of the PCIe and host-memory traffic
+extern "C" int gmg_solver_create_u8(gmg_ctx *ctx, const uint8_t *labels, const int64_t res[3], const double *w0, const double *w1, const double *w2,
+				    int mgLevels, const gmg_solver_options *optIn, gmg_solver **out)
+{
+    return solverCreate(ctx, labels, res, w0, w1, w2, mgLevels, optIn, out);
 }
 
 extern "C" int gmg_solver_levels(gmg_solver *s, int *levels)
@@ -2853,8 +2903,35 @@ static int runGraphed(gmg_solver *s, int kind, const void *p0, const void *p1, i
     return GMG_OK;
 }
 
+// L2 persistence for the level-0 band slab (buildBand): the stream's access-policy window marks accesses inside the slab as
+// persisting, so the band metadata survives the full-grid passes that stream 100+ MB through L2 between two sweep groups.
+// The attribute is a property of the stream (and is captured into the kernel nodes of the graphs), so it is (re)applied
+// whenever another solver last used the context.  GMG_L2_PERSIST=0 switches it off.
+static int applyBandWindow(gmg_solver *s)
+{
+    gmg_ctx *ctx = s->ctx;
+    if (ctx->windowOwner == s) return GMG_OK;
+    static const bool enabled = [] { const char *e = getenv("GMG_L2_PERSIST"); return !(e && e[0] == '0'); }();
+    ctx->windowOwner = s;
+    if (!enabled || ctx->persistBytes == 0) return GMG_OK;
+    const Level &L = s->lv[0];
+    cudaStreamAttrValue attr = {};
+    if (L.bandSlab && L.nBand > 0)
+    {
+	const size_t bytes = std::min(L.bandSlabBytes, ctx->maxWindowBytes);
+	attr.accessPolicyWindow.base_ptr = L.bandSlab;
+	attr.accessPolicyWindow.num_bytes = bytes;
+	attr.accessPolicyWindow.hitRatio = float(std::min(1.0, double(ctx->persistBytes) / double(std::max<size_t>(bytes, 1))));
+	attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    GMG_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return GMG_OK;
+}
+
 static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useInitialGuess)
 {
+    GMG_TRY(applyBandWindow(s));
     if (s->opt.operators_only && s->levels > 1) return invalid("this solver handle was created with operators_only: no coarse factor, no V-cycle");
     return runGraphed(s, 0, x, b, useInitialGuess ? 1 : 0, [&]() { return vcycleLaunches(s, x, b, useInitialGuess); });
 }
@@ -2932,6 +3009,7 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 {
     gmg_ctx *ctx = s->ctx;
     const Level &L0 = s->lv[0];
+    GMG_TRY(applyBandWindow(s));
     if (precond < 0 || precond > 2) return invalid("gmg_pcg: preconditioner must be 0 (none), 1 (multigrid V-cycle) or 2 (diagonal)");
     if (!s->pcgR)
     {
@@ -2991,7 +3069,7 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 	return applyUpdate();
     };
     int iteration = 0;
-    if (useDeviceLoop() && s->useGraphs && !ctx->profiling && ctx->world == 1)
+    if (useDeviceLoop() && s->useGraphs && !ctx->profiling && ctx->world == 1 && !ctx->deviceLoopBroken)
     {
 	// The whole loop as ONE graph launch: [apply, update, test] then a WHILE node around {iteration, test}; the residual
 	// history stays on the device until the loop ends, so the host synchronises once per solve instead of once per
@@ -3007,9 +3085,6 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 	PcgLoopState *dst = static_cast<PcgLoopState *>(s->pcgLoop);
 	double *dhist = reinterpret_cast<double *>(dst + 1);
 	PcgLoopState *hst = static_cast<PcgLoopState *>(s->pcgLoopHost);
-	hst->threshold = threshold; hst->bb = bb; hst->iteration = 0; hst->maxIt = maxIt; hst->histCount = 0;
-	hst->histCap = std::min(HIST_MAX, std::max(maxIt + 1, 1));
-	GMG_CUDA(cudaMemcpyAsync(dst, hst, sizeof(PcgLoopState), cudaMemcpyHostToDevice, ctx->stream));
 	auto key = std::make_tuple(3, static_cast<const void *>(x), static_cast<const void *>(b), precond);
 	auto it = s->graphs.find(key);
 	if (it == s->graphs.end())
@@ -3017,73 +3092,88 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
 	    if (s->graphs.size() >= 16) dropGraphs(s);
 	    gmg_solver::GraphEntry e;
 	    const int64_t before = ctx->launches;
-	    GMG_CUDA(cudaGraphCreate(&e.graph, 0));
-	    cudaGraphConditionalHandle handle;
-	    GMG_CUDA(cudaGraphConditionalHandleCreate(&handle, e.graph, 0, cudaGraphCondAssignDefault));
 	    Scalars *sc = reinterpret_cast<Scalars *>(ctx->scalars);
+	    cudaGraphConditionalHandle handle = 0;
 	    auto check = [&]() -> int {
 		ctx->curLevel = 0;
 		GMG_LAUNCH(ctx, KC_BLAS1, 0);
 		GMG_CUDA(launchK(k_pcg_check, unsigned(1), unsigned(1), size_t(0), ctx->stream, dst, dhist, static_cast<const Scalars *>(sc), handle));
 		return GMG_OK;
 	    };
-	    // head: [apply, update, test]
-	    GMG_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, e.graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-	    ctx->capturing = true;
-	    int st = applyUpdate();
-	    if (st == GMG_OK) st = check();
-	    ctx->capturing = false;
-	    cudaStreamCaptureStatus cs;
-	    const cudaGraphNode_t *deps = nullptr;
-	    size_t nDeps = 0;
-	    cudaError_t ce = cudaStreamGetCaptureInfo(ctx->stream, &cs, nullptr, nullptr, &deps, &nDeps);
-	    std::vector<cudaGraphNode_t> tail(deps, deps + (ce == cudaSuccess ? nDeps : 0));
-	    cudaGraph_t g1 = nullptr;
-	    cudaError_t ce2 = cudaStreamEndCapture(ctx->stream, &g1);
-	    const int64_t headKernels = ctx->launches - before;
-	    if (st != GMG_OK || ce != cudaSuccess || ce2 != cudaSuccess)
-	    {
-		cudaGraphDestroy(e.graph);
-		ctx->launches = before;
+	    // returns GMG_OK with e.exec set, or an error with the stream out of capture mode and nothing leaked
+	    auto build = [&]() -> int {
+		GMG_CUDA(cudaGraphCreate(&e.graph, 0));
+		GMG_CUDA(cudaGraphConditionalHandleCreate(&handle, e.graph, 0, cudaGraphCondAssignDefault));
+		// head: [apply, update, test]
+		GMG_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, e.graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		ctx->capturing = true;
+		int st = applyUpdate();
+		if (st == GMG_OK) st = check();
+		ctx->capturing = false;
+		cudaStreamCaptureStatus cs;
+		const cudaGraphNode_t *deps = nullptr;
+		size_t nDeps = 0;
+		const cudaError_t ce = cudaStreamGetCaptureInfo(ctx->stream, &cs, nullptr, nullptr, &deps, &nDeps);
+		std::vector<cudaGraphNode_t> tail;
+		if (ce == cudaSuccess) tail.assign(deps, deps + nDeps);
+		cudaGraph_t g1 = nullptr;
+		const cudaError_t ce2 = cudaStreamEndCapture(ctx->stream, &g1);
+		e.kernels = ctx->launches - before;
 		if (st != GMG_OK) return st;
 		GMG_CUDA(ce);
 		GMG_CUDA(ce2);
-	    }
-	    // WHILE node around {iteration, test}
-	    cudaGraphNodeParams np = {};
-	    np.type = cudaGraphNodeTypeConditional;
-	    np.conditional.handle = handle;
-	    np.conditional.type = cudaGraphCondTypeWhile;
-	    np.conditional.size = 1;
-	    cudaGraphNode_t whileNode;
-	    GMG_CUDA(cudaGraphAddNode(&whileNode, e.graph, tail.data(), tail.size(), &np));
-	    cudaGraph_t body = np.conditional.phGraph_out[0];
-	    const int64_t beforeBody = ctx->launches;
-	    GMG_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-	    ctx->capturing = true;
-	    st = iterationBody();
-	    if (st == GMG_OK) st = check();
-	    ctx->capturing = false;
-	    cudaGraph_t g2 = nullptr;
-	    ce2 = cudaStreamEndCapture(ctx->stream, &g2);
-	    e.kernels = headKernels;
-	    e.comms = ctx->launches - beforeBody;  // (re-used field: kernels per loop iteration)
+		// WHILE node around {iteration, test}
+		cudaGraphNodeParams np = {};
+		np.type = cudaGraphNodeTypeConditional;
+		np.conditional.handle = handle;
+		np.conditional.type = cudaGraphCondTypeWhile;
+		np.conditional.size = 1;
+		cudaGraphNode_t whileNode;
+		GMG_CUDA(cudaGraphAddNode(&whileNode, e.graph, tail.data(), tail.size(), &np));
+		cudaGraph_t body = np.conditional.phGraph_out[0];
+		const int64_t beforeBody = ctx->launches;
+		GMG_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		ctx->capturing = true;
+		st = iterationBody();
+		if (st == GMG_OK) st = check();
+		ctx->capturing = false;
+		cudaGraph_t g2 = nullptr;
+		const cudaError_t ce3 = cudaStreamEndCapture(ctx->stream, &g2);
+		e.comms = ctx->launches - beforeBody;  // (re-used field: kernels per loop iteration)
+		if (st != GMG_OK) return st;
+		GMG_CUDA(ce3);
+		GMG_CUDA(cudaGraphInstantiate(&e.exec, e.graph, 0));
+		return GMG_OK;
+	    };
+	    const int st = build();
 	    ctx->launches = before;
-	    if (st != GMG_OK) { cudaGraphDestroy(e.graph); return st; }
-	    GMG_CUDA(ce2);
-	    GMG_CUDA(cudaGraphInstantiate(&e.exec, e.graph, 0));
-	    it = s->graphs.emplace(key, e).first;
+	    if (st != GMG_OK)
+	    {
+		// a driver that refuses the conditional graph: remember it and run the host loop below (nothing has executed yet)
+		if (e.graph) cudaGraphDestroy(e.graph);
+		cudaGetLastError();
+		ctx->deviceLoopBroken = true;
+		if (getenv("GMG_TRACE")) fprintf(stderr, "[gmg] device-side PCG loop unavailable (%s): host loop\n", gmg_last_error());
+	    }
+	    else it = s->graphs.emplace(key, e).first;
 	}
-	GMG_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
-	GMG_CUDA(cudaMemcpyAsync(hst, dst, sizeof(PcgLoopState) + sizeof(double) * hst->histCap, cudaMemcpyDeviceToHost, ctx->stream));
-	GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-	iteration = hst->iteration;
-	ctx->launches += it->second.kernels + int64_t(std::max(0, hst->histCount - 1)) * it->second.comms;
-	const double *hh = reinterpret_cast<const double *>(hst + 1);
-	if (hist && histCount)
-	    for (int k = 0; k < hst->histCount && *histCount < histCap; ++k) hist[(*histCount)++] = hh[k];
-	if (iterations) *iterations = iteration;
-	return GMG_OK;
+	if (it != s->graphs.end())
+	{
+	    hst->threshold = threshold; hst->bb = bb; hst->iteration = 0; hst->maxIt = maxIt; hst->histCount = 0;
+	    hst->histCap = std::min(HIST_MAX, std::max(maxIt + 1, 1));
+	    const int cap = hst->histCap;
+	    GMG_CUDA(cudaMemcpyAsync(dst, hst, sizeof(PcgLoopState), cudaMemcpyHostToDevice, ctx->stream));
+	    GMG_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
+	    GMG_CUDA(cudaMemcpyAsync(hst, dst, sizeof(PcgLoopState) + sizeof(double) * cap, cudaMemcpyDeviceToHost, ctx->stream));
+	    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+	    iteration = hst->iteration;
+	    ctx->launches += it->second.kernels + int64_t(std::max(0, hst->histCount - 1)) * it->second.comms;
+	    const double *hh = reinterpret_cast<const double *>(hst + 1);
+	    if (hist && histCount)
+		for (int k = 0; k < hst->histCount && *histCount < histCap; ++k) hist[(*histCount)++] = hh[k];
+	    if (iterations) *iterations = iteration;
+	    return GMG_OK;
+	}
     }
     if (firstSolve) GMG_TRY(applyUpdate());
     else GMG_TRY(runGraphed(s, 1, x, nullptr, 0, applyUpdate));

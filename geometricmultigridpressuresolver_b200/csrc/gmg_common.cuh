@@ -81,6 +81,8 @@ struct Level
     int64_t nActiveGlobal = 0;
     // boundary band: [0,nBoundary) BOUNDARY cells, [nBoundary,nBand) INTERIOR cells of the band; linear order inside each part
     int nBoundary = 0, nBand = 0;
+    char *bandSlab = nullptr;    // one allocation behind bandIdx / bandRef / bandV0 / bandV1 / bandB / bcoef (L2 persisting window)
+    size_t bandSlabBytes = 0;
     int32_t *bandIdx = nullptr;  // [nBand] storage index
     int32_t *bandRef = nullptr;  // [6][nBand] neighbour reference (gmg_kernels.cuh: BandArgs::bandRef)
     bool hasWeights = false;     // level 0 built with face weights: BOUNDARY cells carry fractional coefficients
@@ -136,12 +138,16 @@ struct gmg_ctx
     int curLevel = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int smCount = 148;
+    size_t persistBytes = 0;      // L2 set aside for persisting lines (0 = off)
+    size_t maxWindowBytes = 0;
+    gmg_solver *windowOwner = nullptr;  // solver whose level-0 band slab the stream's access-policy window covers
     // sharding (z-slabs); world == 1 means single GPU
     int rank = 0, world = 1;
     void *nccl = nullptr;         // ncclComm_t
     int64_t commOps = 0;          // communication operations enqueued since the last launch-count reset
     void *p2p = nullptr;          // gmg::P2pState: peer-memory mailboxes (gmg_p2p.cuh); null = NCCL for every exchange
     bool p2pDisabled = false;
+    bool deviceLoopBroken = false; // the driver refused the conditional-graph PCG loop once: host loop from then on
     int p2pGenerations = 0;
     std::vector<gmg_solver *> solvers;  // live solvers of this context (their cached graphs are dropped when the arenas are re-mapped)
     // reduction scratch

@@ -1012,9 +1012,10 @@ struct BoxArgs
     int64_t res[3];
 };
 
-// staging int32 (dense box, x-fastest, row pitch = n[0]) -> byte labels with EXTERIOR outside [validLo, validHi)
-__global__ void __launch_bounds__(BLOCK) k_labels_from_i32(uint8_t *labels, const int32_t *staging, BoxArgs g, int lo0, int lo1, int lo2,
-							  int hi0, int hi1, int hi2)
+// staging int32 / uint8 (dense box, x-fastest, row pitch = n[0]) -> byte labels with EXTERIOR outside [validLo, validHi)
+template <typename LabelT>
+__global__ void __launch_bounds__(BLOCK) k_labels_from_host(uint8_t *labels, const LabelT *staging, BoxArgs g, int lo0, int lo1, int lo2,
+							   int hi0, int hi1, int hi2)
 {
     const int64_t i = int64_t(blockIdx.x) * BLOCK + threadIdx.x;
     if (i >= g.total) return;

@@ -84,6 +84,31 @@ def test_golden_diagonal_pcg(gpu_ctx, name):
     s.close()
 
 
+def test_byte_labels_and_unit_weights_constructor(gpu_ctx):
+    """gmg_solver_create_u8 (one-byte labels) builds the same solver as the int32 form; weights = None is the operators'
+    `boundaryWeights == nullptr` form (Ops.h:237-248) = unit weights."""
+    bl, bw, dx = base_inputs("narrow_band32")
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    b = D.random_rhs(labels, dx, seed=3)
+    s32 = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    s8 = api.GeometricMultigridPoissonSolver(gpu_ctx, labels.astype(np.uint8), w, levels)
+    assert s8.getMGLevels() == s32.getMGLevels()
+    for l in range(s32.getMGLevels()):
+        assert (s8.level_labels(l) == s32.level_labels(l)).all()
+        assert (s8.level_boundary_cells(l) == s32.level_boundary_cells(l)).all()
+    x32, it32, h32 = s32.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 100)
+    x8, it8, h8 = s8.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 100)
+    assert it8 == it32 and (h8 == h32).all() and (x8 == x32).all()
+    ones = [np.ones_like(a) for a in w]
+    s1 = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, ones, levels)
+    sn = api.GeometricMultigridPoissonSolver(gpu_ctx, labels.astype(np.uint8), None, levels)
+    x1, it1, h1 = s1.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 100)
+    xn, itn, hn = sn.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 100)
+    assert itn == it1 and relerr(hn, h1) < 1e-12 and relerr(xn, x1) < 1e-12
+    for s in (s32, s8, s1, sn):
+        s.close()
+
+
 @pytest.mark.parametrize("name", FULL_CASES)
 def test_golden_vcycle_and_operators(gpu_ctx, name):
     g = load_golden(name)

@@ -137,3 +137,20 @@ def test_gather_face_weights_matches_direct_indexing():
     got = api.gather_face_weights(idx, pitch, plane, org, w, bounds)
     want = expect(bounds)
     assert np.array_equal(got, want) and (want == 0).any() and (want != 0).any()
+
+
+def test_plane_wise_narrow_band_labels_match_the_dense_pipeline(port):
+    """bench.py's narrow1024 block builds the one-byte expanded labels plane by plane (no dense float grid); at a size the
+    oracle handles it must equal buildExpandedCellLabels + setBoundaryCellLabels on narrow_band_domain's arrays."""
+    import bench
+
+    for n, t in [(32, 4), (48, 12)]:
+        bl, bw, dx = D.narrow_band_domain(n, t)
+        labels, w, off, levels = port.expand_domain(bl, bw)
+        l8, off8, lev8, box = bench.narrow_band_labels_u8(n, t)
+        sl = tuple(slice(int(box[0][2 - k]), int(box[1][2 - k])) for k in range(3))
+        assert lev8 == levels and list(off8) == list(off)
+        assert (labels[sl] == l8[sl]).all()
+        outside = np.ones(labels.shape, dtype=bool)
+        outside[sl] = False
+        assert (labels[outside] == D.EXTERIOR).all()
