@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 
 #include "gmg_kernels.cuh"
+#include "gmg_cluster.cuh"
 #include "gmg_nccl.h"
 #include "gmg_p2p.cuh"
 
@@ -239,7 +240,7 @@ extern "C" int gmg_ctx_create(int device, void *stream, gmg_ctx **out)
 	{
 	    // up to half of L2 set aside for persisting lines (the band slab of the solver in use, applyBandWindow)
 	    const char *e = getenv("GMG_L2_PERSIST");
-	    if (!(e && e[0] == '0') && prop.persistingL2CacheMaxSize > 0)
+	    if (e && e[0] != '0' && prop.persistingL2CacheMaxSize > 0)
 	    {
 		size_t want = std::min<size_t>(size_t(prop.persistingL2CacheMaxSize), size_t(prop.l2CacheSize) / 2);
 		if (e && atoi(e) > 1) want = std::min<size_t>(size_t(prop.persistingL2CacheMaxSize), size_t(atoi(e)) << 20);
@@ -883,6 +884,14 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 	k_band_dilate<<<gridG, BLOCK, 0, ctx->stream>>>(m1, m0, labelsG, bg);
 	std::swap(m0, m1);
     }
+    {
+	// the band flags the zero-aware interior sweep reads (SM_JACOBI_ZERO), over the global box like the labels
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_band_dilate<<<gridG, BLOCK, 0, ctx->stream>>>(m1, m0, labelsG, bg);
+	GMG_CUDA(devMalloc(&L.flagsAlloc, gg.total));
+	k_band_flag_grid<<<gridG, BLOCK, 0, ctx->stream>>>(L.flagsAlloc, m0, m1, gg.total);
+	L.bandFlags = L.flagsAlloc + int64_t(L.zOff) * g.plane;
+    }
     const uint8_t *mLocal = m0 + int64_t(L.zOff) * g.plane;
     int32_t *idxB = nullptr, *idxI = nullptr;
     int nB = 0, nI = 0;
@@ -1284,7 +1293,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 
 static void freeLevel(Level &L)
 {
-    devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab);
+    devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab); devFree(L.flagsAlloc);
     devFree(L.chunksInterior); devFree(L.chunksActive);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
@@ -2057,6 +2066,8 @@ extern "C" int gmg_solver_destroy(gmg_solver *s)
     devFree(s->coarseIdx); devFree(s->coarseInv); devFree(s->compactBlob); devFree(s->pcgLoop);
     if (s->pcgLoopHost) cudaFreeHost(s->pcgLoopHost);
     delete static_cast<CompactArgs *>(s->compactArgs);
+    delete static_cast<ClusterArgs *>(s->clusterArgs);
+    devFree(s->clusterSlab);
     if (!s->lv.empty())
     {
 	const Geom &g0 = s->lv[0].g;
@@ -2089,6 +2100,7 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     else gmg_solver_default_options(&s->opt);
     if (const char *e = getenv("GMG_NO_GRAPHS")) s->useGraphs = !(e[0] == '1');
     if (const char *e = getenv("GMG_PRINT_STATS")) s->opt.print_stats = (e[0] == '1');
+    if (const char *e = getenv("GMG_ZERO_AWARE")) s->zeroAware = !(e[0] == '0');
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel && ctx->world > 1)
@@ -2321,6 +2333,7 @@ static StencilArgs stencilArgs(gmg_solver *s, int level, const double *in, const
     const Level &L = s->lv[level];
     StencilArgs a;
     a.labels = L.labels;
+    a.flags = L.bandFlags;
     a.in = in;
     a.b = b;
     a.out = out;
@@ -2360,6 +2373,12 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
 	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 25.0);
 	GMG_CUDA(launchK((k_stencil<SM_JACOBI, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
+    else if (mode == SM_JACOBI_ZERO)
+    {
+	// x is zero off the band: its 8 bytes per cell are not read (one flag byte is), and no zero fill ran before
+	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 18.0);
+	GMG_CUDA(launchK((k_stencil<SM_JACOBI_ZERO, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+    }
     else if (mode == SM_RESIDUAL)
     {
 	GMG_LAUNCH(s->ctx, KC_RESIDUAL, n * 25.0);
@@ -2379,7 +2398,8 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
     return GMG_OK;
 }
 
-// `sweeps` boundary-band Jacobi sweeps on grid x (Ops.h:524-619); zeroGrid: x is known to be all zero
+// `sweeps` boundary-band Jacobi sweeps on grid x (Ops.h:524-619); zeroGrid: x is to be taken as all zero -- the grid is
+// never read (it may hold anything), only its band cells are written by the last sweep
 static int launchBand(gmg_solver *s, int level, double *x, const double *b, int sweeps, bool zeroGrid)
 {
     s->ctx->curLevel = level;
@@ -2422,12 +2442,16 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
 	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
 	if (sw == sweeps)
 	{
-	    if (hw) GMG_CUDA(launchK((k_band<true, true, false, false, true>), grid, BLOCK, 0, st, a));
+	    if (zeroGrid && hw) GMG_CUDA(launchK((k_band<true, true, false, false, true, true>), grid, BLOCK, 0, st, a));
+	    else if (zeroGrid) GMG_CUDA(launchK((k_band<true, true, false, false, false, true>), grid, BLOCK, 0, st, a));
+	    else if (hw) GMG_CUDA(launchK((k_band<true, true, false, false, true>), grid, BLOCK, 0, st, a));
 	    else GMG_CUDA(launchK((k_band<true, true, false, false, false>), grid, BLOCK, 0, st, a));
 	}
 	else
 	{
-	    if (hw) GMG_CUDA(launchK((k_band<true, false, false, false, true>), grid, BLOCK, 0, st, a));
+	    if (zeroGrid && hw) GMG_CUDA(launchK((k_band<true, false, false, false, true, true>), grid, BLOCK, 0, st, a));
+	    else if (zeroGrid) GMG_CUDA(launchK((k_band<true, false, false, false, false, true>), grid, BLOCK, 0, st, a));
+	    else if (hw) GMG_CUDA(launchK((k_band<true, false, false, false, true>), grid, BLOCK, 0, st, a));
 	    else GMG_CUDA(launchK((k_band<true, false, false, false, false>), grid, BLOCK, 0, st, a));
 	}
 	std::swap(cur, nxt);
@@ -2512,10 +2536,192 @@ static int launchCoarse(gmg_solver *s, double *x, const double *b)
     return GMG_OK;
 }
 
-// levels [fusedFirst, levels-1] in one shared-memory CTA (gmg_kernels.cuh: k_compact_cycle).  The tables are built on the
-// host: these levels hold a few thousand cells at most.
+// levels [fusedFirst, levels-1] in ONE thread-block cluster with the vectors in distributed shared memory
+// (gmg_cluster.cuh: k_cluster_cycle).  Tables are built on the device, stream-ordered, without a host synchronisation.
+static int buildClusterCycle(gmg_solver *s)
+{
+    s->fusedFirst = -1;
+    if (const char *e = getenv("GMG_CLUSTER_CYCLE")) if (e[0] == '0') return GMG_OK;
+    if (const char *e = getenv("GMG_COARSE_FUSED")) if (e[0] == '0') return GMG_OK;
+    if (s->opt.operators_only || s->levels < 2) return GMG_OK;
+    if (s->opt.use_gauss_seidel) return GMG_OK;  // the fused cycles implement the Jacobi interior sweep only
+    gmg_ctx *ctx = s->ctx;
+    if (ctx->clusterSize < 0) return GMG_OK;     // probed before: this device / driver refuses the cluster launch
+    int smemMax = 0;
+    GMG_CUDA(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    if (ctx->clusterSize == 0)
+    {
+	// one probe per context: the largest cluster (16 needs the non-portable opt-in) that can be resident with the maximum
+	// dynamic shared memory
+	ctx->clusterSize = -1;
+	if (cudaFuncSetAttribute(k_cluster_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax) != cudaSuccess) { cudaGetLastError(); return GMG_OK; }
+	if (cudaFuncSetAttribute(k_cluster_cycle, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+	int want = 16;
+	if (const char *e = getenv("GMG_CLUSTER_SIZE")) want = std::max(1, std::min(16, atoi(e)));
+	for (int cl = want; cl >= 2; cl >>= 1)
+	{
+	    cudaLaunchConfig_t cfg = {};
+	    cfg.gridDim = dim3(cl);
+	    cfg.blockDim = dim3(CLUSTER_THREADS);
+	    cfg.dynamicSmemBytes = size_t(smemMax);
+	    cudaLaunchAttribute attr[1];
+	    attr[0].id = cudaLaunchAttributeClusterDimension;
+	    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	    cfg.attrs = attr;
+	    cfg.numAttrs = 1;
+	    int nClusters = 0;
+	    if (cudaOccupancyMaxActiveClusters(&nClusters, k_cluster_cycle, &cfg) == cudaSuccess && nClusters >= 1) { ctx->clusterSize = cl; break; }
+	    cudaGetLastError();
+	}
+	if (ctx->clusterSize < 0) return GMG_OK;
+    }
+    const int CL = ctx->clusterSize;
+    auto perOf = [&](int64_t n) { return int((divUp(std::max<int64_t>(n, 1), CL) + 1) & ~int64_t(1)); };
+    auto smemOf = [&](int first) {
+	size_t doubles = 0;
+	for (int l = first; l < s->levels; ++l) doubles += size_t(3) * perOf(s->lv[l].nActive);
+	return (doubles + size_t(s->nCoarse) + 2) * sizeof(double);
+    };
+    // finest level (>= 1: level 0 carries face weights and the caller's grids; replicated levels only) whose vectors fit the
+    // cluster's shared memory with at most 8 cells per thread
+    int first = -1;
+    for (int l = std::max(1, s->shardLevels); l < s->levels; ++l)
+	if (s->levels - l <= CLUSTER_MAX_LEVELS && s->lv[l].nActive <= int64_t(CL) * CLUSTER_THREADS * 8 && perOf(s->lv[l].nActive) < (1 << CLUSTER_OWNER_SHIFT) &&
+	    smemOf(l) + 1024 <= size_t(smemMax))
+	{
+	    first = l;
+	    break;
+	}
+    if (const char *c = getenv("GMG_FUSED_FIRST")) first = std::max(first, atoi(c));
+    if (first < 0 || first >= s->levels - 1) return GMG_OK;  // nothing, or only the direct solve: its own kernel does that
+    const int nl = s->levels - first;
+    // one slab for every table
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    struct Offs { size_t cell, nbr, rst, pro, diag, flags; };
+    std::vector<Offs> o(nl);
+    for (int q = 0; q < nl; ++q)
+    {
+	const size_t n = size_t(std::max<int64_t>(s->lv[first + q].nActive, 1));
+	o[q].cell = take(4 * n);
+	o[q].nbr = take(4 * 6 * n);
+	o[q].rst = q > 0 ? take(4 * 64 * n) : 0;
+	o[q].pro = q + 1 < nl ? take(4 * 8 * n) : 0;
+	o[q].diag = take(n);
+	o[q].flags = take(n);
+    }
+    const size_t oSolve = take(4 * size_t(std::max(s->nCoarse, 1)));
+    char *slab = nullptr;
+    GMG_CUDA(devMalloc(&slab, off));
+    ClusterArgs *c = new ClusterArgs;
+    std::memset(c, 0, sizeof(*c));
+    s->clusterArgs = c;
+    s->clusterSlab = slab;
+    // compact lists and position grids (storage index -> compact index), level by level
+    std::vector<int32_t *> pos(nl, nullptr);
+    int smemOff = 0;
+    for (int q = 0; q < nl; ++q)
+    {
+	const Level &L = s->lv[first + q];
+	const int n = int(L.nActive);
+	ClusterLevel &K = c->lv[q];
+	K.n = n;
+	K.per = perOf(n);
+	K.off = smemOff;
+	smemOff += 3 * K.per;
+	K.nbr = reinterpret_cast<const unsigned *>(slab + o[q].nbr);
+	K.rst = reinterpret_cast<const unsigned *>(slab + o[q].rst);
+	K.pro = reinterpret_cast<const unsigned *>(slab + o[q].pro);
+	K.diag = reinterpret_cast<const uint8_t *>(slab + o[q].diag);
+	K.flags = reinterpret_cast<const uint8_t *>(slab + o[q].flags);
+	int32_t *cell = reinterpret_cast<int32_t *>(slab + o[q].cell);
+	const int64_t total = L.g.total;
+	uint8_t *fl = nullptr;
+	int *dCount = nullptr;
+	void *dTemp = nullptr;
+	size_t tempBytes = 0;
+	GMG_CUDA(devMalloc(&fl, size_t(total)));
+	GMG_CUDA(devMalloc(&dCount, sizeof(int)));
+	GMG_CUDA(devMalloc(&pos[q], sizeof(int32_t) * size_t(total)));
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_active_flags<<<unsigned(divUp(total, BLOCK)), BLOCK, 0, ctx->stream>>>(fl, L.labels, total);
+	}
+	thrust::counting_iterator<int32_t> it(0);
+	GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, it, fl, cell, dCount, int(total), ctx->stream));
+	GMG_CUDA(devMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
+	GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, it, fl, cell, dCount, int(total), ctx->stream));
+	++ctx->launches;
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_fill_i32<<<unsigned(divUp(total, BLOCK)), BLOCK, 0, ctx->stream>>>(pos[q], -1, total);
+	}
+	if (n > 0)
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_band_pos<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(pos[q], cell, n);
+	}
+	GMG_CUDA(devFree(dTemp));
+	GMG_CUDA(devFree(dCount));
+	GMG_CUDA(devFree(fl));
+    }
+    for (int q = 0; q < nl; ++q)
+    {
+	const Level &L = s->lv[first + q];
+	const Geom &g = L.g;
+	const ClusterLevel &K = c->lv[q];
+	const int n = K.n;
+	if (n == 0) continue;
+	const int32_t *cell = reinterpret_cast<const int32_t *>(slab + o[q].cell);
+	const unsigned grid = unsigned(divUp(n, BLOCK));
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_cluster_nbr<<<grid, BLOCK, 0, ctx->stream>>>(const_cast<unsigned *>(K.nbr), const_cast<uint8_t *>(K.diag), const_cast<uint8_t *>(K.flags), cell, pos[q],
+							   L.labels, L.bandFlags, n, K.per, g.pitch, g.plane);
+	}
+	if (q > 0)
+	{
+	    const Level &F = s->lv[first + q - 1];
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_cluster_rst<<<grid, BLOCK, 0, ctx->stream>>>(const_cast<unsigned *>(K.rst), cell, pos[q - 1], n, c->lv[q - 1].per, g.pitch, g.plane, F.g.pitch, F.g.plane,
+							   F.g.n[0], F.g.n[1], F.g.n[2], F.shift[0], F.shift[1], F.shift[2]);
+	}
+	if (q + 1 < nl)
+	{
+	    const Level &C = s->lv[first + q + 1];
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_cluster_pro<<<grid, BLOCK, 0, ctx->stream>>>(const_cast<unsigned *>(K.pro), cell, pos[q + 1], n, c->lv[q + 1].per, g.pitch, g.plane, C.g.pitch, C.g.plane,
+							   C.g.n[0], C.g.n[1], C.g.n[2], L.shift[0], L.shift[1], L.shift[2]);
+	}
+    }
+    unsigned *solveRef = reinterpret_cast<unsigned *>(slab + oSolve);
+    if (s->nCoarse > 0)
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_cluster_solve_ref<<<unsigned(divUp(s->nCoarse, BLOCK)), BLOCK, 0, ctx->stream>>>(solveRef, s->coarseIdx, pos[nl - 1], s->nCoarse, c->lv[nl - 1].per);
+    }
+    GMG_CUDA(cudaGetLastError());
+    for (int q = 0; q < nl; ++q) GMG_CUDA(devFree(pos[q]));
+    c->nLevels = nl;
+    c->sweeps = s->opt.boundary_iterations;
+    c->scratchOff = smemOff;
+    c->cellTop = reinterpret_cast<const int32_t *>(slab + o[0].cell);
+    c->bTop = s->lv[first].b;
+    c->xTop = s->lv[first].x;
+    c->solveRef = solveRef;
+    c->nSolve = s->nCoarse;
+    c->inv = s->coarseInv;
+    s->clusterSmem = size_t(smemOff + s->nCoarse + 2) * sizeof(double);
+    s->fusedFirst = first;
+    return GMG_OK;
+}
+
+// levels [fusedFirst, levels-1] in one shared-memory CTA (gmg_kernels.cuh: k_compact_cycle): the fallback where the cluster
+// cycle is not available.  The tables are built on the host: these levels hold a few thousand cells at most.
 static int buildFusedCycle(gmg_solver *s)
 {
+    GMG_TRY(buildClusterCycle(s));
+    if (s->fusedFirst > 0) return GMG_OK;
     s->fusedFirst = -1;
     const char *e = getenv("GMG_COARSE_FUSED");
     if (e && e[0] == '0') return GMG_OK;
@@ -2700,10 +2906,29 @@ static int buildFusedCycle(gmg_solver *s)
 static int launchCoarseCycle(gmg_solver *s)
 {
     s->ctx->curLevel = s->fusedFirst;
-    const CompactArgs &c = *static_cast<const CompactArgs *>(s->compactArgs);
     double bytes = 0;
     for (int l = s->fusedFirst; l < s->levels - 1; ++l) bytes += double(s->lv[l].nActive) * 126.0;
     GMG_LAUNCH(s->ctx, KC_COARSE, bytes);
+    if (s->clusterArgs)
+    {
+	const ClusterArgs &cc = *static_cast<const ClusterArgs *>(s->clusterArgs);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(s->ctx->clusterSize);
+	cfg.blockDim = dim3(CLUSTER_THREADS);
+	cfg.dynamicSmemBytes = s->clusterSmem;
+	cfg.stream = s->ctx->stream;
+	cudaLaunchAttribute attr[2];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = s->ctx->clusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[1].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = usePdl() ? 2 : 1;
+	GMG_CUDA(cudaLaunchKernelEx(&cfg, k_cluster_cycle, cc));
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
+    const CompactArgs &c = *static_cast<const CompactArgs *>(s->compactArgs);
     GMG_CUDA(launchK(k_compact_cycle, unsigned(1), unsigned(CYCLE_THREADS), size_t(s->compactSmem), s->ctx->stream, c));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
@@ -2775,6 +3000,14 @@ static int launchGaussSeidel(gmg_solver *s, int level, double *x, const double *
     return GMG_OK;
 }
 
+// Zero-aware down-stroke: no zero fill of x before the first band sweeps, no read of x in the interior sweep after them
+// (DESIGN.md section 4).  Needs the damped-Jacobi interior smoother and at least one band sweep (the band sweeps are what
+// define the grid's band cells); GMG_ZERO_AWARE=0 restores the zero fill.
+static bool zeroAware(const gmg_solver *s)
+{
+    return s->zeroAware && !s->opt.use_gauss_seidel && s->opt.boundary_iterations >= 1;
+}
+
 // jacobiDepth: how far into the halo the interior sweep still produces valid values (sharded levels)
 // down: the smoothing before the coarse-grid correction (GS: odd then even tiles, forwards; MG.cpp:466-479), else after it
 // (GS: even then odd tiles, backwards; MG.cpp:740-751)
@@ -2789,7 +3022,9 @@ static int smoothLevel(gmg_solver *s, int level, double *&cur, double *&alt, con
     }
     else
     {
-	GMG_TRY(launchStencil(s, level, SM_JACOBI, cur, b, alt, nullptr, clipDepth(s->lv[level], jacobiDepth)));
+	// zeroGrid: the band sweeps above wrote the band cells of a grid that was NOT zero-filled; the interior sweep takes
+	// every other cell as zero (SM_JACOBI_ZERO) and writes every active cell of alt
+	GMG_TRY(launchStencil(s, level, zeroGrid && zeroAware(s) ? SM_JACOBI_ZERO : SM_JACOBI, cur, b, alt, nullptr, clipDepth(s->lv[level], jacobiDepth)));
 	std::swap(cur, alt);
     }
     GMG_TRY(launchBand(s, level, cur, b, it, false));
@@ -2820,7 +3055,7 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
     // level 0 works on the caller's grid and the level's alternate; two Jacobi sweeps per level bring the
     // result back into the caller's buffer (one sweep only when there is a single level)
     double *cur0 = x, *alt0 = s->lv[0].xAlt;
-    if (!useInitialGuess) GMG_TRY(launchZero(s, 0, cur0));
+    if (!useInitialGuess && !zeroAware(s)) GMG_TRY(launchZero(s, 0, cur0));
     GMG_TRY(smoothLevel(s, 0, cur0, alt0, b, !useInitialGuess, downJacobi, true));
     if (nl == 1)
     {
@@ -2837,7 +3072,7 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
 	Level &L = s->lv[level];
 	cur[level] = L.x;
 	alt[level] = L.xAlt;
-	GMG_TRY(launchZero(s, level, cur[level]));
+	if (!zeroAware(s)) GMG_TRY(launchZero(s, level, cur[level]));
 	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, true, downJacobi, true));
 	GMG_TRY(launchStencil(s, level, SM_RESIDUAL, cur[level], L.b, L.r, nullptr, clipDepth(L, 1)));
 	GMG_TRY(restrictDown(s, level, L.r));
@@ -2906,12 +3141,14 @@ static int runGraphed(gmg_solver *s, int kind, const void *p0, const void *p1, i
 // L2 persistence for the level-0 band slab (buildBand): the stream's access-policy window marks accesses inside the slab as
 // persisting, so the band metadata survives the full-grid passes that stream 100+ MB through L2 between two sweep groups.
 // The attribute is a property of the stream (and is captured into the kernel nodes of the graphs), so it is (re)applied
-// whenever another solver last used the context.  GMG_L2_PERSIST=0 switches it off.
+// whenever another solver last used the context.  MEASURED (profiles/r02_ab_switches.md): the set-aside costs the full-grid
+// passes more L2 than the band sweeps gain -- 256^3 solve 10.53 ms with the window, 10.25 ms without; 512^3 V-cycle 6.09 vs
+// 5.4 ms -- so it is OFF unless GMG_L2_PERSIST=1 (or =<MB of set-aside>) asks for it.
 static int applyBandWindow(gmg_solver *s)
 {
     gmg_ctx *ctx = s->ctx;
     if (ctx->windowOwner == s) return GMG_OK;
-    static const bool enabled = [] { const char *e = getenv("GMG_L2_PERSIST"); return !(e && e[0] == '0'); }();
+    static const bool enabled = [] { const char *e = getenv("GMG_L2_PERSIST"); return e && e[0] != '0'; }();
     ctx->windowOwner = s;
     if (!enabled || ctx->persistBytes == 0) return GMG_OK;
     const Level &L = s->lv[0];

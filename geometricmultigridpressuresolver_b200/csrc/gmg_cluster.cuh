@@ -1,0 +1,339 @@
+// gmg_cluster.cuh -- the coarse sub-V-cycle in ONE thread-block cluster with its vectors in distributed shared memory.
+//
+// Measured on B200 (profiles/): a V-cycle step on a level of a few thousand to ~100k cells costs 4-5 us as a kernel of its own
+// -- launch, a chain of dependent L2 loads, drain -- whatever its size, and the three levels below level 1 of the 256^3
+// problem spend 17 such steps each: 40 % of the V-cycle for 2 % of the cells.  Here levels [first, last] -- down-stroke,
+// direct solve, up-stroke -- run inside one kernel of ONE cluster (16 CTAs x 1024 threads, or 8 where 16 is refused):
+//   * every level's cells are a compact list in storage order, cut into equal blocks, one per CTA; the level's vectors
+//     (two ping-pong solution arrays and the right-hand side) live in the OWNING CTA's shared memory;
+//   * a neighbour / restriction tap / prolongation corner is a packed (owner CTA, index) reference resolved with
+//     cluster.map_shared_rank -- a distributed-shared-memory load over the SM-to-SM network, no global memory on the path;
+//     the reference tables themselves are read from global memory (coalesced, L2-resident, independent of the values);
+//   * a step ends on the hardware cluster barrier (barrier.cluster arrive.release / wait.acquire) instead of a kernel boundary.
+// Per cell the arithmetic and its order are those of k_stencil / k_band / k_restrict / k_prolong / k_coarse_solve (and of
+// k_compact_cycle, the one-CTA predecessor of this kernel, kept as the fallback), so the result is bitwise identical.
+// Reference semantics: applyVCycle, MG.cpp:557-784 (the levels below the finest), smoothers Ops.h:262-367 / :524-619,
+// transfer operators Ops.h:734-972, direct solve MG.cpp:669-692.
+#pragma once
+
+#include "gmg_kernels.cuh"
+
+namespace gmg
+{
+constexpr int CLUSTER_THREADS = 1024;
+constexpr int CLUSTER_MAX_LEVELS = 10;
+constexpr unsigned CLUSTER_NONE = 0xffffffffu;
+constexpr int CLUSTER_OWNER_SHIFT = 20;  // packed reference = (owner CTA << 20) | index in the owner's block
+
+struct ClusterLevel
+{
+    int n;                 // active cells of the level
+    int per;               // cells per CTA block (the last blocks may be short or empty)
+    int off;               // offset (doubles) of this level's [xa | xb | b] arrays, `per` each, in every CTA's shared memory
+    const unsigned *nbr;   // [6][n]  packed reference of the -x,+x,-y,+y,-z,+z neighbour, CLUSTER_NONE = not active
+    const unsigned *rst;   // [64][n] packed references (next FINER level) of the 4x4x4 restriction taps (levels below the top)
+    const unsigned *pro;   // [8][n]  packed references (next COARSER level) of the 2x2x2 prolongation corners
+    const uint8_t *diag;   // [n] 6 for INTERIOR; number of non-EXTERIOR neighbours for BOUNDARY (Ops.h:237-248, weight 1)
+    const uint8_t *flags;  // [n] bit0 = boundary band, bits 1..3 = parity of the x, y, z storage index
+};
+
+struct ClusterArgs
+{
+    ClusterLevel lv[CLUSTER_MAX_LEVELS];  // lv[0] is the finest level of the cycle
+    int nLevels;
+    int sweeps;
+    int scratchOff;           // offset (doubles) of the direct solve's gathered right-hand side in CTA 0
+    const int32_t *cellTop;   // [lv[0].n] storage index of lv[0]'s cells in its grid
+    const double *bTop;       // rhs grid of lv[0] (written by the restriction kernel of the level above)
+    double *xTop;             // solution grid of lv[0] (read by the prolongation kernel of the level above)
+    const unsigned *solveRef; // [nSolve] packed reference (coarsest level) of the direct solve's k-th unknown (MG.cpp:296-323 numbering)
+    int nSolve;
+    const double *inv;        // [nSolve][nSolve]
+};
+
+// the value behind a packed reference: `base` is the array's address in THIS CTA's shared memory; every CTA lays its
+// shared memory out identically, so the same offset is valid in the owner's
+__device__ __forceinline__ double clusterLoad(cg::cluster_group &cl, double *base, unsigned ref)
+{
+    return *cl.map_shared_rank(base + (ref & ((1u << CLUSTER_OWNER_SHIFT) - 1u)), ref >> CLUSTER_OWNER_SHIFT);
+}
+
+// A x at this CTA's j-th cell of the level (compact index k), in the operation order of computeLaplacian (Ops.h:177-260):
+// neighbours by (axis, direction), centre last
+__device__ __forceinline__ double clusterLap(cg::cluster_group &cl, const ClusterLevel &L, double *x, int k, int j, double diag)
+{
+    unsigned ref[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) ref[d] = __ldg(L.nbr + size_t(d) * L.n + k);
+    double lap = 0.0;
+#pragma unroll
+    for (int d = 0; d < 6; ++d)
+	if (ref[d] != CLUSTER_NONE) lap -= clusterLoad(cl, x, ref[d]);
+    lap += diag * x[j];
+    return lap;
+}
+
+// one damped-Jacobi sweep xin -> xout over the band cells (bandOnly; everything else is copied) or over all cells
+// (Ops.h:262-367, :524-619), ending on the cluster barrier
+__device__ __forceinline__ void clusterSweep(cg::cluster_group &cl, const ClusterLevel &L, double *xin, double *xout, const double *b, int first, int count,
+					     bool bandOnly)
+{
+    for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
+    {
+	const int k = first + j;
+	if (bandOnly && !(__ldg(L.flags + k) & 1)) { xout[j] = xin[j]; continue; }
+	const double diag = double(__ldg(L.diag + k));
+	const double lap = clusterLap(cl, L, xin, k, j, diag);
+	double r = b[j] - lap;
+	r /= diag;
+	xout[j] = xin[j] + (2.0 / 3.0) * r;
+    }
+    cl.sync();
+}
+
+__global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const ClusterArgs c)
+{
+    pdlLaunch();
+    extern __shared__ double sm[];
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = int(cl.block_rank());
+    const int nl = c.nLevels;
+    // this CTA's block of level q: cells [first, first + count)
+    auto blockOf = [&](int q, int &first, int &count) {
+	const ClusterLevel &L = c.lv[q];
+	first = rank * L.per;
+	count = max(0, min(L.per, L.n - first));
+    };
+    // solution arrays ping-pong: cur[q] tells which of xa / xb holds the level's current solution
+    int cur[CLUSTER_MAX_LEVELS];
+    auto X = [&](int q, int which) { return sm + c.lv[q].off + which * c.lv[q].per; };
+    auto B = [&](int q) { return sm + c.lv[q].off + 2 * c.lv[q].per; };
+    // band sweeps, one interior sweep, band sweeps (MG.cpp:445-513 and its per-level copies)
+    auto smooth = [&](int q) {
+	const ClusterLevel &L = c.lv[q];
+	int first, count;
+	blockOf(q, first, count);
+	for (int s = 0; s < 2 * c.sweeps + 1; ++s)
+	{
+	    clusterSweep(cl, L, X(q, cur[q]), X(q, cur[q] ^ 1), B(q), first, count, s != c.sweeps);
+	    cur[q] ^= 1;
+	}
+    };
+    pdlWait();
+    {
+	int first, count;
+	blockOf(0, first, count);
+	double *b = B(0);
+	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS) b[j] = c.bTop[__ldg(c.cellTop + first + j)];
+    }
+    // ---- down-stroke (MG.cpp:557-667): x = 0, smooth, residual, restrict
+    for (int q = 0; q + 1 < nl; ++q)
+    {
+	const ClusterLevel &L = c.lv[q];
+	const ClusterLevel &C = c.lv[q + 1];
+	int first, count;
+	blockOf(q, first, count);
+	cur[q] = 0;
+	{
+	    double *x = X(q, 0);
+	    for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS) x[j] = 0.0;
+	}
+	cl.sync();
+	smooth(q);
+	{
+	    // residual into the other solution array (the current one is kept for the up-stroke)
+	    double *x = X(q, cur[q]), *t = X(q, cur[q] ^ 1);
+	    const double *b = B(q);
+	    for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
+	    {
+		const int k = first + j;
+		const double lap = clusterLap(cl, L, x, k, j, double(__ldg(L.diag + k)));
+		t[j] = b[j] + (-1.0) * lap;  // Ops.h:731
+	    }
+	}
+	cl.sync();
+	{
+	    int cfirst, ccount;
+	    blockOf(q + 1, cfirst, ccount);
+	    double *t = X(q, cur[q] ^ 1);
+	    double *bc = B(q + 1);
+	    for (int j = threadIdx.x; j < ccount; j += CLUSTER_THREADS)
+	    {
+		const int k = cfirst + j;
+		const double rw[4] = {1. / 8., 3. / 8., 3. / 8., 1. / 8.};
+		double v = 0.0;
+#pragma unroll
+		for (int z = 0; z < 4; ++z)
+#pragma unroll
+		    for (int y = 0; y < 4; ++y)
+		    {
+			unsigned ref[4];
+#pragma unroll
+			for (int xx = 0; xx < 4; ++xx) ref[xx] = __ldg(C.rst + size_t((z * 4 + y) * 4 + xx) * C.n + k);
+#pragma unroll
+			for (int xx = 0; xx < 4; ++xx)
+			    if (ref[xx] != CLUSTER_NONE) v += rw[xx] * rw[y] * rw[z] * clusterLoad(cl, t, ref[xx]);  // an inactive tap adds +0.0, which never changes v
+		    }
+		bc[j] = v;
+	    }
+	}
+	cl.sync();
+    }
+    // ---- direct solve on the coarsest level (MG.cpp:669-692): x = A^-1 b, one warp per row as in k_coarse_solve, in CTA 0
+    {
+	const int q = nl - 1;
+	cur[q] = 0;
+	double *x = X(q, 0);
+	if (rank == 0)
+	{
+	    double *sb = sm + c.scratchOff;
+	    const int n = c.nSolve;
+	    for (int i = threadIdx.x; i < n; i += CLUSTER_THREADS) sb[i] = clusterLoad(cl, B(q), __ldg(c.solveRef + i));
+	    __syncthreads();
+	    const int lane = threadIdx.x & 31;
+	    for (int row = threadIdx.x >> 5; row < n; row += CLUSTER_THREADS / 32)
+	    {
+		const double *r = c.inv + int64_t(row) * n;
+		double acc = 0.0;
+		for (int j = lane; j < n; j += 32) acc += r[j] * sb[j];
+		acc = warpSum(acc);
+		if (lane == 0)
+		{
+		    const unsigned ref = __ldg(c.solveRef + row);
+		    *cl.map_shared_rank(x + (ref & ((1u << CLUSTER_OWNER_SHIFT) - 1u)), ref >> CLUSTER_OWNER_SHIFT) = acc;
+		}
+	    }
+	}
+	cl.sync();
+    }
+    // ---- up-stroke (MG.cpp:695-784): x += 4 trilerp(x_coarse), smooth
+    for (int q = nl - 2; q >= 0; --q)
+    {
+	const ClusterLevel &L = c.lv[q];
+	int first, count;
+	blockOf(q, first, count);
+	double *x = X(q, cur[q]);
+	double *xc = X(q + 1, cur[q + 1]);
+	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
+	{
+	    const int k = first + j;
+	    const int f = __ldg(L.flags + k);
+	    const double wx = (f & 2) ? .25 : .75, wy = (f & 4) ? .25 : .75, wz = (f & 8) ? .25 : .75;
+	    unsigned ref[8];
+#pragma unroll
+	    for (int p = 0; p < 8; ++p) ref[p] = __ldg(L.pro + size_t(p) * L.n + k);
+	    double v[8];
+#pragma unroll
+	    for (int p = 0; p < 8; ++p) v[p] = ref[p] != CLUSTER_NONE ? clusterLoad(cl, xc, ref[p]) : 0.0;
+	    // corner p = x + 2 y + 4 z; lerp nesting x -> y -> z (Ops.h:841-871)
+	    const double e = lerpRef(lerpRef(lerpRef(v[0], v[1], wx), lerpRef(v[2], v[3], wx), wy),
+				     lerpRef(lerpRef(v[4], v[5], wx), lerpRef(v[6], v[7], wx), wy), wz);
+	    x[j] = x[j] + 4. * e;
+	}
+	cl.sync();
+	smooth(q);
+    }
+    {
+	int first, count;
+	blockOf(0, first, count);
+	const double *x = X(0, cur[0]);
+	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS) c.xTop[__ldg(c.cellTop + first + j)] = x[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// table builders (device side: the constructor runs every simulation frame)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_active_flags(uint8_t *flags, const uint8_t *labels, int64_t total)
+{
+    const int64_t i = int64_t(blockIdx.x) * BLOCK + threadIdx.x;
+    if (i < total)
+    {
+	const int l = labels[i];
+	flags[i] = (l == L_INTERIOR || l == L_BOUNDARY) ? 1 : 0;
+    }
+}
+
+__device__ __forceinline__ unsigned clusterPack(int p, int per)
+{
+    if (p < 0) return CLUSTER_NONE;
+    const int owner = p / per;
+    return (unsigned(owner) << CLUSTER_OWNER_SHIFT) | unsigned(p - owner * per);
+}
+
+// neighbour references, diagonal and flags of one level (cell: compact -> storage index; pos: storage index -> compact, -1)
+__global__ void __launch_bounds__(BLOCK) k_cluster_nbr(unsigned *nbr, uint8_t *diag, uint8_t *flags, const int32_t *cell, const int32_t *pos,
+						      const uint8_t *labels, const uint8_t *bandFlags, int n, int per, int pitch, int64_t plane)
+{
+    const int k = blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = cell[k];
+    const int64_t stride[6] = {-1, 1, -int64_t(pitch), int64_t(pitch), -plane, plane};
+    int dg = 0;
+#pragma unroll
+    for (int d = 0; d < 6; ++d)
+    {
+	const int64_t j = i + stride[d];
+	const int l = labels[j];
+	unsigned ref = CLUSTER_NONE;
+	if (l == L_INTERIOR || l == L_BOUNDARY) { ref = clusterPack(pos[j], per); ++dg; }
+	else if (l == L_DIRICHLET) ++dg;
+	nbr[size_t(d) * n + k] = ref;
+    }
+    diag[k] = uint8_t(dg);  // 6 for an INTERIOR cell (all six neighbours active by construction)
+    const int z = int(i / plane);
+    const int64_t rem = i - int64_t(z) * plane;
+    const int y = int(rem / pitch), x = int(rem - int64_t(y) * pitch);
+    flags[k] = uint8_t((bandFlags[i] & 1) | ((x & 1) << 1) | ((y & 1) << 2) | ((z & 1) << 3));
+}
+
+// restriction taps of a coarse level in the next finer one (Ops.h:760-834); shift: coarse storage = (fine storage >> 1) + shift
+__global__ void __launch_bounds__(BLOCK) k_cluster_rst(unsigned *rst, const int32_t *cellC, const int32_t *posF, int nC, int perF, int pitchC, int64_t planeC,
+						      int pitchF, int64_t planeF, int nxF, int nyF, int nzF, int s0, int s1, int s2)
+{
+    const int k = blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= nC) return;
+    const int64_t i = cellC[k];
+    const int cz = int(i / planeC);
+    const int64_t rem = i - int64_t(cz) * planeC;
+    const int cy = int(rem / pitchC), cx = int(rem - int64_t(cy) * pitchC);
+    const int fx = 2 * (cx - s0) - 1, fy = 2 * (cy - s1) - 1, fz = 2 * (cz - s2) - 1;
+    for (int z = 0; z < 4; ++z)
+	for (int y = 0; y < 4; ++y)
+	    for (int x = 0; x < 4; ++x)
+	    {
+		const int X = fx + x, Y = fy + y, Z = fz + z;
+		unsigned ref = CLUSTER_NONE;
+		if (X >= 0 && Y >= 0 && Z >= 0 && X < nxF && Y < nyF && Z < nzF) ref = clusterPack(posF[int64_t(Z) * planeF + int64_t(Y) * pitchF + X], perF);
+		rst[size_t((z * 4 + y) * 4 + x) * nC + k] = ref;
+	    }
+}
+
+// prolongation corners of a fine level in the next coarser one (Ops.h:895-971)
+__global__ void __launch_bounds__(BLOCK) k_cluster_pro(unsigned *pro, const int32_t *cellF, const int32_t *posC, int nF, int perC, int pitchF, int64_t planeF,
+						      int pitchC, int64_t planeC, int nxC, int nyC, int nzC, int s0, int s1, int s2)
+{
+    const int k = blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= nF) return;
+    const int64_t i = cellF[k];
+    const int fz = int(i / planeF);
+    const int64_t rem = i - int64_t(fz) * planeF;
+    const int fy = int(rem / pitchF), fx = int(rem - int64_t(fy) * pitchF);
+    const int mx = (fx >> 1) + s0, my = (fy >> 1) + s1, mz = (fz >> 1) + s2;
+    const int xs = (fx & 1) ? mx : mx - 1, ys = (fy & 1) ? my : my - 1, zs = (fz & 1) ? mz : mz - 1;
+    for (int c = 0; c < 8; ++c)
+    {
+	const int X = xs + (c & 1), Y = ys + ((c >> 1) & 1), Z = zs + (c >> 2);
+	unsigned ref = CLUSTER_NONE;
+	if (X >= 0 && Y >= 0 && Z >= 0 && X < nxC && Y < nyC && Z < nzC) ref = clusterPack(posC[int64_t(Z) * planeC + int64_t(Y) * pitchC + X], perC);
+	pro[size_t(c) * nF + k] = ref;
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_cluster_solve_ref(unsigned *ref, const int32_t *coarseIdx, const int32_t *pos, int n, int per)
+{
+    const int k = blockIdx.x * BLOCK + threadIdx.x;
+    if (k < n) ref[k] = clusterPack(pos[coarseIdx[k]], per);
+}
+
+} // namespace gmg

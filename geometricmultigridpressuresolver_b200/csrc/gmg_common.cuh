@@ -77,6 +77,8 @@ struct Level
     int ownLo = 0, ownHi = 0;    // owned planes [ownLo, ownHi) in local storage coordinates
     uint8_t *labelsAlloc = nullptr; // the level's labels over the GLOBAL box (every rank holds them; 1 byte per cell)
     uint8_t *labels = nullptr;   // = labelsAlloc + zOff * plane
+    uint8_t *flagsAlloc = nullptr;  // band flags over the GLOBAL box (gmg_kernels.cuh: SM_JACOBI_ZERO): bit0 in band, bit1 next to it
+    uint8_t *bandFlags = nullptr;   // = flagsAlloc + zOff * plane
     int64_t nActive = 0, nInterior = 0; // over the local stored box
     int64_t nActiveGlobal = 0;
     // boundary band: [0,nBoundary) BOUNDARY cells, [nBoundary,nBand) INTERIOR cells of the band; linear order inside each part
@@ -147,6 +149,7 @@ struct gmg_ctx
     int64_t commOps = 0;          // communication operations enqueued since the last launch-count reset
     void *p2p = nullptr;          // gmg::P2pState: peer-memory mailboxes (gmg_p2p.cuh); null = NCCL for every exchange
     bool p2pDisabled = false;
+    int clusterSize = 0;           // CTAs of the coarse-cycle cluster: 0 = not probed yet, -1 = cluster launch refused
     bool deviceLoopBroken = false; // the driver refused the conditional-graph PCG loop once: host loop from then on
     int p2pGenerations = 0;
     std::vector<gmg_solver *> solvers;  // live solvers of this context (their cached graphs are dropped when the arenas are re-mapped)
@@ -183,6 +186,10 @@ struct gmg_solver
     void *compactArgs = nullptr;  // host copy of the kernel's CompactArgs
     void *compactBlob = nullptr;  // device tables behind it
     size_t compactSmem = 0;
+    // the same levels in one thread-block cluster with distributed shared memory (gmg_cluster.cuh); preferred when available
+    void *clusterArgs = nullptr;  // host copy of the kernel's ClusterArgs
+    void *clusterSlab = nullptr;  // device tables behind it
+    size_t clusterSmem = 0;
     // PCG work grids (level 0)
     double *pcgR = nullptr, *pcgP = nullptr, *pcgZ = nullptr, *pcgT = nullptr, *pcgX = nullptr, *pcgB = nullptr;
     double *diagInv = nullptr;           // diagonal preconditioner grid (GFS.cpp:487-560), built on first use
@@ -203,6 +210,7 @@ struct gmg_solver
     };
     std::map<std::tuple<int, const void *, const void *, int>, GraphEntry> graphs;
     bool useGraphs = true;
+    bool zeroAware = true;        // zero-aware down-stroke (no zero fill, SM_JACOBI_ZERO); GMG_ZERO_AWARE=0 at creation restores the fill
 };
 
 struct gmg_grid

@@ -128,11 +128,16 @@ struct Scalars
 //   CTAs [nChunks, +boundaryCTAs) : BOUNDARY-labelled cells from the coefficient records (Ops.h:208-255)
 // Reference arithmetic order kept: lap = -sum over (axis, direction) of c*u, then += diag*u(centre).
 // ------------------------------------------------------------------------------------------------
-enum StencilMode { SM_JACOBI = 0, SM_APPLY = 1, SM_RESIDUAL = 2 };
+// SM_JACOBI_ZERO: the interior sweep of a down-stroke, where x is zero everywhere except on the boundary band (the band
+// sweeps before it started from x = 0): the grid is NOT zero-filled first -- whatever it holds off the band is ignored.  A cell
+// whose 7-point neighbourhood holds no band cell gets (2/3) b / 6 without reading x at all; near the band every value is
+// taken through the band mask.  Bitwise the result of SM_JACOBI on a zero-filled grid.
+enum StencilMode { SM_JACOBI = 0, SM_APPLY = 1, SM_RESIDUAL = 2, SM_JACOBI_ZERO = 3 };
 
 struct StencilArgs
 {
     const uint8_t *labels;
+    const uint8_t *flags;   // SM_JACOBI_ZERO: bit0 = cell is in the boundary band, bit1 = INTERIOR cell with a band cell in its 7-point neighbourhood
     const double *in;   // x (Jacobi/residual) or source (apply)
     const double *b;    // rhs (Jacobi/residual)
     double *out;        // Jacobi: new x (out of place); apply: A in; residual: b - A in
@@ -159,6 +164,7 @@ __device__ __forceinline__ double stencilFinish(double lap, double centre, doubl
 {
     if (MODE == SM_APPLY) return lap;
     if (MODE == SM_RESIDUAL) return rhs + (-1.0) * lap;  // addVectors(residual, rhs, residual, -1), Ops.h:731
+    // SM_JACOBI and SM_JACOBI_ZERO:
     double r = rhs - lap;                                 // Ops.h:357-361
     r /= diag;
     return centre + (2.0 / 3.0) * r;
@@ -177,13 +183,18 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 	const int zb = c / a.chunksPerPlane;
 	const int64_t inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * tid;
 	const int z0 = zb * CHUNK_Z;
-	uchar2 lab[CHUNK_Z];
+	uchar2 lab[CHUNK_Z], flg[CHUNK_Z];
 #pragma unroll
 	for (int dz = 0; dz < CHUNK_Z; ++dz)
 	{
 	    const int z = z0 + dz;
 	    lab[dz] = make_uchar2(L_EXTERIOR, L_EXTERIOR);
-	    if (inPlane < a.plane && z >= a.zlo && z < a.zhi) lab[dz] = *reinterpret_cast<const uchar2 *>(a.labels + int64_t(z) * a.plane + inPlane);
+	    flg[dz] = make_uchar2(0, 0);
+	    if (inPlane < a.plane && z >= a.zlo && z < a.zhi)
+	    {
+		lab[dz] = *reinterpret_cast<const uchar2 *>(a.labels + int64_t(z) * a.plane + inPlane);
+		if (MODE == SM_JACOBI_ZERO) flg[dz] = *reinterpret_cast<const uchar2 *>(a.flags + int64_t(z) * a.plane + inPlane);
+	    }
 	}
 	pdlWait();
 #pragma unroll
@@ -194,6 +205,54 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 	    const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
 	    if (!(a0 | a1)) continue;
 	    const int64_t i = int64_t(z) * a.plane + inPlane;
+	    if (MODE == SM_JACOBI_ZERO)
+	    {
+		const double2 rhs = ld2(a.b + i);
+		double o0, o1;
+		if (!((flg[dz].x | flg[dz].y) & 2))
+		{
+		    // no band cell in either neighbourhood: every x is zero, lap = +0.0, and centre + (2/3)((b - 0) / 6) = (2/3)(b / 6)
+		    o0 = (2.0 / 3.0) * (rhs.x / 6.0);
+		    o1 = (2.0 / 3.0) * (rhs.y / 6.0);
+		}
+		else
+		{
+		    // values through the band mask: whatever the grid holds off the band reads as zero
+		    const uint8_t *f = a.flags + i;
+		    const uchar2 fc = *reinterpret_cast<const uchar2 *>(f);
+		    const uchar2 fym = *reinterpret_cast<const uchar2 *>(f - a.pitch), fyp = *reinterpret_cast<const uchar2 *>(f + a.pitch);
+		    const uchar2 fzm = *reinterpret_cast<const uchar2 *>(f - a.plane), fzp = *reinterpret_cast<const uchar2 *>(f + a.plane);
+		    const int fxm = f[-1], fxp = f[2];
+		    double2 c2 = ld2(a.in + i);
+		    double xm = a.in[i - 1], xp = a.in[i + 2];
+		    double2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
+		    double2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
+		    if (!(fc.x & 1)) c2.x = 0.0;
+		    if (!(fc.y & 1)) c2.y = 0.0;
+		    if (!(fxm & 1)) xm = 0.0;
+		    if (!(fxp & 1)) xp = 0.0;
+		    if (!(fym.x & 1)) ym.x = 0.0;
+		    if (!(fym.y & 1)) ym.y = 0.0;
+		    if (!(fyp.x & 1)) yp.x = 0.0;
+		    if (!(fyp.y & 1)) yp.y = 0.0;
+		    if (!(fzm.x & 1)) zm.x = 0.0;
+		    if (!(fzm.y & 1)) zm.y = 0.0;
+		    if (!(fzp.x & 1)) zp.x = 0.0;
+		    if (!(fzp.y & 1)) zp.y = 0.0;
+		    double lap0 = -xm;
+		    lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
+		    lap0 += 6.0 * c2.x;
+		    double lap1 = -c2.x;
+		    lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
+		    lap1 += 6.0 * c2.y;
+		    o0 = stencilFinish<MODE>(lap0, c2.x, rhs.x, 6.0);
+		    o1 = stencilFinish<MODE>(lap1, c2.y, rhs.y, 6.0);
+		}
+		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
+		else if (a0) a.out[i] = o0;
+		else a.out[i + 1] = o1;
+		continue;
+	    }
 	    const double2 c2 = ld2(a.in + i);
 	    const double xm = a.in[i - 1], xp = a.in[i + 2];
 	    const double2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
@@ -278,8 +337,10 @@ constexpr int BAND_PER_THREAD = 2;  // cells per thread: two independent gather 
 // FROM_COMPACT: centre/band-neighbour values come from vin; TO_GRID: result goes to x[idx];
 // FIRST: rhs is gathered from the grid and cached in bandB; ZERO: the grid is known to be all zero;
 // HAS_W: level 0 with face weights -- BOUNDARY cells multiply by their coefficient records (elsewhere every coefficient is 1)
+// FZ: the grid was all zero when this sweep group started, so the frozen (non-band) neighbours are zero and are not read at
+// all -- the grid may hold anything off the band (no zero fill before the group, see SM_JACOBI_ZERO)
 // Prologue (static metadata, before pdlWait): grid index, neighbour references, diagonal, coefficient record.
-template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W>
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false>
 __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 {
     int64_t gi[BAND_PER_THREAD];
@@ -326,7 +387,12 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 		const int r = ref[c][n];
 		if (r == BAND_SKIP) continue;
 		double u;
-		if (FROM_COMPACT) u = r >= 0 ? a.vin[r] : a.x[-2 - r];
+		if (FROM_COMPACT && FZ)
+		{
+		    if (r < 0) continue;  // a frozen neighbour holds 0: lap -= c * 0 changes nothing
+		    u = a.vin[r];
+		}
+		else if (FROM_COMPACT) u = r >= 0 ? a.vin[r] : a.x[-2 - r];
 		else u = a.x[i + stride[n]];
 		if (weighted)
 		{
@@ -350,11 +416,11 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 	else a.vout[k] = v[c];
     }
 }
-template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W>
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false>
 __global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
 {
     pdlLaunch();
-    bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W>(a, blockIdx.x, threadIdx.x);
+    bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W, FZ>(a, blockIdx.x, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t *bandIdx, const double *v, int nBand)
@@ -1200,6 +1266,12 @@ __global__ void __launch_bounds__(BLOCK) k_band_dilate(uint8_t *out, const uint8
 	if (in[i - 1] | in[i + 1] | in[i - g.pitch] | in[i + g.pitch] | in[i - g.plane] | in[i + g.plane]) m = 1;
     }
     out[i] = m;
+}
+// band flags of SM_JACOBI_ZERO: bit0 = in the band, bit1 = in the band dilated once more (INTERIOR cells only)
+__global__ void __launch_bounds__(BLOCK) k_band_flag_grid(uint8_t *flags, const uint8_t *band, const uint8_t *dilated, int64_t total)
+{
+    const int64_t i = int64_t(blockIdx.x) * BLOCK + threadIdx.x;
+    if (i < total) flags[i] = uint8_t((band[i] ? 1 : 0) | (dilated[i] ? 2 : 0));
 }
 // flags for the two compactions: which = 0 -> BOUNDARY cells, 1 -> INTERIOR cells of the band
 __global__ void __launch_bounds__(BLOCK) k_band_flags(uint8_t *flags, const uint8_t *mask, const uint8_t *labels, int which, int64_t total)

@@ -383,3 +383,28 @@ def test_pinned_host_buffers_move_only_the_active_rectangles(gpu_ctx):
         for a in (xp, bp):
             rt.cudaHostUnregister(a.ctypes.data)
     s.close()
+
+
+def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
+    """The coarse levels have three implementations -- one kernel per operator, the one-CTA shared-memory cycle, the
+    thread-block-cluster cycle with distributed shared memory -- and the down-stroke two (zero fill + plain Jacobi, or the
+    zero-aware sweep).  Per cell they run the same arithmetic in the same order: a V-cycle must agree BITWISE between them."""
+    bl, bw, dx = D.flipsplash_domain(64)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    rb = D.random_rhs(labels, dx, seed=21)
+    x0 = D.random_active(labels, 22, scale=dx * dx)
+    results = {}
+    for name, env in [("cluster", {}), ("compact", {"GMG_CLUSTER_CYCLE": "0"}), ("kernels", {"GMG_COARSE_FUSED": "0"}),
+                      ("zero_fill", {"GMG_ZERO_AWARE": "0"}), ("cluster8", {"GMG_CLUSTER_SIZE": "8"}), ("first2", {"GMG_FUSED_FIRST": "2"})]:
+        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+        results[name] = (s.applyVCycle(np.zeros_like(rb), rb), s.applyVCycle(x0, rb, True), s.solveGeometricConjugateGradient(np.zeros_like(rb), rb, 1e-8, 50))
+        s.close()
+    ref = results["kernels"]
+    for name, (v, vg, (x, it, hist)) in results.items():
+        assert (v == ref[0]).all(), name
+        assert (vg == ref[1]).all(), name
+        assert it == ref[2][1] and (hist == ref[2][2]).all() and (x == ref[2][0]).all(), name
