@@ -1,6 +1,7 @@
 // gmg_b200.cu -- host side of the B200-native MGPCG library: C ABI (include/gmg_b200.h), solver
 // construction (labels, bands, coarse factor), V-cycle and PCG drivers.  No CPU fallback: every
 // entry point needs a CUDA device and fails with GMG_ERR_CUDA otherwise.
+#include <cuda.h>  // CUtensorMap and its enums only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -919,7 +920,7 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 	auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
 	const size_t n1 = size_t(std::max(nBand, 1)), nb1 = size_t(std::max(nB, 1));
 	const size_t oIdx = take(sizeof(int32_t) * n1), oRef = take(sizeof(int32_t) * 6 * n1), oV0 = take(sizeof(double) * n1), oV1 = take(sizeof(double) * n1),
-		     oB = take(sizeof(double) * n1), oCoef = take(sizeof(double) * 8 * nb1);
+		     oB = take(sizeof(double) * n1), oCoef = take(sizeof(double) * 8 * nb1), oCode = take(sizeof(unsigned short) * nb1);
 	char *slab = nullptr;
 	GMG_CUDA(devMalloc(&slab, off));
 	L.bandSlab = slab;
@@ -930,6 +931,7 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 	L.bandV1 = reinterpret_cast<double *>(slab + oV1);
 	L.bandB = reinterpret_cast<double *>(slab + oB);
 	L.bcoef = reinterpret_cast<double *>(slab + oCoef);
+	L.wcode = reinterpret_cast<unsigned short *>(slab + oCode);
     }
     GMG_CUDA(cudaMemcpyAsync(L.bandIdx, idxB, sizeof(int32_t) * nB, cudaMemcpyDeviceToDevice, ctx->stream));
     GMG_CUDA(cudaMemcpyAsync(L.bandIdx + nB, idxI, sizeof(int32_t) * nI, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -966,7 +968,7 @@ static int buildCoefs(gmg_ctx *ctx, Level &L, const double *w0, const double *w1
     if (L.nBoundary > 0)
     {
 	GMG_LAUNCH(ctx, KC_SETUP, 0);
-	k_band_coef<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bcoef, L.bandIdx, L.nBoundary, L.labels, w0, w1, w2, L.g.pitch,
+	k_band_coef<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bcoef, L.wcode, L.bandIdx, L.nBoundary, L.labels, w0, w1, w2, L.g.pitch,
 										   L.g.plane);
     }
     L.hasWeights = w0 != nullptr;
@@ -1056,7 +1058,7 @@ struct CoefJob
 static int coefKernelSparse(gmg_ctx *ctx, Level &L, const double *dw)
 {
     GMG_LAUNCH(ctx, KC_SETUP, 0);
-    k_band_coef_sparse<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bcoef, L.bandIdx, L.nBoundary, L.labels, dw, L.g.pitch, L.g.plane);
+    k_band_coef_sparse<<<unsigned(divUp(L.nBoundary, BLOCK)), BLOCK, 0, ctx->stream>>>(L.bcoef, L.wcode, L.bandIdx, L.nBoundary, L.labels, dw, L.g.pitch, L.g.plane);
     return GMG_OK;
 }
 
@@ -1212,6 +1214,74 @@ static int buildChunks(gmg_ctx *ctx, Level &L)
 }
 
 // tile lists of the tiled Gauss-Seidel smoother (Ops.h:441-448: tiles of the expanded grid, parity of tx+ty+tz)
+// TMA path of the full-grid stencil kernels (gmg_kernels.cuh: k_stencil_tma): list of the 64 x 8 x 4 bricks holding an
+// INTERIOR cell.  Built for levels of at least GMG_TMA_MIN_CELLS cells when GMG_TMA=1 (A/B switch, profiles/).
+static int tmaMode()
+{
+    const char *e = getenv("GMG_TMA");  // read at solver creation; GMG_TMA=0 forces the plain-load kernels everywhere
+    return e ? atoi(e) : 1;
+}
+static int buildBricks(gmg_ctx *ctx, Level &L)
+{
+    // default: levels whose grids do not fit L2 (measured, profiles/r02_tma_ab.md: residual 0.78 -> 0.89 of the HBM peak at
+    // 512^3; at 256^3, where a level-0 grid is 34 MB and L2-resident, the brick kernel's longer prologue loses 15 %)
+    const char *mc = getenv("GMG_TMA_MIN_CELLS");
+    const int64_t minCells = mc ? atoll(mc) : int64_t(12) << 20;
+    if (!tmaMode() || L.nInterior < minCells) return GMG_OK;
+    const Geom &g = L.g;
+    L.bricksX = int(divUp(g.n[0], TB_X));
+    L.bricksY = int(divUp(g.n[1], TB_Y));
+    const int bz = int(divUp(g.n[2], TB_Z));
+    const int64_t nb = int64_t(L.bricksX) * L.bricksY * bz;
+    uint8_t *flags = nullptr;
+    GMG_CUDA(devMalloc(&flags, size_t(nb)));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_brick_flags<<<unsigned(nb), BLOCK, 0, ctx->stream>>>(flags, L.labels, L.bricksX, L.bricksY, g.pitch, g.plane, g.n[1], g.n[2]);
+    }
+    GMG_TRY(selectFlagged(ctx, flags, nb, &L.bricks, &L.nBricks));
+    GMG_CUDA(devFree(flags));
+    return GMG_OK;
+}
+
+// 3D tensor map over a vector grid INCLUDING its two guard planes (the tensor's plane 0 is the lower guard plane), box =
+// brick + halo.  Cached per grid pointer: the kernels take it by value (__grid_constant__), so a captured graph keeps its own copy.
+static int tensorMapOf(gmg_solver *s, int level, const double *grid, TmaMap *out)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+				 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+	void *fn = nullptr;
+	cudaDriverEntryPointQueryResult q;
+	if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); fn = nullptr; }
+	return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (!encode) return invalid("cuTensorMapEncodeTiled is not available in this driver");
+    auto key = std::make_pair(level, grid);
+    auto it = s->tensorMaps.find(key);
+    if (it == s->tensorMaps.end())
+    {
+	const Geom &g = s->lv[level].g;
+	static_assert(sizeof(CUtensorMap) == sizeof(TmaMap), "TmaMap must mirror CUtensorMap");
+	TmaMap m;
+	const cuuint64_t dims[3] = {cuuint64_t(g.pitch), cuuint64_t(g.n[1]), cuuint64_t(g.n[2] + 2)};
+	const cuuint64_t strides[2] = {cuuint64_t(g.pitch) * sizeof(double), cuuint64_t(g.plane) * sizeof(double)};
+	const cuuint32_t box[3] = {TB_BOX_X, TB_BOX_Y, TB_BOX_Z};
+	const cuuint32_t estr[3] = {1, 1, 1};
+	const CUresult r = encode(reinterpret_cast<CUtensorMap *>(&m), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(grid) - g.plane, dims, strides, box, estr,
+				  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS)
+	{
+	    char buf[128];
+	    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+	    return invalid(buf);
+	}
+	it = s->tensorMaps.emplace(key, m).first;
+    }
+    *out = it->second;
+    return GMG_OK;
+}
+
 static int buildGsTiles(gmg_ctx *ctx, Level &L)
 {
     const Geom &g = L.g;
@@ -1294,7 +1364,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 static void freeLevel(Level &L)
 {
     devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab); devFree(L.flagsAlloc);
-    devFree(L.chunksInterior); devFree(L.chunksActive);
+    devFree(L.chunksInterior); devFree(L.chunksActive); devFree(L.bricks);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
     L = Level();
@@ -2212,6 +2282,7 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
 	if (st != GMG_OK) return fail(st);
 	if (level == 0) lap("level 0 coefficient records");
 	if ((st = buildChunks(ctx, L)) != GMG_OK) return fail(st);
+	if ((st = buildBricks(ctx, L)) != GMG_OK) return fail(st);
 	if (s->opt.use_gauss_seidel && (st = buildGsTiles(ctx, L)) != GMG_OK) return fail(st);
 	maxGrid = std::max(maxGrid, L.nChunksActive + int(divUp(L.nBoundary, BLOCK)) + 1);
 	if ((st = allocGrid(&L.xAlt, L.g)) != GMG_OK) return fail(st);
@@ -2350,6 +2421,7 @@ static StencilArgs stencilArgs(gmg_solver *s, int level, const double *in, const
     a.nBoundary = L.nBoundary;
     a.bandIdx = L.bandIdx;
     a.bcoef = L.bcoef;
+    a.wcode = L.wcode;
     a.partials = s->ctx->partials;
     a.ticket = s->ctx->ticket;
     a.result = nullptr;
@@ -2368,6 +2440,36 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
     if (grid == 0) return GMG_OK;
     cudaStream_t st = s->ctx->stream;
     const double n = double(L.nActive);
+    if (L.bricks && mode != SM_JACOBI_ZERO)
+    {
+	// TMA-staged variant: one CTA per 64 x 8 x 4 brick
+	TmaMap tm;
+	GMG_TRY(tensorMapOf(s, level, in, &tm));
+	const unsigned tgrid = unsigned(L.nBricks + divUp(L.nBoundary, BLOCK));
+	const int ny = L.g.n[1];
+	if (mode == SM_JACOBI)
+	{
+	    GMG_LAUNCH(s->ctx, KC_JACOBI, n * 25.0);
+	    GMG_CUDA(launchK((k_stencil_tma<SM_JACOBI, false>), tgrid, unsigned(BLOCK), size_t(0), st, a, tm, L.bricks, L.nBricks, L.bricksX, L.bricksY, ny));
+	}
+	else if (mode == SM_RESIDUAL)
+	{
+	    GMG_LAUNCH(s->ctx, KC_RESIDUAL, n * 25.0);
+	    GMG_CUDA(launchK((k_stencil_tma<SM_RESIDUAL, false>), tgrid, unsigned(BLOCK), size_t(0), st, a, tm, L.bricks, L.nBricks, L.bricksX, L.bricksY, ny));
+	}
+	else if (dotResult)
+	{
+	    GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
+	    GMG_CUDA(launchK((k_stencil_tma<SM_APPLY, true>), tgrid, unsigned(BLOCK), size_t(0), st, a, tm, L.bricks, L.nBricks, L.bricksX, L.bricksY, ny));
+	}
+	else
+	{
+	    GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
+	    GMG_CUDA(launchK((k_stencil_tma<SM_APPLY, false>), tgrid, unsigned(BLOCK), size_t(0), st, a, tm, L.bricks, L.nBricks, L.bricksX, L.bricksY, ny));
+	}
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     if (mode == SM_JACOBI)
     {
 	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 25.0);
@@ -2411,6 +2513,7 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
     a.bandIdx = L.bandIdx;
     a.bandRef = L.bandRef;
     a.bcoef = L.bcoef;
+    a.wcode = L.wcode;
     a.bandB = L.bandB;
     a.nBoundary = L.nBoundary;
     a.nBand = L.nBand;
@@ -2576,18 +2679,20 @@ static int buildClusterCycle(gmg_solver *s)
 	if (ctx->clusterSize < 0) return GMG_OK;
     }
     const int CL = ctx->clusterSize;
-    auto perOf = [&](int64_t n) { return int((divUp(std::max<int64_t>(n, 1), CL) + 1) & ~int64_t(1)); };
+    // cells per CTA block: an equal share, but never less than one cell per thread -- a level of a thousand cells lives in ONE
+    // CTA and smooths entirely out of its own shared memory (measured: spread thin over 16 CTAs every neighbour is a remote load)
+    auto perOf = [&](int64_t n) { return int((std::max<int64_t>(divUp(std::max<int64_t>(n, 1), CL), std::min<int64_t>(std::max<int64_t>(n, 1), CLUSTER_THREADS)) + 1) & ~int64_t(1)); };
+    // per cell of a block: two solution arrays + rhs (24 bytes) and the smoother tables (6 x 16-bit codes, diagonal, flags: 14 bytes)
     auto smemOf = [&](int first) {
-	size_t doubles = 0;
-	for (int l = first; l < s->levels; ++l) doubles += size_t(3) * perOf(s->lv[l].nActive);
-	return (doubles + size_t(s->nCoarse) + 2) * sizeof(double);
+	size_t bytes = 0;
+	for (int l = first; l < s->levels; ++l) bytes += size_t(38) * perOf(s->lv[l].nActive) + 32;
+	return bytes + (size_t(s->nCoarse) + 2) * sizeof(double);
     };
     // finest level (>= 1: level 0 carries face weights and the caller's grids; replicated levels only) whose vectors fit the
     // cluster's shared memory with at most 8 cells per thread
     int first = -1;
     for (int l = std::max(1, s->shardLevels); l < s->levels; ++l)
-	if (s->levels - l <= CLUSTER_MAX_LEVELS && s->lv[l].nActive <= int64_t(CL) * CLUSTER_THREADS * 8 && perOf(s->lv[l].nActive) < (1 << CLUSTER_OWNER_SHIFT) &&
-	    smemOf(l) + 1024 <= size_t(smemMax))
+	if (s->levels - l <= CLUSTER_MAX_LEVELS && perOf(s->lv[l].nActive) <= CLUSTER_MAX_PER && smemOf(l) + 1024 <= size_t(smemMax))
 	{
 	    first = l;
 	    break;
@@ -2598,13 +2703,14 @@ static int buildClusterCycle(gmg_solver *s)
     // one slab for every table
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-    struct Offs { size_t cell, nbr, rst, pro, diag, flags; };
+    struct Offs { size_t cell, nbr, nbr16, rst, pro, diag, flags; };
     std::vector<Offs> o(nl);
     for (int q = 0; q < nl; ++q)
     {
 	const size_t n = size_t(std::max<int64_t>(s->lv[first + q].nActive, 1));
 	o[q].cell = take(4 * n);
 	o[q].nbr = take(4 * 6 * n);
+	o[q].nbr16 = take(2 * 6 * n);
 	o[q].rst = q > 0 ? take(4 * 64 * n) : 0;
 	o[q].pro = q + 1 < nl ? take(4 * 8 * n) : 0;
 	o[q].diag = take(n);
@@ -2630,6 +2736,7 @@ static int buildClusterCycle(gmg_solver *s)
 	K.off = smemOff;
 	smemOff += 3 * K.per;
 	K.nbr = reinterpret_cast<const unsigned *>(slab + o[q].nbr);
+	K.nbr16 = reinterpret_cast<const unsigned short *>(slab + o[q].nbr16);
 	K.rst = reinterpret_cast<const unsigned *>(slab + o[q].rst);
 	K.pro = reinterpret_cast<const unsigned *>(slab + o[q].pro);
 	K.diag = reinterpret_cast<const uint8_t *>(slab + o[q].diag);
@@ -2678,6 +2785,7 @@ static int buildClusterCycle(gmg_solver *s)
 	    GMG_LAUNCH(ctx, KC_SETUP, 0);
 	    k_cluster_nbr<<<grid, BLOCK, 0, ctx->stream>>>(const_cast<unsigned *>(K.nbr), const_cast<uint8_t *>(K.diag), const_cast<uint8_t *>(K.flags), cell, pos[q],
 							   L.labels, L.bandFlags, n, K.per, g.pitch, g.plane);
+	    k_cluster_nbr16<<<grid, BLOCK, 0, ctx->stream>>>(const_cast<unsigned short *>(K.nbr16), K.nbr, n, K.per);
 	}
 	if (q > 0)
 	{
@@ -2705,13 +2813,23 @@ static int buildClusterCycle(gmg_solver *s)
     c->nLevels = nl;
     c->sweeps = s->opt.boundary_iterations;
     c->scratchOff = smemOff;
+    {
+	// table region behind the vectors and the direct solve's scratch (16-byte aligned pieces)
+	size_t tab = (size_t(smemOff + s->nCoarse + 2) * sizeof(double) + 15) & ~size_t(15);
+	for (int q = 0; q < nl; ++q)
+	{
+	    c->lv[q].tabOff = int(tab);
+	    tab = (tab + size_t(14) * c->lv[q].per + 15) & ~size_t(15);
+	}
+	s->clusterSmem = tab;
+    }
     c->cellTop = reinterpret_cast<const int32_t *>(slab + o[0].cell);
     c->bTop = s->lv[first].b;
     c->xTop = s->lv[first].x;
     c->solveRef = solveRef;
     c->nSolve = s->nCoarse;
     c->inv = s->coarseInv;
-    s->clusterSmem = size_t(smemOff + s->nCoarse + 2) * sizeof(double);
+    if (s->clusterSmem > size_t(smemMax)) return invalid("cluster cycle: shared-memory estimate too tight");
     s->fusedFirst = first;
     return GMG_OK;
 }
@@ -3166,9 +3284,68 @@ static int applyBandWindow(gmg_solver *s)
     return GMG_OK;
 }
 
+// doPrintStats (MG.h:24, the timing lines of MG.cpp:432-879): the V-cycle is launched kernel by kernel with a CUDA-event pair
+// around every launch and the stages are printed under the reference's own headings -- device times, in seconds like
+// UT_StopWatch's.  Consecutive band sweeps are one "Boundary smoother" line; the levels that run inside the fused coarse
+// cycle (one kernel: no per-stage boundary exists) are one line.
+static int vcyclePrintStats(gmg_solver *s, double *x, const double *b, bool useInitialGuess)
+{
+    gmg_ctx *ctx = s->ctx;
+    flushProfile(ctx);
+    const bool wasProfiling = ctx->profiling;
+    ctx->profiling = true;
+    const int st = vcycleLaunches(s, x, b, useInitialGuess);
+    ctx->profiling = wasProfiling;
+    cudaStreamSynchronize(ctx->stream);
+    std::vector<ProfileRec> recs;
+    recs.swap(ctx->recs);
+    int heading = -100;
+    bool up = false;
+    auto ms = [](const ProfileRec &r) { float t = 0; cudaEventElapsedTime(&t, r.e0, r.e1); return double(t); };
+    for (size_t i = 0; i < recs.size();)
+    {
+	const ProfileRec &r = recs[i];
+	double t = ms(r);
+	size_t j = i + 1;
+	if (r.klass == KC_BAND || r.klass == KC_GS)
+	    for (; j < recs.size() && recs[j].klass == r.klass && recs[j].level == r.level; ++j) t += ms(recs[j]);
+	if (r.klass == KC_COARSE) up = true;
+	const int lvl = r.klass == KC_RESTRICT ? r.level - 1 : r.level;  // a restriction is timed on the level it leaves (MG.cpp:536-552)
+	const int key = (up && r.klass != KC_COARSE ? 1000 : 0) + lvl;
+	if (r.klass != KC_COARSE && r.klass != KC_ZERO && r.klass != KC_BLAS1 && r.klass != KC_HALO && key != heading)
+	{
+	    heading = key;
+	    if (lvl == 0) printf(up ? "    Fine Upstroke Smoother\n" : "    Fine Downstroke Smoother\n");
+	    else printf(up ? "    Upstroke Smoother level: %d\n" : "    Downstroke Smoother level: %d\n", lvl);
+	}
+	switch (r.klass)
+	{
+	case KC_BAND: printf("      Boundary smoother time: %g\n", t * 1e-3); break;
+	case KC_JACOBI: case KC_GS: printf("      Smoother time: %g\n", t * 1e-3); break;
+	case KC_RESIDUAL: printf("      Compute residual time: %g\n", t * 1e-3); break;
+	case KC_RESTRICT: printf("      Restriction time: %g\n", t * 1e-3); break;
+	case KC_PROLONG: printf("      Prolongation time: %g\n", t * 1e-3); break;
+	case KC_COARSE:
+	    if (s->fusedFirst > 0) printf("    Levels %d to %d (down-stroke, direct solve, up-stroke in one kernel) time: %g\n", s->fusedFirst, s->levels - 1, t * 1e-3);
+	    else printf("      Direct solve time: %g\n", t * 1e-3);
+	    break;
+	default: break;
+	}
+	i = j;
+    }
+    fflush(stdout);
+    accumulateRecs(ctx, recs, true);
+    return st;
+}
+
 static int vcycleDevice(gmg_solver *s, double *x, const double *b, bool useInitialGuess)
 {
     GMG_TRY(applyBandWindow(s));
+    if (s->opt.print_stats && !s->ctx->capturing)
+    {
+	if (s->opt.operators_only && s->levels > 1) return invalid("this solver handle was created with operators_only: no coarse factor, no V-cycle");
+	return vcyclePrintStats(s, x, b, useInitialGuess);
+    }
     if (s->opt.operators_only && s->levels > 1) return invalid("this solver handle was created with operators_only: no coarse factor, no V-cycle");
     return runGraphed(s, 0, x, b, useInitialGuess ? 1 : 0, [&]() { return vcycleLaunches(s, x, b, useInitialGuess); });
 }

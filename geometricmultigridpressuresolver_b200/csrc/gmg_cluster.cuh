@@ -6,9 +6,14 @@
 // direct solve, up-stroke -- run inside one kernel of ONE cluster (16 CTAs x 1024 threads, or 8 where 16 is refused):
 //   * every level's cells are a compact list in storage order, cut into equal blocks, one per CTA; the level's vectors
 //     (two ping-pong solution arrays and the right-hand side) live in the OWNING CTA's shared memory;
-//   * a neighbour / restriction tap / prolongation corner is a packed (owner CTA, index) reference resolved with
-//     cluster.map_shared_rank -- a distributed-shared-memory load over the SM-to-SM network, no global memory on the path;
-//     the reference tables themselves are read from global memory (coalesced, L2-resident, independent of the values);
+//   * a neighbour / restriction tap / prolongation corner is a packed (owner CTA, index) reference; a value owned by this
+//     CTA is a plain shared-memory load, a value owned by another CTA a distributed-shared-memory load over the SM-to-SM
+//     network (cluster.map_shared_rank) -- measured first version (profiles/r02_cluster_cycle.md): sending the LOCAL loads
+//     through the cluster window too made level 2 DSMEM-bandwidth-bound (~20 B/cycle/SM), 6 us per sweep;
+//   * the neighbour tables of the smoother (16-bit codes: same / previous / next CTA + index, else a "far" escape into the
+//     32-bit table), diagonals and flags are copied into shared memory ONCE, in the prologue before griddepcontrol.wait, so
+//     a smoothing step touches no global memory at all; the restriction / prolongation tables, used once per V-cycle, are
+//     read from global memory (coalesced, L2-resident);
 //   * a step ends on the hardware cluster barrier (barrier.cluster arrive.release / wait.acquire) instead of a kernel boundary.
 // Per cell the arithmetic and its order are those of k_stencil / k_band / k_restrict / k_prolong / k_coarse_solve (and of
 // k_compact_cycle, the one-CTA predecessor of this kernel, kept as the fallback), so the result is bitwise identical.
@@ -25,11 +30,20 @@ constexpr int CLUSTER_MAX_LEVELS = 10;
 constexpr unsigned CLUSTER_NONE = 0xffffffffu;
 constexpr int CLUSTER_OWNER_SHIFT = 20;  // packed reference = (owner CTA << 20) | index in the owner's block
 
+// 16-bit neighbour code: bits 15..13 = where, bits 12..0 = index in the owner's block (a block holds at most 8192 cells)
+constexpr unsigned short CODE_SAME = 0u << 13, CODE_PREV = 1u << 13, CODE_NEXT = 2u << 13, CODE_NONE = 3u << 13, CODE_FAR = 7u << 13;
+// Largest block the cycle takes: two cells per thread.  Measured (profiles/r02_cluster_cycle.md): the 67k-cell level 2 of the
+// 256^3 problem, 4.2k cells per CTA, costs 6 us per sweep on 16 SMs (fp64 divisions and shared-memory traffic of 4k cells on
+// one SM) against 4.4 us as a kernel of its own over 148 SMs -- the cluster pays only below ~30k cells.
+constexpr int CLUSTER_MAX_PER = 2048;
+
 struct ClusterLevel
 {
     int n;                 // active cells of the level
     int per;               // cells per CTA block (the last blocks may be short or empty)
     int off;               // offset (doubles) of this level's [xa | xb | b] arrays, `per` each, in every CTA's shared memory
+    int tabOff;            // offset (bytes) of this level's shared-memory tables: u16 nbr[6][per], u8 diag[per], u8 flags[per]
+    const unsigned short *nbr16;  // [6][n] 16-bit codes of the six neighbours (staged into shared memory block by block)
     const unsigned *nbr;   // [6][n]  packed reference of the -x,+x,-y,+y,-z,+z neighbour, CLUSTER_NONE = not active
     const unsigned *rst;   // [64][n] packed references (next FINER level) of the 4x4x4 restriction taps (levels below the top)
     const unsigned *pro;   // [8][n]  packed references (next COARSER level) of the 2x2x2 prolongation corners
@@ -53,37 +67,65 @@ struct ClusterArgs
 
 // the value behind a packed reference: `base` is the array's address in THIS CTA's shared memory; every CTA lays its
 // shared memory out identically, so the same offset is valid in the owner's
-__device__ __forceinline__ double clusterLoad(cg::cluster_group &cl, double *base, unsigned ref)
+// (a value this CTA owns is a plain shared-memory load: the cluster window moves ~20 bytes per cycle and SM, shared memory 128)
+__device__ __forceinline__ double clusterLoad(cg::cluster_group &cl, double *base, unsigned ref, int rank)
 {
-    return *cl.map_shared_rank(base + (ref & ((1u << CLUSTER_OWNER_SHIFT) - 1u)), ref >> CLUSTER_OWNER_SHIFT);
+    const unsigned owner = ref >> CLUSTER_OWNER_SHIFT, idx = ref & ((1u << CLUSTER_OWNER_SHIFT) - 1u);
+    if (int(owner) == rank) return base[idx];
+    return *cl.map_shared_rank(base + idx, owner);
+}
+
+// the level's shared-memory tables in this CTA
+struct ClusterTab
+{
+    const unsigned short *nbr;  // [6][per]
+    const uint8_t *diag, *flags;
+};
+__device__ __forceinline__ ClusterTab clusterTab(const ClusterLevel &L, unsigned char *smBytes)
+{
+    ClusterTab t;
+    t.nbr = reinterpret_cast<const unsigned short *>(smBytes + L.tabOff);
+    t.diag = smBytes + L.tabOff + size_t(12) * L.per;
+    t.flags = t.diag + L.per;
+    return t;
 }
 
 // A x at this CTA's j-th cell of the level (compact index k), in the operation order of computeLaplacian (Ops.h:177-260):
-// neighbours by (axis, direction), centre last
-__device__ __forceinline__ double clusterLap(cg::cluster_group &cl, const ClusterLevel &L, double *x, int k, int j, double diag)
+// neighbours by (axis, direction), centre last.  x: the solution array in THIS CTA's shared memory.
+__device__ __forceinline__ double clusterLap(cg::cluster_group &cl, const ClusterLevel &L, const ClusterTab &T, double *__restrict__ x, int rank, int k, int j,
+					     double diag)
 {
-    unsigned ref[6];
+    unsigned short code[6];
 #pragma unroll
-    for (int d = 0; d < 6; ++d) ref[d] = __ldg(L.nbr + size_t(d) * L.n + k);
+    for (int d = 0; d < 6; ++d) code[d] = T.nbr[d * L.per + j];
     double lap = 0.0;
 #pragma unroll
     for (int d = 0; d < 6; ++d)
-	if (ref[d] != CLUSTER_NONE) lap -= clusterLoad(cl, x, ref[d]);
+    {
+	const unsigned where = code[d] & 0xe000u, idx = code[d] & 0x1fffu;
+	if (where == CODE_NONE) continue;
+	double u;
+	if (where == CODE_SAME) u = x[idx];
+	else if (where == CODE_PREV) u = *cl.map_shared_rank(x + idx, rank - 1);
+	else if (where == CODE_NEXT) u = *cl.map_shared_rank(x + idx, rank + 1);
+	else u = clusterLoad(cl, x, __ldg(L.nbr + size_t(d) * L.n + k), rank);  // far: more than one block away (not at the sizes this cycle takes)
+	lap -= u;
+    }
     lap += diag * x[j];
     return lap;
 }
 
 // one damped-Jacobi sweep xin -> xout over the band cells (bandOnly; everything else is copied) or over all cells
 // (Ops.h:262-367, :524-619), ending on the cluster barrier
-__device__ __forceinline__ void clusterSweep(cg::cluster_group &cl, const ClusterLevel &L, double *xin, double *xout, const double *b, int first, int count,
-					     bool bandOnly)
+__device__ __forceinline__ void clusterSweep(cg::cluster_group &cl, const ClusterLevel &L, const ClusterTab &T, double *__restrict__ xin, double *__restrict__ xout,
+					     const double *__restrict__ b, int rank, int first, int count, bool bandOnly)
 {
+#pragma unroll 2
     for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
     {
-	const int k = first + j;
-	if (bandOnly && !(__ldg(L.flags + k) & 1)) { xout[j] = xin[j]; continue; }
-	const double diag = double(__ldg(L.diag + k));
-	const double lap = clusterLap(cl, L, xin, k, j, diag);
+	if (bandOnly && !(T.flags[j] & 1)) { xout[j] = xin[j]; continue; }
+	const double diag = double(T.diag[j]);
+	const double lap = clusterLap(cl, L, T, xin, rank, first + j, j, diag);
 	double r = b[j] - lap;
 	r /= diag;
 	xout[j] = xin[j] + (2.0 / 3.0) * r;
@@ -95,6 +137,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 {
     pdlLaunch();
     extern __shared__ double sm[];
+    unsigned char *smBytes = reinterpret_cast<unsigned char *>(sm);
     cg::cluster_group cl = cg::this_cluster();
     const int rank = int(cl.block_rank());
     const int nl = c.nLevels;
@@ -113,12 +156,30 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 	const ClusterLevel &L = c.lv[q];
 	int first, count;
 	blockOf(q, first, count);
+	const ClusterTab T = clusterTab(L, smBytes);
 	for (int s = 0; s < 2 * c.sweeps + 1; ++s)
 	{
-	    clusterSweep(cl, L, X(q, cur[q]), X(q, cur[q] ^ 1), B(q), first, count, s != c.sweeps);
+	    clusterSweep(cl, L, T, X(q, cur[q]), X(q, cur[q] ^ 1), B(q), rank, first, count, s != c.sweeps);
 	    cur[q] ^= 1;
 	}
     };
+    // prologue: this CTA's blocks of the (static) smoother tables go to shared memory while the restriction above the cycle's
+    // first level is still running
+    for (int q = 0; q < nl; ++q)
+    {
+	const ClusterLevel &L = c.lv[q];
+	int first, count;
+	blockOf(q, first, count);
+	unsigned short *tn = reinterpret_cast<unsigned short *>(smBytes + L.tabOff);
+	uint8_t *td = smBytes + L.tabOff + size_t(12) * L.per, *tf = td + L.per;
+	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
+	{
+#pragma unroll
+	    for (int d = 0; d < 6; ++d) tn[d * L.per + j] = __ldg(L.nbr16 + size_t(d) * L.n + first + j);
+	    td[j] = __ldg(L.diag + first + j);
+	    tf[j] = __ldg(L.flags + first + j);
+	}
+    }
     pdlWait();
     {
 	int first, count;
@@ -144,10 +205,11 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 	    // residual into the other solution array (the current one is kept for the up-stroke)
 	    double *x = X(q, cur[q]), *t = X(q, cur[q] ^ 1);
 	    const double *b = B(q);
+	    const ClusterTab T = clusterTab(L, smBytes);
+#pragma unroll 2
 	    for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
 	    {
-		const int k = first + j;
-		const double lap = clusterLap(cl, L, x, k, j, double(__ldg(L.diag + k)));
+		const double lap = clusterLap(cl, L, T, x, rank, first + j, j, double(T.diag[j]));
 		t[j] = b[j] + (-1.0) * lap;  // Ops.h:731
 	    }
 	}
@@ -162,18 +224,22 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 		const int k = cfirst + j;
 		const double rw[4] = {1. / 8., 3. / 8., 3. / 8., 1. / 8.};
 		double v = 0.0;
+		// one z-slice of taps per round: 16 independent table loads, then 16 independent value loads
 #pragma unroll
 		for (int z = 0; z < 4; ++z)
+		{
+		    unsigned ref[16];
+#pragma unroll
+		    for (int t16 = 0; t16 < 16; ++t16) ref[t16] = __ldg(C.rst + size_t(z * 16 + t16) * C.n + k);
+		    double val[16];
+#pragma unroll
+		    for (int t16 = 0; t16 < 16; ++t16) val[t16] = ref[t16] != CLUSTER_NONE ? clusterLoad(cl, t, ref[t16], rank) : 0.0;
 #pragma unroll
 		    for (int y = 0; y < 4; ++y)
-		    {
-			unsigned ref[4];
-#pragma unroll
-			for (int xx = 0; xx < 4; ++xx) ref[xx] = __ldg(C.rst + size_t((z * 4 + y) * 4 + xx) * C.n + k);
 #pragma unroll
 			for (int xx = 0; xx < 4; ++xx)
-			    if (ref[xx] != CLUSTER_NONE) v += rw[xx] * rw[y] * rw[z] * clusterLoad(cl, t, ref[xx]);  // an inactive tap adds +0.0, which never changes v
-		    }
+			    if (ref[y * 4 + xx] != CLUSTER_NONE) v += rw[xx] * rw[y] * rw[z] * val[y * 4 + xx];  // an inactive tap adds +0.0, which never changes v
+		}
 		bc[j] = v;
 	    }
 	}
@@ -188,7 +254,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 	{
 	    double *sb = sm + c.scratchOff;
 	    const int n = c.nSolve;
-	    for (int i = threadIdx.x; i < n; i += CLUSTER_THREADS) sb[i] = clusterLoad(cl, B(q), __ldg(c.solveRef + i));
+	    for (int i = threadIdx.x; i < n; i += CLUSTER_THREADS) sb[i] = clusterLoad(cl, B(q), __ldg(c.solveRef + i), rank);
 	    __syncthreads();
 	    const int lane = threadIdx.x & 31;
 	    for (int row = threadIdx.x >> 5; row < n; row += CLUSTER_THREADS / 32)
@@ -214,17 +280,18 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 	blockOf(q, first, count);
 	double *x = X(q, cur[q]);
 	double *xc = X(q + 1, cur[q + 1]);
+	const ClusterTab T = clusterTab(L, smBytes);
 	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
 	{
 	    const int k = first + j;
-	    const int f = __ldg(L.flags + k);
+	    const int f = T.flags[j];
 	    const double wx = (f & 2) ? .25 : .75, wy = (f & 4) ? .25 : .75, wz = (f & 8) ? .25 : .75;
 	    unsigned ref[8];
 #pragma unroll
 	    for (int p = 0; p < 8; ++p) ref[p] = __ldg(L.pro + size_t(p) * L.n + k);
 	    double v[8];
 #pragma unroll
-	    for (int p = 0; p < 8; ++p) v[p] = ref[p] != CLUSTER_NONE ? clusterLoad(cl, xc, ref[p]) : 0.0;
+	    for (int p = 0; p < 8; ++p) v[p] = ref[p] != CLUSTER_NONE ? clusterLoad(cl, xc, ref[p], rank) : 0.0;
 	    // corner p = x + 2 y + 4 z; lerp nesting x -> y -> z (Ops.h:841-871)
 	    const double e = lerpRef(lerpRef(lerpRef(v[0], v[1], wx), lerpRef(v[2], v[3], wx), wy),
 				     lerpRef(lerpRef(v[4], v[5], wx), lerpRef(v[6], v[7], wx), wy), wz);
@@ -285,6 +352,30 @@ __global__ void __launch_bounds__(BLOCK) k_cluster_nbr(unsigned *nbr, uint8_t *d
     const int64_t rem = i - int64_t(z) * plane;
     const int y = int(rem / pitch), x = int(rem - int64_t(y) * pitch);
     flags[k] = uint8_t((bandFlags[i] & 1) | ((x & 1) << 1) | ((y & 1) << 2) | ((z & 1) << 3));
+}
+
+// 16-bit neighbour codes from the packed 32-bit references
+__global__ void __launch_bounds__(BLOCK) k_cluster_nbr16(unsigned short *nbr16, const unsigned *nbr, int n, int per)
+{
+    const int k = blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= n) return;
+    const int mine = k / per;
+#pragma unroll
+    for (int d = 0; d < 6; ++d)
+    {
+	const unsigned ref = nbr[size_t(d) * n + k];
+	unsigned short code = CODE_NONE;
+	if (ref != CLUSTER_NONE)
+	{
+	    const int owner = int(ref >> CLUSTER_OWNER_SHIFT);
+	    const unsigned idx = ref & ((1u << CLUSTER_OWNER_SHIFT) - 1u);
+	    if (owner == mine) code = CODE_SAME | (unsigned short)idx;
+	    else if (owner == mine - 1) code = CODE_PREV | (unsigned short)idx;
+	    else if (owner == mine + 1) code = CODE_NEXT | (unsigned short)idx;
+	    else code = CODE_FAR;
+	}
+	nbr16[size_t(d) * n + k] = code;
+    }
 }
 
 // restriction taps of a coarse level in the next finer one (Ops.h:760-834); shift: coarse storage = (fine storage >> 1) + shift

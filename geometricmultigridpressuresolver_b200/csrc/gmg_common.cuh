@@ -89,10 +89,14 @@ struct Level
     int32_t *bandRef = nullptr;  // [6][nBand] neighbour reference (gmg_kernels.cuh: BandArgs::bandRef)
     bool hasWeights = false;     // level 0 built with face weights: BOUNDARY cells carry fractional coefficients
     double *bcoef = nullptr;     // [8][nBoundary]: coefficient on each of the 6 neighbours, the diagonal, the sum of the six face weights
+    unsigned short *wcode = nullptr;  // [nBoundary] two bits per neighbour: coefficient 0 / exactly 1 / fractional (gmg_kernels.cuh: coefCode)
     double *bandV0 = nullptr, *bandV1 = nullptr, *bandB = nullptr;
     // CTAs of the full-grid kernels: chunks holding at least one INTERIOR cell / one active cell
     int nChunksInterior = 0, nChunksActive = 0;
     int32_t *chunksInterior = nullptr, *chunksActive = nullptr;
+    // TMA path (k_stencil_tma): 64 x 8 x 4 bricks holding an INTERIOR cell (linear brick ids, x fastest); null = plain-load kernels
+    int32_t *bricks = nullptr;
+    int nBricks = 0, bricksX = 0, bricksY = 0;
     // V-cycle grids (level 0 uses caller grids for x and b)
     double *x = nullptr, *xAlt = nullptr, *b = nullptr, *r = nullptr;
     int shift[3] = {0, 0, 0};    // coarse storage = (this level's storage >> 1) + shift   (to level+1)
@@ -109,6 +113,8 @@ struct IoGroup
 {
     int z0, z1, x0, x1, y0, y1;
 };
+
+struct TmaMap { alignas(64) unsigned char bytes[128]; };  // an opaque CUtensorMap (encoded in gmg_b200.cu, consumed by k_stencil_tma)
 
 struct ProfileRec
 {
@@ -209,6 +215,7 @@ struct gmg_solver
 	std::vector<gmg::ProfileRec> recs; // profiled variant: per-launch event pairs living inside the graph
     };
     std::map<std::tuple<int, const void *, const void *, int>, GraphEntry> graphs;
+    std::map<std::pair<int, const double *>, gmg::TmaMap> tensorMaps;  // (level, grid) -> tensor map of the TMA stencil kernels
     bool useGraphs = true;
     bool zeroAware = true;        // zero-aware down-stroke (no zero fill, SM_JACOBI_ZERO); GMG_ZERO_AWARE=0 at creation restores the fill
 };

@@ -153,6 +153,7 @@ struct StencilArgs
     int nBoundary;
     const int32_t *bandIdx;
     const double *bcoef;
+    const unsigned short *wcode;  // coefficient codes of the BOUNDARY cells (k_band_coef)
     // fused dot(in, A in) for apply
     double *partials;
     unsigned *ticket;
@@ -168,6 +169,41 @@ __device__ __forceinline__ double stencilFinish(double lap, double centre, doubl
     double r = rhs - lap;                                 // Ops.h:357-361
     r /= diag;
     return centre + (2.0 / 3.0) * r;
+}
+
+// BOUNDARY-labelled cell k of the level's record list (Ops.h:208-255): coefficient record in the prologue, values after the wait
+template <int MODE, bool DOT>
+__device__ __forceinline__ double stencilBoundary(const StencilArgs &a, int k)
+{
+    double acc = 0.0;
+    const int64_t i = k < a.nBoundary ? int64_t(a.bandIdx[k]) : 0;
+    const int z = int(unsigned(i) / unsigned(a.plane));  // a level's box holds fewer than 2^31 cells: 32-bit division
+    const bool live = k < a.nBoundary && z >= a.zlo && z < a.zhi;
+    // prologue: the code word, the diagonal and the (rare) fractional coefficients
+    const unsigned code = live ? a.wcode[k] : 0u;
+    const double diag = live ? a.bcoef[int64_t(6) * a.nBoundary + k] : 1.0;
+    double cn[6];
+#pragma unroll
+    for (int n = 0; n < 6; ++n)
+    {
+	const unsigned c = (code >> (2 * n)) & 3u;
+	cn[n] = c == 2u ? a.bcoef[int64_t(n) * a.nBoundary + k] : double(c);  // 0, exactly 1, or the fractional coefficient
+    }
+    pdlWait();
+    if (live)
+    {
+	const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
+	const double centre = a.in[i];
+	double lap = 0.0;
+#pragma unroll
+	for (int n = 0; n < 6; ++n)
+	    if (cn[n] != 0.0) lap -= cn[n] * a.in[i + stride[n]];
+	lap += diag * centre;
+	const double rhs = (MODE != SM_APPLY) ? a.b[i] : 0.0;
+	a.out[i] = stencilFinish<MODE>(lap, centre, rhs, diag);
+	if (DOT && z >= a.dotLo && z < a.dotHi) acc += centre * lap;
+    }
+    return acc;
 }
 
 // vb = virtual CTA index (blockIdx.x of the stand-alone kernel), tid = thread index inside the BLOCK-wide virtual CTA.
@@ -273,31 +309,7 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 	    if (DOT && z >= a.dotLo && z < a.dotHi) acc += (a0 ? c2.x * lap0 : 0.0) + (a1 ? c2.y * lap1 : 0.0);
 	}
     }
-    else
-    {
-	const int k = (vb - a.nChunks) * BLOCK + tid;
-	const int64_t i = k < a.nBoundary ? int64_t(a.bandIdx[k]) : 0;
-	const int z = int(unsigned(i) / unsigned(a.plane));  // a level's box holds fewer than 2^31 cells: 32-bit division
-	const bool live = k < a.nBoundary && z >= a.zlo && z < a.zhi;
-	double cn[7];
-#pragma unroll
-	for (int n = 0; n < 7; ++n) cn[n] = live ? a.bcoef[int64_t(n) * a.nBoundary + k] : 0.0;
-	pdlWait();
-	if (live)
-	{
-	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
-	    const double centre = a.in[i];
-	    double lap = 0.0;
-#pragma unroll
-	    for (int n = 0; n < 6; ++n)
-		if (cn[n] != 0.0) lap -= cn[n] * a.in[i + stride[n]];
-	    const double diag = cn[6];
-	    lap += diag * centre;
-	    const double rhs = (MODE != SM_APPLY) ? a.b[i] : 0.0;
-	    a.out[i] = stencilFinish<MODE>(lap, centre, rhs, diag);
-	    if (DOT && z >= a.dotLo && z < a.dotHi) acc += centre * lap;
-	}
-    }
+    else acc = stencilBoundary<MODE, DOT>(a, (vb - a.nChunks) * BLOCK + tid);
     return acc;
 }
 
@@ -307,6 +319,154 @@ __global__ void __launch_bounds__(BLOCK) k_stencil(const StencilArgs a)
     pdlLaunch();
     const double acc = stencilBody<MODE, DOT>(a, blockIdx.x, threadIdx.x);
     if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// The same operator with the input staged through shared memory by the Tensor Memory Accelerator (the A/B SURVEY.md
+// section 7 step 7 asks for).  One CTA owns a 64 x 8 x 4 brick of storage cells; ONE elected thread issues a 3D
+// cp.async.bulk.tensor load of the brick plus its halo -- a 68 x 10 x 6 box of `in`, starting two cells left of the brick so
+// that the aligned x-pairs stay 16-byte aligned in shared memory -- and the CTA waits on an mbarrier for the bytes to land.
+// Out-of-range coordinates (the box reaches past the storage box at every edge brick) are zero-filled by the TMA unit, which
+// is exactly the value a vector grid has there.  Every stencil read then comes from shared memory: the seven global loads
+// per thread and plane of k_stencil (five of them re-reading lines a neighbouring thread or plane also reads, through
+// L1/L2) become one bulk copy of each line per brick.  Right-hand side and labels are read once per cell anyway: plain
+// coalesced loads, issued before the wait.  Arithmetic and its order are k_stencil's: bitwise the same result.
+// CTAs [0, nBricks): bricks holding an INTERIOR cell; the rest: the boundary records, exactly as in k_stencil.
+// ------------------------------------------------------------------------------------------------
+constexpr int TB_X = 64, TB_Y = 8, TB_Z = 4;
+constexpr int TB_BOX_X = TB_X + 4, TB_BOX_Y = TB_Y + 2, TB_BOX_Z = TB_Z + 2;
+constexpr unsigned TB_BOX_BYTES = TB_BOX_X * TB_BOX_Y * TB_BOX_Z * sizeof(double);
+
+__device__ __forceinline__ unsigned smemAddr(const void *p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long *bar, unsigned phase)
+{
+    asm volatile(
+	"{\n"
+	".reg .pred p;\n"
+	"WAIT_LOOP:\n"
+	"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	"@p bra WAIT_DONE;\n"
+	"bra WAIT_LOOP;\n"
+	"WAIT_DONE:\n"
+	"}\n" ::"r"(smemAddr(bar)),
+	"r"(phase)
+	: "memory");
+}
+__device__ __forceinline__ void tmaLoad3d(void *dst, const void *tensorMap, int c0, int c1, int c2, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smemAddr(dst)),
+		 "l"(tensorMap), "r"(c0), "r"(c1), "r"(c2), "r"(smemAddr(bar))
+		 : "memory");
+}
+
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(BLOCK) k_stencil_tma(const StencilArgs a, const __grid_constant__ TmaMap tmIn, const int32_t *bricks, int nBricks,
+						      int bricksX, int bricksY, int ny)
+{
+    pdlLaunch();
+    __shared__ alignas(128) double tile[TB_BOX_Z][TB_BOX_Y][TB_BOX_X];
+    __shared__ alignas(8) unsigned long long bar;
+    double acc = 0.0;
+    if (int(blockIdx.x) < nBricks)
+    {
+	const int br = bricks[blockIdx.x];
+	const int bz = br / (bricksX * bricksY), by = (br - bz * bricksX * bricksY) / bricksX, bx = br - (bz * bricksY + by) * bricksX;
+	const int x0 = bx * TB_X, y0 = by * TB_Y, z0 = bz * TB_Z;
+	const int px = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	const int x = x0 + 2 * px, y = y0 + ty;
+	const bool inRow = x < a.pitch && y < ny;
+	const int64_t inPlane = int64_t(y) * a.pitch + x;
+	// prologue: labels of the thread's cells (static)
+	uchar2 lab[TB_Z];
+#pragma unroll
+	for (int dz = 0; dz < TB_Z; ++dz)
+	{
+	    const int z = z0 + dz;
+	    lab[dz] = make_uchar2(L_EXTERIOR, L_EXTERIOR);
+	    if (inRow && z >= a.zlo && z < a.zhi) lab[dz] = *reinterpret_cast<const uchar2 *>(a.labels + int64_t(z) * a.plane + inPlane);
+	}
+	if (threadIdx.x == 0) mbarInit(&bar, 1);
+	__syncthreads();
+	pdlWait();
+	if (threadIdx.x == 0)
+	{
+	    mbarExpectTx(&bar, TB_BOX_BYTES);
+	    // tensor coordinates: x, y, and z + 1 (the tensor starts at the grid's lower guard plane)
+	    tmaLoad3d(&tile[0][0][0], &tmIn, x0 - 2, y0 - 1, z0 - 1 + 1, &bar);
+	}
+	double2 rhs[TB_Z];
+#pragma unroll
+	for (int dz = 0; dz < TB_Z; ++dz)
+	{
+	    rhs[dz] = make_double2(0.0, 0.0);
+	    const bool any = (lab[dz].x == L_INTERIOR) | (lab[dz].y == L_INTERIOR);
+	    if (MODE != SM_APPLY && any) rhs[dz] = ld2(a.b + int64_t(z0 + dz) * a.plane + inPlane);
+	}
+	mbarWait(&bar, 0);
+	const int cx = 2 * px + 2, cy = ty + 1;
+	double2 zm = *reinterpret_cast<const double2 *>(&tile[0][cy][cx]);
+	double2 c2 = *reinterpret_cast<const double2 *>(&tile[1][cy][cx]);
+#pragma unroll
+	for (int dz = 0; dz < TB_Z; ++dz)
+	{
+	    const int z = z0 + dz;
+	    const double2 zp = *reinterpret_cast<const double2 *>(&tile[dz + 2][cy][cx]);
+	    const uchar2 l = lab[dz];
+	    const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
+	    if (a0 | a1)
+	    {
+		const int64_t i = int64_t(z) * a.plane + inPlane;
+		const double xm = tile[dz + 1][cy][cx - 1], xp = tile[dz + 1][cy][cx + 2];
+		const double2 ym = *reinterpret_cast<const double2 *>(&tile[dz + 1][cy - 1][cx]);
+		const double2 yp = *reinterpret_cast<const double2 *>(&tile[dz + 1][cy + 1][cx]);
+		double lap0 = -xm;
+		lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
+		lap0 += 6.0 * c2.x;
+		double lap1 = -c2.x;
+		lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
+		lap1 += 6.0 * c2.y;
+		const double o0 = stencilFinish<MODE>(lap0, c2.x, rhs[dz].x, 6.0);
+		const double o1 = stencilFinish<MODE>(lap1, c2.y, rhs[dz].y, 6.0);
+		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
+		else if (a0) a.out[i] = o0;
+		else a.out[i + 1] = o1;
+		if (DOT && z >= a.dotLo && z < a.dotHi) acc += (a0 ? c2.x * lap0 : 0.0) + (a1 ? c2.y * lap1 : 0.0);
+	    }
+	    zm = c2;
+	    c2 = zp;
+	}
+    }
+    else acc = stencilBoundary<MODE, DOT>(a, (int(blockIdx.x) - nBricks) * BLOCK + int(threadIdx.x));
+    if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
+}
+
+// brick flags: 1 when the 64 x 8 x 4 brick holds an INTERIOR cell
+__global__ void __launch_bounds__(BLOCK) k_brick_flags(uint8_t *flags, const uint8_t *labels, int bricksX, int bricksY, int pitch, int64_t plane, int ny, int nz)
+{
+    const int br = blockIdx.x;
+    const int bz = br / (bricksX * bricksY), by = (br - bz * bricksX * bricksY) / bricksX, bx = br - (bz * bricksY + by) * bricksX;
+    const int x = bx * TB_X + 2 * (threadIdx.x & 31), y = by * TB_Y + (threadIdx.x >> 5);
+    int any = 0;
+    if (x < pitch && y < ny)
+	for (int dz = 0; dz < TB_Z; ++dz)
+	{
+	    const int z = bz * TB_Z + dz;
+	    if (z >= nz) break;
+	    const uchar2 l = *reinterpret_cast<const uchar2 *>(labels + int64_t(z) * plane + int64_t(y) * pitch + x);
+	    any |= (l.x == L_INTERIOR) | (l.y == L_INTERIOR);
+	}
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) flags[br] = uint8_t(any);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -324,6 +484,7 @@ struct BandArgs
     const int32_t *bandRef;  // [6][nBand] neighbour reference: >= 0 position in the band; BAND_SKIP: coefficient 0 (not active);
 			     // <= -2: an active cell outside the band (frozen during the band sweeps) at grid index -2 - ref
     const double *bcoef;
+    const unsigned short *wcode;  // coefficient codes of the BOUNDARY cells (k_band_coef)
     const double *vin;
     double *vout;
     double *bandB;
@@ -346,17 +507,20 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
     int64_t gi[BAND_PER_THREAD];
     int ref[BAND_PER_THREAD][6];
     double diag[BAND_PER_THREAD];
+    unsigned code[BAND_PER_THREAD];
 #pragma unroll
     for (int c = 0; c < BAND_PER_THREAD; ++c)
     {
 	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
 	gi[c] = 0;
 	diag[c] = 6.0;
+	code[c] = 0x555u;  // every coefficient 1
 #pragma unroll
 	for (int n = 0; n < 6; ++n) ref[c][n] = BAND_SKIP;
 	if (k >= a.nBand) continue;
 	if (!FROM_COMPACT || TO_GRID || FIRST) gi[c] = a.bandIdx[k];
 	if (k < a.nBoundary) diag[c] = a.bcoef[int64_t(6) * a.nBoundary + k];
+	if (HAS_W && !ZERO && k < a.nBoundary) code[c] = a.wcode[k];
 	if (!ZERO)
 	{
 #pragma unroll
@@ -396,8 +560,9 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 		else u = a.x[i + stride[n]];
 		if (weighted)
 		{
-		    const double cn = a.bcoef[int64_t(n) * a.nBoundary + k];  // independent of the value gathers: not on the dependent chain
-		    if (cn != 0.0) lap -= cn * u;
+		    const unsigned cc = (code[c] >> (2 * n)) & 3u;
+		    if (cc == 1u) lap -= u;  // 1 * u, bit for bit
+		    else if (cc == 2u) lap -= a.bcoef[int64_t(n) * a.nBoundary + k] * u;  // fractional: rare
 		}
 		else lap -= u;
 	    }
@@ -1316,7 +1481,12 @@ __global__ void __launch_bounds__(BLOCK) k_band_ref(int32_t *bandRef, const int3
 }
 // coefficient record of a BOUNDARY cell (Ops.h:208-255): c_n = 1 (INTERIOR nbr), w (BOUNDARY nbr), 0 otherwise;
 // diag = sum of 1 (INTERIOR), w (BOUNDARY), w (DIRICHLET).  w == nullptr (coarse levels) means weight 1.
-__global__ void __launch_bounds__(BLOCK) k_band_coef(double *bcoef, const int32_t *bandIdx, int nBoundary, const uint8_t *labels,
+// wcode[k]: two bits per neighbour n (bits 2n, 2n+1): 0 = coefficient 0 (skip), 1 = coefficient exactly 1 (no multiply, no load),
+// 2 = fractional (load it).  Most BOUNDARY cells have no fractional coefficient at all -- a ghost-fluid weight sits on a
+// liquid/air face, whose neighbour is DIRICHLET and only enters the diagonal -- so the sweeps read 2 bytes instead of 48.
+__device__ __forceinline__ unsigned coefCode(double cn) { return cn == 0.0 ? 0u : (cn == 1.0 ? 1u : 2u); }
+
+__global__ void __launch_bounds__(BLOCK) k_band_coef(double *bcoef, unsigned short *wcode, const int32_t *bandIdx, int nBoundary, const uint8_t *labels,
 						    const double *w0, const double *w1, const double *w2, int pitch, int64_t plane)
 {
     const int k = blockIdx.x * BLOCK + threadIdx.x;
@@ -1325,6 +1495,7 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef(double *bcoef, const int32_
     const int64_t stride[3] = {1, pitch, plane};
     const double *w[3] = {w0, w1, w2};
     double diag = 0.0, wsum = 0.0;
+    unsigned code = 0;
 #pragma unroll
     for (int n = 0; n < 6; ++n)
     {
@@ -1338,8 +1509,10 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef(double *bcoef, const int32_
 	else if (nl == L_BOUNDARY) { cn = wt; diag += wt; }
 	else if (nl == L_DIRICHLET) { diag += wt; }
 	wsum += wt;
+	code |= coefCode(cn) << (2 * n);
 	bcoef[int64_t(n) * nBoundary + k] = cn;
     }
+    wcode[k] = (unsigned short)code;
     bcoef[int64_t(6) * nBoundary + k] = diag;
     // row 7: the plain sum of the six face weights -- the diagonal the reference's diagonal preconditioner inverts
     // (GFS.cpp:538-548); without weight grids there is no such sum and the operator's diagonal stands in
@@ -1348,7 +1521,7 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef(double *bcoef, const int32_
 
 // The same records from SPARSE face weights: wf[n][k] = weight of face n (-x,+x,-y,+y,-z,+z) of BOUNDARY cell k, gathered on the
 // host from the caller's weight grids (only BOUNDARY cells ever look at a face weight, so the full grids never travel).
-__global__ void __launch_bounds__(BLOCK) k_band_coef_sparse(double *bcoef, const int32_t *bandIdx, int nBoundary, const uint8_t *labels,
+__global__ void __launch_bounds__(BLOCK) k_band_coef_sparse(double *bcoef, unsigned short *wcode, const int32_t *bandIdx, int nBoundary, const uint8_t *labels,
 								   const double *wf, int pitch, int64_t plane)
 {
     const int k = blockIdx.x * BLOCK + threadIdx.x;
@@ -1356,6 +1529,7 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef_sparse(double *bcoef, const
     const int64_t i = bandIdx[k];
     const int64_t stride[3] = {1, pitch, plane};
     double diag = 0.0, wsum = 0.0;
+    unsigned code = 0;
 #pragma unroll
     for (int n = 0; n < 6; ++n)
     {
@@ -1368,8 +1542,10 @@ __global__ void __launch_bounds__(BLOCK) k_band_coef_sparse(double *bcoef, const
 	else if (nl == L_BOUNDARY) { cn = wt; diag += wt; }
 	else if (nl == L_DIRICHLET) { diag += wt; }
 	wsum += wt;
+	code |= coefCode(cn) << (2 * n);
 	bcoef[int64_t(n) * nBoundary + k] = cn;
     }
+    wcode[k] = (unsigned short)code;
     bcoef[int64_t(6) * nBoundary + k] = diag;
     bcoef[int64_t(7) * nBoundary + k] = wsum;  // GFS.cpp:538-548
 }

@@ -387,16 +387,18 @@ def test_pinned_host_buffers_move_only_the_active_rectangles(gpu_ctx):
 
 def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
     """The coarse levels have three implementations -- one kernel per operator, the one-CTA shared-memory cycle, the
-    thread-block-cluster cycle with distributed shared memory -- and the down-stroke two (zero fill + plain Jacobi, or the
-    zero-aware sweep).  Per cell they run the same arithmetic in the same order: a V-cycle must agree BITWISE between them."""
+    thread-block-cluster cycle with distributed shared memory --, the down-stroke two (zero fill + plain Jacobi, or the
+    zero-aware sweep) and the full-grid stencil two (plain loads, or TMA-staged bricks).  Per cell they run the same
+    arithmetic in the same order: a V-cycle must agree BITWISE between them."""
     bl, bw, dx = D.flipsplash_domain(64)
     labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
     rb = D.random_rhs(labels, dx, seed=21)
     x0 = D.random_active(labels, 22, scale=dx * dx)
     results = {}
     for name, env in [("cluster", {}), ("compact", {"GMG_CLUSTER_CYCLE": "0"}), ("kernels", {"GMG_COARSE_FUSED": "0"}),
-                      ("zero_fill", {"GMG_ZERO_AWARE": "0"}), ("cluster8", {"GMG_CLUSTER_SIZE": "8"}), ("first2", {"GMG_FUSED_FIRST": "2"})]:
-        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST"):
+                      ("zero_fill", {"GMG_ZERO_AWARE": "0"}), ("cluster8", {"GMG_CLUSTER_SIZE": "8"}), ("first2", {"GMG_FUSED_FIRST": "2"}),
+                      ("tma", {"GMG_TMA": "1", "GMG_TMA_MIN_CELLS": "100"})]:
+        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
