@@ -253,6 +253,8 @@ extern "C" int gmg_ctx_create(int device, void *stream, gmg_ctx **out)
 		else cudaGetLastError();
 	    }
 	}
+	GMG_CUDA(cudaMalloc(&ctx->groupBarrier, sizeof(GroupBarrier)));
+	GMG_CUDA(cudaMemset(ctx->groupBarrier, 0, sizeof(GroupBarrier)));
 	GMG_CUDA(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
 	GMG_CUDA(cudaMemset(ctx->ticket, 0, sizeof(unsigned)));
 	GMG_CUDA(cudaMalloc(&ctx->scalars, sizeof(Scalars)));
@@ -293,6 +295,7 @@ extern "C" int gmg_ctx_destroy(gmg_ctx *ctx)
     cudaFree(ctx->partials);
     for (void *p : ctx->retired) cudaFree(p);
     cudaFree(ctx->ticket);
+    cudaFree(ctx->groupBarrier);
     cudaFree(ctx->scalars);
     cudaFreeHost(ctx->hostScalars);
     for (int i = 0; i < 2; ++i)
@@ -1243,6 +1246,24 @@ static int buildBricks(gmg_ctx *ctx, Level &L)
     GMG_CUDA(devFree(flags));
     return GMG_OK;
 }
+// coarse bricks of level C (32 x 4 x 2 coarse cells holding an active cell) for the TMA restriction INTO it
+static int buildCoarseBricks(gmg_ctx *ctx, Level &C)
+{
+    const Geom &g = C.g;
+    C.cbricksX = int(divUp(g.n[0], RB_X));
+    C.cbricksY = int(divUp(g.n[1], RB_Y));
+    const int bz = int(divUp(g.n[2], RB_Z));
+    const int64_t nb = int64_t(C.cbricksX) * C.cbricksY * bz;
+    uint8_t *flags = nullptr;
+    GMG_CUDA(devMalloc(&flags, size_t(nb)));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_cbrick_flags<<<unsigned(nb), BLOCK, 0, ctx->stream>>>(flags, C.labels, C.cbricksX, C.cbricksY, g.pitch, g.plane, g.n[1], g.n[2]);
+    }
+    GMG_TRY(selectFlagged(ctx, flags, nb, &C.cbricks, &C.nCBricks));
+    GMG_CUDA(devFree(flags));
+    return GMG_OK;
+}
 
 // 3D tensor map over a vector grid INCLUDING its two guard planes (the tensor's plane 0 is the lower guard plane), box =
 // brick + halo.  Cached per grid pointer: the kernels take it by value (__grid_constant__), so a captured graph keeps its own copy.
@@ -1364,7 +1385,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 static void freeLevel(Level &L)
 {
     devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab); devFree(L.flagsAlloc);
-    devFree(L.chunksInterior); devFree(L.chunksActive); devFree(L.bricks);
+    devFree(L.chunksInterior); devFree(L.chunksActive); devFree(L.bricks); devFree(L.cbricks);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
     L = Level();
@@ -2171,6 +2192,7 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     if (const char *e = getenv("GMG_NO_GRAPHS")) s->useGraphs = !(e[0] == '1');
     if (const char *e = getenv("GMG_PRINT_STATS")) s->opt.print_stats = (e[0] == '1');
     if (const char *e = getenv("GMG_ZERO_AWARE")) s->zeroAware = !(e[0] == '0');
+    if (const char *e = getenv("GMG_BAND_GROUPS")) s->bandGroups = !(e[0] == '0');
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel && ctx->world > 1)
@@ -2283,6 +2305,7 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
 	if (level == 0) lap("level 0 coefficient records");
 	if ((st = buildChunks(ctx, L)) != GMG_OK) return fail(st);
 	if ((st = buildBricks(ctx, L)) != GMG_OK) return fail(st);
+	if (level > 0 && s->lv[level - 1].bricks && (st = buildCoarseBricks(ctx, L)) != GMG_OK) return fail(st);
 	if (s->opt.use_gauss_seidel && (st = buildGsTiles(ctx, L)) != GMG_OK) return fail(st);
 	maxGrid = std::max(maxGrid, L.nChunksActive + int(divUp(L.nBoundary, BLOCK)) + 1);
 	if ((st = allocGrid(&L.xAlt, L.g)) != GMG_OK) return fail(st);
@@ -2524,6 +2547,31 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
     const double bytes = double(L.nBand) * 29.0;
     const bool hw = L.hasWeights;
     double *cur = L.bandV0, *nxt = L.bandV1;
+    if (sweeps >= 2 && s->bandGroups && s->ctx->groupBarrier)
+    {
+	// the whole group in one co-resident launch with grid barriers between the sweeps (k_band_group)
+	gmg_ctx *ctx = s->ctx;
+	if (ctx->bandGroupCtas[0] == 0)
+	{
+	    int per = 0;
+	    GMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_band_group<false, false>, BLOCK, 0));
+	    ctx->bandGroupCtas[0] = std::max(1, per) * ctx->smCount;
+	    GMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_band_group<true, false>, BLOCK, 0));
+	    ctx->bandGroupCtas[1] = std::max(1, per) * ctx->smCount;
+	}
+	const unsigned cap = unsigned(ctx->bandGroupCtas[hw && !zeroGrid ? 1 : 0]);
+	const unsigned g = std::min(grid, cap);
+	a.vin = nxt;   // (the kernel takes the two compact arrays through vin / vout)
+	a.vout = cur;
+	GroupBarrier *bar = static_cast<GroupBarrier *>(ctx->groupBarrier);
+	GMG_LAUNCH(ctx, KC_BAND, bytes * sweeps);
+	if (zeroGrid && hw) GMG_CUDA(launchK((k_band_group<true, true>), g, BLOCK, 0, st, a, sweeps, int(grid), bar));
+	else if (zeroGrid) GMG_CUDA(launchK((k_band_group<false, true>), g, BLOCK, 0, st, a, sweeps, int(grid), bar));
+	else if (hw) GMG_CUDA(launchK((k_band_group<true, false>), g, BLOCK, 0, st, a, sweeps, int(grid), bar));
+	else GMG_CUDA(launchK((k_band_group<false, false>), g, BLOCK, 0, st, a, sweeps, int(grid), bar));
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     // sweep 1: grid -> compact
     a.vin = nullptr;
     a.vout = cur;
@@ -2595,6 +2643,15 @@ static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const do
     a.zlo = zr.lo;
     a.zhi = zr.hi;
     GMG_LAUNCH(s->ctx, KC_RESTRICT, double(s->lv[fineLevel].nActive) * 8.0 + double(C.nActive) * 9.0);
+    if (C.cbricks)
+    {
+	// TMA-staged variant: one CTA per 32 x 4 x 2 brick of coarse cells
+	TmaMap tm;
+	GMG_TRY(tensorMapOf(s, fineLevel, fine, &tm));
+	if (C.nCBricks > 0) GMG_CUDA(launchK(k_restrict_tma, unsigned(C.nCBricks), unsigned(BLOCK), size_t(0), s->ctx->stream, a, tm, C.cbricks, C.cbricksX, C.cbricksY));
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     GMG_CUDA(launchK(k_restrict, unsigned(C.nChunksActive * RESTRICT_SPLIT), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
@@ -2679,9 +2736,13 @@ static int buildClusterCycle(gmg_solver *s)
 	if (ctx->clusterSize < 0) return GMG_OK;
     }
     const int CL = ctx->clusterSize;
-    // cells per CTA block: an equal share, but never less than one cell per thread -- a level of a thousand cells lives in ONE
-    // CTA and smooths entirely out of its own shared memory (measured: spread thin over 16 CTAs every neighbour is a remote load)
-    auto perOf = [&](int64_t n) { return int((std::max<int64_t>(divUp(std::max<int64_t>(n, 1), CL), std::min<int64_t>(std::max<int64_t>(n, 1), CLUSTER_THREADS)) + 1) & ~int64_t(1)); };
+    // cells per CTA block: a level of at most CLUSTER_SOLO_MAX cells lives in CTA 0 alone (its steps end on __syncthreads, not on
+    // the cluster barrier); larger levels get an equal share per CTA, but never less than one cell per thread
+    auto perOf = [&](int64_t n) {
+	n = std::max<int64_t>(n, 1);
+	const int64_t per = n <= CLUSTER_SOLO_MAX ? n : std::max<int64_t>(divUp(n, CL), std::min<int64_t>(n, CLUSTER_THREADS));
+	return int((per + 1) & ~int64_t(1));
+    };
     // per cell of a block: two solution arrays + rhs (24 bytes) and the smoother tables (6 x 16-bit codes, diagonal, flags: 14 bytes)
     auto smemOf = [&](int first) {
 	size_t bytes = 0;
@@ -2692,7 +2753,8 @@ static int buildClusterCycle(gmg_solver *s)
     // cluster's shared memory with at most 8 cells per thread
     int first = -1;
     for (int l = std::max(1, s->shardLevels); l < s->levels; ++l)
-	if (s->levels - l <= CLUSTER_MAX_LEVELS && perOf(s->lv[l].nActive) <= CLUSTER_MAX_PER && smemOf(l) + 1024 <= size_t(smemMax))
+	if (s->levels - l <= CLUSTER_MAX_LEVELS && (s->lv[l].nActive <= CLUSTER_SOLO_MAX || perOf(s->lv[l].nActive) <= CLUSTER_MAX_PER) &&
+	    smemOf(l) + 1024 <= size_t(smemMax))
 	{
 	    first = l;
 	    break;
@@ -2811,6 +2873,8 @@ static int buildClusterCycle(gmg_solver *s)
     GMG_CUDA(cudaGetLastError());
     for (int q = 0; q < nl; ++q) GMG_CUDA(devFree(pos[q]));
     c->nLevels = nl;
+    c->soloFirst = nl;
+    for (int q = nl - 1; q >= 0 && s->lv[first + q].nActive <= CLUSTER_SOLO_MAX; --q) c->soloFirst = q;
     c->sweeps = s->opt.boundary_iterations;
     c->scratchOff = smemOff;
     {

@@ -25,7 +25,7 @@
 
 namespace gmg
 {
-constexpr int CLUSTER_THREADS = 1024;
+constexpr int CLUSTER_THREADS = 512;
 constexpr int CLUSTER_MAX_LEVELS = 10;
 constexpr unsigned CLUSTER_NONE = 0xffffffffu;
 constexpr int CLUSTER_OWNER_SHIFT = 20;  // packed reference = (owner CTA << 20) | index in the owner's block
@@ -35,7 +35,8 @@ constexpr unsigned short CODE_SAME = 0u << 13, CODE_PREV = 1u << 13, CODE_NEXT =
 // Largest block the cycle takes: two cells per thread.  Measured (profiles/r02_cluster_cycle.md): the 67k-cell level 2 of the
 // 256^3 problem, 4.2k cells per CTA, costs 6 us per sweep on 16 SMs (fp64 divisions and shared-memory traffic of 4k cells on
 // one SM) against 4.4 us as a kernel of its own over 148 SMs -- the cluster pays only below ~30k cells.
-constexpr int CLUSTER_MAX_PER = 2048;
+constexpr int CLUSTER_MAX_PER = 1024;
+constexpr int CLUSTER_SOLO_MAX = 2048;  // a level of at most this many cells lives in CTA 0 alone (4 cells per thread)
 
 struct ClusterLevel
 {
@@ -55,6 +56,8 @@ struct ClusterArgs
 {
     ClusterLevel lv[CLUSTER_MAX_LEVELS];  // lv[0] is the finest level of the cycle
     int nLevels;
+    int soloFirst;            // levels [soloFirst, nLevels) live entirely in CTA 0 and step on __syncthreads (nLevels = none)
+    int soloCur[CLUSTER_MAX_LEVELS];  // which ping-pong array holds a solo level's solution after its sub-cycle (known from the sweep count)
     int sweeps;
     int scratchOff;           // offset (doubles) of the direct solve's gathered right-hand side in CTA 0
     const int32_t *cellTop;   // [lv[0].n] storage index of lv[0]'s cells in its grid
@@ -133,6 +136,9 @@ __device__ __forceinline__ void clusterSweep(cg::cluster_group &cl, const Cluste
     cl.sync();
 }
 
+// Levels [soloFirst, nLevels) are small enough (<= CLUSTER_SOLO_MAX cells) to live entirely in CTA 0: there a step ends on
+// __syncthreads (0.08 us) instead of the cluster barrier (0.5 us with 16 x 512 threads, scripts/cluster_probe.cu), every access
+// is a plain shared-memory access, and the other CTAs wait at ONE cluster barrier for the whole sub-cycle.
 __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const ClusterArgs c)
 {
     pdlLaunch();
@@ -151,8 +157,13 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
     int cur[CLUSTER_MAX_LEVELS];
     auto X = [&](int q, int which) { return sm + c.lv[q].off + which * c.lv[q].per; };
     auto B = [&](int q) { return sm + c.lv[q].off + 2 * c.lv[q].per; };
+    // end of a step: the cluster barrier, or the CTA barrier inside the solo sub-cycle
+    auto stepSync = [&](bool solo) {
+	if (solo) __syncthreads();
+	else cl.sync();
+    };
     // band sweeps, one interior sweep, band sweeps (MG.cpp:445-513 and its per-level copies)
-    auto smooth = [&](int q) {
+    auto smooth = [&](int q, bool solo) {
 	const ClusterLevel &L = c.lv[q];
 	int first, count;
 	blockOf(q, first, count);
@@ -160,36 +171,12 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 	for (int s = 0; s < 2 * c.sweeps + 1; ++s)
 	{
 	    clusterSweep(cl, L, T, X(q, cur[q]), X(q, cur[q] ^ 1), B(q), rank, first, count, s != c.sweeps);
+	    stepSync(solo);
 	    cur[q] ^= 1;
 	}
     };
-    // prologue: this CTA's blocks of the (static) smoother tables go to shared memory while the restriction above the cycle's
-    // first level is still running
-    for (int q = 0; q < nl; ++q)
-    {
-	const ClusterLevel &L = c.lv[q];
-	int first, count;
-	blockOf(q, first, count);
-	unsigned short *tn = reinterpret_cast<unsigned short *>(smBytes + L.tabOff);
-	uint8_t *td = smBytes + L.tabOff + size_t(12) * L.per, *tf = td + L.per;
-	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
-	{
-#pragma unroll
-	    for (int d = 0; d < 6; ++d) tn[d * L.per + j] = __ldg(L.nbr16 + size_t(d) * L.n + first + j);
-	    td[j] = __ldg(L.diag + first + j);
-	    tf[j] = __ldg(L.flags + first + j);
-	}
-    }
-    pdlWait();
-    {
-	int first, count;
-	blockOf(0, first, count);
-	double *b = B(0);
-	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS) b[j] = c.bTop[__ldg(c.cellTop + first + j)];
-    }
-    // ---- down-stroke (MG.cpp:557-667): x = 0, smooth, residual, restrict
-    for (int q = 0; q + 1 < nl; ++q)
-    {
+    // down-stroke of level q (MG.cpp:557-667): x = 0, smooth, residual, restrict into level q + 1
+    auto downLevel = [&](int q, bool solo) {
 	const ClusterLevel &L = c.lv[q];
 	const ClusterLevel &C = c.lv[q + 1];
 	int first, count;
@@ -199,8 +186,8 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 	    double *x = X(q, 0);
 	    for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS) x[j] = 0.0;
 	}
-	cl.sync();
-	smooth(q);
+	stepSync(solo);
+	smooth(q, solo);
 	{
 	    // residual into the other solution array (the current one is kept for the up-stroke)
 	    double *x = X(q, cur[q]), *t = X(q, cur[q] ^ 1);
@@ -213,7 +200,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 		t[j] = b[j] + (-1.0) * lap;  // Ops.h:731
 	    }
 	}
-	cl.sync();
+	stepSync(solo);
 	{
 	    int cfirst, ccount;
 	    blockOf(q + 1, cfirst, ccount);
@@ -243,10 +230,10 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 		bc[j] = v;
 	    }
 	}
-	cl.sync();
-    }
-    // ---- direct solve on the coarsest level (MG.cpp:669-692): x = A^-1 b, one warp per row as in k_coarse_solve, in CTA 0
-    {
+	stepSync(solo);
+    };
+    // direct solve on the coarsest level (MG.cpp:669-692): x = A^-1 b, one warp per row as in k_coarse_solve, in CTA 0
+    auto solveCoarsest = [&](bool solo) {
 	const int q = nl - 1;
 	cur[q] = 0;
 	double *x = X(q, 0);
@@ -266,15 +253,16 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 		if (lane == 0)
 		{
 		    const unsigned ref = __ldg(c.solveRef + row);
-		    *cl.map_shared_rank(x + (ref & ((1u << CLUSTER_OWNER_SHIFT) - 1u)), ref >> CLUSTER_OWNER_SHIFT) = acc;
+		    const unsigned owner = ref >> CLUSTER_OWNER_SHIFT, idx = ref & ((1u << CLUSTER_OWNER_SHIFT) - 1u);
+		    if (owner == 0u) x[idx] = acc;
+		    else *cl.map_shared_rank(x + idx, owner) = acc;
 		}
 	    }
 	}
-	cl.sync();
-    }
-    // ---- up-stroke (MG.cpp:695-784): x += 4 trilerp(x_coarse), smooth
-    for (int q = nl - 2; q >= 0; --q)
-    {
+	stepSync(solo);
+    };
+    // up-stroke of level q (MG.cpp:695-784): x += 4 trilerp(x of level q + 1), smooth
+    auto upLevel = [&](int q, bool solo) {
 	const ClusterLevel &L = c.lv[q];
 	int first, count;
 	blockOf(q, first, count);
@@ -297,9 +285,54 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
 				     lerpRef(lerpRef(v[4], v[5], wx), lerpRef(v[6], v[7], wx), wy), wz);
 	    x[j] = x[j] + 4. * e;
 	}
-	cl.sync();
-	smooth(q);
+	stepSync(solo);
+	smooth(q, solo);
+    };
+
+    // prologue: this CTA's blocks of the (static) smoother tables go to shared memory while the restriction above the cycle's
+    // first level is still running
+    for (int q = 0; q < nl; ++q)
+    {
+	const ClusterLevel &L = c.lv[q];
+	int first, count;
+	blockOf(q, first, count);
+	unsigned short *tn = reinterpret_cast<unsigned short *>(smBytes + L.tabOff);
+	uint8_t *td = smBytes + L.tabOff + size_t(12) * L.per, *tf = td + L.per;
+	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
+	{
+#pragma unroll
+	    for (int d = 0; d < 6; ++d) tn[d * L.per + j] = __ldg(L.nbr16 + size_t(d) * L.n + first + j);
+	    td[j] = __ldg(L.diag + first + j);
+	    tf[j] = __ldg(L.flags + first + j);
+	}
     }
+    pdlWait();
+    {
+	int first, count;
+	blockOf(0, first, count);
+	double *b = B(0);
+	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS) b[j] = c.bTop[__ldg(c.cellTop + first + j)];
+    }
+    const int soloFirst = c.soloFirst;  // levels [soloFirst, nl) live in CTA 0 alone (nl = none)
+    // ---- cluster-wide down-stroke; the last restriction lands in CTA 0's block of the first solo level
+    for (int q = 0; q < min(soloFirst, nl - 1); ++q) downLevel(q, false);
+    if (soloFirst < nl)
+    {
+	// ---- the solo sub-cycle in CTA 0; everybody else waits at the barrier below
+	if (soloFirst == 0) cl.sync();  // (the tables and the top rhs written above are CTA-local, but keep the cluster in step)
+	if (rank == 0)
+	{
+	    for (int q = soloFirst; q + 1 < nl; ++q) downLevel(q, true);
+	    solveCoarsest(true);
+	    for (int q = nl - 2; q >= soloFirst; --q) upLevel(q, true);
+	}
+	else
+	    for (int q = soloFirst; q < nl; ++q) cur[q] = c.soloCur[q];  // which array holds a solo level's result: fixed by the sweep count
+	cl.sync();
+    }
+    else solveCoarsest(false);
+    // ---- cluster-wide up-stroke
+    for (int q = min(soloFirst, nl - 1) - 1; q >= 0; --q) upLevel(q, false);
     {
 	int first, count;
 	blockOf(0, first, count);

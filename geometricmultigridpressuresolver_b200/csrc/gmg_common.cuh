@@ -97,6 +97,8 @@ struct Level
     // TMA path (k_stencil_tma): 64 x 8 x 4 bricks holding an INTERIOR cell (linear brick ids, x fastest); null = plain-load kernels
     int32_t *bricks = nullptr;
     int nBricks = 0, bricksX = 0, bricksY = 0;
+    int32_t *cbricks = nullptr;  // 32 x 4 x 2 bricks of THIS level's cells holding an active cell: TMA restriction into this level (k_restrict_tma)
+    int nCBricks = 0, cbricksX = 0, cbricksY = 0;
     // V-cycle grids (level 0 uses caller grids for x and b)
     double *x = nullptr, *xAlt = nullptr, *b = nullptr, *r = nullptr;
     int shift[3] = {0, 0, 0};    // coarse storage = (this level's storage >> 1) + shift   (to level+1)
@@ -163,6 +165,8 @@ struct gmg_ctx
     double *partials = nullptr;   // [maxPartials]
     std::vector<void *> retired;  // outgrown scratch buffers that cached graphs of live solvers may still reference
     unsigned *ticket = nullptr;
+    void *groupBarrier = nullptr;  // gmg::GroupBarrier of the persistent band sweep groups (k_band_group)
+    int bandGroupCtas[2] = {0, 0}; // co-resident CTAs of k_band_group<unweighted / weighted> on this device
     double *scalars = nullptr;    // device scalars (see Scalars)
     double *hostScalars = nullptr; // pinned mirror
     int maxPartials = 0;
@@ -217,6 +221,7 @@ struct gmg_solver
     std::map<std::tuple<int, const void *, const void *, int>, GraphEntry> graphs;
     std::map<std::pair<int, const double *>, gmg::TmaMap> tensorMaps;  // (level, grid) -> tensor map of the TMA stencil kernels
     bool useGraphs = true;
+    bool bandGroups = true;       // a group of band sweeps as ONE co-resident launch with grid barriers (GMG_BAND_GROUPS=0: a launch per sweep)
     bool zeroAware = true;        // zero-aware down-stroke (no zero fill, SM_JACOBI_ZERO); GMG_ZERO_AWARE=0 at creation restores the fill
 };
 

@@ -233,6 +233,70 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 	    }
 	}
 	pdlWait();
+	if (MODE == SM_JACOBI_ZERO)
+	{
+	    // phase 1, every cell: x is zero in the whole neighbourhood, lap = +0.0, and centre + (2/3)((b - 0) / 6) = (2/3)(b / 6);
+	    // a pure stream of b in, x out, the four planes' loads in flight together
+	    int near = 0;
+#pragma unroll
+	    for (int dz = 0; dz < CHUNK_Z; ++dz)
+	    {
+		const bool a0 = (lab[dz].x == L_INTERIOR), a1 = (lab[dz].y == L_INTERIOR);
+		if (!(a0 | a1)) continue;
+		const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
+		const double2 rhs = ld2(a.b + i);
+		const double o0 = (2.0 / 3.0) * (rhs.x / 6.0), o1 = (2.0 / 3.0) * (rhs.y / 6.0);
+		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
+		else if (a0) a.out[i] = o0;
+		else a.out[i + 1] = o1;
+		near |= ((flg[dz].x | flg[dz].y) & 2) << dz;
+	    }
+	    // phase 2, the few cells with a band cell in their neighbourhood (bit dz + 1 of `near`): the full stencil with every
+	    // value taken through the band mask -- whatever the grid holds off the band reads as zero -- overwrites phase 1's
+	    // value.  One plane at a time and everything re-read (cache hits): the common path keeps no registers for it.
+#pragma unroll 1
+	    for (int dz = 0; near != 0 && dz < CHUNK_Z; ++dz)
+	    {
+		if (!((near >> (dz + 1)) & 1)) continue;
+		const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
+		const uchar2 l = *reinterpret_cast<const uchar2 *>(a.labels + i);
+		const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
+		const double2 rhs = ld2(a.b + i);
+		const uint8_t *f = a.flags + i;
+		const uchar2 fc = *reinterpret_cast<const uchar2 *>(f);
+		const uchar2 fym = *reinterpret_cast<const uchar2 *>(f - a.pitch), fyp = *reinterpret_cast<const uchar2 *>(f + a.pitch);
+		const uchar2 fzm = *reinterpret_cast<const uchar2 *>(f - a.plane), fzp = *reinterpret_cast<const uchar2 *>(f + a.plane);
+		const int fxm = f[-1], fxp = f[2];
+		double2 c2 = ld2(a.in + i);
+		double xm = a.in[i - 1], xp = a.in[i + 2];
+		double2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
+		double2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
+		if (!(fc.x & 1)) c2.x = 0.0;
+		if (!(fc.y & 1)) c2.y = 0.0;
+		if (!(fxm & 1)) xm = 0.0;
+		if (!(fxp & 1)) xp = 0.0;
+		if (!(fym.x & 1)) ym.x = 0.0;
+		if (!(fym.y & 1)) ym.y = 0.0;
+		if (!(fyp.x & 1)) yp.x = 0.0;
+		if (!(fyp.y & 1)) yp.y = 0.0;
+		if (!(fzm.x & 1)) zm.x = 0.0;
+		if (!(fzm.y & 1)) zm.y = 0.0;
+		if (!(fzp.x & 1)) zp.x = 0.0;
+		if (!(fzp.y & 1)) zp.y = 0.0;
+		double lap0 = -xm;
+		lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
+		lap0 += 6.0 * c2.x;
+		double lap1 = -c2.x;
+		lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
+		lap1 += 6.0 * c2.y;
+		const double o0 = stencilFinish<MODE>(lap0, c2.x, rhs.x, 6.0);
+		const double o1 = stencilFinish<MODE>(lap1, c2.y, rhs.y, 6.0);
+		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
+		else if (a0) a.out[i] = o0;
+		else a.out[i + 1] = o1;
+	    }
+	    return acc;
+	}
 #pragma unroll
 	for (int dz = 0; dz < CHUNK_Z; ++dz)
 	{
@@ -241,54 +305,6 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 	    const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
 	    if (!(a0 | a1)) continue;
 	    const int64_t i = int64_t(z) * a.plane + inPlane;
-	    if (MODE == SM_JACOBI_ZERO)
-	    {
-		const double2 rhs = ld2(a.b + i);
-		double o0, o1;
-		if (!((flg[dz].x | flg[dz].y) & 2))
-		{
-		    // no band cell in either neighbourhood: every x is zero, lap = +0.0, and centre + (2/3)((b - 0) / 6) = (2/3)(b / 6)
-		    o0 = (2.0 / 3.0) * (rhs.x / 6.0);
-		    o1 = (2.0 / 3.0) * (rhs.y / 6.0);
-		}
-		else
-		{
-		    // values through the band mask: whatever the grid holds off the band reads as zero
-		    const uint8_t *f = a.flags + i;
-		    const uchar2 fc = *reinterpret_cast<const uchar2 *>(f);
-		    const uchar2 fym = *reinterpret_cast<const uchar2 *>(f - a.pitch), fyp = *reinterpret_cast<const uchar2 *>(f + a.pitch);
-		    const uchar2 fzm = *reinterpret_cast<const uchar2 *>(f - a.plane), fzp = *reinterpret_cast<const uchar2 *>(f + a.plane);
-		    const int fxm = f[-1], fxp = f[2];
-		    double2 c2 = ld2(a.in + i);
-		    double xm = a.in[i - 1], xp = a.in[i + 2];
-		    double2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
-		    double2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
-		    if (!(fc.x & 1)) c2.x = 0.0;
-		    if (!(fc.y & 1)) c2.y = 0.0;
-		    if (!(fxm & 1)) xm = 0.0;
-		    if (!(fxp & 1)) xp = 0.0;
-		    if (!(fym.x & 1)) ym.x = 0.0;
-		    if (!(fym.y & 1)) ym.y = 0.0;
-		    if (!(fyp.x & 1)) yp.x = 0.0;
-		    if (!(fyp.y & 1)) yp.y = 0.0;
-		    if (!(fzm.x & 1)) zm.x = 0.0;
-		    if (!(fzm.y & 1)) zm.y = 0.0;
-		    if (!(fzp.x & 1)) zp.x = 0.0;
-		    if (!(fzp.y & 1)) zp.y = 0.0;
-		    double lap0 = -xm;
-		    lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
-		    lap0 += 6.0 * c2.x;
-		    double lap1 = -c2.x;
-		    lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
-		    lap1 += 6.0 * c2.y;
-		    o0 = stencilFinish<MODE>(lap0, c2.x, rhs.x, 6.0);
-		    o1 = stencilFinish<MODE>(lap1, c2.y, rhs.y, 6.0);
-		}
-		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
-		else if (a0) a.out[i] = o0;
-		else a.out[i + 1] = o1;
-		continue;
-	    }
 	    const double2 c2 = ld2(a.in + i);
 	    const double xm = a.in[i - 1], xp = a.in[i + 2];
 	    const double2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
@@ -313,8 +329,9 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
     return acc;
 }
 
+// (the zero-aware sweep streams b -> x on its common path: capped at 40 registers so the rare masked path cannot cost it occupancy)
 template <int MODE, bool DOT>
-__global__ void __launch_bounds__(BLOCK) k_stencil(const StencilArgs a)
+__global__ void __launch_bounds__(BLOCK, MODE == SM_JACOBI_ZERO ? 6 : 1) k_stencil(const StencilArgs a)
 {
     pdlLaunch();
     const double acc = stencilBody<MODE, DOT>(a, blockIdx.x, threadIdx.x);
@@ -501,7 +518,9 @@ constexpr int BAND_PER_THREAD = 2;  // cells per thread: two independent gather 
 // FZ: the grid was all zero when this sweep group started, so the frozen (non-band) neighbours are zero and are not read at
 // all -- the grid may hold anything off the band (no zero fill before the group, see SM_JACOBI_ZERO)
 // Prologue (static metadata, before pdlWait): grid index, neighbour references, diagonal, coefficient record.
-template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false>
+// CGL: values of the compact arrays are read past L1 (ld.cg) -- inside the persistent sweep-group kernel another SM wrote them
+// during the same launch
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false, bool CGL = false>
 __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 {
     int64_t gi[BAND_PER_THREAD];
@@ -543,7 +562,7 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 	if (!ZERO)
 	{
 	    const bool weighted = HAS_W && k < a.nBoundary;
-	    centre = FROM_COMPACT ? a.vin[k] : a.x[i];
+	    centre = FROM_COMPACT ? (CGL ? __ldcg(a.vin + k) : a.vin[k]) : a.x[i];
 	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
 #pragma unroll
 	    for (int n = 0; n < 6; ++n)
@@ -554,9 +573,9 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 		if (FROM_COMPACT && FZ)
 		{
 		    if (r < 0) continue;  // a frozen neighbour holds 0: lap -= c * 0 changes nothing
-		    u = a.vin[r];
+		    u = CGL ? __ldcg(a.vin + r) : a.vin[r];
 		}
-		else if (FROM_COMPACT) u = r >= 0 ? a.vin[r] : a.x[-2 - r];
+		else if (FROM_COMPACT) u = r >= 0 ? (CGL ? __ldcg(a.vin + r) : a.vin[r]) : a.x[-2 - r];
 		else u = a.x[i + stride[n]];
 		if (weighted)
 		{
@@ -586,6 +605,81 @@ __global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
 {
     pdlLaunch();
     bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W, FZ>(a, blockIdx.x, threadIdx.x);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// A whole group of band sweeps (MG.cpp:445-513: myBoundarySmootherIterations = 3 before and after every interior sweep) in ONE
+// launch: the sweeps of a group are dependent steps of a few microseconds each, and a grid-wide barrier between them (one
+// atomic per CTA on a counter, everybody polls a generation word) is cheaper than a kernel boundary with its drain, launch and
+// ramp.  The grid is sized to be co-resident (the host asks the occupancy calculator); CTAs walk the virtual CTAs of the
+// sweep-per-launch kernels with the same bodies, so every cell sees the same arithmetic.  A wait that exceeds two seconds of
+// wall clock sets the error word and gives up instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------
+struct GroupBarrier
+{
+    unsigned count;
+    unsigned generation;
+    int error;
+};
+__device__ __forceinline__ void gridBarrier(GroupBarrier *bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+	__threadfence();
+	const unsigned gen = *reinterpret_cast<volatile unsigned *>(&bar->generation);
+	if (atomicAdd(&bar->count, 1u) == gridDim.x - 1)
+	{
+	    bar->count = 0u;
+	    __threadfence();
+	    atomicAdd(&bar->generation, 1u);
+	}
+	else
+	{
+	    unsigned long long t0 = 0;
+	    unsigned spins = 0;
+	    while (*reinterpret_cast<volatile unsigned *>(&bar->generation) == gen)
+	    {
+		if ((++spins & 4095u) == 0)
+		{
+		    unsigned long long t;
+		    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		    if (t0 == 0) t0 = t;
+		    else if (t - t0 > 2000000000ull) { atomicExch(&bar->error, 1); break; }
+		}
+	    }
+	}
+	__threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool HAS_W, bool ZEROGRID>
+__global__ void __launch_bounds__(BLOCK) k_band_group(BandArgs a, int sweeps, int nVirtual, GroupBarrier *bar)
+{
+    pdlLaunch();
+    double *cur = a.vout, *nxt = const_cast<double *>(a.vin);  // the two compact arrays: sweep 1 writes cur
+    // sweep 1: grid -> compact
+    a.vin = nullptr;
+    a.vout = cur;
+    for (int vb = blockIdx.x; vb < nVirtual; vb += gridDim.x)
+    {
+	if (ZEROGRID) bandBody<false, false, true, true, false>(a, vb, threadIdx.x);
+	else bandBody<false, false, true, false, HAS_W>(a, vb, threadIdx.x);
+    }
+    for (int sw = 2; sw <= sweeps; ++sw)
+    {
+	gridBarrier(bar);
+	a.vin = cur;
+	a.vout = nxt;
+	for (int vb = blockIdx.x; vb < nVirtual; vb += gridDim.x)
+	{
+	    if (sw == sweeps) bandBody<true, true, false, false, HAS_W, ZEROGRID, true>(a, vb, threadIdx.x);
+	    else bandBody<true, false, false, false, HAS_W, ZEROGRID, true>(a, vb, threadIdx.x);
+	}
+	double *t = cur; cur = nxt; nxt = t;
+    }
 }
 
 __global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t *bandIdx, const double *v, int nBand)
@@ -656,6 +750,77 @@ __device__ __forceinline__ void restrictBody(const TransferArgs &a, int vb, int 
     a.out[ci] = v;
 }
 __global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a) { pdlLaunch(); restrictBody(a, blockIdx.x, threadIdx.x); }
+
+
+// ------------------------------------------------------------------------------------------------
+// Restriction with the fine residual staged through shared memory by TMA.  k_restrict issues 48 global loads per coarse
+// cell (16 rows x {scalar, aligned pair, scalar}); every fine value is wanted by 8 coarse cells, so the load/store unit
+// sees 8x the data and the kernel sits at 0.40 of the HBM roofline with its warps waiting on L1/L2 (ncu: 412 M sectors
+// at 512^3 against 45-60 M for the stencil kernels).  Here a CTA owns a 32 x 4 x 2 brick of coarse cells; its 4x4x4 taps
+// cover a 66 x 10 x 6 box of fine cells, fetched by ONE bulk tensor copy (68 wide, one cell further left, so the aligned
+// pair of every row is 16-byte aligned in shared memory -- the same box shape as k_stencil_tma, hence the same tensor
+// map), and the 48 loads per coarse cell become shared-memory loads.  Same arithmetic, same order: bitwise k_restrict.
+// ------------------------------------------------------------------------------------------------
+constexpr int RB_X = 32, RB_Y = 4, RB_Z = 2;
+
+__global__ void __launch_bounds__(BLOCK) k_restrict_tma(const TransferArgs a, const __grid_constant__ TmaMap tmFine, const int32_t *bricks, int bricksX, int bricksY)
+{
+    pdlLaunch();
+    __shared__ alignas(128) double tile[TB_BOX_Z][TB_BOX_Y][TB_BOX_X];
+    __shared__ alignas(8) unsigned long long bar;
+    const int br = bricks[blockIdx.x];
+    const int bz = br / (bricksX * bricksY), by = (br - bz * bricksX * bricksY) / bricksX, bx = br - (bz * bricksY + by) * bricksX;
+    const int c0x = bx * RB_X, c0y = by * RB_Y, c0z = bz * RB_Z;
+    const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) & 3, tz = threadIdx.x >> 7;
+    const int cx = c0x + tx, cy = c0y + ty, cz = c0z + tz;
+    const bool inBox = cx < a.coarsePitch && cy < a.coarseNy && cz >= a.zlo && cz < a.zhi;
+    const int64_t ci = int64_t(cz) * a.coarsePlane + int64_t(cy) * a.coarsePitch + cx;
+    const int l = inBox ? int(a.coarseLabels[ci]) : int(L_EXTERIOR);  // prologue: static
+    if (threadIdx.x == 0) mbarInit(&bar, 1);
+    __syncthreads();
+    pdlWait();
+    if (threadIdx.x == 0)
+    {
+	mbarExpectTx(&bar, TB_BOX_BYTES);
+	// first tap of the brick's first coarse cell: fine 2 (c - shift) - 1; the box starts one cell further left in x; z + 1 = guard plane
+	tmaLoad3d(&tile[0][0][0], &tmFine, 2 * (c0x - a.shift[0]) - 2, 2 * (c0y - a.shift[1]) - 1, 2 * (c0z - a.shift[2]) - 1 + 1, &bar);
+    }
+    mbarWait(&bar, 0);
+    if (!(l == L_INTERIOR || l == L_BOUNDARY)) return;
+    const double rw[4] = {1. / 8., 3. / 8., 3. / 8., 1. / 8.};
+    double v = 0.0;
+#pragma unroll
+    for (int z = 0; z < 4; ++z)
+#pragma unroll
+	for (int y = 0; y < 4; ++y)
+	{
+	    const double *row = &tile[2 * tz + z][2 * ty + y][2 * tx + 1];
+	    const double s0 = row[0];
+	    const double2 s12 = *reinterpret_cast<const double2 *>(row + 1);
+	    const double s3 = row[3];
+	    v += rw[0] * rw[y] * rw[z] * s0;
+	    v += rw[1] * rw[y] * rw[z] * s12.x;
+	    v += rw[2] * rw[y] * rw[z] * s12.y;
+	    v += rw[3] * rw[y] * rw[z] * s3;
+	}
+    a.out[ci] = v;
+}
+
+// coarse-brick flags: 1 when the 32 x 4 x 2 brick of coarse cells holds an active cell
+__global__ void __launch_bounds__(BLOCK) k_cbrick_flags(uint8_t *flags, const uint8_t *labels, int bricksX, int bricksY, int pitch, int64_t plane, int ny, int nz)
+{
+    const int br = blockIdx.x;
+    const int bz = br / (bricksX * bricksY), by = (br - bz * bricksX * bricksY) / bricksX, bx = br - (bz * bricksY + by) * bricksX;
+    const int x = bx * RB_X + (threadIdx.x & 31), y = by * RB_Y + ((threadIdx.x >> 5) & 3), z = bz * RB_Z + (threadIdx.x >> 7);
+    int any = 0;
+    if (x < pitch && y < ny && z < nz)
+    {
+	const int l = labels[int64_t(z) * plane + int64_t(y) * pitch + x];
+	any = (l == L_INTERIOR || l == L_BOUNDARY);
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) flags[br] = uint8_t(any);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Prolongation (Ops.h:873-972): fine (active) += 4 * trilerp(8 coarse cells), fractions .25/.75.

@@ -397,8 +397,8 @@ def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
     results = {}
     for name, env in [("cluster", {}), ("compact", {"GMG_CLUSTER_CYCLE": "0"}), ("kernels", {"GMG_COARSE_FUSED": "0"}),
                       ("zero_fill", {"GMG_ZERO_AWARE": "0"}), ("cluster8", {"GMG_CLUSTER_SIZE": "8"}), ("first2", {"GMG_FUSED_FIRST": "2"}),
-                      ("tma", {"GMG_TMA": "1", "GMG_TMA_MIN_CELLS": "100"})]:
-        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS"):
+                      ("tma", {"GMG_TMA": "1", "GMG_TMA_MIN_CELLS": "100"}), ("sweep_per_launch", {"GMG_BAND_GROUPS": "0"})]:
+        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS", "GMG_BAND_GROUPS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -409,4 +409,8 @@ def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
     for name, (v, vg, (x, it, hist)) in results.items():
         assert (v == ref[0]).all(), name
         assert (vg == ref[1]).all(), name
-        assert it == ref[2][1] and (hist == ref[2][2]).all() and (x == ref[2][0]).all(), name
+        if name == "tma":
+            # the brick kernel sums p.Ap over a different CTA decomposition: same cells, another order of the partial sums
+            assert it == ref[2][1] and relerr(hist, ref[2][2]) < 1e-11 and relerr(x, ref[2][0]) < 1e-11, name
+        else:
+            assert it == ref[2][1] and (hist == ref[2][2]).all() and (x == ref[2][0]).all(), name
