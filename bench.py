@@ -253,6 +253,8 @@ def measure_sweep(torch, api, ctx, dist, rank, world, n, steps, warmup, flush):
     for _ in range(nprof):
         solver.applyVCycleDevice(Z, B)
     prof_fine = ctx.profile(True)
+    by_level = {str(l): {k: {"ms_per_vcycle": round(v[0] / nprof, 4), "launches_per_vcycle": v[1] // nprof} for k, v in row.items() if k != "setup" and v[1] > 0}
+                for l, row in ctx.profile_by_level(nlev).items()}
     ctx.profile_enable(False)
     peak, peak_kind = measured_peak()
     fine = {k: v for k, v in prof_fine.items() if k not in ("setup", "coarse_solve", "halo_exchange") and v[1] > 0 and v[2] > 0}
@@ -271,7 +273,7 @@ def measure_sweep(torch, api, ctx, dist, rank, world, n, steps, warmup, flush):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(f"vcycle{n}", dom), "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "launches": d_n,
                      "avg_launch_us": d_ms / d_n * 1e3, "algorithmic_bytes_per_launch": d_bytes / d_n},
-        "fine_level_kernels": classes,
+        "fine_level_kernels": classes, "kernels_by_level": by_level,
         "halo_exchange_ms_per_vcycle": (halo[0] / nprof) if halo and halo[1] else 0.0,
         "kernel_timing": "CUDA event nodes inside the replayed V-cycle graph (rank 0's slab when sharded)",
         "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "host_build_s": build_s,

@@ -1221,8 +1221,10 @@ static int buildChunks(gmg_ctx *ctx, Level &L)
 // INTERIOR cell.  Built for levels of at least GMG_TMA_MIN_CELLS cells when GMG_TMA=1 (A/B switch, profiles/).
 static int tmaMode()
 {
-    const char *e = getenv("GMG_TMA");  // read at solver creation; GMG_TMA=0 forces the plain-load kernels everywhere
-    return e ? atoi(e) : 1;
+    // read at solver creation; a bit mask of the kernels that take the TMA-staged variant on big levels: 1 interior Jacobi,
+    // 2 residual, 4 apply, 8 restriction, 16 prolongation; GMG_TMA=0 forces the plain-load kernels everywhere
+    const char *e = getenv("GMG_TMA");
+    return e ? atoi(e) : 31;
 }
 static int buildBricks(gmg_ctx *ctx, Level &L)
 {
@@ -1230,7 +1232,8 @@ static int buildBricks(gmg_ctx *ctx, Level &L)
     // 512^3; at 256^3, where a level-0 grid is 34 MB and L2-resident, the brick kernel's longer prologue loses 15 %)
     const char *mc = getenv("GMG_TMA_MIN_CELLS");
     const int64_t minCells = mc ? atoll(mc) : int64_t(12) << 20;
-    if (!tmaMode() || L.nInterior < minCells) return GMG_OK;
+    // (the level's GLOBAL cell count decides, so a z-slab of a sharded level takes the same kernels as the unsharded level)
+    if (!tmaMode() || L.nActiveGlobal < minCells) return GMG_OK;
     const Geom &g = L.g;
     L.bricksX = int(divUp(g.n[0], TB_X));
     L.bricksY = int(divUp(g.n[1], TB_Y));
@@ -1243,6 +1246,11 @@ static int buildBricks(gmg_ctx *ctx, Level &L)
 	k_brick_flags<<<unsigned(nb), BLOCK, 0, ctx->stream>>>(flags, L.labels, L.bricksX, L.bricksY, g.pitch, g.plane, g.n[1], g.n[2]);
     }
     GMG_TRY(selectFlagged(ctx, flags, nb, &L.bricks, &L.nBricks));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_brick_flags_active<<<unsigned(nb), BLOCK, 0, ctx->stream>>>(flags, L.labels, L.bricksX, L.bricksY, g.pitch, g.plane, g.n[1], g.n[2]);
+    }
+    GMG_TRY(selectFlagged(ctx, flags, nb, &L.bricksActive, &L.nBricksActive));
     GMG_CUDA(devFree(flags));
     return GMG_OK;
 }
@@ -1267,7 +1275,7 @@ static int buildCoarseBricks(gmg_ctx *ctx, Level &C)
 
 // 3D tensor map over a vector grid INCLUDING its two guard planes (the tensor's plane 0 is the lower guard plane), box =
 // brick + halo.  Cached per grid pointer: the kernels take it by value (__grid_constant__), so a captured graph keeps its own copy.
-static int tensorMapOf(gmg_solver *s, int level, const double *grid, TmaMap *out)
+static int tensorMapOf(gmg_solver *s, int level, const double *grid, TmaMap *out, int boxKind = 0)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
 				 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1278,7 +1286,7 @@ static int tensorMapOf(gmg_solver *s, int level, const double *grid, TmaMap *out
 	return reinterpret_cast<EncodeFn>(fn);
     }();
     if (!encode) return invalid("cuTensorMapEncodeTiled is not available in this driver");
-    auto key = std::make_pair(level, grid);
+    auto key = std::make_pair(level * 4 + boxKind, grid);
     auto it = s->tensorMaps.find(key);
     if (it == s->tensorMaps.end())
     {
@@ -1287,7 +1295,8 @@ static int tensorMapOf(gmg_solver *s, int level, const double *grid, TmaMap *out
 	TmaMap m;
 	const cuuint64_t dims[3] = {cuuint64_t(g.pitch), cuuint64_t(g.n[1]), cuuint64_t(g.n[2] + 2)};
 	const cuuint64_t strides[2] = {cuuint64_t(g.pitch) * sizeof(double), cuuint64_t(g.plane) * sizeof(double)};
-	const cuuint32_t box[3] = {TB_BOX_X, TB_BOX_Y, TB_BOX_Z};
+	// boxKind 0: a 64 x 8 x 4 brick plus its stencil / restriction halo; 1: the coarse box a fine brick interpolates from
+	const cuuint32_t box[3] = {cuuint32_t(boxKind ? PB_BOX_X : TB_BOX_X), cuuint32_t(boxKind ? PB_BOX_Y : TB_BOX_Y), cuuint32_t(boxKind ? PB_BOX_Z : TB_BOX_Z)};
 	const cuuint32_t estr[3] = {1, 1, 1};
 	const CUresult r = encode(reinterpret_cast<CUtensorMap *>(&m), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(grid) - g.plane, dims, strides, box, estr,
 				  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1385,7 +1394,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 static void freeLevel(Level &L)
 {
     devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab); devFree(L.flagsAlloc);
-    devFree(L.chunksInterior); devFree(L.chunksActive); devFree(L.bricks); devFree(L.cbricks);
+    devFree(L.chunksInterior); devFree(L.chunksActive); devFree(L.bricks); devFree(L.bricksActive); devFree(L.cbricks);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
     L = Level();
@@ -2192,7 +2201,8 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     if (const char *e = getenv("GMG_NO_GRAPHS")) s->useGraphs = !(e[0] == '1');
     if (const char *e = getenv("GMG_PRINT_STATS")) s->opt.print_stats = (e[0] == '1');
     if (const char *e = getenv("GMG_ZERO_AWARE")) s->zeroAware = !(e[0] == '0');
-    if (const char *e = getenv("GMG_BAND_GROUPS")) s->bandGroups = !(e[0] == '0');
+    s->tmaMask = tmaMode();
+    if (const char *e = getenv("GMG_BAND_GROUPS")) s->bandGroups = (e[0] == '1');
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel && ctx->world > 1)
@@ -2463,7 +2473,7 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
     if (grid == 0) return GMG_OK;
     cudaStream_t st = s->ctx->stream;
     const double n = double(L.nActive);
-    if (L.bricks && mode != SM_JACOBI_ZERO)
+    if (L.bricks && mode != SM_JACOBI_ZERO && (s->tmaMask & (mode == SM_JACOBI ? 1 : (mode == SM_RESIDUAL ? 2 : 4))))
     {
 	// TMA-staged variant: one CTA per 64 x 8 x 4 brick
 	TmaMap tm;
@@ -2643,7 +2653,7 @@ static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const do
     a.zlo = zr.lo;
     a.zhi = zr.hi;
     GMG_LAUNCH(s->ctx, KC_RESTRICT, double(s->lv[fineLevel].nActive) * 8.0 + double(C.nActive) * 9.0);
-    if (C.cbricks)
+    if (C.cbricks && (s->tmaMask & 8))
     {
 	// TMA-staged variant: one CTA per 32 x 4 x 2 brick of coarse cells
 	TmaMap tm;
@@ -2670,6 +2680,16 @@ static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const doubl
     a.zlo = zr.lo;
     a.zhi = zr.hi;
     GMG_LAUNCH(s->ctx, KC_PROLONG, double(F.nActive) * 17.0 + double(s->lv[fineLevel + 1].nActive) * 8.0);
+    if (F.bricksActive && (s->tmaMask & 16))
+    {
+	// TMA-staged variant: the coarse box of every 64 x 8 x 4 fine brick through shared memory
+	TmaMap tm;
+	GMG_TRY(tensorMapOf(s, fineLevel + 1, coarse, &tm, 1));
+	if (F.nBricksActive > 0)
+	    GMG_CUDA(launchK(k_prolong_tma, unsigned(F.nBricksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, a, tm, F.bricksActive, F.bricksX, F.bricksY, F.g.n[1]));
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     GMG_CUDA(launchK(k_prolong, unsigned(F.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
@@ -2701,7 +2721,14 @@ static int launchCoarse(gmg_solver *s, double *x, const double *b)
 static int buildClusterCycle(gmg_solver *s)
 {
     s->fusedFirst = -1;
-    if (const char *e = getenv("GMG_CLUSTER_CYCLE")) if (e[0] == '0') return GMG_OK;
+    // OPT-IN (GMG_CLUSTER_CYCLE=1).  Measured on B200 (profiles/r02_cluster_cycle.md): 195 us for levels 3..6 of the 256^3
+    // problem against 98 us for level 3 as kernels of its own plus the one-CTA cycle for levels 4..6 -- half of it the
+    // single-CTA levels (every restriction tap / prolongation corner between a distributed level and a single-CTA level funnels
+    // through one SM's ~20 B/cycle cluster port), a quarter the cluster barriers themselves (0.5 us each, scripts/cluster_probe.cu).
+    {
+	const char *e = getenv("GMG_CLUSTER_CYCLE");
+	if (!(e && e[0] == '1')) return GMG_OK;
+    }
     if (const char *e = getenv("GMG_COARSE_FUSED")) if (e[0] == '0') return GMG_OK;
     if (s->opt.operators_only || s->levels < 2) return GMG_OK;
     if (s->opt.use_gauss_seidel) return GMG_OK;  // the fused cycles implement the Jacobi interior sweep only

@@ -119,7 +119,7 @@ __device__ __forceinline__ double clusterLap(cg::cluster_group &cl, const Cluste
 }
 
 // one damped-Jacobi sweep xin -> xout over the band cells (bandOnly; everything else is copied) or over all cells
-// (Ops.h:262-367, :524-619), ending on the cluster barrier
+// (Ops.h:262-367, :524-619); the caller ends the step (cluster barrier, or __syncthreads inside the solo sub-cycle)
 __device__ __forceinline__ void clusterSweep(cg::cluster_group &cl, const ClusterLevel &L, const ClusterTab &T, double *__restrict__ xin, double *__restrict__ xout,
 					     const double *__restrict__ b, int rank, int first, int count, bool bandOnly)
 {
@@ -133,7 +133,6 @@ __device__ __forceinline__ void clusterSweep(cg::cluster_group &cl, const Cluste
 	r /= diag;
 	xout[j] = xin[j] + (2.0 / 3.0) * r;
     }
-    cl.sync();
 }
 
 // Levels [soloFirst, nLevels) are small enough (<= CLUSTER_SOLO_MAX cells) to live entirely in CTA 0: there a step ends on

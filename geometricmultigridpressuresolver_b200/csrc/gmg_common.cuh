@@ -97,6 +97,8 @@ struct Level
     // TMA path (k_stencil_tma): 64 x 8 x 4 bricks holding an INTERIOR cell (linear brick ids, x fastest); null = plain-load kernels
     int32_t *bricks = nullptr;
     int nBricks = 0, bricksX = 0, bricksY = 0;
+    int32_t *bricksActive = nullptr;  // the same bricks holding an ACTIVE cell (TMA prolongation, k_prolong_tma)
+    int nBricksActive = 0;
     int32_t *cbricks = nullptr;  // 32 x 4 x 2 bricks of THIS level's cells holding an active cell: TMA restriction into this level (k_restrict_tma)
     int nCBricks = 0, cbricksX = 0, cbricksY = 0;
     // V-cycle grids (level 0 uses caller grids for x and b)
@@ -220,8 +222,11 @@ struct gmg_solver
     };
     std::map<std::tuple<int, const void *, const void *, int>, GraphEntry> graphs;
     std::map<std::pair<int, const double *>, gmg::TmaMap> tensorMaps;  // (level, grid) -> tensor map of the TMA stencil kernels
+    int tmaMask = 31;             // which full-grid kernels take the TMA-staged variant on big levels (GMG_TMA, see tmaMode)
     bool useGraphs = true;
-    bool bandGroups = true;       // a group of band sweeps as ONE co-resident launch with grid barriers (GMG_BAND_GROUPS=0: a launch per sweep)
+    bool bandGroups = false;      // a group of band sweeps as ONE co-resident launch with grid barriers: measured SLOWER than a launch per sweep
+				  // (profiles/r02_ab_switches.md: 256^3 solve 11.5 vs 10.3 ms; a barrier over ~900 CTAs costs more than a kernel
+				  // boundary with its prologue overlapped), so it is opt-in (GMG_BAND_GROUPS=1)
     bool zeroAware = true;        // zero-aware down-stroke (no zero fill, SM_JACOBI_ZERO); GMG_ZERO_AWARE=0 at creation restores the fill
 };
 

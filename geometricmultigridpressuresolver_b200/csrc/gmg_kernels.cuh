@@ -901,6 +901,121 @@ __device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int t
 }
 __global__ void __launch_bounds__(BLOCK, 6) k_prolong(const TransferArgs a) { pdlLaunch(); prolongBody(a, blockIdx.x, threadIdx.x); }
 
+
+// ------------------------------------------------------------------------------------------------
+// Prolongation with the coarse values staged through shared memory by TMA: a 64 x 8 x 4 brick of fine cells interpolates
+// from a 34 x 6 x 4 box of coarse cells (one bulk tensor copy, 6.5 KB), so the 18 scalar coarse loads per thread and z-pair of
+// k_prolong -- each coarse value wanted by 3 x 2 threads -- come from shared memory and only the fine read-modify-write (the
+// actual traffic: 17 of 18 bytes per cell) goes through the load/store unit to global memory.  Same arithmetic as prolongBody.
+// ------------------------------------------------------------------------------------------------
+constexpr int PB_BOX_X = TB_X / 2 + 2, PB_BOX_Y = TB_Y / 2 + 2, PB_BOX_Z = TB_Z / 2 + 2;
+constexpr unsigned PB_BOX_BYTES = PB_BOX_X * PB_BOX_Y * PB_BOX_Z * sizeof(double);
+
+__global__ void __launch_bounds__(BLOCK) k_prolong_tma(const TransferArgs a, const __grid_constant__ TmaMap tmCoarse, const int32_t *bricks, int bricksX, int bricksY, int ny)
+{
+    pdlLaunch();
+    __shared__ alignas(128) double tile[PB_BOX_Z][PB_BOX_Y][PB_BOX_X];
+    __shared__ alignas(8) unsigned long long bar;
+    const int br = bricks[blockIdx.x];
+    const int bz = br / (bricksX * bricksY), by = (br - bz * bricksX * bricksY) / bricksX, bx = br - (bz * bricksY + by) * bricksX;
+    const int x0 = bx * TB_X, y0 = by * TB_Y, z0 = bz * TB_Z;
+    const int px = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int fx = x0 + 2 * px, fy = y0 + ty;
+    const bool inRow = fx < a.finePitch && fy < ny;
+    const int64_t inPlane = int64_t(fy) * a.finePitch + fx;
+    // prologue: the fine labels of the thread's cells (static)
+    uchar2 lab[TB_Z];
+#pragma unroll
+    for (int q = 0; q < TB_Z; ++q)
+    {
+	const int fz = z0 + q;
+	lab[q] = make_uchar2(L_EXTERIOR, L_EXTERIOR);
+	if (inRow && fz >= a.zlo && fz < a.zhi) lab[q] = *reinterpret_cast<const uchar2 *>(a.fineLabels + int64_t(fz) * a.finePlane + inPlane);
+    }
+    if (threadIdx.x == 0) mbarInit(&bar, 1);
+    __syncthreads();
+    pdlWait();
+    if (threadIdx.x == 0)
+    {
+	mbarExpectTx(&bar, PB_BOX_BYTES);
+	// coarse cell of the brick's first fine cell, minus one in every direction; z + 1 = the coarse grid's guard plane
+	tmaLoad3d(&tile[0][0][0], &tmCoarse, (x0 >> 1) + a.shift[0] - 1, (y0 >> 1) + a.shift[1] - 1, (z0 >> 1) + a.shift[2] - 1 + 1, &bar);
+    }
+    // the fine values to update: plain coalesced loads, in flight while the coarse box lands
+    double2 old[TB_Z];
+#pragma unroll
+    for (int q = 0; q < TB_Z; ++q)
+    {
+	old[q] = make_double2(0.0, 0.0);
+	const uchar2 l = lab[q];
+	const bool any = (l.x == L_INTERIOR) | (l.x == L_BOUNDARY) | (l.y == L_INTERIOR) | (l.y == L_BOUNDARY);
+	if (any) old[q] = ld2(a.out + int64_t(z0 + q) * a.finePlane + inPlane);
+    }
+    mbarWait(&bar, 0);
+    const int ly = (ty & 1) ? (ty >> 1) + 1 : (ty >> 1);  // ys - box origin
+    const double wy = (ty & 1) ? .25 : .75;               // fy and ty have the same parity (y0 is even)
+#pragma unroll
+    for (int p = 0; p < TB_Z / 2; ++p)
+    {
+	const uchar2 l0 = lab[2 * p], l1 = lab[2 * p + 1];
+	const bool a00 = (l0.x == L_INTERIOR || l0.x == L_BOUNDARY), a01 = (l0.y == L_INTERIOR || l0.y == L_BOUNDARY);
+	const bool a10 = (l1.x == L_INTERIOR || l1.x == L_BOUNDARY), a11 = (l1.y == L_INTERIOR || l1.y == L_BOUNDARY);
+	if (!(a00 | a01 | a10 | a11)) continue;
+	double ex[2][3], ox[2][3];  // [y: ys, ys+1][z: mz-1..mz+1]
+#pragma unroll
+	for (int z = 0; z < 3; ++z)
+#pragma unroll
+	    for (int y = 0; y < 2; ++y)
+	    {
+		const double *row = &tile[p + z][ly + y][px + 1];
+		const double v0 = row[-1], v1 = row[0], v2 = row[1];
+		ex[y][z] = lerpRef(v0, v1, .75);
+		ox[y][z] = lerpRef(v1, v2, .25);
+	    }
+	double ey[3], oy[3];
+#pragma unroll
+	for (int z = 0; z < 3; ++z)
+	{
+	    ey[z] = lerpRef(ex[0][z], ex[1][z], wy);
+	    oy[z] = lerpRef(ox[0][z], ox[1][z], wy);
+	}
+#pragma unroll
+	for (int q = 0; q < 2; ++q)
+	{
+	    const bool ax = q ? a10 : a00, ay = q ? a11 : a01;
+	    if (!(ax | ay)) continue;
+	    const int64_t i = int64_t(z0 + 2 * p + q) * a.finePlane + inPlane;
+	    const double wz = q ? .25 : .75;
+	    const double2 o = old[2 * p + q];
+	    const double e = lerpRef(ey[q], ey[q + 1], wz);
+	    const double od = lerpRef(oy[q], oy[q + 1], wz);
+	    const double n0 = o.x + 4. * e, n1 = o.y + 4. * od;
+	    if (ax & ay) st2(a.out + i, make_double2(n0, n1));
+	    else if (ax) a.out[i] = n0;
+	    else a.out[i + 1] = n1;
+	}
+    }
+}
+
+// brick flags for the prolongation: 1 when the 64 x 8 x 4 brick holds an ACTIVE cell
+__global__ void __launch_bounds__(BLOCK) k_brick_flags_active(uint8_t *flags, const uint8_t *labels, int bricksX, int bricksY, int pitch, int64_t plane, int ny, int nz)
+{
+    const int br = blockIdx.x;
+    const int bz = br / (bricksX * bricksY), by = (br - bz * bricksX * bricksY) / bricksX, bx = br - (bz * bricksY + by) * bricksX;
+    const int x = bx * TB_X + 2 * (threadIdx.x & 31), y = by * TB_Y + (threadIdx.x >> 5);
+    int any = 0;
+    if (x < pitch && y < ny)
+	for (int dz = 0; dz < TB_Z; ++dz)
+	{
+	    const int z = bz * TB_Z + dz;
+	    if (z >= nz) break;
+	    const uchar2 l = *reinterpret_cast<const uchar2 *>(labels + int64_t(z) * plane + int64_t(y) * pitch + x);
+	    any |= (l.x == L_INTERIOR) | (l.x == L_BOUNDARY) | (l.y == L_INTERIOR) | (l.y == L_BOUNDARY);
+	}
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) flags[br] = uint8_t(any);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Coarsest level (MG.cpp:669-692): gather b, x = A^-1 b (dense inverse of the SPD matrix, built on the
 // host at setup from an exact Cholesky factor), scatter.  One warp per row, b staged in shared memory.
