@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "gmg_vcycle", "gmg_pcg", "gmg_grid_create", "gmg_grid_destroy", "gmg_grid_upload", "gmg_grid_download", "gmg_grid_zero", "gmg_grid_copy",
     "gmg_jacobi", "gmg_gauss_seidel", "gmg_boundary_jacobi", "gmg_apply", "gmg_residual", "gmg_restrict", "gmg_prolong_add", "gmg_dot", "gmg_norm2", "gmg_inf_norm",
     "gmg_axpy", "gmg_add_scaled", "gmg_scale", "gmg_vcycle_device", "gmg_pcg_device", "gmg_launch_count", "gmg_timer_begin", "gmg_timer_end",
+    "gmg_build_domain_labels", "gmg_build_boundary_weights", "gmg_build_rhs", "gmg_apply_old_pressure", "gmg_apply_solution_to_pressure", "gmg_apply_pressure_gradient",
     "gmg_profile_enable", "gmg_kernel_class_count", "gmg_kernel_class_name", "gmg_profile_get", "gmg_profile_reset", "gmg_profile_get_level",
 ]
 
@@ -283,6 +284,72 @@ class Context:
         out = np.empty((max(n.value, 1), 3), dtype=np.int64)
         _check(self.lib.gmg_boundary_cells(self.h, lp, _res(l.shape), int(width), out.ctypes.data_as(_i64p), C.byref(n)))
         return out[: n.value]
+
+    # ---- the steps either side of the solve (GFS.cpp:746-1131; base-grid fields, fpreal32 like SIM_RawField) --------------
+    @staticmethod
+    def _f32(a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def buildMGDomainLabels(self, material):
+        """GFS.cpp:746-793: LIQUID (1) -> INTERIOR, AIR (2) -> DIRICHLET, else EXTERIOR."""
+        m, mp = _i32(material)
+        out = np.empty(m.shape, dtype=np.int32)
+        _check(self.lib.gmg_build_domain_labels(self.h, mp, _res(m.shape), out.ctypes.data_as(_i32p)))
+        return out
+
+    def buildMGBoundaryWeights(self, cutCell, liquidSurface, validFaces, domainLabels, axis):
+        """GFS.cpp:796-865 for one axis."""
+        l, lp = _i32(domainLabels)
+        cc, ccp = self._f32(cutCell)
+        ls, lsp = self._f32(liquidSurface)
+        vf, vfp = self._f32(validFaces)
+        assert cc.shape == face_shape(l.shape, axis) and vf.shape == cc.shape and ls.shape == l.shape
+        out = np.empty(cc.shape, dtype=np.float64)
+        _check(self.lib.gmg_build_boundary_weights(self.h, ccp, lsp, vfp, lp, _res(l.shape), int(axis), out.ctypes.data_as(_f64p)))
+        return out
+
+    def _field_ptrs(self, fields):
+        keep = [self._f32(f) for f in fields]
+        return keep, (C.POINTER(C.c_float) * 3)(*[k[1] for k in keep])
+
+    def buildRHS(self, material, velocity, cutCell, exp_shape, offset, solidVelocity=None):
+        """GFS.cpp:868-943: the expanded rhs grid (zero off the LIQUID cells)."""
+        m, mp = _i32(material)
+        kv, vp = self._field_ptrs(velocity)
+        kc, cp = self._field_ptrs(cutCell)
+        sp = None
+        if solidVelocity is not None:
+            ks, sp = self._field_ptrs(solidVelocity)
+        rhs = np.zeros(exp_shape, dtype=np.float64)
+        _check(self.lib.gmg_build_rhs(self.h, mp, vp, cp, sp, _res(m.shape), _res(exp_shape), _vec3(offset), rhs.ctypes.data_as(_f64p)))
+        return rhs
+
+    def applyOldPressure(self, pressure, material, exp_shape, offset):
+        """GFS.cpp:946-997: the warm-start solution grid."""
+        m, mp = _i32(material)
+        p, pp = self._f32(pressure)
+        x = np.zeros(exp_shape, dtype=np.float64)
+        _check(self.lib.gmg_apply_old_pressure(self.h, pp, mp, _res(m.shape), _res(exp_shape), _vec3(offset), x.ctypes.data_as(_f64p)))
+        return x
+
+    def applySolutionToPressure(self, pressure, material, solution, offset):
+        """GFS.cpp:1000-1047: returns the updated fpreal32 pressure field."""
+        m, mp = _i32(material)
+        p, pp = self._f32(np.array(pressure, dtype=np.float32, copy=True))
+        x, xp = _f64(solution)
+        _check(self.lib.gmg_apply_solution_to_pressure(self.h, pp, mp, xp, _res(m.shape), _res(x.shape), _vec3(offset)))
+        return p
+
+    def applyPressureGradient(self, velocity, liquidSurface, pressure, validFaces, material, axis):
+        """GFS.cpp:1050-1131 for one axis: returns the updated fpreal32 face velocities."""
+        m, mp = _i32(material)
+        v, vp = self._f32(np.array(velocity, dtype=np.float32, copy=True))
+        ls, lsp = self._f32(liquidSurface)
+        p, pp = self._f32(pressure)
+        vf, vfp = self._f32(validFaces)
+        _check(self.lib.gmg_apply_pressure_gradient(self.h, vp, lsp, pp, vfp, mp, _res(m.shape), int(axis)))
+        return v
 
     def buildExpandedDomainLazy(self, base_labels, base_weights):
         """buildExpandedDomain for large grids: the expanded arrays come from np.zeros and only the base box is ever written,

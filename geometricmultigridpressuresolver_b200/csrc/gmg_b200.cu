@@ -17,6 +17,7 @@
 
 #include "gmg_kernels.cuh"
 #include "gmg_cluster.cuh"
+#include "gmg_frontend.cuh"
 #include "gmg_nccl.h"
 #include "gmg_p2p.cuh"
 
@@ -1222,9 +1223,12 @@ static int buildChunks(gmg_ctx *ctx, Level &L)
 static int tmaMode()
 {
     // read at solver creation; a bit mask of the kernels that take the TMA-staged variant on big levels: 1 interior Jacobi,
-    // 2 residual, 4 apply, 8 restriction, 16 prolongation; GMG_TMA=0 forces the plain-load kernels everywhere
+    // 2 residual, 4 apply, 8 restriction, 16 prolongation; GMG_TMA=0 forces the plain-load kernels everywhere.
+    // Default 23 = all but the restriction.  Measured 512^3 V-cycle, 30 steps (profiles/r02_tma_ab.md): none 5.30 ms, Jacobi
+    // 5.22, residual 5.27, prolongation 5.20, those three 5.09; the TMA restriction alone 6.04 -- shared-memory-bound on its
+    // 48 loads per coarse cell (ncu: mio_throttle), no faster than k_restrict by itself and slower in the pipeline.
     const char *e = getenv("GMG_TMA");
-    return e ? atoi(e) : 31;
+    return e ? atoi(e) : 23;
 }
 static int buildBricks(gmg_ctx *ctx, Level &L)
 {
@@ -3966,4 +3970,190 @@ extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, in
     GMG_TRY(pcgDevice(s, s->pcgX, s->pcgB, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount));
     const Geom go = ownedGeom(s->lv[0]);
     return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, false, s->hostBounds, &s->ioGroups, s->lv[0].ownLo);
+}
+
+
+// ====================================================================================================
+// the steps either side of the solve (gmg_frontend.cuh).  Host arrays in and out, like the builders above.
+// ====================================================================================================
+namespace
+{
+struct DevBuf
+{
+    void *p = nullptr;
+    ~DevBuf() { if (p) devFree(p); }
+    template <typename T>
+    T *as() { return static_cast<T *>(p); }
+};
+template <typename T>
+int devUpload(gmg_ctx *ctx, DevBuf &b, const T *host, int64_t n)
+{
+    GMG_CUDA(devMalloc(&b.p, sizeof(T) * size_t(std::max<int64_t>(n, 1))));
+    if (host) GMG_CUDA(cudaMemcpyAsync(b.p, host, sizeof(T) * size_t(n), cudaMemcpyHostToDevice, ctx->stream));
+    return GMG_OK;
+}
+int64_t cellsOf(const int64_t r[3]) { return r[0] * r[1] * r[2]; }
+int64_t facesOf(const int64_t r[3], int axis) { return cellsOf(r) / r[axis] * (r[axis] + 1); }
+BaseBox baseBox(const int64_t res[3], const int64_t *expRes, const int64_t *offset)
+{
+    BaseBox g;
+    for (int a = 0; a < 3; ++a) { g.r[a] = res[a]; g.e[a] = expRes ? expRes[a] : res[a]; g.o[a] = offset ? offset[a] : 0; }
+    return g;
+}
+} // namespace
+
+extern "C" int gmg_build_domain_labels(gmg_ctx *ctx, const int32_t *material, const int64_t res[3], int32_t *labels)
+{
+    if (!ctx || !material || !res || !labels) return invalid("gmg_build_domain_labels: null argument");
+    GMG_CUDA(enterCtx(ctx));
+    const int64_t n = cellsOf(res);
+    DevBuf m, l;
+    GMG_TRY(devUpload(ctx, m, material, n));
+    GMG_TRY(devUpload<int32_t>(ctx, l, nullptr, n));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_fe_domain_labels<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(l.as<int32_t>(), m.as<int32_t>(), n);
+    }
+    GMG_CUDA(cudaMemcpyAsync(labels, l.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
+}
+
+extern "C" int gmg_build_boundary_weights(gmg_ctx *ctx, const float *cutCell, const float *liquidSurface, const float *validFaces, const int32_t *domainLabels,
+					  const int64_t res[3], int axis, double *weights)
+{
+    if (!ctx || !cutCell || !liquidSurface || !validFaces || !domainLabels || !res || !weights || axis < 0 || axis > 2) return invalid("gmg_build_boundary_weights: bad argument");
+    GMG_CUDA(enterCtx(ctx));
+    const int64_t n = cellsOf(res), nf = facesOf(res, axis);
+    DevBuf cc, ls, vf, dl, w;
+    GMG_TRY(devUpload(ctx, cc, cutCell, nf));
+    GMG_TRY(devUpload(ctx, ls, liquidSurface, n));
+    GMG_TRY(devUpload(ctx, vf, validFaces, nf));
+    GMG_TRY(devUpload(ctx, dl, domainLabels, n));
+    GMG_TRY(devUpload<double>(ctx, w, nullptr, nf));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_fe_boundary_weights<<<unsigned(divUp(nf, BLOCK)), BLOCK, 0, ctx->stream>>>(w.as<double>(), cc.as<float>(), ls.as<float>(), vf.as<float>(), dl.as<int32_t>(),
+										     baseBox(res, nullptr, nullptr), axis);
+    }
+    GMG_CUDA(cudaMemcpyAsync(weights, w.p, sizeof(double) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
+}
+
+// rhs / solution: expanded host grids, written on the LIQUID cells only (pass them zero-filled, like the reference's
+// rhsGrid.constant(0), GFS.cpp:385): only the base box travels
+static int expandedBoxIO(gmg_ctx *ctx, double *host, double *dev, const BaseBox &g, bool toDevice)
+{
+    cudaMemcpy3DParms p = {};
+    const cudaPitchedPtr hp = make_cudaPitchedPtr(host, size_t(g.e[0]) * sizeof(double), size_t(g.e[0]) * sizeof(double), size_t(g.e[1]));
+    const cudaPitchedPtr dp = make_cudaPitchedPtr(dev, size_t(g.e[0]) * sizeof(double), size_t(g.e[0]) * sizeof(double), size_t(g.e[1]));
+    const cudaPos pos = make_cudaPos(size_t(g.o[0]) * sizeof(double), size_t(g.o[1]), size_t(g.o[2]));
+    p.srcPtr = toDevice ? hp : dp;
+    p.dstPtr = toDevice ? dp : hp;
+    p.srcPos = pos;
+    p.dstPos = pos;
+    p.extent = make_cudaExtent(size_t(g.r[0]) * sizeof(double), size_t(g.r[1]), size_t(g.r[2]));
+    p.kind = toDevice ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    GMG_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    return GMG_OK;
+}
+
+extern "C" int gmg_build_rhs(gmg_ctx *ctx, const int32_t *material, const float *const velocity[3], const float *const cutCell[3],
+			     const float *const solidVelocity[3], const int64_t res[3], const int64_t expRes[3], const int64_t offset[3], double *rhs)
+{
+    if (!ctx || !material || !velocity || !cutCell || !res || !expRes || !offset || !rhs) return invalid("gmg_build_rhs: null argument");
+    GMG_CUDA(enterCtx(ctx));
+    const int64_t n = cellsOf(res);
+    const BaseBox g = baseBox(res, expRes, offset);
+    DevBuf m, r, v[3], c[3], sv[3];
+    FeFields fl;
+    GMG_TRY(devUpload(ctx, m, material, n));
+    for (int a = 0; a < 3; ++a)
+    {
+	if (!velocity[a] || !cutCell[a]) return invalid("gmg_build_rhs: null field");
+	GMG_TRY(devUpload(ctx, v[a], velocity[a], facesOf(res, a)));
+	GMG_TRY(devUpload(ctx, c[a], cutCell[a], facesOf(res, a)));
+	fl.velocity[a] = v[a].as<float>();
+	fl.cutCell[a] = c[a].as<float>();
+	fl.solidVelocity[a] = nullptr;
+	if (solidVelocity && solidVelocity[a])
+	{
+	    GMG_TRY(devUpload(ctx, sv[a], solidVelocity[a], facesOf(res, a)));
+	    fl.solidVelocity[a] = sv[a].as<float>();
+	}
+    }
+    GMG_TRY(devUpload<double>(ctx, r, nullptr, g.e[0] * g.e[1] * g.e[2]));
+    GMG_TRY(expandedBoxIO(ctx, rhs, r.as<double>(), g, true));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_fe_rhs<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(r.as<double>(), m.as<int32_t>(), fl, g);
+    }
+    GMG_TRY(expandedBoxIO(ctx, rhs, r.as<double>(), g, false));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
+}
+
+extern "C" int gmg_apply_old_pressure(gmg_ctx *ctx, const float *pressure, const int32_t *material, const int64_t res[3], const int64_t expRes[3],
+				      const int64_t offset[3], double *solution)
+{
+    if (!ctx || !pressure || !material || !res || !expRes || !offset || !solution) return invalid("gmg_apply_old_pressure: null argument");
+    GMG_CUDA(enterCtx(ctx));
+    const int64_t n = cellsOf(res);
+    const BaseBox g = baseBox(res, expRes, offset);
+    DevBuf m, pr, x;
+    GMG_TRY(devUpload(ctx, m, material, n));
+    GMG_TRY(devUpload(ctx, pr, pressure, n));
+    GMG_TRY(devUpload<double>(ctx, x, nullptr, g.e[0] * g.e[1] * g.e[2]));
+    GMG_TRY(expandedBoxIO(ctx, solution, x.as<double>(), g, true));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_fe_old_pressure<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(x.as<double>(), pr.as<float>(), m.as<int32_t>(), g);
+    }
+    GMG_TRY(expandedBoxIO(ctx, solution, x.as<double>(), g, false));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
+}
+
+extern "C" int gmg_apply_solution_to_pressure(gmg_ctx *ctx, float *pressure, const int32_t *material, const double *solution, const int64_t res[3],
+					      const int64_t expRes[3], const int64_t offset[3])
+{
+    if (!ctx || !pressure || !material || !solution || !res || !expRes || !offset) return invalid("gmg_apply_solution_to_pressure: null argument");
+    GMG_CUDA(enterCtx(ctx));
+    const int64_t n = cellsOf(res);
+    const BaseBox g = baseBox(res, expRes, offset);
+    DevBuf m, pr, x;
+    GMG_TRY(devUpload(ctx, m, material, n));
+    GMG_TRY(devUpload(ctx, pr, pressure, n));
+    GMG_TRY(devUpload<double>(ctx, x, nullptr, g.e[0] * g.e[1] * g.e[2]));
+    GMG_TRY(expandedBoxIO(ctx, const_cast<double *>(solution), x.as<double>(), g, true));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_fe_solution_to_pressure<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(pr.as<float>(), x.as<double>(), m.as<int32_t>(), g);
+    }
+    GMG_CUDA(cudaMemcpyAsync(pressure, pr.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
+}
+
+extern "C" int gmg_apply_pressure_gradient(gmg_ctx *ctx, float *velocity, const float *liquidSurface, const float *pressure, const float *validFaces,
+					   const int32_t *material, const int64_t res[3], int axis)
+{
+    if (!ctx || !velocity || !liquidSurface || !pressure || !validFaces || !material || !res || axis < 0 || axis > 2) return invalid("gmg_apply_pressure_gradient: bad argument");
+    GMG_CUDA(enterCtx(ctx));
+    const int64_t n = cellsOf(res), nf = facesOf(res, axis);
+    DevBuf v, ls, pr, vf, m;
+    GMG_TRY(devUpload(ctx, v, velocity, nf));
+    GMG_TRY(devUpload(ctx, ls, liquidSurface, n));
+    GMG_TRY(devUpload(ctx, pr, pressure, n));
+    GMG_TRY(devUpload(ctx, vf, validFaces, nf));
+    GMG_TRY(devUpload(ctx, m, material, n));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_fe_pressure_gradient<<<unsigned(divUp(nf, BLOCK)), BLOCK, 0, ctx->stream>>>(v.as<float>(), ls.as<float>(), pr.as<float>(), vf.as<float>(), m.as<int32_t>(),
+										      baseBox(res, nullptr, nullptr), axis);
+    }
+    GMG_CUDA(cudaMemcpyAsync(velocity, v.p, sizeof(float) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
 }

@@ -222,7 +222,7 @@ struct gmg_solver
     };
     std::map<std::tuple<int, const void *, const void *, int>, GraphEntry> graphs;
     std::map<std::pair<int, const double *>, gmg::TmaMap> tensorMaps;  // (level, grid) -> tensor map of the TMA stencil kernels
-    int tmaMask = 31;             // which full-grid kernels take the TMA-staged variant on big levels (GMG_TMA, see tmaMode)
+    int tmaMask = 23;             // which full-grid kernels take the TMA-staged variant on big levels (GMG_TMA, see tmaMode)
     bool useGraphs = true;
     bool bandGroups = false;      // a group of band sweeps as ONE co-resident launch with grid barriers: measured SLOWER than a launch per sweep
 				  // (profiles/r02_ab_switches.md: 256^3 solve 11.5 vs 10.3 ms; a barrier over ~900 CTAs costs more than a kernel

@@ -203,6 +203,32 @@ int gmg_vcycle_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, int useInit
 int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, double tol, int maxIt, int preconditioner,
 		   int *iterations, double *relResHistory, int histCap, int *histCount);
 
+/* ---- the steps either side of the solve ------------------------------------------------------------
+ * The pointwise builders of HDK_GeometricFreeSurfacePressureSolver.cpp that turn the simulation's fields into this path's
+ * inputs and its output back into them, on the BASE grid (res = the simulation's cell resolution; cell fields x-fastest, the
+ * face field of axis a has one more entry along a).  SIM_RawField values are fpreal32, hence `float`; material labels are the
+ * enum of HDK_Utilities.h:17 { SOLID = 0, LIQUID = 1, AIR = 2 } as int32; a face is valid where validFaces == 1
+ * (HDK_Utilities.h:21).  rhs / solution are the EXPANDED fp64 grids of the solve (expRes, offset from gmg_expand_dims). */
+/* buildMGDomainLabels, GFS.cpp:746-793: LIQUID -> INTERIOR, AIR -> DIRICHLET, else EXTERIOR */
+int gmg_build_domain_labels(gmg_ctx *ctx, const int32_t *material, const int64_t res[3], int32_t *labels);
+/* buildMGBoundaryWeights, GFS.cpp:796-865, one axis: the cut-cell weight on valid faces, divided by the clamped ghost-fluid
+ * theta (HDK_Utilities.h:25-42) on a liquid/air face; 0 elsewhere */
+int gmg_build_boundary_weights(gmg_ctx *ctx, const float *cutCell, const float *liquidSurface, const float *validFaces,
+			       const int32_t *domainLabels, const int64_t res[3], int axis, double *weights);
+/* buildRHS, GFS.cpp:868-943: cut-cell divergence of every LIQUID cell, written into the expanded rhs grid (other cells are left
+ * as they are: pass it zero-filled like the reference's rhsGrid.constant(0)).  solidVelocity: NULL, or per axis the solid's
+ * velocity already sampled at the face centres (the reference samples a SIM_VectorField there, GFS.cpp:918-921). */
+int gmg_build_rhs(gmg_ctx *ctx, const int32_t *material, const float *const velocity[3], const float *const cutCell[3],
+		  const float *const solidVelocity[3], const int64_t res[3], const int64_t expRes[3], const int64_t offset[3], double *rhs);
+/* applyOldPressure, GFS.cpp:946-997 (the warm start) and applySolutionToPressure, GFS.cpp:1000-1047 */
+int gmg_apply_old_pressure(gmg_ctx *ctx, const float *pressure, const int32_t *material, const int64_t res[3], const int64_t expRes[3],
+			   const int64_t offset[3], double *solution);
+int gmg_apply_solution_to_pressure(gmg_ctx *ctx, float *pressure, const int32_t *material, const double *solution, const int64_t res[3],
+				   const int64_t expRes[3], const int64_t offset[3]);
+/* applyPressureGradient, GFS.cpp:1050-1131, one axis: velocity -= grad p on valid faces, ghost-fluid scaled at the free surface */
+int gmg_apply_pressure_gradient(gmg_ctx *ctx, float *velocity, const float *liquidSurface, const float *pressure, const float *validFaces,
+				const int32_t *material, const int64_t res[3], int axis);
+
 /* ---- measurement hooks ----------------------------------------------------------------------------- */
 /* kernels launched by this library on this context since the last reset (bench.py's gpu_launches) */
 int gmg_launch_count(gmg_ctx *ctx, int64_t *count, int reset);

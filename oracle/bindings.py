@@ -320,6 +320,65 @@ class PortLib(_Base):
     def __init__(self):
         super().__init__(PORT_SO)
 
+    # ---- restatement of the steps either side of the solve (GFS.cpp:746-1131; parity unpinned, see gmg_oracle.c) -------
+    @staticmethod
+    def _f32(a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def _ptrs3(self, fields):
+        keep = [self._f32(f) for f in fields]
+        return keep, (C.POINTER(C.c_float) * 3)(*[k[1] for k in keep])
+
+    def build_domain_labels(self, material):
+        m, mp = _i32(material)
+        out = np.empty(m.shape, dtype=np.int32)
+        self.fn("build_domain_labels", None)(mp, _res(m), out.ctypes.data_as(_i32p))
+        return out
+
+    def build_boundary_weights(self, cut_cell, liquid_surface, valid_faces, domain_labels, axis):
+        l, lp = _i32(domain_labels)
+        cc, ccp = self._f32(cut_cell)
+        ls, lsp = self._f32(liquid_surface)
+        vf, vfp = self._f32(valid_faces)
+        out = np.empty(cc.shape, dtype=np.float64)
+        self.fn("build_boundary_weights", None)(ccp, lsp, vfp, lp, _res(l), int(axis), out.ctypes.data_as(_f64p))
+        return out
+
+    def build_rhs(self, material, velocity, cut_cell, exp_shape, offset, solid_velocity=None):
+        m, mp = _i32(material)
+        kv, vp = self._ptrs3(velocity)
+        kc, cp = self._ptrs3(cut_cell)
+        sp = None
+        if solid_velocity is not None:
+            ks, sp = self._ptrs3(solid_velocity)
+        rhs = np.zeros(exp_shape, dtype=np.float64)
+        self.fn("build_rhs", None)(mp, vp, cp, sp, _res(m), _res_t(tuple(exp_shape)[::-1]), _res_t(offset), rhs.ctypes.data_as(_f64p))
+        return rhs
+
+    def apply_old_pressure(self, pressure, material, exp_shape, offset):
+        m, mp = _i32(material)
+        p, pp = self._f32(pressure)
+        x = np.zeros(exp_shape, dtype=np.float64)
+        self.fn("apply_old_pressure", None)(pp, mp, _res(m), _res_t(tuple(exp_shape)[::-1]), _res_t(offset), x.ctypes.data_as(_f64p))
+        return x
+
+    def apply_solution_to_pressure(self, pressure, material, solution, offset):
+        m, mp = _i32(material)
+        p, pp = self._f32(np.array(pressure, dtype=np.float32, copy=True))
+        x, xp = _f64(solution)
+        self.fn("apply_solution_to_pressure", None)(pp, mp, xp, _res(m), _res(x), _res_t(offset))
+        return p
+
+    def apply_pressure_gradient(self, velocity, liquid_surface, pressure, valid_faces, material, axis):
+        m, mp = _i32(material)
+        v, vp = self._f32(np.array(velocity, dtype=np.float32, copy=True))
+        ls, lsp = self._f32(liquid_surface)
+        p, pp = self._f32(pressure)
+        vf, vfp = self._f32(valid_faces)
+        self.fn("apply_pressure_gradient", None)(vp, None, lsp, pp, vfp, mp, _res(m), int(axis))
+        return v
+
     def threads(self):
         return int(self.fn("threads")())
 

@@ -941,3 +941,142 @@ static int pcg_impl(OrcSolver *s, double *x, const double *b, double tol, int ma
     free(r); free(p); free(z); free(t); free(dinv);
     return iteration;
 }
+
+/* =====================================================================================================================
+ * The steps either side of the path: HDK_GeometricFreeSurfacePressureSolver.cpp builds the solver's
+ * inputs from the simulation's fields and applies its output to them.  PARITY UNPINNED: that file needs live SIM fields
+ * (SIM_RawField, SIM_RawIndexField, SIM_VectorField) and cannot be compiled here, even against the shim, so what follows is
+ * a restatement only, function by function, on plain arrays: cell fields [rz][ry][rx] x-fastest, the face field of axis a
+ * has one more entry along a, SIM_RawField values are fpreal32 (float) and the arithmetic is SolveReal = double
+ * (GFS.h:18-19).  Assumption where the HDK's own return types matter: SIM::FieldUtils::getFieldValue returns the field's
+ * fpreal32, so pressure(forward) - pressure(backward) (GFS.cpp:1095) is a float subtraction.
+ * Material labels: HDK_Utilities.h:17 { SOLID_CELL = 0, LIQUID_CELL = 1, AIR_CELL = 2 }; VALID_FACE = 1 (HDK_Utilities.h:21).
+ * ===================================================================================================================== */
+enum { MAT_SOLID = 0, MAT_LIQUID = 1, MAT_AIR = 2 };
+
+/* HDK_Utilities.h:25-42 */
+static inline double ghost_fluid_weight(double phi0, double phi1)
+{
+    double theta = 0;
+    if (phi0 < 0)
+    {
+	if (phi1 < 0) theta = 1;
+	else if (phi1 >= 0) theta = phi0 / (phi0 - phi1);
+    }
+    else if (phi1 < 0) theta = phi1 / (phi1 - phi0);
+    return theta;
+}
+static inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* GFS.cpp:746-793 buildMGDomainLabels: LIQUID -> INTERIOR, AIR -> DIRICHLET, everything else stays EXTERIOR (GFS.cpp:309) */
+void orc_build_domain_labels(const int *material, const i64 res[3], int *labels)
+{
+    const i64 n = cells_of(res);
+    for (i64 i = 0; i < n; ++i)
+	labels[i] = material[i] == MAT_LIQUID ? INTERIOR_CELL : (material[i] == MAT_AIR ? DIRICHLET_CELL : EXTERIOR_CELL);
+}
+
+/* GFS.cpp:796-865 buildMGBoundaryWeights for one axis: weights[face] = 0 (GFS.cpp:322), then on VALID faces the cut-cell
+ * weight, divided by the clamped ghost-fluid theta on a liquid/air face */
+void orc_build_boundary_weights(const float *cutCell, const float *liquidSurface, const float *validFaces, const int *domainLabels, const i64 res[3],
+				int axis, double *weights)
+{
+    i64 fr[3] = {res[0], res[1], res[2]};
+    ++fr[axis];
+    for (i64 z = 0; z < fr[2]; ++z)
+	for (i64 y = 0; y < fr[1]; ++y)
+	    for (i64 x = 0; x < fr[0]; ++x)
+	    {
+		const i64 f = lin(fr, x, y, z);
+		weights[f] = 0;
+		if (validFaces[f] != 1.0f) continue;
+		double weight = cutCell[f];
+		i64 b[3] = {x, y, z}, fw[3] = {x, y, z};
+		--b[axis];  /* faceToCellMap(face, axis, 0) */
+		const int bl = label_at(domainLabels, res, b[0], b[1], b[2]), fl = label_at(domainLabels, res, fw[0], fw[1], fw[2]);
+		if ((bl == INTERIOR_CELL && fl == DIRICHLET_CELL) || (bl == DIRICHLET_CELL && fl == INTERIOR_CELL))
+		{
+		    const double phi0 = liquidSurface[lin(res, b[0], b[1], b[2])], phi1 = liquidSurface[lin(res, fw[0], fw[1], fw[2])];
+		    double theta = ghost_fluid_weight(phi0, phi1);
+		    theta = clampd(theta, .01, 1.);
+		    weight /= theta;
+		}
+		weights[f] = weight;
+	    }
+}
+
+/* GFS.cpp:868-943 buildRHS: cut-cell divergence of every LIQUID cell into the expanded rhs grid.  solidVelocity (nullable)
+ * holds the solid's velocity component already sampled at every face centre of the axis (the reference samples a
+ * SIM_VectorField at the face position, GFS.cpp:918-921: an HDK interpolation that is not restated). */
+void orc_build_rhs(const int *material, const float *const velocity[3], const float *const cutCell[3], const float *const solidVelocity[3], const i64 res[3],
+		   const i64 expRes[3], const i64 offset[3], double *rhs)
+{
+    for (i64 z = 0; z < res[2]; ++z)
+	for (i64 y = 0; y < res[1]; ++y)
+	    for (i64 x = 0; x < res[0]; ++x)
+	    {
+		if (material[lin(res, x, y, z)] != MAT_LIQUID) continue;
+		double divergence = 0;
+		for (int axis = 0; axis < 3; ++axis)
+		    for (int direction = 0; direction < 2; ++direction)
+		    {
+			i64 fr[3] = {res[0], res[1], res[2]};
+			++fr[axis];
+			i64 fc[3] = {x, y, z};
+			fc[axis] += direction;  /* cellToFaceMap */
+			const i64 f = lin(fr, fc[0], fc[1], fc[2]);
+			const double sign = (direction == 0) ? 1. : -1.;
+			const double weight = cutCell[axis][f];
+			if (weight > 0) divergence += sign * weight * velocity[axis][f];
+			if (solidVelocity && weight < 1) divergence += sign * (1. - weight) * solidVelocity[axis][f];
+		    }
+		rhs[lin(expRes, x + offset[0], y + offset[1], z + offset[2])] = divergence;
+	    }
+}
+
+/* GFS.cpp:946-997 applyOldPressure: the warm start */
+void orc_apply_old_pressure(const float *pressure, const int *material, const i64 res[3], const i64 expRes[3], const i64 offset[3], double *solution)
+{
+    for (i64 z = 0; z < res[2]; ++z)
+	for (i64 y = 0; y < res[1]; ++y)
+	    for (i64 x = 0; x < res[0]; ++x)
+		if (material[lin(res, x, y, z)] == MAT_LIQUID) solution[lin(expRes, x + offset[0], y + offset[1], z + offset[2])] = pressure[lin(res, x, y, z)];
+}
+
+/* GFS.cpp:1000-1047 applySolutionToPressure (the pressure field is fpreal32: the store rounds) */
+void orc_apply_solution_to_pressure(float *pressure, const int *material, const double *solution, const i64 res[3], const i64 expRes[3], const i64 offset[3])
+{
+    for (i64 z = 0; z < res[2]; ++z)
+	for (i64 y = 0; y < res[1]; ++y)
+	    for (i64 x = 0; x < res[0]; ++x)
+		if (material[lin(res, x, y, z)] == MAT_LIQUID) pressure[lin(res, x, y, z)] = (float)solution[lin(expRes, x + offset[0], y + offset[1], z + offset[2])];
+}
+
+/* GFS.cpp:1050-1131 applyPressureGradient for one axis */
+void orc_apply_pressure_gradient(float *velocity, const float *cutCell, const float *liquidSurface, const float *pressure, const float *validFaces,
+				 const int *material, const i64 res[3], int axis)
+{
+    (void)cutCell; /* only asserted > 0 (GFS.cpp:1093) */
+    i64 fr[3] = {res[0], res[1], res[2]};
+    ++fr[axis];
+    for (i64 z = 0; z < fr[2]; ++z)
+	for (i64 y = 0; y < fr[1]; ++y)
+	    for (i64 x = 0; x < fr[0]; ++x)
+	    {
+		const i64 f = lin(fr, x, y, z);
+		if (validFaces[f] != 1.0f) continue;
+		i64 b[3] = {x, y, z}, fw[3] = {x, y, z};
+		--b[axis];
+		if (b[axis] < 0 || fw[axis] >= res[axis]) continue;
+		const i64 bi = lin(res, b[0], b[1], b[2]), fi = lin(res, fw[0], fw[1], fw[2]);
+		const int bm = material[bi], fm = material[fi];
+		double gradient = (float)(pressure[fi] - pressure[bi]);
+		if (bm != MAT_LIQUID || fm != MAT_LIQUID)
+		{
+		    double theta = ghost_fluid_weight(liquidSurface[bi], liquidSurface[fi]);
+		    theta = clampd(theta, .01, 1.);
+		    gradient /= theta;
+		}
+		velocity[f] = (float)(velocity[f] - gradient);
+	    }
+}
