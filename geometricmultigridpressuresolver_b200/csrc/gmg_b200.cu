@@ -1856,6 +1856,30 @@ static int planShards(gmg_solver *s)
 	L.nInterior = nI;
 	L.nActive = nI + nB;
     }
+    // rows of a plane that hold an active cell anywhere in the level (global labels: identical on every rank): the halo
+    // exchange moves only those (haloExchange / k_halo_p2p)
+    for (int l = 0; l < S; ++l)
+    {
+	Level &L = s->lv[l];
+	const int nzG = L.gg.n[2];
+	int4 *d = nullptr;
+	GMG_CUDA(devMalloc(&d, sizeof(int4) * nzG));
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_plane_extents<<<nzG, BLOCK, 0, ctx->stream>>>(d, L.labelsAlloc, L.gg.n[0], L.gg.n[1], L.gg.pitch, L.gg.plane);
+	}
+	std::vector<int4> e(nzG);
+	GMG_CUDA(cudaMemcpyAsync(e.data(), d, sizeof(int4) * nzG, cudaMemcpyDeviceToHost, ctx->stream));
+	GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+	GMG_CUDA(devFree(d));
+	int y0 = L.gg.n[1], y1 = 0;
+	for (const int4 &q : e)
+	    if (q.y > q.x) { y0 = std::min(y0, q.z); y1 = std::max(y1, q.w); }
+	if (y1 <= y0) { y0 = 0; y1 = L.gg.n[1]; }
+	static const bool whole = [] { const char *e = getenv("GMG_HALO_ROWS"); return e && e[0] == '0'; }();
+	L.rowLo = whole ? 0 : y0;
+	L.rowHi = whole ? L.gg.n[1] : y1;
+    }
     // fine -> coarse storage relation between the LOCAL boxes
     for (int l = 0; l + 1 < nl; ++l)
 	for (int a = 0; a < 3; ++a) s->lv[l].shift[a] = s->lv[l].g.org[a] / 2 - s->lv[l + 1].g.org[a];
@@ -2037,6 +2061,8 @@ static int haloExchange(gmg_solver *s, int level, double *p, int depth)
 	const P2pLayout &lay = st->layout;
 	HaloP2pArgs a;
 	a.grid = p; a.plane = L.g.plane; a.ownLo = L.ownLo; a.ownHi = L.ownHi; a.depth = depth;
+	a.segOff = int64_t(L.rowLo) * L.g.pitch;
+	a.segLen = int64_t(L.rowHi - L.rowLo) * L.g.pitch;
 	a.hasLower = rank > 0; a.hasUpper = rank < world - 1;
 	a.slotStride = int64_t((lay.halo[level][0][1] - lay.halo[level][0][0]) / sizeof(double));
 	unsigned long long *myFlags = reinterpret_cast<unsigned long long *>(st->arena + lay.flags);
@@ -2057,8 +2083,9 @@ static int haloExchange(gmg_solver *s, int level, double *p, int depth)
 	    a.flagOnUpper = reinterpret_cast<unsigned long long *>(st->peer[rank + 1] + lay.flags) + P2P_FLAG_HALO + (level * 2 + 0) * 2;
 	}
 	a.seq = st->seq + level; a.tickets = st->tickets; a.error = st->error;
-	// small messages: fewer CTAs meet at the tickets and poll the flags (one CTA per 64 KB, at least 8)
-	const unsigned ctas = unsigned(std::max<size_t>(8, std::min<size_t>(P2P_CTAS, cnt * sizeof(double) / 65536)));
+	// small messages: fewer CTAs meet at the tickets and poll the flags (one CTA per 8 KB of a direction's payload, at least 8)
+	const size_t payload = size_t(depth) * size_t(a.segLen) * sizeof(double);
+	const unsigned ctas = unsigned(std::max<size_t>(8, std::min<size_t>(P2P_CTAS, payload / 8192)));
 	k_halo_p2p<<<ctas, 256, 0, ctx->stream>>>(a);
 	GMG_CUDA(cudaGetLastError());
 	return GMG_OK;
@@ -3204,6 +3231,22 @@ static int launchGaussSeidel(gmg_solver *s, int level, double *x, const double *
     a.tilesX = L.gsTilesX; a.tilesY = L.gsTilesY;
     for (int k = 0; k < 3; ++k) { a.off[k] = L.gsOff[k]; a.n[k] = L.g.n[k]; }
     a.pitch = L.g.pitch; a.plane = L.g.plane; a.forward = forward ? 1 : 0;
+    static const bool v1 = [] { const char *e = getenv("GMG_GS_V1"); return e && e[0] == '1'; }();
+    if (!v1)
+    {
+	// records of the tile's BOUNDARY cells gathered into shared memory before the sweep (k_gauss_seidel2)
+	GsArgs2 a2;
+	a2.g = a;
+	a2.wcode = L.wcode;
+	const size_t smem2 = sizeof(double) * (GS_HALO * GS_HALO * GS_HALO + GS_TILE * GS_TILE * GS_TILE + GS_POOL) + sizeof(unsigned short) * (GS_POOL + GS_TILE * GS_TILE * GS_TILE) +
+			     GS_TILE * GS_TILE * GS_TILE;
+	static bool attr2 = false;
+	if (!attr2) { GMG_CUDA(cudaFuncSetAttribute(k_gauss_seidel2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2))); attr2 = true; }
+	GMG_LAUNCH(s->ctx, KC_GS, double(L.nActive) * 25.0 * 0.5);
+	GMG_CUDA(launchK(k_gauss_seidel2, unsigned(n), unsigned(BLOCK), size_t(smem2), s->ctx->stream, a2));
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     const size_t smem = sizeof(double) * (GS_HALO * GS_HALO * GS_HALO + GS_TILE * GS_TILE * GS_TILE) + GS_TILE * GS_TILE * GS_TILE;
     static bool attr = false;
     if (!attr) { GMG_CUDA(cudaFuncSetAttribute(k_gauss_seidel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }

@@ -75,6 +75,7 @@ struct Level
     bool sharded = false;
     int zOff = 0;                // local plane 0 is global storage plane zOff (even)
     int ownLo = 0, ownHi = 0;    // owned planes [ownLo, ownHi) in local storage coordinates
+    int rowLo = 0, rowHi = 0;    // sharded levels: rows [rowLo, rowHi) of a plane hold every active cell of the level (all a halo exchange moves)
     uint8_t *labelsAlloc = nullptr; // the level's labels over the GLOBAL box (every rank holds them; 1 byte per cell)
     uint8_t *labels = nullptr;   // = labelsAlloc + zOff * plane
     uint8_t *flagsAlloc = nullptr;  // band flags over the GLOBAL box (gmg_kernels.cuh: SM_JACOBI_ZERO): bit0 in band, bit1 next to it

@@ -1294,6 +1294,159 @@ __global__ void __launch_bounds__(BLOCK) k_gauss_seidel(const GsArgs a)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same half-pass with nothing but shared memory on the 46-step critical path.  k_gauss_seidel above fetches a BOUNDARY
+// cell's record inside the wavefront step that updates it -- bpos[cell] -> coefficient rows, two dependent global round trips of
+// ~0.7 us each, paid by the whole CTA at the step's barrier -- so a tile on the free surface costs 46 x a few microseconds.
+// Here every record a tile needs is gathered BEFORE the sweep: each BOUNDARY cell of the tile takes a slot in a shared-memory
+// pool holding its diagonal and its 2-bit coefficient codes (k_band_coef: coefficient 0 / exactly 1 / fractional); a step is
+// then shared-memory loads, fp64 arithmetic and one barrier.  Fractional coefficients (rare: see coefCode) and pool overflow
+// still go to global memory.  Same arithmetic, same order: bitwise k_gauss_seidel.
+// ------------------------------------------------------------------------------------------------
+constexpr int GS_POOL = 1280;               // BOUNDARY records per tile held in shared memory (a 16 x 16 surface patch 3 cells thick is 768)
+constexpr unsigned short GS_SLOT_NONE = 0xffffu, GS_SLOT_OVERFLOW = 0xfffeu;
+
+struct GsArgs2
+{
+    GsArgs g;
+    const unsigned short *wcode;
+};
+
+__global__ void __launch_bounds__(BLOCK, 2) k_gauss_seidel2(const GsArgs2 p)
+{
+    pdlLaunch();
+    const GsArgs &a = p.g;
+    extern __shared__ double gsm[];
+    double *xs = gsm;                                                     // [18][18][18]
+    double *bs = xs + GS_HALO * GS_HALO * GS_HALO;                        // [16][16][16]
+    double *poolDiag = bs + GS_TILE * GS_TILE * GS_TILE;                  // [GS_POOL]
+    unsigned short *poolCode = reinterpret_cast<unsigned short *>(poolDiag + GS_POOL);  // [GS_POOL]
+    unsigned short *slot = poolCode + GS_POOL;                            // [16][16][16] pool slot of a BOUNDARY cell
+    uint8_t *ls = reinterpret_cast<uint8_t *>(slot + GS_TILE * GS_TILE * GS_TILE);      // [16][16][16]
+    __shared__ int poolCount;
+    const int t = a.tiles[blockIdx.x];
+    const int tz = t / (a.tilesX * a.tilesY), ty = (t - tz * a.tilesX * a.tilesY) / a.tilesX, tx = t - (tz * a.tilesY + ty) * a.tilesX;
+    const int ox = a.off[0] + tx * GS_TILE, oy = a.off[1] + ty * GS_TILE, oz = a.off[2] + tz * GS_TILE;
+    if (threadIdx.x == 0) poolCount = 0;
+    __syncthreads();
+    // prologue (static): labels, and the records of the tile's BOUNDARY cells into the pool
+    for (int i = threadIdx.x; i < GS_TILE * GS_TILE * GS_TILE; i += BLOCK)
+    {
+	const int lz = i >> 8, ly = (i >> 4) & 15, lx = i & 15;
+	const int gx = ox + lx, gy = oy + ly, gz = oz + lz;
+	uint8_t l = L_EXTERIOR;
+	unsigned short sl = GS_SLOT_NONE;
+	if (gx >= 0 && gy >= 0 && gz >= 0 && gx < a.n[0] && gy < a.n[1] && gz < a.n[2])
+	{
+	    const int64_t g = int64_t(gz) * a.plane + int64_t(gy) * a.pitch + gx;
+	    l = a.labels[g];
+	    if (l == L_BOUNDARY)
+	    {
+		const int k = a.bpos[g];
+		const int s0 = atomicAdd(&poolCount, 1);
+		if (s0 < GS_POOL)
+		{
+		    poolDiag[s0] = a.bcoef[int64_t(6) * a.nBoundary + k];
+		    poolCode[s0] = p.wcode[k];
+		    sl = (unsigned short)s0;
+		}
+		else sl = GS_SLOT_OVERFLOW;
+	    }
+	}
+	ls[i] = l;
+	slot[i] = sl;
+    }
+    pdlWait();
+    for (int i = threadIdx.x; i < GS_HALO * GS_HALO * GS_HALO; i += BLOCK)
+    {
+	const int lz = i / (GS_HALO * GS_HALO), ly = (i - lz * GS_HALO * GS_HALO) / GS_HALO, lx = i - (lz * GS_HALO + ly) * GS_HALO;
+	const int gx = ox + lx - 1, gy = oy + ly - 1, gz = oz + lz - 1;
+	double v = 0.0;
+	if (gx >= 0 && gy >= 0 && gz >= 0 && gx < a.n[0] && gy < a.n[1] && gz < a.n[2]) v = a.x[int64_t(gz) * a.plane + int64_t(gy) * a.pitch + gx];
+	xs[i] = v;
+    }
+    for (int i = threadIdx.x; i < GS_TILE * GS_TILE * GS_TILE; i += BLOCK)
+    {
+	const int l = ls[i];
+	double v = 0.0;
+	if (l == L_INTERIOR || l == L_BOUNDARY)
+	{
+	    const int lz = i >> 8, ly = (i >> 4) & 15, lx = i & 15;
+	    v = a.b[int64_t(oz + lz) * a.plane + int64_t(oy + ly) * a.pitch + (ox + lx)];
+	}
+	bs[i] = v;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    for (int step = 0; step <= 3 * (GS_TILE - 1); ++step)
+    {
+	const int sfront = a.forward ? step : 3 * (GS_TILE - 1) - step;
+	const int lz = sfront - lx - ly;
+	if (lz >= 0 && lz < GS_TILE)
+	{
+	    const int li = (lz << 8) | (ly << 4) | lx;
+	    const int l = ls[li];
+	    if (l == L_INTERIOR || l == L_BOUNDARY)
+	    {
+		const int c = ((lz + 1) * GS_HALO + (ly + 1)) * GS_HALO + (lx + 1);
+		const double u[6] = {xs[c - 1], xs[c + 1], xs[c - GS_HALO], xs[c + GS_HALO], xs[c - GS_HALO * GS_HALO], xs[c + GS_HALO * GS_HALO]};
+		const double centre = xs[c];
+		double lap = 0.0, diag = 6.0;
+		if (l == L_INTERIOR)
+		{
+#pragma unroll
+		    for (int n = 0; n < 6; ++n) lap -= u[n];
+		}
+		else
+		{
+		    const unsigned sl = slot[li];
+		    if (sl < unsigned(GS_POOL))
+		    {
+			const unsigned code = poolCode[sl];
+			diag = poolDiag[sl];
+#pragma unroll
+			for (int n = 0; n < 6; ++n)
+			{
+			    const unsigned cc = (code >> (2 * n)) & 3u;
+			    if (cc == 1u) lap -= u[n];
+			    else if (cc == 2u)
+			    {
+				const int64_t g = int64_t(oz + lz) * a.plane + int64_t(oy + ly) * a.pitch + (ox + lx);
+				lap -= a.bcoef[int64_t(n) * a.nBoundary + a.bpos[g]] * u[n];
+			    }
+			}
+		    }
+		    else
+		    {
+			const int64_t g = int64_t(oz + lz) * a.plane + int64_t(oy + ly) * a.pitch + (ox + lx);
+			const int k = a.bpos[g];
+#pragma unroll
+			for (int n = 0; n < 6; ++n)
+			{
+			    const double cn = a.bcoef[int64_t(n) * a.nBoundary + k];
+			    if (cn != 0.0) lap -= cn * u[n];
+			}
+			diag = a.bcoef[int64_t(6) * a.nBoundary + k];
+		    }
+		}
+		lap += diag * centre;
+		double r = bs[li] - lap;   // Ops.h:490-493
+		r /= diag;
+		xs[c] = centre + r;
+	    }
+	}
+	__syncthreads();
+    }
+    for (int i = threadIdx.x; i < GS_TILE * GS_TILE * GS_TILE; i += BLOCK)
+    {
+	const int l = ls[i];
+	if (!(l == L_INTERIOR || l == L_BOUNDARY)) continue;
+	const int lz = i >> 8, ly2 = (i >> 4) & 15, lx2 = i & 15;
+	a.x[int64_t(oz + lz) * a.plane + int64_t(oy + ly2) * a.pitch + (ox + lx2)] = xs[((lz + 1) * GS_HALO + (ly2 + 1)) * GS_HALO + (lx2 + 1)];
+    }
+}
+
 // tile flags for the two parities: bit set when the tile holds an active cell
 __global__ void __launch_bounds__(BLOCK) k_gs_tile_flags(uint8_t *flagOdd, uint8_t *flagEven, const uint8_t *labels, int tilesX, int tilesY, int off0,
 							int off1, int off2, int n0, int n1, int n2, int pitch, int64_t plane, int parity0)

@@ -18,7 +18,8 @@ namespace gmg
 {
 constexpr int P2P_MAX_WORLD = 16;
 constexpr int P2P_MAX_LEVELS = 4;
-constexpr int P2P_CTAS = 128;              // every CTA must be resident at once (they wait on each other's flags)
+constexpr int P2P_CTAS = 512;              // every CTA must be resident at once (they wait on each other's flags): 4 per SM hold enough
+                                           // remote stores in flight for NVLink (round 1's <= 69 CTAs kept ~280 KB in flight: ~110 GB/s)
 // A rank that waits longer than this for a neighbour gives up loudly instead of hanging the GPU: the error word becomes
 // sticky, the stale mailbox is NOT copied and the channel's sequence number is NOT advanced.  Wall-clock (%globaltimer), so
 // legitimate skew between the ranks' host threads (first-use graph instantiation, a slow upload) is covered; GMG_P2P_TIMEOUT_S
@@ -111,6 +112,20 @@ __device__ __forceinline__ bool lastCta(unsigned *ticket)
     __syncthreads();
     return last;
 }
+// `planes` planes, of each only the rows [rowLo, rowHi) -- the rows that hold an active cell anywhere in the level (the same
+// on every rank: labels are replicated); everything else in a vector grid is 0 on both sides and stays so
+__device__ __forceinline__ void copyRows(double *dst, const double *src, int planes, int64_t plane, int64_t segOff, int64_t segLen, bool srcIsMailbox)
+{
+    const int64_t n2 = segLen >> 1;  // the row pitch is even
+    const int64_t total = int64_t(planes) * n2;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x)
+    {
+	const int64_t pl = i / n2, j = i - pl * n2;
+	const double2 *s = reinterpret_cast<const double2 *>(src + pl * plane + segOff) + j;
+	double2 *d = reinterpret_cast<double2 *>(dst + pl * plane + segOff) + j;
+	*d = srcIsMailbox ? __ldcg(s) : *s;
+    }
+}
 __device__ __forceinline__ void copyPlanes(double *dst, const double *src, int64_t n, bool srcIsMailbox)
 {
     // n is a multiple of 2 (row pitch is a multiple of 16 doubles); mailboxes were written by another GPU: bypass L1
@@ -125,6 +140,7 @@ struct HaloP2pArgs
 {
     double *grid;                 // plane 0 = first stored plane of the slab
     int64_t plane;
+    int64_t segOff, segLen;       // doubles: offset and length of the active rows inside a plane (segLen even)
     int ownLo, ownHi, depth;
     int hasLower, hasUpper;
     double *toLower, *toUpper;    // [2 slots] REMOTE: the lower neighbour's "from upper" box, the upper neighbour's "from lower" box
@@ -141,9 +157,8 @@ __global__ void __launch_bounds__(256) k_halo_p2p(const HaloP2pArgs a)
 {
     const unsigned long long seq = *a.seq + 1;
     const int slot = int(seq & 1);
-    const int64_t n = int64_t(a.depth) * a.plane;
-    if (a.hasLower) copyPlanes(a.toLower + slot * a.slotStride, a.grid + int64_t(a.ownLo) * a.plane, n, false);
-    if (a.hasUpper) copyPlanes(a.toUpper + slot * a.slotStride, a.grid + int64_t(a.ownHi - a.depth) * a.plane, n, false);
+    if (a.hasLower) copyRows(a.toLower + slot * a.slotStride, a.grid + int64_t(a.ownLo) * a.plane, a.depth, a.plane, a.segOff, a.segLen, false);
+    if (a.hasUpper) copyRows(a.toUpper + slot * a.slotStride, a.grid + int64_t(a.ownHi - a.depth) * a.plane, a.depth, a.plane, a.segOff, a.segLen, false);
     if (lastCta<true>(a.tickets))
     {
 	if (threadIdx.x == 0)
@@ -155,12 +170,12 @@ __global__ void __launch_bounds__(256) k_halo_p2p(const HaloP2pArgs a)
     if (a.hasLower)
     {
 	if (waitFlag(a.myFlagLower + slot, seq, a.error))
-	    copyPlanes(a.grid + int64_t(a.ownLo - a.depth) * a.plane, a.fromLower + slot * a.slotStride, n, true);
+	    copyRows(a.grid + int64_t(a.ownLo - a.depth) * a.plane, a.fromLower + slot * a.slotStride, a.depth, a.plane, a.segOff, a.segLen, true);
     }
     if (a.hasUpper)
     {
 	if (waitFlag(a.myFlagUpper + slot, seq, a.error))
-	    copyPlanes(a.grid + int64_t(a.ownHi) * a.plane, a.fromUpper + slot * a.slotStride, n, true);
+	    copyRows(a.grid + int64_t(a.ownHi) * a.plane, a.fromUpper + slot * a.slotStride, a.depth, a.plane, a.segOff, a.segLen, true);
     }
     if (lastCta<false>(a.tickets + 1))
     {
