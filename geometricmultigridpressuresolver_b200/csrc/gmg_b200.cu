@@ -2500,8 +2500,9 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
     a.result = dotResult;
     a.zlo = zr.lo;
     a.zhi = zr.hi;
-    const unsigned grid = unsigned(L.nChunksInterior + divUp(L.nBoundary, BLOCK));
-    if (grid == 0) return GMG_OK;
+    unsigned grid = unsigned(L.nChunksInterior + divUp(L.nBoundary, BLOCK));
+    if (grid == 0 && !dotResult) return GMG_OK;
+    grid = std::max(grid, 1u);  // a fused dot product on a slab without active cells still delivers its 0 (one idle CTA)
     cudaStream_t st = s->ctx->stream;
     const double n = double(L.nActive);
     if (L.bricks && mode != SM_JACOBI_ZERO && (s->tmaMask & (mode == SM_JACOBI ? 1 : (mode == SM_RESIDUAL ? 2 : 4))))
@@ -2509,7 +2510,7 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
 	// TMA-staged variant: one CTA per 64 x 8 x 4 brick
 	TmaMap tm;
 	GMG_TRY(tensorMapOf(s, level, in, &tm));
-	const unsigned tgrid = unsigned(L.nBricks + divUp(L.nBoundary, BLOCK));
+	const unsigned tgrid = std::max(1u, unsigned(L.nBricks + divUp(L.nBoundary, BLOCK)));
 	const int ny = L.g.n[1];
 	if (mode == SM_JACOBI)
 	{
@@ -3180,9 +3181,13 @@ static int launchVec(gmg_solver *s, int level, double *y, const double *a, const
 {
     s->ctx->curLevel = level;
     const Level &L = s->lv[level];
-    if (L.nChunksActive == 0) return GMG_OK;
+    // a slab without active cells (a sharded level whose liquid does not reach this rank) has nothing to update, but a
+    // REDUCTION still has to deliver its 0 -- and the CG update has to retire rho -- on this rank like on every other
+    const bool reduces = OP == VO_DOT || OP == VO_NORM2 || OP == VO_MAX || OP == VO_CG_UPDATE;
+    if (L.nChunksActive == 0 && !reduces) return GMG_OK;
     VecArgs v;
     v.chunks = L.chunksActive;
+    v.nChunks = L.nChunksActive;
     v.chunksPerPlane = L.g.chunksPerPlane;
     v.plane = L.g.plane;
     v.nz = L.g.n[2];
@@ -3200,7 +3205,7 @@ static int launchVec(gmg_solver *s, int level, double *y, const double *a, const
     v.ticket = s->ctx->ticket;
     v.result = result;
     GMG_LAUNCH(s->ctx, klass, double(L.nActive) * bytesPerCell);
-    GMG_CUDA(launchK((k_vec<OP>), unsigned(L.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, v));
+    GMG_CUDA(launchK((k_vec<OP>), unsigned(std::max(L.nChunksActive, 1)), unsigned(BLOCK), size_t(0), s->ctx->stream, v));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }

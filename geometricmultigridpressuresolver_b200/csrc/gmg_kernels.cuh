@@ -1042,6 +1042,8 @@ __global__ void __launch_bounds__(BLOCK) k_coarse_solve(double *x, const double 
 struct VecArgs
 {
     const int32_t *chunks;
+    int nChunks;        // CTAs beyond it do no cell work (a reduction on a slab without active cells still launches ONE CTA, so that
+			// its result -- 0 -- and the scalars the finishing CTA maintains are written on every rank)
     int chunksPerPlane;
     int64_t plane;
     int nz;
@@ -1076,7 +1078,8 @@ template <int OP>
 __global__ void __launch_bounds__(BLOCK) k_vec(const VecArgs v)
 {
     pdlLaunch();
-    const int c = v.chunks[blockIdx.x];
+    const bool live = int(blockIdx.x) < v.nChunks;
+    const int c = live ? v.chunks[blockIdx.x] : 0;
     pdlWait();
     const int zb = c / v.chunksPerPlane;
     const int64_t inPlane = int64_t(c - zb * v.chunksPerPlane) * CHUNK_CELLS + 2 * threadIdx.x;
@@ -1084,7 +1087,7 @@ __global__ void __launch_bounds__(BLOCK) k_vec(const VecArgs v)
     double s = v.s;
     if (OP == VO_CG_UPDATE) s = v.sc->rhoNew / v.sc->pAp;
     if (OP == VO_CG_DIRECTION) s = v.sc->rhoNew / v.sc->rho;
-    if (inPlane < v.plane)
+    if (live && inPlane < v.plane)
     {
 #pragma unroll
 	for (int dz = 0; dz < CHUNK_Z; ++dz)

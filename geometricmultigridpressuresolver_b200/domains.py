@@ -198,6 +198,35 @@ def liquid_box_domain(n: int):
     return labels, weights, 1.0 / n
 
 
+def _unit_weights(labels):
+    """Face weights 1 between two non-EXTERIOR cells of which at least one is liquid, 0 otherwise (the rule of liquid_box_domain)."""
+    n = labels.shape
+    weights = []
+    for axis in range(3):
+        na = _np_axis(axis)
+        w = np.zeros(face_shape(labels.shape, axis), dtype=np.float64)
+        back = [slice(None)] * 3
+        fwd = [slice(None)] * 3
+        face = [slice(None)] * 3
+        back[na] = slice(0, n[na] - 1)
+        fwd[na] = slice(1, n[na])
+        face[na] = slice(1, n[na])
+        lb, lf = labels[tuple(back)], labels[tuple(fwd)]
+        ok = (lb != EXTERIOR) & (lf != EXTERIOR) & ((lb == INTERIOR) | (lf == INTERIOR))
+        w[tuple(face)] = ok.astype(np.float64)
+        weights.append(w)
+    return weights
+
+
+def half_liquid_box_domain(n: int):
+    """A solid box whose upper z half is liquid and lower z half air: z-slab sharding leaves the lower ranks WITHOUT any active
+    cell (their reductions must still deliver 0 and keep the CG scalars in step -- the N = 8 failure of round 1)."""
+    labels = np.full((n, n, n), EXTERIOR, dtype=np.int32)
+    labels[1 : n - 1, 1 : n - 1, 1 : n - 1] = INTERIOR
+    labels[1 : n // 2 + 3, 1 : n - 1, 1 : n - 1] = DIRICHLET
+    return labels, _unit_weights(labels), 1.0 / n
+
+
 def narrow_band_domain(n: int, thickness: int = 12):
     """Config 5: thin liquid sheet over solid terrain h(x,z) = N(0.5 + 0.1 sin(2 pi x/N) sin(2 pi z/N));
     y < h-thickness solid, h-thickness <= y <= h liquid, above air; x/z walls solid."""
@@ -258,4 +287,5 @@ DOMAINS = {
     "flipsplash": flipsplash_domain,
     "liquid_box": liquid_box_domain,
     "narrow_band": narrow_band_domain,
+    "half_box": half_liquid_box_domain,
 }

@@ -158,7 +158,8 @@ def main():
     ctx_one = api.Context(local)
     ctx_sh = api.Context(local)
     ctx_sh.shard_with_torch(dist)
-    cases = [("sphere", 64, 1), ("sphere", 64, 2), ("flipsplash", 64, 3), ("complex", 64, 2)]
+    # half_box: the lower ranks own no active cell at all (reductions and CG scalars on an empty slab)
+    cases = [("sphere", 64, 1), ("sphere", 64, 2), ("flipsplash", 64, 3), ("complex", 64, 2), ("half_box", 64, 2)]
     if len(sys.argv) > 1 and sys.argv[1] == "quick":
         cases = cases[:2]
     # every rank must own at least the stored halo depth of planes on a sharded level: larger domains for larger worlds

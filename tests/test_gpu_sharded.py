@@ -1,5 +1,6 @@
 """GPU (-m gpu), needs >= 2 devices: z-slab sharding against the unsharded path of the same library.
-One process per GPU under torchrun (tests/mgpu_worker.py); skipped on a one-GPU box."""
+One process per GPU under torchrun (tests/mgpu_worker.py); skipped on a box with fewer GPUs.  The logs of the round's own runs at
+2, 4 and 8 GPUs are profiles/r02_mgpu_worker_n{2,4,8}.log, and `bench.py --gpus N` asserts the same on every run (parity_vs_n1)."""
 import os
 import subprocess
 import sys
@@ -16,7 +17,7 @@ def _gpu_count():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_matches_unsharded(world):
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
