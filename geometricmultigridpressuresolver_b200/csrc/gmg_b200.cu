@@ -2234,6 +2234,7 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     if (const char *e = getenv("GMG_ZERO_AWARE")) s->zeroAware = !(e[0] == '0');
     s->tmaMask = tmaMode();
     if (const char *e = getenv("GMG_BAND_GROUPS")) s->bandGroups = (e[0] == '1');
+    if (const char *e = getenv("GMG_BAND_RESIDENT")) s->bandResident = (e[0] == '1');
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel && ctx->world > 1)
@@ -2589,6 +2590,51 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
     const double bytes = double(L.nBand) * 29.0;
     const bool hw = L.hasWeights;
     double *cur = L.bandV0, *nxt = L.bandV1;
+    if (sweeps >= 2 && s->bandResident && s->ctx->groupBarrier)
+    {
+	// the whole group in one launch of 2 x 512 threads per SM with every cell's metadata resident (k_band_resident);
+	// bands beyond the capacity of 6 cells per thread take the sweep-per-launch kernels below
+	gmg_ctx *ctx = s->ctx;
+	const int64_t gthreads = int64_t(2) * ctx->smCount * BG_THREADS;
+	const int cpt = int(divUp(L.nBand, gthreads));
+	if (cpt <= 6)
+	{
+	    // small bands: fewer CTAs (one cell per thread), a cheaper barrier
+	    const unsigned g = unsigned(std::min<int64_t>(int64_t(2) * ctx->smCount, divUp(L.nBand, BG_THREADS)));
+	    const int c2 = int(divUp(L.nBand, int64_t(g) * BG_THREADS));
+	    const int CP = c2 <= 1 ? 1 : (c2 <= 2 ? 2 : (c2 <= 4 ? 4 : 6));
+	    const size_t smem = size_t(CP) * 6 * BG_THREADS * sizeof(int);
+	    a.vin = nxt;   // (the kernel takes the two compact arrays through vin / vout)
+	    a.vout = cur;
+	    GroupBarrier *bar = static_cast<GroupBarrier *>(ctx->groupBarrier);
+	    static bool attr = false;
+	    if (!attr)
+	    {
+		const int big = 6 * 6 * BG_THREADS * int(sizeof(int));
+		GMG_CUDA(cudaFuncSetAttribute(k_band_resident<false, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+		GMG_CUDA(cudaFuncSetAttribute(k_band_resident<false, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+		GMG_CUDA(cudaFuncSetAttribute(k_band_resident<true, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+		GMG_CUDA(cudaFuncSetAttribute(k_band_resident<true, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+		attr = true;
+	    }
+	    GMG_LAUNCH(ctx, KC_BAND, bytes * sweeps);
+#define GMG_BR(HW, ZG)                                                                                                         \
+    do                                                                                                                         \
+    {                                                                                                                          \
+	if (CP == 1) GMG_CUDA(launchK((k_band_resident<HW, ZG, 1>), g, unsigned(BG_THREADS), smem, st, a, sweeps, bar));       \
+	else if (CP == 2) GMG_CUDA(launchK((k_band_resident<HW, ZG, 2>), g, unsigned(BG_THREADS), smem, st, a, sweeps, bar));  \
+	else if (CP == 4) GMG_CUDA(launchK((k_band_resident<HW, ZG, 4>), g, unsigned(BG_THREADS), smem, st, a, sweeps, bar));  \
+	else GMG_CUDA(launchK((k_band_resident<HW, ZG, 6>), g, unsigned(BG_THREADS), smem, st, a, sweeps, bar));               \
+    } while (0)
+	    if (zeroGrid && hw) GMG_BR(true, true);
+	    else if (zeroGrid) GMG_BR(false, true);
+	    else if (hw) GMG_BR(true, false);
+	    else GMG_BR(false, false);
+#undef GMG_BR
+	    GMG_CUDA(cudaGetLastError());
+	    return GMG_OK;
+	}
+    }
     if (sweeps >= 2 && s->bandGroups && s->ctx->groupBarrier)
     {
 	// the whole group in one co-resident launch with grid barriers between the sweeps (k_band_group)
@@ -2626,7 +2672,7 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
     if (sweeps == 1)
     {
 	GMG_LAUNCH(s->ctx, KC_BAND, double(L.nBand) * 20.0);
-	GMG_CUDA(launchK(k_band_scatter, unsigned(divUp(L.nBand, BLOCK)), BLOCK, 0, st, x, L.bandIdx, cur, L.nBand));
+	GMG_CUDA(launchK(k_band_scatter<double>, unsigned(divUp(L.nBand, BLOCK)), BLOCK, 0, st, x, L.bandIdx, cur, L.nBand));
     }
     for (int sw = 2; sw <= sweeps; ++sw)
     {
@@ -2694,7 +2740,7 @@ static int launchRestrict(gmg_solver *s, int fineLevel, double *coarse, const do
 	GMG_CUDA(cudaGetLastError());
 	return GMG_OK;
     }
-    GMG_CUDA(launchK(k_restrict, unsigned(C.nChunksActive * RESTRICT_SPLIT), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
+    GMG_CUDA(launchK(k_restrict<double>, unsigned(C.nChunksActive * RESTRICT_SPLIT), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }
@@ -2722,7 +2768,7 @@ static int launchProlong(gmg_solver *s, int fineLevel, double *fine, const doubl
 	GMG_CUDA(cudaGetLastError());
 	return GMG_OK;
     }
-    GMG_CUDA(launchK(k_prolong, unsigned(F.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
+    GMG_CUDA(launchK(k_prolong<double>, unsigned(F.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }

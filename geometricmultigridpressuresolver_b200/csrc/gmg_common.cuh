@@ -228,6 +228,9 @@ struct gmg_solver
     bool bandGroups = false;      // a group of band sweeps as ONE co-resident launch with grid barriers: measured SLOWER than a launch per sweep
 				  // (profiles/r02_ab_switches.md: 256^3 solve 11.5 vs 10.3 ms; a barrier over ~900 CTAs costs more than a kernel
 				  // boundary with its prologue overlapped), so it is opt-in (GMG_BAND_GROUPS=1)
+    bool bandResident = false;    // a group of band sweeps as one launch with every cell's metadata on chip (k_band_resident): measured SLOWER too
+				  // (11.04 vs 10.22 ms: with the prologues overlapped a kernel boundary costs what a 296-CTA barrier costs, ~2.5-3 us,
+				  // and two 512-thread CTAs per SM gather with less parallelism than the sweep kernels); opt-in, GMG_BAND_RESIDENT=1
     bool zeroAware = true;        // zero-aware down-stroke (no zero fill, SM_JACOBI_ZERO); GMG_ZERO_AWARE=0 at creation restores the fill
 };
 

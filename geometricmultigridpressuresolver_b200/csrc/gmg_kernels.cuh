@@ -18,8 +18,14 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
-__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+// the value type of a kernel: double everywhere on the reference path; float for the V-cycle of the mixed-precision option
+// (fp32 V-cycle inside the fp64 CG) -- the stencil / band / transfer bodies are templates on it
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
+template <typename T> __device__ __forceinline__ typename Vec2<T>::type ld2(const T *p) { return *reinterpret_cast<const typename Vec2<T>::type *>(p); }
+template <typename T> __device__ __forceinline__ void st2(T *p, typename Vec2<T>::type v) { *reinterpret_cast<typename Vec2<T>::type *>(p) = v; }
+template <typename T> __device__ __forceinline__ typename Vec2<T>::type make2(T a, T b) { typename Vec2<T>::type v; v.x = a; v.y = b; return v; }
 
 // Programmatic dependent launch (see launchK in gmg_b200.cu).  A V-cycle at 256^3 is ~70 dependent steps of a few
 // microseconds, each a chain of dependent loads (chunk id -> labels / neighbour references -> values), so every hot
@@ -134,13 +140,14 @@ struct Scalars
 // taken through the band mask.  Bitwise the result of SM_JACOBI on a zero-filled grid.
 enum StencilMode { SM_JACOBI = 0, SM_APPLY = 1, SM_RESIDUAL = 2, SM_JACOBI_ZERO = 3 };
 
-struct StencilArgs
+template <typename T>
+struct StencilArgsT
 {
     const uint8_t *labels;
     const uint8_t *flags;   // SM_JACOBI_ZERO: bit0 = cell is in the boundary band, bit1 = INTERIOR cell with a band cell in its 7-point neighbourhood
-    const double *in;   // x (Jacobi/residual) or source (apply)
-    const double *b;    // rhs (Jacobi/residual)
-    double *out;        // Jacobi: new x (out of place); apply: A in; residual: b - A in
+    const T *in;        // x (Jacobi/residual) or source (apply)
+    const T *b;         // rhs (Jacobi/residual)
+    T *out;             // Jacobi: new x (out of place); apply: A in; residual: b - A in
     const int32_t *chunks;
     int nChunks;
     int chunksPerPlane;
@@ -159,21 +166,22 @@ struct StencilArgs
     unsigned *ticket;
     double *result;
 };
+typedef StencilArgsT<double> StencilArgs;
 
-template <int MODE>
-__device__ __forceinline__ double stencilFinish(double lap, double centre, double rhs, double diag)
+template <int MODE, typename T>
+__device__ __forceinline__ T stencilFinish(T lap, T centre, T rhs, T diag)
 {
     if (MODE == SM_APPLY) return lap;
-    if (MODE == SM_RESIDUAL) return rhs + (-1.0) * lap;  // addVectors(residual, rhs, residual, -1), Ops.h:731
+    if (MODE == SM_RESIDUAL) return rhs + T(-1.0) * lap;  // addVectors(residual, rhs, residual, -1), Ops.h:731
     // SM_JACOBI and SM_JACOBI_ZERO:
-    double r = rhs - lap;                                 // Ops.h:357-361
+    T r = rhs - lap;                                      // Ops.h:357-361
     r /= diag;
-    return centre + (2.0 / 3.0) * r;
+    return centre + T(2.0 / 3.0) * r;
 }
 
 // BOUNDARY-labelled cell k of the level's record list (Ops.h:208-255): coefficient record in the prologue, values after the wait
-template <int MODE, bool DOT>
-__device__ __forceinline__ double stencilBoundary(const StencilArgs &a, int k)
+template <typename T, int MODE, bool DOT>
+__device__ __forceinline__ double stencilBoundary(const StencilArgsT<T> &a, int k)
 {
     double acc = 0.0;
     const int64_t i = k < a.nBoundary ? int64_t(a.bandIdx[k]) : 0;
@@ -181,27 +189,27 @@ __device__ __forceinline__ double stencilBoundary(const StencilArgs &a, int k)
     const bool live = k < a.nBoundary && z >= a.zlo && z < a.zhi;
     // prologue: the code word, the diagonal and the (rare) fractional coefficients
     const unsigned code = live ? a.wcode[k] : 0u;
-    const double diag = live ? a.bcoef[int64_t(6) * a.nBoundary + k] : 1.0;
-    double cn[6];
+    const T diag = live ? T(a.bcoef[int64_t(6) * a.nBoundary + k]) : T(1.0);
+    T cn[6];
 #pragma unroll
     for (int n = 0; n < 6; ++n)
     {
 	const unsigned c = (code >> (2 * n)) & 3u;
-	cn[n] = c == 2u ? a.bcoef[int64_t(n) * a.nBoundary + k] : double(c);  // 0, exactly 1, or the fractional coefficient
+	cn[n] = c == 2u ? T(a.bcoef[int64_t(n) * a.nBoundary + k]) : T(c);  // 0, exactly 1, or the fractional coefficient
     }
     pdlWait();
     if (live)
     {
 	const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
-	const double centre = a.in[i];
-	double lap = 0.0;
+	const T centre = a.in[i];
+	T lap = T(0.0);
 #pragma unroll
 	for (int n = 0; n < 6; ++n)
-	    if (cn[n] != 0.0) lap -= cn[n] * a.in[i + stride[n]];
+	    if (cn[n] != T(0.0)) lap -= cn[n] * a.in[i + stride[n]];
 	lap += diag * centre;
-	const double rhs = (MODE != SM_APPLY) ? a.b[i] : 0.0;
-	a.out[i] = stencilFinish<MODE>(lap, centre, rhs, diag);
-	if (DOT && z >= a.dotLo && z < a.dotHi) acc += centre * lap;
+	const T rhs = (MODE != SM_APPLY) ? a.b[i] : T(0.0);
+	a.out[i] = stencilFinish<MODE, T>(lap, centre, rhs, diag);
+	if (DOT && z >= a.dotLo && z < a.dotHi) acc += double(centre * lap);
     }
     return acc;
 }
@@ -209,9 +217,10 @@ __device__ __forceinline__ double stencilBoundary(const StencilArgs &a, int k)
 // vb = virtual CTA index (blockIdx.x of the stand-alone kernel), tid = thread index inside the BLOCK-wide virtual CTA.
 // Returns this thread's part of dot(in, A in) when DOT.  Prologue (before pdlWait): chunk id and the labels of the
 // thread's cells, or the boundary cell's index and coefficient record.
-template <int MODE, bool DOT>
-__device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int tid)
+template <typename T, int MODE, bool DOT>
+__device__ __forceinline__ double stencilBody(const StencilArgsT<T> &a, int vb, int tid)
 {
+    typedef typename Vec2<T>::type T2;
     double acc = 0.0;
     if (vb < a.nChunks)
     {
@@ -244,9 +253,9 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 		const bool a0 = (lab[dz].x == L_INTERIOR), a1 = (lab[dz].y == L_INTERIOR);
 		if (!(a0 | a1)) continue;
 		const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
-		const double2 rhs = ld2(a.b + i);
-		const double o0 = (2.0 / 3.0) * (rhs.x / 6.0), o1 = (2.0 / 3.0) * (rhs.y / 6.0);
-		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
+		const T2 rhs = ld2(a.b + i);
+		const T o0 = T(2.0 / 3.0) * (rhs.x / T(6.0)), o1 = T(2.0 / 3.0) * (rhs.y / T(6.0));
+		if (a0 & a1) st2(a.out + i, make2<T>(o0, o1));
 		else if (a0) a.out[i] = o0;
 		else a.out[i + 1] = o1;
 		near |= ((flg[dz].x | flg[dz].y) & 2) << dz;
@@ -261,37 +270,37 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 		const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
 		const uchar2 l = *reinterpret_cast<const uchar2 *>(a.labels + i);
 		const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
-		const double2 rhs = ld2(a.b + i);
+		const T2 rhs = ld2(a.b + i);
 		const uint8_t *f = a.flags + i;
 		const uchar2 fc = *reinterpret_cast<const uchar2 *>(f);
 		const uchar2 fym = *reinterpret_cast<const uchar2 *>(f - a.pitch), fyp = *reinterpret_cast<const uchar2 *>(f + a.pitch);
 		const uchar2 fzm = *reinterpret_cast<const uchar2 *>(f - a.plane), fzp = *reinterpret_cast<const uchar2 *>(f + a.plane);
 		const int fxm = f[-1], fxp = f[2];
-		double2 c2 = ld2(a.in + i);
-		double xm = a.in[i - 1], xp = a.in[i + 2];
-		double2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
-		double2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
-		if (!(fc.x & 1)) c2.x = 0.0;
-		if (!(fc.y & 1)) c2.y = 0.0;
-		if (!(fxm & 1)) xm = 0.0;
-		if (!(fxp & 1)) xp = 0.0;
-		if (!(fym.x & 1)) ym.x = 0.0;
-		if (!(fym.y & 1)) ym.y = 0.0;
-		if (!(fyp.x & 1)) yp.x = 0.0;
-		if (!(fyp.y & 1)) yp.y = 0.0;
-		if (!(fzm.x & 1)) zm.x = 0.0;
-		if (!(fzm.y & 1)) zm.y = 0.0;
-		if (!(fzp.x & 1)) zp.x = 0.0;
-		if (!(fzp.y & 1)) zp.y = 0.0;
-		double lap0 = -xm;
+		T2 c2 = ld2(a.in + i);
+		T xm = a.in[i - 1], xp = a.in[i + 2];
+		T2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
+		T2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
+		if (!(fc.x & 1)) c2.x = T(0.0);
+		if (!(fc.y & 1)) c2.y = T(0.0);
+		if (!(fxm & 1)) xm = T(0.0);
+		if (!(fxp & 1)) xp = T(0.0);
+		if (!(fym.x & 1)) ym.x = T(0.0);
+		if (!(fym.y & 1)) ym.y = T(0.0);
+		if (!(fyp.x & 1)) yp.x = T(0.0);
+		if (!(fyp.y & 1)) yp.y = T(0.0);
+		if (!(fzm.x & 1)) zm.x = T(0.0);
+		if (!(fzm.y & 1)) zm.y = T(0.0);
+		if (!(fzp.x & 1)) zp.x = T(0.0);
+		if (!(fzp.y & 1)) zp.y = T(0.0);
+		T lap0 = -xm;
 		lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
-		lap0 += 6.0 * c2.x;
-		double lap1 = -c2.x;
+		lap0 += T(6.0) * c2.x;
+		T lap1 = -c2.x;
 		lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
-		lap1 += 6.0 * c2.y;
-		const double o0 = stencilFinish<MODE>(lap0, c2.x, rhs.x, 6.0);
-		const double o1 = stencilFinish<MODE>(lap1, c2.y, rhs.y, 6.0);
-		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
+		lap1 += T(6.0) * c2.y;
+		const T o0 = stencilFinish<MODE, T>(lap0, c2.x, rhs.x, T(6.0));
+		const T o1 = stencilFinish<MODE, T>(lap1, c2.y, rhs.y, T(6.0));
+		if (a0 & a1) st2(a.out + i, make2<T>(o0, o1));
 		else if (a0) a.out[i] = o0;
 		else a.out[i + 1] = o1;
 	    }
@@ -305,36 +314,36 @@ __device__ __forceinline__ double stencilBody(const StencilArgs &a, int vb, int 
 	    const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
 	    if (!(a0 | a1)) continue;
 	    const int64_t i = int64_t(z) * a.plane + inPlane;
-	    const double2 c2 = ld2(a.in + i);
-	    const double xm = a.in[i - 1], xp = a.in[i + 2];
-	    const double2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
-	    const double2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
-	    double2 rhs = make_double2(0.0, 0.0);
+	    const T2 c2 = ld2(a.in + i);
+	    const T xm = a.in[i - 1], xp = a.in[i + 2];
+	    const T2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
+	    const T2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
+	    T2 rhs = make2<T>(T(0.0), T(0.0));
 	    if (MODE != SM_APPLY) rhs = ld2(a.b + i);
-	    double lap0 = -xm;
+	    T lap0 = -xm;
 	    lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
-	    lap0 += 6.0 * c2.x;
-	    double lap1 = -c2.x;
+	    lap0 += T(6.0) * c2.x;
+	    T lap1 = -c2.x;
 	    lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
-	    lap1 += 6.0 * c2.y;
-	    const double o0 = stencilFinish<MODE>(lap0, c2.x, rhs.x, 6.0);
-	    const double o1 = stencilFinish<MODE>(lap1, c2.y, rhs.y, 6.0);
-	    if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
+	    lap1 += T(6.0) * c2.y;
+	    const T o0 = stencilFinish<MODE, T>(lap0, c2.x, rhs.x, T(6.0));
+	    const T o1 = stencilFinish<MODE, T>(lap1, c2.y, rhs.y, T(6.0));
+	    if (a0 & a1) st2(a.out + i, make2<T>(o0, o1));
 	    else if (a0) a.out[i] = o0;
 	    else a.out[i + 1] = o1;
-	    if (DOT && z >= a.dotLo && z < a.dotHi) acc += (a0 ? c2.x * lap0 : 0.0) + (a1 ? c2.y * lap1 : 0.0);
+	    if (DOT && z >= a.dotLo && z < a.dotHi) acc += double((a0 ? c2.x * lap0 : T(0.0)) + (a1 ? c2.y * lap1 : T(0.0)));
 	}
     }
-    else acc = stencilBoundary<MODE, DOT>(a, (vb - a.nChunks) * BLOCK + tid);
+    else acc = stencilBoundary<T, MODE, DOT>(a, (vb - a.nChunks) * BLOCK + tid);
     return acc;
 }
 
 // (the zero-aware sweep streams b -> x on its common path: capped at 40 registers so the rare masked path cannot cost it occupancy)
-template <int MODE, bool DOT>
-__global__ void __launch_bounds__(BLOCK, MODE == SM_JACOBI_ZERO ? 6 : 1) k_stencil(const StencilArgs a)
+template <int MODE, bool DOT, typename T = double>
+__global__ void __launch_bounds__(BLOCK, MODE == SM_JACOBI_ZERO ? 6 : 1) k_stencil(const StencilArgsT<T> a)
 {
     pdlLaunch();
-    const double acc = stencilBody<MODE, DOT>(a, blockIdx.x, threadIdx.x);
+    const double acc = stencilBody<T, MODE, DOT>(a, blockIdx.x, threadIdx.x);
     if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
 }
 
@@ -452,8 +461,8 @@ __global__ void __launch_bounds__(BLOCK) k_stencil_tma(const StencilArgs a, cons
 		double lap1 = -c2.x;
 		lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
 		lap1 += 6.0 * c2.y;
-		const double o0 = stencilFinish<MODE>(lap0, c2.x, rhs[dz].x, 6.0);
-		const double o1 = stencilFinish<MODE>(lap1, c2.y, rhs[dz].y, 6.0);
+		const double o0 = stencilFinish<MODE, double>(lap0, c2.x, rhs[dz].x, 6.0);
+		const double o1 = stencilFinish<MODE, double>(lap1, c2.y, rhs[dz].y, 6.0);
 		if (a0 & a1) st2(a.out + i, make_double2(o0, o1));
 		else if (a0) a.out[i] = o0;
 		else a.out[i + 1] = o1;
@@ -463,7 +472,7 @@ __global__ void __launch_bounds__(BLOCK) k_stencil_tma(const StencilArgs a, cons
 	    c2 = zp;
 	}
     }
-    else acc = stencilBoundary<MODE, DOT>(a, (int(blockIdx.x) - nBricks) * BLOCK + int(threadIdx.x));
+    else acc = stencilBoundary<double, MODE, DOT>(a, (int(blockIdx.x) - nBricks) * BLOCK + int(threadIdx.x));
     if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
 }
 
@@ -493,22 +502,24 @@ __global__ void __launch_bounds__(BLOCK) k_brick_flags(uint8_t *flags, const uin
 // from the grid, writing compact array vout -- or the grid itself on the last sweep, which is
 // race-free because nobody reads band cells from the grid in that sweep.
 // ------------------------------------------------------------------------------------------------
-struct BandArgs
+template <typename T>
+struct BandArgsT
 {
-    double *x;           // grid
-    const double *b;     // grid rhs
+    T *x;                // grid
+    const T *b;          // grid rhs
     const int32_t *bandIdx;
     const int32_t *bandRef;  // [6][nBand] neighbour reference: >= 0 position in the band; BAND_SKIP: coefficient 0 (not active);
 			     // <= -2: an active cell outside the band (frozen during the band sweeps) at grid index -2 - ref
     const double *bcoef;
     const unsigned short *wcode;  // coefficient codes of the BOUNDARY cells (k_band_coef)
-    const double *vin;
-    double *vout;
-    double *bandB;
+    const T *vin;
+    T *vout;
+    T *bandB;
     int nBoundary, nBand;
     int pitch;
     int64_t plane;
 };
+typedef BandArgsT<double> BandArgs;
 constexpr int BAND_SKIP = -1;
 constexpr int BAND_PER_THREAD = 2;  // cells per thread: two independent gather chains in flight
 
@@ -520,25 +531,25 @@ constexpr int BAND_PER_THREAD = 2;  // cells per thread: two independent gather 
 // Prologue (static metadata, before pdlWait): grid index, neighbour references, diagonal, coefficient record.
 // CGL: values of the compact arrays are read past L1 (ld.cg) -- inside the persistent sweep-group kernel another SM wrote them
 // during the same launch
-template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false, bool CGL = false>
-__device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false, bool CGL = false, typename T = double>
+__device__ __forceinline__ void bandBody(const BandArgsT<T> &a, int vb, int tid)
 {
     int64_t gi[BAND_PER_THREAD];
     int ref[BAND_PER_THREAD][6];
-    double diag[BAND_PER_THREAD];
+    T diag[BAND_PER_THREAD];
     unsigned code[BAND_PER_THREAD];
 #pragma unroll
     for (int c = 0; c < BAND_PER_THREAD; ++c)
     {
 	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
 	gi[c] = 0;
-	diag[c] = 6.0;
+	diag[c] = T(6.0);
 	code[c] = 0x555u;  // every coefficient 1
 #pragma unroll
 	for (int n = 0; n < 6; ++n) ref[c][n] = BAND_SKIP;
 	if (k >= a.nBand) continue;
 	if (!FROM_COMPACT || TO_GRID || FIRST) gi[c] = a.bandIdx[k];
-	if (k < a.nBoundary) diag[c] = a.bcoef[int64_t(6) * a.nBoundary + k];
+	if (k < a.nBoundary) diag[c] = T(a.bcoef[int64_t(6) * a.nBoundary + k]);
 	if (HAS_W && !ZERO && k < a.nBoundary) code[c] = a.wcode[k];
 	if (!ZERO)
 	{
@@ -547,18 +558,18 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 	}
     }
     pdlWait();
-    double v[BAND_PER_THREAD];
+    T v[BAND_PER_THREAD];
 #pragma unroll
     for (int c = 0; c < BAND_PER_THREAD; ++c)
     {
 	const int k = (vb * BAND_PER_THREAD + c) * BLOCK + tid;
-	v[c] = 0.0;
+	v[c] = T(0.0);
 	if (k >= a.nBand) continue;
 	const int64_t i = gi[c];
-	double rhs;
+	T rhs;
 	if (FIRST) { rhs = a.b[i]; a.bandB[k] = rhs; }
 	else rhs = a.bandB[k];
-	double centre = 0.0, lap = 0.0;
+	T centre = T(0.0), lap = T(0.0);
 	if (!ZERO)
 	{
 	    const bool weighted = HAS_W && k < a.nBoundary;
@@ -569,7 +580,7 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 	    {
 		const int r = ref[c][n];
 		if (r == BAND_SKIP) continue;
-		double u;
+		T u;
 		if (FROM_COMPACT && FZ)
 		{
 		    if (r < 0) continue;  // a frozen neighbour holds 0: lap -= c * 0 changes nothing
@@ -581,15 +592,15 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 		{
 		    const unsigned cc = (code[c] >> (2 * n)) & 3u;
 		    if (cc == 1u) lap -= u;  // 1 * u, bit for bit
-		    else if (cc == 2u) lap -= a.bcoef[int64_t(n) * a.nBoundary + k] * u;  // fractional: rare
+		    else if (cc == 2u) lap -= T(a.bcoef[int64_t(n) * a.nBoundary + k]) * u;  // fractional: rare
 		}
 		else lap -= u;
 	    }
 	    lap += diag[c] * centre;
 	}
-	double r = rhs - lap;
+	T r = rhs - lap;
 	r /= diag[c];
-	v[c] = centre + (2.0 / 3.0) * r;
+	v[c] = centre + T(2.0 / 3.0) * r;
     }
 #pragma unroll
     for (int c = 0; c < BAND_PER_THREAD; ++c)
@@ -600,11 +611,11 @@ __device__ __forceinline__ void bandBody(const BandArgs &a, int vb, int tid)
 	else a.vout[k] = v[c];
     }
 }
-template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false>
-__global__ void __launch_bounds__(BLOCK) k_band(const BandArgs a)
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false, typename T = double>
+__global__ void __launch_bounds__(BLOCK) k_band(const BandArgsT<T> a)
 {
     pdlLaunch();
-    bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W, FZ>(a, blockIdx.x, threadIdx.x);
+    bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W, FZ, false, T>(a, blockIdx.x, threadIdx.x);
 }
 
 
@@ -682,7 +693,123 @@ __global__ void __launch_bounds__(BLOCK) k_band_group(BandArgs a, int sweeps, in
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t *bandIdx, const double *v, int nBand)
+
+// ------------------------------------------------------------------------------------------------
+// The sweep group with its per-cell metadata RESIDENT for the whole group.  k_band_group above only replaces
+// kernel boundaries by barriers -- over ~900 CTAs, measured slower.  Here the grid is two 512-thread CTAs per SM (296 CTAs: a
+// barrier costs ~1.7 us, scripts/barrier_probe.cu), every thread OWNS up to CPT band cells for all sweeps of the group, and
+// what a sweep needs besides the neighbours' values stays on chip: right-hand side, diagonal, current value and coefficient
+// code in registers, the six neighbour references in shared memory (24 B per cell: 148 SMs x 2 x 512 x CPT cells of capacity).
+// Sweep 1 reads everything once; sweeps 2.. only gather the neighbours' values (compact array, ld.cg: written by other SMs
+// during this launch) and the few frozen / fractional ones.  Per cell the arithmetic and its order are bandBody's.
+// ------------------------------------------------------------------------------------------------
+constexpr int BG_THREADS = 512;
+
+template <bool HAS_W, bool ZEROGRID, int CPT>
+__global__ void __launch_bounds__(BG_THREADS, 2) k_band_resident(BandArgs a, int sweeps, GroupBarrier *bar)
+{
+    pdlLaunch();
+    extern __shared__ int refs[];  // [CPT][6][BG_THREADS]
+    const int tid = threadIdx.x;
+    const int gthreads = gridDim.x * BG_THREADS, gtid = blockIdx.x * BG_THREADS + tid;
+    double rhs[CPT], diag[CPT], val[CPT];
+    unsigned code[CPT];
+    // prologue (static): references into shared memory, diagonal, coefficient code (the grid index is re-read where it is
+    // needed, first and last sweep: registers are what limits the cells a thread can own)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+    {
+	const int k = c * gthreads + gtid;
+	diag[c] = 6.0;
+	code[c] = 0x555u;
+	if (k >= a.nBand) continue;
+#pragma unroll
+	for (int n = 0; n < 6; ++n) refs[(c * 6 + n) * BG_THREADS + tid] = a.bandRef[int64_t(n) * a.nBand + k];
+	if (k < a.nBoundary)
+	{
+	    diag[c] = a.bcoef[int64_t(6) * a.nBoundary + k];
+	    if (HAS_W) code[c] = a.wcode[k];
+	}
+    }
+    pdlWait();
+    double *cur = a.vout, *nxt = const_cast<double *>(a.vin);
+    // sweep 1: grid -> compact (bandBody<false, false, true, ZEROGRID, HAS_W>)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+    {
+	const int k = c * gthreads + gtid;
+	if (k >= a.nBand) continue;
+	const int64_t i = a.bandIdx[k];
+	rhs[c] = a.b[i];
+	double centre = 0.0, lap = 0.0;
+	if (!ZEROGRID)
+	{
+	    const bool weighted = HAS_W && k < a.nBoundary;
+	    centre = a.x[i];
+	    const int64_t stride[6] = {-1, 1, -int64_t(a.pitch), int64_t(a.pitch), -a.plane, a.plane};
+#pragma unroll
+	    for (int n = 0; n < 6; ++n)
+	    {
+		if (refs[(c * 6 + n) * BG_THREADS + tid] == BAND_SKIP) continue;
+		const double u = a.x[i + stride[n]];
+		if (weighted)
+		{
+		    const unsigned cc = (code[c] >> (2 * n)) & 3u;
+		    if (cc == 1u) lap -= u;
+		    else if (cc == 2u) lap -= a.bcoef[int64_t(n) * a.nBoundary + k] * u;
+		}
+		else lap -= u;
+	    }
+	    lap += diag[c] * centre;
+	}
+	double r = rhs[c] - lap;
+	r /= diag[c];
+	val[c] = centre + (2.0 / 3.0) * r;
+	if (sweeps == 1) a.x[i] = val[c];
+	else cur[k] = val[c];
+    }
+    for (int sw = 2; sw <= sweeps; ++sw)
+    {
+	gridBarrier(bar);
+	// compact -> compact, the last one compact -> grid (bandBody<true, last, false, false, HAS_W, ZEROGRID, true>)
+#pragma unroll
+	for (int c = 0; c < CPT; ++c)
+	{
+	    const int k = c * gthreads + gtid;
+	    if (k >= a.nBand) continue;
+	    const bool weighted = HAS_W && k < a.nBoundary;
+	    const double centre = val[c];
+	    double lap = 0.0;
+#pragma unroll
+	    for (int n = 0; n < 6; ++n)
+	    {
+		const int r = refs[(c * 6 + n) * BG_THREADS + tid];
+		if (r == BAND_SKIP) continue;
+		double u;
+		if (r >= 0) u = __ldcg(cur + r);
+		else if (ZEROGRID) continue;  // a frozen neighbour holds 0
+		else u = a.x[-2 - r];
+		if (weighted)
+		{
+		    const unsigned cc = (code[c] >> (2 * n)) & 3u;
+		    if (cc == 1u) lap -= u;
+		    else if (cc == 2u) lap -= a.bcoef[int64_t(n) * a.nBoundary + k] * u;
+		}
+		else lap -= u;
+	    }
+	    lap += diag[c] * centre;
+	    double rr = rhs[c] - lap;
+	    rr /= diag[c];
+	    val[c] = centre + (2.0 / 3.0) * rr;
+	    if (sw == sweeps) a.x[a.bandIdx[k]] = val[c];
+	    else nxt[k] = val[c];
+	}
+	double *t = cur; cur = nxt; nxt = t;
+    }
+}
+
+template <typename T = double>
+__global__ void __launch_bounds__(BLOCK) k_band_scatter(T *x, const int32_t *bandIdx, const T *v, int nBand)
 {
     pdlLaunch();
     const int k = blockIdx.x * BLOCK + threadIdx.x;
@@ -695,12 +822,13 @@ __global__ void __launch_bounds__(BLOCK) k_band_scatter(double *x, const int32_t
 // Restriction (Ops.h:734-835): coarse (active) = sum_{z,y,x} w[x]w[y]w[z] fine(2c-1+(x,y,z)), weights (1,3,3,1)/8.
 // One thread per coarse cell over the chunks holding active coarse cells.
 // ------------------------------------------------------------------------------------------------
-struct TransferArgs
+template <typename T>
+struct TransferArgsT
 {
     const uint8_t *fineLabels, *coarseLabels;
-    const double *fine;
-    const double *coarse;
-    double *out;
+    const T *fine;
+    const T *coarse;
+    T *out;
     const int32_t *chunks;
     int chunksPerPlane;
     int finePitch, coarsePitch;
@@ -709,13 +837,15 @@ struct TransferArgs
     int shift[3];
     int zlo, zhi;  // clip on the destination's z-planes (coarse planes for restriction, fine planes for prolongation)
 };
+typedef TransferArgsT<double> TransferArgs;
 
 // One virtual CTA covers one z-plane and one 256-cell half of a chunk (8 virtual CTAs per chunk): a coarse cell is 64 fine
 // reads, so the work is spread over as many threads as there are coarse cells.
 constexpr int RESTRICT_SPLIT = CHUNK_Z * 2;
-__device__ __forceinline__ void restrictBody(const TransferArgs &a, int vb, int tid)
+template <typename T>
+__device__ __forceinline__ void restrictBody(const TransferArgsT<T> &a, int vb, int tid)
 {
-    const double rw[4] = {1. / 8., 3. / 8., 3. / 8., 1. / 8.};
+    const T rw[4] = {T(1. / 8.), T(3. / 8.), T(3. / 8.), T(1. / 8.)};
     const int c = a.chunks[vb / RESTRICT_SPLIT];
     const int sub = vb % RESTRICT_SPLIT;
     const int zb = c / a.chunksPerPlane;
@@ -730,18 +860,18 @@ __device__ __forceinline__ void restrictBody(const TransferArgs &a, int vb, int 
     if (!(l == L_INTERIOR || l == L_BOUNDARY)) return;
     const int cy = int(unsigned(inPlane) / unsigned(a.coarsePitch)), cx = int(inPlane - int64_t(cy) * a.coarsePitch);
     const int fx = 2 * (cx - a.shift[0]) - 1, fy = 2 * (cy - a.shift[1]) - 1, fz = 2 * (cz - a.shift[2]) - 1;
-    const double *f = a.fine + (int64_t(fz) * a.finePlane + int64_t(fy) * a.finePitch + fx);
-    double v = 0.0;
+    const T *f = a.fine + (int64_t(fz) * a.finePlane + int64_t(fy) * a.finePitch + fx);
+    T v = T(0.0);
 #pragma unroll
     for (int z = 0; z < 4; ++z)
 #pragma unroll
 	for (int y = 0; y < 4; ++y)
 	{
-	    const double *row = f + int64_t(z) * a.finePlane + int64_t(y) * a.finePitch;
+	    const T *row = f + int64_t(z) * a.finePlane + int64_t(y) * a.finePitch;
 	    // fx is odd: row[1..2] is an aligned pair
-	    const double s0 = row[0];
-	    const double2 s12 = ld2(row + 1);
-	    const double s3 = row[3];
+	    const T s0 = row[0];
+	    const typename Vec2<T>::type s12 = ld2(row + 1);
+	    const T s3 = row[3];
 	    v += rw[0] * rw[y] * rw[z] * s0;
 	    v += rw[1] * rw[y] * rw[z] * s12.x;
 	    v += rw[2] * rw[y] * rw[z] * s12.y;
@@ -749,7 +879,8 @@ __device__ __forceinline__ void restrictBody(const TransferArgs &a, int vb, int 
 	}
     a.out[ci] = v;
 }
-__global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgs a) { pdlLaunch(); restrictBody(a, blockIdx.x, threadIdx.x); }
+template <typename T = double>
+__global__ void __launch_bounds__(BLOCK) k_restrict(const TransferArgsT<T> a) { pdlLaunch(); restrictBody<T>(a, blockIdx.x, threadIdx.x); }
 
 
 // ------------------------------------------------------------------------------------------------
@@ -826,11 +957,13 @@ __global__ void __launch_bounds__(BLOCK) k_cbrick_flags(uint8_t *flags, const ui
 // Prolongation (Ops.h:873-972): fine (active) += 4 * trilerp(8 coarse cells), fractions .25/.75.
 // One thread per aligned fine pair (the two x-children of one coarse cell).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double lerpRef(double v0, double v1, double f) { return (1. - f) * v0 + f * v1; }  // Ops.h:841-848
+template <typename T>
+__device__ __forceinline__ T lerpRef(T v0, T v1, T f) { return (T(1.) - f) * v0 + f * v1; }  // Ops.h:841-848
 
 // A thread owns the two x-children of one coarse cell in TWO consecutive z-planes (the two z-children): they interpolate
 // from the same 3 x 2 x 3 coarse values, which are loaded once.
-__device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int tid)
+template <typename T>
+__device__ __forceinline__ void prolongBody(const TransferArgsT<T> &a, int vb, int tid)
 {
     const int c = a.chunks[vb];
     const int zb = c / a.chunksPerPlane;
@@ -850,7 +983,7 @@ __device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int t
     const int mx = (fx >> 1) + a.shift[0];
     const int my = (fy >> 1) + a.shift[1];
     const int ys = (fy & 1) ? my : my - 1;
-    const double wy = (fy & 1) ? .25 : .75;
+    const T wy = (fy & 1) ? T(.25) : T(.75);
 #pragma unroll
     for (int p = 0; p < CHUNK_Z / 2; ++p)
     {
@@ -863,23 +996,23 @@ __device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int t
 	const int mz = (fz0 >> 1) + a.shift[2];
 	// x-lerps right after each row load (even x-child: start = m-1, f = .75; odd: start = m, f = .25), then y, then z:
 	// the nesting and operation order of Ops.h:841-871, with 12 live values instead of 18
-	double ex[2][3], ox[2][3];  // [y: ys, ys+1][z: mz-1..mz+1]
+	T ex[2][3], ox[2][3];  // [y: ys, ys+1][z: mz-1..mz+1]
 #pragma unroll
 	for (int z = 0; z < 3; ++z)
 #pragma unroll
 	    for (int y = 0; y < 2; ++y)
 	    {
-		const double *row = a.coarse + (int64_t(mz - 1 + z) * a.coarsePlane + int64_t(ys + y) * a.coarsePitch + mx);
-		const double v0 = row[-1], v1 = row[0], v2 = row[1];
-		ex[y][z] = lerpRef(v0, v1, .75);
-		ox[y][z] = lerpRef(v1, v2, .25);
+		const T *row = a.coarse + (int64_t(mz - 1 + z) * a.coarsePlane + int64_t(ys + y) * a.coarsePitch + mx);
+		const T v0 = row[-1], v1 = row[0], v2 = row[1];
+		ex[y][z] = lerpRef<T>(v0, v1, T(.75));
+		ox[y][z] = lerpRef<T>(v1, v2, T(.25));
 	    }
-	double ey[3], oy[3];
+	T ey[3], oy[3];
 #pragma unroll
 	for (int z = 0; z < 3; ++z)
 	{
-	    ey[z] = lerpRef(ex[0][z], ex[1][z], wy);
-	    oy[z] = lerpRef(ox[0][z], ox[1][z], wy);
+	    ey[z] = lerpRef<T>(ex[0][z], ex[1][z], wy);
+	    oy[z] = lerpRef<T>(ox[0][z], ox[1][z], wy);
 	}
 	// the two z-children: even plane start = m-1, f = .75; odd plane start = m, f = .25
 #pragma unroll
@@ -888,18 +1021,19 @@ __device__ __forceinline__ void prolongBody(const TransferArgs &a, int vb, int t
 	    const bool ax = q ? a10 : a00, ay = q ? a11 : a01;
 	    if (!(ax | ay)) continue;
 	    const int64_t i = q ? i1 : i0;
-	    const double wz = q ? .25 : .75;
-	    const double2 old = ld2(a.out + i);
-	    const double e = lerpRef(ey[q], ey[q + 1], wz);
-	    const double o = lerpRef(oy[q], oy[q + 1], wz);
-	    const double n0 = old.x + 4. * e, n1 = old.y + 4. * o;
-	    if (ax & ay) st2(a.out + i, make_double2(n0, n1));
+	    const T wz = q ? T(.25) : T(.75);
+	    const typename Vec2<T>::type old = ld2(a.out + i);
+	    const T e = lerpRef<T>(ey[q], ey[q + 1], wz);
+	    const T o = lerpRef<T>(oy[q], oy[q + 1], wz);
+	    const T n0 = old.x + T(4.) * e, n1 = old.y + T(4.) * o;
+	    if (ax & ay) st2(a.out + i, make2<T>(n0, n1));
 	    else if (ax) a.out[i] = n0;
 	    else a.out[i + 1] = n1;
 	}
     }
 }
-__global__ void __launch_bounds__(BLOCK, 6) k_prolong(const TransferArgs a) { pdlLaunch(); prolongBody(a, blockIdx.x, threadIdx.x); }
+template <typename T = double>
+__global__ void __launch_bounds__(BLOCK, 6) k_prolong(const TransferArgsT<T> a) { pdlLaunch(); prolongBody<T>(a, blockIdx.x, threadIdx.x); }
 
 
 // ------------------------------------------------------------------------------------------------
@@ -1653,8 +1787,8 @@ __global__ void __launch_bounds__(CYCLE_THREADS, 1) k_compact_cycle(const Compac
 		v[q] = j != CYCLE_NONE ? xc[j] : 0.0;
 	    }
 	    // corner q = x + 2 y + 4 z; lerp nesting x -> y -> z (Ops.h:841-871)
-	    const double e = lerpRef(lerpRef(lerpRef(v[0], v[1], wx), lerpRef(v[2], v[3], wx), wy),
-				     lerpRef(lerpRef(v[4], v[5], wx), lerpRef(v[6], v[7], wx), wy), wz);
+	    const double e = lerpRef<double>(lerpRef<double>(lerpRef<double>(v[0], v[1], wx), lerpRef<double>(v[2], v[3], wx), wy),
+				     lerpRef<double>(lerpRef<double>(v[4], v[5], wx), lerpRef<double>(v[6], v[7], wx), wy), wz);
 	    x[k] = x[k] + 4. * e;
 	}
 	__syncthreads();

@@ -10,7 +10,8 @@ import subprocess
 import sys
 
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-CLASSES = [("k_stencil<0", "jacobi_interior"), ("k_stencil<1", "apply_poisson"), ("k_stencil<2", "residual"), ("k_band", "band_jacobi"),
+CLASSES = [("k_stencil<0", "jacobi_interior"), ("k_stencil<3", "jacobi_interior"), ("k_stencil<1", "apply_poisson"), ("k_stencil<2", "residual"),
+           ("k_stencil_tma<0", "jacobi_interior"), ("k_stencil_tma<1", "apply_poisson"), ("k_stencil_tma<2", "residual"), ("k_band", "band_jacobi"),
            ("k_restrict", "restrict"), ("k_prolong", "prolong_add"), ("k_zero", "zero_fill"), ("k_vec<3", "reduce"), ("k_vec<4", "reduce"),
            ("k_vec", "blas1"), ("k_gauss_seidel", "gauss_seidel")]
 
@@ -25,7 +26,7 @@ def klass(name):
 
 def main():
     out = {}
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    path = os.environ.get("GMG_TRAFFIC_JSON") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
     if os.path.exists(path):
         out = json.load(open(path))
     for arg in sys.argv[1:]:

@@ -397,8 +397,8 @@ def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
     results = {}
     for name, env in [("cluster", {"GMG_CLUSTER_CYCLE": "1"}), ("compact", {}), ("kernels", {"GMG_COARSE_FUSED": "0"}),
                       ("zero_fill", {"GMG_ZERO_AWARE": "0"}), ("cluster8", {"GMG_CLUSTER_CYCLE": "1", "GMG_CLUSTER_SIZE": "8"}), ("first2", {"GMG_CLUSTER_CYCLE": "1", "GMG_FUSED_FIRST": "2"}),
-                      ("tma", {"GMG_TMA": "31", "GMG_TMA_MIN_CELLS": "100"}), ("sweep_groups", {"GMG_BAND_GROUPS": "1"})]:
-        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS", "GMG_BAND_GROUPS"):
+                      ("tma", {"GMG_TMA": "31", "GMG_TMA_MIN_CELLS": "100"}), ("sweep_groups", {"GMG_BAND_GROUPS": "1"}), ("sweep_resident", {"GMG_BAND_RESIDENT": "1"})]:
+        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS", "GMG_BAND_GROUPS", "GMG_BAND_RESIDENT"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
