@@ -590,6 +590,31 @@ def run_gpu_arm(args, rank, world, local_rank):
               "what": "same solve with useGaussSeidel = true (tiled Gauss-Seidel wavefront kernel), mean of 3 after 2 warm-ups"}
         sg.close()
 
+    # ---- mixed precision, reported beside the fp64 headline, never as it: fp32 V-cycle inside the fp64 CG -----------
+    mixed = None
+    if world == 1 and not args.quick:
+        try:
+            sm = api.GeometricMultigridPoissonSolver(ctx, labels, w, levels, box=box, mixed_precision=True)
+            Bm, Xm = sm.grid(0, b_host), sm.grid(0)
+            mms = []
+            for k in range(5):
+                Xm.zero()
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                ctx.timer_begin()
+                itm, histm = sm.solveDevice(Xm, Bm, TOL, MAX_IT)
+                t = ctx.timer_end()
+                if k >= 2:
+                    mms.append(t)
+            X.zero()
+            it64, hist64 = solver.solveDevice(X, B, TOL, MAX_IT)
+            mixed = {"solve_ms": float(np.mean(mms)), "iterations": int(itm), "iterations_fp64": int(it64), "final_rel_residual": float(histm[-1]),
+                     "max_rel_history_drift_vs_fp64": rel_history_dev(histm, hist64),
+                     "what": "gmg_solver_options.mixed_precision = 1: fp32 V-cycle (kernel levels) inside the fp64 CG, mean of 3 after 2 warm-ups; NOT the headline dtype"}
+            Bm.close(); Xm.close(); sm.close()
+        except Exception as e:
+            mixed = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- parity, asserted (a failed bar makes the process exit non-zero after the line is printed) -------------------------
     parity_failed = []
     X.zero()
@@ -662,7 +687,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "kernel_timing": "CUDA events recorded as nodes inside the replayed PCG graphs (warm L2, back-to-back launches); separate pass from `value`",
             "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "gauss_seidel": gs, "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "wall_s_timed_region": wall_s,
             "parity_vs_cpu": parity_vs_cpu, "parity_vs_n1": parity_vs_n1, "parity_failed": parity_failed,
-            "sweep512": sweep, "narrow1024": narrow,
+            "sweep512": sweep, "narrow1024": narrow, "mixed_precision": mixed,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

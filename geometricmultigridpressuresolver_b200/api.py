@@ -105,6 +105,7 @@ class SolverOptions(C.Structure):
         ("box_lo", C.c_int64 * 3),
         ("box_hi", C.c_int64 * 3),
         ("operators_only", C.c_int),
+        ("mixed_precision", C.c_int),
     ]
 
 
@@ -433,7 +434,7 @@ class GeometricMultigridPoissonSolver:
     """HDK::GeometricMultigridPoissonSolver (HDK_GeometricMultigridPoissonSolver.h:10-53) on the GPU."""
 
     def __init__(self, ctx: Context, initialCellLabels, boundaryWeights, mgLevels: int, useGaussSeidel: bool = False, doPrintStats: bool = False,
-                 coarse_matrix_scale: float = 1.0, box=None, boundary_iterations: int = 3, boundary_width: int = 3):
+                 coarse_matrix_scale: float = 1.0, box=None, boundary_iterations: int = 3, boundary_width: int = 3, mixed_precision: bool = False):
         self.ctx = ctx
         self.lib = ctx.lib
         # one-byte labels (uint8 / int8 arrays) go through gmg_solver_create_u8: a quarter of the host memory and PCIe traffic
@@ -456,6 +457,7 @@ class GeometricMultigridPoissonSolver:
         opt.coarse_matrix_scale = float(coarse_matrix_scale)
         opt.boundary_iterations = int(boundary_iterations)
         opt.boundary_width = int(boundary_width)
+        opt.mixed_precision = int(mixed_precision)  # fp32 V-cycle inside the fp64 CG (README.md:34-35 TODO of the reference); not reference arithmetic
         if box is not None:
             for a in range(3):
                 opt.box_lo[a] = int(box[0][a])

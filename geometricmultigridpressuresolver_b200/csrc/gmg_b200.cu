@@ -115,6 +115,19 @@ static void freeGrid(double *p, const Geom &g)
 {
     if (p) devFree(p - g.plane);
 }
+static int allocGrid32(float **p, const Geom &g)
+{
+    float *base = nullptr;
+    const int64_t n = g.total + 2 * g.plane;
+    GMG_CUDA(devMalloc(&base, sizeof(float) * n));
+    GMG_CUDA(cudaMemsetAsync(base, 0, sizeof(float) * n, g_stream));
+    *p = base + g.plane;
+    return GMG_OK;
+}
+static void freeGrid32(float *p, const Geom &g)
+{
+    if (p) devFree(p - g.plane);
+}
 
 // Programmatic dependent launch: a V-cycle is a chain of ~60 dependent kernels, most of them a few microseconds long, so the
 // launch-to-launch gap matters as much as the kernels.  Every hot kernel starts with griddepcontrol.launch_dependents +
@@ -1401,6 +1414,8 @@ static void freeLevel(Level &L)
     devFree(L.chunksInterior); devFree(L.chunksActive); devFree(L.bricks); devFree(L.bricksActive); devFree(L.cbricks);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
+    freeGrid32(L.x32, L.g); freeGrid32(L.xAlt32, L.g); freeGrid32(L.b32, L.g); freeGrid32(L.r32, L.g);
+    devFree(L.bandV0f); devFree(L.bandV1f); devFree(L.bandBf);
     L = Level();
 }
 
@@ -2232,6 +2247,7 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     if (const char *e = getenv("GMG_NO_GRAPHS")) s->useGraphs = !(e[0] == '1');
     if (const char *e = getenv("GMG_PRINT_STATS")) s->opt.print_stats = (e[0] == '1');
     if (const char *e = getenv("GMG_ZERO_AWARE")) s->zeroAware = !(e[0] == '0');
+    if (const char *e = getenv("GMG_MIXED")) s->opt.mixed_precision = (e[0] == '1');
     s->tmaMask = tmaMode();
     if (const char *e = getenv("GMG_BAND_GROUPS")) s->bandGroups = (e[0] == '1');
     if (const char *e = getenv("GMG_BAND_RESIDENT")) s->bandResident = (e[0] == '1');
@@ -3588,11 +3604,252 @@ static int ensureDiagInverse(gmg_solver *s)
     return GMG_OK;
 }
 
+
+// ====================================================================================================
+// Mixed precision (the reference's own TODO, README.md:34-35): the multigrid preconditioner in fp32 inside
+// the fp64 CG.  The levels that run as kernels use the float instantiations of the same stencil / band / transfer bodies on
+// fp32 copies of their grids (half the bytes of every V-cycle pass); the fused coarse cycle keeps its fp64 shared-memory
+// arithmetic and converts at its top level.  r crosses into fp32 once, z back into fp64 once.  Single GPU, Jacobi smoother.
+// ====================================================================================================
+static int ensureMixed(gmg_solver *s)
+{
+    if (s->lv[0].x32) return GMG_OK;
+    if (s->ctx->world > 1) return invalid("mixed_precision is available on single-GPU contexts only");
+    if (s->opt.use_gauss_seidel) return invalid("mixed_precision needs the damped-Jacobi smoother");
+    if (s->fusedFirst > 0 && !s->compactArgs) return invalid("mixed_precision does not combine with the cluster coarse cycle (GMG_CLUSTER_CYCLE=1)");
+    if (s->opt.boundary_iterations < 1) return invalid("mixed_precision needs at least one boundary smoother iteration");
+    if (s->levels < 2) return invalid("mixed_precision needs at least two levels");
+    // levels [0, nReg) run as fp32 kernels; level nReg is the top of the fused coarse cycle, or the direct solve's level
+    const int nReg = s->fusedFirst > 0 ? s->fusedFirst : s->levels - 1;
+    for (int l = 0; l <= nReg; ++l)
+    {
+	Level &L = s->lv[l];
+	GMG_TRY(allocGrid32(&L.x32, L.g));
+	GMG_TRY(allocGrid32(&L.b32, L.g));
+	if (l < nReg)
+	{
+	    GMG_TRY(allocGrid32(&L.xAlt32, L.g));
+	    GMG_TRY(allocGrid32(&L.r32, L.g));
+	    const size_t n1 = size_t(std::max(L.nBand, 1));
+	    GMG_CUDA(devMalloc(&L.bandV0f, sizeof(float) * n1));
+	    GMG_CUDA(devMalloc(&L.bandV1f, sizeof(float) * n1));
+	    GMG_CUDA(devMalloc(&L.bandBf, sizeof(float) * n1));
+	}
+    }
+    return GMG_OK;
+}
+
+static int launchStencil32(gmg_solver *s, int level, int mode, const float *in, const float *b, float *out)
+{
+    s->ctx->curLevel = level;
+    const Level &L = s->lv[level];
+    StencilArgsT<float> a;
+    a.labels = L.labels; a.flags = L.bandFlags; a.in = in; a.b = b; a.out = out;
+    a.chunks = L.chunksInterior; a.nChunks = L.nChunksInterior; a.chunksPerPlane = L.g.chunksPerPlane;
+    a.pitch = L.g.pitch; a.plane = L.g.plane; a.nz = L.g.n[2]; a.zlo = 0; a.zhi = L.g.n[2]; a.dotLo = 0; a.dotHi = L.g.n[2];
+    a.nBoundary = L.nBoundary; a.bandIdx = L.bandIdx; a.bcoef = L.bcoef; a.wcode = L.wcode;
+    a.partials = nullptr; a.ticket = nullptr; a.result = nullptr;
+    const unsigned grid = unsigned(L.nChunksInterior + divUp(L.nBoundary, BLOCK));
+    if (grid == 0) return GMG_OK;
+    cudaStream_t st = s->ctx->stream;
+    const double n = double(L.nActive);
+    if (mode == SM_JACOBI)
+    {
+	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 13.0);
+	GMG_CUDA(launchK((k_stencil<SM_JACOBI, false, float>), grid, unsigned(BLOCK), size_t(0), st, a));
+    }
+    else if (mode == SM_JACOBI_ZERO)
+    {
+	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 10.0);
+	GMG_CUDA(launchK((k_stencil<SM_JACOBI_ZERO, false, float>), grid, unsigned(BLOCK), size_t(0), st, a));
+    }
+    else
+    {
+	GMG_LAUNCH(s->ctx, KC_RESIDUAL, n * 13.0);
+	GMG_CUDA(launchK((k_stencil<SM_RESIDUAL, false, float>), grid, unsigned(BLOCK), size_t(0), st, a));
+    }
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+static int launchBand32(gmg_solver *s, int level, float *x, const float *b, int sweeps, bool zeroGrid)
+{
+    s->ctx->curLevel = level;
+    const Level &L = s->lv[level];
+    if (L.nBand == 0 || sweeps <= 0) return GMG_OK;
+    BandArgsT<float> a;
+    a.x = x; a.b = b; a.bandIdx = L.bandIdx; a.bandRef = L.bandRef; a.bcoef = L.bcoef; a.wcode = L.wcode; a.bandB = L.bandBf;
+    a.nBoundary = L.nBoundary; a.nBand = L.nBand; a.pitch = L.g.pitch; a.plane = L.g.plane;
+    const unsigned grid = unsigned(divUp(L.nBand, BLOCK * BAND_PER_THREAD));
+    cudaStream_t st = s->ctx->stream;
+    const double bytes = double(L.nBand) * 17.0;
+    const bool hw = L.hasWeights;
+    float *cur = L.bandV0f, *nxt = L.bandV1f;
+    a.vin = nullptr;
+    a.vout = cur;
+    {
+	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
+	if (zeroGrid) GMG_CUDA(launchK((k_band<false, false, true, true, false, false, float>), grid, BLOCK, 0, st, a));
+	else if (hw) GMG_CUDA(launchK((k_band<false, false, true, false, true, false, float>), grid, BLOCK, 0, st, a));
+	else GMG_CUDA(launchK((k_band<false, false, true, false, false, false, float>), grid, BLOCK, 0, st, a));
+    }
+    if (sweeps == 1)
+    {
+	GMG_LAUNCH(s->ctx, KC_BAND, double(L.nBand) * 12.0);
+	GMG_CUDA(launchK(k_band_scatter<float>, unsigned(divUp(L.nBand, BLOCK)), BLOCK, 0, st, x, L.bandIdx, static_cast<const float *>(cur), L.nBand));
+    }
+    for (int sw = 2; sw <= sweeps; ++sw)
+    {
+	a.vin = cur;
+	a.vout = nxt;
+	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
+	if (sw == sweeps)
+	{
+	    if (zeroGrid && hw) GMG_CUDA(launchK((k_band<true, true, false, false, true, true, float>), grid, BLOCK, 0, st, a));
+	    else if (zeroGrid) GMG_CUDA(launchK((k_band<true, true, false, false, false, true, float>), grid, BLOCK, 0, st, a));
+	    else if (hw) GMG_CUDA(launchK((k_band<true, true, false, false, true, false, float>), grid, BLOCK, 0, st, a));
+	    else GMG_CUDA(launchK((k_band<true, true, false, false, false, false, float>), grid, BLOCK, 0, st, a));
+	}
+	else
+	{
+	    if (zeroGrid && hw) GMG_CUDA(launchK((k_band<true, false, false, false, true, true, float>), grid, BLOCK, 0, st, a));
+	    else if (zeroGrid) GMG_CUDA(launchK((k_band<true, false, false, false, false, true, float>), grid, BLOCK, 0, st, a));
+	    else if (hw) GMG_CUDA(launchK((k_band<true, false, false, false, true, false, float>), grid, BLOCK, 0, st, a));
+	    else GMG_CUDA(launchK((k_band<true, false, false, false, false, false, float>), grid, BLOCK, 0, st, a));
+	}
+	std::swap(cur, nxt);
+    }
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+static TransferArgsT<float> transferArgs32(gmg_solver *s, int fineLevel)
+{
+    const Level &F = s->lv[fineLevel], &C = s->lv[fineLevel + 1];
+    TransferArgsT<float> a;
+    a.fineLabels = F.labels; a.coarseLabels = C.labels;
+    a.finePitch = F.g.pitch; a.coarsePitch = C.g.pitch; a.finePlane = F.g.plane; a.coarsePlane = C.g.plane;
+    a.fineNz = F.g.n[2]; a.coarseNz = C.g.n[2]; a.coarseNy = C.g.n[1];
+    for (int k = 0; k < 3; ++k) a.shift[k] = F.shift[k];
+    a.fine = nullptr; a.coarse = nullptr; a.out = nullptr; a.chunks = nullptr; a.chunksPerPlane = 0;
+    a.zlo = 0; a.zhi = 0;
+    return a;
+}
+
+// one V-cycle in fp32: x32 = M^-1 b32 on level 0's fp32 grids (zero initial guess; the structure of vcycleLaunches)
+static int vcycleLaunches32(gmg_solver *s)
+{
+    const int it = s->opt.boundary_iterations;
+    const int nReg = s->fusedFirst > 0 ? s->fusedFirst : s->levels - 1;  // levels 0 .. nReg-1 run as kernels
+    std::vector<float *> cur(std::max(nReg, 1)), alt(std::max(nReg, 1));
+    auto smooth = [&](int level, bool zeroGrid) -> int {
+	Level &L = s->lv[level];
+	GMG_TRY(launchBand32(s, level, cur[level], L.b32, it, zeroGrid));
+	GMG_TRY(launchStencil32(s, level, zeroGrid ? SM_JACOBI_ZERO : SM_JACOBI, cur[level], L.b32, alt[level]));
+	std::swap(cur[level], alt[level]);
+	GMG_TRY(launchBand32(s, level, cur[level], L.b32, it, false));
+	return GMG_OK;
+    };
+    for (int level = 0; level < nReg; ++level)
+    {
+	Level &L = s->lv[level], &C = s->lv[level + 1];
+	cur[level] = L.x32;
+	alt[level] = L.xAlt32;
+	GMG_TRY(smooth(level, true));
+	GMG_TRY(launchStencil32(s, level, SM_RESIDUAL, cur[level], L.b32, L.r32));
+	if (C.nChunksActive > 0)
+	{
+	    s->ctx->curLevel = level + 1;
+	    TransferArgsT<float> a = transferArgs32(s, level);
+	    a.fine = L.r32; a.out = C.b32; a.chunks = C.chunksActive; a.chunksPerPlane = C.g.chunksPerPlane; a.zlo = 0; a.zhi = C.g.n[2];
+	    GMG_LAUNCH(s->ctx, KC_RESTRICT, double(L.nActive) * 4.0 + double(C.nActive) * 5.0);
+	    GMG_CUDA(launchK(k_restrict<float>, unsigned(C.nChunksActive * RESTRICT_SPLIT), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
+	}
+    }
+    if (s->fusedFirst <= 0)
+    {
+	// no fused cycle: the direct solve of the coarsest level in fp64, through that level's fp64 grids
+	Level &C = s->lv[s->levels - 1];
+	s->ctx->curLevel = s->levels - 1;
+	if (C.nChunksActive > 0)
+	{
+	    GMG_LAUNCH(s->ctx, KC_BLAS1, double(C.nActive) * 12.0);
+	    GMG_CUDA(launchK((k_convert<double, float>), unsigned(C.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, C.b, static_cast<const float *>(C.b32),
+			     C.chunksActive, C.g.chunksPerPlane, C.g.plane, C.g.n[2]));
+	}
+	GMG_TRY(launchCoarse(s, C.x, C.b));
+	if (C.nChunksActive > 0)
+	{
+	    GMG_LAUNCH(s->ctx, KC_BLAS1, double(C.nActive) * 12.0);
+	    GMG_CUDA(launchK((k_convert<float, double>), unsigned(C.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, C.x32, static_cast<const double *>(C.x),
+			     C.chunksActive, C.g.chunksPerPlane, C.g.plane, C.g.n[2]));
+	}
+    }
+    else
+    {
+	// the fused coarse cycle, fp64 inside, reading / writing the fp32 grids of its top level
+	s->ctx->curLevel = s->fusedFirst;
+	CompactArgs c = *static_cast<const CompactArgs *>(s->compactArgs);
+	c.bTop32 = s->lv[s->fusedFirst].b32;
+	c.xTop32 = s->lv[s->fusedFirst].x32;
+	double bytes = 0;
+	for (int l = s->fusedFirst; l < s->levels - 1; ++l) bytes += double(s->lv[l].nActive) * 126.0;
+	GMG_LAUNCH(s->ctx, KC_COARSE, bytes);
+	GMG_CUDA(launchK(k_compact_cycle, unsigned(1), unsigned(CYCLE_THREADS), size_t(s->compactSmem), s->ctx->stream, c));
+    }
+    for (int level = nReg - 1; level >= 0; --level)
+    {
+	Level &L = s->lv[level], &C = s->lv[level + 1];
+	if (L.nChunksActive > 0)
+	{
+	    s->ctx->curLevel = level;
+	    TransferArgsT<float> a = transferArgs32(s, level);
+	    // the level below hands over its result in its x32 grid (two Jacobi swaps, or the fused cycle)
+	    a.coarse = C.x32; a.out = cur[level]; a.chunks = L.chunksActive; a.chunksPerPlane = L.g.chunksPerPlane; a.zlo = 0; a.zhi = L.g.n[2];
+	    GMG_LAUNCH(s->ctx, KC_PROLONG, double(L.nActive) * 9.0 + double(C.nActive) * 4.0);
+	    GMG_CUDA(launchK(k_prolong<float>, unsigned(L.nChunksActive), unsigned(BLOCK), size_t(0), s->ctx->stream, a));
+	}
+	GMG_TRY(smooth(level, false));
+    }
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;  // two swaps per level: every level's result is back in its x32
+}
+
+// z = M^-1 r with the fp32 V-cycle: r -> fp32, V-cycle, -> fp64
+static int mixedPreconditioner(gmg_solver *s, double *z, const double *r)
+{
+    GMG_TRY(ensureMixed(s));
+    gmg_ctx *ctx = s->ctx;
+    Level &L = s->lv[0];
+    if (L.nChunksActive == 0) return GMG_OK;
+    ctx->curLevel = 0;
+    {
+	GMG_LAUNCH(ctx, KC_BLAS1, double(L.nActive) * 12.0);
+	GMG_CUDA(launchK((k_convert<float, double>), unsigned(L.nChunksActive), unsigned(BLOCK), size_t(0), ctx->stream, L.b32, r, L.chunksActive, L.g.chunksPerPlane,
+			 L.g.plane, L.g.n[2]));
+    }
+    GMG_TRY(vcycleLaunches32(s));
+    {
+	ctx->curLevel = 0;
+	GMG_LAUNCH(ctx, KC_BLAS1, double(L.nActive) * 12.0);
+	GMG_CUDA(launchK((k_convert<double, float>), unsigned(L.nChunksActive), unsigned(BLOCK), size_t(0), ctx->stream, z, static_cast<const float *>(L.x32), L.chunksActive,
+			 L.g.chunksPerPlane, L.g.plane, L.g.n[2]));
+    }
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
 // z = M^-1 r for the three preconditioners of the ABI: 0 none (plain CG), 1 multigrid V-cycle (GFS.cpp:468-472),
 // 2 diagonal (GFS.cpp:562-603)
 static int applyPreconditioner(gmg_solver *s, int precond, double *z, const double *r, bool direct)
 {
     const ZRange own = clipDepth(s->lv[0], 0);
+    if (precond == 1 && s->opt.mixed_precision)
+    {
+	if (direct || !s->useGraphs) return mixedPreconditioner(s, z, r);
+	GMG_TRY(ensureMixed(s));  // allocations stay outside the capture
+	return runGraphed(s, 4, z, r, 0, [&]() { return mixedPreconditioner(s, z, r); });
+    }
     if (precond == 1) return direct ? vcycleLaunches(s, z, r, false) : vcycleDevice(s, z, r, false);
     if (precond == 2) return launchVec<VO_MUL>(s, 0, z, r, s->diagInv, nullptr, 0, nullptr, KC_BLAS1, 24.0, own);
     return launchVec<VO_COPY>(s, 0, z, r, nullptr, nullptr, 0, nullptr, KC_BLAS1, 16.0, own);
@@ -3648,6 +3905,7 @@ static int pcgDevice(gmg_solver *s, double *x, const double *b, double tol, int 
     // is replayed once costs more than it saves.  From the second solve on they are cached graphs like the rest.
     if (precond == 1 && s->opt.operators_only && s->levels > 1) return invalid("this solver handle was created with operators_only: no coarse factor, no V-cycle");
     if (precond == 2) GMG_TRY(ensureDiagInverse(s));
+    if (precond == 1 && s->opt.mixed_precision) GMG_TRY(ensureMixed(s));
     // (single GPU only: on a sharded context every exchange stays inside the graphs it was validated in)
     const bool firstSolve = (s->pcgSolves++ == 0) && !ctx->profiling && ctx->world == 1;
     GMG_TRY(applyPreconditioner(s, precond, p, r, firstSolve));

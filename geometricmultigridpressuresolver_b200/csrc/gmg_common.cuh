@@ -104,6 +104,9 @@ struct Level
     int nCBricks = 0, cbricksX = 0, cbricksY = 0;
     // V-cycle grids (level 0 uses caller grids for x and b)
     double *x = nullptr, *xAlt = nullptr, *b = nullptr, *r = nullptr;
+    // mixed precision (gmg_solver_options::mixed_precision): the V-cycle's grids and compact band arrays once more in fp32
+    float *x32 = nullptr, *xAlt32 = nullptr, *b32 = nullptr, *r32 = nullptr;
+    float *bandV0f = nullptr, *bandV1f = nullptr, *bandBf = nullptr;
     int shift[3] = {0, 0, 0};    // coarse storage = (this level's storage >> 1) + shift   (to level+1)
     // tiled Gauss-Seidel (only built when the solver uses it): 16^3 tiles of the EXPANDED grid laid over the storage box
     int32_t *gsTiles[2] = {nullptr, nullptr};  // [0] even, [1] odd tiles holding an active cell (linear tile ids)

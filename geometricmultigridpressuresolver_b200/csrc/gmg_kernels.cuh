@@ -1298,6 +1298,27 @@ __global__ void __launch_bounds__(BLOCK) k_vec(const VecArgs v)
     if (OP == VO_MAX) gridReduce<true>(acc, v.partials, v.ticket, v.result);
 }
 
+// fp64 <-> fp32 over the active chunks (mixed precision: the V-cycle's input and output cross the precision boundary once each)
+template <typename TO, typename FROM>
+__global__ void __launch_bounds__(BLOCK) k_convert(TO *dst, const FROM *src, const int32_t *chunks, int chunksPerPlane, int64_t plane, int nz)
+{
+    pdlLaunch();
+    const int c = chunks[blockIdx.x];
+    pdlWait();
+    const int zb = c / chunksPerPlane;
+    const int64_t inPlane = int64_t(c - zb * chunksPerPlane) * CHUNK_CELLS + 2 * threadIdx.x;
+    if (inPlane >= plane) return;
+#pragma unroll
+    for (int dz = 0; dz < CHUNK_Z; ++dz)
+    {
+	const int z = zb * CHUNK_Z + dz;
+	if (z >= nz) break;
+	const int64_t i = int64_t(z) * plane + inPlane;
+	const typename Vec2<FROM>::type v = ld2(src + i);
+	st2(dst + i, make2<TO>(TO(v.x), TO(v.y)));
+    }
+}
+
 // zero the active chunks of a grid (x = 0 at the start of a V-cycle level, MG.cpp:439-440, :566)
 __device__ __forceinline__ void zeroBody(double *y, int c, int chunksPerPlane, int64_t plane, int nz, int tid)
 {
@@ -1647,6 +1668,8 @@ struct CompactArgs
     const int32_t *cellTop;   // [lv[0].n] storage index of lv[0]'s cells in its grid
     const double *bTop;       // rhs grid of lv[0] (written by the restriction kernel of the level above)
     double *xTop;             // solution grid of lv[0] (read by the prolongation kernel of the level above)
+    const float *bTop32;      // mixed precision: the same two grids in fp32 (then bTop / xTop are unused); the cycle itself stays fp64
+    float *xTop32;
     const double *inv;        // [nSolve][nSolve]
 };
 
@@ -1708,7 +1731,10 @@ __global__ void __launch_bounds__(CYCLE_THREADS, 1) k_compact_cycle(const Compac
 	pdlWait();
 	const CompactLevel &L = c.lv[0];
 	double *b = sm + L.off + 2 * L.n;
-	for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) b[k] = c.bTop[__ldg(c.cellTop + k)];
+	if (c.bTop32)
+	    for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) b[k] = double(c.bTop32[__ldg(c.cellTop + k)]);
+	else
+	    for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) b[k] = c.bTop[__ldg(c.cellTop + k)];
     }
     // ---- down-stroke (MG.cpp:557-667): x = 0, smooth, residual, restrict
     for (int l = 0; l + 1 < nl; ++l)
@@ -1797,7 +1823,10 @@ __global__ void __launch_bounds__(CYCLE_THREADS, 1) k_compact_cycle(const Compac
     {
 	const CompactLevel &L = c.lv[0];
 	const double *x = sm + L.off;
-	for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) c.xTop[__ldg(c.cellTop + k)] = x[k];
+	if (c.xTop32)
+	    for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) c.xTop32[__ldg(c.cellTop + k)] = float(x[k]);
+	else
+	    for (int k = threadIdx.x; k < L.n; k += CYCLE_THREADS) c.xTop[__ldg(c.cellTop + k)] = x[k];
     }
 }
 

@@ -111,6 +111,11 @@ typedef struct gmg_solver_options
     int64_t box_lo[3], box_hi[3]; /* optional non-EXTERIOR bounds hint (all zero = scan the labels) */
     int operators_only;       /* 1: build labels/bands/records only, no coarse factor -- a handle for the stateless operator
 				 functions of the facade (gmg_vcycle / gmg_pcg with the V-cycle then fail with GMG_ERR_INVALID) */
+    int mixed_precision;      /* 1: gmg_pcg applies the multigrid preconditioner in fp32 (every V-cycle grid and smoother sweep of the
+				 levels that run as kernels; the fused coarse cycle stays fp64) inside the fp64 CG -- the reference's own
+				 TODO (README.md:34-35).  NOT the reference arithmetic: the residual history drifts (bench.py reports by how
+				 much) although the CG itself, its operator and its convergence test stay fp64.  Single-GPU contexts,
+				 damped-Jacobi smoother; gmg_vcycle and the operator entry points are unaffected.  Default 0. */
 } gmg_solver_options;
 void gmg_solver_default_options(gmg_solver_options *opt);
 

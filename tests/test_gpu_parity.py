@@ -414,3 +414,28 @@ def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
             assert it == ref[2][1] and relerr(hist, ref[2][2]) < 1e-11 and relerr(x, ref[2][0]) < 1e-11, name
         else:
             assert it == ref[2][1] and (hist == ref[2][2]).all() and (x == ref[2][0]).all(), name
+
+
+@pytest.mark.parametrize("dom,n,kw", [("sphere", 64, {}), ("flipsplash", 64, {}), ("complex", 48, {})])
+def test_mixed_precision_preconditioner(gpu_ctx, dom, n, kw):
+    """mixed_precision = 1: the V-cycle in fp32 inside the fp64 CG.  Not the reference arithmetic -- what is asserted is
+    that the fp64 CG still converges to the same pressure: iteration count within +-2 of the fp64 preconditioner, residual history
+    within 5 % per iteration, final pressure within 1e-5 relative of the fp64 run (the solve tolerance is 1e-6), and that the fp64
+    path of the same library is untouched (bitwise equal to a solver created without the option)."""
+    bl, bw, dx = D.DOMAINS[dom](n, **kw)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    b = rhs_for(labels, off, bl.shape, dx)
+    s64 = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    s32 = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels, mixed_precision=True)
+    x64, it64, h64 = s64.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 1000)
+    x32, it32, h32 = s32.solveGeometricConjugateGradient(np.zeros_like(b), b, 1e-6, 1000)
+    assert abs(it32 - it64) <= 2 and h32[-1] < 1e-6
+    m = min(len(h32), len(h64))
+    assert (np.abs(h32[:m] - h64[:m]) / h64[:m]).max() < 0.05
+    assert relerr(x32, x64) < 1e-5
+    assert not x32[~D.active_mask(labels)].any()
+    # the V-cycle entry point of the mixed solver is still the fp64 one
+    rb = D.random_rhs(labels, dx, seed=7)
+    assert (s32.applyVCycle(np.zeros_like(rb), rb) == s64.applyVCycle(np.zeros_like(rb), rb)).all()
+    s64.close()
+    s32.close()
