@@ -682,7 +682,10 @@ def run_gpu_arm(args, rank, world, local_rank):
             "vcycle_frac_of_hbm_peak": vcycle_bytes / (vcycle_ms * 1e-3) / 1e9 / peak,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "launches": d_n, "avg_launch_us": d_ms / d_n * 1e3,
-                         "algorithmic_bytes_per_launch": d_bytes / d_n},
+                         "algorithmic_bytes_per_launch": d_bytes / d_n,
+                         # the event-record nodes serialise the graph (no prologue overlap) and cost ~5 us per launch: the instrumented
+                         # solve takes total_ms / nprof, the timed one `value`; the same class time scaled by that ratio, for context only
+                         "instrumented_solve_ms": total_ms / nprof, "frac_scaled_to_uninstrumented_solve": achieved / peak * (total_ms / nprof) / ms_per_step},
             "kernels": kernels, "kernels_by_level": by_level,
             "kernel_timing": "CUDA events recorded as nodes inside the replayed PCG graphs (warm L2, back-to-back launches); separate pass from `value`",
             "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "gauss_seidel": gs, "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "wall_s_timed_region": wall_s,
