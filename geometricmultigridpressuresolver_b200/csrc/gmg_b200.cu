@@ -1411,6 +1411,8 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 static void freeLevel(Level &L)
 {
     devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab); devFree(L.flagsAlloc);
+    delete static_cast<ClusterSmoothArgs *>(L.smoothArgs);
+    devFree(L.smoothSlab);
     devFree(L.chunksInterior); devFree(L.chunksActive); devFree(L.bricks); devFree(L.bricksActive); devFree(L.cbricks);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
@@ -2192,6 +2194,7 @@ static int allreduceScalar(gmg_solver *s, double *dev, int op = NCCL_SUM)
 }
 
 static int buildFusedCycle(gmg_solver *s);
+static int buildClusterSmooth(gmg_solver *s);
 
 extern "C" int gmg_solver_destroy(gmg_solver *s)
 {
@@ -2382,6 +2385,7 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     if ((st = ensureScratch(ctx, maxGrid)) != GMG_OK) return fail(st);
     if (!s->opt.operators_only && (st = buildCoarseSolve(s)) != GMG_OK) return fail(st);
     if ((st = buildFusedCycle(s)) != GMG_OK) return fail(st);
+    if ((st = buildClusterSmooth(s)) != GMG_OK) return fail(st);
     lap("coarse direct solver");
     if ((st = p2pEnsure(s)) != GMG_OK) return fail(st);
     if (s->shardLevels > 0)
@@ -3019,6 +3023,129 @@ static int buildClusterCycle(gmg_solver *s)
     return GMG_OK;
 }
 
+// one level's smoothing in a cluster (gmg_cluster.cuh: k_cluster_smooth): levels of 2k..16k cells above the fused coarse cycle
+static int buildClusterSmooth(gmg_solver *s)
+{
+    {
+	const char *e = getenv("GMG_CLUSTER_SMOOTH");
+	if (e && e[0] == '0') return GMG_OK;
+    }
+    if (s->opt.operators_only || s->opt.use_gauss_seidel || s->opt.boundary_iterations < 1) return GMG_OK;
+    gmg_ctx *ctx = s->ctx;
+    int smemMax = 0;
+    GMG_CUDA(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    if (ctx->smoothClusterSize == 0)
+    {
+	ctx->smoothClusterSize = -1;
+	if (cudaFuncSetAttribute(k_cluster_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax) != cudaSuccess) { cudaGetLastError(); return GMG_OK; }
+	if (cudaFuncSetAttribute(k_cluster_smooth, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+	for (int cl = 16; cl >= 8; cl >>= 1)
+	{
+	    cudaLaunchConfig_t cfg = {};
+	    cfg.gridDim = dim3(cl);
+	    cfg.blockDim = dim3(CLUSTER_THREADS);
+	    cfg.dynamicSmemBytes = 64 << 10;
+	    cudaLaunchAttribute attr[1];
+	    attr[0].id = cudaLaunchAttributeClusterDimension;
+	    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	    cfg.attrs = attr;
+	    cfg.numAttrs = 1;
+	    int nClusters = 0;
+	    if (cudaOccupancyMaxActiveClusters(&nClusters, k_cluster_smooth, &cfg) == cudaSuccess && nClusters >= 1) { ctx->smoothClusterSize = cl; break; }
+	    cudaGetLastError();
+	}
+    }
+    if (ctx->smoothClusterSize < 0) return GMG_OK;
+    const int CL = ctx->smoothClusterSize;
+    const int last = s->fusedFirst > 0 ? s->fusedFirst : s->levels - 1;  // levels [1, last) run as kernels
+    for (int level = std::max(1, s->shardLevels); level < last; ++level)
+    {
+	Level &L = s->lv[level];
+	const int n = int(L.nActive);
+	if (L.nActive < 2048 || L.nActive > int64_t(CL) * CLUSTER_THREADS * 2) continue;
+	const int per = int((divUp(n, CL) + 1) & ~int64_t(1));
+	if (per > CLUSTER_MAX_PER) continue;
+	size_t off = 0;
+	auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+	const size_t oCell = take(4 * size_t(n)), oNbr = take(4 * 6 * size_t(n)), oNbr16 = take(2 * 6 * size_t(n)), oDiag = take(n), oFlags = take(n);
+	char *slab = nullptr;
+	GMG_CUDA(devMalloc(&slab, off));
+	ClusterSmoothArgs *c = new ClusterSmoothArgs;
+	std::memset(c, 0, sizeof(*c));
+	L.smoothArgs = c;
+	L.smoothSlab = slab;
+	ClusterLevel &K = c->lv;
+	K.n = n; K.per = per; K.off = 0;
+	K.tabOff = int((size_t(3) * per * sizeof(double) + 15) & ~size_t(15));
+	K.nbr = reinterpret_cast<const unsigned *>(slab + oNbr);
+	K.nbr16 = reinterpret_cast<const unsigned short *>(slab + oNbr16);
+	K.diag = reinterpret_cast<const uint8_t *>(slab + oDiag);
+	K.flags = reinterpret_cast<const uint8_t *>(slab + oFlags);
+	L.smoothSmem = size_t(K.tabOff) + size_t(14) * per + 16;
+	int32_t *cell = reinterpret_cast<int32_t *>(slab + oCell);
+	const int64_t total = L.g.total;
+	uint8_t *fl = nullptr;
+	int *dCount = nullptr;
+	int32_t *pos = nullptr;
+	void *dTemp = nullptr;
+	size_t tempBytes = 0;
+	GMG_CUDA(devMalloc(&fl, size_t(total)));
+	GMG_CUDA(devMalloc(&dCount, sizeof(int)));
+	GMG_CUDA(devMalloc(&pos, sizeof(int32_t) * size_t(total)));
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_active_flags<<<unsigned(divUp(total, BLOCK)), BLOCK, 0, ctx->stream>>>(fl, L.labels, total);
+	}
+	thrust::counting_iterator<int32_t> it(0);
+	GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, it, fl, cell, dCount, int(total), ctx->stream));
+	GMG_CUDA(devMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
+	GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, it, fl, cell, dCount, int(total), ctx->stream));
+	++ctx->launches;
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_fill_i32<<<unsigned(divUp(total, BLOCK)), BLOCK, 0, ctx->stream>>>(pos, -1, total);
+	    k_band_pos<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(pos, cell, n);
+	    k_cluster_nbr<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(const_cast<unsigned *>(K.nbr), const_cast<uint8_t *>(K.diag), const_cast<uint8_t *>(K.flags), cell,
+										pos, L.labels, L.bandFlags, n, per, L.g.pitch, L.g.plane);
+	    k_cluster_nbr16<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(const_cast<unsigned short *>(K.nbr16), K.nbr, n, per);
+	}
+	GMG_CUDA(cudaGetLastError());
+	GMG_CUDA(devFree(dTemp));
+	GMG_CUDA(devFree(dCount));
+	GMG_CUDA(devFree(fl));
+	GMG_CUDA(devFree(pos));
+	c->sweeps = s->opt.boundary_iterations;
+	c->cell = cell;
+    }
+    return GMG_OK;
+}
+
+// band sweeps + interior sweep + band sweeps (+ residual on the way down) of one level as ONE cluster kernel
+static int launchClusterSmooth(gmg_solver *s, int level, double *x, const double *b, double *r, bool up)
+{
+    gmg_ctx *ctx = s->ctx;
+    ctx->curLevel = level;
+    Level &L = s->lv[level];
+    ClusterSmoothArgs a = *static_cast<const ClusterSmoothArgs *>(L.smoothArgs);
+    a.x = x; a.b = b; a.r = r;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctx->smoothClusterSize);
+    cfg.blockDim = dim3(CLUSTER_THREADS);
+    cfg.dynamicSmemBytes = L.smoothSmem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ctx->smoothClusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = usePdl() ? 2 : 1;
+    GMG_LAUNCH(ctx, KC_BAND, double(L.nBand) * 29.0 * 2 * s->opt.boundary_iterations + double(L.nActive) * (up ? 25.0 : 50.0));
+    GMG_CUDA(cudaLaunchKernelEx(&cfg, k_cluster_smooth, a, up ? 1 : 0));
+    GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
 // levels [fusedFirst, levels-1] in one shared-memory CTA (gmg_kernels.cuh: k_compact_cycle): the fallback where the cluster
 // cycle is not available.  The tables are built on the host: these levels hold a few thousand cells at most.
 static int buildFusedCycle(gmg_solver *s)
@@ -3395,6 +3522,13 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
 	Level &L = s->lv[level];
 	cur[level] = L.x;
 	alt[level] = L.xAlt;
+	if (L.smoothArgs)
+	{
+	    // the level's whole down-stroke smoothing and residual in one cluster kernel (result in cur[level] = L.x, L.r)
+	    GMG_TRY(launchClusterSmooth(s, level, cur[level], L.b, L.r, false));
+	    GMG_TRY(restrictDown(s, level, L.r));
+	    continue;
+	}
 	if (!zeroAware(s)) GMG_TRY(launchZero(s, level, cur[level]));
 	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, true, downJacobi, true));
 	GMG_TRY(launchStencil(s, level, SM_RESIDUAL, cur[level], L.b, L.r, nullptr, clipDepth(L, 1)));
@@ -3408,6 +3542,7 @@ static int vcycleLaunches(gmg_solver *s, double *x, const double *b, bool useIni
 	// the level below hands over its result in its own x grid (two Jacobi swaps, or the direct solve / fused cycle)
 	GMG_TRY(launchProlong(s, level, cur[level], s->lv[level + 1].x, clipDepth(L, 0)));
 	GMG_TRY(haloExchange(s, level, cur[level], HALO_X));
+	if (L.smoothArgs) { GMG_TRY(launchClusterSmooth(s, level, cur[level], L.b, nullptr, true)); continue; }
 	GMG_TRY(smoothLevel(s, level, cur[level], alt[level], L.b, false, upJacobi, false));
     }
     GMG_TRY(launchProlong(s, 0, cur0, s->lv[1].x, clipDepth(s->lv[0], 0)));

@@ -340,6 +340,80 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_cycle(const Clus
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// ONE level's smoothing in a cluster (what the measurements above leave standing).  A level of 2k..16k cells costs 4.1 us per
+// V-cycle step as a kernel of its own and 17 steps per V-cycle; in a 16-CTA cluster with one cell per thread a step is a
+// cluster barrier (~0.45 us) plus a few hundred cycles of shared-memory loads and fp64.  What did NOT pay is moving values
+// between a distributed level and its neighbours inside the cluster (one SM's ~20 B/cycle port) -- so here the level's
+// right-hand side comes from its grid and its solution / residual go back to their grids, and restriction, the coarser levels
+// and prolongation stay the kernels they were.
+//   up == 0 (down-stroke, MG.cpp:557-667): x = 0, band sweeps + interior sweep + band sweeps, residual; writes x and r
+//   up == 1 (up-stroke,   MG.cpp:695-784): x = grid (the prolongation kernel has added the correction), the same sweeps; writes x
+// Same arithmetic, same order as the per-kernel path: bitwise identical (tests/test_gpu_parity.py).
+// ------------------------------------------------------------------------------------------------
+struct ClusterSmoothArgs
+{
+    ClusterLevel lv;        // the level (tables as in ClusterArgs)
+    int sweeps;
+    const int32_t *cell;    // [n] storage index of the compact cells
+    const double *b;        // rhs grid
+    double *x;              // solution grid
+    double *r;              // residual grid (down-stroke)
+};
+
+__global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_cluster_smooth(const ClusterSmoothArgs c, int up)
+{
+    pdlLaunch();
+    extern __shared__ double sm[];
+    unsigned char *smBytes = reinterpret_cast<unsigned char *>(sm);
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = int(cl.block_rank());
+    const ClusterLevel &L = c.lv;
+    const int first = rank * L.per, count = max(0, min(L.per, L.n - first));
+    double *xa = sm + L.off, *xb = xa + L.per, *b = xb + L.per;
+    // prologue: this CTA's block of the (static) tables
+    {
+	unsigned short *tn = reinterpret_cast<unsigned short *>(smBytes + L.tabOff);
+	uint8_t *td = smBytes + L.tabOff + size_t(12) * L.per, *tf = td + L.per;
+	for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
+	{
+#pragma unroll
+	    for (int d = 0; d < 6; ++d) tn[d * L.per + j] = __ldg(L.nbr16 + size_t(d) * L.n + first + j);
+	    td[j] = __ldg(L.diag + first + j);
+	    tf[j] = __ldg(L.flags + first + j);
+	}
+    }
+    pdlWait();
+    for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
+    {
+	const int64_t g = __ldg(c.cell + first + j);
+	b[j] = c.b[g];
+	xa[j] = up ? c.x[g] : 0.0;
+    }
+    cl.sync();
+    const ClusterTab T = clusterTab(L, smBytes);
+    double *cur = xa, *nxt = xb;
+    for (int s = 0; s < 2 * c.sweeps + 1; ++s)
+    {
+	clusterSweep(cl, L, T, cur, nxt, b, rank, first, count, s != c.sweeps);
+	cl.sync();
+	double *t = cur; cur = nxt; nxt = t;
+    }
+    for (int j = threadIdx.x; j < count; j += CLUSTER_THREADS)
+    {
+	const int64_t g = __ldg(c.cell + first + j);
+	c.x[g] = cur[j];
+	if (!up)
+	{
+	    const double lap = clusterLap(cl, L, T, cur, rank, first + j, j, double(T.diag[j]));
+	    c.r[g] = b[j] + (-1.0) * lap;  // Ops.h:731
+	}
+    }
+    // (no CTA may leave while a neighbour still reads its shared memory for the residual)
+    cl.sync();
+}
+
 // ------------------------------------------------------------------------------------------------
 // table builders (device side: the constructor runs every simulation frame)
 // ------------------------------------------------------------------------------------------------

@@ -107,6 +107,9 @@ struct Level
     // mixed precision (gmg_solver_options::mixed_precision): the V-cycle's grids and compact band arrays once more in fp32
     float *x32 = nullptr, *xAlt32 = nullptr, *b32 = nullptr, *r32 = nullptr;
     float *bandV0f = nullptr, *bandV1f = nullptr, *bandBf = nullptr;
+    void *smoothArgs = nullptr;  // gmg::ClusterSmoothArgs: this level smooths inside one thread-block cluster (gmg_cluster.cuh: k_cluster_smooth)
+    void *smoothSlab = nullptr;  // its tables
+    size_t smoothSmem = 0;
     int shift[3] = {0, 0, 0};    // coarse storage = (this level's storage >> 1) + shift   (to level+1)
     // tiled Gauss-Seidel (only built when the solver uses it): 16^3 tiles of the EXPANDED grid laid over the storage box
     int32_t *gsTiles[2] = {nullptr, nullptr};  // [0] even, [1] odd tiles holding an active cell (linear tile ids)
@@ -163,6 +166,7 @@ struct gmg_ctx
     int64_t commOps = 0;          // communication operations enqueued since the last launch-count reset
     void *p2p = nullptr;          // gmg::P2pState: peer-memory mailboxes (gmg_p2p.cuh); null = NCCL for every exchange
     bool p2pDisabled = false;
+    int smoothClusterSize = 0;     // CTAs of the one-level smoothing cluster (k_cluster_smooth): 0 = not probed, -1 = refused
     int clusterSize = 0;           // CTAs of the coarse-cycle cluster: 0 = not probed yet, -1 = cluster launch refused
     bool deviceLoopBroken = false; // the driver refused the conditional-graph PCG loop once: host loop from then on
     int p2pGenerations = 0;

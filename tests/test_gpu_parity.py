@@ -395,10 +395,10 @@ def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
     rb = D.random_rhs(labels, dx, seed=21)
     x0 = D.random_active(labels, 22, scale=dx * dx)
     results = {}
-    for name, env in [("cluster", {"GMG_CLUSTER_CYCLE": "1"}), ("compact", {}), ("kernels", {"GMG_COARSE_FUSED": "0"}),
+    for name, env in [("cluster", {"GMG_CLUSTER_CYCLE": "1"}), ("compact", {}), ("kernels", {"GMG_COARSE_FUSED": "0", "GMG_CLUSTER_SMOOTH": "0"}), ("level_kernels", {"GMG_CLUSTER_SMOOTH": "0"}),
                       ("zero_fill", {"GMG_ZERO_AWARE": "0"}), ("cluster8", {"GMG_CLUSTER_CYCLE": "1", "GMG_CLUSTER_SIZE": "8"}), ("first2", {"GMG_CLUSTER_CYCLE": "1", "GMG_FUSED_FIRST": "2"}),
                       ("tma", {"GMG_TMA": "31", "GMG_TMA_MIN_CELLS": "100"}), ("sweep_groups", {"GMG_BAND_GROUPS": "1"}), ("sweep_resident", {"GMG_BAND_RESIDENT": "1"})]:
-        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS", "GMG_BAND_GROUPS", "GMG_BAND_RESIDENT"):
+        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS", "GMG_BAND_GROUPS", "GMG_BAND_RESIDENT", "GMG_CLUSTER_SMOOTH"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
