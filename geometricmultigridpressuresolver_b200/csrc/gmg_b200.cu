@@ -11,12 +11,14 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <numeric>
 #include <thread>
 
 #include <dlfcn.h>
 
 #include "gmg_kernels.cuh"
 #include "gmg_cluster.cuh"
+#include "gmg_band_tiles.cuh"
 #include "gmg_frontend.cuh"
 #include "gmg_nccl.h"
 #include "gmg_p2p.cuh"
@@ -1413,6 +1415,8 @@ static void freeLevel(Level &L)
     devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab); devFree(L.flagsAlloc);
     delete static_cast<ClusterSmoothArgs *>(L.smoothArgs);
     devFree(L.smoothSlab);
+    delete static_cast<BandTileArgs *>(L.tileArgs);
+    devFree(L.tileSlab);
     devFree(L.chunksInterior); devFree(L.chunksActive); devFree(L.bricks); devFree(L.bricksActive); devFree(L.cbricks);
     devFree(L.gsTiles[0]); devFree(L.gsTiles[1]); devFree(L.bpos);
     freeGrid(L.x, L.g); freeGrid(L.xAlt, L.g); freeGrid(L.b, L.g); freeGrid(L.r, L.g);
@@ -2195,6 +2199,7 @@ static int allreduceScalar(gmg_solver *s, double *dev, int op = NCCL_SUM)
 
 static int buildFusedCycle(gmg_solver *s);
 static int buildClusterSmooth(gmg_solver *s);
+static int buildBandTiles(gmg_solver *s);
 
 extern "C" int gmg_solver_destroy(gmg_solver *s)
 {
@@ -2254,6 +2259,8 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     s->tmaMask = tmaMode();
     if (const char *e = getenv("GMG_BAND_GROUPS")) s->bandGroups = (e[0] == '1');
     if (const char *e = getenv("GMG_BAND_RESIDENT")) s->bandResident = (e[0] == '1');
+    if (const char *e = getenv("GMG_BAND_TILES")) s->bandTiles = (e[0] == '1');
+    if (const char *e = getenv("GMG_BAND_PER_THREAD")) s->bandPerThread = atoi(e);
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel && ctx->world > 1)
@@ -2401,6 +2408,9 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     }
     if ((st = finishCoefsSparse(ctx, s->lv[0], &coefJob)) != GMG_OK) return fail(st);
     lap("level 0 coefficient records (join)");
+    // (after the join: the tiles copy the diagonals and coefficient codes of level 0)
+    if ((st = buildBandTiles(s)) != GMG_OK) return fail(st);
+    lap("band tiles");
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(cudaFail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__));
     s->setupMs = nowMs() - tStart;
     *out = s;
@@ -2610,6 +2620,18 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
     const double bytes = double(L.nBand) * 29.0;
     const bool hw = L.hasWeights;
     double *cur = L.bandV0, *nxt = L.bandV1;
+    if (sweeps == 3 && L.tileArgs && s->bandTiles && (zeroGrid || L.tilesCoResident))
+    {
+	// the whole group as ring-halo tiles: one launch, no barrier between the sweeps (gmg_band_tiles.cuh)
+	BandTileArgs t = *static_cast<const BandTileArgs *>(L.tileArgs);
+	t.x = x;
+	t.b = b;
+	GMG_LAUNCH(s->ctx, KC_BAND, bytes * sweeps);
+	if (zeroGrid) GMG_CUDA(launchK(k_band_tile<true>, unsigned(L.nTiles), unsigned(BT_THREADS), L.tileSmem, st, t));
+	else GMG_CUDA(launchK(k_band_tile<false>, unsigned(L.nTiles), unsigned(BT_THREADS), L.tileSmem, st, t));
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     if (sweeps >= 2 && s->bandResident && s->ctx->groupBarrier)
     {
 	// the whole group in one launch of 2 x 512 threads per SM with every cell's metadata resident (k_band_resident);
@@ -2680,14 +2702,37 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
 	GMG_CUDA(cudaGetLastError());
 	return GMG_OK;
     }
+    // cells per thread: two, or three where two would need a second wave of CTAs and three do not
+    gmg_ctx *ctx = s->ctx;
+    if (ctx->bandSlots[0] == 0)
+    {
+	int per = 0;
+	GMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_band<true, false, false, false, true, false, double, 2>, BLOCK, 0));
+	ctx->bandSlots[0] = std::max(1, per) * ctx->smCount;
+	GMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_band<true, false, false, false, true, false, double, 3>, BLOCK, 0));
+	ctx->bandSlots[1] = std::max(1, per) * ctx->smCount;
+    }
+    const unsigned grid3 = unsigned(divUp(L.nBand, BLOCK * 3));
+    // measured (profiles/r02_band_fusion.md): no gain at 256^3 level 0 (the one level where it applies), a loss when forced everywhere:
+    // two cells per thread unless GMG_BAND_PER_THREAD=3 / =-1 (pick per level) asks otherwise
+    bool pt3 = s->bandPerThread == -1 && int(grid) > ctx->bandSlots[0] && int(grid3) <= ctx->bandSlots[1];
+    if (s->bandPerThread == 2) pt3 = false;
+    if (s->bandPerThread == 3) pt3 = true;
+    const unsigned gridK = pt3 ? grid3 : grid;
+#define GMG_BAND(FC, TG, FI, ZE, HW, FZ)                                                                                            \
+    do                                                                                                                             \
+    {                                                                                                                              \
+	if (pt3) GMG_CUDA(launchK((k_band<FC, TG, FI, ZE, HW, FZ, double, 3>), gridK, BLOCK, 0, st, a));                            \
+	else GMG_CUDA(launchK((k_band<FC, TG, FI, ZE, HW, FZ, double, 2>), gridK, BLOCK, 0, st, a));                                \
+    } while (0)
     // sweep 1: grid -> compact
     a.vin = nullptr;
     a.vout = cur;
     {
 	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
-	if (zeroGrid) GMG_CUDA(launchK((k_band<false, false, true, true, false>), grid, BLOCK, 0, st, a));
-	else if (hw) GMG_CUDA(launchK((k_band<false, false, true, false, true>), grid, BLOCK, 0, st, a));
-	else GMG_CUDA(launchK((k_band<false, false, true, false, false>), grid, BLOCK, 0, st, a));
+	if (zeroGrid) GMG_BAND(false, false, true, true, false, false);
+	else if (hw) GMG_BAND(false, false, true, false, true, false);
+	else GMG_BAND(false, false, true, false, false, false);
     }
     if (sweeps == 1)
     {
@@ -2701,20 +2746,21 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
 	GMG_LAUNCH(s->ctx, KC_BAND, bytes);
 	if (sw == sweeps)
 	{
-	    if (zeroGrid && hw) GMG_CUDA(launchK((k_band<true, true, false, false, true, true>), grid, BLOCK, 0, st, a));
-	    else if (zeroGrid) GMG_CUDA(launchK((k_band<true, true, false, false, false, true>), grid, BLOCK, 0, st, a));
-	    else if (hw) GMG_CUDA(launchK((k_band<true, true, false, false, true>), grid, BLOCK, 0, st, a));
-	    else GMG_CUDA(launchK((k_band<true, true, false, false, false>), grid, BLOCK, 0, st, a));
+	    if (zeroGrid && hw) GMG_BAND(true, true, false, false, true, true);
+	    else if (zeroGrid) GMG_BAND(true, true, false, false, false, true);
+	    else if (hw) GMG_BAND(true, true, false, false, true, false);
+	    else GMG_BAND(true, true, false, false, false, false);
 	}
 	else
 	{
-	    if (zeroGrid && hw) GMG_CUDA(launchK((k_band<true, false, false, false, true, true>), grid, BLOCK, 0, st, a));
-	    else if (zeroGrid) GMG_CUDA(launchK((k_band<true, false, false, false, false, true>), grid, BLOCK, 0, st, a));
-	    else if (hw) GMG_CUDA(launchK((k_band<true, false, false, false, true>), grid, BLOCK, 0, st, a));
-	    else GMG_CUDA(launchK((k_band<true, false, false, false, false>), grid, BLOCK, 0, st, a));
+	    if (zeroGrid && hw) GMG_BAND(true, false, false, false, true, true);
+	    else if (zeroGrid) GMG_BAND(true, false, false, false, false, true);
+	    else if (hw) GMG_BAND(true, false, false, false, true, false);
+	    else GMG_BAND(true, false, false, false, false, false);
 	}
 	std::swap(cur, nxt);
     }
+#undef GMG_BAND
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;
 }
@@ -3143,6 +3189,234 @@ static int launchClusterSmooth(gmg_solver *s, int level, double *x, const double
     GMG_LAUNCH(ctx, KC_BAND, double(L.nBand) * 29.0 * 2 * s->opt.boundary_iterations + double(L.nActive) * (up ? 25.0 : 50.0));
     GMG_CUDA(cudaLaunchKernelEx(&cfg, k_cluster_smooth, a, up ? 1 : 0));
     GMG_CUDA(cudaGetLastError());
+    return GMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ring-halo tiles of a level's band (gmg_band_tiles.cuh): built once per solver, on the device.
+// ------------------------------------------------------------------------------------------------
+static int sortKeys64(gmg_ctx *ctx, unsigned long long *keys, unsigned long long *out, int64_t n, int bits)
+{
+    void *dTemp = nullptr;
+    size_t tempBytes = 0;
+    GMG_CUDA(cub::DeviceRadixSort::SortKeys(dTemp, tempBytes, keys, out, n, 0, bits, ctx->stream));
+    GMG_CUDA(devMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
+    GMG_CUDA(cub::DeviceRadixSort::SortKeys(dTemp, tempBytes, keys, out, n, 0, bits, ctx->stream));
+    ++ctx->launches;
+    GMG_CUDA(devFree(dTemp));
+    return GMG_OK;
+}
+// sorted keys -> the first of every run of equal (key >> shift), empty keys dropped; *out is allocated here
+static int uniqueKeys64(gmg_ctx *ctx, const unsigned long long *sorted, int64_t n, int shift, unsigned long long **out, int *count)
+{
+    uint8_t *head = nullptr;
+    int *dCount = nullptr;
+    unsigned long long *tmp = nullptr;
+    GMG_CUDA(devMalloc(&head, size_t(std::max<int64_t>(n, 1))));
+    GMG_CUDA(devMalloc(&dCount, sizeof(int)));
+    GMG_CUDA(devMalloc(&tmp, sizeof(unsigned long long) * size_t(std::max<int64_t>(n, 1))));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_tile_heads<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(head, sorted, n, shift);
+    }
+    void *dTemp = nullptr;
+    size_t tempBytes = 0;
+    GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, sorted, head, tmp, dCount, int(n), ctx->stream));
+    GMG_CUDA(devMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
+    GMG_CUDA(cub::DeviceSelect::Flagged(dTemp, tempBytes, sorted, head, tmp, dCount, int(n), ctx->stream));
+    ++ctx->launches;
+    int h = 0;
+    GMG_CUDA(cudaMemcpyAsync(&h, dCount, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *count = h;
+    *out = tmp;
+    GMG_CUDA(devFree(dTemp));
+    GMG_CUDA(devFree(dCount));
+    GMG_CUDA(devFree(head));
+    return GMG_OK;
+}
+
+static int buildLevelTiles(gmg_solver *s, Level &L)
+{
+    gmg_ctx *ctx = s->ctx;
+    const int nBand = L.nBand;
+    const int own = int(std::min<int64_t>(1536, std::max<int64_t>(256, divUp(divUp(nBand, int64_t(2) * ctx->smCount), 128) * 128)));
+    const int nTiles = int(divUp(nBand, own));
+    const unsigned gridBand = unsigned(divUp(nBand, BLOCK));
+    cudaStream_t st = ctx->stream;
+    // 1. Morton order of the band cells, equal cuts
+    unsigned *key = nullptr, *keyOut = nullptr;
+    int32_t *val = nullptr, *order = nullptr, *tileOf = nullptr, *sortedPos = nullptr;
+    GMG_CUDA(devMalloc(&key, sizeof(unsigned) * nBand));
+    GMG_CUDA(devMalloc(&keyOut, sizeof(unsigned) * nBand));
+    GMG_CUDA(devMalloc(&val, sizeof(int32_t) * nBand));
+    GMG_CUDA(devMalloc(&order, sizeof(int32_t) * nBand));
+    GMG_CUDA(devMalloc(&tileOf, sizeof(int32_t) * nBand));
+    GMG_CUDA(devMalloc(&sortedPos, sizeof(int32_t) * nBand));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_tile_keys<<<gridBand, BLOCK, 0, st>>>(key, val, L.bandIdx, nBand, L.g.pitch, L.g.plane);
+    }
+    {
+	void *dTemp = nullptr;
+	size_t tempBytes = 0;
+	GMG_CUDA(cub::DeviceRadixSort::SortPairs(dTemp, tempBytes, key, keyOut, val, order, nBand, 0, 30, st));
+	GMG_CUDA(devMalloc(&dTemp, std::max<size_t>(tempBytes, 16)));
+	GMG_CUDA(cub::DeviceRadixSort::SortPairs(dTemp, tempBytes, key, keyOut, val, order, nBand, 0, 30, st));
+	++ctx->launches;
+	GMG_CUDA(devFree(dTemp));
+    }
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_tile_assign<<<gridBand, BLOCK, 0, st>>>(tileOf, sortedPos, order, nBand, own);
+    }
+    GMG_CUDA(devFree(key)); GMG_CUDA(devFree(keyOut)); GMG_CUDA(devFree(val));
+    // 2. ring 1: band neighbours in another tile
+    unsigned long long *k1 = nullptr, *k1s = nullptr, *ring1 = nullptr;
+    int n1 = 0;
+    GMG_CUDA(devMalloc(&k1, sizeof(unsigned long long) * 6 * size_t(nBand)));
+    GMG_CUDA(devMalloc(&k1s, sizeof(unsigned long long) * 6 * size_t(nBand)));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_tile_ring1<<<gridBand, BLOCK, 0, st>>>(k1, L.bandRef, tileOf, nBand);
+    }
+    GMG_TRY(sortKeys64(ctx, k1, k1s, int64_t(6) * nBand, 64));
+    GMG_TRY(uniqueKeys64(ctx, k1s, int64_t(6) * nBand, 0, &ring1, &n1));
+    GMG_CUDA(devFree(k1)); GMG_CUDA(devFree(k1s));
+    // 3. ring 2: band neighbours of ring 1 outside the tile and ring 1; 4. the halo of a tile sorted (ring, position)
+    unsigned long long *halo = nullptr;
+    int nHalo = 0;
+    int *dCnt = nullptr;
+    GMG_CUDA(devMalloc(&dCnt, sizeof(int) * 2 * nTiles));
+    GMG_CUDA(cudaMemsetAsync(dCnt, 0, sizeof(int) * 2 * nTiles, st));
+    if (n1 > 0)
+    {
+	unsigned long long *k2 = nullptr, *k2s = nullptr, *uni = nullptr;
+	GMG_CUDA(devMalloc(&k2, sizeof(unsigned long long) * 7 * size_t(n1)));
+	GMG_CUDA(devMalloc(&k2s, sizeof(unsigned long long) * 7 * size_t(n1)));
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_tile_ring2<<<unsigned(divUp(n1, BLOCK)), BLOCK, 0, st>>>(k2, ring1, n1, L.bandRef, tileOf, nBand);
+	}
+	GMG_TRY(sortKeys64(ctx, k2, k2s, int64_t(7) * n1, 64));
+	GMG_TRY(uniqueKeys64(ctx, k2s, int64_t(7) * n1, 1, &uni, &nHalo));
+	GMG_CUDA(devFree(k2)); GMG_CUDA(devFree(k2s));
+	{
+	    GMG_LAUNCH(ctx, KC_SETUP, 0);
+	    k_tile_rekey<<<unsigned(divUp(nHalo, BLOCK)), BLOCK, 0, st>>>(uni, dCnt, nHalo);
+	}
+	GMG_CUDA(devMalloc(&halo, sizeof(unsigned long long) * size_t(nHalo)));
+	GMG_TRY(sortKeys64(ctx, uni, halo, nHalo, 64));
+	GMG_CUDA(devFree(uni));
+    }
+    GMG_CUDA(devFree(ring1));
+    // 5. tile headers
+    std::vector<int> cnt(2 * size_t(nTiles));
+    GMG_CUDA(cudaMemcpyAsync(cnt.data(), dCnt, sizeof(int) * 2 * nTiles, cudaMemcpyDeviceToHost, st));
+    GMG_CUDA(cudaStreamSynchronize(st));
+    GMG_CUDA(devFree(dCnt));
+    std::vector<int4> tiles(nTiles);
+    std::vector<int32_t> haloStart(nTiles);
+    int maxLoc = 0, maxCalc = 0;
+    int64_t totalLoc = 0, hs = 0, sumR1 = 0, sumR2 = 0;
+    for (int t = 0; t < nTiles; ++t)
+    {
+	const int nOwn = std::min(own, nBand - t * own);
+	const int r1 = cnt[2 * t], r2 = cnt[2 * t + 1];
+	tiles[t] = make_int4(int(totalLoc), nOwn, nOwn + r1, nOwn + r1 + r2);
+	haloStart[t] = int32_t(hs);
+	maxLoc = std::max(maxLoc, nOwn + r1 + r2);
+	maxCalc = std::max(maxCalc, nOwn + r1);
+	totalLoc += nOwn + r1 + r2;
+	hs += r1 + r2;
+	sumR1 += r1;
+	sumR2 += r2;
+    }
+    auto release = [&]() {
+	devFree(order); devFree(tileOf); devFree(sortedPos); devFree(halo);
+    };
+    const size_t smem = size_t(14) * maxLoc + size_t(28) * maxCalc;
+    int smemMax = 0;
+    GMG_CUDA(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    if (maxLoc > BT_MAX_LOC || smem > size_t(smemMax) || totalLoc > int64_t(0x7fffffff) / 8) { release(); return GMG_OK; }
+    // 6. per-tile tables
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    const size_t oTiles = take(sizeof(int4) * nTiles), oHs = take(sizeof(int32_t) * nTiles), oGi = take(sizeof(int32_t) * totalLoc), oJ = take(sizeof(int32_t) * totalLoc),
+		 oCode = take(sizeof(unsigned short) * totalLoc), oDiag = take(sizeof(double) * totalLoc), oRef = take(sizeof(unsigned short) * 6 * totalLoc), oErr = take(sizeof(int));
+    char *slab = nullptr;
+    GMG_CUDA(devMalloc(&slab, off));
+    L.tileSlab = slab;
+    GMG_CUDA(cudaMemcpyAsync(slab + oTiles, tiles.data(), sizeof(int4) * nTiles, cudaMemcpyHostToDevice, st));
+    GMG_CUDA(cudaMemcpyAsync(slab + oHs, haloStart.data(), sizeof(int32_t) * nTiles, cudaMemcpyHostToDevice, st));
+    GMG_CUDA(cudaMemsetAsync(slab + oErr, 0, sizeof(int), st));
+    TileFillArgs f;
+    f.tiles = reinterpret_cast<const int4 *>(slab + oTiles);
+    f.haloStart = reinterpret_cast<const int32_t *>(slab + oHs);
+    f.halo = halo;
+    f.order = order; f.tileOf = tileOf; f.sortedPos = sortedPos; f.bandIdx = L.bandIdx; f.bandRef = L.bandRef;
+    f.bcoef = L.bcoef; f.wcode = L.wcode;
+    f.locGi = reinterpret_cast<int32_t *>(slab + oGi);
+    f.locJ = reinterpret_cast<int32_t *>(slab + oJ);
+    f.locCode = reinterpret_cast<unsigned short *>(slab + oCode);
+    f.locRef = reinterpret_cast<unsigned short *>(slab + oRef);
+    f.locDiag = reinterpret_cast<double *>(slab + oDiag);
+    f.error = reinterpret_cast<int *>(slab + oErr);
+    f.nTiles = nTiles; f.own = own; f.nBand = nBand; f.nBoundary = L.nBoundary; f.hasWeights = L.hasWeights ? 1 : 0; f.totalLoc = int(totalLoc);
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_tile_fill<<<unsigned(divUp(totalLoc, BLOCK)), BLOCK, 0, st>>>(f);
+    }
+    int err = 0;
+    GMG_CUDA(cudaMemcpyAsync(&err, slab + oErr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GMG_CUDA(cudaStreamSynchronize(st));
+    GMG_CUDA(cudaGetLastError());
+    release();
+    if (err)
+    {
+	// a neighbour of a computed cell is missing from the tile: never expected; keep the sweep-per-launch kernels
+	devFree(L.tileSlab);
+	L.tileSlab = nullptr;
+	return GMG_OK;
+    }
+    BandTileArgs *a = new BandTileArgs;
+    std::memset(a, 0, sizeof(*a));
+    a->tiles = f.tiles; a->locGi = f.locGi; a->locJ = f.locJ; a->locCode = f.locCode; a->locDiag = f.locDiag; a->locRef = f.locRef;
+    a->bcoef = L.bcoef;
+    a->bar = static_cast<GroupBarrier *>(ctx->groupBarrier);
+    a->nBoundary = std::max(L.nBoundary, 1);
+    a->pitch = L.g.pitch; a->plane = L.g.plane;
+    a->maxLoc = maxLoc; a->maxCalc = maxCalc;
+    L.tileArgs = a;
+    L.tileSmem = smem;
+    L.nTiles = nTiles;
+    static bool attr = false;
+    if (!attr)
+    {
+	GMG_CUDA(cudaFuncSetAttribute(k_band_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
+	GMG_CUDA(cudaFuncSetAttribute(k_band_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
+	attr = true;
+    }
+    int per = 0;
+    GMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_band_tile<false>, BT_THREADS, smem));
+    L.tilesCoResident = int64_t(per) * ctx->smCount >= nTiles;
+    if (const char *e = getenv("GMG_BAND_TILES_ZERO_ONLY")) { if (e[0] == '1') L.tilesCoResident = false; }
+    if (s->opt.print_stats)
+	printf("      band tiles: %d cells -> %d tiles of %d (+%.0f %% ring 1, +%.0f %% ring 2), %zu B shared memory, %d CTAs per SM%s\n", nBand, nTiles, own,
+	       100.0 * double(sumR1) / nBand, 100.0 * double(sumR2) / nBand, smem, per, L.tilesCoResident ? "" : " (not co-resident: zero-grid groups only)");
+    return GMG_OK;
+}
+
+static int buildBandTiles(gmg_solver *s)
+{
+    if (!s->bandTiles || s->opt.operators_only || s->opt.boundary_iterations != 3) return GMG_OK;
+    const int last = s->fusedFirst > 0 ? s->fusedFirst : s->levels - 1;  // levels [0, last) run as kernels
+    for (int level = 0; level < last; ++level)
+    {
+	Level &L = s->lv[level];
+	if (L.smoothArgs || L.nBand < 512) continue;
+	GMG_TRY(buildLevelTiles(s, L));
+    }
     return GMG_OK;
 }
 

@@ -110,6 +110,11 @@ struct Level
     void *smoothArgs = nullptr;  // gmg::ClusterSmoothArgs: this level smooths inside one thread-block cluster (gmg_cluster.cuh: k_cluster_smooth)
     void *smoothSlab = nullptr;  // its tables
     size_t smoothSmem = 0;
+    void *tileArgs = nullptr;    // gmg::BandTileArgs: the band sweep groups of this level run as tiles with ring halos (gmg_band_tiles.cuh: k_band_tile)
+    void *tileSlab = nullptr;    // its tables
+    size_t tileSmem = 0;
+    int nTiles = 0;
+    bool tilesCoResident = false;  // every tile fits on the device at once: the groups that start from a non-zero grid may use them too
     int shift[3] = {0, 0, 0};    // coarse storage = (this level's storage >> 1) + shift   (to level+1)
     // tiled Gauss-Seidel (only built when the solver uses it): 16^3 tiles of the EXPANDED grid laid over the storage box
     int32_t *gsTiles[2] = {nullptr, nullptr};  // [0] even, [1] odd tiles holding an active cell (linear tile ids)
@@ -166,6 +171,7 @@ struct gmg_ctx
     int64_t commOps = 0;          // communication operations enqueued since the last launch-count reset
     void *p2p = nullptr;          // gmg::P2pState: peer-memory mailboxes (gmg_p2p.cuh); null = NCCL for every exchange
     bool p2pDisabled = false;
+    int bandSlots[2] = {0, 0};     // resident CTAs of the band sweep kernel with two / three cells per thread
     int smoothClusterSize = 0;     // CTAs of the one-level smoothing cluster (k_cluster_smooth): 0 = not probed, -1 = refused
     int clusterSize = 0;           // CTAs of the coarse-cycle cluster: 0 = not probed yet, -1 = cluster launch refused
     bool deviceLoopBroken = false; // the driver refused the conditional-graph PCG loop once: host loop from then on
@@ -235,6 +241,8 @@ struct gmg_solver
     bool bandGroups = false;      // a group of band sweeps as ONE co-resident launch with grid barriers: measured SLOWER than a launch per sweep
 				  // (profiles/r02_ab_switches.md: 256^3 solve 11.5 vs 10.3 ms; a barrier over ~900 CTAs costs more than a kernel
 				  // boundary with its prologue overlapped), so it is opt-in (GMG_BAND_GROUPS=1)
+    int bandPerThread = 0;        // cells per thread of the band sweep kernels: 0 = picked per level (launchBand), 2 / 3 = forced (GMG_BAND_PER_THREAD)
+    bool bandTiles = false;       // band sweep groups as ring-halo tiles, one launch per group (k_band_tile): measured SLOWER (GMG_BAND_TILES=1 enables)
     bool bandResident = false;    // a group of band sweeps as one launch with every cell's metadata on chip (k_band_resident): measured SLOWER too
 				  // (11.04 vs 10.22 ms: with the prologues overlapped a kernel boundary costs what a 296-CTA barrier costs, ~2.5-3 us,
 				  // and two 512-thread CTAs per SM gather with less parallelism than the sweep kernels); opt-in, GMG_BAND_RESIDENT=1

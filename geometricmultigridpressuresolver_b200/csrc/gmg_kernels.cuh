@@ -531,7 +531,7 @@ constexpr int BAND_PER_THREAD = 2;  // cells per thread: two independent gather 
 // Prologue (static metadata, before pdlWait): grid index, neighbour references, diagonal, coefficient record.
 // CGL: values of the compact arrays are read past L1 (ld.cg) -- inside the persistent sweep-group kernel another SM wrote them
 // during the same launch
-template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false, bool CGL = false, typename T = double>
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false, bool CGL = false, typename T = double, int BAND_PER_THREAD = gmg::BAND_PER_THREAD>
 __device__ __forceinline__ void bandBody(const BandArgsT<T> &a, int vb, int tid)
 {
     int64_t gi[BAND_PER_THREAD];
@@ -611,11 +611,14 @@ __device__ __forceinline__ void bandBody(const BandArgsT<T> &a, int vb, int tid)
 	else a.vout[k] = v[c];
     }
 }
-template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false, typename T = double>
-__global__ void __launch_bounds__(BLOCK) k_band(const BandArgsT<T> a)
+// PT: cells per thread.  A sweep is one dependent round of gathers per CTA, so a grid that does not fit the device at once pays the
+// round twice (256^3, level 0: 1211 CTAs of 2 cells per thread over 888 resident slots); three cells per thread bring it back to
+// one wave (launchBand picks)
+template <bool FROM_COMPACT, bool TO_GRID, bool FIRST, bool ZERO, bool HAS_W, bool FZ = false, typename T = double, int PT = BAND_PER_THREAD>
+__global__ void __launch_bounds__(BLOCK, PT > 2 ? 6 : 1) k_band(const BandArgsT<T> a)
 {
     pdlLaunch();
-    bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W, FZ, false, T>(a, blockIdx.x, threadIdx.x);
+    bandBody<FROM_COMPACT, TO_GRID, FIRST, ZERO, HAS_W, FZ, false, T, PT>(a, blockIdx.x, threadIdx.x);
 }
 
 

@@ -395,10 +395,10 @@ def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
     rb = D.random_rhs(labels, dx, seed=21)
     x0 = D.random_active(labels, 22, scale=dx * dx)
     results = {}
-    for name, env in [("cluster", {"GMG_CLUSTER_CYCLE": "1"}), ("compact", {}), ("kernels", {"GMG_COARSE_FUSED": "0", "GMG_CLUSTER_SMOOTH": "0"}), ("level_kernels", {"GMG_CLUSTER_SMOOTH": "0"}),
+    for name, env in [("cluster", {"GMG_CLUSTER_CYCLE": "1"}), ("compact", {}), ("kernels", {"GMG_COARSE_FUSED": "0", "GMG_CLUSTER_SMOOTH": "0", "GMG_BAND_TILES": "0", "GMG_BAND_PER_THREAD": "2"}), ("level_kernels", {"GMG_CLUSTER_SMOOTH": "0"}),
                       ("zero_fill", {"GMG_ZERO_AWARE": "0"}), ("cluster8", {"GMG_CLUSTER_CYCLE": "1", "GMG_CLUSTER_SIZE": "8"}), ("first2", {"GMG_CLUSTER_CYCLE": "1", "GMG_FUSED_FIRST": "2"}),
-                      ("tma", {"GMG_TMA": "31", "GMG_TMA_MIN_CELLS": "100"}), ("sweep_groups", {"GMG_BAND_GROUPS": "1"}), ("sweep_resident", {"GMG_BAND_RESIDENT": "1"})]:
-        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS", "GMG_BAND_GROUPS", "GMG_BAND_RESIDENT", "GMG_CLUSTER_SMOOTH"):
+                      ("tma", {"GMG_TMA": "31", "GMG_TMA_MIN_CELLS": "100"}), ("sweep_groups", {"GMG_BAND_GROUPS": "1", "GMG_BAND_TILES": "0", "GMG_BAND_PER_THREAD": "2"}), ("sweep_resident", {"GMG_BAND_RESIDENT": "1", "GMG_BAND_TILES": "0", "GMG_BAND_PER_THREAD": "2"}), ("sweep_kernels", {"GMG_BAND_TILES": "0", "GMG_BAND_PER_THREAD": "2"})]:
+        for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS", "GMG_BAND_GROUPS", "GMG_BAND_RESIDENT", "GMG_CLUSTER_SMOOTH", "GMG_BAND_TILES", "GMG_BAND_PER_THREAD"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -414,6 +414,37 @@ def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
             assert it == ref[2][1] and relerr(hist, ref[2][2]) < 1e-11 and relerr(x, ref[2][0]) < 1e-11, name
         else:
             assert it == ref[2][1] and (hist == ref[2][2]).all() and (x == ref[2][0]).all(), name
+
+
+@pytest.mark.parametrize("dom,n,kw", [("sphere", 64, {}), ("complex", 48, {}), ("narrow_band", 64, {"thickness": 6}), ("flipsplash", 48, {"shape": (48, 32, 64)}),
+                                      ("sphere", 128, {})])
+def test_band_sweep_tiles_agree_bitwise(gpu_ctx, monkeypatch, dom, n, kw):
+    """A group of three band sweeps runs as three launches over the whole band list (two or three cells per thread) or -- opt-in,
+    measured slower -- as ONE launch of ring-halo tiles (gmg_band_tiles.cuh: sweep 1 on a tile + two rings, sweep 2 on the tile + one
+    ring, sweep 3 on the tile).  Same per-cell
+    arithmetic: the band smoother alone, a V-cycle (zero guess and initial guess) and a PCG solve must agree BITWISE, on weighted
+    (ghost-fluid) and unweighted levels, with the tiles used for every group or only for the groups that start from a zero grid."""
+    bl, bw, dx = D.DOMAINS[dom](n, **kw)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    rb = D.random_rhs(labels, dx, seed=31)
+    x0 = D.random_active(labels, 32, scale=dx * dx)
+    out = {}
+    for name, env in [("sweeps", {"GMG_BAND_PER_THREAD": "2"}), ("tiles", {"GMG_BAND_TILES": "1"}), ("zero_only", {"GMG_BAND_TILES": "1", "GMG_BAND_TILES_ZERO_ONLY": "1"}),
+                      ("three_per_thread", {"GMG_BAND_PER_THREAD": "3"}), ("default", {})]:
+        for k in ("GMG_BAND_TILES", "GMG_BAND_TILES_ZERO_ONLY", "GMG_BAND_PER_THREAD"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+        X, B = s.grid(0, x0), s.grid(0, rb)
+        s.boundaryJacobiPoissonSmoother(X, B, 3)
+        out[name] = (X.download(), s.applyVCycle(np.zeros_like(rb), rb), s.applyVCycle(x0, rb, True),
+                     s.solveGeometricConjugateGradient(np.zeros_like(rb), rb, 1e-8, 40))
+        s.close()
+    ref = out["sweeps"]
+    for name, (bj, v, vg, (x, it, hist)) in out.items():
+        assert (bj == ref[0]).all() and (v == ref[1]).all() and (vg == ref[2]).all(), name
+        assert it == ref[3][1] and (hist == ref[3][2]).all() and (x == ref[3][0]).all(), name
 
 
 @pytest.mark.parametrize("dom,n,kw", [("sphere", 64, {}), ("flipsplash", 64, {}), ("complex", 48, {})])
