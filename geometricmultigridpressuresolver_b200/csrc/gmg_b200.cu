@@ -2261,6 +2261,8 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     if (const char *e = getenv("GMG_BAND_RESIDENT")) s->bandResident = (e[0] == '1');
     if (const char *e = getenv("GMG_BAND_TILES")) s->bandTiles = (e[0] == '1');
     if (const char *e = getenv("GMG_BAND_PER_THREAD")) s->bandPerThread = atoi(e);
+    if (const char *e = getenv("GMG_STENCIL_CAP")) s->stencilCap = atoi(e);
+    if (const char *e = getenv("GMG_STENCIL_LOOP")) s->stencilLoop = atoi(e);
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
     if (s->opt.use_gauss_seidel && ctx->world > 1)
@@ -2566,10 +2568,59 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
 	GMG_CUDA(cudaGetLastError());
 	return GMG_OK;
     }
+    // stencilCap: bit 0 Jacobi, bit 1 residual, bit 2 apply -- the 40-register instantiation (6 resident CTAs per SM instead of 4)
+    if (s->stencilLoop)
+    {
+	// persistent variant: what fits the device at once, every CTA walking its chunks with the next chunk's labels prefetched
+	gmg_ctx *ctx = s->ctx;
+	if (ctx->stencilSlots == 0)
+	{
+	    int per = 0;
+	    GMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stencil_loop<SM_JACOBI, false>, BLOCK, 0));
+	    ctx->stencilSlots = std::max(1, per) * ctx->smCount;
+	    if (const char *e = getenv("GMG_STENCIL_LOOP_SLOTS")) ctx->stencilSlots = std::max(1, atoi(e));  // tests: force the loop on small grids
+	}
+	const unsigned g = std::min(grid, unsigned(ctx->stencilSlots));
+	const int bit = mode == SM_JACOBI ? 1 : (mode == SM_JACOBI_ZERO ? 8 : (mode == SM_RESIDUAL ? 2 : 4));
+	if ((s->stencilLoop & bit) && grid > g)
+	{
+	    if (mode == SM_JACOBI)
+	    {
+		GMG_LAUNCH(s->ctx, KC_JACOBI, n * 25.0);
+		GMG_CUDA(launchK((k_stencil_loop<SM_JACOBI, false>), g, unsigned(BLOCK), size_t(0), st, a, int(grid)));
+	    }
+	    else if (mode == SM_JACOBI_ZERO)
+	    {
+		GMG_LAUNCH(s->ctx, KC_JACOBI, n * 18.0);
+		GMG_CUDA(launchK((k_stencil_loop<SM_JACOBI_ZERO, false>), g, unsigned(BLOCK), size_t(0), st, a, int(grid)));
+	    }
+	    else if (mode == SM_RESIDUAL)
+	    {
+		GMG_LAUNCH(s->ctx, KC_RESIDUAL, n * 25.0);
+		GMG_CUDA(launchK((k_stencil_loop<SM_RESIDUAL, false>), g, unsigned(BLOCK), size_t(0), st, a, int(grid)));
+	    }
+	    else if (dotResult)
+	    {
+		GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
+		GMG_CUDA(launchK((k_stencil_loop<SM_APPLY, true>), g, unsigned(BLOCK), size_t(0), st, a, int(grid)));
+	    }
+	    else
+	    {
+		GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
+		GMG_CUDA(launchK((k_stencil_loop<SM_APPLY, false>), g, unsigned(BLOCK), size_t(0), st, a, int(grid)));
+	    }
+	    GMG_CUDA(cudaGetLastError());
+	    return GMG_OK;
+	}
+    }
+    // measured at 256^3 (4.3 M cells, plain loads): apply 38.3 -> 32.3 us, residual 34.6 -> 31.5 us, Jacobi no gain (it spills);
+    // on a 0.5 M-cell level everything loses 5-10 % -- so: residual + apply on levels of at least 2 M cells unless GMG_STENCIL_CAP says otherwise
+    const int cap = s->stencilCap >= 0 ? s->stencilCap : (n >= 2.0e6 ? 6 : 0);
     if (mode == SM_JACOBI)
     {
 	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 25.0);
-	GMG_CUDA(launchK((k_stencil<SM_JACOBI, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	if (cap & 1) GMG_CUDA(launchK((k_stencil<SM_JACOBI, false, double, 6>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	else GMG_CUDA(launchK((k_stencil<SM_JACOBI, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     else if (mode == SM_JACOBI_ZERO)
     {
@@ -2580,17 +2631,20 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
     else if (mode == SM_RESIDUAL)
     {
 	GMG_LAUNCH(s->ctx, KC_RESIDUAL, n * 25.0);
-	GMG_CUDA(launchK((k_stencil<SM_RESIDUAL, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	if (cap & 2) GMG_CUDA(launchK((k_stencil<SM_RESIDUAL, false, double, 6>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	else GMG_CUDA(launchK((k_stencil<SM_RESIDUAL, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     else if (dotResult)
     {
 	GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
-	GMG_CUDA(launchK((k_stencil<SM_APPLY, true>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	if (cap & 4) GMG_CUDA(launchK((k_stencil<SM_APPLY, true, double, 6>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	else GMG_CUDA(launchK((k_stencil<SM_APPLY, true>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     else
     {
 	GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0);
-	GMG_CUDA(launchK((k_stencil<SM_APPLY, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	if (cap & 4) GMG_CUDA(launchK((k_stencil<SM_APPLY, false, double, 6>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	else GMG_CUDA(launchK((k_stencil<SM_APPLY, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     GMG_CUDA(cudaGetLastError());
     return GMG_OK;

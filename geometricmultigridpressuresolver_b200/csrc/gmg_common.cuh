@@ -171,6 +171,7 @@ struct gmg_ctx
     int64_t commOps = 0;          // communication operations enqueued since the last launch-count reset
     void *p2p = nullptr;          // gmg::P2pState: peer-memory mailboxes (gmg_p2p.cuh); null = NCCL for every exchange
     bool p2pDisabled = false;
+    int stencilSlots = 0;          // resident CTAs of k_stencil_loop
     int bandSlots[2] = {0, 0};     // resident CTAs of the band sweep kernel with two / three cells per thread
     int smoothClusterSize = 0;     // CTAs of the one-level smoothing cluster (k_cluster_smooth): 0 = not probed, -1 = refused
     int clusterSize = 0;           // CTAs of the coarse-cycle cluster: 0 = not probed yet, -1 = cluster launch refused
@@ -241,6 +242,8 @@ struct gmg_solver
     bool bandGroups = false;      // a group of band sweeps as ONE co-resident launch with grid barriers: measured SLOWER than a launch per sweep
 				  // (profiles/r02_ab_switches.md: 256^3 solve 11.5 vs 10.3 ms; a barrier over ~900 CTAs costs more than a kernel
 				  // boundary with its prologue overlapped), so it is opt-in (GMG_BAND_GROUPS=1)
+    int stencilLoop = 0;          // persistent full-grid stencil kernels (k_stencil_loop): bit 0 Jacobi, bit 1 residual, bit 2 apply, bit 3 zero-aware Jacobi (GMG_STENCIL_LOOP)
+    int stencilCap = -1;          // full-grid stencil kernels capped at 40 registers: bit 0 Jacobi, bit 1 residual, bit 2 apply; -1 = by level size (GMG_STENCIL_CAP)
     int bandPerThread = 0;        // cells per thread of the band sweep kernels: 0 = picked per level (launchBand), 2 / 3 = forced (GMG_BAND_PER_THREAD)
     bool bandTiles = false;       // band sweep groups as ring-halo tiles, one launch per group (k_band_tile): measured SLOWER (GMG_BAND_TILES=1 enables)
     bool bandResident = false;    // a group of band sweeps as one launch with every cell's metadata on chip (k_band_resident): measured SLOWER too

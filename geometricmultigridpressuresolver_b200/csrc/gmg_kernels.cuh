@@ -216,110 +216,93 @@ __device__ __forceinline__ double stencilBoundary(const StencilArgsT<T> &a, int 
 
 // vb = virtual CTA index (blockIdx.x of the stand-alone kernel), tid = thread index inside the BLOCK-wide virtual CTA.
 // Returns this thread's part of dot(in, A in) when DOT.  Prologue (before pdlWait): chunk id and the labels of the
-// thread's cells, or the boundary cell's index and coefficient record.
+// thread's cells (stencilLabels), or the boundary cell's index and coefficient record; then the values (stencilChunk).
+struct ChunkLabels
+{
+    uchar2 lab[CHUNK_Z], flg[CHUNK_Z];
+    int64_t inPlane;
+    int z0;
+};
+template <typename T, int MODE>
+__device__ __forceinline__ void stencilLabels(const StencilArgsT<T> &a, int vb, int tid, ChunkLabels &cl)
+{
+    const int c = a.chunks[vb];
+    const int zb = c / a.chunksPerPlane;
+    cl.inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * tid;
+    cl.z0 = zb * CHUNK_Z;
+    const int64_t inPlane = cl.inPlane;
+    const int z0 = cl.z0;
+#pragma unroll
+    for (int dz = 0; dz < CHUNK_Z; ++dz)
+    {
+	const int z = z0 + dz;
+	cl.lab[dz] = make_uchar2(L_EXTERIOR, L_EXTERIOR);
+	cl.flg[dz] = make_uchar2(0, 0);
+	if (inPlane < a.plane && z >= a.zlo && z < a.zhi)
+	{
+	    cl.lab[dz] = *reinterpret_cast<const uchar2 *>(a.labels + int64_t(z) * a.plane + inPlane);
+	    if (MODE == SM_JACOBI_ZERO) cl.flg[dz] = *reinterpret_cast<const uchar2 *>(a.flags + int64_t(z) * a.plane + inPlane);
+	}
+    }
+}
 template <typename T, int MODE, bool DOT>
-__device__ __forceinline__ double stencilBody(const StencilArgsT<T> &a, int vb, int tid)
+__device__ __forceinline__ double stencilChunk(const StencilArgsT<T> &a, const ChunkLabels &cl)
 {
     typedef typename Vec2<T>::type T2;
     double acc = 0.0;
-    if (vb < a.nChunks)
+    const int64_t inPlane = cl.inPlane;
+    const int z0 = cl.z0;
+    const uchar2 *lab = cl.lab, *flg = cl.flg;
+    if (MODE == SM_JACOBI_ZERO)
     {
-	const int c = a.chunks[vb];
-	const int zb = c / a.chunksPerPlane;
-	const int64_t inPlane = int64_t(c - zb * a.chunksPerPlane) * CHUNK_CELLS + 2 * tid;
-	const int z0 = zb * CHUNK_Z;
-	uchar2 lab[CHUNK_Z], flg[CHUNK_Z];
+	// phase 1, every cell: x is zero in the whole neighbourhood, lap = +0.0, and centre + (2/3)((b - 0) / 6) = (2/3)(b / 6);
+	// a pure stream of b in, x out, the four planes' loads in flight together
+	int near = 0;
 #pragma unroll
 	for (int dz = 0; dz < CHUNK_Z; ++dz)
 	{
-	    const int z = z0 + dz;
-	    lab[dz] = make_uchar2(L_EXTERIOR, L_EXTERIOR);
-	    flg[dz] = make_uchar2(0, 0);
-	    if (inPlane < a.plane && z >= a.zlo && z < a.zhi)
-	    {
-		lab[dz] = *reinterpret_cast<const uchar2 *>(a.labels + int64_t(z) * a.plane + inPlane);
-		if (MODE == SM_JACOBI_ZERO) flg[dz] = *reinterpret_cast<const uchar2 *>(a.flags + int64_t(z) * a.plane + inPlane);
-	    }
-	}
-	pdlWait();
-	if (MODE == SM_JACOBI_ZERO)
-	{
-	    // phase 1, every cell: x is zero in the whole neighbourhood, lap = +0.0, and centre + (2/3)((b - 0) / 6) = (2/3)(b / 6);
-	    // a pure stream of b in, x out, the four planes' loads in flight together
-	    int near = 0;
-#pragma unroll
-	    for (int dz = 0; dz < CHUNK_Z; ++dz)
-	    {
-		const bool a0 = (lab[dz].x == L_INTERIOR), a1 = (lab[dz].y == L_INTERIOR);
-		if (!(a0 | a1)) continue;
-		const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
-		const T2 rhs = ld2(a.b + i);
-		const T o0 = T(2.0 / 3.0) * (rhs.x / T(6.0)), o1 = T(2.0 / 3.0) * (rhs.y / T(6.0));
-		if (a0 & a1) st2(a.out + i, make2<T>(o0, o1));
-		else if (a0) a.out[i] = o0;
-		else a.out[i + 1] = o1;
-		near |= ((flg[dz].x | flg[dz].y) & 2) << dz;
-	    }
-	    // phase 2, the few cells with a band cell in their neighbourhood (bit dz + 1 of `near`): the full stencil with every
-	    // value taken through the band mask -- whatever the grid holds off the band reads as zero -- overwrites phase 1's
-	    // value.  One plane at a time and everything re-read (cache hits): the common path keeps no registers for it.
-#pragma unroll 1
-	    for (int dz = 0; near != 0 && dz < CHUNK_Z; ++dz)
-	    {
-		if (!((near >> (dz + 1)) & 1)) continue;
-		const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
-		const uchar2 l = *reinterpret_cast<const uchar2 *>(a.labels + i);
-		const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
-		const T2 rhs = ld2(a.b + i);
-		const uint8_t *f = a.flags + i;
-		const uchar2 fc = *reinterpret_cast<const uchar2 *>(f);
-		const uchar2 fym = *reinterpret_cast<const uchar2 *>(f - a.pitch), fyp = *reinterpret_cast<const uchar2 *>(f + a.pitch);
-		const uchar2 fzm = *reinterpret_cast<const uchar2 *>(f - a.plane), fzp = *reinterpret_cast<const uchar2 *>(f + a.plane);
-		const int fxm = f[-1], fxp = f[2];
-		T2 c2 = ld2(a.in + i);
-		T xm = a.in[i - 1], xp = a.in[i + 2];
-		T2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
-		T2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
-		if (!(fc.x & 1)) c2.x = T(0.0);
-		if (!(fc.y & 1)) c2.y = T(0.0);
-		if (!(fxm & 1)) xm = T(0.0);
-		if (!(fxp & 1)) xp = T(0.0);
-		if (!(fym.x & 1)) ym.x = T(0.0);
-		if (!(fym.y & 1)) ym.y = T(0.0);
-		if (!(fyp.x & 1)) yp.x = T(0.0);
-		if (!(fyp.y & 1)) yp.y = T(0.0);
-		if (!(fzm.x & 1)) zm.x = T(0.0);
-		if (!(fzm.y & 1)) zm.y = T(0.0);
-		if (!(fzp.x & 1)) zp.x = T(0.0);
-		if (!(fzp.y & 1)) zp.y = T(0.0);
-		T lap0 = -xm;
-		lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
-		lap0 += T(6.0) * c2.x;
-		T lap1 = -c2.x;
-		lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
-		lap1 += T(6.0) * c2.y;
-		const T o0 = stencilFinish<MODE, T>(lap0, c2.x, rhs.x, T(6.0));
-		const T o1 = stencilFinish<MODE, T>(lap1, c2.y, rhs.y, T(6.0));
-		if (a0 & a1) st2(a.out + i, make2<T>(o0, o1));
-		else if (a0) a.out[i] = o0;
-		else a.out[i + 1] = o1;
-	    }
-	    return acc;
-	}
-#pragma unroll
-	for (int dz = 0; dz < CHUNK_Z; ++dz)
-	{
-	    const int z = z0 + dz;
-	    const uchar2 l = lab[dz];
-	    const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
+	    const bool a0 = (lab[dz].x == L_INTERIOR), a1 = (lab[dz].y == L_INTERIOR);
 	    if (!(a0 | a1)) continue;
-	    const int64_t i = int64_t(z) * a.plane + inPlane;
-	    const T2 c2 = ld2(a.in + i);
-	    const T xm = a.in[i - 1], xp = a.in[i + 2];
-	    const T2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
-	    const T2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
-	    T2 rhs = make2<T>(T(0.0), T(0.0));
-	    if (MODE != SM_APPLY) rhs = ld2(a.b + i);
+	    const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
+	    const T2 rhs = ld2(a.b + i);
+	    const T o0 = T(2.0 / 3.0) * (rhs.x / T(6.0)), o1 = T(2.0 / 3.0) * (rhs.y / T(6.0));
+	    if (a0 & a1) st2(a.out + i, make2<T>(o0, o1));
+	    else if (a0) a.out[i] = o0;
+	    else a.out[i + 1] = o1;
+	    near |= ((flg[dz].x | flg[dz].y) & 2) << dz;
+	}
+	// phase 2, the few cells with a band cell in their neighbourhood (bit dz + 1 of `near`): the full stencil with every
+	// value taken through the band mask -- whatever the grid holds off the band reads as zero -- overwrites phase 1's
+	// value.  One plane at a time and everything re-read (cache hits): the common path keeps no registers for it.
+#pragma unroll 1
+	for (int dz = 0; near != 0 && dz < CHUNK_Z; ++dz)
+	{
+	    if (!((near >> (dz + 1)) & 1)) continue;
+	    const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
+	    const uchar2 l = *reinterpret_cast<const uchar2 *>(a.labels + i);
+	    const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
+	    const T2 rhs = ld2(a.b + i);
+	    const uint8_t *f = a.flags + i;
+	    const uchar2 fc = *reinterpret_cast<const uchar2 *>(f);
+	    const uchar2 fym = *reinterpret_cast<const uchar2 *>(f - a.pitch), fyp = *reinterpret_cast<const uchar2 *>(f + a.pitch);
+	    const uchar2 fzm = *reinterpret_cast<const uchar2 *>(f - a.plane), fzp = *reinterpret_cast<const uchar2 *>(f + a.plane);
+	    const int fxm = f[-1], fxp = f[2];
+	    T2 c2 = ld2(a.in + i);
+	    T xm = a.in[i - 1], xp = a.in[i + 2];
+	    T2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
+	    T2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
+	    if (!(fc.x & 1)) c2.x = T(0.0);
+	    if (!(fc.y & 1)) c2.y = T(0.0);
+	    if (!(fxm & 1)) xm = T(0.0);
+	    if (!(fxp & 1)) xp = T(0.0);
+	    if (!(fym.x & 1)) ym.x = T(0.0);
+	    if (!(fym.y & 1)) ym.y = T(0.0);
+	    if (!(fyp.x & 1)) yp.x = T(0.0);
+	    if (!(fyp.y & 1)) yp.y = T(0.0);
+	    if (!(fzm.x & 1)) zm.x = T(0.0);
+	    if (!(fzm.y & 1)) zm.y = T(0.0);
+	    if (!(fzp.x & 1)) zp.x = T(0.0);
+	    if (!(fzp.y & 1)) zp.y = T(0.0);
 	    T lap0 = -xm;
 	    lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
 	    lap0 += T(6.0) * c2.x;
@@ -331,19 +314,88 @@ __device__ __forceinline__ double stencilBody(const StencilArgsT<T> &a, int vb, 
 	    if (a0 & a1) st2(a.out + i, make2<T>(o0, o1));
 	    else if (a0) a.out[i] = o0;
 	    else a.out[i + 1] = o1;
-	    if (DOT && z >= a.dotLo && z < a.dotHi) acc += double((a0 ? c2.x * lap0 : T(0.0)) + (a1 ? c2.y * lap1 : T(0.0)));
 	}
+	return acc;
+    }
+#pragma unroll
+    for (int dz = 0; dz < CHUNK_Z; ++dz)
+    {
+	const int z = z0 + dz;
+	const uchar2 l = lab[dz];
+	const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
+	if (!(a0 | a1)) continue;
+	const int64_t i = int64_t(z) * a.plane + inPlane;
+	const T2 c2 = ld2(a.in + i);
+	const T xm = a.in[i - 1], xp = a.in[i + 2];
+	const T2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
+	const T2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
+	T2 rhs = make2<T>(T(0.0), T(0.0));
+	if (MODE != SM_APPLY) rhs = ld2(a.b + i);
+	T lap0 = -xm;
+	lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
+	lap0 += T(6.0) * c2.x;
+	T lap1 = -c2.x;
+	lap1 -= xp; lap1 -= ym.y; lap1 -= yp.y; lap1 -= zm.y; lap1 -= zp.y;
+	lap1 += T(6.0) * c2.y;
+	const T o0 = stencilFinish<MODE, T>(lap0, c2.x, rhs.x, T(6.0));
+	const T o1 = stencilFinish<MODE, T>(lap1, c2.y, rhs.y, T(6.0));
+	if (a0 & a1) st2(a.out + i, make2<T>(o0, o1));
+	else if (a0) a.out[i] = o0;
+	else a.out[i + 1] = o1;
+	if (DOT && z >= a.dotLo && z < a.dotHi) acc += double((a0 ? c2.x * lap0 : T(0.0)) + (a1 ? c2.y * lap1 : T(0.0)));
+    }
+    return acc;
+}
+template <typename T, int MODE, bool DOT>
+__device__ __forceinline__ double stencilBody(const StencilArgsT<T> &a, int vb, int tid)
+{
+    double acc = 0.0;
+    if (vb < a.nChunks)
+    {
+	ChunkLabels cl;
+	stencilLabels<T, MODE>(a, vb, tid, cl);
+	pdlWait();
+	acc = stencilChunk<T, MODE, DOT>(a, cl);
     }
     else acc = stencilBoundary<T, MODE, DOT>(a, (vb - a.nChunks) * BLOCK + tid);
     return acc;
 }
 
 // (the zero-aware sweep streams b -> x on its common path: capped at 40 registers so the rare masked path cannot cost it occupancy)
-template <int MODE, bool DOT, typename T = double>
-__global__ void __launch_bounds__(BLOCK, MODE == SM_JACOBI_ZERO ? 6 : 1) k_stencil(const StencilArgsT<T> a)
+// MINB = 6 on the other modes too trades loads in flight per thread for resident CTAs (56 -> 40 registers): see launchStencil
+template <int MODE, bool DOT, typename T = double, int MINB = (MODE == SM_JACOBI_ZERO ? 6 : 1)>
+__global__ void __launch_bounds__(BLOCK, MINB) k_stencil(const StencilArgsT<T> a)
 {
     pdlLaunch();
     const double acc = stencilBody<T, MODE, DOT>(a, blockIdx.x, threadIdx.x);
+    if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
+}
+
+// The same operator as a PERSISTENT kernel: the grid is what fits the device at once, a CTA walks the virtual CTAs vb, vb + grid, ...
+// and loads the chunk id and labels of its NEXT chunk before it computes the current one.  A virtual CTA of k_stencil is a chain of
+// three dependent round trips (chunk id -> labels -> values); only the first wave overlaps the first two with its predecessor (PDL),
+// and a 256^3 level is 4-6 waves.  Here every chunk after a CTA's first costs one round trip.  Same per-cell arithmetic; the fused dot
+// product sums over another decomposition (different rounding of p.Ap, like the TMA kernel).
+template <int MODE, bool DOT, typename T = double>
+__global__ void __launch_bounds__(BLOCK, 6) k_stencil_loop(const StencilArgsT<T> a, int nVirtual)
+{
+    pdlLaunch();
+    const int tid = threadIdx.x;
+    double acc = 0.0;
+    int vb = blockIdx.x;
+    ChunkLabels cur = {};
+    if (vb < a.nChunks) stencilLabels<T, MODE>(a, vb, tid, cur);
+    pdlWait();
+    while (vb < a.nChunks)
+    {
+	const int nx = vb + int(gridDim.x);
+	ChunkLabels nxt = {};
+	if (nx < a.nChunks) stencilLabels<T, MODE>(a, nx, tid, nxt);
+	acc += stencilChunk<T, MODE, DOT>(a, cur);
+	cur = nxt;
+	vb = nx;
+    }
+    for (; vb < nVirtual; vb += int(gridDim.x)) acc += stencilBoundary<T, MODE, DOT>(a, (vb - a.nChunks) * BLOCK + tid);
     if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
 }
 
