@@ -283,6 +283,146 @@ def measure_sweep(torch, api, ctx, dist, rank, world, n, steps, warmup, flush):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ 512^3 free-surface solve (north_star target)
+def flipsplash_inputs_gpu(torch, n):
+    """domains.flipsplash_domain + ghost_fluid_weights with the same arithmetic in the same order, evaluated by torch on the GPU (the numpy
+    generator needs ~60 s and ~12 GB per rank at 512^3).  Returns host arrays (labels int32, [w_x, w_y, w_z] float64, dx)."""
+    dev, f64 = "cuda", torch.float64
+    a = torch.arange(n, dtype=f64, device=dev)
+    k, j, i = a[:, None, None], a[None, :, None], a[None, None, :]
+    N = float(n)
+    phi = (j - 0.25 * n).expand(n, n, n).clone()
+    r = 0.06 * N
+    for cx in (n / 3.0, n / 2.0, 2.0 * n / 3.0):
+        for cz in (n / 3.0, n / 2.0, 2.0 * n / 3.0):
+            phi = torch.minimum(phi, torch.sqrt((i - cx) ** 2 + (j - 0.65 * n) ** 2 + (k - cz) ** 2) - r)
+    phi /= N
+    labels = torch.where(phi <= 0, D.INTERIOR, D.DIRICHLET).to(torch.int32)
+    labels[:, :, 0] = D.EXTERIOR
+    labels[:, :, n - 1] = D.EXTERIOR
+    labels[0, :, :] = D.EXTERIOR
+    labels[n - 1, :, :] = D.EXTERIOR
+    labels[:, 0, :] = D.EXTERIOR
+    weights = []
+    for axis in range(3):
+        na = 2 - axis
+        lb, lf = labels.narrow(na, 0, n - 1), labels.narrow(na, 1, n - 1)
+        pb, pf = phi.narrow(na, 0, n - 1), phi.narrow(na, 1, n - 1)
+        theta = torch.zeros_like(pb)
+        both, ca, cb = (pb < 0) & (pf < 0), (pb < 0) & (pf >= 0), (pb >= 0) & (pf < 0)
+        theta = torch.where(both, torch.ones_like(theta), theta)
+        theta = torch.where(ca, pb / (pb - pf), theta)
+        theta = torch.where(cb, pf / (pf - pb), theta)
+        theta = theta.clamp(0.01, 1.0)
+        both_int = (lb == D.INTERIOR) & (lf == D.INTERIOR)
+        mixed = ((lb == D.INTERIOR) & (lf == D.DIRICHLET)) | ((lb == D.DIRICHLET) & (lf == D.INTERIOR))
+        inner = torch.where(both_int, torch.ones_like(theta), torch.where(mixed, 1.0 / theta, torch.zeros_like(theta)))
+        del theta, both, ca, cb, both_int, mixed
+        shape = [n, n, n]
+        shape[na] += 1
+        w = torch.zeros(shape, dtype=f64, device=dev)
+        w.narrow(na, 1, n - 1).copy_(inner)
+        del inner
+        weights.append(w.cpu().numpy())
+        del w
+    out = labels.cpu().numpy(), weights, 1.0 / N
+    del phi, labels
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_solve_big(torch, api, ctx, dist, rank, world, local_rank, n, steps, warmup, flush):
+    """The north_star's target workload: an n^3 (512^3) flipSplash-shaped FREE-SURFACE MGPCG solve to 1e-6, sharded over the ranks like the
+    headline solve.  Block `solve512` of the line: solve ms (max over ranks), iterations, per-kernel-class fractions of the measured HBM
+    peak at the fine level, and at N > 1 the agreement with an unsharded solve of the same inputs on rank 0."""
+    t0 = time.perf_counter()
+    sb, sw, sdx = flipsplash_inputs_gpu(torch, 64)
+    nb, nw, ndx = D.flipsplash_domain(64)
+    same = bool((sb == nb).all() and sdx == ndx)  # labels must be identical; a face weight may differ in the last bit (division / sqrt rounding)
+    wdev = max(float(np.abs(x - y).max()) for x, y in zip(sw, nw))
+    bl, bw, dx = flipsplash_inputs_gpu(torch, n)
+    labels, w, off, levels, box = ctx.buildExpandedDomainLazy(bl, bw)
+    del bl, bw
+    solver = api.GeometricMultigridPoissonSolver(ctx, labels, w, levels, box=box)
+    active = solver.active_cells(0)
+    rng = np.random.default_rng(SEED)
+    b_host = np.zeros(labels.shape, dtype=np.float64)
+    sl = tuple(slice(int(box[0][2 - k]), int(box[1][2 - k])) for k in range(3))
+    b_host[sl] = rng.random(tuple(s.stop - s.start for s in sl)) * dx * dx * D.active_mask(labels[sl])
+    B, X = solver.grid(0, b_host), solver.grid(0)
+    nlev = solver.getMGLevels()
+    build_s = time.perf_counter() - t0
+
+    def sync():
+        torch.cuda.synchronize()
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    it, hist = 0, []
+    for _ in range(warmup):
+        X.zero()
+        it, hist = solver.solveDevice(X, B, TOL, MAX_IT)
+    sync()
+    ctx.launch_count(reset=True)
+    ms_list = []
+    for _ in range(steps):
+        X.zero()
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.timer_begin()
+        it, hist = solver.solveDevice(X, B, TOL, MAX_IT)
+        ms_list.append(ctx.timer_end())
+    sync()
+    launches, comm_ops = ctx.launch_count(), ctx.comm_count()
+    ms = float(np.mean(ms_list))
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    X.zero()
+    solver.solveDevice(X, B, TOL, MAX_IT)
+    prof_all, prof_fine = ctx.profile(False), ctx.profile(True)
+    ctx.profile_enable(False)
+    peak, peak_kind = measured_peak()
+    fine = {k: v for k, v in prof_fine.items() if k not in ("setup", "coarse_solve", "halo_exchange") and v[1] > 0 and v[2] > 0}
+    total_ms = sum(v[0] for k, v in prof_all.items() if k != "setup")
+    classes = {k: {"us_per_launch": v[0] / v[1] * 1e3, "launches_per_solve": v[1], "algorithmic_gbs": v[2] / (v[0] * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": v[2] / (v[0] * 1e-3) / 1e9 / peak, "share_of_solve": prof_all[k][0] / total_ms} for k, v in fine.items()}
+    halo = prof_all.get("halo_exchange")
+    agreement = None
+    if world > 1:
+        if rank == 0:
+            ctx1 = api.Context(local_rank)
+            s1 = api.GeometricMultigridPoissonSolver(ctx1, labels, w, levels, box=box)
+            B1, X1 = s1.grid(0, b_host), s1.grid(0)
+            t1 = []
+            for _ in range(2):
+                X1.zero()
+                ctx1.timer_begin()
+                it1, hist1 = s1.solveDevice(X1, B1, TOL, MAX_IT)
+                t1.append(ctx1.timer_end())
+            agreement = {"n1_solve_ms": float(t1[-1]), "iterations_equal": bool(it1 == it), "max_rel_history_dev": rel_history_dev(hist, hist1), "bar": 1e-9}
+            B1.close(); X1.close(); s1.close(); ctx1.close()
+        dist.barrier()
+    out = {
+        "workload": f"{n}^3 flipSplash-shaped free-surface domain (pool + 3x3 falling blobs, ghost-fluid face weights), expanded {2 * n}^3, MGPCG to 1e-6, Jacobi smoother",
+        "levels": nlev, "active_cells": active, "solve_ms": ms, "iterations": int(it), "final_rel_residual": float(hist[-1]) if len(hist) else None,
+        "steps": steps, "warmup": warmup, "l2": "256 MB flush write before every timed solve",
+        "fine_level_kernels": classes, "halo_exchange_ms_per_solve": halo[0] if halo and halo[1] else 0.0,
+        "kernel_timing": "CUDA event nodes inside the replayed PCG graphs, one instrumented solve (rank 0's slab when sharded)",
+        "peak": peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+        "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "host_build_s": build_s, "inputs": "generated by torch on the GPU (every rank the same arrays); against domains.flipsplash_domain at 64^3: labels "
+                  + ("identical" if same else "DIFFERENT") + f", face weights within {wdev:.1e}",
+        "agreement_1_vs_n": agreement, "parallelism": "single GPU" if world == 1 else f"{world} z-slabs",
+    }
+    B.close(); X.close(); solver.close()
+    del w, b_host, labels
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ 1024^3 narrow band
 def narrow_band_labels_u8(n, thickness=12):
     """BASELINE.json configs[4] without ever holding a dense n^3 float array: the EXPANDED one-byte label
@@ -662,6 +802,13 @@ def run_gpu_arm(args, rank, world, local_rank):
     sweep = None
     if not args.no_sweep and not args.quick:
         sweep = measure_sweep(torch, api, ctx, dist, rank, world, args.sweep_size, 10, 3, flush)
+    solve_big = None
+    if not args.no_sweep and not args.quick:
+        # the north_star's target workload (512^3 free-surface MGPCG), sharded like the headline solve
+        solve_big = measure_solve_big(torch, api, ctx, dist, rank, world, local_rank, args.sweep_size, 3, 1, flush)
+        ag = (solve_big or {}).get("agreement_1_vs_n")
+        if ag and (not ag["iterations_equal"] or ag["max_rel_history_dev"] > 1e-9):
+            parity_failed.append("solve512_agreement_1_vs_n")
     narrow = None
     narrow_size = args.narrow_size if args.narrow_size is not None else (1024 if world == 8 else 0)
     if narrow_size:
@@ -690,7 +837,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "kernel_timing": "CUDA events recorded as nodes inside the replayed PCG graphs (warm L2, back-to-back launches); separate pass from `value`",
             "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "gauss_seidel": gs, "gpu_launches": int(launches), "nccl_ops": int(comm_ops), "wall_s_timed_region": wall_s,
             "parity_vs_cpu": parity_vs_cpu, "parity_vs_n1": parity_vs_n1, "parity_failed": parity_failed,
-            "sweep512": sweep, "narrow1024": narrow, "mixed_precision": mixed,
+            "sweep512": sweep, "solve512": solve_big, "narrow1024": narrow, "mixed_precision": mixed,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -722,6 +869,20 @@ def run_vcycle_sweep(args, rank, world, local_rank):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if args.workload == "solve512":
+        blk = measure_solve_big(torch, api, ctx, dist, rank, world, local_rank, args.size, args.steps, args.warmup, flush)
+        clocks = sampler.stop()
+        if rank == 0:
+            line = {"metric": "mgpcg_solve_ms", "value": blk["solve_ms"], "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": blk["solve_ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": blk["workload"], "levels": blk["levels"], "active_cells": blk["active_cells"], "l2": blk["l2"],
+                               "parallelism": blk["parallelism"]}, "clocks": clocks}
+            line.update({k: v for k, v in blk.items() if k not in ("workload", "levels", "active_cells", "l2", "parallelism", "steps", "warmup")})
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     blk = measure_sweep(torch, api, ctx, dist, rank, world, args.size, args.steps, args.warmup, flush)
     clocks = sampler.stop()
     if rank == 0:
@@ -742,7 +903,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=None)
-    ap.add_argument("--workload", default="pcg", choices=["pcg", "vcycle"], help="pcg: the headline 256^3 MGPCG solve; vcycle: V-cycle-only sweep (config 4)")
+    ap.add_argument("--workload", default="pcg", choices=["pcg", "vcycle", "solve512"],
+                    help="pcg: the headline 256^3 MGPCG solve; vcycle: V-cycle-only sweep (config 4); solve512: the north_star's 512^3 free-surface solve as a line of its own")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="A/B runs: value, V-cycle and per-kernel times only (no e2e, Gauss-Seidel, CPU baseline, sweep512)")
@@ -752,13 +914,13 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.size is None:
-        args.size = 512 if args.workload == "vcycle" else 256
+        args.size = 512 if args.workload in ("vcycle", "solve512") else 256
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
-    elif args.workload == "vcycle":
+    elif args.workload in ("vcycle", "solve512"):
         run_vcycle_sweep(args, rank, world, local_rank)
     else:
         run_gpu_arm(args, rank, world, local_rank)
