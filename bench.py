@@ -404,7 +404,10 @@ def measure_solve_big(torch, api, ctx, dist, rank, world, local_rank, n, steps, 
                 ctx1.timer_begin()
                 it1, hist1 = s1.solveDevice(X1, B1, TOL, MAX_IT)
                 t1.append(ctx1.timer_end())
-            agreement = {"n1_solve_ms": float(t1[-1]), "iterations_equal": bool(it1 == it), "max_rel_history_dev": rel_history_dev(hist, hist1), "bar": 1e-9}
+            agreement = {"n1_solve_ms": float(t1[-1]), "iterations_equal": bool(it1 == it), "max_rel_history_dev": rel_history_dev(hist, hist1),
+                         "rel_history_dev_per_iteration": [float(abs(a - b) / abs(b)) for a, b in zip(hist, hist1)],
+                         "bar": 1e-6, "bar_note": "north_star asks 1e-5; the V-cycle is bitwise the unsharded one, the dot products are all-reduced in another order: "
+                                                  "the deviation starts at rounding level and is amplified by the CG recurrence (measured 1e-9 .. 4e-8 after 18 iterations)"}
             B1.close(); X1.close(); s1.close(); ctx1.close()
         dist.barrier()
     out = {
@@ -807,7 +810,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         # the north_star's target workload (512^3 free-surface MGPCG), sharded like the headline solve
         solve_big = measure_solve_big(torch, api, ctx, dist, rank, world, local_rank, args.sweep_size, 3, 1, flush)
         ag = (solve_big or {}).get("agreement_1_vs_n")
-        if ag and (not ag["iterations_equal"] or ag["max_rel_history_dev"] > 1e-9):
+        if ag and (not ag["iterations_equal"] or ag["max_rel_history_dev"] > ag["bar"]):
             parity_failed.append("solve512_agreement_1_vs_n")
     narrow = None
     narrow_size = args.narrow_size if args.narrow_size is not None else (1024 if world == 8 else 0)
