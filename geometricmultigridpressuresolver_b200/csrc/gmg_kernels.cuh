@@ -1543,55 +1543,78 @@ __global__ void __launch_bounds__(BLOCK, 2) k_gauss_seidel2(const GsArgs2 p)
     const int ox = a.off[0] + tx * GS_TILE, oy = a.off[1] + ty * GS_TILE, oz = a.off[2] + tz * GS_TILE;
     if (threadIdx.x == 0) poolCount = 0;
     __syncthreads();
+    // A thread owns the column (lx, ly) of the tile: cell i = q * 256 + tid is (lx, ly, lz = q).  Every phase below issues the
+    // column's 16 loads TOGETHER (unrolled, predicated) -- the first version walked them one dependent round trip at a time
+    // (label -> position -> record, 16 times over) and a tile spent half of its 60 us there (profiles/r02_gauss_seidel.md).
+    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    const int gx0 = ox + lx, gy0 = oy + ly;
+    const bool inXY = gx0 >= 0 && gy0 >= 0 && gx0 < a.n[0] && gy0 < a.n[1];
+    const int64_t g0 = int64_t(oz) * a.plane + int64_t(gy0) * a.pitch + gx0;
     // prologue (static): labels, and the records of the tile's BOUNDARY cells into the pool
-    for (int i = threadIdx.x; i < GS_TILE * GS_TILE * GS_TILE; i += BLOCK)
+    uint8_t lab[GS_TILE];
+#pragma unroll
+    for (int q = 0; q < GS_TILE; ++q)
     {
-	const int lz = i >> 8, ly = (i >> 4) & 15, lx = i & 15;
-	const int gx = ox + lx, gy = oy + ly, gz = oz + lz;
-	uint8_t l = L_EXTERIOR;
+	const int gz = oz + q;
+	lab[q] = (inXY && gz >= 0 && gz < a.n[2]) ? a.labels[g0 + int64_t(q) * a.plane] : uint8_t(L_EXTERIOR);
+    }
+    int bp[GS_TILE];
+#pragma unroll
+    for (int q = 0; q < GS_TILE; ++q) bp[q] = lab[q] == L_BOUNDARY ? a.bpos[g0 + int64_t(q) * a.plane] : -1;
+    double dg[GS_TILE];
+    unsigned short cd[GS_TILE];
+#pragma unroll
+    for (int q = 0; q < GS_TILE; ++q)
+    {
+	dg[q] = bp[q] >= 0 ? a.bcoef[int64_t(6) * a.nBoundary + bp[q]] : 0.0;
+	cd[q] = bp[q] >= 0 ? p.wcode[bp[q]] : (unsigned short)0;
+    }
+#pragma unroll
+    for (int q = 0; q < GS_TILE; ++q)
+    {
 	unsigned short sl = GS_SLOT_NONE;
-	if (gx >= 0 && gy >= 0 && gz >= 0 && gx < a.n[0] && gy < a.n[1] && gz < a.n[2])
+	if (bp[q] >= 0)
 	{
-	    const int64_t g = int64_t(gz) * a.plane + int64_t(gy) * a.pitch + gx;
-	    l = a.labels[g];
-	    if (l == L_BOUNDARY)
+	    const int s0 = atomicAdd(&poolCount, 1);
+	    if (s0 < GS_POOL)
 	    {
-		const int k = a.bpos[g];
-		const int s0 = atomicAdd(&poolCount, 1);
-		if (s0 < GS_POOL)
-		{
-		    poolDiag[s0] = a.bcoef[int64_t(6) * a.nBoundary + k];
-		    poolCode[s0] = p.wcode[k];
-		    sl = (unsigned short)s0;
-		}
-		else sl = GS_SLOT_OVERFLOW;
+		poolDiag[s0] = dg[q];
+		poolCode[s0] = cd[q];
+		sl = (unsigned short)s0;
 	    }
+	    else sl = GS_SLOT_OVERFLOW;
 	}
-	ls[i] = l;
-	slot[i] = sl;
+	ls[q * BLOCK + threadIdx.x] = lab[q];
+	slot[q * BLOCK + threadIdx.x] = sl;
     }
     pdlWait();
-    for (int i = threadIdx.x; i < GS_HALO * GS_HALO * GS_HALO; i += BLOCK)
     {
-	const int lz = i / (GS_HALO * GS_HALO), ly = (i - lz * GS_HALO * GS_HALO) / GS_HALO, lx = i - (lz * GS_HALO + ly) * GS_HALO;
-	const int gx = ox + lx - 1, gy = oy + ly - 1, gz = oz + lz - 1;
-	double v = 0.0;
-	if (gx >= 0 && gy >= 0 && gz >= 0 && gx < a.n[0] && gy < a.n[1] && gz < a.n[2]) v = a.x[int64_t(gz) * a.plane + int64_t(gy) * a.pitch + gx];
-	xs[i] = v;
-    }
-    for (int i = threadIdx.x; i < GS_TILE * GS_TILE * GS_TILE; i += BLOCK)
-    {
-	const int l = ls[i];
-	double v = 0.0;
-	if (l == L_INTERIOR || l == L_BOUNDARY)
+	constexpr int HALO_CELLS = GS_HALO * GS_HALO * GS_HALO, HALO_ROUNDS = (HALO_CELLS + BLOCK - 1) / BLOCK;
+	double hv[HALO_ROUNDS];
+#pragma unroll
+	for (int q = 0; q < HALO_ROUNDS; ++q)
 	{
-	    const int lz = i >> 8, ly = (i >> 4) & 15, lx = i & 15;
-	    v = a.b[int64_t(oz + lz) * a.plane + int64_t(oy + ly) * a.pitch + (ox + lx)];
+	    const int i = q * BLOCK + int(threadIdx.x);
+	    const int hz = i / (GS_HALO * GS_HALO), hy = (i - hz * GS_HALO * GS_HALO) / GS_HALO, hx = i - (hz * GS_HALO + hy) * GS_HALO;
+	    const int gx = ox + hx - 1, gy = oy + hy - 1, gz = oz + hz - 1;
+	    hv[q] = 0.0;
+	    if (i < HALO_CELLS && gx >= 0 && gy >= 0 && gz >= 0 && gx < a.n[0] && gy < a.n[1] && gz < a.n[2])
+		hv[q] = a.x[int64_t(gz) * a.plane + int64_t(gy) * a.pitch + gx];
 	}
-	bs[i] = v;
+	double bv[GS_TILE];
+#pragma unroll
+	for (int q = 0; q < GS_TILE; ++q)
+	    bv[q] = (lab[q] == L_INTERIOR || lab[q] == L_BOUNDARY) ? a.b[g0 + int64_t(q) * a.plane] : 0.0;
+#pragma unroll
+	for (int q = 0; q < HALO_ROUNDS; ++q)
+	{
+	    const int i = q * BLOCK + int(threadIdx.x);
+	    if (i < HALO_CELLS) xs[i] = hv[q];
+	}
+#pragma unroll
+	for (int q = 0; q < GS_TILE; ++q) bs[q * BLOCK + threadIdx.x] = bv[q];
     }
     __syncthreads();
-    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
     for (int step = 0; step <= 3 * (GS_TILE - 1); ++step)
     {
 	const int sfront = a.forward ? step : 3 * (GS_TILE - 1) - step;
