@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "gmg_vcycle", "gmg_pcg", "gmg_grid_create", "gmg_grid_destroy", "gmg_grid_upload", "gmg_grid_download", "gmg_grid_zero", "gmg_grid_copy",
     "gmg_jacobi", "gmg_gauss_seidel", "gmg_boundary_jacobi", "gmg_apply", "gmg_residual", "gmg_restrict", "gmg_prolong_add", "gmg_dot", "gmg_norm2", "gmg_inf_norm",
     "gmg_axpy", "gmg_add_scaled", "gmg_scale", "gmg_vcycle_device", "gmg_pcg_device", "gmg_launch_count", "gmg_timer_begin", "gmg_timer_end",
-    "gmg_build_domain_labels", "gmg_build_boundary_weights", "gmg_build_rhs", "gmg_apply_old_pressure", "gmg_apply_solution_to_pressure", "gmg_apply_pressure_gradient",
+    "gmg_build_material_labels", "gmg_build_valid_faces", "gmg_build_domain_labels", "gmg_build_boundary_weights", "gmg_build_rhs", "gmg_apply_old_pressure", "gmg_apply_solution_to_pressure", "gmg_apply_pressure_gradient",
     "gmg_profile_enable", "gmg_kernel_class_count", "gmg_kernel_class_name", "gmg_profile_get", "gmg_profile_reset", "gmg_profile_get_level",
 ]
 
@@ -291,6 +291,26 @@ class Context:
     def _f32(a):
         a = np.ascontiguousarray(a, dtype=np.float32)
         return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def buildMaterialCellLabels(self, liquidSurface, solidSurface, cutCell):
+        """HDK_Utilities.cpp:87-148: SOLID (0) / LIQUID (1) / AIR (2) from the surface SDF, the solid SDF sampled at the cell centres
+        and the three cut-cell weight fields."""
+        ls, lsp = self._f32(liquidSurface)
+        so, sop = self._f32(solidSurface)
+        assert so.shape == ls.shape and all(np.shape(cutCell[a]) == face_shape(ls.shape, a) for a in range(3))
+        kc, cp = self._field_ptrs(cutCell)
+        out = np.empty(ls.shape, dtype=np.int32)
+        _check(self.lib.gmg_build_material_labels(self.h, lsp, sop, cp, _res(ls.shape), out.ctypes.data_as(_i32p)))
+        return out
+
+    def buildValidFaces(self, material, cutCell, axis):
+        """GFS.cpp:717-744 for one axis: 1 on faces with a cut-cell weight > 0 next to a LIQUID cell, else 0 (fpreal32)."""
+        m, mp = _i32(material)
+        cc, ccp = self._f32(cutCell)
+        assert cc.shape == face_shape(m.shape, axis)
+        out = np.empty(cc.shape, dtype=np.float32)
+        _check(self.lib.gmg_build_valid_faces(self.h, mp, ccp, _res(m.shape), int(axis), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
 
     def buildMGDomainLabels(self, material):
         """GFS.cpp:746-793: LIQUID (1) -> INTERIOR, AIR (2) -> DIRICHLET, else EXTERIOR."""

@@ -2260,6 +2260,7 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     if (const char *e = getenv("GMG_BAND_GROUPS")) s->bandGroups = (e[0] == '1');
     if (const char *e = getenv("GMG_BAND_RESIDENT")) s->bandResident = (e[0] == '1');
     if (const char *e = getenv("GMG_BAND_TILES")) s->bandTiles = (e[0] == '1');
+    if (const char *e = getenv("GMG_BAND_GROUP_MAX")) s->bandGroupMax = atoll(e);
     if (const char *e = getenv("GMG_BAND_PER_THREAD")) s->bandPerThread = atoi(e);
     if (const char *e = getenv("GMG_STENCIL_CAP")) s->stencilCap = atoi(e);
     if (const char *e = getenv("GMG_STENCIL_LOOP")) s->stencilLoop = atoi(e);
@@ -2686,7 +2687,8 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
 	GMG_CUDA(cudaGetLastError());
 	return GMG_OK;
     }
-    if (sweeps >= 2 && s->bandResident && s->ctx->groupBarrier)
+    const bool groupHere = s->bandGroupMax <= 0 || L.nBand <= s->bandGroupMax;
+    if (sweeps >= 2 && s->bandResident && groupHere && s->ctx->groupBarrier)
     {
 	// the whole group in one launch of 2 x 512 threads per SM with every cell's metadata resident (k_band_resident);
 	// bands beyond the capacity of 6 cells per thread take the sweep-per-launch kernels below
@@ -2731,7 +2733,7 @@ static int launchBand(gmg_solver *s, int level, double *x, const double *b, int 
 	    return GMG_OK;
 	}
     }
-    if (sweeps >= 2 && s->bandGroups && s->ctx->groupBarrier)
+    if (sweeps >= 2 && s->bandGroups && groupHere && s->ctx->groupBarrier)
     {
 	// the whole group in one co-resident launch with grid barriers between the sweeps (k_band_group)
 	gmg_ctx *ctx = s->ctx;
@@ -4969,6 +4971,50 @@ extern "C" int gmg_apply_pressure_gradient(gmg_ctx *ctx, float *velocity, const 
 										      baseBox(res, nullptr, nullptr), axis);
     }
     GMG_CUDA(cudaMemcpyAsync(velocity, v.p, sizeof(float) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
+}
+
+extern "C" int gmg_build_material_labels(gmg_ctx *ctx, const float *liquidSurface, const float *solidSurface, const float *const cutCell[3], const int64_t res[3],
+					 int32_t *material)
+{
+    if (!ctx || !liquidSurface || !solidSurface || !cutCell || !res || !material) return invalid("gmg_build_material_labels: null argument");
+    GMG_CUDA(enterCtx(ctx));
+    const int64_t n = cellsOf(res);
+    DevBuf ls, so, c[3], m;
+    FeCut fc;
+    GMG_TRY(devUpload(ctx, ls, liquidSurface, n));
+    GMG_TRY(devUpload(ctx, so, solidSurface, n));
+    for (int a = 0; a < 3; ++a)
+    {
+	if (!cutCell[a]) return invalid("gmg_build_material_labels: null field");
+	GMG_TRY(devUpload(ctx, c[a], cutCell[a], facesOf(res, a)));
+	fc.cutCell[a] = c[a].as<float>();
+    }
+    GMG_TRY(devUpload<int32_t>(ctx, m, nullptr, n));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_fe_material_labels<<<unsigned(divUp(n, BLOCK)), BLOCK, 0, ctx->stream>>>(m.as<int32_t>(), ls.as<float>(), so.as<float>(), fc, baseBox(res, nullptr, nullptr));
+    }
+    GMG_CUDA(cudaMemcpyAsync(material, m.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMG_OK;
+}
+
+extern "C" int gmg_build_valid_faces(gmg_ctx *ctx, const int32_t *material, const float *cutCell, const int64_t res[3], int axis, float *validFaces)
+{
+    if (!ctx || !material || !cutCell || !res || !validFaces || axis < 0 || axis > 2) return invalid("gmg_build_valid_faces: bad argument");
+    GMG_CUDA(enterCtx(ctx));
+    const int64_t n = cellsOf(res), nf = facesOf(res, axis);
+    DevBuf m, c, v;
+    GMG_TRY(devUpload(ctx, m, material, n));
+    GMG_TRY(devUpload(ctx, c, cutCell, nf));
+    GMG_TRY(devUpload<float>(ctx, v, nullptr, nf));
+    {
+	GMG_LAUNCH(ctx, KC_SETUP, 0);
+	k_fe_valid_faces<<<unsigned(divUp(nf, BLOCK)), BLOCK, 0, ctx->stream>>>(v.as<float>(), m.as<int32_t>(), c.as<float>(), baseBox(res, nullptr, nullptr), axis);
+    }
+    GMG_CUDA(cudaMemcpyAsync(validFaces, v.p, sizeof(float) * nf, cudaMemcpyDeviceToHost, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     return GMG_OK;
 }

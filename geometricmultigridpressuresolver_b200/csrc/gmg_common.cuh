@@ -249,6 +249,8 @@ struct gmg_solver
     bool bandResident = false;    // a group of band sweeps as one launch with every cell's metadata on chip (k_band_resident): measured SLOWER too
 				  // (11.04 vs 10.22 ms: with the prologues overlapped a kernel boundary costs what a 296-CTA barrier costs, ~2.5-3 us,
 				  // and two 512-thread CTAs per SM gather with less parallelism than the sweep kernels); opt-in, GMG_BAND_RESIDENT=1
+    int64_t bandGroupMax = 0;     // GMG_BAND_GROUP_MAX: the two one-launch group variants above only on levels whose band has at most this many cells
+				  // (0 = no limit): a barrier over a few dozen CTAs is cheaper than one over 296 or ~900
     bool zeroAware = true;        // zero-aware down-stroke (no zero fill, SM_JACOBI_ZERO); GMG_ZERO_AWARE=0 at creation restores the fill
 };
 

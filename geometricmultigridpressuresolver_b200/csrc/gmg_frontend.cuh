@@ -132,4 +132,77 @@ __global__ void __launch_bounds__(BLOCK) k_fe_pressure_gradient(float *velocity,
     if (bm != MAT_LIQUID || fm != MAT_LIQUID) gradient /= ghostFluidTheta(double(liquidSurface[bi]), double(liquidSurface[fi]));
     velocity[f] = float(double(velocity[f]) - gradient);
 }
+
+// HDK_Utilities.cpp:87-148 buildMaterialCellLabels with isCellLiquid (:5-45) inlined: a cell with no open face (every one of its six
+// cut-cell weights <= 0) is SOLID; otherwise LIQUID if its surface value is <= 0, or if the solid sample is >= 0 (:24) and an open
+// face leads to an in-range neighbour whose surface value is <= 0 (:26-41); else AIR.  solidAtCentres is the solid SDF sampled at
+// the surface field's cell centres (solidSurface.getValue(pos), :22-24 -- the HDK's own interpolation stays with the caller; for a
+// collision field aligned with the surface field it is the field itself).
+struct FeCut
+{
+    const float *cutCell[3];
+};
+__global__ void __launch_bounds__(BLOCK) k_fe_material_labels(int32_t *material, const float *liquidSurface, const float *solidAtCentres, FeCut fc, BaseBox g)
+{
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= g.r[0] * g.r[1] * g.r[2]) return;
+    const long long c[3] = {i % g.r[0], (i / g.r[0]) % g.r[1], i / (g.r[0] * g.r[1])};
+    const long long stride[3] = {1, g.r[0], g.r[0] * g.r[1]};
+    bool open[3][2];
+    bool inFluid = false;
+#pragma unroll
+    for (int axis = 0; axis < 3; ++axis)
+#pragma unroll
+	for (int direction = 0; direction < 2; ++direction)
+	{
+	    long long fr[3] = {g.r[0], g.r[1], g.r[2]};
+	    ++fr[axis];
+	    long long f[3] = {c[0], c[1], c[2]};
+	    f[axis] += direction;  // cellToFaceMap
+	    open[axis][direction] = fc.cutCell[axis][f[0] + fr[0] * (f[1] + fr[1] * f[2])] > 0;
+	    inFluid |= open[axis][direction];
+	}
+    int label = MAT_SOLID;
+    if (inFluid)
+    {
+	bool liquid = liquidSurface[i] <= 0.;
+	if (!liquid && solidAtCentres[i] >= 0)
+	{
+#pragma unroll
+	    for (int axis = 0; axis < 3; ++axis)
+#pragma unroll
+		for (int direction = 0; direction < 2; ++direction)
+		{
+		    if (!open[axis][direction]) continue;
+		    const long long a = c[axis] + (direction == 0 ? -1 : 1);  // cellToCellMap
+		    if (a < 0 || a >= g.r[axis]) continue;
+		    if (liquidSurface[i + (direction == 0 ? -stride[axis] : stride[axis])] <= 0) liquid = true;
+		}
+	}
+	label = liquid ? MAT_LIQUID : MAT_AIR;
+    }
+    material[i] = label;
+}
+
+// GFS.cpp:717-744 buildValidFaces -> HDK_Utilities.h:137-189 classifyValidFaces, one axis: a face is VALID (1) where its cut-cell
+// weight is > 0, both of its cells are in range and at least one of them is LIQUID; INVALID (0) elsewhere (:724)
+__global__ void __launch_bounds__(BLOCK) k_fe_valid_faces(float *validFaces, const int32_t *material, const float *cutCell, BaseBox g, int axis)
+{
+    long long fr[3] = {g.r[0], g.r[1], g.r[2]};
+    ++fr[axis];
+    const long long f = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (f >= fr[0] * fr[1] * fr[2]) return;
+    float v = 0.f;
+    if (cutCell[f] > 0)
+    {
+	const long long c[3] = {f % fr[0], (f / fr[0]) % fr[1], f / (fr[0] * fr[1])};
+	if (c[axis] - 1 >= 0 && c[axis] < g.r[axis])
+	{
+	    const long long fi = c[0] + g.r[0] * (c[1] + g.r[1] * c[2]);
+	    const long long stride = axis == 0 ? 1 : (axis == 1 ? g.r[0] : g.r[0] * g.r[1]);
+	    if (material[fi - stride] == MAT_LIQUID || material[fi] == MAT_LIQUID) v = 1.f;
+	}
+    }
+    validFaces[f] = v;
+}
 } // namespace gmg

@@ -214,6 +214,15 @@ int gmg_pcg_device(gmg_solver *s, gmg_grid *x, const gmg_grid *b, double tol, in
  * face field of axis a has one more entry along a).  SIM_RawField values are fpreal32, hence `float`; material labels are the
  * enum of HDK_Utilities.h:17 { SOLID = 0, LIQUID = 1, AIR = 2 } as int32; a face is valid where validFaces == 1
  * (HDK_Utilities.h:21).  rhs / solution are the EXPANDED fp64 grids of the solve (expRes, offset from gmg_expand_dims). */
+/* buildMaterialCellLabels, HDK_Utilities.cpp:87-148 (isCellLiquid :5-45): SOLID where none of a cell's six cut-cell weights is > 0;
+ * else LIQUID where the surface value is <= 0, or the solid sample is >= 0 and an open face leads to a cell whose surface value
+ * is <= 0; else AIR.  solidSurface: the solid SDF sampled at the surface field's cell centres (solidSurface.getValue(pos),
+ * HDK_Utilities.cpp:22-24; the HDK interpolation stays with the caller -- for an aligned collision field it is the field). */
+int gmg_build_material_labels(gmg_ctx *ctx, const float *liquidSurface, const float *solidSurface, const float *const cutCell[3],
+			      const int64_t res[3], int32_t *material);
+/* buildValidFaces, GFS.cpp:717-744 (classifyValidFaces, HDK_Utilities.h:137-189), one axis: 1 where the cut-cell weight is > 0 and one
+ * of the face's two (in-range) cells is LIQUID, 0 elsewhere */
+int gmg_build_valid_faces(gmg_ctx *ctx, const int32_t *material, const float *cutCell, const int64_t res[3], int axis, float *validFaces);
 /* buildMGDomainLabels, GFS.cpp:746-793: LIQUID -> INTERIOR, AIR -> DIRICHLET, else EXTERIOR */
 int gmg_build_domain_labels(gmg_ctx *ctx, const int32_t *material, const int64_t res[3], int32_t *labels);
 /* buildMGBoundaryWeights, GFS.cpp:796-865, one axis: the cut-cell weight on valid faces, divided by the clamped ghost-fluid

@@ -330,6 +330,21 @@ class PortLib(_Base):
         keep = [self._f32(f) for f in fields]
         return keep, (C.POINTER(C.c_float) * 3)(*[k[1] for k in keep])
 
+    def build_material_labels(self, liquid_surface, solid_at_centres, cut_cell):
+        ls, lsp = self._f32(liquid_surface)
+        so, sop = self._f32(solid_at_centres)
+        kc, cp = self._ptrs3(cut_cell)
+        out = np.empty(ls.shape, dtype=np.int32)
+        self.fn("build_material_labels", None)(lsp, sop, cp, _res(ls), out.ctypes.data_as(_i32p))
+        return out
+
+    def build_valid_faces(self, material, cut_cell, axis):
+        m, mp = _i32(material)
+        cc, ccp = self._f32(cut_cell)
+        out = np.empty(cc.shape, dtype=np.float32)
+        self.fn("build_valid_faces", None)(mp, ccp, _res(m), int(axis), out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out
+
     def build_domain_labels(self, material):
         m, mp = _i32(material)
         out = np.empty(m.shape, dtype=np.int32)

@@ -968,6 +968,77 @@ static inline double ghost_fluid_weight(double phi0, double phi1)
 }
 static inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+/* HDK_Utilities.cpp:5-45 isCellLiquid.  solidAtCentres = solidSurface.getValue(indexToPos(cell)) (:21-24): the solid SDF sampled at
+ * the surface field's cell centres -- an HDK interpolation that is not restated; the caller supplies the samples. */
+static int is_cell_liquid(const float *liquidSurface, const float *solidAtCentres, const float *const cutCell[3], const i64 res[3], i64 x, i64 y, i64 z)
+{
+    if (liquidSurface[lin(res, x, y, z)] <= 0.) return 1;
+    if (solidAtCentres[lin(res, x, y, z)] >= 0)
+    {
+	for (int axis = 0; axis < 3; ++axis)
+	    for (int direction = 0; direction < 2; ++direction)
+	    {
+		i64 fr[3] = {res[0], res[1], res[2]};
+		++fr[axis];
+		i64 fc[3] = {x, y, z};
+		fc[axis] += direction;  /* cellToFaceMap */
+		if (cutCell[axis][lin(fr, fc[0], fc[1], fc[2])] > 0)
+		{
+		    i64 ac[3] = {x, y, z};
+		    ac[axis] += direction == 0 ? -1 : 1;  /* cellToCellMap */
+		    if (ac[axis] < 0 || ac[axis] >= res[axis]) continue;
+		    if (liquidSurface[lin(res, ac[0], ac[1], ac[2])] <= 0) return 1;
+		}
+	    }
+    }
+    return 0;
+}
+
+/* HDK_Utilities.cpp:87-148 buildMaterialCellLabels: SOLID_CELL everywhere (:99), then every cell with an open face (a cut-cell
+ * weight > 0 on one of its six faces, :122-133) becomes LIQUID_CELL or AIR_CELL by isCellLiquid (:135-141) */
+void orc_build_material_labels(const float *liquidSurface, const float *solidAtCentres, const float *const cutCell[3], const i64 res[3], int *material)
+{
+    for (i64 z = 0; z < res[2]; ++z)
+	for (i64 y = 0; y < res[1]; ++y)
+	    for (i64 x = 0; x < res[0]; ++x)
+	    {
+		int isInFluid = 0;
+		for (int axis = 0; axis < 3; ++axis)
+		    for (int direction = 0; direction < 2; ++direction)
+		    {
+			i64 fr[3] = {res[0], res[1], res[2]};
+			++fr[axis];
+			i64 fc[3] = {x, y, z};
+			fc[axis] += direction;
+			if (cutCell[axis][lin(fr, fc[0], fc[1], fc[2])] > 0) isInFluid = 1;
+		    }
+		int label = MAT_SOLID;
+		if (isInFluid) label = is_cell_liquid(liquidSurface, solidAtCentres, cutCell, res, x, y, z) ? MAT_LIQUID : MAT_AIR;
+		material[lin(res, x, y, z)] = label;
+	    }
+}
+
+/* GFS.cpp:717-744 buildValidFaces for one axis: INVALID_FACE everywhere (:724), then classifyValidFaces (HDK_Utilities.h:137-189):
+ * VALID_FACE where the cut-cell weight is > 0 (:173), both cells of the face are in range (:180) and one of them is LIQUID (:182-183).
+ * (The tile bookkeeping in between, findOccupiedFaceTiles / uncompressTiles, only uncompresses the tiles that can hold such a face.) */
+void orc_build_valid_faces(const int *material, const float *cutCell, const i64 res[3], int axis, float *validFaces)
+{
+    i64 fr[3] = {res[0], res[1], res[2]};
+    ++fr[axis];
+    for (i64 z = 0; z < fr[2]; ++z)
+	for (i64 y = 0; y < fr[1]; ++y)
+	    for (i64 x = 0; x < fr[0]; ++x)
+	    {
+		const i64 f = lin(fr, x, y, z);
+		validFaces[f] = 0.f;
+		if (!(cutCell[f] > 0)) continue;
+		i64 b[3] = {x, y, z}, fw[3] = {x, y, z};
+		--b[axis];  /* faceToCellMap(face, axis, 0) */
+		if (b[axis] >= 0 && fw[axis] < res[axis])
+		    if (material[lin(res, b[0], b[1], b[2])] == MAT_LIQUID || material[lin(res, fw[0], fw[1], fw[2])] == MAT_LIQUID) validFaces[f] = 1.f;
+	    }
+}
+
 /* GFS.cpp:746-793 buildMGDomainLabels: LIQUID -> INTERIOR, AIR -> DIRICHLET, everything else stays EXTERIOR (GFS.cpp:309) */
 void orc_build_domain_labels(const int *material, const i64 res[3], int *labels)
 {

@@ -1,4 +1,5 @@
-"""The steps either side of the solve: buildMGDomainLabels, buildMGBoundaryWeights, buildRHS, applyOldPressure,
+"""The steps either side of the solve: buildMaterialCellLabels (HDK_Utilities.cpp:87-148), buildValidFaces
+(HDK_GeometricFreeSurfacePressureSolver.cpp:717-744), buildMGDomainLabels, buildMGBoundaryWeights, buildRHS, applyOldPressure,
 applySolutionToPressure, applyPressureGradient (HDK_GeometricFreeSurfacePressureSolver.cpp:746-1131).
 
 PARITY UNPINNED at the reference: that file needs live SIM fields and cannot be compiled here.  What is checked:
@@ -45,6 +46,46 @@ def make_fields(n=24, seed=3):
         vel.append((rng.random(w.shape).astype(np.float32) - 0.5) * (w > 0))
     pressure = rng.random(material.shape).astype(np.float32)
     return material, phi, cut, valid, vel, pressure
+
+
+def make_solid_sdf(shape, seed=11):
+    """Solid samples at the cell centres with both signs, so that both branches of isCellLiquid (HDK_Utilities.cpp:24) are taken."""
+    rng = np.random.default_rng(seed)
+    return (rng.random(shape).astype(np.float32) - 0.5)
+
+
+def np_material_labels(phi, solid, cut):
+    wet = phi <= 0
+    in_fluid = np.zeros(phi.shape, dtype=bool)
+    through_open_face = np.zeros(phi.shape, dtype=bool)
+    for axis in range(3):
+        na = 2 - axis
+        n = phi.shape[na]
+        for direction in (0, 1):
+            sl = [slice(None)] * 3
+            sl[na] = slice(direction, direction + n)
+            open_face = cut[axis][tuple(sl)] > 0
+            in_fluid |= open_face
+            nb = np.zeros(phi.shape, dtype=bool)  # is the neighbour across that face in range and wet?
+            dst, src = [slice(None)] * 3, [slice(None)] * 3
+            if direction == 0:
+                dst[na], src[na] = slice(1, n), slice(0, n - 1)
+            else:
+                dst[na], src[na] = slice(0, n - 1), slice(1, n)
+            nb[tuple(dst)] = wet[tuple(src)]
+            through_open_face |= open_face & nb
+    liquid = wet | ((solid >= 0) & through_open_face)
+    return np.where(in_fluid, np.where(liquid, LIQUID, AIR), SOLID).astype(np.int32)
+
+
+def np_valid_faces(material, cut, axis):
+    na = 2 - axis
+    n = material.shape[na]
+    out = np.zeros(cut.shape, dtype=np.float32)
+    face, back, fwd = [slice(None)] * 3, [slice(None)] * 3, [slice(None)] * 3
+    face[na], back[na], fwd[na] = slice(1, n), slice(0, n - 1), slice(1, n)
+    out[tuple(face)] = ((material[tuple(back)] == LIQUID) | (material[tuple(fwd)] == LIQUID)) & (cut[tuple(face)] > 0)
+    return out
 
 
 def np_domain_labels(material):
@@ -115,6 +156,32 @@ def test_oracle_restatement_against_numpy(port):
     assert (p2 == np.where(material == LIQUID, pressure, np.float32(-1.0))).all()
 
 
+def test_oracle_material_labels_and_valid_faces_against_numpy(port):
+    material, phi, cut, valid, vel, pressure = make_fields()
+    # a solid sample < 0 everywhere: only the surface value decides, which is how make_fields labelled the tank
+    dry = np.full(phi.shape, -1.0, dtype=np.float32)
+    assert (port.build_material_labels(phi, dry, cut) == material).all()
+    for solid in (dry, make_solid_sdf(phi.shape), np.zeros(phi.shape, np.float32)):
+        m = port.build_material_labels(phi, solid, cut)
+        assert (m == np_material_labels(phi, solid, cut)).all()
+        for axis in range(3):
+            v = port.build_valid_faces(m, cut[axis], axis)
+            assert v.dtype == np.float32 and (v == np_valid_faces(m, cut[axis], axis)).all()
+    assert (np_material_labels(phi, make_solid_sdf(phi.shape), cut) != material).any()  # the second branch of isCellLiquid was taken
+    for axis in range(3):
+        assert (port.build_valid_faces(material, cut[axis], axis) == valid[axis]).all()
+    # open faces on the outer border of the grid are never valid (HDK_Utilities.h:180) and do not reach outside (HDK_Utilities.cpp:35)
+    cut_open = [np.ones_like(c) for c in cut]
+    m = port.build_material_labels(phi, dry, cut_open)
+    assert (m == np.where(phi <= 0, LIQUID, AIR)).all()
+    for axis in range(3):
+        v = port.build_valid_faces(m, cut_open[axis], axis)
+        assert (v == np_valid_faces(m, cut_open[axis], axis)).all()
+        edge = [slice(None)] * 3
+        edge[2 - axis] = 0
+        assert not v[tuple(edge)].any()
+
+
 def test_projection_chain_on_the_oracle(port):
     """The restated builders wired as GFS.cpp:296-660 wires them, around the oracle's MGPCG: the cut-cell divergence of every liquid
     cell drops by seven orders of magnitude (what the fpreal32 pressure / velocity fields allow) -- the node's own check,
@@ -131,6 +198,31 @@ def test_projection_chain_on_the_oracle(port):
     nv = [port.apply_pressure_gradient(vel[a], phi, p, valid[a], material, a) for a in range(3)]
     after = np.abs(port.build_rhs(material, nv, cut, labels.shape, off)).max()
     assert after < 1e-5 * np.abs(rhs).max()
+
+
+@pytest.mark.gpu
+def test_material_labels_and_valid_faces_match_the_restatement(gpu_ctx, port):
+    material, phi, cut, valid, vel, pressure = make_fields(32, 5)
+    dry = np.full(phi.shape, -1.0, dtype=np.float32)
+    assert (gpu_ctx.buildMaterialCellLabels(phi, dry, cut) == material).all()
+    for solid, cc in ((dry, cut), (make_solid_sdf(phi.shape), cut), (np.zeros(phi.shape, np.float32), [np.ones_like(c) for c in cut])):
+        mg = gpu_ctx.buildMaterialCellLabels(phi, solid, cc)
+        assert mg.dtype == np.int32 and (mg == port.build_material_labels(phi, solid, cc)).all()
+        for axis in range(3):
+            vg = gpu_ctx.buildValidFaces(mg, cc[axis], axis)
+            assert vg.dtype == np.float32 and (vg == port.build_valid_faces(mg, cc[axis], axis)).all()
+    for axis in range(3):
+        assert (gpu_ctx.buildValidFaces(material, cut[axis], axis) == valid[axis]).all()
+    # an elongated grid: the three strides differ
+    rng = np.random.default_rng(2)
+    shape = (10, 14, 22)
+    phi2 = rng.random(shape).astype(np.float32) - 0.5
+    cut2 = [(rng.random(D.face_shape(shape, a)) < 0.7).astype(np.float32) * rng.random(D.face_shape(shape, a)).astype(np.float32) for a in range(3)]
+    solid2 = make_solid_sdf(shape, 4)
+    m2 = gpu_ctx.buildMaterialCellLabels(phi2, solid2, cut2)
+    assert (m2 == port.build_material_labels(phi2, solid2, cut2)).all() and (m2 == np_material_labels(phi2, solid2, cut2)).all()
+    for axis in range(3):
+        assert (gpu_ctx.buildValidFaces(m2, cut2[axis], axis) == np_valid_faces(m2, cut2[axis], axis)).all()
 
 
 @pytest.mark.gpu
@@ -167,8 +259,10 @@ def test_projection_chain_leaves_the_liquid_divergence_free(gpu_ctx):
     from geometricmultigridpressuresolver_b200 import api
 
     n = 32
-    material, phi, cut, valid, vel, _ = make_fields(n, 9)
+    _, phi, cut, _, vel, _ = make_fields(n, 9)
     cut = [np.where(c > 0, 1.0, 0.0).astype(np.float32) for c in cut]  # open / closed faces only
+    material = gpu_ctx.buildMaterialCellLabels(phi, np.full(phi.shape, -1.0, np.float32), cut)
+    valid = [gpu_ctx.buildValidFaces(material, cut[a], a) for a in range(3)]
     base_labels = gpu_ctx.buildMGDomainLabels(material)
     base_w = [gpu_ctx.buildMGBoundaryWeights(cut[a], phi, valid[a], base_labels, a) for a in range(3)]
     labels, w, off, levels = gpu_ctx.buildExpandedDomain(base_labels, base_w)
