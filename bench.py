@@ -7,8 +7,8 @@ A step is one complete multigrid-preconditioned CG solve of the 256^3 flipSplash
 (BASELINE.json configs[2]; expanded 512^3, 7 levels, seeded random rhs, zero initial guess, tol 1e-6).
   value      solve ms with labels/weights/rhs already resident in HBM (gmg_pcg_device), CUDA events on the library's stream
   e2e        the same solve through the reference-facing entry points with HOST buffers:
-             gmg_solver_create (labels + BOUNDARY-cell face weights H2D, hierarchy build) + gmg_pcg (rhs/x0 H2D from pinned memory,
-             pressure D2H) + gmg_solver_destroy -- wall clock around the blocking calls
+             gmg_solver_create (labels + BOUNDARY-cell face weights H2D, hierarchy build) + gmg_pcg_from_zero (rhs H2D from pinned memory;
+             the zero initial guess is declared, not sent; pressure D2H) + gmg_solver_destroy -- wall clock around the blocking calls
   roofline   the dominant fine-level kernel class: algorithmic bytes per launch / CUDA-event duration per launch,
              against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  the reference's own sources (oracle/_ref, compiled unmodified against the HDK/Eigen shim) -- or the plain-C
@@ -681,7 +681,9 @@ def run_gpu_arm(args, rank, world, local_rank):
             t0 = time.perf_counter()
             s2 = api.GeometricMultigridPoissonSolver(ctx, labels, w, levels, box=box)
             t1 = time.perf_counter()
-            x_out, it2, hist2 = s2.solveGeometricConjugateGradient(x_np, b_np, TOL, MAX_IT, inplace=True)
+            # no warm start: the solution grid is the constant zero of GFS.cpp:392-398 and is declared so (gmg_pcg_from_zero), like the
+            # facade does for a constant-compressed UT_VoxelArray; the pressure is written into the same page-locked array
+            x_out, it2, hist2 = s2.solveGeometricConjugateGradient(x_np, b_np, TOL, MAX_IT, inplace=True, solutionIsZero=True)
             s2.close()
             t2 = time.perf_counter()
             if step > 0:
@@ -689,10 +691,10 @@ def run_gpu_arm(args, rank, world, local_rank):
                 e2e_setup.append((t1 - t0) * 1e3)
         box_cells = int(np.prod([hi[a] - int(off[a]) + 4 for a in range(3)]))
         # construction: int32 labels of the box + the six face weights of every BOUNDARY cell (the weight grids themselves stay on the
-        # host: only BOUNDARY cells look at them; their index list comes back first); per solve: rhs + x0 in, pressure out
+        # host: only BOUNDARY cells look at them; their index list comes back first); per solve: rhs in (x0 = 0 is declared, not sent), pressure out
         n_boundary = int((labels == 3).sum())
-        io_cells, io_copies = solver.transfer_cells()  # rhs / x0 / pressure move the active rectangles of each z-plane only
-        h2d = box_cells * 4 + n_boundary * 48 + 2 * io_cells * 8
+        io_cells, io_copies = solver.transfer_cells()  # rhs / pressure move the active rectangles of each z-plane only
+        h2d = box_cells * 4 + n_boundary * 48 + io_cells * 8
         d2h = io_cells * 8 + n_boundary * 4
         e2e_val = float(np.mean(e2e_ms))
         if dist is not None:
@@ -700,16 +702,16 @@ def run_gpu_arm(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_val = float(t.item())
             sh, zlo, zhi, _ = solver.shard_info(0)
-            if sh:  # per rank: its slab of the weights / rhs / x0 (+ the replicated one-byte labels); summed over the ranks below
+            if sh:  # per rank: its slab of the weights / rhs (+ the replicated one-byte labels); summed over the ranks below
                 frac = (zhi - zlo + 20) / float(hi[2] - int(off[2]) + 4)
-                h2d = int(box_cells * 4 + n_boundary * frac * 48 + io_cells * 2 * 8)
+                h2d = int(box_cells * 4 + n_boundary * frac * 48 + io_cells * 8)
                 d2h = int(io_cells * 8 * (zhi - zlo) / float(zhi - zlo + 20))
             t = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64)
             dist.all_reduce(t)
             h2d, d2h = int(t[0].item()), int(t[1].item())
         e2e = {"value": e2e_val, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "setup_ms": float(np.mean(e2e_setup)), "iterations": int(it2),
-               "what": "gmg_solver_create (labels + BOUNDARY-cell face weights H2D, hierarchy build) + gmg_pcg (rhs/x0 H2D, pressure D2H) + gmg_solver_destroy; all host buffers page-locked"}
+               "what": "gmg_solver_create (labels + BOUNDARY-cell face weights H2D, hierarchy build) + gmg_pcg_from_zero (rhs H2D, x0 = 0 declared by the caller, pressure D2H) + gmg_solver_destroy; all host buffers page-locked"}
         for a in [x_np, b_np, labels] + list(w):
             rt.cudaHostUnregister(a.ctypes.data)
 

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "gmg_expand_dims", "gmg_expand_labels", "gmg_expand_weights", "gmg_set_boundary_labels", "gmg_coarsen_labels", "gmg_boundary_cells",
     "gmg_solver_default_options", "gmg_solver_create", "gmg_solver_create_u8", "gmg_solver_destroy", "gmg_solver_levels", "gmg_solver_level_res",
     "gmg_solver_get_labels", "gmg_solver_get_boundary_cells", "gmg_solver_active_cells", "gmg_solver_coarse_unknowns", "gmg_solver_setup_ms", "gmg_solver_transfer_cells", "gmg_transfer_plan", "gmg_gather_face_weights",
-    "gmg_vcycle", "gmg_pcg", "gmg_grid_create", "gmg_grid_destroy", "gmg_grid_upload", "gmg_grid_download", "gmg_grid_zero", "gmg_grid_copy",
+    "gmg_vcycle", "gmg_pcg", "gmg_pcg_from_zero", "gmg_grid_create", "gmg_grid_destroy", "gmg_grid_upload", "gmg_grid_download", "gmg_grid_zero", "gmg_grid_copy",
     "gmg_jacobi", "gmg_gauss_seidel", "gmg_boundary_jacobi", "gmg_apply", "gmg_residual", "gmg_restrict", "gmg_prolong_add", "gmg_dot", "gmg_norm2", "gmg_inf_norm",
     "gmg_axpy", "gmg_add_scaled", "gmg_scale", "gmg_vcycle_device", "gmg_pcg_device", "gmg_launch_count", "gmg_timer_begin", "gmg_timer_end",
     "gmg_build_material_labels", "gmg_build_valid_faces", "gmg_build_domain_labels", "gmg_build_boundary_weights", "gmg_build_rhs", "gmg_apply_old_pressure", "gmg_apply_solution_to_pressure", "gmg_apply_pressure_gradient",
@@ -561,17 +561,24 @@ class GeometricMultigridPoissonSolver:
         return int(useMGPreconditioner)
 
     def solveGeometricConjugateGradient(self, solutionGrid, rhsGrid, tolerance, maxIterations, useMGPreconditioner=True,
-                                        inplace: bool = False):
+                                        inplace: bool = False, solutionIsZero: bool = False):
         """CG.h:11-207 with A = applyPoissonMatrix, M^-1 = applyVCycle (GFS.cpp:430-483) or the diagonal preconditioner
         (GFS.cpp:485-618, useMGPreconditioner="diagonal").
         Returns (solution, iterations printed by CG.h:198 or -1 on an early-out, relative-residual history).
-        inplace=True writes the pressure into solutionGrid itself (as the reference does) instead of a copy."""
-        x, xp = _f64(solutionGrid if inplace else np.array(solutionGrid, copy=True))
+        inplace=True writes the pressure into solutionGrid itself (as the reference does) instead of a copy.
+        solutionIsZero=True: the caller declares solutionGrid constant zero on entry (the node's solutionGrid.constant(0) without a warm
+        start, GFS.cpp:392-398; solutionGrid may then be None): it is not uploaded (gmg_pcg_from_zero)."""
         b, bp = _f64(rhsGrid)
+        if solutionGrid is None:
+            if not solutionIsZero:
+                raise ValueError("solutionGrid is None without solutionIsZero")
+            solutionGrid, inplace = np.zeros(b.shape, dtype=np.float64), True
+        x, xp = _f64(solutionGrid if inplace else np.array(solutionGrid, copy=True))
         hist = np.zeros(int(maxIterations) + 2, dtype=np.float64)
         it, cnt = C.c_int(), C.c_int()
-        _check(self.lib.gmg_pcg(self.h, xp, bp, C.c_double(tolerance), int(maxIterations), self._precond(useMGPreconditioner), C.byref(it),
-                                hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt)))
+        fn = self.lib.gmg_pcg_from_zero if solutionIsZero else self.lib.gmg_pcg
+        _check(fn(self.h, xp, bp, C.c_double(tolerance), int(maxIterations), self._precond(useMGPreconditioner), C.byref(it),
+                  hist.ctypes.data_as(_f64p), len(hist), C.byref(cnt)))
         return x, int(it.value), hist[: cnt.value].copy()
 
     # ---- device-resident operators ----------------------------------------------------------------

@@ -4775,18 +4775,33 @@ extern "C" int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInit
     return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, !useInitialGuess, s->hostBounds, &s->ioGroups, s->lv[0].ownLo);
 }
 
-extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations, double *relResHistory,
-		       int histCap, int *histCount)
+static int pcgHost(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations, double *relResHistory, int histCap,
+		   int *histCount, bool fromZero)
 {
     if (!s || !x || !b) return invalid("gmg_pcg: null argument");
     GMG_CUDA(enterCtx(s->ctx));
     GMG_TRY(ensureHostIO(s));
     const Geom &g = s->lv[0].g;
-    GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels, s->hostBounds, &s->ioGroups));
+    // fromZero: the caller declares x == 0 on entry (the node's solutionGrid.constant(0) without a warm start, GFS.cpp:392-398): nothing of
+    // it crosses PCIe, the device grid is cleared instead; the arithmetic is the same (r = b - A 0)
+    if (fromZero) GMG_CUDA(cudaMemsetAsync(s->pcgX, 0, sizeof(double) * g.total, s->ctx->stream));
+    else GMG_TRY(uploadValues(s->ctx, s->pcgX, x, g.res, g, s->lv[0].labels, s->hostBounds, &s->ioGroups));
     GMG_TRY(uploadValues(s->ctx, s->pcgB, b, g.res, g, s->lv[0].labels, s->hostBounds, &s->ioGroups));
     GMG_TRY(pcgDevice(s, s->pcgX, s->pcgB, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount));
     const Geom go = ownedGeom(s->lv[0]);
     return downloadValues(s->ctx, x, s->pcgX + int64_t(s->lv[0].ownLo) * g.plane, g.res, go, false, s->hostBounds, &s->ioGroups, s->lv[0].ownLo);
+}
+
+extern "C" int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations, double *relResHistory,
+		       int histCap, int *histCount)
+{
+    return pcgHost(s, x, b, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount, false);
+}
+
+extern "C" int gmg_pcg_from_zero(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations, double *relResHistory,
+				 int histCap, int *histCount)
+{
+    return pcgHost(s, x, b, tol, maxIt, preconditioner, iterations, relResHistory, histCap, histCount, true);
 }
 
 

@@ -1537,11 +1537,11 @@ __global__ void __launch_bounds__(BLOCK, 2) k_gauss_seidel2(const GsArgs2 p)
     unsigned short *poolCode = reinterpret_cast<unsigned short *>(poolDiag + GS_POOL);  // [GS_POOL]
     unsigned short *slot = poolCode + GS_POOL;                            // [16][16][16] pool slot of a BOUNDARY cell
     uint8_t *ls = reinterpret_cast<uint8_t *>(slot + GS_TILE * GS_TILE * GS_TILE);      // [16][16][16]
-    __shared__ int poolCount;
+    __shared__ int poolCount, frontLo, frontHi;
     const int t = a.tiles[blockIdx.x];
     const int tz = t / (a.tilesX * a.tilesY), ty = (t - tz * a.tilesX * a.tilesY) / a.tilesX, tx = t - (tz * a.tilesY + ty) * a.tilesX;
     const int ox = a.off[0] + tx * GS_TILE, oy = a.off[1] + ty * GS_TILE, oz = a.off[2] + tz * GS_TILE;
-    if (threadIdx.x == 0) poolCount = 0;
+    if (threadIdx.x == 0) { poolCount = 0; frontLo = 3 * GS_TILE; frontHi = -1; }
     __syncthreads();
     // A thread owns the column (lx, ly) of the tile: cell i = q * 256 + tid is (lx, ly, lz = q).  Every phase below issues the
     // column's 16 loads TOGETHER (unrolled, predicated) -- the first version walked them one dependent round trip at a time
@@ -1561,6 +1561,25 @@ __global__ void __launch_bounds__(BLOCK, 2) k_gauss_seidel2(const GsArgs2 p)
     int bp[GS_TILE];
 #pragma unroll
     for (int q = 0; q < GS_TILE; ++q) bp[q] = lab[q] == L_BOUNDARY ? a.bpos[g0 + int64_t(q) * a.plane] : -1;
+    {
+	// the wavefronts lx + ly + lz = s that hold an active cell of this tile: a front without one changes nothing, so the sweep
+	// below only walks [frontLo, frontHi] (a tile of a coarse level is mostly EXTERIOR: 22 of the 46 fronts at 8^3 active cells)
+	int lo = 3 * GS_TILE, hi = -1;
+#pragma unroll
+	for (int q = 0; q < GS_TILE; ++q)
+	    if (lab[q] == L_INTERIOR || lab[q] == L_BOUNDARY)
+	    {
+		lo = min(lo, lx + ly + q);
+		hi = max(hi, lx + ly + q);
+	    }
+	lo = __reduce_min_sync(0xffffffffu, lo);
+	hi = __reduce_max_sync(0xffffffffu, hi);
+	if ((threadIdx.x & 31) == 0 && hi >= 0)
+	{
+	    atomicMin(&frontLo, lo);
+	    atomicMax(&frontHi, hi);
+	}
+    }
     double dg[GS_TILE];
     unsigned short cd[GS_TILE];
 #pragma unroll
@@ -1615,9 +1634,10 @@ __global__ void __launch_bounds__(BLOCK, 2) k_gauss_seidel2(const GsArgs2 p)
 	for (int q = 0; q < GS_TILE; ++q) bs[q * BLOCK + threadIdx.x] = bv[q];
     }
     __syncthreads();
-    for (int step = 0; step <= 3 * (GS_TILE - 1); ++step)
+    const int firstFront = frontLo, lastFront = frontHi;
+    for (int step = 0; step <= lastFront - firstFront; ++step)
     {
-	const int sfront = a.forward ? step : 3 * (GS_TILE - 1) - step;
+	const int sfront = a.forward ? firstFront + step : lastFront - step;
 	const int lz = sfront - lx - ly;
 	if (lz >= 0 && lz < GS_TILE)
 	{

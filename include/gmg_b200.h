@@ -169,6 +169,11 @@ int gmg_vcycle(gmg_solver *s, double *x, const double *b, int useInitialGuess);
  * The loop itself runs on the device (a WHILE node around the captured iteration): one host synchronisation per solve. */
 int gmg_pcg(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations,
 	    double *relResHistory, int histCap, int *histCount);
+/* The same solve with the initial guess DECLARED zero by the caller -- the node's solutionGrid.constant(0) without a warm start
+ * (HDK_GeometricFreeSurfacePressureSolver.cpp:392-398; a constant UT_VoxelArray says so in O(tiles)).  x is output only: it is
+ * neither read nor uploaded, the device grid is cleared instead; same arithmetic (r = b - A 0), same results as gmg_pcg on zeros. */
+int gmg_pcg_from_zero(gmg_solver *s, double *x, const double *b, double tol, int maxIt, int preconditioner, int *iterations,
+		      double *relResHistory, int histCap, int *histCount);
 
 /* ---- device-resident grids and single operators (what the facade's operator functions call) ----------- */
 int gmg_grid_create(gmg_solver *s, int level, gmg_grid **out); /* zero-filled */

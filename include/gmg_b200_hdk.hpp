@@ -715,7 +715,9 @@ public:
     int solve(UT_VoxelArray<StoreReal> &solutionGrid, const UT_VoxelArray<StoreReal> &rhsGrid, StoreReal tolerance, int maxIterations,
 	      bool useMGPreconditioner = true, std::vector<double> *relativeResidualHistory = nullptr)
     {
-	auto b = myDomain->upload(rhsGrid), x = myDomain->upload(solutionGrid);
+	// a solution grid that is still the constant zero of solutionGrid.constant(0) (GFS.cpp:392-398: no warm start) says so in O(tiles):
+	// it is neither flattened nor uploaded
+	auto b = myDomain->upload(rhsGrid), x = isConstantZero(solutionGrid) ? myDomain->zeros() : myDomain->upload(solutionGrid);
 	std::vector<double> hist(size_t(maxIterations) + 2);
 	int iterations = -1, count = 0;
 	B200::check(gmg_pcg_device(myDomain->solver, x.g, b.g, tolerance, maxIterations, useMGPreconditioner, &iterations, hist.data(), int(hist.size()), &count),
@@ -731,6 +733,17 @@ public:
 	return iterations;
     }
     GeometricMultigridOperators::DeviceDomain &domain() { return *myDomain; }
+
+    // every tile constant-compressed with the value 0 (UT_VoxelTile::isConstant / operator()): what constant(0) leaves behind
+    static bool isConstantZero(const UT_VoxelArray<StoreReal> &v)
+    {
+	for (int i = 0, n = v.numTiles(); i < n; ++i)
+	{
+	    const auto *tile = v.getLinearTile(i);
+	    if (!tile->isConstant() || (*tile)(0, 0, 0) != StoreReal(0)) return false;
+	}
+	return true;
+    }
 
 private:
     std::unique_ptr<GeometricMultigridOperators::DeviceDomain> myDomain;

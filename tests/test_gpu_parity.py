@@ -216,6 +216,27 @@ def test_early_outs_and_errors(gpu_ctx):
     s.close()
 
 
+def test_pcg_from_zero_equals_pcg_on_a_zero_grid(gpu_ctx):
+    """gmg_pcg_from_zero (the caller declares the solution grid constant zero: nothing of it is uploaded) against gmg_pcg on an explicit
+    zero array: bitwise the same pressure, history and iteration count; the output array's content on entry does not matter."""
+    bl, bw, dx = D.flipsplash_domain(32)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    b = D.random_rhs(labels, dx)
+    x1, it1, h1 = s.solveGeometricConjugateGradient(np.zeros(labels.shape), b, 1e-8, 200)
+    x2, it2, h2 = s.solveGeometricConjugateGradient(None, b, 1e-8, 200, solutionIsZero=True)
+    assert it1 == it2 and (h1 == h2).all() and (x1 == x2).all()
+    for pre in ("diagonal", False):
+        y1, j1, g1 = s.solveGeometricConjugateGradient(np.zeros(labels.shape), b, 1e-4, 50, useMGPreconditioner=pre)
+        y2, j2, g2 = s.solveGeometricConjugateGradient(None, b, 1e-4, 50, useMGPreconditioner=pre, solutionIsZero=True)
+        assert j1 == j2 and (g1 == g2).all() and (y1 == y2).all()
+    x3, it3, h3 = s.solveGeometricConjugateGradient(np.zeros(labels.shape), np.zeros(labels.shape), 1e-6, 10, inplace=True, solutionIsZero=True)
+    assert it3 == -1 and not x3.any()  # "RHS is zero" (CG.h:35-40)
+    with pytest.raises(ValueError):
+        s.solveGeometricConjugateGradient(None, b, 1e-8, 200)
+    s.close()
+
+
 def test_diagonal_free_plain_cg_matches_oracle_operators(gpu_ctx, port):
     """preconditioner = 0 runs plain CG on the same kernels; cross-check with numpy CG over oracle operators."""
     bl, bw, dx = D.complex_domain(24)
