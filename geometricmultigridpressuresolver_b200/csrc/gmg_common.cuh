@@ -138,6 +138,7 @@ struct ProfileRec
     int level;
     double bytes;
     cudaEvent_t e0, e1;
+    int n;  // launches inside the bracket (1, or the sweeps of a band sweep group in profiling mode 2)
 };
 
 } // namespace gmg
@@ -150,6 +151,9 @@ struct gmg_ctx
     bool ownStream = false;
     int64_t launches = 0;
     bool profiling = false;
+    bool profileGroups = false;   // gmg_profile_enable(ctx, 2): ONE event pair around the back-to-back sweeps of a band sweep group instead of one per
+				  // sweep -- the event-record nodes cost ~5 us per bracket and break the prologue overlap between the launches they separate
+    bool scopeMuted = false;      // inside such a group bracket: the launches' own brackets only count
     bool capturing = false;       // inside a stream capture: profiling events become external event-record nodes
     std::vector<gmg::ProfileRec> recs;
     std::vector<cudaEvent_t> eventPool;
@@ -288,7 +292,10 @@ struct LaunchScope
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int klass;
     double bytes;
-    LaunchScope(gmg_ctx *c, int k, double b);
+    int n;       // launches this bracket stands for; 0 = a group bracket that was not opened (profiling mode != 2)
+    bool group;  // a group bracket: does not count as a launch itself, mutes the brackets of the launches inside it
+    bool live = false;
+    LaunchScope(gmg_ctx *c, int k, double b, int launches = 1, bool isGroup = false);
     ~LaunchScope();
 };
 #define GMG_LAUNCH(ctx, klass, bytes) gmg::LaunchScope _scope_##__LINE__(ctx, klass, bytes)

@@ -261,7 +261,10 @@ int gmg_timer_begin(gmg_ctx *ctx);
 int gmg_timer_end(gmg_ctx *ctx, double *ms);
 /* accumulated device time (ms) and launches per kernel class since the last reset; classes are listed by
  * gmg_kernel_class_name(i), i in [0, gmg_kernel_class_count()).  Only collected when enabled (adds events).
- * fineLevelOnly != 0 restricts the sums to launches on level 0, where the HBM roofline is quoted. */
+ * fineLevelOnly != 0 restricts the sums to launches on level 0, where the HBM roofline is quoted.
+ * on = 1: one event pair per launch.  on = 2: the same, except that the back-to-back sweeps of a band sweep group share ONE pair
+ * (counted as that many launches): an event-record node costs ~5 us and keeps the launches it separates from overlapping, which
+ * overstates a 10 us kernel by half. */
 int gmg_profile_enable(gmg_ctx *ctx, int on);
 int gmg_kernel_class_count(void);
 const char *gmg_kernel_class_name(int i);

@@ -237,6 +237,32 @@ def test_pcg_from_zero_equals_pcg_on_a_zero_grid(gpu_ctx):
     s.close()
 
 
+def test_profile_group_brackets_count_the_same_launches(gpu_ctx):
+    """gmg_profile_enable(ctx, 2) puts one event pair around a band sweep group instead of one per sweep: same launches, same
+    algorithmic bytes, same result as mode 1; the brackets are fewer, so the class cannot take longer than with a pair per launch."""
+    bl, bw, dx = D.flipsplash_domain(48)
+    labels, w, off, levels = gpu_ctx.buildExpandedDomain(bl, bw)
+    s = api.GeometricMultigridPoissonSolver(gpu_ctx, labels, w, levels)
+    b = D.random_rhs(labels, dx)
+    B = s.grid(0, b)
+    prof, sol = {}, {}
+    for mode in (1, 2):
+        X = s.grid(0)
+        s.solveDevice(X, B, 1e-6, 100)  # captures the profiled graph of this mode
+        gpu_ctx.profile_enable(mode)
+        gpu_ctx.profile_reset()
+        X.zero()
+        it, hist = s.solveDevice(X, B, 1e-6, 100)[:2]
+        prof[mode] = gpu_ctx.profile(False)["band_jacobi"]
+        sol[mode] = (it, X.download())
+        gpu_ctx.profile_enable(False)
+    assert prof[1][1] == prof[2][1] > 0 and prof[1][2] == prof[2][2]
+    print("band_jacobi ms: a pair per launch", prof[1][0], "a pair per group", prof[2][0])
+    assert prof[2][0] < 1.05 * prof[1][0]
+    assert sol[1][0] == sol[2][0] and (sol[1][1] == sol[2][1]).all()
+    s.close()
+
+
 def test_diagonal_free_plain_cg_matches_oracle_operators(gpu_ctx, port):
     """preconditioner = 0 runs plain CG on the same kernels; cross-check with numpy CG over oracle operators."""
     bl, bw, dx = D.complex_domain(24)
