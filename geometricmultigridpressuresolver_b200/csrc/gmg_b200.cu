@@ -922,6 +922,9 @@ static int buildBand(gmg_ctx *ctx, Level &L, int width)
 	GMG_CUDA(devMalloc(&L.flagsAlloc, gg.total));
 	k_band_flag_grid<<<gridG, BLOCK, 0, ctx->stream>>>(L.flagsAlloc, m0, m1, gg.total);
 	L.bandFlags = L.flagsAlloc + int64_t(L.zOff) * g.plane;
+	GMG_CUDA(devMalloc(&L.nbrMaskAlloc, gg.total));
+	k_band_nbr_mask<<<gridG, BLOCK, 0, ctx->stream>>>(L.nbrMaskAlloc, m0, labelsG, bg);
+	L.nbrMask = L.nbrMaskAlloc + int64_t(L.zOff) * g.plane;
     }
     const uint8_t *mLocal = m0 + int64_t(L.zOff) * g.plane;
     int32_t *idxB = nullptr, *idxI = nullptr;
@@ -1423,7 +1426,7 @@ static int exportBand(gmg_ctx *ctx, const Level &L, int64_t *xyz, int64_t *count
 
 static void freeLevel(Level &L)
 {
-    devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab); devFree(L.flagsAlloc);
+    devFree(L.labelsAlloc ? L.labelsAlloc : L.labels); devFree(L.bandSlab); devFree(L.flagsAlloc); devFree(L.nbrMaskAlloc);
     delete static_cast<ClusterSmoothArgs *>(L.smoothArgs);
     devFree(L.smoothSlab);
     delete static_cast<BandTileArgs *>(L.tileArgs);
@@ -2274,6 +2277,7 @@ static int solverCreate(gmg_ctx *ctx, const LabelT *labels, const int64_t res[3]
     if (const char *e = getenv("GMG_BAND_GROUP_MAX")) s->bandGroupMax = atoll(e);
     if (const char *e = getenv("GMG_BAND_PER_THREAD")) s->bandPerThread = atoi(e);
     if (const char *e = getenv("GMG_STENCIL_CAP")) s->stencilCap = atoi(e);
+    if (const char *e = getenv("GMG_STENCIL_BATCH")) s->stencilBatch = atoi(e);
     if (const char *e = getenv("GMG_STENCIL_LOOP")) s->stencilLoop = atoi(e);
     if (s->opt.boundary_width < 1) s->opt.boundary_width = 3;
     if (s->opt.boundary_iterations < 0) s->opt.boundary_iterations = 3;
@@ -2513,7 +2517,7 @@ static StencilArgs stencilArgs(gmg_solver *s, int level, const double *in, const
     const Level &L = s->lv[level];
     StencilArgs a;
     a.labels = L.labels;
-    a.flags = L.bandFlags;
+    a.flags = L.nbrMask;
     a.in = in;
     a.b = b;
     a.out = out;
@@ -2580,7 +2584,7 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
 	GMG_CUDA(cudaGetLastError());
 	return GMG_OK;
     }
-    // stencilCap: bit 0 Jacobi, bit 1 residual, bit 2 apply -- the 40-register instantiation (6 resident CTAs per SM instead of 4)
+    // stencilCap: bit 0 Jacobi, bit 1 residual, bit 2 apply, bit 3 zero-aware Jacobi -- the 40-register instantiation (6 resident CTAs per SM instead of 4)
     if (s->stencilLoop)
     {
 	// persistent variant: what fits the device at once, every CTA walking its chunks with the next chunk's labels prefetched
@@ -2625,6 +2629,24 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
 	    return GMG_OK;
 	}
     }
+    if (s->stencilBatch == 2 || s->stencilBatch == 4)
+    {
+	// the loads of 2 / 4 planes in flight together (k_stencil_b)
+#define GMG_SB(M, D)                                                                                                                   \
+    do                                                                                                                                 \
+    {                                                                                                                                  \
+	if (s->stencilBatch == 4) GMG_CUDA(launchK((k_stencil_b<M, D, 4>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));         \
+	else GMG_CUDA(launchK((k_stencil_b<M, D, 2>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));                              \
+    } while (0)
+	if (mode == SM_JACOBI) { GMG_LAUNCH(s->ctx, KC_JACOBI, n * 25.0); GMG_SB(SM_JACOBI, false); }
+	else if (mode == SM_JACOBI_ZERO) { GMG_LAUNCH(s->ctx, KC_JACOBI, n * 18.0); GMG_SB(SM_JACOBI_ZERO, false); }
+	else if (mode == SM_RESIDUAL) { GMG_LAUNCH(s->ctx, KC_RESIDUAL, n * 25.0); GMG_SB(SM_RESIDUAL, false); }
+	else if (dotResult) { GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0); GMG_SB(SM_APPLY, true); }
+	else { GMG_LAUNCH(s->ctx, KC_APPLY, n * 17.0); GMG_SB(SM_APPLY, false); }
+#undef GMG_SB
+	GMG_CUDA(cudaGetLastError());
+	return GMG_OK;
+    }
     // measured at 256^3 (4.3 M cells, plain loads): apply 38.3 -> 32.3 us, residual 34.6 -> 31.5 us, Jacobi no gain (it spills);
     // on a 0.5 M-cell level everything loses 5-10 % -- so: residual + apply on levels of at least 2 M cells unless GMG_STENCIL_CAP says otherwise
     const int cap = s->stencilCap >= 0 ? s->stencilCap : (n >= 2.0e6 ? 6 : 0);
@@ -2638,7 +2660,8 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
     {
 	// x is zero off the band: its 8 bytes per cell are not read (one flag byte is), and no zero fill ran before
 	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 18.0);
-	GMG_CUDA(launchK((k_stencil<SM_JACOBI_ZERO, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	if (cap & 8) GMG_CUDA(launchK((k_stencil<SM_JACOBI_ZERO, false, double, 6>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	else GMG_CUDA(launchK((k_stencil<SM_JACOBI_ZERO, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     else if (mode == SM_RESIDUAL)
     {
@@ -4122,7 +4145,7 @@ static int launchStencil32(gmg_solver *s, int level, int mode, const float *in, 
     s->ctx->curLevel = level;
     const Level &L = s->lv[level];
     StencilArgsT<float> a;
-    a.labels = L.labels; a.flags = L.bandFlags; a.in = in; a.b = b; a.out = out;
+    a.labels = L.labels; a.flags = L.nbrMask; a.in = in; a.b = b; a.out = out;
     a.chunks = L.chunksInterior; a.nChunks = L.nChunksInterior; a.chunksPerPlane = L.g.chunksPerPlane;
     a.pitch = L.g.pitch; a.plane = L.g.plane; a.nz = L.g.n[2]; a.zlo = 0; a.zhi = L.g.n[2]; a.dotLo = 0; a.dotHi = L.g.n[2];
     a.nBoundary = L.nBoundary; a.bandIdx = L.bandIdx; a.bcoef = L.bcoef; a.wcode = L.wcode;

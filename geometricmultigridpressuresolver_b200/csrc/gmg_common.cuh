@@ -80,6 +80,8 @@ struct Level
     uint8_t *labels = nullptr;   // = labelsAlloc + zOff * plane
     uint8_t *flagsAlloc = nullptr;  // band flags over the GLOBAL box (gmg_kernels.cuh: SM_JACOBI_ZERO): bit0 in band, bit1 next to it
     uint8_t *bandFlags = nullptr;   // = flagsAlloc + zOff * plane
+    uint8_t *nbrMaskAlloc = nullptr;  // neighbour masks over the GLOBAL box (k_band_nbr_mask): what the zero-aware interior sweep reads
+    uint8_t *nbrMask = nullptr;       // = nbrMaskAlloc + zOff * plane
     int64_t nActive = 0, nInterior = 0; // over the local stored box
     int64_t nActiveGlobal = 0;
     // boundary band: [0,nBoundary) BOUNDARY cells, [nBoundary,nBand) INTERIOR cells of the band; linear order inside each part
@@ -247,6 +249,7 @@ struct gmg_solver
 				  // (profiles/r02_ab_switches.md: 256^3 solve 11.5 vs 10.3 ms; a barrier over ~900 CTAs costs more than a kernel
 				  // boundary with its prologue overlapped), so it is opt-in (GMG_BAND_GROUPS=1)
     int stencilLoop = 0;          // persistent full-grid stencil kernels (k_stencil_loop): bit 0 Jacobi, bit 1 residual, bit 2 apply, bit 3 zero-aware Jacobi (GMG_STENCIL_LOOP)
+    int stencilBatch = 0;         // full-grid stencil kernels with the loads of 2 / 4 planes issued together (k_stencil_b); 0 = one plane at a time (GMG_STENCIL_BATCH)
     int stencilCap = -1;          // full-grid stencil kernels capped at 40 registers: bit 0 Jacobi, bit 1 residual, bit 2 apply; -1 = by level size (GMG_STENCIL_CAP)
     int bandPerThread = 0;        // cells per thread of the band sweep kernels: 0 = picked per level (launchBand), 2 / 3 = forced (GMG_BAND_PER_THREAD)
     bool bandTiles = false;       // band sweep groups as ring-halo tiles, one launch per group (k_band_tile): measured SLOWER (GMG_BAND_TILES=1 enables)

@@ -144,7 +144,8 @@ template <typename T>
 struct StencilArgsT
 {
     const uint8_t *labels;
-    const uint8_t *flags;   // SM_JACOBI_ZERO: bit0 = cell is in the boundary band, bit1 = INTERIOR cell with a band cell in its 7-point neighbourhood
+    const uint8_t *flags;   // SM_JACOBI_ZERO: the level's neighbour-mask grid (k_band_nbr_mask): bit0 = the cell is in the boundary band, bits 1..6 = its
+			    // -x, +x, -y, +y, -z, +z neighbour is (INTERIOR cells only); 0 = no band cell anywhere in the 7-point neighbourhood
     const T *in;        // x (Jacobi/residual) or source (apply)
     const T *b;         // rhs (Jacobi/residual)
     T *out;             // Jacobi: new x (out of place); apply: A in; residual: b - A in
@@ -255,9 +256,11 @@ __device__ __forceinline__ double stencilChunk(const StencilArgsT<T> &a, const C
     const uchar2 *lab = cl.lab, *flg = cl.flg;
     if (MODE == SM_JACOBI_ZERO)
     {
-	// phase 1, every cell: x is zero in the whole neighbourhood, lap = +0.0, and centre + (2/3)((b - 0) / 6) = (2/3)(b / 6);
-	// a pure stream of b in, x out, the four planes' loads in flight together
-	int near = 0;
+	// One branch-free pass, the four planes' loads in flight together like the other modes.  The mask byte of a cell (prologue)
+	// says which of its seven stencil points lie on the band: a point is LOADED only where its bit is set and is zero elsewhere,
+	// whatever the grid holds there.  For the common cell -- mask 0, no band cell in the neighbourhood -- every load is predicated
+	// off and the arithmetic below runs on zeros: lap = +0.0, x = 0 + (2/3)((b - 0) / 6), a pure stream of b in, x out.  It is the
+	// plain sweep's instruction sequence on masked values, hence bitwise its result on a zero-filled grid.
 #pragma unroll
 	for (int dz = 0; dz < CHUNK_Z; ++dz)
 	{
@@ -265,44 +268,22 @@ __device__ __forceinline__ double stencilChunk(const StencilArgsT<T> &a, const C
 	    if (!(a0 | a1)) continue;
 	    const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
 	    const T2 rhs = ld2(a.b + i);
-	    const T o0 = T(2.0 / 3.0) * (rhs.x / T(6.0)), o1 = T(2.0 / 3.0) * (rhs.y / T(6.0));
-	    if (a0 & a1) st2(a.out + i, make2<T>(o0, o1));
-	    else if (a0) a.out[i] = o0;
-	    else a.out[i + 1] = o1;
-	    near |= ((flg[dz].x | flg[dz].y) & 2) << dz;
-	}
-	// phase 2, the few cells with a band cell in their neighbourhood (bit dz + 1 of `near`): the full stencil with every
-	// value taken through the band mask -- whatever the grid holds off the band reads as zero -- overwrites phase 1's
-	// value.  One plane at a time and everything re-read (cache hits): the common path keeps no registers for it.
-#pragma unroll 1
-	for (int dz = 0; near != 0 && dz < CHUNK_Z; ++dz)
-	{
-	    if (!((near >> (dz + 1)) & 1)) continue;
-	    const int64_t i = int64_t(z0 + dz) * a.plane + inPlane;
-	    const uchar2 l = *reinterpret_cast<const uchar2 *>(a.labels + i);
-	    const bool a0 = (l.x == L_INTERIOR), a1 = (l.y == L_INTERIOR);
-	    const T2 rhs = ld2(a.b + i);
-	    const uint8_t *f = a.flags + i;
-	    const uchar2 fc = *reinterpret_cast<const uchar2 *>(f);
-	    const uchar2 fym = *reinterpret_cast<const uchar2 *>(f - a.pitch), fyp = *reinterpret_cast<const uchar2 *>(f + a.pitch);
-	    const uchar2 fzm = *reinterpret_cast<const uchar2 *>(f - a.plane), fzp = *reinterpret_cast<const uchar2 *>(f + a.plane);
-	    const int fxm = f[-1], fxp = f[2];
-	    T2 c2 = ld2(a.in + i);
-	    T xm = a.in[i - 1], xp = a.in[i + 2];
-	    T2 ym = ld2(a.in + i - a.pitch), yp = ld2(a.in + i + a.pitch);
-	    T2 zm = ld2(a.in + i - a.plane), zp = ld2(a.in + i + a.plane);
-	    if (!(fc.x & 1)) c2.x = T(0.0);
-	    if (!(fc.y & 1)) c2.y = T(0.0);
-	    if (!(fxm & 1)) xm = T(0.0);
-	    if (!(fxp & 1)) xp = T(0.0);
-	    if (!(fym.x & 1)) ym.x = T(0.0);
-	    if (!(fym.y & 1)) ym.y = T(0.0);
-	    if (!(fyp.x & 1)) yp.x = T(0.0);
-	    if (!(fyp.y & 1)) yp.y = T(0.0);
-	    if (!(fzm.x & 1)) zm.x = T(0.0);
-	    if (!(fzm.y & 1)) zm.y = T(0.0);
-	    if (!(fzp.x & 1)) zp.x = T(0.0);
-	    if (!(fzp.y & 1)) zp.y = T(0.0);
+	    const unsigned m0 = flg[dz].x, m1 = flg[dz].y, m = m0 | m1;
+	    const T2 zero2 = make2<T>(T(0.0), T(0.0));
+	    T2 c2 = (m & 1u) ? ld2(a.in + i) : zero2;
+	    const T xm = (m0 & 2u) ? a.in[i - 1] : T(0.0), xp = (m1 & 4u) ? a.in[i + 2] : T(0.0);
+	    T2 ym = (m & 8u) ? ld2(a.in + i - a.pitch) : zero2, yp = (m & 16u) ? ld2(a.in + i + a.pitch) : zero2;
+	    T2 zm = (m & 32u) ? ld2(a.in + i - a.plane) : zero2, zp = (m & 64u) ? ld2(a.in + i + a.plane) : zero2;
+	    if (!(m0 & 1u)) c2.x = T(0.0);
+	    if (!(m1 & 1u)) c2.y = T(0.0);
+	    if (!(m0 & 8u)) ym.x = T(0.0);
+	    if (!(m1 & 8u)) ym.y = T(0.0);
+	    if (!(m0 & 16u)) yp.x = T(0.0);
+	    if (!(m1 & 16u)) yp.y = T(0.0);
+	    if (!(m0 & 32u)) zm.x = T(0.0);
+	    if (!(m1 & 32u)) zm.y = T(0.0);
+	    if (!(m0 & 64u)) zp.x = T(0.0);
+	    if (!(m1 & 64u)) zp.y = T(0.0);
 	    T lap0 = -xm;
 	    lap0 -= c2.y; lap0 -= ym.x; lap0 -= yp.x; lap0 -= zm.x; lap0 -= zp.x;
 	    lap0 += T(6.0) * c2.x;
@@ -346,6 +327,97 @@ __device__ __forceinline__ double stencilChunk(const StencilArgsT<T> &a, const C
     }
     return acc;
 }
+// The same chunk with the loads of PB planes issued TOGETHER before any of them is used.  stencilChunk above walks its four planes
+// one after the other -- loads, arithmetic, store, next plane: the store to `out` may alias the next plane's loads as far as the
+// compiler knows, and the division's slow-path call splits the block -- so a CTA is a chain of four dependent round trips, and a
+// 256^3 level is 5-6 waves of such CTAs.  Here every value a group of PB planes needs sits in registers first (the centre pairs of
+// planes zb - 1 .. zb + PB are loaded once and serve as centre, -z and +z neighbour: 6 plane loads instead of 12 at PB = 4), then
+// the group is computed and stored.  Which points are read: all seven, or (SM_JACOBI_ZERO) those the cell's mask byte names.
+// Same per-cell arithmetic in the same order, same accumulation order of the fused dot product: bitwise stencilChunk.
+template <typename T, int MODE, bool DOT, int PB>
+__device__ __forceinline__ double stencilChunkBatched(const StencilArgsT<T> &a, const ChunkLabels &cl)
+{
+    typedef typename Vec2<T>::type T2;
+    static_assert(CHUNK_Z % PB == 0, "plane groups must tile the chunk");
+    double acc = 0.0;
+    const int64_t inPlane = cl.inPlane;
+    const T2 zero2 = make2<T>(T(0.0), T(0.0));
+#pragma unroll
+    for (int g = 0; g < CHUNK_Z / PB; ++g)
+    {
+	const int zb = cl.z0 + g * PB;
+	bool a0[PB], a1[PB];
+	unsigned m0[PB], m1[PB];
+#pragma unroll
+	for (int q = 0; q < PB; ++q)
+	{
+	    const uchar2 l = cl.lab[g * PB + q];
+	    a0[q] = (l.x == L_INTERIOR);
+	    a1[q] = (l.y == L_INTERIOR);
+	    const bool act = a0[q] | a1[q];
+	    m0[q] = !act ? 0u : (MODE == SM_JACOBI_ZERO ? unsigned(cl.flg[g * PB + q].x) : 0x7fu);
+	    m1[q] = !act ? 0u : (MODE == SM_JACOBI_ZERO ? unsigned(cl.flg[g * PB + q].y) : 0x7fu);
+	}
+	T2 c[PB + 2];
+#pragma unroll
+	for (int k = 0; k < PB + 2; ++k)
+	{
+	    unsigned need = 0u;
+	    if (k >= 1 && k <= PB) need |= (m0[k - 1] | m1[k - 1]) & 1u;   // centre of plane k - 1
+	    if (k <= PB - 1) need |= (m0[k] | m1[k]) & 32u;                // -z neighbour of plane k
+	    if (k >= 2) need |= (m0[k - 2] | m1[k - 2]) & 64u;            // +z neighbour of plane k - 2
+	    c[k] = need ? ld2(a.in + int64_t(zb - 1 + k) * a.plane + inPlane) : zero2;
+	}
+	T xm[PB], xp[PB];
+	T2 ym[PB], yp[PB], rhs[PB];
+#pragma unroll
+	for (int q = 0; q < PB; ++q)
+	{
+	    const int64_t i = int64_t(zb + q) * a.plane + inPlane;
+	    const unsigned m = m0[q] | m1[q];
+	    xm[q] = (m0[q] & 2u) ? a.in[i - 1] : T(0.0);
+	    xp[q] = (m1[q] & 4u) ? a.in[i + 2] : T(0.0);
+	    ym[q] = (m & 8u) ? ld2(a.in + i - a.pitch) : zero2;
+	    yp[q] = (m & 16u) ? ld2(a.in + i + a.pitch) : zero2;
+	    rhs[q] = (MODE != SM_APPLY && (a0[q] | a1[q])) ? ld2(a.b + i) : zero2;
+	}
+#pragma unroll
+	for (int q = 0; q < PB; ++q)
+	{
+	    if (!(a0[q] | a1[q])) continue;
+	    const int z = zb + q;
+	    const int64_t i = int64_t(z) * a.plane + inPlane;
+	    T2 c2 = c[q + 1], zm = c[q], zp = c[q + 2], ymq = ym[q], ypq = yp[q];
+	    if (MODE == SM_JACOBI_ZERO)
+	    {
+		if (!(m0[q] & 1u)) c2.x = T(0.0);
+		if (!(m1[q] & 1u)) c2.y = T(0.0);
+		if (!(m0[q] & 8u)) ymq.x = T(0.0);
+		if (!(m1[q] & 8u)) ymq.y = T(0.0);
+		if (!(m0[q] & 16u)) ypq.x = T(0.0);
+		if (!(m1[q] & 16u)) ypq.y = T(0.0);
+		if (!(m0[q] & 32u)) zm.x = T(0.0);
+		if (!(m1[q] & 32u)) zm.y = T(0.0);
+		if (!(m0[q] & 64u)) zp.x = T(0.0);
+		if (!(m1[q] & 64u)) zp.y = T(0.0);
+	    }
+	    T lap0 = -xm[q];
+	    lap0 -= c2.y; lap0 -= ymq.x; lap0 -= ypq.x; lap0 -= zm.x; lap0 -= zp.x;
+	    lap0 += T(6.0) * c2.x;
+	    T lap1 = -c2.x;
+	    lap1 -= xp[q]; lap1 -= ymq.y; lap1 -= ypq.y; lap1 -= zm.y; lap1 -= zp.y;
+	    lap1 += T(6.0) * c2.y;
+	    const T o0 = stencilFinish<MODE, T>(lap0, c2.x, rhs[q].x, T(6.0));
+	    const T o1 = stencilFinish<MODE, T>(lap1, c2.y, rhs[q].y, T(6.0));
+	    if (a0[q] & a1[q]) st2(a.out + i, make2<T>(o0, o1));
+	    else if (a0[q]) a.out[i] = o0;
+	    else a.out[i + 1] = o1;
+	    if (DOT && z >= a.dotLo && z < a.dotHi) acc += double((a0[q] ? c2.x * lap0 : T(0.0)) + (a1[q] ? c2.y * lap1 : T(0.0)));
+	}
+    }
+    return acc;
+}
+
 template <typename T, int MODE, bool DOT>
 __device__ __forceinline__ double stencilBody(const StencilArgsT<T> &a, int vb, int tid)
 {
@@ -361,13 +433,30 @@ __device__ __forceinline__ double stencilBody(const StencilArgsT<T> &a, int vb, 
     return acc;
 }
 
-// (the zero-aware sweep streams b -> x on its common path: capped at 40 registers so the rare masked path cannot cost it occupancy)
-// MINB = 6 on the other modes too trades loads in flight per thread for resident CTAs (56 -> 40 registers): see launchStencil
-template <int MODE, bool DOT, typename T = double, int MINB = (MODE == SM_JACOBI_ZERO ? 6 : 1)>
+// MINB = 6 trades loads in flight per thread for resident CTAs (56 -> 40 registers): see launchStencil
+template <int MODE, bool DOT, typename T = double, int MINB = 1>
 __global__ void __launch_bounds__(BLOCK, MINB) k_stencil(const StencilArgsT<T> a)
 {
     pdlLaunch();
     const double acc = stencilBody<T, MODE, DOT>(a, blockIdx.x, threadIdx.x);
+    if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
+}
+
+// k_stencil with stencilChunkBatched: PB = 4 keeps a whole chunk's values in registers (2 CTAs per SM), PB = 2 half of it (3 CTAs per SM)
+template <int MODE, bool DOT, int PB>
+__global__ void __launch_bounds__(BLOCK, PB >= 4 ? 2 : 3) k_stencil_b(const StencilArgsT<double> a)
+{
+    pdlLaunch();
+    double acc = 0.0;
+    const int vb = blockIdx.x, tid = threadIdx.x;
+    if (vb < a.nChunks)
+    {
+	ChunkLabels cl;
+	stencilLabels<double, MODE>(a, vb, tid, cl);
+	pdlWait();
+	acc = stencilChunkBatched<double, MODE, DOT, PB>(a, cl);
+    }
+    else acc = stencilBoundary<double, MODE, DOT>(a, (vb - a.nChunks) * BLOCK + tid);
     if (DOT) gridReduce(acc, a.partials, a.ticket, a.result);
 }
 
@@ -2134,6 +2223,18 @@ __global__ void __launch_bounds__(BLOCK) k_band_flag_grid(uint8_t *flags, const 
 {
     const int64_t i = int64_t(blockIdx.x) * BLOCK + threadIdx.x;
     if (i < total) flags[i] = uint8_t((band[i] ? 1 : 0) | (dilated[i] ? 2 : 0));
+}
+// neighbour mask of SM_JACOBI_ZERO: bit0 = the cell is in the band; on INTERIOR cells (never on the storage border) bits 1..6 = the
+// -x, +x, -y, +y, -z, +z neighbour is in the band
+__global__ void __launch_bounds__(BLOCK) k_band_nbr_mask(uint8_t *mask, const uint8_t *band, const uint8_t *labels, BoxArgs g)
+{
+    const int64_t i = int64_t(blockIdx.x) * BLOCK + threadIdx.x;
+    if (i >= g.total) return;
+    unsigned m = band[i] ? 1u : 0u;
+    if (labels[i] == L_INTERIOR)
+	m |= (band[i - 1] ? 2u : 0u) | (band[i + 1] ? 4u : 0u) | (band[i - g.pitch] ? 8u : 0u) | (band[i + g.pitch] ? 16u : 0u) | (band[i - g.plane] ? 32u : 0u) |
+	     (band[i + g.plane] ? 64u : 0u);
+    mask[i] = uint8_t(m);
 }
 // flags for the two compactions: which = 0 -> BOUNDARY cells, 1 -> INTERIOR cells of the band
 __global__ void __launch_bounds__(BLOCK) k_band_flags(uint8_t *flags, const uint8_t *mask, const uint8_t *labels, int which, int64_t total)
