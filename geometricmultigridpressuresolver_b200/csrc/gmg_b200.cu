@@ -2584,7 +2584,8 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
 	GMG_CUDA(cudaGetLastError());
 	return GMG_OK;
     }
-    // stencilCap: bit 0 Jacobi, bit 1 residual, bit 2 apply, bit 3 zero-aware Jacobi -- the 40-register instantiation (6 resident CTAs per SM instead of 4)
+    // stencilCap: bit 0 Jacobi, bit 1 residual, bit 2 apply, bit 3 zero-aware Jacobi -- the 40-register instantiation (6 resident CTAs per SM instead of 4);
+    // bit 4 zero-aware Jacobi, bit 5 Jacobi at 48 registers (5 CTAs per SM)
     if (s->stencilLoop)
     {
 	// persistent variant: what fits the device at once, every CTA walking its chunks with the next chunk's labels prefetched
@@ -2654,6 +2655,7 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
     {
 	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 25.0);
 	if (cap & 1) GMG_CUDA(launchK((k_stencil<SM_JACOBI, false, double, 6>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	else if (cap & 32) GMG_CUDA(launchK((k_stencil<SM_JACOBI, false, double, 5>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
 	else GMG_CUDA(launchK((k_stencil<SM_JACOBI, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     else if (mode == SM_JACOBI_ZERO)
@@ -2661,6 +2663,7 @@ static int launchStencil(gmg_solver *s, int level, int mode, const double *in, c
 	// x is zero off the band: its 8 bytes per cell are not read (one flag byte is), and no zero fill ran before
 	GMG_LAUNCH(s->ctx, KC_JACOBI, n * 18.0);
 	if (cap & 8) GMG_CUDA(launchK((k_stencil<SM_JACOBI_ZERO, false, double, 6>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
+	else if (cap & 16) GMG_CUDA(launchK((k_stencil<SM_JACOBI_ZERO, false, double, 5>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
 	else GMG_CUDA(launchK((k_stencil<SM_JACOBI_ZERO, false>), unsigned(grid), unsigned(BLOCK), size_t(0), st, a));
     }
     else if (mode == SM_RESIDUAL)

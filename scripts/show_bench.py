@@ -23,6 +23,7 @@ for f in sys.argv[1:]:
     for k, v in (d.get("fine_level_kernels") or {}).items():
         print("     %-16s %8.1f us x%d  %.0f GB/s  frac %.3f" % (k, v["us_per_launch"], v["launches_per_vcycle"], v["algorithmic_gbs"], v["frac_of_hbm_peak"]))
     for l, row in (d.get("kernels_by_level") or {}).items():
-        parts = ["%s %.3f/%d" % (k[:8], v["ms_per_solve"], v["launches_per_solve"]) for k, v in row.items() if v["launches_per_solve"]]
+        per = "solve" if any("ms_per_solve" in v for v in row.values()) else "vcycle"
+        parts = ["%s %.3f/%d" % (k[:8], v["ms_per_" + per], v["launches_per_" + per]) for k, v in row.items() if v.get("launches_per_" + per)]
         if parts:
             print("     L%s: %s" % (l, "  ".join(parts)))

@@ -445,7 +445,7 @@ def test_vcycle_paths_agree_bitwise(gpu_ctx, monkeypatch):
     for name, env in [("cluster", {"GMG_CLUSTER_CYCLE": "1"}), ("compact", {}), ("kernels", {"GMG_COARSE_FUSED": "0", "GMG_CLUSTER_SMOOTH": "0", "GMG_BAND_TILES": "0", "GMG_BAND_PER_THREAD": "2"}), ("level_kernels", {"GMG_CLUSTER_SMOOTH": "0"}),
                       ("zero_fill", {"GMG_ZERO_AWARE": "0"}), ("cluster8", {"GMG_CLUSTER_CYCLE": "1", "GMG_CLUSTER_SIZE": "8"}), ("first2", {"GMG_CLUSTER_CYCLE": "1", "GMG_FUSED_FIRST": "2"}),
                       ("tma", {"GMG_TMA": "31", "GMG_TMA_MIN_CELLS": "100"}), ("sweep_groups", {"GMG_BAND_GROUPS": "1", "GMG_BAND_TILES": "0", "GMG_BAND_PER_THREAD": "2"}), ("sweep_resident", {"GMG_BAND_RESIDENT": "1", "GMG_BAND_TILES": "0", "GMG_BAND_PER_THREAD": "2"}), ("sweep_kernels", {"GMG_BAND_TILES": "0", "GMG_BAND_PER_THREAD": "2"}),
-                      ("stencil_loop", {"GMG_STENCIL_LOOP": "15", "GMG_STENCIL_LOOP_SLOTS": "24"}), ("stencil_cap", {"GMG_STENCIL_CAP": "15"}),
+                      ("stencil_loop", {"GMG_STENCIL_LOOP": "15", "GMG_STENCIL_LOOP_SLOTS": "24"}), ("stencil_cap", {"GMG_STENCIL_CAP": "15"}), ("stencil_cap48", {"GMG_STENCIL_CAP": "54"}),
                       ("stencil_batch2", {"GMG_STENCIL_BATCH": "2"}), ("stencil_batch4", {"GMG_STENCIL_BATCH": "4"}), ("stencil_one_plane", {"GMG_STENCIL_BATCH": "0"})]:
         for k in ("GMG_CLUSTER_CYCLE", "GMG_COARSE_FUSED", "GMG_ZERO_AWARE", "GMG_CLUSTER_SIZE", "GMG_FUSED_FIRST", "GMG_TMA", "GMG_TMA_MIN_CELLS", "GMG_BAND_GROUPS", "GMG_BAND_RESIDENT", "GMG_CLUSTER_SMOOTH", "GMG_BAND_TILES", "GMG_BAND_PER_THREAD", "GMG_STENCIL_LOOP", "GMG_STENCIL_LOOP_SLOTS", "GMG_STENCIL_CAP", "GMG_STENCIL_BATCH"):
             monkeypatch.delenv(k, raising=False)
