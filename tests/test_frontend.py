@@ -182,6 +182,24 @@ def test_oracle_material_labels_and_valid_faces_against_numpy(port):
         assert not v[tuple(edge)].any()
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 5, 3), (4, 1, 7), (6, 3, 1), (2, 2, 2), (5, 9, 17)])
+def test_oracle_material_labels_on_ragged_and_degenerate_grids(port, shape):
+    """One-cell-thick axes, a single cell, unequal strides: every face of such a grid touches the border somewhere
+    (HDK_Utilities.cpp:35, HDK_Utilities.h:180)."""
+    rng = np.random.default_rng(sum(shape))
+    phi = rng.random(shape).astype(np.float32) - 0.5
+    solid = make_solid_sdf(shape, 7)
+    cut = [(rng.random(D.face_shape(shape, a)) < 0.6).astype(np.float32) * (rng.random(D.face_shape(shape, a)).astype(np.float32) + 0.01) for a in range(3)]
+    m = port.build_material_labels(phi, solid, cut)
+    assert (m == np_material_labels(phi, solid, cut)).all()
+    for axis in range(3):
+        assert (port.build_valid_faces(m, cut[axis], axis) == np_valid_faces(m, cut[axis], axis)).all()
+    closed = [np.zeros_like(c) for c in cut]
+    assert (port.build_material_labels(phi, solid, closed) == SOLID).all()  # no open face anywhere: everything is SOLID (:99)
+    for axis in range(3):
+        assert not port.build_valid_faces(m, closed[axis], axis).any()
+
+
 def test_projection_chain_on_the_oracle(port):
     """The restated builders wired as GFS.cpp:296-660 wires them, around the oracle's MGPCG: the cut-cell divergence of every liquid
     cell drops by seven orders of magnitude (what the fpreal32 pressure / velocity fields allow) -- the node's own check,
