@@ -230,6 +230,25 @@ class RefLib(_Base):
         self.fn("set_threads", None)(int(n or os.cpu_count() or 1))
         return self.threads()
 
+    def build_material_labels(self, liquid_surface, solid_at_centres, cut_cell):
+        """HDK::Utilities::buildMaterialCellLabels -- the reference's own HDK_Utilities.cpp, compiled unmodified."""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        ls, so, cc = f32(liquid_surface), f32(solid_at_centres), [f32(c) for c in cut_cell]
+        fp = C.POINTER(C.c_float)
+        out = np.empty(ls.shape, dtype=np.int32)
+        self.fn("build_material_labels", None)(ls.ctypes.data_as(fp), so.ctypes.data_as(fp), cc[0].ctypes.data_as(fp), cc[1].ctypes.data_as(fp), cc[2].ctypes.data_as(fp),
+                                               _res(ls), out.ctypes.data_as(_i32p))
+        return out
+
+    def build_valid_faces(self, material, cut_cell, axis):
+        """findOccupiedFaceTiles + uncompressTiles + classifyValidFaces (the reference's own templates) in the order of GFS.cpp:717-744."""
+        m, mp = _i32(material)
+        cc = np.ascontiguousarray(cut_cell, dtype=np.float32)
+        out = np.empty(cc.shape, dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        self.fn("build_valid_faces", None)(mp, cc.ctypes.data_as(fp), _res(m), int(axis), out.ctypes.data_as(fp))
+        return out
+
     def expand_labels(self, base):
         b, bp = _i32(base)
         out = _i32p()

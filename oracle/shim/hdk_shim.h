@@ -2,7 +2,7 @@
 //
 // Minimal stand-in for the slice of the Houdini 18 HDK that the reference's
 // hot-path sources use (HDK_GeometricMultigridOperators.{h,cpp},
-// HDK_GeometricMultigridPoissonSolver.{h,cpp}, HDK_GeometricCGPoissonSolver.h),
+// HDK_GeometricMultigridPoissonSolver.{h,cpp}, HDK_GeometricCGPoissonSolver.h, HDK_Utilities.{h,cpp}),
 // so that those files compile UNMODIFIED from /root/reference/Source into
 // oracle/_ref/.  The symbol list follows SURVEY.md appendix B.
 //
@@ -474,6 +474,7 @@ public:
     bool isTileConstant() const { return myTile->isConstant(); }
     T getValue() const { return myTile->isConstant() ? myTile->constantValue() : myTile->rawData()[myIdx]; }
     void setValue(T v) { myTile->set(myLocal[0], myLocal[1], myLocal[2], v); }
+    void setCompressOnExit(bool) {}  // HDK: re-compress a tile when the iterator leaves it; storage only, values unaffected
 
     int x() const { return myTileOrigin[0] + myLocal[0]; }
     int y() const { return myTileOrigin[1] + myLocal[1]; }
@@ -641,11 +642,80 @@ private:
     bool myFast = false;
 };
 
+// ---------------------------------------------------------------- SIM_RawField / SIM_RawIndexField
+// The slice HDK_Utilities.{h,cpp} uses (buildMaterialCellLabels, classifyValidFaces, ...): a voxel array of fpreal32 / exint
+// with a resolution, tile access and -- SIM_RawField only -- a CELL-SAMPLED position map on the unit-spaced lattice
+// (indexToPos = index + 0.5) with trilinear getValue(pos), clamped at the border.  At a cell centre the interpolation weights
+// are exactly 0 and 1, so getValue(indexToPos(cell)) is the cell's own value: the aligned-fields case the product's entry point
+// documents (gmg_build_material_labels).
+using UT_VoxelArrayF = UT_VoxelArray<fpreal32>;
+using UT_VoxelArrayI = UT_VoxelArray<exint>;
+using UT_VoxelArrayIteratorF = UT_VoxelArrayIterator<fpreal32>;
+using UT_VoxelArrayIteratorI = UT_VoxelArrayIterator<exint>;
+using UT_VoxelTileIteratorF = UT_VoxelTileIterator<fpreal32>;
+using UT_VoxelTileIteratorI = UT_VoxelTileIterator<exint>;
+
+class SIM_RawField
+{
+public:
+    void init(int x, int y, int z) { myField.size(x, y, z); myField.constant(0); }
+    void match(const SIM_RawField &o) { const UT_Vector3I r = o.getVoxelRes(); init(int(r[0]), int(r[1]), int(r[2])); }
+    void makeConstant(fpreal32 v) { myField.constant(v); }
+    UT_Vector3I getVoxelRes() const { return myField.getVoxelRes(); }
+    const UT_VoxelArrayF *field() const { return &myField; }
+    UT_VoxelArrayF *fieldNC() { return &myField; }
+    bool indexToPos(int x, int y, int z, UT_Vector3 &pos) const
+    {
+	pos = UT_Vector3(fpreal32(x) + 0.5f, fpreal32(y) + 0.5f, fpreal32(z) + 0.5f);
+	return true;
+    }
+    fpreal32 getValue(const UT_Vector3 &pos) const
+    {
+	int i0[3];
+	fpreal32 f[3];
+	const UT_Vector3I r = getVoxelRes();
+	for (int a = 0; a < 3; ++a)
+	{
+	    fpreal32 p = pos[a] - 0.5f;
+	    p = p < 0 ? 0 : (p > fpreal32(r[a] - 1) ? fpreal32(r[a] - 1) : p);
+	    i0[a] = int(p);
+	    f[a] = p - fpreal32(i0[a]);
+	}
+	auto at = [&](int dx, int dy, int dz) { return myField(i0[0] + dx, i0[1] + dy, i0[2] + dz); };  // clamped read
+	auto lerp = [](fpreal32 v0, fpreal32 v1, fpreal32 t) { return (1 - t) * v0 + t * v1; };
+	return lerp(lerp(lerp(at(0, 0, 0), at(1, 0, 0), f[0]), lerp(at(0, 1, 0), at(1, 1, 0), f[0]), f[1]),
+		    lerp(lerp(at(0, 0, 1), at(1, 0, 1), f[0]), lerp(at(0, 1, 1), at(1, 1, 1), f[0]), f[1]), f[2]);
+    }
+
+private:
+    UT_VoxelArrayF myField;
+};
+
+class SIM_RawIndexField
+{
+public:
+    void init(int x, int y, int z) { myField.size(x, y, z); myField.constant(0); }
+    void match(const SIM_RawField &o) { const UT_Vector3I r = o.getVoxelRes(); init(int(r[0]), int(r[1]), int(r[2])); }
+    void match(const SIM_RawIndexField &o) { const UT_Vector3I r = o.getVoxelRes(); init(int(r[0]), int(r[1]), int(r[2])); }
+    void makeConstant(exint v) { myField.constant(v); }
+    UT_Vector3I getVoxelRes() const { return myField.getVoxelRes(); }
+    const UT_VoxelArrayI *field() const { return &myField; }
+    UT_VoxelArrayI *fieldNC() { return &myField; }
+
+private:
+    UT_VoxelArrayI myField;
+};
+
 // ---------------------------------------------------------------- SIM::FieldUtils
 namespace SIM
 {
 namespace FieldUtils
 {
+    inline fpreal32 getFieldValue(const SIM_RawField &field, const UT_Vector3I &cell) { return (*field.field())(cell); }
+    inline exint getFieldValue(const SIM_RawIndexField &field, const UT_Vector3I &cell) { return (*field.field())(cell); }
+    inline void setFieldValue(SIM_RawField &field, const UT_Vector3I &cell, const fpreal32 value) { field.fieldNC()->setValue(cell, value); }
+    inline void setFieldValue(SIM_RawIndexField &field, const UT_Vector3I &cell, const exint value) { field.fieldNC()->setValue(cell, value); }
+
     // cell -> neighbouring cell along axis; direction 0 = backward, 1 = forward
     SYS_FORCE_INLINE UT_Vector3I cellToCellMap(const UT_Vector3I &cell, const int axis, const int direction)
     {

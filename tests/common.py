@@ -49,3 +49,26 @@ def rhs_for(labels, off, base_shape, dx):
 
 def relerr(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+# ---- fields of the front-end fixture tests/golden/frontend_fields.npz (tests/golden/make_golden_frontend.py) ----------------
+FRONTEND_CASES = {"tank24": ((24, 24, 24), 11), "slab_40x18x33": ((40, 18, 33), 12), "thin_17x1x35": ((17, 1, 35), 13)}
+
+
+def frontend_fields(name):
+    """Seeded surface SDF, solid SDF (both signs) and cut-cell weights (closed, open, fractional; one solid block with every face
+    closed) of a front-end fixture case: (phi, solid, [cut_x, cut_y, cut_z]), all float32."""
+    shape, seed = FRONTEND_CASES[name]
+    rng = np.random.default_rng(seed)
+    phi = rng.random(shape).astype(np.float32) - np.float32(0.45)
+    solid = rng.random(shape).astype(np.float32) - np.float32(0.5)
+    cut = []
+    for a in range(3):
+        fs = D.face_shape(shape, a)
+        cut.append((rng.random(fs) < 0.65).astype(np.float32) * (rng.random(fs).astype(np.float32) * np.float32(0.95) + np.float32(0.05)))
+    blk = tuple(slice(0, max(1, s // 2)) for s in shape)
+    for a in range(3):
+        sl = list(blk)
+        sl[2 - a] = slice(0, blk[2 - a].stop + 1)
+        cut[a][tuple(sl)] = 0.0
+    return phi, solid, cut

@@ -2,7 +2,9 @@
 (HDK_GeometricFreeSurfacePressureSolver.cpp:717-744), buildMGDomainLabels, buildMGBoundaryWeights, buildRHS, applyOldPressure,
 applySolutionToPressure, applyPressureGradient (HDK_GeometricFreeSurfacePressureSolver.cpp:746-1131).
 
-PARITY UNPINNED at the reference: that file needs live SIM fields and cannot be compiled here.  What is checked:
+buildMaterialCellLabels / buildValidFaces are PINNED: HDK_Utilities.{h,cpp} compile unmodified over the shim's SIM_RawField, the C
+restatement is held to them (tests/test_oracle_vs_reference.py) and to a fixture generated from them (tests/golden/frontend_fields.npz).
+The other six are PARITY UNPINNED at the reference: GFS.cpp needs the node class and live SIM fields and cannot be compiled here.  What is checked:
   CPU  the C restatement (oracle/gmg_oracle.c) against an independent vectorised numpy restatement of the same lines;
   GPU  the CUDA kernels (csrc/gmg_frontend.cuh, through the C ABI) against the C restatement: labels bit-exact, fpreal32 outputs
        bit-exact, fp64 outputs to 1e-14 (fused multiply-adds), and the whole chain fields -> labels/weights/rhs -> MGPCG ->
@@ -198,6 +200,42 @@ def test_oracle_material_labels_on_ragged_and_degenerate_grids(port, shape):
     assert (port.build_material_labels(phi, solid, closed) == SOLID).all()  # no open face anywhere: everything is SOLID (:99)
     for axis in range(3):
         assert not port.build_valid_faces(m, closed[axis], axis).any()
+
+
+def _frontend_fixture():
+    import os
+
+    from tests.common import GOLDEN_DIR
+
+    return np.load(os.path.join(GOLDEN_DIR, "frontend_fields.npz"))
+
+
+def _check_against_fixture(build_material_labels, build_valid_faces):
+    """Material labels and valid-face flags of the seeded fixture fields against the outputs of the reference's OWN HDK_Utilities sources
+    (tests/golden/make_golden_frontend.py): bit for bit."""
+    import hashlib
+
+    from tests.common import FRONTEND_CASES, frontend_fields
+
+    g = _frontend_fixture()
+    for name in FRONTEND_CASES:
+        phi, solid, cut = frontend_fields(name)
+        shas = [hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() for a in [phi, solid] + cut]
+        assert shas == list(g[f"{name}__inputs_sha"]), "the fixture's inputs no longer reproduce"
+        material = build_material_labels(phi, solid, cut)
+        assert material.dtype == np.int32 and (material == g[f"{name}__material"]).all(), name
+        for axis in range(3):
+            v = build_valid_faces(material, cut[axis], axis)
+            assert v.dtype == np.float32 and (v == g[f"{name}__valid{axis}"]).all(), (name, axis)
+
+
+def test_oracle_restatement_against_the_reference_generated_fixture(port):
+    _check_against_fixture(port.build_material_labels, port.build_valid_faces)
+
+
+@pytest.mark.gpu
+def test_material_labels_and_valid_faces_against_the_reference_generated_fixture(gpu_ctx):
+    _check_against_fixture(gpu_ctx.buildMaterialCellLabels, gpu_ctx.buildValidFaces)
 
 
 def test_projection_chain_on_the_oracle(port):

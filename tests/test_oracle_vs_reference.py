@@ -115,3 +115,48 @@ def test_coarse_matrix_job_count_quirk(port):
     v1 = port.solver(labels, w, lv, False, coarse_scale=1.0).vcycle(np.zeros_like(b), b)
     assert relerr(v3, v_ref) < 1e-11
     assert relerr(v1, v_ref) > 1e-3  # and it really is a different operator
+
+
+@pytest.mark.parametrize("shape,seed", [((24, 24, 24), 3), ((40, 18, 33), 5), ((16, 16, 16), 1), ((1, 5, 3), 2), ((17, 1, 35), 4), ((2, 2, 2), 6)])
+def test_material_labels_and_valid_faces_against_the_reference_sources(port, ref, shape, seed):
+    """buildMaterialCellLabels is the reference's own HDK_Utilities.cpp (compiled unmodified over the shim's SIM_RawField), buildValidFaces its
+    own templates findOccupiedFaceTiles / uncompressTiles / classifyValidFaces in the order of GFS.cpp:717-744: this pins the C restatement the
+    GPU kernels are held to (tests/test_frontend.py).  Shapes span several 16^3 tiles, partial tiles and one-cell-thick axes."""
+    rng = np.random.default_rng(seed)
+    phi = (rng.random(shape).astype(np.float32) - 0.45)
+    solid = (rng.random(shape).astype(np.float32) - 0.5)
+    cut = []
+    for a in range(3):
+        fs = D.face_shape(shape, a)
+        w = (rng.random(fs) < 0.65).astype(np.float32) * (rng.random(fs).astype(np.float32) * 0.95 + 0.05)
+        cut.append(w)
+    # a solid block with every face closed, so whole tiles of the label field stay constant SOLID
+    blk = tuple(slice(0, max(1, s // 2)) for s in shape)
+    for a in range(3):
+        na = 2 - a
+        sl = list(blk)
+        sl[na] = slice(0, blk[na].stop + 1)
+        cut[a][tuple(sl)] = 0.0
+    for so in (solid, np.full(shape, -1.0, np.float32), np.zeros(shape, np.float32)):
+        m_ref = ref.build_material_labels(phi, so, cut)
+        m_port = port.build_material_labels(phi, so, cut)
+        assert (m_ref == m_port).all()
+        assert (m_ref[blk] == 0).all()
+        for axis in range(3):
+            v_ref = ref.build_valid_faces(m_ref, cut[axis], axis)
+            v_port = port.build_valid_faces(m_ref, cut[axis], axis)
+            assert v_ref.dtype == np.float32 and (v_ref == v_port).all()
+    assert set(np.unique(m_ref)) <= {0, 1, 2}
+
+
+def test_material_labels_of_the_frontend_test_fields_against_the_reference_sources(port, ref):
+    from tests.test_frontend import make_fields, make_solid_sdf
+
+    for n, seed in ((24, 3), (32, 5), (32, 9)):
+        material, phi, cut, valid, vel, pressure = make_fields(n, seed)
+        dry = np.full(phi.shape, -1.0, dtype=np.float32)
+        assert (ref.build_material_labels(phi, dry, cut) == material).all()
+        wet = make_solid_sdf(phi.shape)
+        assert (ref.build_material_labels(phi, wet, cut) == port.build_material_labels(phi, wet, cut)).all()
+        for axis in range(3):
+            assert (ref.build_valid_faces(material, cut[axis], axis) == valid[axis]).all()
