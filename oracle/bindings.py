@@ -240,6 +240,89 @@ class RefLib(_Base):
                                                _res(ls), out.ctypes.data_as(_i32p))
         return out
 
+    # ---- the node's own source, HDK_GeometricFreeSurfacePressureSolver.cpp compiled unmodified (shim/hdk_node_shim.h) ----
+    @staticmethod
+    def _f32c(a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def _f32x3(self, fields, copy=False):
+        keep = [self._f32c(np.array(f, dtype=np.float32, copy=True) if copy else f) for f in fields]
+        return [k[0] for k in keep], (C.POINTER(C.c_float) * 3)(*[k[1] for k in keep])
+
+    def node_domain_labels(self, material):
+        m, mp = _i32(material)
+        out = np.empty(m.shape, dtype=np.int32)
+        self.fn("node_domain_labels", None)(mp, _res(m), out.ctypes.data_as(_i32p))
+        return out
+
+    def node_boundary_weights(self, cut_cell, liquid_surface, valid_faces, material, domain_labels, axis):
+        m, mp = _i32(material)
+        l, lp = _i32(domain_labels)
+        cc, ccp = self._f32c(cut_cell)
+        ls, lsp = self._f32c(liquid_surface)
+        vf, vfp = self._f32c(valid_faces)
+        out = np.empty(cc.shape, dtype=np.float64)
+        self.fn("node_boundary_weights", None)(ccp, lsp, vfp, mp, lp, _res(m), int(axis), out.ctypes.data_as(_f64p))
+        return out
+
+    def node_rhs(self, material, velocity, cut_cell, exp_labels, offset, solid_velocity=None):
+        m, mp = _i32(material)
+        el, elp = _i32(exp_labels)
+        kv, vp = self._f32x3(velocity)
+        kc, cp = self._f32x3(cut_cell)
+        sp = None
+        if solid_velocity is not None:
+            ks, sp = self._f32x3(solid_velocity)
+        rhs = np.zeros(el.shape, dtype=np.float64)
+        self.fn("node_rhs", None)(mp, vp, cp, sp, _res(m), elp, _res(el), _res_t(offset), rhs.ctypes.data_as(_f64p))
+        return rhs
+
+    def node_old_pressure(self, pressure, material, exp_labels, offset):
+        m, mp = _i32(material)
+        el, elp = _i32(exp_labels)
+        p, pp = self._f32c(pressure)
+        x = np.zeros(el.shape, dtype=np.float64)
+        self.fn("node_old_pressure", None)(pp, mp, _res(m), elp, _res(el), _res_t(offset), x.ctypes.data_as(_f64p))
+        return x
+
+    def node_solution_to_pressure(self, pressure, material, solution, exp_labels, offset):
+        m, mp = _i32(material)
+        el, elp = _i32(exp_labels)
+        p, pp = self._f32c(np.array(pressure, dtype=np.float32, copy=True))
+        x, xp = _f64(solution)
+        self.fn("node_solution_to_pressure", None)(pp, mp, xp, _res(m), elp, _res(el), _res_t(offset))
+        return p
+
+    def node_pressure_gradient(self, velocity, cut_cell, liquid_surface, pressure, valid_faces, material, axis):
+        m, mp = _i32(material)
+        v, vp = self._f32c(np.array(velocity, dtype=np.float32, copy=True))
+        cc, ccp = self._f32c(cut_cell)
+        ls, lsp = self._f32c(liquid_surface)
+        p, pp = self._f32c(pressure)
+        vf, vfp = self._f32c(valid_faces)
+        self.fn("node_pressure_gradient", None)(vp, ccp, lsp, pp, vfp, mp, _res(m), int(axis))
+        return v
+
+    def node_solve(self, liquid_surface, velocity, cut_cell, solid_surface=None, solid_velocity=None, pressure=None, density=1000.0, tolerance=1e-5,
+                   max_iterations=2500, use_mg_preconditioner=True, use_old_pressure=False):
+        """HDK_GeometricFreeSurfacePressureSolver::solveGasSubclass, the reference's whole pressure projection on its production wiring.
+        Returns (ok, pressure, [velocity x3], [validFaces x3], log)."""
+        ls, lsp = self._f32c(liquid_surface)
+        vel, vp = self._f32x3(velocity, copy=True)
+        kc, cp = self._f32x3(cut_cell)
+        sop = svp = None
+        if solid_surface is not None:
+            so, sop = self._f32c(solid_surface)
+        if solid_velocity is not None:
+            ksv, svp = self._f32x3(solid_velocity)
+        pr, prp = self._f32c(np.zeros(ls.shape, np.float32) if pressure is None else np.array(pressure, dtype=np.float32, copy=True))
+        valid, vfp = self._f32x3([np.zeros(v.shape, np.float32) for v in vel])
+        log = C.create_string_buffer(1 << 16)
+        ok = self.fn("node_solve", C.c_int)(lsp, sop, vp, cp, svp, prp, vfp, C.c_float(density), _res(ls), C.c_double(tolerance), int(max_iterations),
+                                            int(bool(use_mg_preconditioner)), int(bool(use_old_pressure)), log, len(log))
+        return bool(ok), pr, vel, valid, log.value.decode(errors="replace")
+
     def build_valid_faces(self, material, cut_cell, axis):
         """findOccupiedFaceTiles + uncompressTiles + classifyValidFaces (the reference's own templates) in the order of GFS.cpp:717-744."""
         m, mp = _i32(material)
@@ -339,7 +422,7 @@ class PortLib(_Base):
     def __init__(self):
         super().__init__(PORT_SO)
 
-    # ---- restatement of the steps either side of the solve (GFS.cpp:746-1131; parity unpinned, see gmg_oracle.c) -------
+    # ---- restatement of the steps either side of the solve (GFS.cpp:717-1131; pinned to the node's own source by tests/test_node_reference.py) -------
     @staticmethod
     def _f32(a):
         a = np.ascontiguousarray(a, dtype=np.float32)

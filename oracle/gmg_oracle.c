@@ -944,12 +944,14 @@ static int pcg_impl(OrcSolver *s, double *x, const double *b, double tol, int ma
 
 /* =====================================================================================================================
  * The steps either side of the path: HDK_GeometricFreeSurfacePressureSolver.cpp builds the solver's
- * inputs from the simulation's fields and applies its output to them.  PARITY UNPINNED: that file needs live SIM fields
- * (SIM_RawField, SIM_RawIndexField, SIM_VectorField) and cannot be compiled here, even against the shim, so what follows is
- * a restatement only, function by function, on plain arrays: cell fields [rz][ry][rx] x-fastest, the face field of axis a
+ * inputs from the simulation's fields and applies its output to them.  PINNED: that file and HDK_Utilities.cpp compile
+ * unmodified over oracle/shim/hdk_node_shim.h (SIM_RawField, SIM_RawIndexField, SIM_VectorField, GAS_SubSolver stand-ins) into
+ * oracle/_ref, and tests/test_node_reference.py / tests/test_oracle_vs_reference.py hold every function below to them bit for
+ * bit (and the chain of them to the node's whole solveGasSubclass).  The restatement is function by function, on plain arrays: cell fields [rz][ry][rx] x-fastest, the face field of axis a
  * has one more entry along a, SIM_RawField values are fpreal32 (float) and the arithmetic is SolveReal = double
- * (GFS.h:18-19).  Assumption where the HDK's own return types matter: SIM::FieldUtils::getFieldValue returns the field's
- * fpreal32, so pressure(forward) - pressure(backward) (GFS.cpp:1095) is a float subtraction.
+ * (GFS.h:18-19).  Assumption where the HDK's own return types matter (encoded in the shim, not verifiable offline):
+ * SIM::FieldUtils::getFieldValue returns the field's fpreal32, so pressure(forward) - pressure(backward) (GFS.cpp:1095) is a
+ * float subtraction.
  * Material labels: HDK_Utilities.h:17 { SOLID_CELL = 0, LIQUID_CELL = 1, AIR_CELL = 2 }; VALID_FACE = 1 (HDK_Utilities.h:21).
  * ===================================================================================================================== */
 enum { MAT_SOLID = 0, MAT_LIQUID = 1, MAT_AIR = 2 };

@@ -21,6 +21,15 @@
 #include "HDK_GeometricMultigridOperators.h"
 #include "HDK_GeometricMultigridPoissonSolver.h"
 #include "HDK_Utilities.h"
+// the node's own source (HDK_GeometricFreeSurfacePressureSolver.cpp, compiled unmodified over shim/hdk_node_shim.h): its builders
+// are private members, so this translation unit -- test infrastructure -- reads the class declaration with every member public.
+// Everything the header pulls in has been included above already, so the two macros touch nothing but the class itself.
+#include "hdk_node_shim.h"
+#define private public
+#define protected public
+#include "HDK_GeometricFreeSurfacePressureSolver.h"
+#undef protected
+#undef private
 
 namespace Ops = HDK::GeometricMultigridOperators;
 using Real = double;
@@ -572,6 +581,196 @@ void ref_build_valid_faces(const int32_t *material, const float *cutCell, const 
     HDK::Utilities::uncompressTiles(valid, isTileOccupiedList);
     HDK::Utilities::classifyValidFaces(valid, labels, cut, isLiquid, axis);
     fromVoxels(validFaces, *valid.field());
+}
+// ---- the node's own functions (HDK_GeometricFreeSurfacePressureSolver.cpp:746-1131 and solveGasSubclass :113-714), unmodified ------
+// Fields live on one unit-spaced lattice: cell fields x-fastest [rz][ry][rx], the face field of axis a with one more entry along a.
+namespace
+{
+using Node = HDK_GeometricFreeSurfacePressureSolver;
+void cellField(SIM_RawField &f, const float *src, const int64_t res[3])
+{
+    f.init(int(res[0]), int(res[1]), int(res[2]));
+    if (src) toVoxels(*f.fieldNC(), src, res);
+}
+void faceField(SIM_RawField &f, const float *src, const int64_t res[3], int axis)
+{
+    f.init(SIM_FieldSample(SIM_SAMPLE_FACEX + axis), UT_Vector3(0, 0, 0), UT_Vector3(float(res[0]), float(res[1]), float(res[2])), int(res[0]), int(res[1]), int(res[2]));
+    int64_t fr[3];
+    faceRes(fr, res, axis);
+    if (src) toVoxels(*f.fieldNC(), src, fr);
+}
+void vectorField(SIM_VectorField &v, const float *const src[3], const int64_t res[3])
+{
+    v.initFaces(int(res[0]), int(res[1]), int(res[2]));
+    for (int a = 0; a < 3; ++a)
+    {
+	int64_t fr[3];
+	faceRes(fr, res, a);
+	if (src && src[a]) toVoxels(*v.getField(a)->fieldNC(), src[a], fr);
+    }
+}
+void indexField(SIM_RawIndexField &f, const int32_t *src, const int64_t res[3])
+{
+    std::vector<exint> wide(size_t(res[0]) * res[1] * res[2]);
+    for (size_t i = 0; i < wide.size(); ++i) wide[i] = src[i];
+    toVoxels(*f.fieldNC(), wide.data(), res);
+}
+} // namespace
+
+// buildMGDomainLabels, :746-793 (the label grid starts as EXTERIOR, :309)
+void ref_node_domain_labels(const int32_t *material, const int64_t res[3], int32_t *labels)
+{
+    Node node(nullptr);
+    SIM_RawIndexField mat;
+    indexField(mat, material, res);
+    UT_VoxelArray<int> out;
+    out.size(int(res[0]), int(res[1]), int(res[2]));
+    out.constant(Ops::CellLabels::EXTERIOR_CELL);
+    node.buildMGDomainLabels(out, mat);
+    fromVoxels(labels, out);
+}
+// buildMGBoundaryWeights, :796-865, one axis (the weight grid starts as 0, :322)
+void ref_node_boundary_weights(const float *cutCell, const float *liquidSurface, const float *validFaces, const int32_t *material, const int32_t *domainLabels,
+			       const int64_t res[3], int axis, double *weights)
+{
+    Node node(nullptr);
+    SIM_RawField cut, liquid, valid;
+    faceField(cut, cutCell, res, axis);
+    faceField(valid, validFaces, res, axis);
+    cellField(liquid, liquidSurface, res);
+    SIM_RawIndexField mat;
+    indexField(mat, material, res);
+    UT_VoxelArray<int> labels;
+    toVoxels(labels, domainLabels, res);
+    int64_t fr[3];
+    faceRes(fr, res, axis);
+    UT_VoxelArray<double> w;
+    w.size(int(fr[0]), int(fr[1]), int(fr[2]));
+    w.constant(0);
+    node.buildMGBoundaryWeights(w, cut, liquid, valid, mat, labels, axis);
+    fromVoxels(weights, w);
+}
+// buildRHS, :868-943: rhs is the expanded grid (zero on entry, :385); expLabels the expanded labels WITH their BOUNDARY cells set
+void ref_node_rhs(const int32_t *material, const float *const velocity[3], const float *const cutCell[3], const float *const solidVelocity[3], const int64_t res[3],
+		  const int32_t *expLabels, const int64_t expRes[3], const int64_t offset[3], double *rhs)
+{
+    Node node(nullptr);
+    SIM_RawIndexField mat;
+    indexField(mat, material, res);
+    SIM_VectorField vel, solidVel;
+    vectorField(vel, velocity, res);
+    if (solidVelocity) vectorField(solidVel, solidVelocity, res);
+    SIM_RawField cut[3];
+    for (int a = 0; a < 3; ++a) faceField(cut[a], cutCell[a], res, a);
+    const std::array<const SIM_RawField *, 3> cutCellWeights = {&cut[0], &cut[1], &cut[2]};
+    UT_VoxelArray<int> labels;
+    toVoxels(labels, expLabels, expRes);
+    UT_VoxelArray<double> grid;
+    grid.size(int(expRes[0]), int(expRes[1]), int(expRes[2]));
+    grid.constant(0);
+    node.buildRHS(grid, mat, vel, solidVelocity ? &solidVel : nullptr, cutCellWeights, labels, UT_Vector3I(offset[0], offset[1], offset[2]));
+    fromVoxels(rhs, grid);
+}
+// applyOldPressure, :946-997 (the solution grid starts as 0, :398)
+void ref_node_old_pressure(const float *pressure, const int32_t *material, const int64_t res[3], const int32_t *expLabels, const int64_t expRes[3], const int64_t offset[3],
+			   double *solution)
+{
+    Node node(nullptr);
+    SIM_RawIndexField mat;
+    indexField(mat, material, res);
+    SIM_RawField pr;
+    cellField(pr, pressure, res);
+    UT_VoxelArray<int> labels;
+    toVoxels(labels, expLabels, expRes);
+    UT_VoxelArray<double> grid;
+    grid.size(int(expRes[0]), int(expRes[1]), int(expRes[2]));
+    grid.constant(0);
+    node.applyOldPressure(grid, pr, mat, labels, UT_Vector3I(offset[0], offset[1], offset[2]));
+    fromVoxels(solution, grid);
+}
+// applySolutionToPressure, :1000-1047: pressure in / out (only LIQUID cells are written)
+void ref_node_solution_to_pressure(float *pressure, const int32_t *material, const double *solution, const int64_t res[3], const int32_t *expLabels,
+				   const int64_t expRes[3], const int64_t offset[3])
+{
+    Node node(nullptr);
+    SIM_RawIndexField mat;
+    indexField(mat, material, res);
+    SIM_RawField pr;
+    cellField(pr, pressure, res);
+    UT_VoxelArray<int> labels;
+    toVoxels(labels, expLabels, expRes);
+    UT_VoxelArray<double> grid;
+    toVoxels(grid, solution, expRes);
+    node.applySolutionToPressure(pr, mat, labels, grid, UT_Vector3I(offset[0], offset[1], offset[2]));
+    fromVoxels(pressure, *pr.field());
+}
+// applyPressureGradient, :1050-1131, one axis: velocity in / out
+void ref_node_pressure_gradient(float *velocity, const float *cutCell, const float *liquidSurface, const float *pressure, const float *validFaces, const int32_t *material,
+				const int64_t res[3], int axis)
+{
+    Node node(nullptr);
+    SIM_RawField vel, cut, liquid, pr, valid;
+    faceField(vel, velocity, res, axis);
+    faceField(cut, cutCell, res, axis);
+    faceField(valid, validFaces, res, axis);
+    cellField(liquid, liquidSurface, res);
+    cellField(pr, pressure, res);
+    SIM_RawIndexField mat;
+    indexField(mat, material, res);
+    node.applyPressureGradient(vel, cut, liquid, pr, valid, mat, axis);
+    fromVoxels(velocity, *vel.field());
+}
+// The whole node: solveGasSubclass, :113-714 -- fields in, one pressure projection (production wiring: tiled Gauss-Seidel V-cycle as the
+// preconditioner, :463-466, or the diagonal one), pressure / velocity / validFaces out.  solidSurface, solidVelocity, pressure may be
+// null (the node then takes "no solid", no solid motion, a local zero pressure).  Returns 1 if the node reported success; its log goes
+// to `log` (truncated to logCap).
+int ref_node_solve(const float *liquidSurface, const float *solidSurface, float *const velocity[3], const float *const cutCell[3], const float *const solidVelocity[3],
+		   float *pressure, float *const validFaces[3], float density, const int64_t res[3], double tolerance, int maxIterations, int useMGPreconditioner,
+		   int useOldPressure, char *log, int logCap)
+{
+    Node node(nullptr);
+    node.options[SIM_NAME_TOLERANCE] = tolerance;
+    node.options["maxIterations"] = maxIterations;
+    node.options["useMGPreconditioner"] = useMGPreconditioner;
+    node.options["useOldPressure"] = useOldPressure;
+    SIM_ScalarField surface, solid, pr, dens;
+    SIM_VectorField vel, cut, solidVel, valid;
+    cellField(*surface.getField(), liquidSurface, res);
+    cellField(*dens.getField(), nullptr, res);
+    dens.getField()->makeConstant(density);
+    vectorField(vel, velocity, res);
+    vectorField(cut, cutCell, res);
+    vectorField(valid, nullptr, res);
+    SIM_Object obj;
+    obj.scalarFields[GAS_NAME_SURFACE] = &surface;
+    obj.scalarFields[GAS_NAME_DENSITY] = &dens;
+    obj.vectorFields[GAS_NAME_VELOCITY] = &vel;
+    obj.vectorFields["cutCellWeights"] = &cut;
+    obj.vectorFields["validFaces"] = &valid;
+    if (solidSurface) { cellField(*solid.getField(), solidSurface, res); obj.scalarFields[GAS_NAME_COLLISION] = &solid; }
+    if (solidVelocity) { vectorField(solidVel, solidVelocity, res); obj.vectorFields[GAS_NAME_COLLISIONVELOCITY] = &solidVel; }
+    cellField(*pr.getField(), pressure, res);
+    obj.scalarFields[GAS_NAME_PRESSURE] = &pr;
+    SIM_Engine engine;
+    std::ostringstream captured;
+    std::streambuf *old = std::cout.rdbuf(captured.rdbuf());
+    const bool ok = node.solveGasSubclass(engine, &obj, 0, 1. / 24.);
+    std::cout.rdbuf(old);
+    std::string text = captured.str();
+    for (const std::string &e : obj.errors) text += "ERROR: " + e + "\n";
+    if (log && logCap > 0)
+    {
+	const size_t n = std::min(text.size(), size_t(logCap - 1));
+	std::memcpy(log, text.data() + (text.size() - n), n);  // the tail holds the iteration count and the divergence check
+	log[n] = 0;
+    }
+    fromVoxels(pressure, *pr.getField()->field());
+    for (int a = 0; a < 3; ++a)
+    {
+	fromVoxels(velocity[a], *vel.getField(a)->field());
+	fromVoxels(validFaces[a], *valid.getField(a)->field());
+    }
+    return ok ? 1 : 0;
 }
 // bench.py --impl reference: use every host core even when the launcher (torchrun) exported OMP_NUM_THREADS=1
 void ref_set_threads(int n)

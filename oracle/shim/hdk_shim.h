@@ -78,6 +78,7 @@ public:
 
     bool operator==(const UT_Vector3T &o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2]; }
     bool operator!=(const UT_Vector3T &o) const { return !(*this == o); }
+    T maxComponent() const { return std::max(v[0], std::max(v[1], v[2])); }
 
 private:
     T v[3];
@@ -384,6 +385,14 @@ public:
 											  std::min(GMG_TILESIZE, z - tz * GMG_TILESIZE));
     }
     void constant(T v) { for (auto &t : myTiles) t.makeConstant(v); }
+    // every tile constant-compressed with one and the same value
+    bool isConstant(T *cval = nullptr) const
+    {
+	for (const auto &t : myTiles)
+	    if (!t.isConstant() || !(t.constantValue() == myTiles[0].constantValue())) return false;
+	if (cval && !myTiles.empty()) *cval = myTiles[0].constantValue();
+	return true;
+    }
 
     UT_Vector3I getVoxelRes() const { return UT_Vector3I(myRes[0], myRes[1], myRes[2]); }
     int getXRes() const { return myRes[0]; }
@@ -644,10 +653,10 @@ private:
 
 // ---------------------------------------------------------------- SIM_RawField / SIM_RawIndexField
 // The slice HDK_Utilities.{h,cpp} uses (buildMaterialCellLabels, classifyValidFaces, ...): a voxel array of fpreal32 / exint
-// with a resolution, tile access and -- SIM_RawField only -- a CELL-SAMPLED position map on the unit-spaced lattice
-// (indexToPos = index + 0.5) with trilinear getValue(pos), clamped at the border.  At a cell centre the interpolation weights
-// are exactly 0 and 1, so getValue(indexToPos(cell)) is the cell's own value: the aligned-fields case the product's entry point
-// documents (gmg_build_material_labels).
+// with a resolution, tile access and -- SIM_RawField only -- a sample type (cell centres, or the faces of one axis), the box its
+// cell lattice spans, indexToPos and a trilinear getValue(pos) clamped at the border.  At a sample position the interpolation
+// weights are exactly 0 and 1, so getValue(indexToPos(cell)) of an ALIGNED field is that field's own value: the case the
+// product's entry points document (gmg_build_material_labels, gmg_build_rhs).
 using UT_VoxelArrayF = UT_VoxelArray<fpreal32>;
 using UT_VoxelArrayI = UT_VoxelArray<exint>;
 using UT_VoxelArrayIteratorF = UT_VoxelArrayIterator<fpreal32>;
@@ -655,40 +664,74 @@ using UT_VoxelArrayIteratorI = UT_VoxelArrayIterator<exint>;
 using UT_VoxelTileIteratorF = UT_VoxelTileIterator<fpreal32>;
 using UT_VoxelTileIteratorI = UT_VoxelTileIterator<exint>;
 
+enum SIM_FieldSample { SIM_SAMPLE_CENTER = 0, SIM_SAMPLE_FACEX, SIM_SAMPLE_FACEY, SIM_SAMPLE_FACEZ };
+
 class SIM_RawField
 {
 public:
-    void init(int x, int y, int z) { myField.size(x, y, z); myField.constant(0); }
-    void match(const SIM_RawField &o) { const UT_Vector3I r = o.getVoxelRes(); init(int(r[0]), int(r[1]), int(r[2])); }
+    // (x, y, z) = resolution of the CELL lattice; a face-sampled field has one more entry along its axis.  orig / size: the box
+    // the cell lattice spans (default: the unit-spaced lattice starting at 0).
+    void init(SIM_FieldSample sample, const UT_Vector3 &orig, const UT_Vector3 &size, int x, int y, int z)
+    {
+	mySample = sample;
+	myOrig = orig;
+	mySize = size;
+	myCells = UT_Vector3I(x, y, z);
+	const int fa = faceAxis();
+	myField.size(x + (fa == 0), y + (fa == 1), z + (fa == 2));
+	myField.constant(0);
+    }
+    void init(int x, int y, int z) { init(SIM_SAMPLE_CENTER, UT_Vector3(0, 0, 0), UT_Vector3(fpreal32(x), fpreal32(y), fpreal32(z)), x, y, z); }
+    void match(const SIM_RawField &o) { init(o.mySample, o.myOrig, o.mySize, int(o.myCells[0]), int(o.myCells[1]), int(o.myCells[2])); }
     void makeConstant(fpreal32 v) { myField.constant(v); }
+    // the resolution of the voxel array itself
     UT_Vector3I getVoxelRes() const { return myField.getVoxelRes(); }
     const UT_VoxelArrayF *field() const { return &myField; }
     UT_VoxelArrayF *fieldNC() { return &myField; }
+    SIM_FieldSample getSample() const { return mySample; }
+    const UT_Vector3 &getOrig() const { return myOrig; }
+    const UT_Vector3 &getSize() const { return mySize; }
+    UT_Vector3 getVoxelSize() const { return UT_Vector3(mySize[0] / fpreal32(myCells[0]), mySize[1] / fpreal32(myCells[1]), mySize[2] / fpreal32(myCells[2])); }
+    bool isAligned(const SIM_RawField *o) const
+    {
+	return mySample == o->mySample && myCells == o->myCells && myOrig == o->myOrig && mySize == o->mySize;
+    }
+    // centre samples sit at (index + 0.5) dx, the samples of a face field at index dx along its own axis
     bool indexToPos(int x, int y, int z, UT_Vector3 &pos) const
     {
-	pos = UT_Vector3(fpreal32(x) + 0.5f, fpreal32(y) + 0.5f, fpreal32(z) + 0.5f);
+	const UT_Vector3 dx = getVoxelSize();
+	const int idx[3] = {x, y, z};
+	const int fa = faceAxis();
+	for (int a = 0; a < 3; ++a) pos[a] = myOrig[a] + (fpreal32(idx[a]) + (a == fa ? 0.f : 0.5f)) * dx[a];
 	return true;
     }
+    // trilinear, clamped at the border; at a sample position the weights are exactly 0 and 1
     fpreal32 getValue(const UT_Vector3 &pos) const
     {
 	int i0[3];
 	fpreal32 f[3];
 	const UT_Vector3I r = getVoxelRes();
+	const UT_Vector3 dx = getVoxelSize();
+	const int fa = faceAxis();
 	for (int a = 0; a < 3; ++a)
 	{
-	    fpreal32 p = pos[a] - 0.5f;
+	    fpreal32 p = (pos[a] - myOrig[a]) / dx[a] - (a == fa ? 0.f : 0.5f);
 	    p = p < 0 ? 0 : (p > fpreal32(r[a] - 1) ? fpreal32(r[a] - 1) : p);
 	    i0[a] = int(p);
 	    f[a] = p - fpreal32(i0[a]);
 	}
-	auto at = [&](int dx, int dy, int dz) { return myField(i0[0] + dx, i0[1] + dy, i0[2] + dz); };  // clamped read
+	auto at = [&](int ddx, int ddy, int ddz) { return myField(i0[0] + ddx, i0[1] + ddy, i0[2] + ddz); };  // clamped read
 	auto lerp = [](fpreal32 v0, fpreal32 v1, fpreal32 t) { return (1 - t) * v0 + t * v1; };
 	return lerp(lerp(lerp(at(0, 0, 0), at(1, 0, 0), f[0]), lerp(at(0, 1, 0), at(1, 1, 0), f[0]), f[1]),
 		    lerp(lerp(at(0, 0, 1), at(1, 0, 1), f[0]), lerp(at(0, 1, 1), at(1, 1, 1), f[0]), f[1]), f[2]);
     }
 
 private:
+    int faceAxis() const { return mySample == SIM_SAMPLE_CENTER ? -1 : int(mySample) - int(SIM_SAMPLE_FACEX); }
     UT_VoxelArrayF myField;
+    SIM_FieldSample mySample = SIM_SAMPLE_CENTER;
+    UT_Vector3 myOrig = UT_Vector3(0, 0, 0), mySize = UT_Vector3(1, 1, 1);
+    UT_Vector3I myCells = UT_Vector3I(1, 1, 1);
 };
 
 class SIM_RawIndexField

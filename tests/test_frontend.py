@@ -2,9 +2,9 @@
 (HDK_GeometricFreeSurfacePressureSolver.cpp:717-744), buildMGDomainLabels, buildMGBoundaryWeights, buildRHS, applyOldPressure,
 applySolutionToPressure, applyPressureGradient (HDK_GeometricFreeSurfacePressureSolver.cpp:746-1131).
 
-buildMaterialCellLabels / buildValidFaces are PINNED: HDK_Utilities.{h,cpp} compile unmodified over the shim's SIM_RawField, the C
-restatement is held to them (tests/test_oracle_vs_reference.py) and to a fixture generated from them (tests/golden/frontend_fields.npz).
-The other six are PARITY UNPINNED at the reference: GFS.cpp needs the node class and live SIM fields and cannot be compiled here.  What is checked:
+All eight are PINNED to the reference's own sources: HDK_Utilities.{h,cpp} and HDK_GeometricFreeSurfacePressureSolver.cpp compile unmodified
+over the shim (oracle/shim/hdk_node_shim.h), the C restatement is held to them bit for bit (tests/test_oracle_vs_reference.py,
+tests/test_node_reference.py) and to fixtures generated from them (tests/golden/frontend_fields.npz, node_projection.npz).  What is checked here:
   CPU  the C restatement (oracle/gmg_oracle.c) against an independent vectorised numpy restatement of the same lines;
   GPU  the CUDA kernels (csrc/gmg_frontend.cuh, through the C ABI) against the C restatement: labels bit-exact, fpreal32 outputs
        bit-exact, fp64 outputs to 1e-14 (fused multiply-adds), and the whole chain fields -> labels/weights/rhs -> MGPCG ->
