@@ -20,6 +20,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libgmg_ref.so")
 REF_DBG_SO = os.path.join(HERE, "_ref", "libgmg_ref_dbg.so")
+REF_TESTNODE_SO = os.path.join(HERE, "_ref", "libgmg_ref_testnode.so")
 PORT_SO = os.path.join(HERE, "libgmg_oracle.so")
 
 _i64p = C.POINTER(C.c_int64)
@@ -595,3 +596,21 @@ class _PortSolver:
             self.close()
         except Exception:
             pass
+
+
+class TestNodeLib:
+    """The reference's own diagnostic node (HDK_TestGeometricMultigrid.cpp, compiled unmodified): options in, its log out."""
+
+    __test__ = False  # not a pytest class
+
+    def __init__(self):
+        self.lib = C.CDLL(REF_TESTNODE_SO)
+        self.lib.ref_testnode_set_threads(int(os.cpu_count() or 1))
+
+    def run(self, **options):
+        """options: the node's DOP parameters (HDK_TestGeometricMultigrid.h:10-35), e.g. gridSize=32, useComplexDomain=1, testSymmetry=1."""
+        text = ";".join(f"{k}={float(v)!r}" for k, v in options.items())
+        buf = C.create_string_buffer(1 << 20)
+        ok = self.lib.ref_testnode_run(text.encode(), buf, len(buf))
+        return bool(ok), buf.value.decode(errors="replace")
+

@@ -14,6 +14,7 @@
 #define GMG_ORACLE_HDK_NODE_SHIM_H
 
 #include <map>
+#include <random>
 #include <string>
 
 #include "hdk_shim.h"
@@ -81,7 +82,12 @@ enum { SIM_MESSAGE = 0 };
 enum UT_ErrorSeverity { UT_ERROR_NONE = 0, UT_ERROR_MESSAGE, UT_ERROR_PROMPT, UT_ERROR_WARNING, UT_ERROR_ABORT, UT_ERROR_FATAL };
 
 // ---------------------------------------------------------------- parameter description (inert)
-enum PRM_Type { PRM_STRING, PRM_TOGGLE, PRM_FLT, PRM_INT };
+enum PRM_Type { PRM_STRING, PRM_TOGGLE, PRM_FLT, PRM_INT, PRM_SEPARATOR };
+class PRM_Conditional
+{
+public:
+    PRM_Conditional(const char * = nullptr) {}
+};
 class PRM_Name
 {
 public:
@@ -93,11 +99,16 @@ public:
     PRM_Default(fpreal = 0, const char * = nullptr) {}
 };
 static PRM_Default PRMoneDefaults[1] = {PRM_Default(1)};
+static PRM_Default PRMzeroDefaults[1] = {PRM_Default(0)};
 class PRM_Template
 {
 public:
     PRM_Template() {}
-    PRM_Template(PRM_Type, int, PRM_Name *, PRM_Default * = nullptr) {}
+    // (type, vector size, name, defaults, choice list, range, callback, spare data, parameter group, help text, conditional)
+    PRM_Template(PRM_Type, int, PRM_Name *, PRM_Default * = nullptr, void * = nullptr, void * = nullptr, void * = nullptr, void * = nullptr, int = 1,
+		 const char * = nullptr, PRM_Conditional * = nullptr)
+    {
+    }
 };
 class SIM_DopDescription
 {

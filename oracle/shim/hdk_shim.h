@@ -705,6 +705,13 @@ public:
 	for (int a = 0; a < 3; ++a) pos[a] = myOrig[a] + (fpreal32(idx[a]) + (a == fa ? 0.f : 0.5f)) * dx[a];
 	return true;
     }
+    // HDK: cut-cell face fractions of an SDF -- a geometric routine of the HDK that is not restated.  Only the diagnostic node's solid-sphere
+    // option calls it (HDK_TestGeometricMultigrid.cpp:320), which the oracle never enables.
+    void computeSDFWeightsFace(const SIM_RawField *, int, bool, fpreal = 0)
+    {
+	std::cerr << "hdk_shim: SIM_RawField::computeSDFWeightsFace is not available (useSolidSphere is off-path)" << std::endl;
+	std::abort();
+    }
     // trilinear, clamped at the border; at a sample position the weights are exactly 0 and 1
     fpreal32 getValue(const UT_Vector3 &pos) const
     {

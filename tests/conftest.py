@@ -34,6 +34,18 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def testnode():
+    """The reference's own diagnostic node (HDK_TestGeometricMultigrid.cpp over the shim); only where oracle/_ref was built."""
+    from oracle import bindings
+
+    if os.path.isdir("/root/reference/Source"):
+        bindings.build(ref=True)
+    if not os.path.exists(bindings.REF_TESTNODE_SO):
+        pytest.skip("oracle/_ref/libgmg_ref_testnode.so not present (built only where /root/reference exists)")
+    return bindings.TestNodeLib()
+
+
+@pytest.fixture(scope="session")
 def gpu_ctx():
     from geometricmultigridpressuresolver_b200 import api
 

@@ -87,6 +87,24 @@ def node_fixture():
     np.savez_compressed(os.path.join(HERE, "node_projection.npz"), **out)
 
 
+def testnode_fixture():
+    """tests/golden/reference_testnode.json: what the reference's own diagnostic node (HDK_TestGeometricMultigrid.cpp, compiled unmodified)
+    prints for its MGPCG test on its own domains: iteration count and relative-residual history (ten digits)."""
+    import json
+
+    from oracle.bindings import TestNodeLib
+    from tests.test_reference_testnode import CG_CASES, FIXTURE, node_cg
+
+    node = TestNodeLib()
+    out = {}
+    for dom, n in CG_CASES:
+        it, hist = node_cg(node, dom, n)
+        out[f"{dom}{n}"] = {"iterations": it, "history": hist}
+        print(dom, n, "iterations", it, "final", hist[-1])
+    json.dump(out, open(FIXTURE, "w"), indent=1)
+
+
 if __name__ == "__main__":
     main()
     node_fixture()
+    testnode_fixture()
