@@ -7,6 +7,8 @@ oracle/_ref/libgmg_ref_testnode.so -- run as its author runs it inside Houdini (
   * its MGPCG test (Test.cpp:675-1010: its own buildSimpleDomain / buildComplexDomain, its own delta right-hand side, tiled Gauss-Seidel
     V-cycle as the preconditioner) against the C restatement on domains.py's re-creation of those domains: same iteration count, the printed
     residual history to its ten digits.  This pins the synthetic input generators every other test builds on.
+  * its smoother test (Test.cpp:1962-2105: band sweeps around a damped-Jacobi or a four-half-pass tiled Gauss-Seidel interior sweep) against the
+    same sequence of restated operators: the printed residual norms, round by round.
   * tests/golden/reference_testnode.json keeps what the node printed, for the boxes without /root/reference (CPU: the restatement; GPU: the
     CUDA path in Gauss-Seidel mode)."""
 import json
@@ -89,3 +91,32 @@ def test_gpu_against_the_stored_log_of_the_reference_cg_test(gpu_ctx, dom, n):
     assert abs(it - stored["iterations"]) <= 1
     m = min(len(hist), len(stored["history"]))
     assert m > 0 and max(abs(a - c) / a for a, c in zip(stored["history"][:m], hist[:m])) < 1e-5  # the north_star's bar
+
+
+@pytest.mark.parametrize("dom,gs", [("simple", 0), ("complex", 0), ("complex", 1)])
+def test_the_reference_smoother_test_against_the_restatement(testnode, port, dom, gs):
+    """Test.cpp:1962-2105: 3 band sweeps, one interior sweep (damped Jacobi, or the four tiled Gauss-Seidel half-passes odd-forward,
+    even-forward, even-backward, odd-backward), 3 band sweeps, then the residual's max (clamped at 0: the infNorm quirk) and L2 norm -- six
+    rounds on the node's own domain and delta right-hand side, against the same sequence of restated operators."""
+    n, rounds = 32, 6
+    ok, log = testnode.run(gridSize=n, useComplexDomain=int(dom == "complex"), testSmoother=1, maxSmootherIterations=rounds, useGaussSeidelSmoothing=gs,
+                           deltaFunctionAmplitude=AMPLITUDE)
+    assert ok, log[-2000:]
+    inf_node = [float(v) for v in re.findall(r"L-infinity norm: ([-+.\deE]+)", log)]
+    l2_node = [float(v) for v in re.findall(r"L-2 norm: ([-+.\deE]+)", log)]
+    assert len(inf_node) == rounds == len(l2_node)
+    labels, w, levels, b = delta_problem(port.expand_domain, dom, n)
+    cells = port.boundary_cells(labels, 3)
+    x = np.zeros_like(b)
+    for k in range(rounds):
+        x = port.boundary_jacobi(x, b, labels, cells, 3, w)
+        if gs:
+            for odd, forward in ((True, True), (False, True), (False, False), (True, False)):
+                x = port.gauss_seidel(x, b, labels, odd, forward, w)
+        else:
+            x = port.jacobi(x, b, labels, w)
+        x = port.boundary_jacobi(x, b, labels, cells, 3, w)
+        r = port.residual(x, b, labels, w)
+        assert abs(port.inf_norm(r, labels) - inf_node[k]) <= 2e-9 * inf_node[k], k
+        assert abs(np.sqrt(port.norm2(r, labels)) - l2_node[k]) <= 2e-9 * l2_node[k], k
+    assert l2_node[-1] < l2_node[0]
