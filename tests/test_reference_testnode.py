@@ -9,6 +9,8 @@ oracle/_ref/libgmg_ref_testnode.so -- run as its author runs it inside Houdini (
     residual history to its ten digits.  This pins the synthetic input generators every other test builds on.
   * its smoother test (Test.cpp:1962-2105: band sweeps around a damped-Jacobi or a four-half-pass tiled Gauss-Seidel interior sweep) against the
     same sequence of restated operators: the printed residual norms, round by round.
+  * its V-cycle convergence test (Test.cpp:1877-1960: fifty damped-Jacobi V-cycles with useInitialGuess from a sinusoid, zero right-hand side)
+    and its diagonally preconditioned CG branch, likewise.
   * tests/golden/reference_testnode.json keeps what the node printed, for the boxes without /root/reference (CPU: the restatement; GPU: the
     CUDA path in Gauss-Seidel mode)."""
 import json
@@ -120,3 +122,45 @@ def test_the_reference_smoother_test_against_the_restatement(testnode, port, dom
         assert abs(port.inf_norm(r, labels) - inf_node[k]) <= 2e-9 * inf_node[k], k
         assert abs(np.sqrt(port.norm2(r, labels)) - l2_node[k]) <= 2e-9 * l2_node[k], k
     assert l2_node[-1] < l2_node[0]
+
+
+@pytest.mark.parametrize("dom", ["simple", "complex"])
+def test_the_reference_vcycle_convergence_test_against_the_restatement(testnode, port, dom):
+    """Test.cpp:1877-1960: fifty damped-Jacobi V-cycles with `useInitialGuess` on a zero right-hand side, from the node's two-mode sinusoid
+    (its cell positions are fpreal32: dx times the EXPANDED cell index), printing max(x, 0) and the L2 norm after each one -- the north_star's
+    smoother mode in the reference's own convergence test."""
+    n = 32
+    ok, log = testnode.run(gridSize=n, useComplexDomain=int(dom == "complex"), testOneLevelVCycle=1)
+    assert ok, log[-2000:]
+    inf_node = [float(v) for v in re.findall(r"L-infinity norm: ([-+.\deE]+)", log)]
+    l2_node = [float(v) for v in re.findall(r"L-2 norm: ([-+.\deE]+)", log)]
+    assert len(inf_node) == 51 == len(l2_node)  # the initial guess, then fifty cycles
+    bl, bw, dx = D.DOMAINS[dom](n)
+    labels, w, off, levels = port.expand_domain(bl, bw)
+    active = D.active_mask(labels)
+    k, j, i = np.meshgrid(*[np.arange(s) for s in labels.shape], indexing="ij")
+    px, py, pz = [(dx * a).astype(np.float32).astype(np.float64) for a in (i, j, k)]
+    guess = np.sin(2 * np.pi * px) * np.sin(2 * np.pi * py) * np.sin(2 * np.pi * pz) + np.sin(4 * np.pi * px) * np.sin(4 * np.pi * py) * np.sin(4 * np.pi * py)
+    x = np.where(active, guess, 0.0)
+    s = port.solver(labels, w, levels, False)
+    zero = np.zeros_like(x)
+    for it in range(51):
+        if it:
+            x = s.vcycle(x, zero, True)
+        assert abs(port.inf_norm(x, labels) - inf_node[it]) <= 5e-9 * inf_node[0], it
+        assert abs(np.sqrt(port.norm2(x, labels)) - l2_node[it]) <= 5e-9 * l2_node[0], it
+    assert l2_node[-1] < 1e-6 * l2_node[0]
+
+
+@pytest.mark.parametrize("dom,n", [("simple", 16), ("complex", 24)])
+def test_the_reference_diagonal_cg_test_against_the_restatement(testnode, port, dom, n):
+    """The node's other CG branch (Test.cpp:838-1010, useMultigridPreconditioner off): its own diagonal preconditioner."""
+    ok, log = testnode.run(gridSize=n, useComplexDomain=int(dom == "complex"), testConjugateGradient=1, useMultigridPreconditioner=0, solveCGGeometrically=1,
+                           solverTolerance=TOL, maxSolverIterations=MAX_IT, deltaFunctionAmplitude=AMPLITUDE)
+    assert ok, log[-2000:]
+    hist_node = [float(v) for v in re.findall(r"Relative error: ([-+.\deE]+)", log)]
+    it_node = int(re.findall(r"Iterations: (\d+)", log)[-1])
+    labels, w, levels, b = delta_problem(port.expand_domain, dom, n)
+    x, it, hist = port.solver(labels, w, levels, True).pcg(np.zeros_like(b), b, TOL, MAX_IT, diagonal=True)
+    assert it == it_node and len(hist) == len(hist_node)
+    assert max(abs(a - c) / c for a, c in zip(hist_node, hist)) < 1e-7  # a hundred CG steps amplify the last printed digit
