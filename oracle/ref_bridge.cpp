@@ -534,56 +534,6 @@ int ref_pcg_diag(RefSolver *s, double *x, const double *b, double tol, int maxIt
 {
     return refPcgImpl(s, x, b, tol, maxIt, 2, history, histCap, histCount, solveSeconds);
 }
-// ---- the steps in front of the solve whose reference source compiles here: HDK_Utilities.{h,cpp}, unmodified ----------------
-// buildMaterialCellLabels, HDK_Utilities.cpp:87-148 (isCellLiquid :5-45).  Fields are cell-sampled on one lattice (oracle/shim:
-// SIM_RawField), so solidSurface.getValue(indexToPos(cell)) is the solid field's own cell value.
-void ref_build_material_labels(const float *liquidSurface, const float *solidSurface, const float *cut0, const float *cut1, const float *cut2, const int64_t res[3],
-			       int32_t *material)
-{
-    SIM_RawField liquid, solid, cut[3];
-    toVoxels(*liquid.fieldNC(), liquidSurface, res);
-    toVoxels(*solid.fieldNC(), solidSurface, res);
-    const float *cs[3] = {cut0, cut1, cut2};
-    for (int a = 0; a < 3; ++a)
-    {
-	int64_t fr[3] = {res[0], res[1], res[2]};
-	++fr[a];
-	toVoxels(*cut[a].fieldNC(), cs[a], fr);
-    }
-    SIM_RawIndexField labels;
-    const std::array<const SIM_RawField *, 3> cutCellWeights = {&cut[0], &cut[1], &cut[2]};
-    HDK::Utilities::buildMaterialCellLabels(labels, liquid, solid, cutCellWeights);
-    std::vector<exint> wide(size_t(res[0]) * res[1] * res[2]);
-    fromVoxels(wide.data(), *labels.field());
-    for (size_t i = 0; i < wide.size(); ++i) material[i] = int32_t(wide[i]);
-}
-// buildValidFaces for one axis: the call sequence of HDK_GeometricFreeSurfacePressureSolver.cpp:717-744 (that file needs the node
-// class and cannot be compiled) over the reference's own templates findOccupiedFaceTiles, uncompressTiles, classifyValidFaces
-// (HDK_Utilities.h:78-189).  Release build only: the templates assert equal resolutions of the cell and the face field.
-void ref_build_valid_faces(const int32_t *material, const float *cutCell, const int64_t res[3], int axis, float *validFaces)
-{
-    using MaterialLabels = HDK::Utilities::FreeSurfaceMaterialLabels;
-    std::vector<exint> wide(size_t(res[0]) * res[1] * res[2]);
-    for (size_t i = 0; i < wide.size(); ++i) wide[i] = material[i];
-    SIM_RawIndexField labels;
-    toVoxels(*labels.fieldNC(), wide.data(), res);
-    int64_t fr[3] = {res[0], res[1], res[2]};
-    ++fr[axis];
-    SIM_RawField cut, valid;
-    toVoxels(*cut.fieldNC(), cutCell, fr);
-    valid.init(int(fr[0]), int(fr[1]), int(fr[2]));
-    valid.makeConstant(HDK::Utilities::INVALID_FACE);
-    UT_Array<bool> isTileOccupiedList;
-    isTileOccupiedList.setSize(valid.field()->numTiles());
-    isTileOccupiedList.constant(false);
-    auto isLiquid = [](const exint label) { return label == MaterialLabels::LIQUID_CELL; };
-    HDK::Utilities::findOccupiedFaceTiles(isTileOccupiedList, valid, labels, isLiquid, axis);
-    HDK::Utilities::uncompressTiles(valid, isTileOccupiedList);
-    HDK::Utilities::classifyValidFaces(valid, labels, cut, isLiquid, axis);
-    fromVoxels(validFaces, *valid.field());
-}
-// ---- the node's own functions (HDK_GeometricFreeSurfacePressureSolver.cpp:746-1131 and solveGasSubclass :113-714), unmodified ------
-// Fields live on one unit-spaced lattice: cell fields x-fastest [rz][ry][rx], the face field of axis a with one more entry along a.
 namespace
 {
 using Node = HDK_GeometricFreeSurfacePressureSolver;
@@ -616,6 +566,50 @@ void indexField(SIM_RawIndexField &f, const int32_t *src, const int64_t res[3])
     toVoxels(*f.fieldNC(), wide.data(), res);
 }
 } // namespace
+
+// ---- the steps in front of the solve whose reference source compiles here: HDK_Utilities.{h,cpp}, unmodified ----------------
+// buildMaterialCellLabels, HDK_Utilities.cpp:87-148 (isCellLiquid :5-45).  Fields are cell-sampled on one lattice (oracle/shim:
+// SIM_RawField), so solidSurface.getValue(indexToPos(cell)) is the solid field's own cell value.
+void ref_build_material_labels(const float *liquidSurface, const float *solidSurface, const float *cut0, const float *cut1, const float *cut2, const int64_t res[3],
+			       int32_t *material)
+{
+    SIM_RawField liquid, solid, cut[3];
+    cellField(liquid, liquidSurface, res);
+    cellField(solid, solidSurface, res);
+    const float *cs[3] = {cut0, cut1, cut2};
+    for (int a = 0; a < 3; ++a) faceField(cut[a], cs[a], res, a);
+    SIM_RawIndexField labels;
+    const std::array<const SIM_RawField *, 3> cutCellWeights = {&cut[0], &cut[1], &cut[2]};
+    HDK::Utilities::buildMaterialCellLabels(labels, liquid, solid, cutCellWeights);
+    std::vector<exint> wide(size_t(res[0]) * res[1] * res[2]);
+    fromVoxels(wide.data(), *labels.field());
+    for (size_t i = 0; i < wide.size(); ++i) material[i] = int32_t(wide[i]);
+}
+// buildValidFaces for one axis: the call sequence of HDK_GeometricFreeSurfacePressureSolver.cpp:717-744 (that file needs the node
+// class and cannot be compiled) over the reference's own templates findOccupiedFaceTiles, uncompressTiles, classifyValidFaces
+// (HDK_Utilities.h:78-189).
+void ref_build_valid_faces(const int32_t *material, const float *cutCell, const int64_t res[3], int axis, float *validFaces)
+{
+    using MaterialLabels = HDK::Utilities::FreeSurfaceMaterialLabels;
+    std::vector<exint> wide(size_t(res[0]) * res[1] * res[2]);
+    for (size_t i = 0; i < wide.size(); ++i) wide[i] = material[i];
+    SIM_RawIndexField labels;
+    toVoxels(*labels.fieldNC(), wide.data(), res);
+    SIM_RawField cut, valid;
+    faceField(cut, cutCell, res, axis);
+    faceField(valid, nullptr, res, axis);
+    valid.makeConstant(HDK::Utilities::INVALID_FACE);
+    UT_Array<bool> isTileOccupiedList;
+    isTileOccupiedList.setSize(valid.field()->numTiles());
+    isTileOccupiedList.constant(false);
+    auto isLiquid = [](const exint label) { return label == MaterialLabels::LIQUID_CELL; };
+    HDK::Utilities::findOccupiedFaceTiles(isTileOccupiedList, valid, labels, isLiquid, axis);
+    HDK::Utilities::uncompressTiles(valid, isTileOccupiedList);
+    HDK::Utilities::classifyValidFaces(valid, labels, cut, isLiquid, axis);
+    fromVoxels(validFaces, *valid.field());
+}
+// ---- the node's own functions (HDK_GeometricFreeSurfacePressureSolver.cpp:746-1131 and solveGasSubclass :113-714), unmodified ------
+// Fields live on one unit-spaced lattice: cell fields x-fastest [rz][ry][rx], the face field of axis a with one more entry along a.
 
 // buildMGDomainLabels, :746-793 (the label grid starts as EXTERIOR, :309)
 void ref_node_domain_labels(const int32_t *material, const int64_t res[3], int32_t *labels)

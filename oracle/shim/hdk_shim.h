@@ -684,8 +684,9 @@ public:
     void init(int x, int y, int z) { init(SIM_SAMPLE_CENTER, UT_Vector3(0, 0, 0), UT_Vector3(fpreal32(x), fpreal32(y), fpreal32(z)), x, y, z); }
     void match(const SIM_RawField &o) { init(o.mySample, o.myOrig, o.mySize, int(o.myCells[0]), int(o.myCells[1]), int(o.myCells[2])); }
     void makeConstant(fpreal32 v) { myField.constant(v); }
-    // the resolution of the voxel array itself
-    UT_Vector3I getVoxelRes() const { return myField.getVoxelRes(); }
+    // HDK: "the resolution of the voxel grid that we are sampling" -- the CELL lattice, whatever the sample type (the reference asserts it equal
+    // between a cell field and a face field, HDK_Utilities.h:89, :148); the array itself (field()) has one more entry along a face field's axis
+    UT_Vector3I getVoxelRes() const { return myCells; }
     const UT_VoxelArrayF *field() const { return &myField; }
     UT_VoxelArrayF *fieldNC() { return &myField; }
     SIM_FieldSample getSample() const { return mySample; }
@@ -717,7 +718,7 @@ public:
     {
 	int i0[3];
 	fpreal32 f[3];
-	const UT_Vector3I r = getVoxelRes();
+	const UT_Vector3I r = myField.getVoxelRes();
 	const UT_Vector3 dx = getVoxelSize();
 	const int fa = faceAxis();
 	for (int a = 0; a < 3; ++a)
