@@ -237,3 +237,29 @@ def test_frontend_kernels_against_the_node_fixture(gpu_ctx):
 def test_projection_against_the_node_fixture(gpu_ctx, name):
     """The node's production wiring on the GPU: tiled Gauss-Seidel V-cycle inside the PCG, every step either side of it a CUDA kernel."""
     check_projection_against_fixture(GpuSteps(gpu_ctx), name, p_tol=1e-5, iteration_slack=1)
+
+
+def test_no_reference_assert_trips_on_the_fixture_fields():
+    """The same calls through oracle/_ref/libgmg_ref_dbg.so -- the reference's sources with their asserts LIVE (no NDEBUG): every precondition the
+    node checks on its own data (weights > 0 on valid faces, liquid / air pairing at the free surface, active labels under every liquid cell,
+    matching resolutions, ...) holds on the seeded fields these tests use."""
+    from oracle import bindings
+
+    if not os.path.exists(bindings.REF_DBG_SO):
+        pytest.skip("oracle/_ref/libgmg_ref_dbg.so not present (built only where /root/reference exists)")
+    dbg = bindings.RefLib(debug=True)
+    n, seed = NODE_BUILDERS_CASE
+    material, phi, cut, valid, vel, pressure = make_fields(n, seed)
+    bl = dbg.node_domain_labels(material)
+    bw = [dbg.node_boundary_weights(cut[a], phi, valid[a], material, bl, a) for a in range(3)]
+    labels, w, off, levels = dbg.expand_domain(bl, bw)
+    dbg.node_rhs(material, vel, cut, labels, off, [np.full_like(v, 0.25) for v in vel])
+    x = dbg.node_old_pressure(pressure, material, labels, off)
+    dbg.node_solution_to_pressure(pressure, material, x, labels, off)
+    for a in range(3):
+        dbg.node_pressure_gradient(vel[a], cut[a], phi, pressure, valid[a], material, a)
+        dbg.build_valid_faces(material, cut[a], a)
+    assert (dbg.build_material_labels(phi, np.full(phi.shape, -1.0, np.float32), cut) == material).all()
+    _, phi, cut, _, vel, _ = make_fields(24, 9)
+    ok, p, v, vf, log = dbg.node_solve(phi, vel, nonfractional(cut), tolerance=TOL, max_iterations=MAX_IT)
+    assert ok and (p == fixture()["mg24__pressure"]).all()  # -O1 with asserts, -O3 without: the same pressure, bit for bit
