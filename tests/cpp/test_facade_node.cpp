@@ -7,10 +7,13 @@
 //   GPU box, where tests/test_zz_facade_node.py runs it.   usage: test_facade_node [gridSize = 24]
 //
 // Gates: material labels, valid faces, domain labels, old pressure, pressure and velocity (integer / fpreal32) bit for bit; boundary weights
-// and right-hand sides (fp64, the kernels may contract a multiply-add) <= 1e-14 relative L-inf.
+// and right-hand sides (fp64, the kernels may contract a multiply-add) <= 1e-14 relative L-inf; one whole projection against the node's own
+// solveGasSubclass: valid faces bit for bit, iteration count +-1, pressure <= 1e-5, velocity <= 2e-5 (the north_star's bars).
 #include <cstdio>
 #include <iostream>
 #include <random>
+#include <sstream>
+#include <string>
 
 #include "HDK_GeometricCGPoissonSolver.h"
 #include "HDK_GeometricMultigridOperators.h"
@@ -126,6 +129,163 @@ static void makeFields(Fields &f, int n, unsigned seed)
 	    for (int y = 0; y < r[1]; ++y)
 		for (int x = 0; x < r[0]; ++x) g->fieldNC()->setValue(x, y, z, 0.5f * u(rng));
     }
+}
+
+template <typename T>
+static void copyGrid(UT_VoxelArray<T> &dst, const UT_VoxelArray<T> &src)
+{
+    const UT_Vector3I r = src.getVoxelRes();
+    for (int z = 0; z < r[2]; ++z)
+	for (int y = 0; y < r[1]; ++y)
+	    for (int x = 0; x < r[0]; ++x) dst.setValue(x, y, z, src(x, y, z));
+}
+static void copyVector(SIM_VectorField &dst, const SIM_VectorField &src, int n)
+{
+    dst.initFaces(n, n, n);
+    for (int a = 0; a < 3; ++a) copyGrid(*dst.getField(a)->fieldNC(), *src.getField(a)->field());
+}
+static double maxAbs(const UT_VoxelArray<fpreal32> &a)
+{
+    const UT_Vector3I r = a.getVoxelRes();
+    double m = 0;
+    for (int z = 0; z < r[2]; ++z)
+	for (int y = 0; y < r[1]; ++y)
+	    for (int x = 0; x < r[0]; ++x) m = std::max(m, double(std::fabs(a(x, y, z))));
+    return m;
+}
+static double maxDiff(const UT_VoxelArray<fpreal32> &a, const UT_VoxelArray<fpreal32> &b)
+{
+    const UT_Vector3I r = a.getVoxelRes();
+    double m = 0;
+    for (int z = 0; z < r[2]; ++z)
+	for (int y = 0; y < r[1]; ++y)
+	    for (int x = 0; x < r[0]; ++x) m = std::max(m, double(std::fabs(a(x, y, z) - b(x, y, z))));
+    return m;
+}
+
+// One whole pressure projection: the reference node's own solveGasSubclass (HDK_GeometricFreeSurfacePressureSolver.cpp:113-714, unmodified,
+// production wiring: tiled Gauss-Seidel V-cycle inside the PCG) against the same body written with the facade -- what the patched node runs.
+static void wholeProjection(const Fields &f, bool withSolid)
+{
+    const int n = f.n;
+    const double tolerance = 1e-7;
+    const int maxIterations = 400;
+    // ---- the reference node on its own SIM_Object
+    SIM_ScalarField surface, collision, density, pressureR;
+    SIM_VectorField velocityR, cutR, validR, collisionVel;
+    surface.getField()->init(n, n, n);
+    copyGrid(*surface.getField()->fieldNC(), *f.liquid.field());
+    density.getField()->init(n, n, n);
+    density.getField()->makeConstant(1000.f);
+    pressureR.getField()->init(n, n, n);
+    copyVector(velocityR, f.velocity, n);
+    copyVector(cutR, f.cut, n);
+    validR.initFaces(n, n, n);
+    SIM_Object obj;
+    obj.scalarFields[GAS_NAME_SURFACE] = &surface;
+    obj.scalarFields[GAS_NAME_DENSITY] = &density;
+    obj.scalarFields[GAS_NAME_PRESSURE] = &pressureR;
+    obj.vectorFields[GAS_NAME_VELOCITY] = &velocityR;
+    obj.vectorFields["cutCellWeights"] = &cutR;
+    obj.vectorFields["validFaces"] = &validR;
+    if (withSolid)
+    {
+	collision.getField()->init(n, n, n);
+	copyGrid(*collision.getField()->fieldNC(), *f.solid.field());
+	copyVector(collisionVel, f.solidVelocityAligned, n);
+	obj.scalarFields[GAS_NAME_COLLISION] = &collision;
+	obj.vectorFields[GAS_NAME_COLLISIONVELOCITY] = &collisionVel;
+    }
+    Node node(nullptr);
+    node.options[SIM_NAME_TOLERANCE] = tolerance;
+    node.options["maxIterations"] = maxIterations;
+    node.options["useMGPreconditioner"] = 1;
+    node.options["useOldPressure"] = 0;
+    SIM_Engine engine;
+    std::ostringstream captured;
+    std::streambuf *old = std::cout.rdbuf(captured.rdbuf());
+    const bool ok = node.solveGasSubclass(engine, &obj, 0, 1. / 24.);
+    std::cout.rdbuf(old);
+    EXPECT(ok && obj.errors.empty(), "the reference node failed: %s", obj.errors.empty() ? "?" : obj.errors[0].c_str());
+    int iterationsR = -1;
+    {
+	const std::string text = captured.str();
+	const size_t at = text.rfind("Iterations: ");
+	if (at != std::string::npos) iterationsR = std::atoi(text.c_str() + at + 12);
+    }
+
+    // ---- the same body with the facade (the calls of solveGasSubclass, GFS.cpp:262-660, re-qualified)
+    namespace NewOps = HDKB200::GeometricMultigridOperators;
+    const std::array<const SIM_RawField *, 3> cut = {f.cut.getField(0), f.cut.getField(1), f.cut.getField(2)};
+    SIM_RawField noSolid;
+    noSolid.init(n, n, n);
+    noSolid.makeConstant(-10.f);  // GFS.cpp:207-219: no collision field = "all fluid", -10 dx
+    const SIM_RawField &solidSurface = withSolid ? f.solid : noSolid;
+    SIM_RawIndexField material;
+    HDKB200::Utilities::buildMaterialCellLabels(material, f.liquid, solidSurface, cut);
+    SIM_VectorField valid, velocity;
+    valid.initFaces(n, n, n);
+    copyVector(velocity, f.velocity, n);
+    New::buildValidFaces(valid, material, cut);
+    for (int a = 0; a < 3; ++a)
+	EXPECT(differing(*valid.getField(a)->field(), *validR.getField(a)->field()) == 0, "projection: valid faces differ on axis %d", a);
+    UT_VoxelArray<int> base;
+    base.size(n, n, n);
+    base.constant(NewOps::EXTERIOR_CELL);
+    New::buildMGDomainLabels(base, material);
+    std::array<UT_VoxelArray<double>, 3> baseW;
+    for (int a = 0; a < 3; ++a)
+    {
+	UT_Vector3I size(n, n, n);
+	++size[a];
+	baseW[a].size(int(size[0]), int(size[1]), int(size[2]));
+	baseW[a].constant(0);
+	New::buildMGBoundaryWeights(baseW[a], *cut[a], f.liquid, *valid.getField(a), material, base, a);
+    }
+    UT_VoxelArray<int> labels;
+    auto isExt = [](const int v) { return v == NewOps::EXTERIOR_CELL; };
+    auto isInt = [](const int v) { return v == NewOps::INTERIOR_CELL; };
+    auto isDir = [](const int v) { return v == NewOps::DIRICHLET_CELL; };
+    const std::pair<UT_Vector3I, int> settings = NewOps::buildExpandedCellLabels(labels, base, isExt, isInt, isDir);
+    const UT_Vector3I offset = settings.first;
+    const int mgLevels = settings.second;
+    std::array<UT_VoxelArray<double>, 3> weights;
+    for (int a = 0; a < 3; ++a)
+    {
+	UT_Vector3I size = labels.getVoxelRes();
+	++size[a];
+	weights[a].size(int(size[0]), int(size[1]), int(size[2]));
+	weights[a].constant(0);
+	NewOps::buildExpandedBoundaryWeights(weights[a], baseW[a], labels, offset, a);
+    }
+    NewOps::setBoundaryCellLabels(labels, weights);
+    const UT_Vector3I er = labels.getVoxelRes();
+    UT_VoxelArray<double> rhs, solution;
+    rhs.size(int(er[0]), int(er[1]), int(er[2]));
+    rhs.constant(0);
+    solution.size(int(er[0]), int(er[1]), int(er[2]));
+    solution.constant(0);
+    New::buildRHS(rhs, material, velocity, withSolid ? &f.solidVelocityAligned : nullptr, cut, labels, offset);
+    HDKB200::GeometricMultigridPoissonSolver mg(labels, weights, mgLevels, true /* useGaussSeidel, GFS.cpp:463-466 */);
+    std::vector<double> history;
+    const int iterations = HDKB200::solveGeometricConjugateGradient(mg, solution, rhs, tolerance, maxIterations, true, &history);
+    SIM_RawField pressure;
+    pressure.init(n, n, n);
+    pressure.makeConstant(0);
+    New::applySolutionToPressure(pressure, material, labels, solution, offset);
+    for (int a = 0; a < 3; ++a) New::applyPressureGradient(*velocity.getField(a), *cut[a], f.liquid, pressure, *valid.getField(a), material, a);
+
+    EXPECT(iterationsR >= 0 && std::abs(iterations - iterationsR) <= 1, "projection: iterations %d vs the node's %d", iterations, iterationsR);
+    const double pScale = maxAbs(*pressureR.getField()->field());
+    const double pDiff = maxDiff(*pressure.field(), *pressureR.getField()->field());
+    EXPECT(pScale > 0 && pDiff <= 1e-5 * pScale, "projection: pressure deviates by %.3e of %.3e", pDiff, pScale);
+    for (int a = 0; a < 3; ++a)
+    {
+	const double vDiff = maxDiff(*velocity.getField(a)->field(), *velocityR.getField(a)->field());
+	EXPECT(vDiff <= 2e-5 * std::max(pScale, maxAbs(*velocityR.getField(a)->field())), "projection: velocity axis %d deviates by %.3e", a, vDiff);
+    }
+    std::printf("projection (%s): %d iterations (node: %d), pressure deviation %.2e of %.2e\n", withSolid ? "solid field, moving solid" : "no solid", iterations,
+		iterationsR, pDiff, pScale);
 }
 
 int main(int argc, char **argv)
@@ -265,6 +425,10 @@ int main(int argc, char **argv)
 	New::applyPressureGradient(vN, *cut[a], f.liquid, f.pressure, *validR.getField(a), matR, a);
 	EXPECT(differing(*vR.field(), *vN.field()) == 0, "applyPressureGradient differs on axis %d", a);
     }
+
+    // ---- one whole projection, the node against the facade
+    wholeProjection(f, false);
+    wholeProjection(f, true);
 
     if (g_fail) { std::printf("FACADE_NODE_FAILED %d\n", g_fail); return 1; }
     std::printf("FACADE_NODE_OK gridSize %d, %ld liquid cells\n", n, liquidCells);
