@@ -119,7 +119,7 @@ def build_inputs(n):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_run(n, steps, warmup, budget_s=240.0, keep_solution=False):
+def cpu_reference_run(n, steps, warmup, budget_s=240.0, keep_solution=False, use_gs=False):
     """Times the reference's CPU implementation (constructor + PCG) on this box's host cores -- ALL of them: torchrun exports
     OMP_NUM_THREADS=1 to its workers, which round 1's N>1 reference arm silently obeyed."""
     from oracle import bindings
@@ -142,7 +142,7 @@ def cpu_reference_run(n, steps, warmup, budget_s=240.0, keep_solution=False):
     clamp = None
     for step in range(warmup + steps):
         t0 = time.perf_counter()
-        s = lib.solver(labels, w, levels, False)
+        s = lib.solver(labels, w, levels, bool(use_gs))
         t1 = time.perf_counter()
         x, iters, hist = s.pcg(np.zeros_like(b), b, TOL, MAX_IT)
         t2 = time.perf_counter()
@@ -749,6 +749,16 @@ def run_gpu_arm(args, rank, world, local_rank):
         gs = {"solve_ms": float(np.mean(gms)), "iterations": int(itg), "final_rel_residual": float(histg[-1]),
               "what": "same solve with useGaussSeidel = true (tiled Gauss-Seidel wavefront kernel), mean of 3 after 2 warm-ups"}
         sg.close()
+        if rank == 0 and not args.no_cpu_baseline:
+            # the reference's own sources in the same mode on this box's host cores, once: for context beside the Jacobi-mode cpu_baseline
+            try:
+                rg = cpu_reference_run(n, 1, 0, use_gs=True)
+                gs["cpu_reference"] = {"ms": rg["ms"], "setup_ms": rg["setup_ms"], "solve_ms": rg["solve_ms"], "iterations": rg["iterations"], "cores": rg["cores"],
+                                       "kind": rg["kind"], "final_rel_residual": rg["final_rel_residual"],
+                                       "iterations_equal": bool(int(rg["iterations"]) == int(itg)),
+                                       "max_rel_history_dev": rel_history_dev(histg, rg["history"])}
+            except Exception as e:  # context only: never fails the line
+                gs["cpu_reference"] = {"error": repr(e)[:200]}
 
     # ---- mixed precision, reported beside the fp64 headline, never as it: fp32 V-cycle inside the fp64 CG -----------
     mixed = None
